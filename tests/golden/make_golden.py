@@ -1,0 +1,290 @@
+"""Generate the golden fixtures under tests/golden/ by RUNNING THE REFERENCE in this container.
+
+Run (only where /root/reference exists; the GPU box never runs this):
+
+    python tests/golden/make_golden.py
+
+It imports the unmodified reference from /root/reference/src with the three absent
+third-party packages (matplotlib, seaborn, vanilla_option_pricers) replaced by
+``MagicMock`` modules (they are only touched by plotting / implied-vol code that is
+outside the hot path) and stores inputs + outputs of every hot-path function of
+SURVEY.md §8(a) as ``.npz`` files.  The fixtures pin ``oracle/`` (CPU restatement) and,
+through it and directly, the CUDA path.
+
+Nothing here is imported by the product or by the tests; the tests read only the
+``.npz`` files this script wrote.
+"""
+from __future__ import annotations
+
+import os
+import sys
+from unittest.mock import MagicMock
+
+import numpy as np
+
+REF_SRC = "/root/reference/src"
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def _import_reference():
+    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.backends",
+                 "matplotlib.backends.backend_pdf", "matplotlib.lines", "matplotlib.ticker",
+                 "matplotlib.figure", "matplotlib.axes", "matplotlib.dates", "matplotlib.colors",
+                 "seaborn", "vanilla_option_pricers", "vanilla_option_pricers.bsm",
+                 "vanilla_option_pricers.bachelier"):
+        sys.modules.setdefault(name, MagicMock())
+    sys.path.insert(0, REF_SRC)
+
+
+def main() -> None:
+    _import_reference()
+    import scipy
+    import numba
+    from stochvolmodels.pricers import logsv_pricer as lp
+    from stochvolmodels.pricers import heston_pricer as hp
+    from stochvolmodels.pricers.logsv import affine_expansion as afe
+    from stochvolmodels.pricers.logsv.logsv_params import LogSvParams
+    from stochvolmodels.utils import mgf_pricer as mgfp
+    from stochvolmodels.utils import mc_payoffs as mcp
+    from stochvolmodels.utils.funcs import set_time_grid
+    from stochvolmodels.utils.config import VariableType
+    from stochvolmodels.data.sample_option_chains import get_btc_test_chain_data
+
+    versions = np.array([f"numpy={np.__version__}", f"scipy={scipy.__version__}", f"numba={numba.__version__}"])
+    Q = LogSvParams(sigma0=1.0, theta=1.0, kappa1=5.0, kappa2=5.0, beta=0.2, volvol=2.0)
+    K5 = np.array([0.8, 0.9, 1.0, 1.1, 1.2])
+    T5 = np.array(['P', 'P', 'C', 'C', 'C'])
+
+    # ------------------------------------------------------------------ a7 set_time_grid
+    cases = [(0.25, 252), (0.25, 360), (1.0, 1023), (0.7, 360), (1.0, 252), (0.04289242541152263, 252),
+             (0.05833333333333334, 252), (0.0972222222222222, 582), (1.0 / 12.0, 360), (0.02, 360), (1e-3, 360)]
+    tg = np.array([[ttm, n, *set_time_grid(ttm, n)[:2]] for ttm, n in cases])
+    np.savez(os.path.join(OUT, "time_grid.npz"), cases=tg, versions=versions)
+
+    # ------------------------------------------------------------------ a12 grids and weights
+    grids = {}
+    for name, vs, spot in (("mma", 0.2041241452319315, True), ("inv", 0.2041241452319315, False), ("dflt", 0.28, True)):
+        phi, psi, theta = mgfp.get_transform_var_grid(variable_type=VariableType.LOG_RETURN, is_spot_measure=spot, vol_scaler=vs)
+        grids[f"phi_{name}"] = phi
+        grids[f"w_{name}"] = mgfp._compute_legacy_pricer_weights(phi, True)
+    grids["vol_scaler_q_025"] = np.array(lp.set_vol_scaler(sigma0=1.0, ttm=0.25))
+    grids["vol_scaler_btc"] = np.array(lp.set_vol_scaler(sigma0=0.8376, ttm=0.04289242541152263))
+    np.savez(os.path.join(OUT, "grids.npz"), versions=versions, **grids)
+
+    # ------------------------------------------------------------------ a8 M, L, H
+    mlh = {}
+    phis = np.array([-0.5 + 0.0j, -0.5 + 3.7j, 0.5 + 11.25j, -0.3 + 0.4j])
+    psis = np.array([0.0j, 0.0j, 0.0j, -0.5 + 2.0j])
+    k = 0
+    for order in (afe.ExpansionOrder.FIRST, afe.ExpansionOrder.SECOND):
+        for spot in (True, False):
+            for eta in (1.0, 0.85):
+                for phi, psi in zip(phis, psis):
+                    M, L, H = afe.func_a_ode_quadratic_terms(theta=1.0413, kappa1=3.1844, kappa2=3.058, beta=0.1514,
+                                                             volvol=1.8458, phi=phi, psi=psi, is_spot_measure=spot,
+                                                             expansion_order=order, vol_backbone_eta=eta)
+                    mlh[f"case{k}_in"] = np.array([order.value, float(spot), eta, phi.real, phi.imag, psi.real, psi.imag])
+                    mlh[f"case{k}_M"], mlh[f"case{k}_L"], mlh[f"case{k}_H"] = M, L, H
+                    # one RHS evaluation at a fixed complex state
+                    A = (np.arange(1, M.shape[0] + 1) * (0.1 - 0.05j)).astype(np.complex128)
+                    mlh[f"case{k}_rhs"] = afe.func_rhs(0.0, A, M, L, H)
+                    k += 1
+    mlh["ncases"] = np.array(k)
+    mlh["params"] = np.array([1.0413, 3.1844, 3.058, 0.1514, 1.8458])
+    np.savez(os.path.join(OUT, "mlh.npz"), versions=versions, **mlh)
+
+    # ------------------------------------------------------------------ a9-a11, a13 LogSV Fourier chain
+    def fourier_case(tag, params, ttms, forwards, discfactors, strikes_ttms, types_ttms, spot, order=afe.ExpansionOrder.SECOND,
+                     backbone=None):
+        """run logsv_chain_pricer and ALSO replay its loop to capture a_t1 / log_mgf per maturity."""
+        if backbone is not None:
+            params.set_vol_backbone(backbone)
+        prices = lp.logsv_chain_pricer(params=params, ttms=ttms, forwards=forwards, discfactors=discfactors,
+                                       strikes_ttms=strikes_ttms, optiontypes_ttms=types_ttms,
+                                       is_spot_measure=spot, expansion_order=order)
+        vol_scaler = lp.set_vol_scaler(sigma0=params.sigma0, ttm=np.min(ttms))
+        phi, psi, theta = mgfp.get_transform_var_grid(variable_type=VariableType.LOG_RETURN, is_spot_measure=spot,
+                                                      vol_scaler=vol_scaler)
+        a_t0 = np.zeros((phi.shape[0], afe.get_expansion_n(order)), dtype=np.complex128)
+        ttm0 = 0.0
+        out = dict(params=np.array([params.sigma0, params.theta, params.kappa1, params.kappa2, params.beta, params.volvol]),
+                   ttms=ttms, forwards=forwards, discfactors=discfactors, is_spot=np.array(spot), order=np.array(order.value),
+                   vol_scaler=np.array(vol_scaler), phi=phi, nslices=np.array(len(ttms)))
+        etas = []
+        for m, ttm in enumerate(ttms):
+            eta = params.get_vol_backbone_eta(tau=ttm)
+            etas.append(eta)
+            a_t0, log_mgf = afe.compute_logsv_a_mgf_grid(ttm=ttm - ttm0, phi_grid=phi, psi_grid=psi, theta_grid=theta,
+                                                          a_t0=a_t0, expansion_order=order, is_spot_measure=spot,
+                                                          **{kk: vv for kk, vv in params.to_dict().items()},
+                                                          vol_backbone_eta=eta)
+            out[f"a_t1_{m}"] = a_t0
+            out[f"log_mgf_{m}"] = log_mgf
+            out[f"strikes_{m}"] = np.asarray(strikes_ttms[m], dtype=float)
+            out[f"types_{m}"] = np.asarray(types_ttms[m])
+            out[f"prices_{m}"] = np.asarray(prices[m])
+            ttm0 = ttm
+        out["etas"] = np.array(etas, dtype=float)
+        np.savez(os.path.join(OUT, f"logsv_fourier_{tag}.npz"), versions=versions, **out)
+        print(tag, [np.asarray(p)[:3] for p in prices])
+
+    # G1: quickstart 3m + 6m
+    fourier_case("g1_quickstart", LogSvParams(1.0, 1.0, 5.0, 5.0, 0.2, 2.0), np.array([0.25, 0.5]), np.ones(2), np.ones(2),
+                 (K5, K5), (T5, T5), True)
+    # G2: inverse measure
+    fourier_case("g2_inverse", LogSvParams(1.0, 1.0, 5.0, 5.0, 0.2, 2.0), np.array([0.25]), np.ones(1), np.ones(1),
+                 (K5,), (np.array(['IP', 'IP', 'IC', 'IC', 'IC']),), False)
+    # C3: 5 maturities x 21 strikes
+    K21 = np.linspace(0.5, 1.5, 21)
+    T21 = np.where(K21 >= 1.0, 'C', 'P')
+    ttms5 = np.array([1.0 / 12.0, 0.25, 0.5, 0.75, 1.0])
+    fourier_case("c3_5x21", LogSvParams(1.0, 1.0, 5.0, 5.0, 0.2, 2.0), ttms5, np.ones(5), np.ones(5),
+                 tuple(K21 for _ in ttms5), tuple(T21 for _ in ttms5), True)
+    # BTC chain with the reference's BTC parameters
+    btc = get_btc_test_chain_data()
+    fourier_case("btc", LogSvParams(sigma0=0.8376, theta=1.0413, kappa1=3.1844, kappa2=3.058, beta=0.1514, volvol=1.8458),
+                 btc.ttms, btc.forwards, btc.discfactors, tuple(btc.strikes_ttms), tuple(btc.optiontypes_ttms), True)
+    # FIRST order, discounting, forward != 1, negative beta
+    fourier_case("first_order", LogSvParams(sigma0=0.35, theta=0.3, kappa1=2.0, kappa2=1.5, beta=-0.6, volvol=0.9),
+                 np.array([0.1, 0.6]), np.array([100.0, 101.5]), np.array([0.995, 0.97]),
+                 (np.array([80.0, 100.0, 125.0]), np.array([70.0, 95.0, 101.5, 140.0])),
+                 (np.array(['P', 'C', 'C']), np.array(['P', 'P', 'C', 'C'])), True, order=afe.ExpansionOrder.FIRST)
+    # vol backbone (eta != 1) under the inverse measure, SECOND order
+    import pandas as pd
+    fourier_case("backbone_inverse", LogSvParams(sigma0=0.8, theta=1.0, kappa1=3.0, kappa2=3.0, beta=0.15, volvol=1.5),
+                 np.array([0.1, 0.3]), np.array([1.0, 1.0]), np.array([1.0, 1.0]),
+                 (K5, K5), (np.array(['IP', 'IP', 'IC', 'C', 'P']), np.array(['IP', 'IP', 'IC', 'IC', 'IC'])), False,
+                 backbone=pd.Series([0.9, 1.1], index=[0.1, 0.3]))
+
+    # ------------------------------------------------------------------ a14 Heston Fourier
+    def heston_case(tag, v0, theta, kappa, volvol, rho, ttms, forwards, discfactors, strikes_ttms, types_ttms):
+        prices = hp.heston_chain_pricer(v0=v0, theta=theta, kappa=kappa, volvol=volvol, rho=rho, ttms=ttms, forwards=forwards,
+                                        strikes_ttms=strikes_ttms, optiontypes_ttms=types_ttms, discfactors=discfactors)
+        vol_scaler = np.minimum(0.3, np.sqrt(v0 * ttms[0]))
+        phi, psi, _ = mgfp.get_transform_var_grid(variable_type=VariableType.LOG_RETURN, vol_scaler=vol_scaler)
+        out = dict(params=np.array([v0, theta, kappa, rho, volvol]), ttms=ttms, forwards=forwards, discfactors=discfactors,
+                   vol_scaler=np.array(vol_scaler), phi=phi, nslices=np.array(len(ttms)))
+        a_t0 = np.zeros(phi.shape[0], dtype=np.complex128)
+        b_t0 = np.zeros(phi.shape[0], dtype=np.complex128)
+        ttm0 = 0.0
+        for m, ttm in enumerate(ttms):
+            log_mgf, a_t0, b_t0 = hp.compute_heston_mgf_grid(ttm=ttm - ttm0, v0=v0, theta=theta, kappa=kappa, volvol=volvol, rho=rho,
+                                                             phi_grid=phi, psi_grid=psi, a_t0=a_t0, b_t0=b_t0)
+            out[f"log_mgf_{m}"], out[f"a_t1_{m}"], out[f"b_t1_{m}"] = log_mgf, a_t0, b_t0
+            out[f"strikes_{m}"] = np.asarray(strikes_ttms[m], dtype=float)
+            out[f"types_{m}"] = np.asarray(types_ttms[m])
+            out[f"prices_{m}"] = np.asarray(prices[m])
+            ttm0 = ttm
+        np.savez(os.path.join(OUT, f"heston_fourier_{tag}.npz"), versions=versions, **out)
+        print("heston", tag, [np.asarray(p)[:3] for p in prices])
+
+    heston_case("g4", 0.04, 0.04, 4.0, 0.4, -0.5, np.array([0.25, 1.0]), np.ones(2), np.ones(2), (K5, K5), (T5, T5))
+    heston_case("c3_5x21", 0.04, 0.04, 4.0, 0.4, -0.5, ttms5, np.ones(5), np.ones(5),
+                tuple(K21 for _ in ttms5), tuple(T21 for _ in ttms5))
+    heston_case("btc", 0.8, 1.0, 2.0, 2.0, 0.0, btc.ttms, btc.forwards, np.array([0.999, 0.998, 0.996, 0.99]),
+                tuple(btc.strikes_ttms), tuple(btc.optiontypes_ttms))
+
+    # ------------------------------------------------------------------ a1-a3 LogSV MC with fixed randoms
+    def mc_fixed_case(tag, params, ttms, forwards, discfactors, strikes_ttms, types_ttms, etas, spot, nb_path, n_per_year, seed,
+                      variable_type=VariableType.LOG_RETURN):
+        W0s, W1s, dts = lp.get_randoms_for_chain_valuation(ttms=ttms, nb_path=nb_path, nb_steps_per_year=n_per_year, seed=seed)
+        prices, stds = lp.logsv_mc_chain_pricer_fixed_randoms(ttms=ttms, forwards=forwards, discfactors=discfactors,
+                                                              strikes_ttms=strikes_ttms, optiontypes_ttms=types_ttms,
+                                                              W0s=W0s, W1s=W1s, dts=dts, v0=params.sigma0, theta=params.theta,
+                                                              kappa1=params.kappa1, kappa2=params.kappa2, beta=params.beta,
+                                                              volvol=params.volvol, vol_backbone_etas=etas, is_spot_measure=spot,
+                                                              variable_type=variable_type)
+        out = dict(params=np.array([params.sigma0, params.theta, params.kappa1, params.kappa2, params.beta, params.volvol]),
+                   ttms=ttms, forwards=forwards, discfactors=discfactors, etas=etas, is_spot=np.array(spot),
+                   nb_path=np.array(nb_path), n_per_year=np.array(n_per_year), seed=np.array(seed),
+                   variable_type=np.array(variable_type.value), nslices=np.array(len(ttms)),
+                   dts=np.array(list(dts)), nsteps=np.array([w.shape[0] for w in W0s]), W0_head=np.asarray(W0s[0])[0, :3])
+        # replay slice by slice for terminal states
+        x0 = np.zeros(nb_path); q0 = np.zeros(nb_path); s0 = params.sigma0 * np.ones(nb_path); ttm0 = 0.0
+        for m, ttm in enumerate(ttms):
+            x0, s0, q0 = lp.simulate_logsv_x_vol_terminal(ttm=ttm - ttm0, x0=x0, sigma0=s0, qvar0=q0, theta=params.theta,
+                                                           kappa1=params.kappa1, kappa2=params.kappa2, beta=params.beta,
+                                                           volvol=params.volvol, vol_backbone_eta=etas[m], nb_path=nb_path,
+                                                           dt=dts[m], is_spot_measure=spot, W0=W0s[m], W1=W1s[m])
+            ttm0 = ttm
+            out[f"x_{m}"], out[f"sigma_{m}"], out[f"qvar_{m}"] = x0.copy(), s0.copy(), q0.copy()
+            out[f"strikes_{m}"] = np.asarray(strikes_ttms[m], dtype=float)
+            out[f"types_{m}"] = np.asarray(types_ttms[m])
+            out[f"prices_{m}"], out[f"stderr_{m}"] = np.asarray(prices[m]), np.asarray(stds[m])
+        np.savez(os.path.join(OUT, f"logsv_mc_fixed_{tag}.npz"), versions=versions, **out)
+        print("mc", tag, np.asarray(prices[0])[:3], np.asarray(stds[0])[:3])
+
+    mc_fixed_case("g5_c1", Q, np.array([0.25]), np.ones(1), np.ones(1), (K5,), (T5,), np.ones(1), True, 10000, 252, 10)
+    mc_fixed_case("inverse_eta", LogSvParams(0.8376, 1.0413, 3.1844, 3.058, 0.1514, 1.8458), np.array([0.1, 0.3]),
+                  np.array([1.0, 1.02]), np.array([0.999, 0.99]), (K5, K5),
+                  (np.array(['IP', 'IP', 'IC', 'IC', 'IC']), np.array(['IP', 'P', 'C', 'IC', 'IC'])),
+                  np.array([0.9, 1.1]), False, 4000, 360, 3)
+    mc_fixed_case("btc_small", LogSvParams(0.8376, 1.0413, 3.1844, 3.058, 0.1514, 1.8458), btc.ttms, btc.forwards, btc.discfactors,
+                  tuple(btc.strikes_ttms), tuple(btc.optiontypes_ttms), np.ones(4), True, 5000, 252, 11)
+    mc_fixed_case("qvar", Q, np.array([0.25, 0.5]), np.ones(2), np.ones(2),
+                  (np.array([0.5, 1.0, 1.5]), np.array([0.5, 1.0, 1.5])), (np.array(['P', 'C', 'C']), np.array(['P', 'C', 'C'])),
+                  np.ones(2), True, 3000, 252, 5, variable_type=VariableType.Q_VAR)
+
+    # ------------------------------------------------------------------ a6 Heston MC stepper (py_func + numpy global seed)
+    def heston_mc_case(tag, v0, theta, kappa, rho, volvol, ttm, nb_path, seed):
+        np.random.seed(seed)
+        x, v, q = hp.simulate_heston_x_vol_terminal.py_func(ttm=ttm, x0=np.zeros(nb_path), var0=v0 * np.ones(nb_path),
+                                                            qvar0=np.zeros(nb_path), theta=theta, kappa=kappa, rho=rho,
+                                                            volvol=volvol, nb_path=nb_path)
+        S, dt, _ = set_time_grid(ttm, 360)
+        prices, stds = mcp.compute_mc_vars_payoff(x0=x, sigma0=np.sqrt(v), qvar0=q, ttm=ttm, forward=1.0, strikes_ttm=K5,
+                                                  optiontypes_ttm=T5, discfactor=0.98)
+        np.savez(os.path.join(OUT, f"heston_mc_fixed_{tag}.npz"), versions=versions,
+                 params=np.array([v0, theta, kappa, rho, volvol]), ttm=np.array(ttm), nb_path=np.array(nb_path),
+                 seed=np.array(seed), nsteps=np.array(S), dt=np.array(dt), x=x, var=v, qvar=q, strikes=K5, types=T5,
+                 forward=np.array(1.0), discfactor=np.array(0.98), prices=prices, stderr=stds)
+        print("heston mc", tag, prices[:3], "min v", v.min())
+
+    heston_mc_case("dflt", 0.04, 0.04, 4.0, -0.5, 0.4, 0.7, 5000, 7)
+    heston_mc_case("floor", 0.01, 0.02, 1.0, -0.7, 1.0, 0.5, 4000, 8)   # Feller violated: the 1e-4 floor binds
+
+    # ------------------------------------------------------------------ a5 payoffs: all four codes, Q_VAR, NaN paths
+    # NaN-free inputs go through the COMPILED reference.  Inputs with NaN paths go through ``.py_func`` (the Python
+    # source semantics: np.nanmean / np.nanstd skip NaN paths): the compiled function is ``fastmath=True`` (LLVM
+    # assumes no NaNs) and returns NaN / garbage for such inputs, so only the source-level behaviour can be pinned.
+    rng = np.random.RandomState(42)
+    x = 0.3 * rng.normal(size=2000) - 0.05
+    qv = 0.1 * np.abs(rng.normal(size=2000)) + 0.01
+    strikes = np.array([0.7, 0.9, 1.0, 1.1, 1.3, 1.0, 0.95, 1.05])
+    types = np.array(['P', 'P', 'C', 'C', 'C', 'IC', 'IP', 'IC'])
+    qstrikes = np.array([0.1, 0.2, 0.3, 0.2])
+    qtypes = np.array(['P', 'C', 'C', 'IC'])
+    kw = dict(sigma0=np.ones_like(x), ttm=0.5, forward=1.03, discfactor=0.97)
+    p1, s1 = mcp.compute_mc_vars_payoff(x0=x, qvar0=qv, strikes_ttm=strikes, optiontypes_ttm=types,
+                                        variable_type=VariableType.LOG_RETURN, **kw)
+    p2, s2 = mcp.compute_mc_vars_payoff(x0=x, qvar0=qv, strikes_ttm=qstrikes, optiontypes_ttm=qtypes,
+                                        variable_type=VariableType.Q_VAR, **kw)
+    xn = x.copy()
+    xn[[3, 77, 500]] = np.nan
+    p3, s3 = mcp.compute_mc_vars_payoff.py_func(x0=xn, qvar0=qv, strikes_ttm=strikes, optiontypes_ttm=types,
+                                                variable_type=VariableType.LOG_RETURN, **kw)
+    p4, s4 = mcp.compute_mc_vars_payoff.py_func(x0=xn, qvar0=qv, strikes_ttm=qstrikes, optiontypes_ttm=qtypes,
+                                                variable_type=VariableType.Q_VAR, **kw)
+    np.savez(os.path.join(OUT, "payoffs.npz"), versions=versions, x=x, x_nan=xn, qvar=qv, ttm=np.array(0.5), forward=np.array(1.03),
+             discfactor=np.array(0.97), strikes=strikes, types=types, prices=p1, stderr=s1,
+             qstrikes=qstrikes, qtypes=qtypes, qprices=p2, qstderr=s2,
+             prices_nan=p3, stderr_nan=s3, qprices_nan=p4, qstderr_nan=s4)
+
+    # ------------------------------------------------------------------ a13 Fourier sum on a closed-form (lognormal) MGF
+    vol, ttm = 0.3, 0.4
+    for spot, tag in ((True, "mma"), (False, "inv")):
+        phi, _, _ = mgfp.get_transform_var_grid(variable_type=VariableType.LOG_RETURN, is_spot_measure=spot,
+                                                vol_scaler=vol * np.sqrt(ttm))
+        sgn = 1.0 if spot else -1.0
+        log_mgf = 0.5 * vol * vol * ttm * (phi * phi + sgn * phi)
+        types = np.array(['P', 'P', 'C', 'C', 'C']) if spot else np.array(['IP', 'P', 'C', 'IC', 'IC'])
+        prices = mgfp.vanilla_slice_pricer_with_mgf_grid(log_mgf_grid=log_mgf, phi_grid=phi, forward=1.5, strikes=1.5 * K5,
+                                                         optiontypes=types, discfactor=0.9, is_spot_measure=spot)
+        np.savez(os.path.join(OUT, f"fourier_sum_{tag}.npz"), versions=versions, phi=phi, log_mgf=log_mgf, forward=np.array(1.5),
+                 strikes=1.5 * K5, types=types, discfactor=np.array(0.9), is_spot=np.array(spot), prices=prices)
+
+    print("golden fixtures written to", OUT)
+
+
+if __name__ == "__main__":
+    main()
