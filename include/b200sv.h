@@ -1,0 +1,193 @@
+/* b200sv.h -- C ABI of libb200sv.so: the B200 (sm_100a) replacement for the two numerical hot paths of
+ * ArturSepp/StochVolModels (stochvolmodels 2.2.0).  Plain pointers and sizes; no torch / C++ types.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to
+ * /root/reference/src/stochvolmodels).  The reference is pure Python + Numba, so "the FFI for this path" is a
+ * ctypes binding: INTEGRATION.md shows the stub a maintainer adds inside LogSVPricer / HestonPricer.
+ *
+ * Conventions
+ *   - return 0 on success, <0 on error; b200sv_last_error() returns a thread-local message.
+ *   - arrays are caller-owned; no pointer is retained after return.
+ *   - "host-level" calls (no _dev_ in the name) take HOST pointers, run on the current CUDA device, and are
+ *     synchronous: H2D copies of the inputs and D2H copies of the results happen inside the call.
+ *   - "device-level" calls (b200sv_dev_*) take DEVICE pointers and a cudaStream_t (as void*; NULL = the legacy
+ *     default stream), enqueue work and return without synchronising.  They are what a multi-GPU host composes with
+ *     its own collectives (two tiny all-reduces per maturity, see DESIGN.md "multi-GPU").
+ *   - option chain layout ("CSR"): strikes[offsets[m] .. offsets[m+1]) belong to maturity m;
+ *     types[] uses B200SV_CALL.. codes in the same positions.
+ *   - all floating point crossing the ABI is IEEE float64, as in the reference.
+ */
+#ifndef B200SV_H
+#define B200SV_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200SV_VERSION 100 /* 0.1.0 */
+
+/* option payoff codes: utils/config.py:8-14 OptionType {'C','P','IC','IP'} */
+enum { B200SV_CALL = 0, B200SV_PUT = 1, B200SV_INV_CALL = 2, B200SV_INV_PUT = 3 };
+/* utils/config.py:17-24 VariableType */
+enum { B200SV_LOG_RETURN = 1, B200SV_Q_VAR = 2, B200SV_SIGMA = 3 };
+/* pricers/logsv/affine_expansion.py:43-54 ExpansionOrder */
+enum { B200SV_ORDER_FIRST = 1, B200SV_ORDER_SECOND = 2 };
+
+/* MC arithmetic flags (bit-or).  Default 0 = fp64 state arithmetic, Gaussians drawn by a float Box-Muller on the SFU
+ * and widened (the draws are random inputs, not reference arithmetic).  B200SV_GAUSS_F64 draws them in fp64 as well;
+ * B200SV_STATE_F32 keeps x / log-sigma / qvar in float registers (payoff moments stay fp64). */
+enum { B200SV_STATE_F64 = 0, B200SV_STATE_F32 = 1, B200SV_GAUSS_F32 = 0, B200SV_GAUSS_F64 = 2 };
+/* Heston variance scheme: reference floor-Euler (pricers/heston_pricer.py:369-379) */
+enum { B200SV_HESTON_EULER_FLOOR = 0 };
+
+/* pricers/logsv/logsv_params.py:35-83 LogSvParams (the six model floats; kappa2=None already mapped to kappa1/theta) */
+typedef struct {
+  double sigma0, theta, kappa1, kappa2, beta, volvol;
+} b200sv_logsv_params;
+
+/* pricers/heston_pricer.py:27-41 HestonParams */
+typedef struct {
+  double v0, theta, kappa, rho, volvol;
+} b200sv_heston_params;
+
+const char* b200sv_last_error(void);
+int b200sv_version(void);
+/* number of this library's kernels launched by the calling thread since the last reset (bench "gpu_launches") */
+long long b200sv_launch_count(void);
+void b200sv_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Monte Carlo, host-level
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* replaces logsv_mc_chain_pricer (pricers/logsv_pricer.py:806-867) = chain loop over
+ * simulate_logsv_x_vol_terminal (:950-1047) + compute_mc_vars_payoff (utils/mc_payoffs.py:10-88).
+ * nb_steps_per_year follows set_time_grid (utils/funcs.py:24-47): S_m = int((ttm_m - ttm_{m-1}) * n) + 1.
+ * Single-GPU, synchronous.  etas may be NULL (all 1).  prices_out, stderr_out: offsets[M]-offsets[0] doubles each. */
+int b200sv_logsv_mc_chain(const b200sv_logsv_params* params, int M, const double* ttms, const double* forwards,
+                          const double* discfactors, const double* etas, const int* offsets, const double* strikes,
+                          const int8_t* types, long long nb_path, int nb_steps_per_year, int is_spot_measure,
+                          int variable_type, uint64_t seed, int flags, double* prices_out, double* stderr_out);
+
+/* replaces heston_mc_chain_pricer (pricers/heston_pricer.py:285-331) + simulate_heston_x_vol_terminal (:334-381).
+ * nb_steps_per_year: the reference hard-wires 360 (:344). */
+int b200sv_heston_mc_chain(const b200sv_heston_params* params, int M, const double* ttms, const double* forwards,
+                           const double* discfactors, const int* offsets, const double* strikes, const int8_t* types,
+                           long long nb_path, int nb_steps_per_year, int variable_type, uint64_t seed, int flags,
+                           int scheme, double* prices_out, double* stderr_out);
+
+/* replaces LogSVPricer.simulate_terminal_values (pricers/logsv_pricer.py:590-611) -> simulate_logsv_x_vol_terminal.
+ * x, sigma, qvar: nb_path doubles each (host, out). */
+int b200sv_logsv_terminal(const b200sv_logsv_params* params, double ttm, long long nb_path, int nb_steps_per_year,
+                          int is_spot_measure, double eta, uint64_t seed, int flags, double* x, double* sigma,
+                          double* qvar);
+
+/* replaces HestonPricer.simulate_terminal_values (pricers/heston_pricer.py:90-108). */
+int b200sv_heston_terminal(const b200sv_heston_params* params, double ttm, long long nb_path, int nb_steps_per_year,
+                           uint64_t seed, int flags, int scheme, double* x, double* var, double* qvar);
+
+/* replaces simulate_logsv_x_vol_terminal called with W0, W1, dt (pricers/logsv_pricer.py:1027-1047), the stepping
+ * inside logsv_mc_chain_pricer_fixed_randoms (:1100-1162).  W0, W1: unit normals, row-major [S][N] (scaled by
+ * sqrt(dt) inside, :1028-1030).  x, sigma, qvar: N doubles, updated in place.  Strict fp64, no FMA contraction,
+ * reference evaluation order. */
+int b200sv_logsv_step_fixed(double* x, double* sigma, double* qvar, const double* W0, const double* W1, int S,
+                            long long N, double dt, const b200sv_logsv_params* params, double eta, int is_spot_measure);
+
+/* Heston twin of the above (loop body pricers/heston_pricer.py:372-379). */
+int b200sv_heston_step_fixed(double* x, double* var, double* qvar, const double* W0, const double* W1, int S,
+                             long long N, double dt, const b200sv_heston_params* params);
+
+/* replaces compute_mc_vars_payoff (utils/mc_payoffs.py:10-88): forward re-centring with the nan-mean over all paths,
+ * per-strike discounted nan-mean and nan-std/sqrt(N).  qvar may be NULL for B200SV_LOG_RETURN. */
+int b200sv_mc_payoffs(const double* x, const double* qvar, long long N, double ttm, double forward, const double* strikes,
+                      const int8_t* types, int J, double discfactor, int variable_type, double* prices_out,
+                      double* stderr_out);
+
+/* parity/debug export of the device RNG stream (csrc/philox.cuh): unit normals of paths [path0, path0+n) for chain
+ * slice `slice`, steps 0..nsteps-1; z0, z1 row-major [nsteps][n] host doubles. */
+int b200sv_device_normals(uint64_t seed, long long path0, long long n, int slice, int nsteps, int flags, double* z0,
+                          double* z1);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Monte Carlo, device-level building blocks (multi-GPU hosts put their all-reduces between them)
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* one maturity slice of the fused stepper for local paths [0, n_local) whose global ids start at path_offset.
+ * state arrays are float64 (B200SV_STATE_F64) or float32 (B200SV_STATE_F32) device arrays of n_local elements;
+ * init != 0: start from (0, v_init, 0) instead of loading.  moments_out[2] (device) receives
+ * (sum over non-NaN paths of forward*exp(x), count of non-NaN paths) for THIS rank. */
+int b200sv_dev_logsv_slice(void* x, void* sigma, void* qvar, long long n_local, long long path_offset, int init,
+                           const b200sv_logsv_params* params, double eta, int is_spot_measure, int nsteps, double dt,
+                           int slice_index, double forward, uint64_t seed, int flags, double* moments_out, void* stream);
+int b200sv_dev_heston_slice(void* x, void* var, void* qvar, long long n_local, long long path_offset, int init,
+                            const b200sv_heston_params* params, int nsteps, double dt, int slice_index, double forward,
+                            uint64_t seed, int flags, int scheme, double* moments_out, void* stream);
+
+/* per-strike payoff sums for local paths given the GLOBAL (all-reduced) re-centring moments[2]:
+ * sums_out[3*J] (device) = (sum pay, sum pay^2, count non-NaN) per strike for THIS rank.
+ * strikes / types are DEVICE arrays of J entries. */
+int b200sv_dev_payoff_sums(const void* x, const void* qvar, long long n_local, int flags, double ttm, double forward,
+                           const double* strikes, const int8_t* types, int J, int variable_type,
+                           const double* moments, double* sums_out, void* stream);
+
+/* turn GLOBAL sums[3*J] into prices / std errors (device arrays of J): price = df*s1/n, se = df*sqrt(s2/n-(s1/n)^2)/sqrt(N). */
+int b200sv_dev_payoff_finalize(const double* sums, int J, double discfactor, long long total_paths, double* prices_out,
+                               double* stderr_out, void* stream);
+
+/* device-level twins of b200sv_logsv_step_fixed / b200sv_heston_step_fixed (all arrays on the device; W row-major [S][N]):
+ * the calibration inner loop logsv_mc_chain_pricer_fixed_randoms (pricers/logsv_pricer.py:1100-1162) keeps W0s/W1s
+ * resident in HBM across optimizer iterations and calls these per maturity. */
+int b200sv_dev_logsv_step_fixed(double* x, double* sigma, double* qvar, const double* W0, const double* W1, int S,
+                                long long N, double dt, const b200sv_logsv_params* params, double eta,
+                                int is_spot_measure, void* stream);
+int b200sv_dev_heston_step_fixed(double* x, double* var, double* qvar, const double* W0, const double* W1, int S,
+                                 long long N, double dt, const b200sv_heston_params* params, void* stream);
+
+/* moments_out[2] (device) = (sum over non-NaN paths of forward*exp(x), count) for externally produced float64 states. */
+int b200sv_dev_spot_moments(const double* x, long long n, double forward, double* moments_out, void* stream);
+
+/* test hook: out[2i] = exp(L[i]), out[2i+1] = exp(-L[i]) through the stepper's shared-polynomial exp pair (host arrays). */
+int b200sv_debug_exp_pair(const double* L, long long n, double* out);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Fourier / MGF, host-level
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* replaces logsv_chain_pricer, LOG_RETURN branch (pricers/logsv_pricer.py:669-739): transform grid
+ * (utils/mgf_pricer.py:11-34), per maturity the affine-expansion ODEs integrated with SciPy's RK45 control law
+ * (pricers/logsv/affine_expansion.py:229-303, 492-529) carried across maturities, log-MGF contraction (:674-685)
+ * and the Simpson/Fourier sums (utils/mgf_pricer.py:174-221).  vol_scaler <= 0 selects set_vol_scaler (:664-666).
+ * P = grid size (reference: 1000).  Optional outputs (may be NULL): a_out [M][P][n] complex128 interleaved,
+ * log_mgf_out [M][P] complex128 interleaved. */
+int b200sv_logsv_price_chain(const b200sv_logsv_params* params, int M, const double* ttms, const double* forwards,
+                             const double* discfactors, const double* etas, const int* offsets, const double* strikes,
+                             const int8_t* types, int is_spot_measure, int expansion_order, double vol_scaler, int P,
+                             double* prices_out, double* a_out, double* log_mgf_out);
+
+/* replaces heston_chain_pricer, LOG_RETURN branch (pricers/heston_pricer.py:217-282) with compute_heston_mgf_grid
+ * (:183-214).  vol_scaler <= 0 selects min(0.3, sqrt(v0*ttms[0])) (:234-235). */
+int b200sv_heston_price_chain(const b200sv_heston_params* params, int M, const double* ttms, const double* forwards,
+                              const double* discfactors, const int* offsets, const double* strikes, const int8_t* types,
+                              double vol_scaler, int P, double* prices_out, double* log_mgf_out);
+
+/* replaces compute_logsv_a_mgf_grid, non-analytic branch (pricers/logsv/affine_expansion.py:570-685 -> solve_a_ode_grid
+ * :492-529): phi, psi, a (in: A(0), out: A(dtau)), log_mgf_out are complex128 interleaved host arrays of P, P, P*n, P. */
+int b200sv_logsv_mgf_grid(const double* phi, const double* psi, int P, double dtau, double* a_inout,
+                          const b200sv_logsv_params* params, double eta, int is_spot_measure, int expansion_order,
+                          double* log_mgf_out);
+
+/* replaces compute_heston_mgf_grid (pricers/heston_pricer.py:183-214); a, b in/out complex128[P]. */
+int b200sv_heston_mgf_grid(const double* phi, const double* psi, int P, double dtau, double* a_inout, double* b_inout,
+                           const b200sv_heston_params* params, double* log_mgf_out);
+
+/* replaces vanilla_slice_pricer_with_mgf_grid (utils/mgf_pricer.py:174-221). */
+int b200sv_fourier_vanilla(const double* log_mgf, const double* phi, int P, double forward, const double* strikes,
+                           const int8_t* types, int J, double discfactor, int is_spot_measure, double* prices_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SV_H */

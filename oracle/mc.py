@@ -191,8 +191,8 @@ def device_normals(seed: int, path_ids, slice_idx: int, nb_steps: int, gauss: st
     gauss="f64": one call per step s (call = s); u1 = 2 - d(r0,r1) in (0,1], u2 = d(r2,r3) - 1 in [0,1);
                  Z0 = R cos(2 pi u2), Z1 = R sin(2 pi u2), R = sqrt(-2 ln u1).
     gauss="f32": one call per TWO steps (call = s // 2); even step uses (r0, r1), odd step (r2, r3);
-                 u1 = fma(float(ra), 2^-32, 2^-33), u2 = float(rb) * 2^-32, float32 Box-Muller with
-                 the same formulas.  The device uses MUFU approximations (lg2/sin/cos), so this variant
+                 u1 = fma(float(ra), 2^-32, 2^-33), angle = float(int32(rb)) * pi * 2^-31, float32 Box-Muller:
+                 Z0 = R cos(angle), Z1 = R sin(angle).  The device uses MUFU approximations (lg2/sin/cos), so this variant
                  agrees with the device only to ~1e-6 absolute; bit-level checks of that mode use the normals
                  exported by ``b200sv_device_normals`` instead.
     """
@@ -220,9 +220,8 @@ def device_normals(seed: int, path_ids, slice_idx: int, nb_steps: int, gauss: st
                     break
                 ra, rb = r[2 * half], r[2 * half + 1]
                 u1 = ra.astype(f32) * f32(2.0 ** -32) + f32(2.0 ** -33)
-                u2 = rb.astype(f32) * f32(2.0 ** -32)
                 rad = np.sqrt(f32(-2.0) * np.log(u1))
-                ang = f32(2.0 * np.pi) * u2
+                ang = rb.view(np.int32).astype(f32) * f32(np.pi * 2.0 ** -31)      # [-pi, pi]
                 Z0[s] = (rad * np.cos(ang)).astype(np.float64)
                 Z1[s] = (rad * np.sin(ang)).astype(np.float64)
     else:

@@ -1,0 +1,895 @@
+// mc_kernels.cu -- fused Monte Carlo hot path for sm_100a (B200).
+//
+// Replaces, behind the C ABI of include/b200sv.h, the reference functions (paths under
+// /root/reference/src/stochvolmodels):
+//   simulate_logsv_x_vol_terminal     pricers/logsv_pricer.py:950-1047
+//   logsv_mc_chain_pricer             pricers/logsv_pricer.py:806-867
+//   logsv_mc_chain_pricer_fixed_randoms (stepping part)  pricers/logsv_pricer.py:1100-1162
+//   simulate_heston_x_vol_terminal    pricers/heston_pricer.py:334-381
+//   heston_mc_chain_pricer            pricers/heston_pricer.py:285-331
+//   compute_mc_vars_payoff            utils/mc_payoffs.py:10-88
+//   set_time_grid                     utils/funcs.py:24-47
+//
+// Design: one persistent wave of CTAs; a thread owns one path at a time, keeps (x, log sigma, sigma,
+// sigma^2, qvar) in registers for the whole maturity slice, draws its Gaussians in-kernel (Philox4x32-10 keyed by the
+// GLOBAL path id), and touches HBM only to load / store the SoA state at slice boundaries (24 B + 24 B per path per slice
+// in fp64).  The forward re-centring of the payoffs needs the mean over ALL paths first, hence two phases per slice:
+//   slice kernel  -> per-CTA (sum F e^x, count) partials -> fixed-order reduction            [all-reduce #1 if multi-GPU]
+//   payoff kernel -> per-CTA per-strike (sum, sum^2, count) partials -> fixed-order reduction [all-reduce #2 if multi-GPU]
+// All moment arithmetic is fp64 and every reduction has a fixed order => bitwise reproducible for a given launch shape.
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "../../include/b200sv.h"
+#include "common.cuh"
+#include "fastmath64.cuh"
+#include "philox.cuh"
+
+namespace b200sv {
+
+static thread_local long long g_launches = 0;
+constexpr int kThreads = 256;
+constexpr int kStrikeChunk = 8;
+
+// --------------------------------------------------------------------------------------------------------------------
+// per-step model updates
+// --------------------------------------------------------------------------------------------------------------------
+struct LogsvConsts {   // all dt / sqrt(dt) factors folded in on the host (fp64)
+  double cx;    // alpha * 0.5 * eta^2 * dt          x  += cx * sigma^2 + ce * sigma * z0
+  double ce;    // eta * sqrt(dt)
+  double a0;    // (-kappa1 + kappa2*theta - 0.5*vartheta^2) * dt
+  double a1;    // kappa1 * theta * dt               L  += a0 + a1 / sigma + a2 * sigma + b0 z0 + b1 z1
+  double a2;    // (adj - kappa2) * dt
+  double b0;    // beta * sqrt(dt)
+  double b1;    // volvol * sqrt(dt)
+  double cq;    // 0.5 * eta^2 * dt                  q  += cq * (sigma_old^2 + sigma_new^2)
+};
+
+struct HestonConsts {
+  double hx;    // -0.5 * dt                         x += hx * v + sdt * sqrt(v) * z0
+  double sdt;   // sqrt(dt)
+  double dt;    //                                   q += dt * v
+  double kdt;   // kappa * dt                        v += kdt * (theta - v) + sqrt(v) * (c0 z0 + c1 z1);  v = max(v, 1e-4)
+  double theta;
+  double c0;    // volvol * rho * sqrt(dt)
+  double c1;    // volvol * sqrt(1 - rho^2) * sqrt(dt)
+};
+
+static LogsvConsts make_logsv_consts(const b200sv_logsv_params& p, double eta, bool spot, double dt) {
+  // measure switch: pricers/logsv_pricer.py:1032-1035
+  const double alpha = spot ? -1.0 : 1.0, adj = spot ? 0.0 : p.beta * eta;
+  const double vt2 = p.beta * p.beta + p.volvol * p.volvol, sdt = std::sqrt(dt);
+  LogsvConsts c;
+  c.cx = alpha * 0.5 * eta * eta * dt;
+  c.ce = eta * sdt;
+  c.a0 = (-p.kappa1 + p.kappa2 * p.theta - 0.5 * vt2) * dt;
+  c.a1 = p.kappa1 * p.theta * dt;
+  c.a2 = (adj - p.kappa2) * dt;
+  c.b0 = p.beta * sdt;
+  c.b1 = p.volvol * sdt;
+  c.cq = 0.5 * eta * eta * dt;
+  return c;
+}
+
+static HestonConsts make_heston_consts(const b200sv_heston_params& p, double dt) {
+  const double sdt = std::sqrt(dt);
+  HestonConsts c;
+  c.hx = -0.5 * dt;
+  c.sdt = sdt;
+  c.dt = dt;
+  c.kdt = p.kappa * dt;
+  c.theta = p.theta;
+  c.c0 = p.volvol * p.rho * sdt;
+  c.c1 = p.volvol * std::sqrt(1.0 - p.rho * p.rho) * sdt;
+  return c;
+}
+
+template <typename Real>
+struct LogsvPath;
+
+// fp64 state: reformulated update (same scheme, constants folded, 1/sigma = exp(-L) from the shared polynomial)
+template <>
+struct LogsvPath<double> {
+  double x, L, s, s2, inv, q;
+  double cx, ce, a0, a1, a2, b0, b1, cq;
+  __device__ __forceinline__ LogsvPath(const LogsvConsts& c)
+      : cx(c.cx), ce(c.ce), a0(c.a0), a1(c.a1), a2(c.a2), b0(c.b0), b1(c.b1), cq(c.cq) {}
+  __device__ __forceinline__ void load(double x0, double sigma0, double q0) {
+    x = x0;
+    q = q0;
+    L = log(sigma0);               // vol_var = np.log(sigma0), logsv_pricer.py:1039
+    L = fmin(fmax(L, -700.0), 700.0);
+    exp_pair(L, s, inv);
+    s = sigma0;                    // keep the loaded sigma itself for the first step
+    s2 = s * s;
+  }
+  __device__ __forceinline__ void step(double z0, double z1) {
+    const double t = s * z0;
+    x = fma(cx, s2, x);
+    x = fma(ce, t, x);
+    double l = L + a0;
+    l = fma(a1, inv, l);
+    l = fma(a2, s, l);
+    l = fma(b0, z0, l);
+    l = fma(b1, z1, l);
+    L = fmin(fmax(l, -700.0), 700.0);
+    exp_pair(L, s, inv);
+    const double s2n = s * s;
+    q = fma(cq, s2 + s2n, q);
+    s2 = s2n;
+  }
+  __device__ __forceinline__ double sigma() const { return s; }
+};
+
+// fp32 state (opt-in B200SV_STATE_F32): SFU exp / reciprocal
+template <>
+struct LogsvPath<float> {
+  float x, L, s, s2, inv, q;
+  float cx, ce, a0, a1, a2, b0, b1, cq;
+  __device__ __forceinline__ LogsvPath(const LogsvConsts& c)
+      : cx((float)c.cx), ce((float)c.ce), a0((float)c.a0), a1((float)c.a1), a2((float)c.a2), b0((float)c.b0),
+        b1((float)c.b1), cq((float)c.cq) {}
+  __device__ __forceinline__ void load(float x0, float sigma0, float q0) {
+    x = x0;
+    q = q0;
+    L = __logf(sigma0);
+    s = sigma0;
+    s2 = s * s;
+    inv = __frcp_rn(s);
+  }
+  __device__ __forceinline__ void step(float z0, float z1) {
+    const float t = s * z0;
+    x = fmaf(cx, s2, x);
+    x = fmaf(ce, t, x);
+    float l = L + a0;
+    l = fmaf(a1, inv, l);
+    l = fmaf(a2, s, l);
+    l = fmaf(b0, z0, l);
+    l = fmaf(b1, z1, l);
+    L = fminf(fmaxf(l, -80.0f), 80.0f);
+    s = __expf(L);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(s));
+    const float s2n = s * s;
+    q = fmaf(cq, s2 + s2n, q);
+    s2 = s2n;
+  }
+  __device__ __forceinline__ float sigma() const { return s; }
+};
+
+template <typename Real>
+struct HestonPath {
+  Real x, v, q;
+  Real hx, sdt, dt, kdt, theta, c0, c1;
+  __device__ __forceinline__ HestonPath(const HestonConsts& c)
+      : hx((Real)c.hx), sdt((Real)c.sdt), dt((Real)c.dt), kdt((Real)c.kdt), theta((Real)c.theta), c0((Real)c.c0), c1((Real)c.c1) {}
+  __device__ __forceinline__ void load(Real x0, Real v0, Real q0) {
+    x = x0;
+    v = v0;
+    q = q0;
+  }
+  // pricers/heston_pricer.py:372-379 (floor-Euler): everything on the OLD variance, then v = max(v, 1e-4)
+  __device__ __forceinline__ void step(Real z0, Real z1) {
+    const Real sig = sqrt(v);
+    x = fma(hx, v, x);
+    x = fma(sig * sdt, z0, x);
+    q = fma(dt, v, q);
+    Real vn = fma(kdt, theta - v, v);
+    vn = fma(sig, fma(c0, z0, c1 * z1), vn);
+    v = vn > (Real)1e-4 ? vn : (Real)1e-4;     // np.maximum(var0, 1e-4); NaN-propagating like numpy is moot: no NaN can arise
+  }
+  __device__ __forceinline__ Real sigma() const { return v; }
+};
+
+// --------------------------------------------------------------------------------------------------------------------
+// fused slice kernel
+// --------------------------------------------------------------------------------------------------------------------
+template <typename Real>
+struct SliceArgs {
+  Real* x;
+  Real* v;      // sigma (LogSV) or variance (Heston)
+  Real* q;
+  long long n;
+  unsigned long long path_offset;
+  int init;
+  double v_init;
+  int nsteps;
+  unsigned int slice;
+  unsigned long long seed;
+  double forward;
+  double* partials;   // [gridDim.x][2]
+};
+
+template <typename Path, typename Consts, typename Real, bool GAUSS64>
+__global__ void __launch_bounds__(kThreads) mc_slice_kernel(SliceArgs<Real> a, Consts consts) {
+  __shared__ double red[2 * kThreads / 32];
+  double acc[2] = {0.0, 0.0};
+  Path p(consts);
+  const long long stride = (long long)gridDim.x * kThreads;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < a.n; i += stride) {
+    if (a.init)
+      p.load((Real)0, (Real)a.v_init, (Real)0);
+    else
+      p.load(a.x[i], a.v[i], a.q[i]);
+    StepNormals<Real, GAUSS64> rng(a.seed, a.path_offset + (unsigned long long)i, a.slice);
+    if constexpr (GAUSS64) {
+      for (int s = 0; s < a.nsteps; ++s) {
+        Real z0, z1;
+        rng.get((uint32_t)s, z0, z1);
+        p.step(z0, z1);
+      }
+    } else {
+      const int ncalls = a.nsteps >> 1;
+      for (int c = 0; c < ncalls; ++c) {
+        Real a0, a1, b0, b1;
+        rng.get2((uint32_t)c, a0, a1, b0, b1);
+        p.step(a0, a1);
+        p.step(b0, b1);
+      }
+      if (a.nsteps & 1) {
+        Real a0, a1, b0, b1;
+        rng.get2((uint32_t)ncalls, a0, a1, b0, b1);
+        p.step(a0, a1);
+      }
+    }
+    a.x[i] = p.x;
+    a.v[i] = p.sigma();
+    a.q[i] = p.q;
+    // spots_t = forward*np.exp(x0); nanmean over all paths (utils/mc_payoffs.py:61-62)
+    const double spot = a.forward * exp((double)p.x);
+    if (spot == spot) {
+      acc[0] += spot;
+      acc[1] += 1.0;
+    }
+  }
+  block_sum<2, kThreads>(acc, red);
+  if (threadIdx.x == 0) {
+    a.partials[2 * blockIdx.x + 0] = acc[0];
+    a.partials[2 * blockIdx.x + 1] = acc[1];
+  }
+}
+
+// out[k] = sum_b partials[b*K + k] for k < K_out, fixed order: one warp per k, lanes stride over b, shuffle tree.
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __restrict__ partials, int nblk, int K, int K_out,
+                                                              double* __restrict__ out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int k = warp; k < K_out; k += nw) {
+    double s = 0.0;
+    for (int b = lane; b < nblk; b += 32) s += partials[(size_t)b * K + k];
+    s = warp_sum(s);
+    if (lane == 0) out[k] = s;
+  }
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// strict fixed-random steppers (parity entry points): reference evaluation order, no FMA contraction
+// --------------------------------------------------------------------------------------------------------------------
+struct LogsvRaw {
+  double theta, kappa1, kappa2, beta, volvol, eta, alpha, adj, dt;
+};
+
+__global__ void __launch_bounds__(kThreads) logsv_step_fixed_kernel(double* __restrict__ x, double* __restrict__ sigma,
+                                                                   double* __restrict__ qvar, const double* __restrict__ W0,
+                                                                   const double* __restrict__ W1, int S, long long N, LogsvRaw r) {
+  // pricers/logsv_pricer.py:1027-1047, expression by expression (fastmath=False in the reference)
+  const double sdt = __dsqrt_rn(r.dt);
+  const double vartheta2 = __dadd_rn(__dmul_rn(r.beta, r.beta), __dmul_rn(r.volvol, r.volvol));
+  const double eta2 = __dmul_rn(r.eta, r.eta);
+  const double k1theta = __dmul_rn(r.kappa1, r.theta);
+  const double half_alpha = __dmul_rn(r.alpha, 0.5);
+  const double half_vt2 = __dmul_rn(0.5, vartheta2);
+  const long long stride = (long long)gridDim.x * kThreads;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < N; i += stride) {
+    double xi = x[i], si = sigma[i], qi = qvar[i];
+    double L = log(si);
+    for (int s = 0; s < S; ++s) {
+      const double w0 = __dmul_rn(sdt, __ldg(W0 + (size_t)s * N + i));
+      const double w1 = __dmul_rn(sdt, __ldg(W1 + (size_t)s * N + i));
+      const double s2dt = __dmul_rn(__dmul_rn(__dmul_rn(eta2, si), si), r.dt);
+      xi = __dadd_rn(__dadd_rn(xi, __dmul_rn(half_alpha, s2dt)), __dmul_rn(__dmul_rn(r.eta, si), w0));
+      double d = __dadd_rn(__dadd_rn(__ddiv_rn(k1theta, si), -r.kappa1), __dmul_rn(r.kappa2, __dadd_rn(r.theta, -si)));
+      d = __dadd_rn(__dadd_rn(d, __dmul_rn(r.adj, si)), -half_vt2);
+      L = __dadd_rn(__dadd_rn(__dadd_rn(L, __dmul_rn(d, r.dt)), __dmul_rn(r.beta, w0)), __dmul_rn(r.volvol, w1));
+      si = exp(L);
+      qi = __dadd_rn(qi, __dmul_rn(0.5, __dadd_rn(s2dt, __dmul_rn(__dmul_rn(__dmul_rn(eta2, si), si), r.dt))));
+    }
+    x[i] = xi;
+    sigma[i] = si;
+    qvar[i] = qi;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) heston_step_fixed_kernel(double* __restrict__ x, double* __restrict__ var,
+                                                                    double* __restrict__ qvar, const double* __restrict__ W0,
+                                                                    const double* __restrict__ W1, int S, long long N,
+                                                                    b200sv_heston_params p, double dt) {
+  // pricers/heston_pricer.py:366-379
+  const double sdt = __dsqrt_rn(dt);
+  const double rho_1 = __dsqrt_rn(__dadd_rn(1.0, -__dmul_rn(p.rho, p.rho)));
+  const long long stride = (long long)gridDim.x * kThreads;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < N; i += stride) {
+    double xi = x[i], vi = var[i], qi = qvar[i];
+    for (int s = 0; s < S; ++s) {
+      const double w0 = __dmul_rn(sdt, __ldg(W0 + (size_t)s * N + i));
+      const double w1 = __dmul_rn(sdt, __ldg(W1 + (size_t)s * N + i));
+      const double sig = __dsqrt_rn(vi);
+      const double vdt = __dmul_rn(vi, dt);
+      xi = __dadd_rn(__dadd_rn(xi, -__dmul_rn(0.5, vdt)), __dmul_rn(sig, w0));
+      qi = __dadd_rn(qi, vdt);
+      const double drift = __dmul_rn(__dmul_rn(p.kappa, __dadd_rn(p.theta, -vi)), dt);
+      const double diff = __dmul_rn(__dmul_rn(sig, p.volvol), __dadd_rn(__dmul_rn(p.rho, w0), __dmul_rn(rho_1, w1)));
+      vi = __dadd_rn(__dadd_rn(vi, drift), diff);
+      vi = vi < 1e-4 ? 1e-4 : vi;   // np.maximum(var0, 1e-4): NaN stays NaN
+    }
+    x[i] = xi;
+    var[i] = vi;
+    qvar[i] = qi;
+  }
+}
+
+// (sum F e^x over non-NaN, count) partials for externally supplied states (b200sv_mc_payoffs)
+__global__ void __launch_bounds__(kThreads) spot_moments_kernel(const double* __restrict__ x, long long n, double forward,
+                                                               double* __restrict__ partials) {
+  __shared__ double red[2 * kThreads / 32];
+  double acc[2] = {0.0, 0.0};
+  const long long stride = (long long)gridDim.x * kThreads;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+    const double spot = forward * exp(x[i]);
+    if (spot == spot) {
+      acc[0] += spot;
+      acc[1] += 1.0;
+    }
+  }
+  block_sum<2, kThreads>(acc, red);
+  if (threadIdx.x == 0) {
+    partials[2 * blockIdx.x + 0] = acc[0];
+    partials[2 * blockIdx.x + 1] = acc[1];
+  }
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// payoff sums: utils/mc_payoffs.py:61-88
+// --------------------------------------------------------------------------------------------------------------------
+template <typename Real>
+__global__ void __launch_bounds__(kThreads) payoff_kernel(const Real* __restrict__ x, const Real* __restrict__ q, long long n,
+                                                         double ttm, double forward, const double* __restrict__ strikes,
+                                                         const int8_t* __restrict__ types, int J, int variable_type,
+                                                         const double* __restrict__ moments, double* __restrict__ partials,
+                                                         int Kpad /* = 3 * kStrikeChunk * gridDim.y */) {
+  __shared__ double red[3 * kStrikeChunk * kThreads / 32];
+  const int j0 = blockIdx.y * kStrikeChunk;
+  double kk[kStrikeChunk];
+  int ty[kStrikeChunk];
+#pragma unroll
+  for (int c = 0; c < kStrikeChunk; ++c) {
+    const int j = j0 + c;
+    kk[c] = j < J ? strikes[j] : 0.0;
+    ty[c] = j < J ? (int)types[j] : -1;
+  }
+  // correnction = np.nanmean(spots_t) - forward
+  const double corr = moments[0] / moments[1] - forward;
+  const double inv_ttm_is_qvar = variable_type == B200SV_Q_VAR ? 1.0 : 0.0;
+  double acc[3 * kStrikeChunk];
+#pragma unroll
+  for (int c = 0; c < 3 * kStrikeChunk; ++c) acc[c] = 0.0;
+  const long long stride = (long long)gridDim.x * kThreads;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+    const double spot = forward * exp((double)x[i]) - corr;
+    const double under = inv_ttm_is_qvar != 0.0 ? (double)q[i] / ttm : spot;
+#pragma unroll
+    for (int c = 0; c < kStrikeChunk; ++c) {
+      if (ty[c] >= 0) {
+        const bool is_put = (ty[c] & 1);
+        double pay = is_put ? (under < kk[c] ? kk[c] - under : 0.0) : (under > kk[c] ? under - kk[c] : 0.0);
+        // np.where(np.greater(nan, k), ..., 0.0) == 0.0: a NaN underlying pays 0 for C/P and 0/NaN = NaN (skipped) for IC/IP
+        if (ty[c] >= 2) pay = pay / spot;
+        if (pay == pay) {
+          acc[3 * c + 0] += pay;
+          acc[3 * c + 1] += pay * pay;
+          acc[3 * c + 2] += 1.0;
+        }
+      }
+    }
+  }
+  block_sum<3 * kStrikeChunk, kThreads>(acc, red);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int c = 0; c < 3 * kStrikeChunk; ++c) partials[(size_t)blockIdx.x * Kpad + 3 * j0 + c] = acc[c];
+  }
+}
+
+__global__ void payoff_finalize_kernel(const double* __restrict__ sums, int J, double discfactor, double total_paths,
+                                       double* __restrict__ prices, double* __restrict__ stderrs) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= J) return;
+  const double s1 = sums[3 * j], s2 = sums[3 * j + 1], cnt = sums[3 * j + 2];
+  const double mean = s1 / cnt;
+  double var = s2 / cnt - mean * mean;
+  var = var > 0.0 ? var : 0.0;
+  prices[j] = discfactor * mean;                               // discfactor*np.nanmean(payoff)
+  stderrs[j] = discfactor * sqrt(var) / sqrt(total_paths);     // discfactor*np.nanstd(payoff) / sqrt(x0.shape[0])
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// debug / parity export of the normals the fused kernel draws
+// --------------------------------------------------------------------------------------------------------------------
+template <bool GAUSS64>
+__global__ void device_normals_kernel(unsigned long long seed, unsigned long long path0, long long n, unsigned int slice,
+                                      int nsteps, double* __restrict__ z0, double* __restrict__ z1) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  StepNormals<double, GAUSS64> rng(seed, path0 + (unsigned long long)i, slice);
+  if constexpr (GAUSS64) {
+    for (int s = 0; s < nsteps; ++s) {
+      double a, b;
+      rng.get((uint32_t)s, a, b);
+      z0[(size_t)s * n + i] = a;
+      z1[(size_t)s * n + i] = b;
+    }
+  } else {
+    for (int c = 0; 2 * c < nsteps; ++c) {
+      double a0, a1, b0, b1;
+      rng.get2((uint32_t)c, a0, a1, b0, b1);
+      z0[(size_t)(2 * c) * n + i] = a0;
+      z1[(size_t)(2 * c) * n + i] = a1;
+      if (2 * c + 1 < nsteps) {
+        z0[(size_t)(2 * c + 1) * n + i] = b0;
+        z1[(size_t)(2 * c + 1) * n + i] = b1;
+      }
+    }
+  }
+}
+
+// exp_pair self-test kernel (tests): out[2i] = exp(L), out[2i+1] = exp(-L)
+__global__ void exp_pair_kernel(const double* __restrict__ L, long long n, double* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double a, b;
+  exp_pair(L[i], a, b);
+  out[2 * i] = a;
+  out[2 * i + 1] = b;
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// host side
+// --------------------------------------------------------------------------------------------------------------------
+static int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(-2, std::string(what) + ": " + cudaGetErrorString(e));
+  ++g_launches;
+  return 0;
+}
+
+// int(ttm * n) + 1 and dt = linspace(0, ttm, S+1)[1] - [0] (utils/funcs.py:44-47; numpy linspace: step = ttm / S, y[1] = 1*step)
+static void time_grid(double ttm, int n_per_year, int* S, double* dt) {
+  *S = (int)(ttm * (double)n_per_year) + 1;
+  *dt = (*S == 1) ? ttm : ttm / (double)(*S);   // linspace sets the LAST point to `stop` exactly; with S == 1 y[1] is that point
+}
+
+template <int MODEL, typename Real, bool G64>
+static int launch_slice_t(void* x, void* v, void* q, long long n, long long path_offset, int init, double v_init, int nsteps,
+                          int slice_index, double forward, uint64_t seed, const LogsvConsts* lc, const HestonConsts* hc,
+                          double* moments_out, cudaStream_t st) {
+  SliceArgs<Real> a;
+  a.x = (Real*)x;
+  a.v = (Real*)v;
+  a.q = (Real*)q;
+  a.n = n;
+  a.path_offset = (unsigned long long)path_offset;
+  a.init = init;
+  a.v_init = v_init;
+  a.nsteps = nsteps;
+  a.slice = (unsigned int)slice_index;
+  a.seed = seed;
+  a.forward = forward;
+  Grid g;
+  if constexpr (MODEL == 0)
+    g = persistent_grid(mc_slice_kernel<LogsvPath<Real>, LogsvConsts, Real, G64>, kThreads, n);
+  else
+    g = persistent_grid(mc_slice_kernel<HestonPath<Real>, HestonConsts, Real, G64>, kThreads, n);
+  double* partials = nullptr;
+  B200SV_CUDA(cudaMallocAsync(&partials, sizeof(double) * 2 * g.blocks, st));
+  a.partials = partials;
+  if constexpr (MODEL == 0)
+    mc_slice_kernel<LogsvPath<Real>, LogsvConsts, Real, G64><<<g.blocks, g.threads, 0, st>>>(a, *lc);
+  else
+    mc_slice_kernel<HestonPath<Real>, HestonConsts, Real, G64><<<g.blocks, g.threads, 0, st>>>(a, *hc);
+  if (int rc = check_launch("mc_slice_kernel")) return rc;
+  reduce_partials_kernel<<<1, 64, 0, st>>>(partials, g.blocks, 2, 2, moments_out);
+  if (int rc = check_launch("reduce_partials_kernel")) return rc;
+  B200SV_CUDA(cudaFreeAsync(partials, st));
+  return 0;
+}
+
+template <int MODEL>
+static int launch_slice(void* x, void* v, void* q, long long n, long long path_offset, int init, double v_init, int nsteps,
+                        int slice_index, double forward, uint64_t seed, int flags, const LogsvConsts* lc, const HestonConsts* hc,
+                        double* moments_out, cudaStream_t st) {
+  const bool f32 = flags & B200SV_STATE_F32, g64 = flags & B200SV_GAUSS_F64;
+  if (!f32 && !g64) return launch_slice_t<MODEL, double, false>(x, v, q, n, path_offset, init, v_init, nsteps, slice_index, forward, seed, lc, hc, moments_out, st);
+  if (!f32 && g64) return launch_slice_t<MODEL, double, true>(x, v, q, n, path_offset, init, v_init, nsteps, slice_index, forward, seed, lc, hc, moments_out, st);
+  if (f32 && !g64) return launch_slice_t<MODEL, float, false>(x, v, q, n, path_offset, init, v_init, nsteps, slice_index, forward, seed, lc, hc, moments_out, st);
+  return launch_slice_t<MODEL, float, true>(x, v, q, n, path_offset, init, v_init, nsteps, slice_index, forward, seed, lc, hc, moments_out, st);
+}
+
+template <typename Real>
+static int launch_payoff_t(const void* x, const void* q, long long n, double ttm, double forward, const double* strikes,
+                           const int8_t* types, int J, int variable_type, const double* moments, double* sums_out,
+                           cudaStream_t st) {
+  const int chunks = (J + kStrikeChunk - 1) / kStrikeChunk;
+  const int Kpad = 3 * kStrikeChunk * chunks;
+  Grid g = persistent_grid(payoff_kernel<Real>, kThreads, n);
+  g.blocks = std::max(1, g.blocks / chunks);
+  double* partials = nullptr;
+  B200SV_CUDA(cudaMallocAsync(&partials, sizeof(double) * (size_t)Kpad * g.blocks, st));
+  payoff_kernel<Real><<<dim3(g.blocks, chunks), g.threads, 0, st>>>((const Real*)x, (const Real*)q, n, ttm, forward, strikes,
+                                                                      types, J, variable_type, moments, partials, Kpad);
+  if (int rc = check_launch("payoff_kernel")) return rc;
+  reduce_partials_kernel<<<1, 256, 0, st>>>(partials, g.blocks, Kpad, 3 * J, sums_out);
+  if (int rc = check_launch("reduce_partials_kernel")) return rc;
+  B200SV_CUDA(cudaFreeAsync(partials, st));
+  return 0;
+}
+
+static int validate_chain(int M, const double* ttms, const int* offsets, const int8_t* types, int variable_type) {
+  B200SV_REQUIRE(M >= 1, "M must be >= 1");
+  double t0 = 0.0;
+  for (int m = 0; m < M; ++m) {
+    B200SV_REQUIRE(ttms[m] > t0, "ttms must be positive and strictly increasing");   // data/option_chain.py:147-153
+    B200SV_REQUIRE(offsets[m + 1] >= offsets[m], "offsets must be non-decreasing");
+    t0 = ttms[m];
+  }
+  for (int j = offsets[0]; j < offsets[M]; ++j)
+    if (types[j] < 0 || types[j] > 3) return fail(-3, "unknown option payoff code");      // utils/mc_payoffs.py:83-84
+  if (variable_type != B200SV_LOG_RETURN && variable_type != B200SV_Q_VAR)
+    return fail(-4, "variable_type not implemented");                                      // utils/mc_payoffs.py:69-70
+  return 0;
+}
+
+// shared host-level chain driver
+template <int MODEL>
+static int mc_chain_host(const b200sv_logsv_params* lp, const b200sv_heston_params* hp, int M, const double* ttms,
+                         const double* forwards, const double* discfactors, const double* etas, const int* offsets,
+                         const double* strikes, const int8_t* types, long long nb_path, int nb_steps_per_year, int is_spot,
+                         int variable_type, uint64_t seed, int flags, double* prices_out, double* stderr_out) {
+  B200SV_REQUIRE(nb_path >= 1, "nb_path must be >= 1");
+  B200SV_REQUIRE(nb_steps_per_year >= 1, "nb_steps_per_year must be >= 1");
+  if (int rc = validate_chain(M, ttms, offsets, types, variable_type)) return rc;
+  const int Jtot = offsets[M] - offsets[0];
+  const size_t esz = (flags & B200SV_STATE_F32) ? 4 : 8;
+  cudaStream_t st = 0;
+  char *x = nullptr;
+  double *d_strikes = nullptr, *d_out = nullptr, *d_mom = nullptr, *d_sums = nullptr;
+  int8_t* d_types = nullptr;
+  B200SV_CUDA(cudaMallocAsync(&x, 3 * esz * (size_t)nb_path, st));
+  char *v = x + esz * (size_t)nb_path, *q = x + 2 * esz * (size_t)nb_path;
+  const int Jalloc = std::max(Jtot, 1);
+  B200SV_CUDA(cudaMallocAsync(&d_strikes, sizeof(double) * Jalloc, st));
+  B200SV_CUDA(cudaMallocAsync(&d_types, Jalloc, st));
+  B200SV_CUDA(cudaMallocAsync(&d_out, sizeof(double) * 2 * Jalloc, st));
+  B200SV_CUDA(cudaMallocAsync(&d_mom, sizeof(double) * 2, st));
+  B200SV_CUDA(cudaMallocAsync(&d_sums, sizeof(double) * 3 * Jalloc, st));
+  if (Jtot > 0) {
+    B200SV_CUDA(cudaMemcpyAsync(d_strikes, strikes + offsets[0], sizeof(double) * Jtot, cudaMemcpyHostToDevice, st));
+    B200SV_CUDA(cudaMemcpyAsync(d_types, types + offsets[0], Jtot, cudaMemcpyHostToDevice, st));
+  }
+  double t0 = 0.0;
+  int rc = 0;
+  for (int m = 0; m < M && rc == 0; ++m) {
+    int S;
+    double dt;
+    time_grid(ttms[m] - t0, nb_steps_per_year, &S, &dt);
+    t0 = ttms[m];
+    if (MODEL == 0) {
+      const LogsvConsts c = make_logsv_consts(*lp, etas ? etas[m] : 1.0, is_spot != 0, dt);
+      rc = launch_slice<0>(x, v, q, nb_path, 0, m == 0, lp->sigma0, S, m, forwards[m], seed, flags, &c, nullptr, d_mom, st);
+    } else {
+      const HestonConsts c = make_heston_consts(*hp, dt);
+      rc = launch_slice<1>(x, v, q, nb_path, 0, m == 0, hp->v0, S, m, forwards[m], seed, flags, nullptr, &c, d_mom, st);
+    }
+    if (rc) break;
+    const int J = offsets[m + 1] - offsets[m], jo = offsets[m] - offsets[0];
+    if (J == 0) continue;
+    if (flags & B200SV_STATE_F32)
+      rc = launch_payoff_t<float>(x, q, nb_path, ttms[m], forwards[m], d_strikes + jo, d_types + jo, J, variable_type, d_mom, d_sums, st);
+    else
+      rc = launch_payoff_t<double>(x, q, nb_path, ttms[m], forwards[m], d_strikes + jo, d_types + jo, J, variable_type, d_mom, d_sums, st);
+    if (rc) break;
+    payoff_finalize_kernel<<<(J + 127) / 128, 128, 0, st>>>(d_sums, J, discfactors[m], (double)nb_path, d_out + jo, d_out + Jalloc + jo);
+    rc = check_launch("payoff_finalize_kernel");
+  }
+  if (rc == 0 && Jtot > 0) {
+    cudaError_t e = cudaMemcpyAsync(prices_out, d_out, sizeof(double) * Jtot, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(stderr_out, d_out + Jalloc, sizeof(double) * Jtot, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) rc = fail(-2, std::string("D2H: ") + cudaGetErrorString(e));
+  }
+  cudaFreeAsync(x, st);
+  cudaFreeAsync(d_strikes, st);
+  cudaFreeAsync(d_types, st);
+  cudaFreeAsync(d_out, st);
+  cudaFreeAsync(d_mom, st);
+  cudaFreeAsync(d_sums, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (rc == 0 && e != cudaSuccess) rc = fail(-2, std::string("sync: ") + cudaGetErrorString(e));
+  return rc;
+}
+
+template <int MODEL>
+static int terminal_host(const b200sv_logsv_params* lp, const b200sv_heston_params* hp, double ttm, long long nb_path,
+                         int nb_steps_per_year, int is_spot, double eta, uint64_t seed, int flags, double* x, double* v, double* q) {
+  B200SV_REQUIRE(nb_path >= 1 && ttm > 0.0 && nb_steps_per_year >= 1, "nb_path, ttm, nb_steps_per_year must be positive");
+  B200SV_REQUIRE(!(flags & B200SV_STATE_F32), "terminal values are returned as float64: use B200SV_STATE_F64");
+  cudaStream_t st = 0;
+  double *d = nullptr, *d_mom = nullptr;
+  B200SV_CUDA(cudaMallocAsync(&d, sizeof(double) * 3 * (size_t)nb_path, st));
+  B200SV_CUDA(cudaMallocAsync(&d_mom, sizeof(double) * 2, st));
+  int S;
+  double dt;
+  time_grid(ttm, nb_steps_per_year, &S, &dt);
+  int rc;
+  if (MODEL == 0) {
+    const LogsvConsts c = make_logsv_consts(*lp, eta, is_spot != 0, dt);
+    rc = launch_slice<0>(d, d + nb_path, d + 2 * nb_path, nb_path, 0, 1, lp->sigma0, S, 0, 1.0, seed, flags, &c, nullptr, d_mom, st);
+  } else {
+    const HestonConsts c = make_heston_consts(*hp, dt);
+    rc = launch_slice<1>(d, d + nb_path, d + 2 * nb_path, nb_path, 0, 1, hp->v0, S, 0, 1.0, seed, flags, nullptr, &c, d_mom, st);
+  }
+  if (rc == 0) {
+    cudaError_t e = cudaMemcpyAsync(x, d, sizeof(double) * nb_path, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(v, d + nb_path, sizeof(double) * nb_path, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(q, d + 2 * nb_path, sizeof(double) * nb_path, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) rc = fail(-2, std::string("D2H: ") + cudaGetErrorString(e));
+  }
+  cudaFreeAsync(d, st);
+  cudaFreeAsync(d_mom, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (rc == 0 && e != cudaSuccess) rc = fail(-2, std::string("sync: ") + cudaGetErrorString(e));
+  return rc;
+}
+
+}  // namespace b200sv
+
+using namespace b200sv;
+
+extern "C" {
+
+const char* b200sv_last_error(void) { return last_error().c_str(); }
+int b200sv_version(void) { return B200SV_VERSION; }
+long long b200sv_launch_count(void) { return g_launches; }
+void b200sv_reset_launch_count(void) { g_launches = 0; }
+
+// internal hook for the MGF translation unit
+void b200sv_internal_count_launch(void) { ++g_launches; }
+
+int b200sv_logsv_mc_chain(const b200sv_logsv_params* params, int M, const double* ttms, const double* forwards,
+                          const double* discfactors, const double* etas, const int* offsets, const double* strikes,
+                          const int8_t* types, long long nb_path, int nb_steps_per_year, int is_spot_measure, int variable_type,
+                          uint64_t seed, int flags, double* prices_out, double* stderr_out) {
+  B200SV_REQUIRE(params && ttms && forwards && discfactors && offsets && prices_out && stderr_out, "null pointer");
+  return mc_chain_host<0>(params, nullptr, M, ttms, forwards, discfactors, etas, offsets, strikes, types, nb_path,
+                          nb_steps_per_year, is_spot_measure, variable_type, seed, flags, prices_out, stderr_out);
+}
+
+int b200sv_heston_mc_chain(const b200sv_heston_params* params, int M, const double* ttms, const double* forwards,
+                           const double* discfactors, const int* offsets, const double* strikes, const int8_t* types,
+                           long long nb_path, int nb_steps_per_year, int variable_type, uint64_t seed, int flags, int scheme,
+                           double* prices_out, double* stderr_out) {
+  B200SV_REQUIRE(params && ttms && forwards && discfactors && offsets && prices_out && stderr_out, "null pointer");
+  B200SV_REQUIRE(scheme == B200SV_HESTON_EULER_FLOOR, "unknown Heston scheme");
+  return mc_chain_host<1>(nullptr, params, M, ttms, forwards, discfactors, nullptr, offsets, strikes, types, nb_path,
+                          nb_steps_per_year, 1, variable_type, seed, flags, prices_out, stderr_out);
+}
+
+int b200sv_logsv_terminal(const b200sv_logsv_params* params, double ttm, long long nb_path, int nb_steps_per_year,
+                          int is_spot_measure, double eta, uint64_t seed, int flags, double* x, double* sigma, double* qvar) {
+  B200SV_REQUIRE(params && x && sigma && qvar, "null pointer");
+  return terminal_host<0>(params, nullptr, ttm, nb_path, nb_steps_per_year, is_spot_measure, eta, seed, flags, x, sigma, qvar);
+}
+
+int b200sv_heston_terminal(const b200sv_heston_params* params, double ttm, long long nb_path, int nb_steps_per_year,
+                           uint64_t seed, int flags, int scheme, double* x, double* var, double* qvar) {
+  B200SV_REQUIRE(params && x && var && qvar, "null pointer");
+  B200SV_REQUIRE(scheme == B200SV_HESTON_EULER_FLOOR, "unknown Heston scheme");
+  return terminal_host<1>(nullptr, params, ttm, nb_path, nb_steps_per_year, 1, 1.0, seed, flags, x, var, qvar);
+}
+
+// ---- device-level ---------------------------------------------------------------------------------------------------
+int b200sv_dev_logsv_slice(void* x, void* sigma, void* qvar, long long n_local, long long path_offset, int init,
+                           const b200sv_logsv_params* params, double eta, int is_spot_measure, int nsteps, double dt,
+                           int slice_index, double forward, uint64_t seed, int flags, double* moments_out, void* stream) {
+  B200SV_REQUIRE(x && sigma && qvar && params && moments_out, "null pointer");
+  B200SV_REQUIRE(n_local >= 1 && nsteps >= 1 && dt > 0.0, "n_local, nsteps, dt must be positive");
+  const LogsvConsts c = make_logsv_consts(*params, eta, is_spot_measure != 0, dt);
+  return launch_slice<0>(x, sigma, qvar, n_local, path_offset, init, params->sigma0, nsteps, slice_index, forward, seed, flags,
+                         &c, nullptr, moments_out, (cudaStream_t)stream);
+}
+
+int b200sv_dev_heston_slice(void* x, void* var, void* qvar, long long n_local, long long path_offset, int init,
+                            const b200sv_heston_params* params, int nsteps, double dt, int slice_index, double forward,
+                            uint64_t seed, int flags, int scheme, double* moments_out, void* stream) {
+  B200SV_REQUIRE(x && var && qvar && params && moments_out, "null pointer");
+  B200SV_REQUIRE(n_local >= 1 && nsteps >= 1 && dt > 0.0, "n_local, nsteps, dt must be positive");
+  B200SV_REQUIRE(scheme == B200SV_HESTON_EULER_FLOOR, "unknown Heston scheme");
+  const HestonConsts c = make_heston_consts(*params, dt);
+  return launch_slice<1>(x, var, qvar, n_local, path_offset, init, params->v0, nsteps, slice_index, forward, seed, flags, nullptr,
+                         &c, moments_out, (cudaStream_t)stream);
+}
+
+int b200sv_dev_payoff_sums(const void* x, const void* qvar, long long n_local, int flags, double ttm, double forward,
+                           const double* strikes, const int8_t* types, int J, int variable_type, const double* moments,
+                           double* sums_out, void* stream) {
+  B200SV_REQUIRE(x && strikes && types && moments && sums_out, "null pointer");
+  B200SV_REQUIRE(J >= 1 && n_local >= 1, "J and n_local must be >= 1");
+  if (variable_type != B200SV_LOG_RETURN && variable_type != B200SV_Q_VAR) return fail(-4, "variable_type not implemented");
+  B200SV_REQUIRE(variable_type == B200SV_LOG_RETURN || qvar, "qvar required for Q_VAR");
+  if (flags & B200SV_STATE_F32)
+    return launch_payoff_t<float>(x, qvar ? qvar : x, n_local, ttm, forward, strikes, types, J, variable_type, moments, sums_out, (cudaStream_t)stream);
+  return launch_payoff_t<double>(x, qvar ? qvar : x, n_local, ttm, forward, strikes, types, J, variable_type, moments, sums_out, (cudaStream_t)stream);
+}
+
+int b200sv_dev_payoff_finalize(const double* sums, int J, double discfactor, long long total_paths, double* prices_out,
+                               double* stderr_out, void* stream) {
+  B200SV_REQUIRE(sums && prices_out && stderr_out && J >= 1, "null pointer / J");
+  payoff_finalize_kernel<<<(J + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, J, discfactor, (double)total_paths, prices_out, stderr_out);
+  return check_launch("payoff_finalize_kernel");
+}
+
+int b200sv_dev_logsv_step_fixed(double* x, double* sigma, double* qvar, const double* W0, const double* W1, int S, long long N,
+                                double dt, const b200sv_logsv_params* params, double eta, int is_spot_measure, void* stream) {
+  B200SV_REQUIRE(x && sigma && qvar && W0 && W1 && params, "null pointer");
+  B200SV_REQUIRE(S >= 0 && N >= 1 && dt > 0.0, "S, N, dt");
+  LogsvRaw r{params->theta, params->kappa1, params->kappa2, params->beta, params->volvol, eta,
+             is_spot_measure ? -1.0 : 1.0, is_spot_measure ? 0.0 : params->beta * eta, dt};
+  Grid g = persistent_grid(logsv_step_fixed_kernel, kThreads, N);
+  logsv_step_fixed_kernel<<<g.blocks, g.threads, 0, (cudaStream_t)stream>>>(x, sigma, qvar, W0, W1, S, N, r);
+  return check_launch("logsv_step_fixed_kernel");
+}
+
+int b200sv_dev_heston_step_fixed(double* x, double* var, double* qvar, const double* W0, const double* W1, int S, long long N,
+                                 double dt, const b200sv_heston_params* params, void* stream) {
+  B200SV_REQUIRE(x && var && qvar && W0 && W1 && params, "null pointer");
+  B200SV_REQUIRE(S >= 0 && N >= 1 && dt > 0.0, "S, N, dt");
+  Grid g = persistent_grid(heston_step_fixed_kernel, kThreads, N);
+  heston_step_fixed_kernel<<<g.blocks, g.threads, 0, (cudaStream_t)stream>>>(x, var, qvar, W0, W1, S, N, *params, dt);
+  return check_launch("heston_step_fixed_kernel");
+}
+
+int b200sv_dev_spot_moments(const double* x, long long n, double forward, double* moments_out, void* stream) {
+  B200SV_REQUIRE(x && moments_out && n >= 1, "null pointer / n");
+  cudaStream_t st = (cudaStream_t)stream;
+  Grid g = persistent_grid(spot_moments_kernel, kThreads, n);
+  double* partials = nullptr;
+  B200SV_CUDA(cudaMallocAsync(&partials, sizeof(double) * 2 * g.blocks, st));
+  spot_moments_kernel<<<g.blocks, g.threads, 0, st>>>(x, n, forward, partials);
+  if (int rc = check_launch("spot_moments_kernel")) return rc;
+  reduce_partials_kernel<<<1, 64, 0, st>>>(partials, g.blocks, 2, 2, moments_out);
+  if (int rc = check_launch("reduce_partials_kernel")) return rc;
+  B200SV_CUDA(cudaFreeAsync(partials, st));
+  return 0;
+}
+
+// ---- host-level fixed-random steppers and payoffs ------------------------------------------------------------------------
+static int step_fixed_host(int model, double* x, double* v, double* q, const double* W0, const double* W1, int S, long long N,
+                           double dt, const b200sv_logsv_params* lp, double eta, int is_spot, const b200sv_heston_params* hp) {
+  B200SV_REQUIRE(x && v && q && (S == 0 || (W0 && W1)), "null pointer");
+  B200SV_REQUIRE(S >= 0 && N >= 1 && dt > 0.0, "S, N, dt");
+  cudaStream_t st = 0;
+  double *d = nullptr, *w = nullptr;
+  const size_t nb = sizeof(double) * (size_t)N, wb = sizeof(double) * (size_t)N * (size_t)std::max(S, 1);
+  B200SV_CUDA(cudaMallocAsync(&d, 3 * nb, st));
+  B200SV_CUDA(cudaMallocAsync(&w, 2 * wb, st));
+  B200SV_CUDA(cudaMemcpyAsync(d, x, nb, cudaMemcpyHostToDevice, st));
+  B200SV_CUDA(cudaMemcpyAsync(d + N, v, nb, cudaMemcpyHostToDevice, st));
+  B200SV_CUDA(cudaMemcpyAsync(d + 2 * N, q, nb, cudaMemcpyHostToDevice, st));
+  if (S > 0) {
+    B200SV_CUDA(cudaMemcpyAsync(w, W0, wb, cudaMemcpyHostToDevice, st));
+    B200SV_CUDA(cudaMemcpyAsync(w + (size_t)N * S, W1, wb, cudaMemcpyHostToDevice, st));
+  }
+  int rc = model == 0 ? b200sv_dev_logsv_step_fixed(d, d + N, d + 2 * N, w, w + (size_t)N * S, S, N, dt, lp, eta, is_spot, st)
+                      : b200sv_dev_heston_step_fixed(d, d + N, d + 2 * N, w, w + (size_t)N * S, S, N, dt, hp, st);
+  if (rc == 0) {
+    cudaError_t e = cudaMemcpyAsync(x, d, nb, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(v, d + N, nb, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(q, d + 2 * N, nb, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) rc = fail(-2, std::string("D2H: ") + cudaGetErrorString(e));
+  }
+  cudaFreeAsync(d, st);
+  cudaFreeAsync(w, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (rc == 0 && e != cudaSuccess) rc = fail(-2, std::string("sync: ") + cudaGetErrorString(e));
+  return rc;
+}
+
+int b200sv_logsv_step_fixed(double* x, double* sigma, double* qvar, const double* W0, const double* W1, int S, long long N,
+                            double dt, const b200sv_logsv_params* params, double eta, int is_spot_measure) {
+  B200SV_REQUIRE(params, "null pointer");
+  return step_fixed_host(0, x, sigma, qvar, W0, W1, S, N, dt, params, eta, is_spot_measure, nullptr);
+}
+
+int b200sv_heston_step_fixed(double* x, double* var, double* qvar, const double* W0, const double* W1, int S, long long N,
+                             double dt, const b200sv_heston_params* params) {
+  B200SV_REQUIRE(params, "null pointer");
+  return step_fixed_host(1, x, var, qvar, W0, W1, S, N, dt, nullptr, 1.0, 1, params);
+}
+
+int b200sv_mc_payoffs(const double* x, const double* qvar, long long N, double ttm, double forward, const double* strikes,
+                      const int8_t* types, int J, double discfactor, int variable_type, double* prices_out, double* stderr_out) {
+  B200SV_REQUIRE(x && strikes && types && prices_out && stderr_out, "null pointer");
+  B200SV_REQUIRE(N >= 1 && J >= 1, "N and J must be >= 1");
+  for (int j = 0; j < J; ++j)
+    if (types[j] < 0 || types[j] > 3) return fail(-3, "unknown option payoff code");
+  if (variable_type != B200SV_LOG_RETURN && variable_type != B200SV_Q_VAR) return fail(-4, "variable_type not implemented");
+  B200SV_REQUIRE(variable_type == B200SV_LOG_RETURN || qvar, "qvar required for Q_VAR");
+  cudaStream_t st = 0;
+  double *d = nullptr, *dk = nullptr, *d_mom = nullptr, *d_sums = nullptr, *d_out = nullptr;
+  int8_t* dt_ = nullptr;
+  const size_t nb = sizeof(double) * (size_t)N;
+  B200SV_CUDA(cudaMallocAsync(&d, 2 * nb, st));
+  B200SV_CUDA(cudaMallocAsync(&dk, sizeof(double) * J, st));
+  B200SV_CUDA(cudaMallocAsync(&dt_, J, st));
+  B200SV_CUDA(cudaMallocAsync(&d_mom, sizeof(double) * 2, st));
+  B200SV_CUDA(cudaMallocAsync(&d_sums, sizeof(double) * 3 * J, st));
+  B200SV_CUDA(cudaMallocAsync(&d_out, sizeof(double) * 2 * J, st));
+  B200SV_CUDA(cudaMemcpyAsync(d, x, nb, cudaMemcpyHostToDevice, st));
+  if (qvar) B200SV_CUDA(cudaMemcpyAsync(d + N, qvar, nb, cudaMemcpyHostToDevice, st));
+  B200SV_CUDA(cudaMemcpyAsync(dk, strikes, sizeof(double) * J, cudaMemcpyHostToDevice, st));
+  B200SV_CUDA(cudaMemcpyAsync(dt_, types, J, cudaMemcpyHostToDevice, st));
+  int rc = b200sv_dev_spot_moments(d, N, forward, d_mom, st);
+  if (rc == 0) rc = launch_payoff_t<double>(d, d + N, N, ttm, forward, dk, dt_, J, variable_type, d_mom, d_sums, st);
+  if (rc == 0) rc = b200sv_dev_payoff_finalize(d_sums, J, discfactor, N, d_out, d_out + J, st);
+  if (rc == 0) {
+    cudaError_t e = cudaMemcpyAsync(prices_out, d_out, sizeof(double) * J, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(stderr_out, d_out + J, sizeof(double) * J, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) rc = fail(-2, std::string("D2H: ") + cudaGetErrorString(e));
+  }
+  cudaFreeAsync(d, st);
+  cudaFreeAsync(dk, st);
+  cudaFreeAsync(dt_, st);
+  cudaFreeAsync(d_mom, st);
+  cudaFreeAsync(d_sums, st);
+  cudaFreeAsync(d_out, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (rc == 0 && e != cudaSuccess) rc = fail(-2, std::string("sync: ") + cudaGetErrorString(e));
+  return rc;
+}
+
+int b200sv_device_normals(uint64_t seed, long long path0, long long n, int slice, int nsteps, int flags, double* z0, double* z1) {
+  B200SV_REQUIRE(z0 && z1 && n >= 1 && nsteps >= 1, "null pointer / sizes");
+  cudaStream_t st = 0;
+  double* d = nullptr;
+  const size_t nb = sizeof(double) * (size_t)n * nsteps;
+  B200SV_CUDA(cudaMallocAsync(&d, 2 * nb, st));
+  const int blocks = (int)((n + 127) / 128);
+  if (flags & B200SV_GAUSS_F64)
+    device_normals_kernel<true><<<blocks, 128, 0, st>>>(seed, (unsigned long long)path0, n, (unsigned)slice, nsteps, d, d + (size_t)n * nsteps);
+  else
+    device_normals_kernel<false><<<blocks, 128, 0, st>>>(seed, (unsigned long long)path0, n, (unsigned)slice, nsteps, d, d + (size_t)n * nsteps);
+  int rc = check_launch("device_normals_kernel");
+  if (rc == 0) {
+    cudaError_t e = cudaMemcpyAsync(z0, d, nb, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(z1, d + (size_t)n * nsteps, nb, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) rc = fail(-2, std::string("D2H: ") + cudaGetErrorString(e));
+  }
+  cudaFreeAsync(d, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (rc == 0 && e != cudaSuccess) rc = fail(-2, std::string("sync: ") + cudaGetErrorString(e));
+  return rc;
+}
+
+int b200sv_debug_exp_pair(const double* L, long long n, double* out /* 2n */) {
+  B200SV_REQUIRE(L && out && n >= 1, "null pointer / n");
+  cudaStream_t st = 0;
+  double *dl = nullptr, *dout = nullptr;
+  B200SV_CUDA(cudaMallocAsync(&dl, sizeof(double) * n, st));
+  B200SV_CUDA(cudaMallocAsync(&dout, sizeof(double) * 2 * n, st));
+  B200SV_CUDA(cudaMemcpyAsync(dl, L, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  exp_pair_kernel<<<(int)((n + 127) / 128), 128, 0, st>>>(dl, n, dout);
+  int rc = check_launch("exp_pair_kernel");
+  if (rc == 0) B200SV_CUDA(cudaMemcpyAsync(out, dout, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, st));
+  cudaFreeAsync(dl, st);
+  cudaFreeAsync(dout, st);
+  B200SV_CUDA(cudaStreamSynchronize(st));
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,636 @@
+// mgf_kernels.cu -- Fourier / moment-generating-function hot path for sm_100a (B200).
+//
+// Replaces (paths under /root/reference/src/stochvolmodels):
+//   func_a_ode_quadratic_terms, func_rhs            pricers/logsv/affine_expansion.py:67-205
+//   solve_ode_for_a / solve_a_ode_grid (RK45)       pricers/logsv/affine_expansion.py:229-303, 492-529
+//       -> scipy.integrate.solve_ivp(method="RK45", rtol=1e-3, atol=1e-6): scipy/integrate/_ivp/rk.py, common.py
+//   compute_logsv_a_mgf_grid (log-MGF contraction)  pricers/logsv/affine_expansion.py:570-685
+//   logsv_chain_pricer (LOG_RETURN)                 pricers/logsv_pricer.py:669-739
+//   compute_heston_mgf_grid, heston_chain_pricer    pricers/heston_pricer.py:183-282
+//   get_phi_grid, _compute_legacy_pricer_weights, vanilla_slice_pricer_with_mgf_grid   utils/mgf_pricer.py:11-34,157-221
+//
+// Design: the grid is P = 1000 independent ODE systems per maturity -- latency bound, no data reuse, no
+// tensor-core shape.  One thread integrates one grid point through ALL maturities of the chain with the coefficient
+// vector A in registers (the reference carries a_t0 across maturities the same way), using the exact step-size control
+// law of SciPy's RK45 so that accepted steps -- and therefore prices -- match the reference to ~1e-13.  CTAs are kept
+// tiny (8..64 threads) so the 1000 threads spread over as many SMs as possible and a warp waits for few slow lanes.
+// A second kernel does the Simpson-weighted Fourier sums, one CTA per strike, fixed-order fp64 reduction.
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "../../include/b200sv.h"
+#include "common.cuh"
+
+extern "C" void b200sv_internal_count_launch(void);
+
+namespace b200sv {
+
+struct cd {
+  double re, im;
+};
+__host__ __device__ __forceinline__ cd mk(double re, double im = 0.0) { return cd{re, im}; }
+__device__ __forceinline__ cd operator+(cd a, cd b) { return cd{a.re + b.re, a.im + b.im}; }
+__device__ __forceinline__ cd operator-(cd a, cd b) { return cd{a.re - b.re, a.im - b.im}; }
+__device__ __forceinline__ cd operator-(cd a) { return cd{-a.re, -a.im}; }
+__device__ __forceinline__ cd operator*(cd a, cd b) { return cd{a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+__device__ __forceinline__ cd operator*(double s, cd a) { return cd{s * a.re, s * a.im}; }
+__device__ __forceinline__ cd operator*(cd a, double s) { return cd{s * a.re, s * a.im}; }
+__device__ __forceinline__ double cabs2(cd a) { return a.re * a.re + a.im * a.im; }
+__device__ __forceinline__ double cabs_(cd a) { return hypot(a.re, a.im); }
+// Smith's division (what numpy uses for complex128)
+__device__ __forceinline__ cd operator/(cd a, cd b) {
+  if (fabs(b.re) >= fabs(b.im)) {
+    const double r = b.im / b.re, d = b.re + b.im * r;
+    return cd{(a.re + a.im * r) / d, (a.im - a.re * r) / d};
+  }
+  const double r = b.re / b.im, d = b.re * r + b.im;
+  return cd{(a.re * r + a.im) / d, (a.im * r - a.re) / d};
+}
+__device__ __forceinline__ cd csqrt_(cd z) {   // principal branch
+  if (z.re == 0.0 && z.im == 0.0) return cd{0.0, z.im};
+  const double t = sqrt(0.5 * (fabs(z.re) + hypot(z.re, z.im)));
+  if (z.re >= 0.0) return cd{t, z.im / (2.0 * t)};
+  return cd{fabs(z.im) / (2.0 * t), copysign(t, z.im)};
+}
+__device__ __forceinline__ cd cexp_(cd z) {
+  double s, c;
+  sincos(z.im, &s, &c);
+  const double e = exp(z.re);
+  return cd{e * c, e * s};
+}
+__device__ __forceinline__ cd clog_(cd z) { return cd{log(hypot(z.re, z.im)), atan2(z.im, z.re)}; }
+
+// --------------------------------------------------------------------------------------------------------------------
+// LogSV affine expansion: per-grid-point coefficients of A' = A^T M A + L A + H (sparse, hand-expanded)
+// --------------------------------------------------------------------------------------------------------------------
+struct LogsvModel {   // phi-independent reals, built on the host: affine_expansion.py:121-135
+  double theta, th2, v2, qv, qv2, lam, k2p, kp, beta_eta, eta2;
+  int spot;
+};
+
+static LogsvModel make_model(const b200sv_logsv_params& p, double eta, bool spot) {
+  LogsvModel m;
+  m.theta = p.theta;
+  m.th2 = p.theta * p.theta;
+  m.v2 = p.beta * p.beta + p.volvol * p.volvol;
+  m.qv = p.theta * m.v2;
+  m.qv2 = m.th2 * m.v2;
+  m.eta2 = eta * eta;
+  if (spot) {
+    m.lam = 0.0;
+    m.k2p = p.kappa2;
+    m.kp = p.kappa1 + p.kappa2 * p.theta;
+  } else {
+    m.lam = p.beta * m.th2 * eta;
+    m.k2p = p.kappa2 - p.beta * eta;
+    m.kp = p.kappa1 + p.kappa2 * p.theta - 2 * p.beta * p.theta * eta;
+  }
+  m.beta_eta = p.beta * eta;
+  m.spot = spot ? 1 : 0;
+  return m;
+}
+
+struct Coef {   // the phi/psi-dependent entries of L and H (affine_expansion.py:166-183)
+  cd l01, l11, l12, l21, l22, l23, l32, l33, l34, l43, l44, h0, h1, h2;
+};
+
+__device__ __forceinline__ Coef make_coef(const LogsvModel& m, cd phi, cd psi) {
+  Coef c;
+  const cd b = m.beta_eta * phi;
+  c.l01 = mk(m.lam) - m.th2 * b;
+  c.l11 = mk(-m.kp) - (2.0 * m.theta) * b;
+  c.l12 = 2.0 * (mk(m.lam + m.qv) - m.th2 * b);
+  c.l21 = mk(-m.k2p) - b;
+  c.l22 = mk(m.v2 - 2.0 * m.kp) - (4.0 * m.theta) * b;
+  c.l23 = 3.0 * (mk(2.0 * m.qv) - m.th2 * b);
+  c.l32 = -2.0 * (mk(m.k2p) + b);
+  c.l33 = 3.0 * (mk(m.v2 - m.kp) - (2.0 * m.theta) * b);
+  c.l34 = 4.0 * (mk(3.0 * m.qv) - m.th2 * b);
+  c.l43 = -3.0 * (mk(m.k2p) + b);
+  c.l44 = 2.0 * (mk(m.v2 - 2.0 * m.kp) - (4.0 * m.theta) * b);
+  const cd r = m.spot ? phi * (phi + mk(1.0)) - 2.0 * psi : phi * (phi - mk(1.0)) - 2.0 * psi;
+  c.h0 = (0.5 * m.th2 * m.eta2) * r;
+  c.h1 = (m.theta * m.eta2) * r;
+  c.h2 = (0.5 * m.eta2) * r;
+  return c;
+}
+
+template <int N>
+__device__ __forceinline__ void rhs(const cd (&A)[N], const LogsvModel& m, const Coef& c, cd (&out)[N]) {
+  const double v2 = m.v2, qv = m.qv, qv2 = m.qv2;
+  const cd a1 = A[1], a2 = A[2];
+  const cd a11 = a1 * a1, a12 = a1 * a2, a22 = a2 * a2;
+  if constexpr (N == 5) {
+    const cd a3 = A[3], a4 = A[4];
+    const cd a13 = a1 * a3, a14 = a1 * a4, a23 = a2 * a3, a24 = a2 * a4, a33 = a3 * a3;
+    out[0] = (0.5 * qv2) * a11 + c.l01 * a1 + qv2 * a2 + c.h0;
+    out[1] = qv * a11 + (2.0 * qv2) * a12 + c.l11 * a1 + c.l12 * a2 + (3.0 * qv2) * a3 + c.h1;
+    out[2] = (0.5 * v2) * a11 + (2.0 * qv2) * a22 + (4.0 * qv) * a12 + (3.0 * qv2) * a13 + c.l21 * a1 + c.l22 * a2 + c.l23 * a3 +
+             (6.0 * qv2) * a4 + c.h2;
+    out[3] = (4.0 * qv) * a22 + (2.0 * v2) * a12 + (6.0 * qv) * a13 + (4.0 * qv2) * a14 + (6.0 * qv2) * a23 + c.l32 * a2 +
+             c.l33 * a3 + c.l34 * a4;
+    out[4] = (2.0 * v2) * a22 + (4.5 * qv2) * a33 + (3.0 * v2) * a13 + (8.0 * qv) * a14 + (12.0 * qv) * a23 + (8.0 * qv2) * a24 +
+             c.l43 * a3 + c.l44 * a4;
+  } else {
+    out[0] = (0.5 * qv2) * a11 + c.l01 * a1 + qv2 * a2 + c.h0;
+    out[1] = qv * a11 + (2.0 * qv2) * a12 + c.l11 * a1 + c.l12 * a2 + c.h1;
+    out[2] = (0.5 * v2) * a11 + (2.0 * qv2) * a22 + (4.0 * qv) * a12 + c.l21 * a1 + c.l22 * a2 + c.h2;
+  }
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// SciPy RK45 clone (scipy/integrate/_ivp/rk.py:111-170 step loop, :14-69 stages, :538-552 tableau;
+//                   scipy/integrate/_ivp/common.py:63-65 norm, :109-134 select_initial_step)
+// --------------------------------------------------------------------------------------------------------------------
+constexpr double kRtol = 1e-3, kAtol = 1e-6;   // solve_ivp defaults, affine_expansion.py:300-301 passes none
+
+template <int N>
+__device__ __forceinline__ double rms_scaled(const cd (&v)[N], const double (&scale)[N]) {
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    const double re = v[k].re / scale[k], im = v[k].im / scale[k];
+    s += re * re + im * im;
+  }
+  return sqrt(s) / sqrt((double)N);
+}
+
+// returns 0 ok, 1 step size underflow (SciPy: TOO_SMALL_STEP -> solver fails, reference keeps the last accepted state)
+template <int N>
+__device__ int rk45(cd (&y)[N], double T, const LogsvModel& m, const Coef& c, int* nfev_out) {
+  constexpr double A21 = 1.0 / 5;
+  constexpr double A31 = 3.0 / 40, A32 = 9.0 / 40;
+  constexpr double A41 = 44.0 / 45, A42 = -56.0 / 15, A43 = 32.0 / 9;
+  constexpr double A51 = 19372.0 / 6561, A52 = -25360.0 / 2187, A53 = 64448.0 / 6561, A54 = -212.0 / 729;
+  constexpr double A61 = 9017.0 / 3168, A62 = -355.0 / 33, A63 = 46732.0 / 5247, A64 = 49.0 / 176, A65 = -5103.0 / 18656;
+  constexpr double B1 = 35.0 / 384, B3 = 500.0 / 1113, B4 = 125.0 / 192, B5 = -2187.0 / 6784, B6 = 11.0 / 84;
+  constexpr double E1 = -71.0 / 57600, E3 = 71.0 / 16695, E4 = -71.0 / 1920, E5 = 17253.0 / 339200, E6 = -22.0 / 525, E7 = 1.0 / 40;
+
+  cd f[N];
+  rhs<N>(y, m, c, f);
+  int nfev = 1;
+  double scale[N];
+  // ---- select_initial_step
+  double h_abs;
+  {
+#pragma unroll
+    for (int k = 0; k < N; ++k) scale[k] = kAtol + cabs_(y[k]) * kRtol;
+    const double d0 = rms_scaled<N>(y, scale), d1 = rms_scaled<N>(f, scale);
+    double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+    h0 = fmin(h0, T);
+    cd y1[N], f1[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) y1[k] = y[k] + h0 * f[k];
+    rhs<N>(y1, m, c, f1);
+    ++nfev;
+#pragma unroll
+    for (int k = 0; k < N; ++k) f1[k] = f1[k] - f[k];
+    const double d2 = rms_scaled<N>(f1, scale) / h0;
+    const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / fmax(d1, d2), 0.2);
+    h_abs = fmin(fmin(100.0 * h0, h1), T);
+  }
+  double t = 0.0;
+  int status = 0;
+  for (int guard = 0; t < T && guard < 100000; ++guard) {
+    const double min_step = 10.0 * (__longlong_as_double(__double_as_longlong(t) + 1) - t);   // 10*|nextafter(t, inf) - t|, t >= 0
+    if (h_abs < min_step) h_abs = min_step;           // max_step = inf
+    bool rejected = false;
+    for (;;) {
+      if (h_abs < min_step) {
+        status = 1;
+        break;
+      }
+      double t_new = t + h_abs;
+      if (t_new - T > 0.0) t_new = T;
+      const double h = t_new - t;
+      h_abs = fabs(h);
+      cd k2[N], k3[N], k4[N], k5[N], k6[N], k7[N], yt[N], yn[N];
+#pragma unroll
+      for (int k = 0; k < N; ++k) yt[k] = y[k] + (f[k] * A21) * h;
+      rhs<N>(yt, m, c, k2);
+#pragma unroll
+      for (int k = 0; k < N; ++k) yt[k] = y[k] + (f[k] * A31 + k2[k] * A32) * h;
+      rhs<N>(yt, m, c, k3);
+#pragma unroll
+      for (int k = 0; k < N; ++k) yt[k] = y[k] + (f[k] * A41 + k2[k] * A42 + k3[k] * A43) * h;
+      rhs<N>(yt, m, c, k4);
+#pragma unroll
+      for (int k = 0; k < N; ++k) yt[k] = y[k] + (f[k] * A51 + k2[k] * A52 + k3[k] * A53 + k4[k] * A54) * h;
+      rhs<N>(yt, m, c, k5);
+#pragma unroll
+      for (int k = 0; k < N; ++k) yt[k] = y[k] + (f[k] * A61 + k2[k] * A62 + k3[k] * A63 + k4[k] * A64 + k5[k] * A65) * h;
+      rhs<N>(yt, m, c, k6);
+#pragma unroll
+      for (int k = 0; k < N; ++k) yn[k] = y[k] + h * (f[k] * B1 + k3[k] * B3 + k4[k] * B4 + k5[k] * B5 + k6[k] * B6);
+      rhs<N>(yn, m, c, k7);
+      nfev += 6;
+      cd err[N];
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        scale[k] = kAtol + fmax(cabs_(y[k]), cabs_(yn[k])) * kRtol;
+        err[k] = (f[k] * E1 + k3[k] * E3 + k4[k] * E4 + k5[k] * E5 + k6[k] * E6 + k7[k] * E7) * h;
+      }
+      const double en = rms_scaled<N>(err, scale);
+      if (en < 1.0) {
+        double factor = en == 0.0 ? 10.0 : fmin(10.0, 0.9 * pow(en, -0.2));
+        if (rejected) factor = fmin(1.0, factor);
+        h_abs *= factor;
+        t = t_new;
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+          y[k] = yn[k];
+          f[k] = k7[k];     // FSAL
+        }
+        break;
+      }
+      h_abs *= fmax(0.2, 0.9 * pow(en, -0.2));
+      rejected = true;
+    }
+    if (status) break;
+  }
+  if (nfev_out) *nfev_out = nfev;
+  return status;
+}
+
+struct ChainSpec {   // per-maturity scalars (device array of M entries)
+  double dtau;
+  LogsvModel model;
+};
+
+// one thread = one grid point through all M maturities.  a_io: [P][N] in (A(0)) ; a_out: [M][P][N]; log_mgf: [M][P]
+template <int N>
+__global__ void logsv_mgf_kernel(const cd* __restrict__ phi, const cd* __restrict__ psi, int P, int M,
+                                 const ChainSpec* __restrict__ spec, const cd* __restrict__ a_in, cd* __restrict__ a_out,
+                                 cd* __restrict__ log_mgf, double y, int* __restrict__ status, int* __restrict__ nfev) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  cd A[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) A[k] = a_in ? a_in[(size_t)p * N + k] : mk(0.0);
+  const cd ph = phi[p], ps = psi ? psi[p] : mk(0.0);
+  // ys = [1, y, y^2, y^3, y^4] (affine_expansion.py:674-681)
+  const double y2 = y * y;
+  const double ys[5] = {1.0, y, y2, y2 * y, y2 * y2};
+  int st = 0, nf = 0;
+  for (int mm = 0; mm < M; ++mm) {
+    const LogsvModel model = spec[mm].model;
+    const Coef c = make_coef(model, ph, ps);
+    int nfe = 0;
+    st |= rk45<N>(A, spec[mm].dtau, model, c, &nfe);
+    nf += nfe;
+    cd lm = mk(0.0);
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      a_out[((size_t)mm * P + p) * N + k] = A[k];
+      lm = lm + A[k] * ys[k];
+    }
+    log_mgf[(size_t)mm * P + p] = lm;
+  }
+  if (status) status[p] = st;
+  if (nfev) nfev[p] = nf;
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// Heston closed form: pricers/heston_pricer.py:199-214, chained over maturities with (a, b) carried in registers
+// --------------------------------------------------------------------------------------------------------------------
+__global__ void heston_mgf_kernel(const cd* __restrict__ phi, const cd* __restrict__ psi, int P, int M,
+                                  const double* __restrict__ dtaus, b200sv_heston_params hp, const cd* __restrict__ a_in,
+                                  const cd* __restrict__ b_in, cd* __restrict__ a_out, cd* __restrict__ b_out,
+                                  cd* __restrict__ log_mgf) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const cd ph = phi[p], ps = psi ? psi[p] : mk(0.0);
+  cd a = a_in ? a_in[p] : mk(0.0), b = b_in ? b_in[p] : mk(0.0);
+  const double vv2 = hp.volvol * hp.volvol;
+  const cd b1 = mk(hp.kappa) + (hp.rho * hp.volvol) * ph;
+  const cd b0 = (0.5 * ph) * (ph + mk(1.0)) - ps;
+  const cd zeta = csqrt_(b1 * b1 - (2.0 * b0) * vv2);
+  const cd psi_p = zeta - b1, psi_m = b1 + zeta;
+  const cd two_zeta = 2.0 * zeta;
+  for (int mm = 0; mm < M; ++mm) {
+    const double tau = dtaus[mm];
+    const cd ez = cexp_(-(zeta * tau));
+    const cd c_p = (psi_p + vv2 * b) / two_zeta, c_m = (psi_m - vv2 * b) / two_zeta;
+    const cd den = c_p * ez + c_m;
+    const cd b_new = -((-(psi_m * c_p)) * ez + psi_p * c_m) / (vv2 * den);
+    const cd a_new = (-(hp.theta * hp.kappa / vv2)) * (psi_p * tau + 2.0 * clog_(den)) + a;
+    a = a_new;
+    b = b_new;
+    if (a_out) a_out[(size_t)mm * P + p] = a;
+    if (b_out) b_out[(size_t)mm * P + p] = b;
+    log_mgf[(size_t)mm * P + p] = a + b * hp.v0;
+  }
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// Fourier sums: utils/mgf_pricer.py:190-219.  One CTA per strike.
+// --------------------------------------------------------------------------------------------------------------------
+struct StrikeSpec {
+  double strike, forward, discfactor;
+  int type;     // B200SV_CALL ..
+  int slice;    // which log_mgf row
+};
+
+constexpr int kFourierThreads = 256;
+
+__global__ void __launch_bounds__(kFourierThreads) fourier_vanilla_kernel(const cd* __restrict__ log_mgf, const cd* __restrict__ phi,
+                                                                         int P, const StrikeSpec* __restrict__ specs,
+                                                                         int is_spot, int half_re, double* __restrict__ prices) {
+  __shared__ double red[kFourierThreads / 32];
+  const StrikeSpec sp = specs[blockIdx.x];
+  const cd* lm = log_mgf + (size_t)sp.slice * P;
+  const double x = log(sp.forward / sp.strike);
+  const double h3 = (phi[1].im - phi[0].im) / 3.0;
+  double acc[1] = {0.0};
+  for (int j = threadIdx.x; j < P; j += kFourierThreads) {
+    // legacy Simpson weights (utils/mgf_pricer.py:163-170): 1,4,2,4,... with first/last = 1 and THEN every odd index = 4
+    double wq = (j & 1) ? 4.0 : ((j == 0 || j == P - 1) ? 1.0 : 2.0);
+    const double dp = h3 * wq;
+    const cd ph = phi[j];
+    cd w;
+    if (half_re) {
+      w = mk((dp / M_PI) / (ph.im * ph.im + 0.25));
+    } else {
+      const cd den = is_spot ? (ph + mk(1.0)) * ph : (ph - mk(1.0)) * ph;
+      w = -(mk(dp / M_PI) / den);
+    }
+    const cd z = lm[j] - x * ph;
+    const cd term = w * cexp_(z);
+    if (term.re == term.re) acc[0] += term.re;     // np.nansum(np.real(...))
+  }
+  block_sum<1, kFourierThreads>(acc, red);
+  if (threadIdx.x == 0) {
+    const double capped = acc[0], F = sp.forward, K = sp.strike, df = sp.discfactor;
+    double price;
+    if (is_spot)
+      price = sp.type == B200SV_CALL ? df * (F - K * capped) : df * (K - K * capped);
+    else
+      price = (sp.type == B200SV_CALL || sp.type == B200SV_INV_CALL) ? F * df * (1.0 - capped) : F * df * (exp(-x) - capped);
+    prices[blockIdx.x] = price;
+  }
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// host side
+// --------------------------------------------------------------------------------------------------------------------
+static int launched(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(-2, std::string(what) + ": " + cudaGetErrorString(e));
+  b200sv_internal_count_launch();
+  return 0;
+}
+
+static int mgf_block_threads(int P) {
+  int t = 4;
+  while (t < 64 && t * 148 < P) t <<= 1;
+  return t;
+}
+
+// np.linspace(0, stop, P): y[i] = i*step, step = stop/(P-1), last = stop; phi = re + 1j*p (utils/mgf_pricer.py:22-33)
+static void build_phi(double vol_scaler, bool spot, int P, std::vector<double>& phi) {
+  phi.resize(2 * (size_t)P);
+  const double stop = 5.6 / vol_scaler, step = stop / (double)(P - 1);
+  for (int i = 0; i < P; ++i) {
+    phi[2 * i] = spot ? -0.5 : 0.5;
+    phi[2 * i + 1] = (double)i * step;
+  }
+  phi[2 * (size_t)(P - 1) + 1] = stop;
+}
+
+static int check_fourier_types(const int8_t* types, int n, bool spot) {
+  for (int j = 0; j < n; ++j) {
+    if (types[j] < 0 || types[j] > 3) return fail(-5, "not implemented");
+    // MMA measure rejects inverse payoffs (utils/mgf_pricer.py:206-212); the inverse measure accepts C == IC, P == IP (:214-217)
+    if (spot && types[j] >= 2) return fail(-5, "not implemented");
+  }
+  return 0;
+}
+
+static bool all_half_re(const double* phi, int P) {
+  for (int i = 0; i < P; ++i)
+    if (std::fabs(phi[2 * i]) != 0.5) return false;
+  return true;
+}
+
+struct DevBuf {   // RAII for stream-ordered temporaries
+  void* p = nullptr;
+  cudaStream_t st;
+  explicit DevBuf(cudaStream_t s) : st(s) {}
+  cudaError_t alloc(size_t n) { return cudaMallocAsync(&p, n ? n : 1, st); }
+  ~DevBuf() {
+    if (p) cudaFreeAsync(p, st);
+  }
+  template <typename T>
+  T* as() {
+    return (T*)p;
+  }
+};
+
+}  // namespace b200sv
+
+using namespace b200sv;
+
+extern "C" {
+
+int b200sv_logsv_price_chain(const b200sv_logsv_params* params, int M, const double* ttms, const double* forwards,
+                             const double* discfactors, const double* etas, const int* offsets, const double* strikes,
+                             const int8_t* types, int is_spot_measure, int expansion_order, double vol_scaler, int P,
+                             double* prices_out, double* a_out, double* log_mgf_out) {
+  B200SV_REQUIRE(params && ttms && forwards && discfactors && offsets && prices_out, "null pointer");
+  B200SV_REQUIRE(M >= 1 && P >= 3, "M >= 1, P >= 3");
+  if (expansion_order != B200SV_ORDER_FIRST && expansion_order != B200SV_ORDER_SECOND)
+    return fail(-4, "expansion_order not implemented");                    // affine_expansion.py:680-681
+  const bool spot = is_spot_measure != 0;
+  const int Jtot = offsets[M] - offsets[0];
+  if (int rc = check_fourier_types(types + offsets[0], Jtot, spot)) return rc;
+  double t0 = 0.0, tmin = ttms[0];
+  for (int m = 0; m < M; ++m) {
+    B200SV_REQUIRE(ttms[m] > t0, "ttms must be positive and strictly increasing");
+    t0 = ttms[m];
+    tmin = std::min(tmin, ttms[m]);
+  }
+  if (!(vol_scaler > 0.0)) vol_scaler = params->sigma0 * std::sqrt(std::min(tmin, 0.5 / 12.0));   // logsv_pricer.py:664-666
+  const int N = expansion_order == B200SV_ORDER_FIRST ? 3 : 5;
+  std::vector<double> phi;
+  build_phi(vol_scaler, spot, P, phi);
+  std::vector<ChainSpec> spec(M);
+  t0 = 0.0;
+  for (int m = 0; m < M; ++m) {
+    spec[m].dtau = ttms[m] - t0;
+    spec[m].model = make_model(*params, etas ? etas[m] : 1.0, spot);
+    t0 = ttms[m];
+  }
+  std::vector<StrikeSpec> ss(std::max(Jtot, 1));
+  for (int m = 0; m < M; ++m)
+    for (int j = offsets[m]; j < offsets[m + 1]; ++j) {
+      B200SV_REQUIRE(strikes[j] > 0.0, "strikes must be positive");
+      ss[j - offsets[0]] = StrikeSpec{strikes[j], forwards[m], discfactors[m], (int)types[j], m};
+    }
+  cudaStream_t st = 0;
+  DevBuf d_phi(st), d_spec(st), d_a(st), d_lm(st), d_ss(st), d_pr(st), d_stat(st);
+  B200SV_CUDA(d_phi.alloc(sizeof(cd) * P));
+  B200SV_CUDA(d_spec.alloc(sizeof(ChainSpec) * M));
+  B200SV_CUDA(d_a.alloc(sizeof(cd) * (size_t)M * P * N));
+  B200SV_CUDA(d_lm.alloc(sizeof(cd) * (size_t)M * P));
+  B200SV_CUDA(d_ss.alloc(sizeof(StrikeSpec) * ss.size()));
+  B200SV_CUDA(d_pr.alloc(sizeof(double) * ss.size()));
+  B200SV_CUDA(d_stat.alloc(sizeof(int) * P));
+  B200SV_CUDA(cudaMemcpyAsync(d_phi.p, phi.data(), sizeof(cd) * P, cudaMemcpyHostToDevice, st));
+  B200SV_CUDA(cudaMemcpyAsync(d_spec.p, spec.data(), sizeof(ChainSpec) * M, cudaMemcpyHostToDevice, st));
+  B200SV_CUDA(cudaMemcpyAsync(d_ss.p, ss.data(), sizeof(StrikeSpec) * ss.size(), cudaMemcpyHostToDevice, st));
+  const int tpb = mgf_block_threads(P), nb = (P + tpb - 1) / tpb;
+  const double y = params->sigma0 - params->theta;
+  if (N == 5)
+    logsv_mgf_kernel<5><<<nb, tpb, 0, st>>>(d_phi.as<cd>(), nullptr, P, M, d_spec.as<ChainSpec>(), nullptr, d_a.as<cd>(), d_lm.as<cd>(), y, d_stat.as<int>(), nullptr);
+  else
+    logsv_mgf_kernel<3><<<nb, tpb, 0, st>>>(d_phi.as<cd>(), nullptr, P, M, d_spec.as<ChainSpec>(), nullptr, d_a.as<cd>(), d_lm.as<cd>(), y, d_stat.as<int>(), nullptr);
+  if (int rc = launched("logsv_mgf_kernel")) return rc;
+  if (Jtot > 0) {
+    fourier_vanilla_kernel<<<Jtot, kFourierThreads, 0, st>>>(d_lm.as<cd>(), d_phi.as<cd>(), P, d_ss.as<StrikeSpec>(), spot ? 1 : 0, 1, d_pr.as<double>());
+    if (int rc = launched("fourier_vanilla_kernel")) return rc;
+    B200SV_CUDA(cudaMemcpyAsync(prices_out, d_pr.p, sizeof(double) * Jtot, cudaMemcpyDeviceToHost, st));
+  }
+  if (a_out) B200SV_CUDA(cudaMemcpyAsync(a_out, d_a.p, sizeof(cd) * (size_t)M * P * N, cudaMemcpyDeviceToHost, st));
+  if (log_mgf_out) B200SV_CUDA(cudaMemcpyAsync(log_mgf_out, d_lm.p, sizeof(cd) * (size_t)M * P, cudaMemcpyDeviceToHost, st));
+  B200SV_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int b200sv_heston_price_chain(const b200sv_heston_params* params, int M, const double* ttms, const double* forwards,
+                              const double* discfactors, const int* offsets, const double* strikes, const int8_t* types,
+                              double vol_scaler, int P, double* prices_out, double* log_mgf_out) {
+  B200SV_REQUIRE(params && ttms && forwards && discfactors && offsets && prices_out, "null pointer");
+  B200SV_REQUIRE(M >= 1 && P >= 3, "M >= 1, P >= 3");
+  const int Jtot = offsets[M] - offsets[0];
+  if (int rc = check_fourier_types(types + offsets[0], Jtot, true)) return rc;
+  if (!(vol_scaler > 0.0)) vol_scaler = std::min(0.3, std::sqrt(params->v0 * ttms[0]));   // heston_pricer.py:234-235
+  std::vector<double> phi;
+  build_phi(vol_scaler, true, P, phi);
+  std::vector<double> dtaus(M);
+  double t0 = 0.0;
+  for (int m = 0; m < M; ++m) {
+    B200SV_REQUIRE(ttms[m] > t0, "ttms must be positive and strictly increasing");
+    dtaus[m] = ttms[m] - t0;
+    t0 = ttms[m];
+  }
+  std::vector<StrikeSpec> ss(std::max(Jtot, 1));
+  for (int m = 0; m < M; ++m)
+    for (int j = offsets[m]; j < offsets[m + 1]; ++j) {
+      B200SV_REQUIRE(strikes[j] > 0.0, "strikes must be positive");
+      ss[j - offsets[0]] = StrikeSpec{strikes[j], forwards[m], discfactors[m], (int)types[j], m};
+    }
+  cudaStream_t st = 0;
+  DevBuf d_phi(st), d_dt(st), d_lm(st), d_ss(st), d_pr(st);
+  B200SV_CUDA(d_phi.alloc(sizeof(cd) * P));
+  B200SV_CUDA(d_dt.alloc(sizeof(double) * M));
+  B200SV_CUDA(d_lm.alloc(sizeof(cd) * (size_t)M * P));
+  B200SV_CUDA(d_ss.alloc(sizeof(StrikeSpec) * ss.size()));
+  B200SV_CUDA(d_pr.alloc(sizeof(double) * ss.size()));
+  B200SV_CUDA(cudaMemcpyAsync(d_phi.p, phi.data(), sizeof(cd) * P, cudaMemcpyHostToDevice, st));
+  B200SV_CUDA(cudaMemcpyAsync(d_dt.p, dtaus.data(), sizeof(double) * M, cudaMemcpyHostToDevice, st));
+  B200SV_CUDA(cudaMemcpyAsync(d_ss.p, ss.data(), sizeof(StrikeSpec) * ss.size(), cudaMemcpyHostToDevice, st));
+  const int tpb = mgf_block_threads(P), nb = (P + tpb - 1) / tpb;
+  heston_mgf_kernel<<<nb, tpb, 0, st>>>(d_phi.as<cd>(), nullptr, P, M, d_dt.as<double>(), *params, nullptr, nullptr, nullptr, nullptr, d_lm.as<cd>());
+  if (int rc = launched("heston_mgf_kernel")) return rc;
+  if (Jtot > 0) {
+    fourier_vanilla_kernel<<<Jtot, kFourierThreads, 0, st>>>(d_lm.as<cd>(), d_phi.as<cd>(), P, d_ss.as<StrikeSpec>(), 1, 1, d_pr.as<double>());
+    if (int rc = launched("fourier_vanilla_kernel")) return rc;
+    B200SV_CUDA(cudaMemcpyAsync(prices_out, d_pr.p, sizeof(double) * Jtot, cudaMemcpyDeviceToHost, st));
+  }
+  if (log_mgf_out) B200SV_CUDA(cudaMemcpyAsync(log_mgf_out, d_lm.p, sizeof(cd) * (size_t)M * P, cudaMemcpyDeviceToHost, st));
+  B200SV_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int b200sv_logsv_mgf_grid(const double* phi, const double* psi, int P, double dtau, double* a_inout,
+                          const b200sv_logsv_params* params, double eta, int is_spot_measure, int expansion_order,
+                          double* log_mgf_out) {
+  B200SV_REQUIRE(phi && a_inout && params && log_mgf_out, "null pointer");
+  B200SV_REQUIRE(P >= 1 && dtau > 0.0, "P >= 1, dtau > 0");
+  if (expansion_order != B200SV_ORDER_FIRST && expansion_order != B200SV_ORDER_SECOND)
+    return fail(-4, "expansion_order not implemented");
+  const int N = expansion_order == B200SV_ORDER_FIRST ? 3 : 5;
+  ChainSpec spec{dtau, make_model(*params, eta, is_spot_measure != 0)};
+  cudaStream_t st = 0;
+  DevBuf d_phi(st), d_psi(st), d_spec(st), d_a0(st), d_a1(st), d_lm(st);
+  B200SV_CUDA(d_phi.alloc(sizeof(cd) * P));
+  B200SV_CUDA(d_psi.alloc(sizeof(cd) * P));
+  B200SV_CUDA(d_spec.alloc(sizeof(ChainSpec)));
+  B200SV_CUDA(d_a0.alloc(sizeof(cd) * (size_t)P * N));
+  B200SV_CUDA(d_a1.alloc(sizeof(cd) * (size_t)P * N));
+  B200SV_CUDA(d_lm.alloc(sizeof(cd) * P));
+  B200SV_CUDA(cudaMemcpyAsync(d_phi.p, phi, sizeof(cd) * P, cudaMemcpyHostToDevice, st));
+  if (psi) B200SV_CUDA(cudaMemcpyAsync(d_psi.p, psi, sizeof(cd) * P, cudaMemcpyHostToDevice, st));
+  B200SV_CUDA(cudaMemcpyAsync(d_spec.p, &spec, sizeof(ChainSpec), cudaMemcpyHostToDevice, st));
+  B200SV_CUDA(cudaMemcpyAsync(d_a0.p, a_inout, sizeof(cd) * (size_t)P * N, cudaMemcpyHostToDevice, st));
+  const int tpb = mgf_block_threads(P), nb = (P + tpb - 1) / tpb;
+  const double y = params->sigma0 - params->theta;
+  const cd* dpsi = psi ? d_psi.as<cd>() : nullptr;
+  if (N == 5)
+    logsv_mgf_kernel<5><<<nb, tpb, 0, st>>>(d_phi.as<cd>(), dpsi, P, 1, d_spec.as<ChainSpec>(), d_a0.as<cd>(), d_a1.as<cd>(), d_lm.as<cd>(), y, nullptr, nullptr);
+  else
+    logsv_mgf_kernel<3><<<nb, tpb, 0, st>>>(d_phi.as<cd>(), dpsi, P, 1, d_spec.as<ChainSpec>(), d_a0.as<cd>(), d_a1.as<cd>(), d_lm.as<cd>(), y, nullptr, nullptr);
+  if (int rc = launched("logsv_mgf_kernel")) return rc;
+  B200SV_CUDA(cudaMemcpyAsync(a_inout, d_a1.p, sizeof(cd) * (size_t)P * N, cudaMemcpyDeviceToHost, st));
+  B200SV_CUDA(cudaMemcpyAsync(log_mgf_out, d_lm.p, sizeof(cd) * P, cudaMemcpyDeviceToHost, st));
+  B200SV_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int b200sv_heston_mgf_grid(const double* phi, const double* psi, int P, double dtau, double* a_inout, double* b_inout,
+                           const b200sv_heston_params* params, double* log_mgf_out) {
+  B200SV_REQUIRE(phi && a_inout && b_inout && params && log_mgf_out, "null pointer");
+  B200SV_REQUIRE(P >= 1 && dtau > 0.0, "P >= 1, dtau > 0");
+  cudaStream_t st = 0;
+  DevBuf d_phi(st), d_psi(st), d_dt(st), d_a(st), d_b(st), d_a1(st), d_b1(st), d_lm(st);
+  B200SV_CUDA(d_phi.alloc(sizeof(cd) * P));
+  B200SV_CUDA(d_psi.alloc(sizeof(cd) * P));
+  B200SV_CUDA(d_dt.alloc(sizeof(double)));
+  B200SV_CUDA(d_a.alloc(sizeof(cd) * P));
+  B200SV_CUDA(d_b.alloc(sizeof(cd) * P));
+  B200SV_CUDA(d_a1.alloc(sizeof(cd) * P));
+  B200SV_CUDA(d_b1.alloc(sizeof(cd) * P));
+  B200SV_CUDA(d_lm.alloc(sizeof(cd) * P));
+  B200SV_CUDA(cudaMemcpyAsync(d_phi.p, phi, sizeof(cd) * P, cudaMemcpyHostToDevice, st));
+  if (psi) B200SV_CUDA(cudaMemcpyAsync(d_psi.p, psi, sizeof(cd) * P, cudaMemcpyHostToDevice, st));
+  B200SV_CUDA(cudaMemcpyAsync(d_dt.p, &dtau, sizeof(double), cudaMemcpyHostToDevice, st));
+  B200SV_CUDA(cudaMemcpyAsync(d_a.p, a_inout, sizeof(cd) * P, cudaMemcpyHostToDevice, st));
+  B200SV_CUDA(cudaMemcpyAsync(d_b.p, b_inout, sizeof(cd) * P, cudaMemcpyHostToDevice, st));
+  const int tpb = mgf_block_threads(P), nb = (P + tpb - 1) / tpb;
+  heston_mgf_kernel<<<nb, tpb, 0, st>>>(d_phi.as<cd>(), psi ? d_psi.as<cd>() : nullptr, P, 1, d_dt.as<double>(), *params,
+                                        d_a.as<cd>(), d_b.as<cd>(), d_a1.as<cd>(), d_b1.as<cd>(), d_lm.as<cd>());
+  if (int rc = launched("heston_mgf_kernel")) return rc;
+  B200SV_CUDA(cudaMemcpyAsync(a_inout, d_a1.p, sizeof(cd) * P, cudaMemcpyDeviceToHost, st));
+  B200SV_CUDA(cudaMemcpyAsync(b_inout, d_b1.p, sizeof(cd) * P, cudaMemcpyDeviceToHost, st));
+  B200SV_CUDA(cudaMemcpyAsync(log_mgf_out, d_lm.p, sizeof(cd) * P, cudaMemcpyDeviceToHost, st));
+  B200SV_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int b200sv_fourier_vanilla(const double* log_mgf, const double* phi, int P, double forward, const double* strikes,
+                           const int8_t* types, int J, double discfactor, int is_spot_measure, double* prices_out) {
+  B200SV_REQUIRE(log_mgf && phi && strikes && types && prices_out, "null pointer");
+  B200SV_REQUIRE(P >= 3 && J >= 1, "P >= 3, J >= 1");
+  const bool spot = is_spot_measure != 0;
+  if (int rc = check_fourier_types(types, J, spot)) return rc;
+  std::vector<StrikeSpec> ss(J);
+  for (int j = 0; j < J; ++j) ss[j] = StrikeSpec{strikes[j], forward, discfactor, (int)types[j], 0};
+  cudaStream_t st = 0;
+  DevBuf d_phi(st), d_lm(st), d_ss(st), d_pr(st);
+  B200SV_CUDA(d_phi.alloc(sizeof(cd) * P));
+  B200SV_CUDA(d_lm.alloc(sizeof(cd) * P));
+  B200SV_CUDA(d_ss.alloc(sizeof(StrikeSpec) * J));
+  B200SV_CUDA(d_pr.alloc(sizeof(double) * J));
+  B200SV_CUDA(cudaMemcpyAsync(d_phi.p, phi, sizeof(cd) * P, cudaMemcpyHostToDevice, st));
+  B200SV_CUDA(cudaMemcpyAsync(d_lm.p, log_mgf, sizeof(cd) * P, cudaMemcpyHostToDevice, st));
+  B200SV_CUDA(cudaMemcpyAsync(d_ss.p, ss.data(), sizeof(StrikeSpec) * J, cudaMemcpyHostToDevice, st));
+  fourier_vanilla_kernel<<<J, kFourierThreads, 0, st>>>(d_lm.as<cd>(), d_phi.as<cd>(), P, d_ss.as<StrikeSpec>(), spot ? 1 : 0,
+                                                        all_half_re(phi, P) ? 1 : 0, d_pr.as<double>());
+  if (int rc = launched("fourier_vanilla_kernel")) return rc;
+  B200SV_CUDA(cudaMemcpyAsync(prices_out, d_pr.p, sizeof(double) * J, cudaMemcpyDeviceToHost, st));
+  B200SV_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,99 @@
+// philox.cuh -- counter-based RNG for the fused MC kernels: Philox4x32-10 (Salmon, Moraes, Dror, Shaw,
+// "Parallel random numbers: as easy as 1, 2, 3", SC'11) + Box-Muller.
+//
+// The reference draws from Numba's process-global MT19937 (logsv_pricer.py:1025-1026) and pins no stream
+// (SURVEY.md §8c), so the stream is this repo's to define.  It is defined ONCE here and restated in
+// oracle/mc.py::device_normals so the fused kernel can be checked path by path:
+//
+//   key     = (seed_lo, seed_hi)
+//   counter = (path_lo, path_hi, call, slice)       path = GLOBAL path id => results independent of the
+//                                                   GPU count / grid / block size
+//   gauss f64: call = step;      u1 = 2 - d(r0,r1) in (0,1], u2 = d(r2,r3) - 1 in [0,1),
+//                                d(hi,lo) = double with exponent 0x3FF and mantissa (hi>>12):lo
+//                                Z0 = R cos(2 pi u2), Z1 = R sin(2 pi u2), R = sqrt(-2 ln u1)
+//   gauss f32: call = step / 2;  even step uses (r0,r1), odd step (r2,r3);
+//                                u1 = fma(float(ra), 2^-32, 2^-33) in (0,1], angle = int32(rb) * pi * 2^-31
+//                                float Box-Muller through the SFU (lg2 / sin / cos approx), widened to Real
+#pragma once
+#include <cstdint>
+
+namespace b200sv {
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)M0 * c.x;   // IMAD.WIDE.U32
+    const uint64_t p1 = (uint64_t)M1 * c.z;
+    c = make_uint4((uint32_t)(p1 >> 32) ^ c.y ^ k.x, (uint32_t)p1, (uint32_t)(p0 >> 32) ^ c.w ^ k.y, (uint32_t)p0);
+    k.x += W0;
+    k.y += W1;
+  }
+  return c;
+}
+
+// ---- float Box-Muller on the SFU -------------------------------------------------------------------
+__device__ __forceinline__ void box_muller_f32(uint32_t ra, uint32_t rb, float& z0, float& z1) {
+  const float u1 = fmaf(__uint2float_rn(ra), 2.3283064365386963e-10f, 1.1641532182693481e-10f);  // (0, 1]
+  // R = sqrt(-2 ln u1) = sqrt(-2 ln2 * lg2(u1))
+  const float rad = sqrtf(-1.3862943611198906f * __log2f(u1));
+  const float ang = __int2float_rn((int32_t)rb) * 1.4629180792671596e-09f;                        // pi * 2^-31 => [-pi, pi]
+  float s, c;
+  __sincosf(ang, &s, &c);
+  z0 = rad * c;
+  z1 = rad * s;
+}
+
+// ---- double Box-Muller ------------------------------------------------------------------------------
+__device__ __forceinline__ double u52(uint32_t hi, uint32_t lo) {   // [1, 2)
+  return __hiloint2double((int)(0x3FF00000u | (hi >> 12)), (int)lo);
+}
+__device__ __forceinline__ void box_muller_f64(uint4 r, double& z0, double& z1) {
+  const double u1 = 2.0 - u52(r.x, r.y);   // (0, 1]
+  const double u2 = u52(r.z, r.w) - 1.0;   // [0, 1)
+  const double rad = sqrt(-2.0 * log(u1));
+  double s, c;
+  sincospi(2.0 * u2, &s, &c);
+  z0 = rad * c;
+  z1 = rad * s;
+}
+
+// Per-path generator that hands out one (Z0, Z1) pair per time step in the order defined above.
+template <typename Real, bool GAUSS64>
+struct StepNormals;
+
+template <typename Real>
+struct StepNormals<Real, true> {
+  uint2 key;
+  uint32_t plo, phi, slice;
+  __device__ __forceinline__ StepNormals(uint64_t seed, uint64_t path, uint32_t slice_)
+      : key(make_uint2((uint32_t)seed, (uint32_t)(seed >> 32))), plo((uint32_t)path), phi((uint32_t)(path >> 32)), slice(slice_) {}
+  // one step
+  __device__ __forceinline__ void get(uint32_t step, Real& z0, Real& z1) {
+    double a, b;
+    box_muller_f64(philox4x32_10(make_uint4(plo, phi, step, slice), key), a, b);
+    z0 = (Real)a;
+    z1 = (Real)b;
+  }
+};
+
+template <typename Real>
+struct StepNormals<Real, false> {
+  uint2 key;
+  uint32_t plo, phi, slice;
+  __device__ __forceinline__ StepNormals(uint64_t seed, uint64_t path, uint32_t slice_)
+      : key(make_uint2((uint32_t)seed, (uint32_t)(seed >> 32))), plo((uint32_t)path), phi((uint32_t)(path >> 32)), slice(slice_) {}
+  // two consecutive steps (2*call, 2*call+1) from one Philox call
+  __device__ __forceinline__ void get2(uint32_t call, Real& a0, Real& a1, Real& b0, Real& b1) {
+    const uint4 r = philox4x32_10(make_uint4(plo, phi, call, slice), key);
+    float x0, x1, y0, y1;
+    box_muller_f32(r.x, r.y, x0, x1);
+    box_muller_f32(r.z, r.w, y0, y1);
+    a0 = (Real)x0;
+    a1 = (Real)x1;
+    b0 = (Real)y0;
+    b1 = (Real)y1;
+  }
+};
+
+}  // namespace b200sv

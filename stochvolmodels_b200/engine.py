@@ -1,0 +1,229 @@
+"""numpy <-> C-ABI marshalling for the host-level entry points of libb200sv (include/b200sv.h).
+
+Thin by design: validation that the reference does in Python (exception classes, messages) lives here; all arithmetic is in
+the CUDA library.  No function in this module computes a price on the CPU.
+"""
+from __future__ import annotations
+
+import os
+from ctypes import byref
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _capi as C
+from .utils.config import VariableType
+
+
+def fresh_seed() -> int:
+    """explicit seeds replace the reference's process-global Numba RNG (utils/funcs.py:51-60); default = OS entropy."""
+    return int.from_bytes(os.urandom(8), "little")
+
+
+def mc_flags(precision: str = "fp64", gauss: str = "fp32") -> int:
+    """precision: 'fp64' (default) | 'fp32' state arithmetic; gauss: 'fp32' (default, SFU Box-Muller) | 'fp64'."""
+    if precision not in ("fp64", "fp32"):
+        raise ValueError("precision must be 'fp64' or 'fp32'")
+    if gauss not in ("fp32", "fp64"):
+        raise ValueError("gauss must be 'fp32' or 'fp64'")
+    return (C.STATE_F32 if precision == "fp32" else C.STATE_F64) | (C.GAUSS_F64 if gauss == "fp64" else C.GAUSS_F32)
+
+
+def variable_code(variable_type) -> int:
+    v = variable_type.value if isinstance(variable_type, VariableType) or hasattr(variable_type, "value") else int(variable_type)
+    if v not in (C.LOG_RETURN, C.Q_VAR):
+        raise NotImplementedError        # utils/mc_payoffs.py:69-70, pricers/logsv_pricer.py:733-734
+    return v
+
+
+def logsv_params_c(sigma0, theta, kappa1, kappa2, beta, volvol) -> C.LogsvParamsC:
+    return C.LogsvParamsC(float(sigma0), float(theta), float(kappa1), float(kappa2), float(beta), float(volvol))
+
+
+def heston_params_c(v0, theta, kappa, rho, volvol) -> C.HestonParamsC:
+    return C.HestonParamsC(float(v0), float(theta), float(kappa), float(rho), float(volvol))
+
+
+def _chain_arrays(ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms):
+    ttms, forwards, discfactors = C.f64(ttms), C.f64(forwards), C.f64(discfactors)
+    M = ttms.shape[0]
+    if not (forwards.shape[0] == discfactors.shape[0] == len(strikes_ttms) == len(optiontypes_ttms) == M):
+        raise ValueError("ttms, forwards, discfactors, strikes_ttms, and optiontypes_ttms must have the same length")
+    offsets, strikes, types = C.flatten_chain(strikes_ttms, optiontypes_ttms)
+    return M, ttms, forwards, discfactors, offsets, strikes, types
+
+
+# ---- Monte Carlo --------------------------------------------------------------------------------------------------------
+def logsv_mc_chain(params: C.LogsvParamsC, ttms, forwards, discfactors, etas, strikes_ttms, optiontypes_ttms, nb_path: int,
+                   nb_steps_per_year: int, is_spot_measure: bool, variable_type, seed: int, flags: int
+                   ) -> Tuple[List[np.ndarray], List[np.ndarray]]:
+    vt = variable_code(variable_type)
+    M, ttms, forwards, discfactors, offsets, strikes, types = _chain_arrays(ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms)
+    etas = C.f64(np.ones(M) if etas is None else etas)
+    prices, stds = np.empty(strikes.shape[0]), np.empty(strikes.shape[0])
+    C.call("b200sv_logsv_mc_chain", byref(params), M, C.dptr(ttms), C.dptr(forwards), C.dptr(discfactors), C.dptr(etas),
+           C.iptr(offsets), C.dptr(strikes), C.i8ptr(types), int(nb_path), int(nb_steps_per_year), int(bool(is_spot_measure)), vt,
+           int(seed) & 0xFFFFFFFFFFFFFFFF, int(flags), C.dptr(prices), C.dptr(stds))
+    return C.split_chain(prices, offsets), C.split_chain(stds, offsets)
+
+
+def heston_mc_chain(params: C.HestonParamsC, ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms, nb_path: int,
+                    nb_steps_per_year: int, variable_type, seed: int, flags: int, scheme: int = C.HESTON_EULER_FLOOR
+                    ) -> Tuple[List[np.ndarray], List[np.ndarray]]:
+    vt = variable_code(variable_type)
+    M, ttms, forwards, discfactors, offsets, strikes, types = _chain_arrays(ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms)
+    prices, stds = np.empty(strikes.shape[0]), np.empty(strikes.shape[0])
+    C.call("b200sv_heston_mc_chain", byref(params), M, C.dptr(ttms), C.dptr(forwards), C.dptr(discfactors), C.iptr(offsets),
+           C.dptr(strikes), C.i8ptr(types), int(nb_path), int(nb_steps_per_year), vt, int(seed) & 0xFFFFFFFFFFFFFFFF, int(flags),
+           int(scheme), C.dptr(prices), C.dptr(stds))
+    return C.split_chain(prices, offsets), C.split_chain(stds, offsets)
+
+
+def logsv_terminal(params: C.LogsvParamsC, ttm: float, nb_path: int, nb_steps_per_year: int, is_spot_measure: bool, eta: float,
+                   seed: int, flags: int):
+    x, s, q = np.empty(nb_path), np.empty(nb_path), np.empty(nb_path)
+    C.call("b200sv_logsv_terminal", byref(params), float(ttm), int(nb_path), int(nb_steps_per_year), int(bool(is_spot_measure)),
+           float(eta), int(seed) & 0xFFFFFFFFFFFFFFFF, int(flags), C.dptr(x), C.dptr(s), C.dptr(q))
+    return x, s, q
+
+
+def heston_terminal(params: C.HestonParamsC, ttm: float, nb_path: int, nb_steps_per_year: int, seed: int, flags: int,
+                    scheme: int = C.HESTON_EULER_FLOOR):
+    x, v, q = np.empty(nb_path), np.empty(nb_path), np.empty(nb_path)
+    C.call("b200sv_heston_terminal", byref(params), float(ttm), int(nb_path), int(nb_steps_per_year),
+           int(seed) & 0xFFFFFFFFFFFFFFFF, int(flags), int(scheme), C.dptr(x), C.dptr(v), C.dptr(q))
+    return x, v, q
+
+
+def _fixed_inputs(x0, v0, q0, W0, W1):
+    """length-1 initial values broadcast like pricers/logsv_pricer.py:1007-1020 (x0 -> zeros, qvar0 -> zeros, sigma0 -> const)."""
+    W0, W1 = C.f64(W0), C.f64(W1)
+    if W0.ndim != 2 or W0.shape != W1.shape:
+        raise ValueError("W0 and W1 must be 2-d arrays [nb_steps, nb_path] of the same shape")
+    S, N = W0.shape
+
+    def bcast(a, kind):
+        a = np.atleast_1d(np.asarray(a, dtype=np.float64))
+        if a.shape[0] == 1:
+            return np.full(N, a[0]) if kind == "v" else np.zeros(N)
+        assert a.shape[0] == N
+        return np.array(a, dtype=np.float64, copy=True)
+
+    return bcast(x0, "x"), bcast(v0, "v"), bcast(q0, "q"), W0, W1, S, N
+
+
+def logsv_step_fixed(x0, sigma0, qvar0, W0, W1, dt: float, params: C.LogsvParamsC, eta: float, is_spot_measure: bool):
+    x, s, q, W0, W1, S, N = _fixed_inputs(x0, sigma0, qvar0, W0, W1)
+    C.call("b200sv_logsv_step_fixed", C.dptr(x), C.dptr(s), C.dptr(q), C.dptr(W0), C.dptr(W1), S, N, float(dt), byref(params),
+           float(eta), int(bool(is_spot_measure)))
+    return x, s, q
+
+
+def heston_step_fixed(x0, var0, qvar0, W0, W1, dt: float, params: C.HestonParamsC):
+    x, v, q, W0, W1, S, N = _fixed_inputs(x0, var0, qvar0, W0, W1)
+    C.call("b200sv_heston_step_fixed", C.dptr(x), C.dptr(v), C.dptr(q), C.dptr(W0), C.dptr(W1), S, N, float(dt), byref(params))
+    return x, v, q
+
+
+def mc_payoffs(x, qvar, ttm, forward, strikes, optiontypes, discfactor=1.0, variable_type=VariableType.LOG_RETURN):
+    vt = variable_code(variable_type)
+    x = C.f64(x)
+    q = C.f64(qvar) if qvar is not None else None
+    strikes = C.f64(strikes)
+    types = C.encode_types(optiontypes)
+    J = strikes.shape[0]
+    prices, stds = np.empty(J), np.empty(J)
+    C.call("b200sv_mc_payoffs", C.dptr(x), C.dptr(q), x.shape[0], float(ttm), float(forward), C.dptr(strikes), C.i8ptr(types), J,
+           float(discfactor), vt, C.dptr(prices), C.dptr(stds))
+    return prices, stds
+
+
+def device_normals(seed: int, path0: int, n: int, slice_idx: int, nsteps: int, flags: int):
+    z0, z1 = np.empty((nsteps, n)), np.empty((nsteps, n))
+    C.call("b200sv_device_normals", int(seed) & 0xFFFFFFFFFFFFFFFF, int(path0), int(n), int(slice_idx), int(nsteps), int(flags),
+           C.dptr(z0), C.dptr(z1))
+    return z0, z1
+
+
+def debug_exp_pair(L):
+    L = C.f64(L)
+    out = np.empty(2 * L.shape[0])
+    C.call("b200sv_debug_exp_pair", C.dptr(L), L.shape[0], C.dptr(out))
+    return out[0::2].copy(), out[1::2].copy()
+
+
+# ---- Fourier / MGF --------------------------------------------------------------------------------------------------------
+def _check_fourier_types(optiontypes_ttms, is_spot_measure: bool):
+    for types in optiontypes_ttms:
+        for t in types:
+            t = str(t)
+            if t not in C.TYPE_CODES or (is_spot_measure and t in ("IC", "IP")):
+                raise ValueError("not implemented")       # utils/mgf_pricer.py:206-219
+
+
+def logsv_price_chain(params: C.LogsvParamsC, ttms, forwards, discfactors, etas, strikes_ttms, optiontypes_ttms,
+                      is_spot_measure: bool = True, expansion_order: int = C.ORDER_SECOND, vol_scaler: Optional[float] = None,
+                      max_phi: int = 1000, return_grids: bool = False):
+    _check_fourier_types(optiontypes_ttms, is_spot_measure)
+    M, ttms, forwards, discfactors, offsets, strikes, types = _chain_arrays(ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms)
+    etas = C.f64(np.ones(M) if etas is None else etas)
+    n = 3 if expansion_order == C.ORDER_FIRST else 5
+    prices = np.empty(strikes.shape[0])
+    a_out = np.empty((M, max_phi, n), dtype=np.complex128) if return_grids else None
+    lm_out = np.empty((M, max_phi), dtype=np.complex128) if return_grids else None
+    C.call("b200sv_logsv_price_chain", byref(params), M, C.dptr(ttms), C.dptr(forwards), C.dptr(discfactors), C.dptr(etas),
+           C.iptr(offsets), C.dptr(strikes), C.i8ptr(types), int(bool(is_spot_measure)), int(expansion_order),
+           float(vol_scaler) if vol_scaler is not None else -1.0, int(max_phi), C.dptr(prices),
+           a_out.ctypes.data_as(C._dp) if return_grids else None, lm_out.ctypes.data_as(C._dp) if return_grids else None)
+    out = C.split_chain(prices, offsets)
+    return (out, a_out, lm_out) if return_grids else out
+
+
+def heston_price_chain(params: C.HestonParamsC, ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms,
+                       vol_scaler: Optional[float] = None, max_phi: int = 1000, return_grids: bool = False):
+    _check_fourier_types(optiontypes_ttms, True)
+    M, ttms, forwards, discfactors, offsets, strikes, types = _chain_arrays(ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms)
+    prices = np.empty(strikes.shape[0])
+    lm_out = np.empty((M, max_phi), dtype=np.complex128) if return_grids else None
+    C.call("b200sv_heston_price_chain", byref(params), M, C.dptr(ttms), C.dptr(forwards), C.dptr(discfactors), C.iptr(offsets),
+           C.dptr(strikes), C.i8ptr(types), float(vol_scaler) if vol_scaler is not None else -1.0, int(max_phi), C.dptr(prices),
+           lm_out.ctypes.data_as(C._dp) if return_grids else None)
+    out = C.split_chain(prices, offsets)
+    return (out, lm_out) if return_grids else out
+
+
+def logsv_mgf_grid(phi, psi, dtau: float, a_t0, params: C.LogsvParamsC, eta: float, is_spot_measure: bool, expansion_order: int):
+    phi = C.c128(phi)
+    psi = C.c128(psi) if psi is not None else None
+    P = phi.shape[0]
+    n = 3 if expansion_order == C.ORDER_FIRST else 5
+    a = np.array(C.c128(a_t0), copy=True)
+    if a.shape != (P, n):
+        raise ValueError(f"a_t0 must have shape ({P}, {n})")
+    lm = np.empty(P, dtype=np.complex128)
+    C.call("b200sv_logsv_mgf_grid", phi.ctypes.data_as(C._dp), psi.ctypes.data_as(C._dp) if psi is not None else None, P, float(dtau),
+           a.ctypes.data_as(C._dp), byref(params), float(eta), int(bool(is_spot_measure)), int(expansion_order), lm.ctypes.data_as(C._dp))
+    return a, lm
+
+
+def heston_mgf_grid(phi, psi, dtau: float, a_t0, b_t0, params: C.HestonParamsC):
+    phi = C.c128(phi)
+    psi = C.c128(psi) if psi is not None else None
+    P = phi.shape[0]
+    a = np.array(C.c128(a_t0), copy=True) if a_t0 is not None else np.zeros(P, dtype=np.complex128)
+    b = np.array(C.c128(b_t0), copy=True) if b_t0 is not None else np.zeros(P, dtype=np.complex128)
+    lm = np.empty(P, dtype=np.complex128)
+    C.call("b200sv_heston_mgf_grid", phi.ctypes.data_as(C._dp), psi.ctypes.data_as(C._dp) if psi is not None else None, P, float(dtau),
+           a.ctypes.data_as(C._dp), b.ctypes.data_as(C._dp), byref(params), lm.ctypes.data_as(C._dp))
+    return lm, a, b
+
+
+def fourier_vanilla(log_mgf, phi, forward, strikes, optiontypes, discfactor=1.0, is_spot_measure=True):
+    _check_fourier_types([optiontypes], is_spot_measure)
+    log_mgf, phi, strikes = C.c128(log_mgf), C.c128(phi), C.f64(strikes)
+    types = C.encode_types(optiontypes)
+    J = strikes.shape[0]
+    prices = np.empty(J)
+    C.call("b200sv_fourier_vanilla", log_mgf.ctypes.data_as(C._dp), phi.ctypes.data_as(C._dp), phi.shape[0], float(forward),
+           C.dptr(strikes), C.i8ptr(types), J, float(discfactor), int(bool(is_spot_measure)), C.dptr(prices))
+    return prices

@@ -1,0 +1,142 @@
+"""Multi-GPU Monte Carlo: one process per GPU (torchrun), paths sharded by contiguous GLOBAL path-id ranges.
+
+The path shards naturally: state never leaves its GPU; per maturity there are exactly two exchange steps,
+both tiny all-reduces of fp64 moments:
+    (1) [sum F*exp(x), count]               -> forward re-centring  (utils/mc_payoffs.py:61-63)
+    (2) [sum pay, sum pay^2, count] x J     -> prices / standard errors (:85-88)
+torch is plumbing only: device memory (``torch.empty``), the current CUDA stream, and ``torch.distributed`` (NCCL over
+NVLink on GPUs, gloo in the CPU tests).  All arithmetic is in libb200sv kernels, called through the device-level C ABI
+(``b200sv_dev_*``) with raw pointers.  Because the Philox counter is the global path id, prices do not depend on the number of
+GPUs beyond fp64 summation order.
+"""
+from __future__ import annotations
+
+from ctypes import byref, c_void_p
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _capi as C
+from .utils.funcs import set_time_grid
+
+
+def shard_paths(nb_path: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """(n_local, path_offset) of ``rank``: contiguous ranges, remainder spread over the first ranks."""
+    base, rem = divmod(int(nb_path), int(world_size))
+    n_local = base + (1 if rank < rem else 0)
+    offset = rank * base + min(rank, rem)
+    return n_local, offset
+
+
+class CudaMcEngine:
+    """Device-resident MC state + kernel launches on the current CUDA device (used for N>=1 ranks and by bench.py)."""
+
+    def __init__(self, model: str, params_c, n_local: int, path_offset: int, flags: int, max_strikes: int, device=None):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("CudaMcEngine needs a CUDA device; stochvolmodels_b200 has no CPU fallback")
+        C.load_library()
+        self.torch = torch
+        self.model = model
+        self.params_c = params_c
+        self.n_local, self.path_offset, self.flags = int(n_local), int(path_offset), int(flags)
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        sdtype = torch.float32 if (flags & C.STATE_F32) else torch.float64
+        self.state = torch.empty((3, max(self.n_local, 1)), dtype=sdtype, device=self.device)
+        self.moments = torch.zeros(2, dtype=torch.float64, device=self.device)
+        self.sums = torch.zeros(3 * max(max_strikes, 1), dtype=torch.float64, device=self.device)
+        self.out = torch.zeros(2 * max(max_strikes, 1), dtype=torch.float64, device=self.device)
+        self.cap = max(max_strikes, 1)
+
+    def _stream(self):
+        return c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def to_device(self, array: np.ndarray, dtype):
+        return self.torch.as_tensor(np.ascontiguousarray(array), dtype=dtype).to(self.device, non_blocking=False)
+
+    def simulate_slice(self, m: int, init: bool, nsteps: int, dt: float, eta: float, is_spot: bool, forward: float, seed: int):
+        """advance local paths through maturity slice m; leaves the LOCAL (sum F e^x, count) in ``self.moments``."""
+        x, v, q = (c_void_p(self.state[i].data_ptr()) for i in range(3))
+        if self.n_local == 0:
+            self.moments.zero_()
+            return self.moments
+        if self.model == "logsv":
+            C.call("b200sv_dev_logsv_slice", x, v, q, self.n_local, self.path_offset, int(init), byref(self.params_c), float(eta),
+                   int(bool(is_spot)), int(nsteps), float(dt), int(m), float(forward), int(seed) & 0xFFFFFFFFFFFFFFFF, self.flags,
+                   c_void_p(self.moments.data_ptr()), self._stream())
+        else:
+            C.call("b200sv_dev_heston_slice", x, v, q, self.n_local, self.path_offset, int(init), byref(self.params_c), int(nsteps),
+                   float(dt), int(m), float(forward), int(seed) & 0xFFFFFFFFFFFFFFFF, self.flags, C.HESTON_EULER_FLOOR,
+                   c_void_p(self.moments.data_ptr()), self._stream())
+        return self.moments
+
+    def payoff_sums(self, ttm: float, forward: float, strikes_dev, types_dev, J: int, variable_type: int):
+        """LOCAL per-strike (sum, sum^2, count) given the GLOBAL moments in ``self.moments``; returns a view of 3*J doubles."""
+        sums = self.sums[: 3 * J]
+        if self.n_local == 0:
+            sums.zero_()
+            return sums
+        C.call("b200sv_dev_payoff_sums", c_void_p(self.state[0].data_ptr()), c_void_p(self.state[2].data_ptr()), self.n_local,
+               self.flags, float(ttm), float(forward), c_void_p(strikes_dev.data_ptr()), c_void_p(types_dev.data_ptr()), int(J),
+               int(variable_type), c_void_p(self.moments.data_ptr()), c_void_p(sums.data_ptr()), self._stream())
+        return sums
+
+    def finalize(self, sums, J: int, discfactor: float, total_paths: int):
+        """GLOBAL sums -> (prices, std errors) device views of J doubles each."""
+        prices, stds = self.out[:J], self.out[self.cap: self.cap + J]
+        C.call("b200sv_dev_payoff_finalize", c_void_p(sums.data_ptr()), int(J), float(discfactor), int(total_paths),
+               c_void_p(prices.data_ptr()), c_void_p(stds.data_ptr()), self._stream())
+        return prices, stds
+
+
+def mc_chain_distributed(model: str, params_c, ttms, forwards, discfactors, etas, strikes_ttms, optiontypes_ttms, nb_path: int,
+                         nb_steps_per_year: int, is_spot_measure: bool, variable_type: int, seed: int, flags: int,
+                         group=None, engine_factory: Optional[Callable] = None, return_engine: bool = False):
+    """Chain MC with ``nb_path`` TOTAL paths split over the ranks of ``group`` (default: the world; works unsharded when
+    torch.distributed is not initialised).  Every rank returns the same (prices, std errors) lists.
+
+    Mirrors the slice loop of logsv_mc_chain_pricer / heston_mc_chain_pricer (pricers/logsv_pricer.py:840-865,
+    pricers/heston_pricer.py:304-329): the terminal state of slice m seeds slice m+1.
+    """
+    import torch
+    import torch.distributed as dist
+    distributed = dist.is_available() and dist.is_initialized()
+    world = dist.get_world_size(group) if distributed else 1
+    rank = dist.get_rank(group) if distributed else 0
+    n_local, offset = shard_paths(nb_path, world, rank)
+    ttms = np.asarray(ttms, dtype=np.float64)
+    M = ttms.shape[0]
+    offsets, strikes, types = C.flatten_chain(strikes_ttms, optiontypes_ttms)
+    sizes = np.diff(offsets)
+    Jmax = int(sizes.max()) if M else 0
+    factory = engine_factory or CudaMcEngine
+    eng = factory(model, params_c, n_local, offset, flags, Jmax)
+    strikes_dev = eng.to_device(strikes, torch.float64)
+    types_dev = eng.to_device(types, torch.int8)
+    etas = np.ones(M) if etas is None else np.asarray(etas, dtype=np.float64)
+    results = []
+    t0 = 0.0
+    for m in range(M):
+        nsteps, dt, _ = set_time_grid(ttms[m] - t0, nb_steps_per_year)
+        t0 = ttms[m]
+        moments = eng.simulate_slice(m, m == 0, nsteps, dt, float(etas[m]), is_spot_measure, float(forwards[m]), seed)
+        if world > 1:
+            dist.all_reduce(moments, op=dist.ReduceOp.SUM, group=group)              # exchange (1): 16 bytes
+        J = int(sizes[m])
+        if J == 0:
+            results.append((None, None))
+            continue
+        jo = int(offsets[m])
+        sums = eng.payoff_sums(float(ttms[m]), float(forwards[m]), strikes_dev[jo: jo + J], types_dev[jo: jo + J], J, variable_type)
+        if world > 1:
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)                 # exchange (2): 24*J bytes
+        prices, stds = eng.finalize(sums, J, float(discfactors[m]), int(nb_path))
+        results.append((prices.clone(), stds.clone()))
+    prices_out: List[np.ndarray] = []
+    stds_out: List[np.ndarray] = []
+    for p, s in results:
+        prices_out.append(p.cpu().numpy() if p is not None else np.zeros(0))
+        stds_out.append(s.cpu().numpy() if s is not None else np.zeros(0))
+    if return_engine:
+        return prices_out, stds_out, eng
+    return prices_out, stds_out

@@ -1,0 +1,50 @@
+"""Affine-expansion log-MGF grid on the GPU: reference pricers/logsv/affine_expansion.py (default RK45 branch)."""
+from __future__ import annotations
+
+from enum import Enum
+from typing import Optional, Tuple
+
+import numpy as np
+
+from ... import engine
+from ... import _capi as C
+from ...utils.config import VariableType
+
+
+class ExpansionOrder(Enum):
+    """truncation order (affine_expansion.py:43-54)."""
+    ZERO = 0
+    FIRST = 1
+    SECOND = 2
+
+
+def get_expansion_n(expansion_order: ExpansionOrder = ExpansionOrder.FIRST) -> int:
+    return 3 if expansion_order == ExpansionOrder.FIRST else 5
+
+
+def _order_code(expansion_order) -> int:
+    v = expansion_order.value if hasattr(expansion_order, "value") else int(expansion_order)
+    if v not in (1, 2):
+        raise NotImplementedError           # affine_expansion.py:680-681
+    return v
+
+
+def compute_logsv_a_mgf_grid(ttm: float, phi_grid: np.ndarray, psi_grid: np.ndarray, theta_grid: np.ndarray, sigma0: float,
+                             theta: float, kappa1: float, kappa2: float, beta: float, volvol: float,
+                             variable_type: VariableType = VariableType.LOG_RETURN,
+                             expansion_order: ExpansionOrder = ExpansionOrder.SECOND, a_t0: Optional[np.ndarray] = None,
+                             is_stiff_solver: bool = False, is_analytic: bool = False, is_spot_measure: bool = True,
+                             vol_backbone_eta: float = 1.0, **kwargs) -> Tuple[np.ndarray, np.ndarray]:
+    """(a_t1, log_mgf) over the transform grid, one RK45 (SciPy control law) ODE solve per grid point on the GPU
+    (affine_expansion.py:570-685 -> :492-529).  The BDF (``is_stiff_solver``) and semi-analytic (``is_analytic``) branches are
+    not the default path and are not rebuilt."""
+    if is_stiff_solver or is_analytic:
+        raise NotImplementedError("only the default RK45 branch is implemented on the GPU")
+    order = _order_code(expansion_order)
+    n = get_expansion_n(ExpansionOrder(order))
+    if a_t0 is None:
+        a_t0 = np.zeros((phi_grid.shape[0], n), dtype=np.complex128)
+        if variable_type == VariableType.SIGMA:
+            a_t0[:, 1] = -theta_grid      # affine_expansion.py:562-564
+    params = engine.logsv_params_c(sigma0, theta, kappa1, kappa2, beta, volvol)
+    return engine.logsv_mgf_grid(phi_grid, psi_grid, ttm, a_t0, params, vol_backbone_eta, is_spot_measure, order)

@@ -1,0 +1,247 @@
+"""LogSVPricer on B200: drop-in for the two hot paths of the reference ``pricers/logsv_pricer.py``.
+
+Same public names, argument meaning, defaults, return shapes and exception classes as the reference:
+
+* ``LogSVPricer.price_chain``                 (logsv_pricer.py:345-366)  -> ``logsv_chain_pricer`` (:669-739)
+* ``LogSVPricer.model_mc_price_chain``        (:369-427)                -> ``logsv_mc_chain_pricer`` (:806-867)
+* ``LogSVPricer.simulate_terminal_values``    (:590-611)                -> ``simulate_logsv_x_vol_terminal`` (:950-1047)
+* ``logsv_mc_chain_pricer_fixed_randoms``     (:1100-1162), ``get_randoms_for_chain_valuation`` (:1051-1074)
+* inherited ``compute_chain_prices_with_vols`` / ``price_slice`` / ``price_vanilla`` / ``compute_mc_chain_implied_vols``
+
+Extra OPTIONAL kwargs (all default to reference behaviour where one exists): ``seed`` (the reference draws from Numba's global
+RNG and exposes no seed; default = OS entropy), ``precision`` ('fp64' | 'fp32'), ``gauss`` ('fp32' | 'fp64'), ``distributed``
+(shard ``nb_path`` over the ranks of an initialised ``torch.distributed`` world; default True when one exists).
+Unknown kwargs are accepted and ignored on both routes, as in the reference (:349, :376, :681).
+
+Calibration (:105-333, :441-558) and the rough-vol route (:1164-1232) are callers / neighbours of the hot path and out of scope.
+"""
+from __future__ import annotations
+
+from dataclasses import asdict, dataclass
+from typing import Any, Dict, List, Optional, Tuple
+
+import numpy as np
+
+from .. import _capi as C
+from .. import engine
+from ..data.option_chain import OptionChain
+from ..utils.config import VariableType
+from ..utils.funcs import set_time_grid, timer
+from .logsv.affine_expansion import ExpansionOrder, _order_code
+from .model_pricer import ModelParams, ModelPricer
+
+
+@dataclass
+class LogSvParams(ModelParams):
+    """the six parameters of the log-normal SV model with quadratic drift (reference pricers/logsv/logsv_params.py:35-83),
+    plus the optional ``vol_backbone`` term structure (a pandas Series of eta indexed by maturity)."""
+    sigma0: float = 0.2
+    theta: float = 0.2
+    kappa1: float = 1.0
+    kappa2: Optional[float] = 2.5
+    beta: float = -1.0
+    volvol: float = 1.0
+    vol_backbone: Any = None
+
+    def __post_init__(self):
+        if self.kappa2 is None:              # logsv_params.py:92-93
+            self.kappa2 = self.kappa1 / self.theta
+
+    def to_dict(self) -> Dict[str, Any]:
+        return asdict(self)
+
+    def to_str(self) -> str:
+        return (f"sigma0={self.sigma0:0.2f}, theta={self.theta:0.2f}, kappa1={self.kappa1:0.2f}, kappa2={self.kappa2:0.2f}, "
+                f"beta={self.beta:0.2f}, volvol={self.volvol:0.2f}")
+
+    def set_vol_backbone(self, vol_backbone) -> None:
+        self.vol_backbone = vol_backbone
+
+    def get_vol_backbone_eta(self, tau: float) -> float:
+        """eta at the nearest quoted maturity at or beyond tau; 1.0 without a backbone (logsv_params.py:140-151)."""
+        if self.vol_backbone is None:
+            return 1.0
+        index = np.asarray(self.vol_backbone.index, dtype=float)
+        return float(np.asarray(self.vol_backbone)[np.searchsorted(index, tau, side="left")])
+
+    def get_vol_backbone_etas(self, ttms: np.ndarray) -> np.ndarray:
+        return np.array([self.get_vol_backbone_eta(tau) for tau in ttms], dtype=float)
+
+    @property
+    def kappa(self) -> float:
+        return self.kappa1 + self.kappa2 * self.theta
+
+    @property
+    def theta2(self) -> float:
+        return self.theta * self.theta
+
+    @property
+    def vartheta2(self) -> float:
+        return self.beta * self.beta + self.volvol * self.volvol
+
+
+LOGSV_BTC_PARAMS = LogSvParams(sigma0=0.8376, theta=1.0413, kappa1=3.1844, kappa2=3.058, beta=0.1514, volvol=1.8458)   # logsv_pricer.py:102
+
+
+def _params_c(params) -> C.LogsvParamsC:
+    kappa2 = params.kappa2 if params.kappa2 is not None else params.kappa1 / params.theta
+    return engine.logsv_params_c(params.sigma0, params.theta, params.kappa1, kappa2, params.beta, params.volvol)
+
+
+def _use_distributed(kwargs) -> bool:
+    if not kwargs.get("distributed", True):
+        return False
+    try:
+        import torch.distributed as dist
+    except Exception:       # torch absent: single-process only
+        return False
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+class LogSVPricer(ModelPricer):
+    """ModelPricer for the log-normal SV model, Fourier + Monte Carlo routes on the GPU."""
+
+    def price_chain(self, option_chain: OptionChain, params: LogSvParams, is_spot_measure: bool = True, **kwargs) -> List[np.ndarray]:
+        """Fourier prices of the chain (MMA measure Eqs. (5.4)/(5.9); inverse measure (5.13)/(5.16))."""
+        kwargs.pop("vol_backbone_etas", None)
+        return logsv_chain_pricer(params=params, ttms=option_chain.ttms, forwards=option_chain.forwards,
+                                  discfactors=option_chain.discfactors, strikes_ttms=option_chain.strikes_ttms,
+                                  optiontypes_ttms=option_chain.optiontypes_ttms, is_spot_measure=is_spot_measure, **kwargs)
+
+    @timer
+    def model_mc_price_chain(self, option_chain: OptionChain, params: LogSvParams, is_spot_measure: bool = True,
+                             variable_type: VariableType = VariableType.LOG_RETURN, nb_path: int = 100000,
+                             nb_steps: Optional[int] = None, **kwargs) -> Tuple[List[np.ndarray], List[np.ndarray]]:
+        """MC prices and standard errors, one array per maturity.  ``nb_steps`` is a PER-YEAR rate whose default is
+        ``int(360*max(ttms)) + 1`` (reference quirk, logsv_pricer.py:427)."""
+        if kwargs.get("use_rough_mc"):
+            raise NotImplementedError("rough-vol MC is outside the B200 hot path (SURVEY.md §2 row 12)")
+        vol_backbone_etas = params.get_vol_backbone_etas(ttms=option_chain.ttms)
+        return logsv_mc_chain_pricer(v0=params.sigma0, theta=params.theta, kappa1=params.kappa1, kappa2=params.kappa2,
+                                     beta=params.beta, volvol=params.volvol, vol_backbone_etas=vol_backbone_etas,
+                                     ttms=option_chain.ttms, forwards=option_chain.forwards, discfactors=option_chain.discfactors,
+                                     strikes_ttms=option_chain.strikes_ttms, optiontypes_ttms=option_chain.optiontypes_ttms,
+                                     is_spot_measure=is_spot_measure, variable_type=variable_type, nb_path=nb_path,
+                                     nb_steps_per_year=nb_steps or int(360 * np.max(option_chain.ttms)) + 1,
+                                     seed=kwargs.get("seed"), precision=kwargs.get("precision", "fp64"),
+                                     gauss=kwargs.get("gauss", "fp32"), distributed=kwargs.get("distributed", True))
+
+    @timer
+    def simulate_terminal_values(self, params: LogSvParams, ttm: float = 1.0, nb_path: int = 100000, is_spot_measure: bool = True,
+                                 **kwargs) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """terminal (log-return, vol, quadratic variance), float64[nb_path] each; 360 steps/year and eta = 1 as in the
+        reference (:600-610)."""
+        return simulate_logsv_x_vol_terminal(ttm=ttm, x0=np.zeros(1), sigma0=params.sigma0 * np.ones(1), qvar0=np.zeros(1),
+                                             theta=params.theta, kappa1=params.kappa1, kappa2=params.kappa2, beta=params.beta,
+                                             volvol=params.volvol, nb_path=nb_path, is_spot_measure=is_spot_measure,
+                                             nb_steps_per_year=kwargs.get("nb_steps_per_year", 360), seed=kwargs.get("seed"),
+                                             gauss=kwargs.get("gauss", "fp32"))
+
+
+def set_vol_scaler(sigma0: float, ttm: float) -> float:
+    """transform-grid scaler sigma0*sqrt(min(min ttm, 0.5/12)) (logsv_pricer.py:664-666)."""
+    return sigma0 * np.sqrt(np.minimum(np.min(ttm), 0.5 / 12.0))
+
+
+def logsv_chain_pricer(params: LogSvParams, ttms: np.ndarray, forwards: np.ndarray, discfactors: np.ndarray,
+                       strikes_ttms: List[np.ndarray], optiontypes_ttms: List[np.ndarray], is_stiff_solver: bool = False,
+                       is_analytic: bool = False, is_spot_measure: bool = True,
+                       expansion_order: ExpansionOrder = ExpansionOrder.SECOND,
+                       variable_type: VariableType = VariableType.LOG_RETURN, vol_scaler: float = None, **kwargs) -> List[np.ndarray]:
+    """Fourier chain pricer (reference :669-739): one fused GPU call for the whole chain -- transform grid, RK45 ODE solves of the
+    affine expansion carried across maturities, log-MGF, Simpson sums.  ``return_grids=True`` additionally returns
+    (a_t1 [M,P,n], log_mgf [M,P])."""
+    if variable_type != VariableType.LOG_RETURN and getattr(variable_type, "value", variable_type) != 1:
+        raise NotImplementedError       # Q_VAR Fourier route: SURVEY.md §8f #3; SIGMA: reference raises too (:733-734)
+    if is_stiff_solver or is_analytic:
+        raise NotImplementedError("only the default RK45 branch is implemented on the GPU")
+    order = _order_code(expansion_order)
+    etas = np.array([params.get_vol_backbone_eta(tau=ttm) for ttm in ttms], dtype=float)
+    return engine.logsv_price_chain(_params_c(params), ttms, forwards, discfactors, etas, strikes_ttms, optiontypes_ttms,
+                                    is_spot_measure=is_spot_measure, expansion_order=order, vol_scaler=vol_scaler,
+                                    max_phi=int(kwargs.get("max_phi", 1000)), return_grids=bool(kwargs.get("return_grids", False)))
+
+
+def logsv_mc_chain_pricer(ttms: np.ndarray, forwards: np.ndarray, discfactors: np.ndarray, strikes_ttms, optiontypes_ttms,
+                          v0: float, theta: float, kappa1: float, kappa2: float, beta: float, volvol: float,
+                          vol_backbone_etas: np.ndarray, is_spot_measure: bool = True, nb_path: int = 100000,
+                          nb_steps_per_year: int = 360, variable_type: VariableType = VariableType.LOG_RETURN,
+                          seed: Optional[int] = None, precision: str = "fp64", gauss: str = "fp32", distributed: bool = True
+                          ) -> Tuple[List[np.ndarray], List[np.ndarray]]:
+    """chain MC (reference :806-867): every maturity is simulated from the terminal state of the previous one by the fused
+    stepper, followed by forward-recentred payoff moments.  Under an initialised torch.distributed world ``nb_path`` is the
+    TOTAL path count, sharded over the ranks (two fp64 all-reduces per maturity)."""
+    params_c = engine.logsv_params_c(v0, theta, kappa1, kappa2, beta, volvol)
+    flags = engine.mc_flags(precision, gauss)
+    seed = engine.fresh_seed() if seed is None else int(seed)
+    if _use_distributed({"distributed": distributed}):
+        from ..multi_gpu import mc_chain_distributed
+        C.encode_types(np.concatenate([np.asarray(t) for t in optiontypes_ttms]))
+        return mc_chain_distributed("logsv", params_c, ttms, forwards, discfactors, vol_backbone_etas, strikes_ttms,
+                                    optiontypes_ttms, nb_path, nb_steps_per_year, is_spot_measure,
+                                    engine.variable_code(variable_type), seed, flags)
+    return engine.logsv_mc_chain(params_c, ttms, forwards, discfactors, vol_backbone_etas, strikes_ttms, optiontypes_ttms, nb_path,
+                                 nb_steps_per_year, is_spot_measure, variable_type, seed, flags)
+
+
+def simulate_logsv_x_vol_terminal(ttm: float, x0: np.ndarray, sigma0: np.ndarray, qvar0: np.ndarray, theta: float, kappa1: float,
+                                  kappa2: float, beta: float, volvol: float, vol_backbone_eta: float = 1.0,
+                                  is_spot_measure: bool = True, nb_path: int = 100000, nb_steps_per_year: int = 360,
+                                  W0: Optional[np.ndarray] = None, W1: Optional[np.ndarray] = None, dt: Optional[float] = None,
+                                  seed: Optional[int] = None, gauss: str = "fp32") -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """terminal (x, sigma, qvar) after ``ttm`` (reference :950-1047).
+
+    With ``W0, W1, dt`` (unit normals [nb_steps, nb_path]) the strict fixed-random kernel reproduces the reference arithmetic
+    (fp64, reference evaluation order, no FMA contraction).  Without them the fused Philox kernel is used and the initial state
+    must be the length-1 broadcast form the reference's own callers use (constant sigma0, zero x0 / qvar0)."""
+    if W0 is not None or W1 is not None:
+        if W0 is None or W1 is None or dt is None:
+            raise ValueError("W0, W1 and dt must be supplied together")
+        params_c = engine.logsv_params_c(1.0, theta, kappa1, kappa2, beta, volvol)
+        return engine.logsv_step_fixed(x0, sigma0, qvar0, W0, W1, dt, params_c, vol_backbone_eta, is_spot_measure)
+    x0, sigma0, qvar0 = np.atleast_1d(x0), np.atleast_1d(sigma0), np.atleast_1d(qvar0)
+    for a in (x0, sigma0, qvar0):
+        assert a.shape[0] in (1, nb_path)            # :1007-1020
+    x_ok = x0.shape[0] == 1 or not np.any(x0)            # a length-1 x0 / qvar0 is replaced by zeros in the reference (:1007-1015)
+    q_ok = qvar0.shape[0] == 1 or not np.any(qvar0)
+    if not (x_ok and q_ok and np.all(sigma0 == sigma0[0])):
+        raise NotImplementedError("the fused kernel starts every path from (0, sigma0, 0); pass W0/W1/dt for per-path initial states")
+    params_c = engine.logsv_params_c(float(sigma0[0]), theta, kappa1, kappa2, beta, volvol)
+    seed = engine.fresh_seed() if seed is None else int(seed)
+    return engine.logsv_terminal(params_c, ttm, nb_path, nb_steps_per_year, is_spot_measure, vol_backbone_eta, seed,
+                                 engine.mc_flags("fp64", gauss))
+
+
+def get_randoms_for_chain_valuation(ttms: np.ndarray, nb_path: int = 100000, nb_steps_per_year: int = 360, seed: int = 10):
+    """fixed unit normals per maturity from a LOCAL legacy generator: per slice W0 then W1, never touching numpy's global state
+    (reference :1051-1074)."""
+    rng = np.random.RandomState(seed)
+    W0s, W1s, dts = [], [], []
+    ttm0 = 0.0
+    for ttm in ttms:
+        nb_steps_, dt, _ = set_time_grid(ttm=ttm - ttm0, nb_steps_per_year=nb_steps_per_year)
+        W0s.append(rng.normal(0, 1, size=(nb_steps_, nb_path)))
+        W1s.append(rng.normal(0, 1, size=(nb_steps_, nb_path)))
+        dts.append(dt)
+        ttm0 = ttm
+    return W0s, W1s, dts
+
+
+def logsv_mc_chain_pricer_fixed_randoms(ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms, W0s, W1s, dts, v0: float,
+                                        theta: float, kappa1: float, kappa2: float, beta: float, volvol: float,
+                                        vol_backbone_etas: np.ndarray, is_spot_measure: bool = True,
+                                        variable_type: VariableType = VariableType.LOG_RETURN, return_states: bool = False):
+    """chain valuation with caller-supplied unit normals (reference :1100-1162): strict-arithmetic stepper + payoff kernels."""
+    params_c = engine.logsv_params_c(v0, theta, kappa1, kappa2, beta, volvol)
+    nb_path = W0s[0].shape[1]
+    x, q, s = np.zeros(nb_path), np.zeros(nb_path), v0 * np.ones(nb_path)
+    prices, stds, states = [], [], []
+    for ttm, forward, discfactor, strikes, types, eta, W0, W1, dt in zip(ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms,
+                                                                         vol_backbone_etas, W0s, W1s, dts):
+        x, s, q = engine.logsv_step_fixed(x, s, q, W0, W1, dt, params_c, eta, is_spot_measure)
+        p, e = engine.mc_payoffs(x, q, ttm, forward, strikes, types, discfactor, variable_type)
+        prices.append(p)
+        stds.append(e)
+        if return_states:
+            states.append((x.copy(), s.copy(), q.copy()))
+    return (prices, stds, states) if return_states else (prices, stds)

@@ -1,0 +1,250 @@
+"""GPU parity tests of the Monte Carlo path, through the C ABI (ctypes) and the Pricer API.
+
+Tiers:
+  arithmetic  -- fixed-random steppers vs golden states from the reference: <= 1e-12 abs
+                 fused Philox kernel vs the oracle fed with the same normals: <= 1e-10
+  statistical -- Philox prices within 3 standard errors of the Fourier price (reference tests use 4 SE)
+"""
+import numpy as np
+import pytest
+
+from conftest import chain_from_golden, load_golden
+from oracle import cport, mc, mgf
+
+pytestmark = pytest.mark.gpu
+
+K5 = np.array([0.8, 0.9, 1.0, 1.1, 1.2])
+T5 = np.array(["P", "P", "C", "C", "C"])
+Q = (1.0, 1.0, 5.0, 5.0, 0.2, 2.0)
+
+
+def _fixed_randoms(g):
+    rng = np.random.RandomState(int(g["seed"]))
+    N = int(g["nb_path"])
+    out0, out1 = [], []
+    for S in g["nsteps"]:
+        out0.append(rng.normal(0, 1, size=(int(S), N)))
+        out1.append(rng.normal(0, 1, size=(int(S), N)))
+    return out0, out1
+
+
+def test_exp_pair_accuracy(cuda_lib):
+    from stochvolmodels_b200 import engine
+    L = np.concatenate([np.linspace(-30, 30, 200001), np.random.RandomState(0).normal(0, 2, 100000), [0.0, -700.0, 700.0, 1e-300, -1e-17]])
+    ep, em = engine.debug_exp_pair(L)
+    rel_p = np.abs(ep / np.exp(L) - 1)
+    rel_m = np.abs(em / np.exp(-L) - 1)
+    assert rel_p.max() < 4.5e-16 and rel_m.max() < 4.5e-16, (rel_p.max(), rel_m.max())
+
+
+@pytest.mark.parametrize("tag", ["g5_c1", "inverse_eta", "btc_small", "qvar"])
+def test_logsv_fixed_randoms_vs_reference_golden(cuda_lib, tag):
+    """b200sv_logsv_step_fixed + b200sv_mc_payoffs == logsv_mc_chain_pricer_fixed_randoms of the reference."""
+    from stochvolmodels_b200.pricers.logsv_pricer import get_randoms_for_chain_valuation, logsv_mc_chain_pricer_fixed_randoms
+    from stochvolmodels_b200.utils.config import VariableType
+    g = load_golden(f"logsv_mc_fixed_{tag}.npz")
+    strikes, types = chain_from_golden(g)
+    W0s, W1s, dts = get_randoms_for_chain_valuation(g["ttms"], int(g["nb_path"]), int(g["n_per_year"]), int(g["seed"]))
+    np.testing.assert_array_equal(np.array(dts), g["dts"])
+    np.testing.assert_array_equal(W0s[0][0, :3], g["W0_head"])
+    s0, th, k1, k2, b, vv = g["params"]
+    p, e, st = logsv_mc_chain_pricer_fixed_randoms(g["ttms"], g["forwards"], g["discfactors"], strikes, types, W0s, W1s, dts, s0, th, k1,
+                                                   k2, b, vv, g["etas"], bool(g["is_spot"]), VariableType(int(g["variable_type"])), True)
+    for m in range(int(g["nslices"])):
+        for a, name in zip(st[m], ("x", "sigma", "qvar")):
+            np.testing.assert_allclose(a, g[f"{name}_{m}"], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(p[m], g[f"prices_{m}"], rtol=1e-9, atol=1e-13)      # 1/S payoffs amplify 1e-16 to ~1e-11
+        np.testing.assert_allclose(e[m], g[f"stderr_{m}"], rtol=1e-8, atol=1e-13)
+
+
+@pytest.mark.parametrize("tag", ["dflt", "floor"])
+def test_heston_fixed_randoms_vs_reference_golden(cuda_lib, tag):
+    from stochvolmodels_b200.pricers.heston_pricer import simulate_heston_x_vol_terminal
+    from stochvolmodels_b200.utils.mc_payoffs import compute_mc_vars_payoff
+    g = load_golden(f"heston_mc_fixed_{tag}.npz")
+    N, S = int(g["nb_path"]), int(g["nsteps"])
+    rng = np.random.RandomState(int(g["seed"]))
+    W0, W1 = rng.normal(0, 1, size=(S, N)), rng.normal(0, 1, size=(S, N))
+    v0, theta, kappa, rho, volvol = g["params"]
+    x, v, q = simulate_heston_x_vol_terminal(float(g["ttm"]), np.zeros(1), v0 * np.ones(1), np.zeros(1), theta, kappa, rho, volvol,
+                                             nb_path=N, W0=W0, W1=W1, dt=float(g["dt"]))
+    np.testing.assert_allclose(x, g["x"], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(v, g["var"], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(q, g["qvar"], rtol=0, atol=1e-13)
+    p, e = compute_mc_vars_payoff(x, np.sqrt(v), q, float(g["ttm"]), float(g["forward"]), g["strikes"], g["types"], float(g["discfactor"]))
+    np.testing.assert_allclose(p, g["prices"], rtol=1e-11)
+    np.testing.assert_allclose(e, g["stderr"], rtol=1e-9)
+
+
+def test_payoffs_vs_reference_golden_incl_nan_paths(cuda_lib):
+    from stochvolmodels_b200.utils.config import VariableType
+    from stochvolmodels_b200.utils.mc_payoffs import compute_mc_vars_payoff
+    g = load_golden("payoffs.npz")
+    kw = dict(sigma0=np.ones(1), ttm=float(g["ttm"]), forward=float(g["forward"]), discfactor=float(g["discfactor"]))
+    for xs, suf in (("x", ""), ("x_nan", "_nan")):
+        p, e = compute_mc_vars_payoff(x0=g[xs], qvar0=g["qvar"], strikes_ttm=g["strikes"], optiontypes_ttm=g["types"], **kw)
+        np.testing.assert_allclose(p, g["prices" + suf], rtol=1e-12)
+        np.testing.assert_allclose(e, g["stderr" + suf], rtol=1e-10)
+        p, e = compute_mc_vars_payoff(x0=g[xs], qvar0=g["qvar"], strikes_ttm=g["qstrikes"], optiontypes_ttm=g["qtypes"],
+                                      variable_type=VariableType.Q_VAR, **kw)
+        np.testing.assert_allclose(p, g["qprices" + suf], rtol=1e-12)
+        np.testing.assert_allclose(e, g["qstderr" + suf], rtol=1e-10)
+    with pytest.raises(ValueError, match="payoff"):                       # utils/mc_payoffs.py:83-84
+        compute_mc_vars_payoff(x0=g["x"], qvar0=g["qvar"], strikes_ttm=np.ones(1), optiontypes_ttm=np.array(["BAD"]), **kw)
+    with pytest.raises(NotImplementedError):                              # utils/mc_payoffs.py:69-70
+        compute_mc_vars_payoff(x0=g["x"], qvar0=g["qvar"], strikes_ttm=np.ones(1), optiontypes_ttm=np.array(["C"]),
+                               variable_type=VariableType.SIGMA, **kw)
+
+
+def test_device_normals_match_oracle_restatement(cuda_lib):
+    from stochvolmodels_b200 import _capi as C, engine
+    ids = 123456789012 + np.arange(4096)            # exercises the high counter word
+    for slice_idx, nsteps in ((0, 5), (3, 8)):
+        z0, z1 = engine.device_normals(10, int(ids[0]), ids.shape[0], slice_idx, nsteps, C.GAUSS_F64)
+        o0, o1 = mc.device_normals(10, ids, slice_idx, nsteps, "f64")
+        np.testing.assert_allclose(z0, o0, rtol=0, atol=5e-15)
+        np.testing.assert_allclose(z1, o1, rtol=0, atol=5e-15)
+        z0, z1 = engine.device_normals(10, int(ids[0]), ids.shape[0], slice_idx, nsteps, C.GAUSS_F32)
+        o0, o1 = mc.device_normals(10, ids, slice_idx, nsteps, "f32")
+        np.testing.assert_allclose(z0, o0, rtol=0, atol=2e-5)          # SFU lg2/sin/cos vs libm float
+        np.testing.assert_allclose(z1, o1, rtol=0, atol=2e-5)
+    z = np.concatenate([a.ravel() for a in engine.device_normals(99, 0, 1 << 20, 0, 4, C.GAUSS_F32)])
+    n = z.size
+    assert abs(z.mean()) < 4 / np.sqrt(n) and abs(z.var() - 1) < 4 * np.sqrt(2 / n) and abs(np.mean(z ** 4) - 3) < 4 * np.sqrt(96 / n)
+
+
+@pytest.mark.parametrize("gauss", ["fp64", "fp32"])
+@pytest.mark.parametrize("is_spot", [True, False])
+def test_fused_logsv_kernel_vs_oracle_same_normals(cuda_lib, gauss, is_spot):
+    """terminal states and chain prices of the fused Philox kernel == numpy oracle stepper fed with the kernel's own normals."""
+    from stochvolmodels_b200 import _capi as C, engine
+    N, npy, seed = 20000, 252, 4242
+    params = (0.8376, 1.0413, 3.1844, 3.058, 0.1514, 1.8458)
+    ttms, fw, df, etas = np.array([0.1, 0.3, 0.35]), np.array([1.0, 1.02, 1.03]), np.array([0.999, 0.99, 0.98]), np.array([0.9, 1.1, 1.0])
+    types = [T5, T5, T5] if is_spot else [np.array(["IP", "IP", "IC", "IC", "IC"])] * 3
+    flags = engine.mc_flags("fp64", gauss)
+    steps = mc.chain_steps(ttms, npy)
+    Z = [engine.device_normals(seed, 0, N, m, steps[m][0], flags) for m in range(3)]
+    po, eo, st = mc.logsv_mc_chain_fixed(params, ttms, fw, df, [K5] * 3, types, etas, [z[0] for z in Z], [z[1] for z in Z],
+                                         [d for _, d in steps], is_spot, 1, True)
+    pg, eg = engine.logsv_mc_chain(engine.logsv_params_c(*params), ttms, fw, df, etas, [K5] * 3, types, N, npy, is_spot, 1, seed, flags)
+    for m in range(3):
+        np.testing.assert_allclose(pg[m], po[m], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(eg[m], eo[m], rtol=1e-8, atol=1e-12)
+    # single slice terminal values: paths themselves
+    x, s, q = engine.logsv_terminal(engine.logsv_params_c(*params), 0.1, N, npy, is_spot, 0.9, seed, flags)
+    np.testing.assert_allclose(x, st[0][0], rtol=0, atol=1e-11)
+    np.testing.assert_allclose(s, st[0][1], rtol=1e-11, atol=0)
+    np.testing.assert_allclose(q, st[0][2], rtol=0, atol=1e-11)
+
+
+@pytest.mark.parametrize("gauss", ["fp64", "fp32"])
+def test_fused_heston_kernel_vs_oracle_same_normals(cuda_lib, gauss):
+    from stochvolmodels_b200 import engine
+    N, npy, seed = 20000, 360, 777
+    params = (0.01, 0.02, 1.0, -0.7, 1.0)           # Feller violated -> floor binds
+    ttms, fw, df = np.array([0.2, 0.5]), np.array([1.0, 1.01]), np.array([0.995, 0.98])
+    flags = engine.mc_flags("fp64", gauss)
+    steps = mc.chain_steps(ttms, npy)
+    Z = [engine.device_normals(seed, 0, N, m, steps[m][0], flags) for m in range(2)]
+    po, eo, st = mc.heston_mc_chain_fixed(params, ttms, fw, df, [K5] * 2, [T5] * 2, [z[0] for z in Z], [z[1] for z in Z],
+                                          [d for _, d in steps], 1, True)
+    pg, eg = engine.heston_mc_chain(engine.heston_params_c(*params), ttms, fw, df, [K5] * 2, [T5] * 2, N, npy, 1, seed, flags)
+    for m in range(2):
+        np.testing.assert_allclose(pg[m], po[m], rtol=1e-9, atol=1e-13)
+        np.testing.assert_allclose(eg[m], eo[m], rtol=1e-8, atol=1e-13)
+    x, v, q = engine.heston_terminal(engine.heston_params_c(*params), 0.2, N, npy, seed, flags)
+    np.testing.assert_allclose(x, st[0][0], rtol=0, atol=1e-11)
+    np.testing.assert_allclose(v, st[0][1], rtol=0, atol=1e-12)
+    assert v.min() >= 1e-4 and np.isclose(v.min(), 1e-4)
+
+
+def test_large_n_fp64_chain_vs_c_port(cuda_lib):
+    """1e6 paths x BTC chain: GPU (all-fp64 mode) vs the C port of the reference algorithm on the same Philox stream."""
+    from stochvolmodels_b200 import engine, get_btc_test_chain_data
+    chain = get_btc_test_chain_data()
+    params = (0.8376, 1.0413, 3.1844, 3.058, 0.1514, 1.8458)
+    N, npy, seed = 1_000_000, 252, 31337
+    pc, ec = cport.mc_chain("logsv", params, chain.ttms, chain.forwards, chain.discfactors, None, chain.strikes_ttms,
+                            chain.optiontypes_ttms, N, npy, True, 1, seed, "f64")
+    pg, eg = engine.logsv_mc_chain(engine.logsv_params_c(*params), chain.ttms, chain.forwards, chain.discfactors, None,
+                                   chain.strikes_ttms, chain.optiontypes_ttms, N, npy, True, 1, seed, engine.mc_flags("fp64", "fp64"))
+    for m in range(4):
+        np.testing.assert_allclose(pg[m], pc[m], rtol=1e-9)
+        np.testing.assert_allclose(eg[m], ec[m], rtol=1e-8)
+
+
+@pytest.mark.parametrize("precision,gauss", [("fp64", "fp32"), ("fp64", "fp64"), ("fp32", "fp32")])
+def test_logsv_mc_within_3se_of_fourier_quickstart(cuda_lib, precision, gauss):
+    """BASELINE config 1/4 gate: every strike within 3 SE (and <= 1e-3 abs) of the reference Fourier price (golden G1)."""
+    from stochvolmodels_b200 import LogSvParams, LogSVPricer, OptionChain
+    g = load_golden("logsv_fourier_g1_quickstart.npz")
+    chain = OptionChain(ttms=np.array([0.25, 0.5]), forwards=np.ones(2), strikes_ttms=[K5, K5], optiontypes_ttms=[T5, T5])
+    prices, ses = LogSVPricer().model_mc_price_chain(chain, LogSvParams(*Q), nb_path=4_000_000, nb_steps=252, seed=2024,
+                                                     precision=precision, gauss=gauss)
+    for m in range(2):
+        z = (prices[m] - g[f"prices_{m}"]) / ses[m]
+        assert np.all(np.abs(z) < 3.0), z
+        assert np.all(np.abs(prices[m] - g[f"prices_{m}"]) < 1e-3)
+        assert np.all(ses[m] > 0) and np.all(ses[m] < 6e-4)
+
+
+def test_logsv_mc_btc_chain_within_3se_of_fourier(cuda_lib):
+    from stochvolmodels_b200 import LOGSV_BTC_PARAMS, LogSVPricer, get_btc_test_chain_data
+    g = load_golden("logsv_fourier_btc.npz")
+    chain = get_btc_test_chain_data()
+    prices, ses = LogSVPricer().model_mc_price_chain(chain, LOGSV_BTC_PARAMS, nb_path=10_000_000, nb_steps=252, seed=7)
+    for m in range(4):
+        z = (prices[m] - g[f"prices_{m}"]) / ses[m]
+        assert np.all(np.abs(z) < 3.0), (m, z)
+        assert np.all(np.abs(prices[m] - g[f"prices_{m}"]) / chain.forwards[m] < 1e-3)
+
+
+def test_heston_mc_within_3se_of_fourier(cuda_lib):
+    from stochvolmodels_b200 import HestonParams, HestonPricer, OptionChain
+    g = load_golden("heston_fourier_g4.npz")
+    chain = OptionChain(ttms=np.array([0.25, 1.0]), forwards=np.ones(2), strikes_ttms=[K5, K5], optiontypes_ttms=[T5, T5])
+    prices, ses = HestonPricer().model_mc_price_chain(chain, HestonParams(), nb_path=4_000_000, seed=5)
+    for m in range(2):
+        z = (prices[m] - g[f"prices_{m}"]) / ses[m]
+        # floor-Euler at 360 steps/yr carries a small discretisation bias on top of MC noise (reference test uses 4 SE at 40k paths)
+        assert np.all(np.abs(prices[m] - g[f"prices_{m}"]) < 3.0 * ses[m] + 2e-4), z
+
+
+def test_terminal_moments_and_api(cuda_lib):
+    """E[e^x] = 1 under the MMA measure, finite positive vols (reference tests/test_logsv_characterization.py:442-458)."""
+    from stochvolmodels_b200 import HestonParams, HestonPricer, LogSvParams, LogSVPricer
+    x, s, q = LogSVPricer().simulate_terminal_values(LogSvParams(*Q), ttm=0.25, nb_path=2_000_000, seed=11)
+    assert x.shape == s.shape == q.shape == (2_000_000,) and x.dtype == np.float64
+    ex = np.exp(x)
+    assert abs(ex.mean() - 1.0) < 4 * ex.std() / np.sqrt(x.size)
+    assert np.all(s > 0) and np.all(q > 0) and np.all(np.isfinite(x))
+    x2, s2, q2 = LogSVPricer().simulate_terminal_values(LogSvParams(*Q), ttm=0.25, nb_path=2_000_000, seed=11)
+    np.testing.assert_array_equal(x, x2)                       # same seed replays bit-for-bit
+    x3, _, _ = LogSVPricer().simulate_terminal_values(LogSvParams(*Q), ttm=0.25, nb_path=1000, seed=12)
+    assert not np.array_equal(x3, x[:1000])
+    xh, vh, qh = HestonPricer().simulate_terminal_values(HestonParams(), ttm=1.0, nb_path=1_000_000, seed=3)
+    assert vh.min() >= 1e-4 and abs(np.exp(xh).mean() - 1.0) < 4 * np.exp(xh).std() / 1000.0
+    assert abs(qh.mean() - 0.04) < 1e-3                         # E[int v dt] = theta*T when v0 = theta
+
+
+def test_path_offset_makes_shards_consistent(cuda_lib):
+    """device-level API: two half-ranges with path offsets reproduce the unsharded terminal states bit-for-bit."""
+    import torch
+    from ctypes import byref, c_void_p
+    from stochvolmodels_b200 import _capi as C, engine
+    N = 100_000
+    pc = engine.logsv_params_c(*Q)
+    def run(n, off):
+        st = torch.empty((3, n), dtype=torch.float64, device="cuda")
+        mom = torch.zeros(2, dtype=torch.float64, device="cuda")
+        C.call("b200sv_dev_logsv_slice", c_void_p(st[0].data_ptr()), c_void_p(st[1].data_ptr()), c_void_p(st[2].data_ptr()), n, off, 1,
+               byref(pc), 1.0, 1, 64, 0.25 / 64, 0, 1.0, 10, 0, c_void_p(mom.data_ptr()), c_void_p(torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        return st.cpu().numpy(), mom.cpu().numpy()
+    full, mfull = run(N, 0)
+    a, ma = run(N // 2, 0)
+    b, mb = run(N - N // 2, N // 2)
+    np.testing.assert_array_equal(np.concatenate([a, b], axis=1), full)
+    np.testing.assert_allclose(ma + mb, mfull, rtol=1e-13)
+    assert mfull[1] == N

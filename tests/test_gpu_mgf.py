@@ -1,0 +1,123 @@
+"""GPU parity tests of the Fourier / MGF path (north_star: <= 1e-10 relative vs the reference CPU path)."""
+import numpy as np
+import pytest
+
+from conftest import chain_from_golden, load_golden
+from oracle import mgf
+
+pytestmark = pytest.mark.gpu
+K5 = np.array([0.8, 0.9, 1.0, 1.1, 1.2])
+T5 = np.array(["P", "P", "C", "C", "C"])
+
+
+@pytest.mark.parametrize("tag", ["g1_quickstart", "g2_inverse", "c3_5x21", "btc", "first_order", "backbone_inverse"])
+def test_logsv_fourier_chain_vs_reference_golden(cuda_lib, tag):
+    from stochvolmodels_b200 import engine
+    g = load_golden(f"logsv_fourier_{tag}.npz")
+    strikes, types = chain_from_golden(g)
+    prices, a, lm = engine.logsv_price_chain(engine.logsv_params_c(*g["params"]), g["ttms"], g["forwards"], g["discfactors"], g["etas"],
+                                             strikes, types, bool(g["is_spot"]), int(g["order"]), None, 1000, True)
+    for m in range(int(g["nslices"])):
+        np.testing.assert_allclose(a[m], g[f"a_t1_{m}"], rtol=0, atol=1e-11)
+        np.testing.assert_allclose(lm[m], g[f"log_mgf_{m}"], rtol=0, atol=1e-11)
+        np.testing.assert_allclose(prices[m], g[f"prices_{m}"], rtol=1e-10, atol=1e-13 * g["forwards"][m])
+
+
+@pytest.mark.parametrize("tag", ["g4", "c3_5x21", "btc"])
+def test_heston_fourier_chain_vs_reference_golden(cuda_lib, tag):
+    from stochvolmodels_b200 import engine
+    g = load_golden(f"heston_fourier_{tag}.npz")
+    strikes, types = chain_from_golden(g)
+    prices, lm = engine.heston_price_chain(engine.heston_params_c(*g["params"]), g["ttms"], g["forwards"], g["discfactors"], strikes, types,
+                                           None, 1000, True)
+    for m in range(int(g["nslices"])):
+        np.testing.assert_allclose(lm[m], g[f"log_mgf_{m}"], rtol=1e-11, atol=1e-11)
+        np.testing.assert_allclose(prices[m], g[f"prices_{m}"], rtol=1e-10, atol=1e-13 * g["forwards"][m])
+
+
+def test_single_maturity_grid_entry_points(cuda_lib):
+    """compute_logsv_a_mgf_grid / compute_heston_mgf_grid with carried state == golden second slice."""
+    from stochvolmodels_b200.pricers.heston_pricer import compute_heston_mgf_grid
+    from stochvolmodels_b200.pricers.logsv.affine_expansion import ExpansionOrder, compute_logsv_a_mgf_grid
+    g = load_golden("logsv_fourier_g1_quickstart.npz")
+    s0, th, k1, k2, b, vv = g["params"]
+    phi = g["phi"]
+    z = np.zeros_like(phi)
+    a1, lm1 = compute_logsv_a_mgf_grid(0.25, phi, z, z, s0, th, k1, k2, b, vv, expansion_order=ExpansionOrder.SECOND)
+    a2, lm2 = compute_logsv_a_mgf_grid(0.25, phi, z, z, s0, th, k1, k2, b, vv, a_t0=a1)
+    np.testing.assert_allclose(a1, g["a_t1_0"], atol=1e-11, rtol=0)
+    np.testing.assert_allclose(lm2, g["log_mgf_1"], atol=1e-11, rtol=0)
+    # MGF roots: log-MGF == 0 at Phi in {0, -1} under the MMA measure (reference tests/test_logsv_characterization.py:141-163)
+    roots = np.array([0.0 + 0j, -1.0 + 0j])
+    _, lm0 = compute_logsv_a_mgf_grid(0.25, roots, np.zeros(2, complex), np.zeros(2, complex), s0, th, k1, k2, b, vv)
+    np.testing.assert_allclose(lm0, 0.0, atol=1e-14)
+    with pytest.raises(NotImplementedError):
+        compute_logsv_a_mgf_grid(0.25, phi, z, z, s0, th, k1, k2, b, vv, expansion_order=ExpansionOrder.ZERO)
+    h = load_golden("heston_fourier_g4.npz")
+    v0, theta, kappa, rho, volvol = h["params"]
+    lm, a, bb = compute_heston_mgf_grid(v0, theta, kappa, volvol, rho, 0.25, h["phi"], np.zeros_like(h["phi"]))
+    np.testing.assert_allclose(lm, h["log_mgf_0"], rtol=1e-12, atol=1e-12)
+    lm, a, bb = compute_heston_mgf_grid(v0, theta, kappa, volvol, rho, 0.75, h["phi"], np.zeros_like(h["phi"]), a, bb)
+    np.testing.assert_allclose(lm, h["log_mgf_1"], rtol=1e-11, atol=1e-11)
+    np.testing.assert_allclose(a, h["a_t1_1"], rtol=1e-11, atol=1e-11)
+    np.testing.assert_allclose(bb, h["b_t1_1"], rtol=1e-11, atol=1e-11)
+
+
+@pytest.mark.parametrize("tag", ["mma", "inv"])
+def test_fourier_sum_vs_reference_golden(cuda_lib, tag):
+    from stochvolmodels_b200.utils.mgf_pricer import vanilla_slice_pricer_with_mgf_grid
+    g = load_golden(f"fourier_sum_{tag}.npz")
+    p = vanilla_slice_pricer_with_mgf_grid(g["log_mgf"], g["phi"], float(g["forward"]), g["strikes"], g["types"], float(g["discfactor"]), bool(g["is_spot"]))
+    np.testing.assert_allclose(p, g["prices"], rtol=1e-12)
+    # general branch (|Re phi| != 1/2) against the oracle
+    phi = g["phi"] + (0.2 if tag == "mma" else -0.2)
+    sgn = 1.0 if tag == "mma" else -1.0
+    lm = 0.5 * 0.09 * 0.4 * (phi * phi + sgn * phi)
+    p = vanilla_slice_pricer_with_mgf_grid(lm, phi, 1.5, g["strikes"], g["types"], 0.9, bool(g["is_spot"]))
+    o = mgf.vanilla_slice_prices(lm, phi, 1.5, g["strikes"], g["types"], 0.9, bool(g["is_spot"]))
+    np.testing.assert_allclose(p, o, rtol=1e-12)
+    # nansum semantics: a NaN grid entry is skipped
+    lm2 = g["log_mgf"].copy()
+    lm2[17] = np.nan
+    p = vanilla_slice_pricer_with_mgf_grid(lm2, g["phi"], float(g["forward"]), g["strikes"], g["types"], float(g["discfactor"]), bool(g["is_spot"]))
+    o = mgf.vanilla_slice_prices(lm2, g["phi"], float(g["forward"]), g["strikes"], g["types"], float(g["discfactor"]), bool(g["is_spot"]))
+    np.testing.assert_allclose(p, o, rtol=1e-12)
+
+
+def test_error_conventions(cuda_lib):
+    from stochvolmodels_b200 import LogSvParams, LogSVPricer, OptionChain, VariableType
+    from stochvolmodels_b200.utils.mgf_pricer import vanilla_slice_pricer_with_mgf_grid
+    g = load_golden("fourier_sum_mma.npz")
+    with pytest.raises(ValueError, match="not implemented"):          # MMA measure rejects inverse payoffs (utils/mgf_pricer.py:206-212)
+        vanilla_slice_pricer_with_mgf_grid(g["log_mgf"], g["phi"], 1.5, g["strikes"][:1], np.array(["IC"]), 1.0, True)
+    chain = OptionChain.slice_to_chain(0.25, 1.0, K5, T5)
+    with pytest.raises(NotImplementedError):                          # pricers/logsv_pricer.py:733-734
+        LogSVPricer().price_chain(chain, LogSvParams(1, 1, 5, 5, 0.2, 2), variable_type=VariableType.SIGMA)
+
+
+def test_quickstart_through_pricer_api(cuda_lib):
+    """examples/getting_started/quickstart.py:23-46 with the reference's asserted values (rtol 5e-6)."""
+    from stochvolmodels_b200 import LogSvParams, LogSVPricer, OptionChain
+    params = LogSvParams(sigma0=1.0, theta=1.0, kappa1=5.0, kappa2=5.0, beta=0.2, volvol=2.0)
+    pricer = LogSVPricer()
+    price, ivol = pricer.price_vanilla(params=params, ttm=0.25, forward=1.0, strike=1.0, optiontype="C")
+    chain = OptionChain.get_uniform_chain(ttms=np.array([0.25, 0.5]), ids=np.array(["3m", "6m"]), forwards=np.array([1.0, 1.0]), strikes=K5)
+    prices, ivols = pricer.compute_chain_prices_with_vols(option_chain=chain, params=params)
+    np.testing.assert_allclose(price, 0.197331, rtol=5e-6, atol=1e-8)
+    np.testing.assert_allclose(ivol, 0.999577, rtol=5e-6, atol=1e-8)
+    np.testing.assert_allclose(prices[1][2], 0.275202, rtol=5e-6, atol=1e-8)
+    np.testing.assert_allclose(ivols[1][2], 0.995757, rtol=5e-6, atol=1e-8)
+    # price_chain == price_slice == price_vanilla (reference tests/test_logsv_characterization.py:101-138)
+    sl, _ = pricer.price_slice(params=params, ttm=0.25, forward=1.0, strikes=K5, optiontypes=T5)
+    np.testing.assert_allclose(sl, prices[0], rtol=0, atol=1e-14)
+    assert abs(sl[2] - price) < 1e-14
+    assert [p.shape for p in prices] == [(5,), (5,)] and all(p.dtype == np.float64 for p in prices)
+
+
+def test_heston_pricer_api(cuda_lib):
+    from stochvolmodels_b200 import HestonParams, HestonPricer, OptionChain, VariableType
+    g = load_golden("heston_fourier_g4.npz")
+    chain = OptionChain(ttms=np.array([0.25, 1.0]), forwards=np.ones(2), strikes_ttms=[K5, K5], optiontypes_ttms=[T5, T5])
+    prices = HestonPricer().price_chain(chain, HestonParams(), variable_type=VariableType.LOG_RETURN, some_unknown_kwarg=1)
+    for m in range(2):
+        np.testing.assert_allclose(prices[m], g[f"prices_{m}"], rtol=1e-10, atol=1e-13)
