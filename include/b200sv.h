@@ -128,9 +128,10 @@ int b200sv_dev_heston_slice(void* x, void* var, void* qvar, long long n_local, l
 
 /* per-strike payoff sums for local paths given the GLOBAL (all-reduced) re-centring moments[2]:
  * sums_out[3*J] (device) = (sum pay, sum pay^2, count non-NaN) per strike for THIS rank.
- * strikes / types are DEVICE arrays of J entries. */
+ * strikes / types are DEVICE arrays of J entries.  payoff_kinds_hint: what the HOST knows about types[] -- bit 0: some
+ * 'C'/'P', bit 1: some 'IC'/'IP'; 1 selects the branch-free vanilla kernel, anything else (0 = unknown) the general one. */
 int b200sv_dev_payoff_sums(const void* x, const void* qvar, long long n_local, int flags, double ttm, double forward,
-                           const double* strikes, const int8_t* types, int J, int variable_type,
+                           const double* strikes, const int8_t* types, int J, int variable_type, int payoff_kinds_hint,
                            const double* moments, double* sums_out, void* stream);
 
 /* turn GLOBAL sums[3*J] into prices / std errors (device arrays of J): price = df*s1/n, se = df*sqrt(s2/n-(s1/n)^2)/sqrt(N). */

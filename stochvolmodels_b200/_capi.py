@@ -13,7 +13,7 @@ from ctypes import POINTER, Structure, c_char_p, c_double, c_int, c_int8, c_long
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libb200sv.so")
+LIB_PATH = os.environ.get("B200SV_LIB") or os.path.join(_PKG, "lib", "libb200sv.so")   # B200SV_LIB: tuning builds only
 
 # enums of include/b200sv.h
 CALL, PUT, INV_CALL, INV_PUT = 0, 1, 2, 3
@@ -61,8 +61,8 @@ SIGNATURES = {
                                c_int, c_double, c_uint64, c_int, c_void_p, c_void_p],
     "b200sv_dev_heston_slice": [c_void_p, c_void_p, c_void_p, c_longlong, c_longlong, c_int, _hp, c_int, c_double, c_int, c_double,
                                 c_uint64, c_int, c_int, c_void_p, c_void_p],
-    "b200sv_dev_payoff_sums": [c_void_p, c_void_p, c_longlong, c_int, c_double, c_double, c_void_p, c_void_p, c_int, c_int, c_void_p,
-                               c_void_p, c_void_p],
+    "b200sv_dev_payoff_sums": [c_void_p, c_void_p, c_longlong, c_int, c_double, c_double, c_void_p, c_void_p, c_int, c_int, c_int,
+                               c_void_p, c_void_p, c_void_p],
     "b200sv_dev_payoff_finalize": [c_void_p, c_int, c_double, c_longlong, c_void_p, c_void_p, c_void_p],
     "b200sv_dev_logsv_step_fixed": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_double, _lp, c_double,
                                     c_int, c_void_p],

@@ -30,6 +30,9 @@ namespace b200sv {
 
 static thread_local long long g_launches = 0;
 constexpr int kThreads = 256;
+#ifndef B200SV_SLICE_MINBLOCKS
+#define B200SV_SLICE_MINBLOCKS 2   // resident CTAs / SM the slice kernel is register-budgeted for (tuned on B200, profiles/)
+#endif
 constexpr int kStrikeChunk = 8;
 
 // --------------------------------------------------------------------------------------------------------------------
@@ -88,60 +91,64 @@ static HestonConsts make_heston_consts(const b200sv_heston_params& p, double dt)
 template <typename Real>
 struct LogsvPath;
 
-// fp64 state: reformulated update (same scheme, constants folded, 1/sigma = exp(-L) from the shared polynomial)
+// fp64 state: same scheme, reformulated so that the per-step work is the log-vol recursion plus two running sums:
+//   A  = sum_{k=1..S} sigma_k^2      (new sigma of every step)
+//   XM = sum_{k=0..S-1} sigma_k z0_k (martingale part of x, old sigma)
+// from which  x_S = x_0 + cx*(sigma_0^2 + A - sigma_S^2) + ce*XM          [sum_k cx*sigma_k^2 + ce*sigma_k*z0_k]
+//             q_S = q_0 + cq*(sigma_0^2 + 2A - sigma_S^2)                 [sum_k cq*(sigma_k^2 + sigma_{k+1}^2)]
+// (logsv_pricer.py:1041-1045 summed over the slice).  1/sigma = exp(-L) comes from the shared polynomial.
 template <>
 struct LogsvPath<double> {
-  double x, L, s, s2, inv, q;
+  double L, s, inv, A, XM, x0, q0, s2_first;
   double cx, ce, a0, a1, a2, b0, b1, cq;
   __device__ __forceinline__ LogsvPath(const LogsvConsts& c)
       : cx(c.cx), ce(c.ce), a0(c.a0), a1(c.a1), a2(c.a2), b0(c.b0), b1(c.b1), cq(c.cq) {}
-  __device__ __forceinline__ void load(double x0, double sigma0, double q0) {
-    x = x0;
-    q = q0;
-    L = log(sigma0);               // vol_var = np.log(sigma0), logsv_pricer.py:1039
-    L = fmin(fmax(L, -700.0), 700.0);
+  __device__ __forceinline__ void load(double x_, double sigma0, double q_) {
+    x0 = x_;
+    q0 = q_;
+    L = clamp_log(log(sigma0));    // vol_var = np.log(sigma0), logsv_pricer.py:1039
     exp_pair(L, s, inv);
     s = sigma0;                    // keep the loaded sigma itself for the first step
-    s2 = s * s;
+    s2_first = s * s;
+    A = 0.0;
+    XM = 0.0;
   }
   __device__ __forceinline__ void step(double z0, double z1) {
-    const double t = s * z0;
-    x = fma(cx, s2, x);
-    x = fma(ce, t, x);
+    XM = fma(s, z0, XM);
     double l = L + a0;
     l = fma(a1, inv, l);
     l = fma(a2, s, l);
     l = fma(b0, z0, l);
     l = fma(b1, z1, l);
-    L = fmin(fmax(l, -700.0), 700.0);
+    L = clamp_log(l);
     exp_pair(L, s, inv);
-    const double s2n = s * s;
-    q = fma(cq, s2 + s2n, q);
-    s2 = s2n;
+    A = fma(s, s, A);
   }
   __device__ __forceinline__ double sigma() const { return s; }
+  __device__ __forceinline__ double x() const { return fma(ce, XM, fma(cx, (s2_first - s * s) + A, x0)); }
+  __device__ __forceinline__ double q() const { return fma(cq, (s2_first - s * s) + 2.0 * A, q0); }
 };
 
-// fp32 state (opt-in B200SV_STATE_F32): SFU exp / reciprocal
+// fp32 state (opt-in B200SV_STATE_F32): same structure, SFU exp / reciprocal
 template <>
 struct LogsvPath<float> {
-  float x, L, s, s2, inv, q;
+  float L, s, inv, A, XM, x0, q0, s2_first;
   float cx, ce, a0, a1, a2, b0, b1, cq;
   __device__ __forceinline__ LogsvPath(const LogsvConsts& c)
       : cx((float)c.cx), ce((float)c.ce), a0((float)c.a0), a1((float)c.a1), a2((float)c.a2), b0((float)c.b0),
         b1((float)c.b1), cq((float)c.cq) {}
-  __device__ __forceinline__ void load(float x0, float sigma0, float q0) {
-    x = x0;
-    q = q0;
+  __device__ __forceinline__ void load(float x_, float sigma0, float q_) {
+    x0 = x_;
+    q0 = q_;
     L = __logf(sigma0);
     s = sigma0;
-    s2 = s * s;
+    s2_first = s * s;
     inv = __frcp_rn(s);
+    A = 0.0f;
+    XM = 0.0f;
   }
   __device__ __forceinline__ void step(float z0, float z1) {
-    const float t = s * z0;
-    x = fmaf(cx, s2, x);
-    x = fmaf(ce, t, x);
+    XM = fmaf(s, z0, XM);
     float l = L + a0;
     l = fmaf(a1, inv, l);
     l = fmaf(a2, s, l);
@@ -150,35 +157,39 @@ struct LogsvPath<float> {
     L = fminf(fmaxf(l, -80.0f), 80.0f);
     s = __expf(L);
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(s));
-    const float s2n = s * s;
-    q = fmaf(cq, s2 + s2n, q);
-    s2 = s2n;
+    A = fmaf(s, s, A);
   }
   __device__ __forceinline__ float sigma() const { return s; }
+  __device__ __forceinline__ float x() const { return fmaf(ce, XM, fmaf(cx, (s2_first - s * s) + A, x0)); }
+  __device__ __forceinline__ float q() const { return fmaf(cq, (s2_first - s * s) + 2.0f * A, q0); }
 };
 
 template <typename Real>
 struct HestonPath {
-  Real x, v, q;
+  Real v, V, XM, x0, q0;
   Real hx, sdt, dt, kdt, theta, c0, c1;
   __device__ __forceinline__ HestonPath(const HestonConsts& c)
       : hx((Real)c.hx), sdt((Real)c.sdt), dt((Real)c.dt), kdt((Real)c.kdt), theta((Real)c.theta), c0((Real)c.c0), c1((Real)c.c1) {}
-  __device__ __forceinline__ void load(Real x0, Real v0, Real q0) {
-    x = x0;
-    v = v0;
-    q = q0;
+  __device__ __forceinline__ void load(Real x_, Real v_, Real q_) {
+    x0 = x_;
+    v = v_;
+    q0 = q_;
+    V = (Real)0;
+    XM = (Real)0;
   }
-  // pricers/heston_pricer.py:372-379 (floor-Euler): everything on the OLD variance, then v = max(v, 1e-4)
+  // pricers/heston_pricer.py:372-379 (floor-Euler): everything on the OLD variance, then v = max(v, 1e-4).
+  // V = sum v_k, XM = sum sqrt(v_k) z0_k  =>  x_S = x_0 - 0.5*dt*V + sqrt(dt)*XM,  q_S = q_0 + dt*V.
   __device__ __forceinline__ void step(Real z0, Real z1) {
     const Real sig = sqrt(v);
-    x = fma(hx, v, x);
-    x = fma(sig * sdt, z0, x);
-    q = fma(dt, v, q);
+    V += v;
+    XM = fma(sig, z0, XM);
     Real vn = fma(kdt, theta - v, v);
     vn = fma(sig, fma(c0, z0, c1 * z1), vn);
-    v = vn > (Real)1e-4 ? vn : (Real)1e-4;     // np.maximum(var0, 1e-4); NaN-propagating like numpy is moot: no NaN can arise
+    v = vn > (Real)1e-4 ? vn : (Real)1e-4;     // np.maximum(var0, 1e-4)
   }
   __device__ __forceinline__ Real sigma() const { return v; }
+  __device__ __forceinline__ Real x() const { return fma(sdt, XM, fma(hx, V, x0)); }
+  __device__ __forceinline__ Real q() const { return fma(dt, V, q0); }
 };
 
 // --------------------------------------------------------------------------------------------------------------------
@@ -201,7 +212,7 @@ struct SliceArgs {
 };
 
 template <typename Path, typename Consts, typename Real, bool GAUSS64>
-__global__ void __launch_bounds__(kThreads) mc_slice_kernel(SliceArgs<Real> a, Consts consts) {
+__global__ void __launch_bounds__(kThreads, B200SV_SLICE_MINBLOCKS) mc_slice_kernel(SliceArgs<Real> a, Consts consts) {
   __shared__ double red[2 * kThreads / 32];
   double acc[2] = {0.0, 0.0};
   Path p(consts);
@@ -219,24 +230,29 @@ __global__ void __launch_bounds__(kThreads) mc_slice_kernel(SliceArgs<Real> a, C
         p.step(z0, z1);
       }
     } else {
+      // one Philox call feeds two steps; the NEXT call is issued before the two fp64 steps of the current one so the
+      // integer / SFU stream of the generator overlaps the fp64 stream of the recursion inside a warp
       const int ncalls = a.nsteps >> 1;
+      Real n0, n1, n2, n3;
+      rng.get2(0u, n0, n1, n2, n3);
       for (int c = 0; c < ncalls; ++c) {
-        Real a0, a1, b0, b1;
-        rng.get2((uint32_t)c, a0, a1, b0, b1);
-        p.step(a0, a1);
-        p.step(b0, b1);
+        Real m0, m1, m2, m3;
+        rng.get2((uint32_t)(c + 1), m0, m1, m2, m3);
+        p.step(n0, n1);
+        p.step(n2, n3);
+        n0 = m0;
+        n1 = m1;
+        n2 = m2;
+        n3 = m3;
       }
-      if (a.nsteps & 1) {
-        Real a0, a1, b0, b1;
-        rng.get2((uint32_t)ncalls, a0, a1, b0, b1);
-        p.step(a0, a1);
-      }
+      if (a.nsteps & 1) p.step(n0, n1);
     }
-    a.x[i] = p.x;
+    const Real xT = p.x();
+    a.x[i] = xT;
     a.v[i] = p.sigma();
-    a.q[i] = p.q;
+    a.q[i] = p.q();
     // spots_t = forward*np.exp(x0); nanmean over all paths (utils/mc_payoffs.py:61-62)
-    const double spot = a.forward * exp((double)p.x);
+    const double spot = a.forward * exp((double)xT);
     if (spot == spot) {
       acc[0] += spot;
       acc[1] += 1.0;
@@ -350,6 +366,7 @@ __global__ void __launch_bounds__(kThreads) spot_moments_kernel(const double* __
 // --------------------------------------------------------------------------------------------------------------------
 // payoff sums: utils/mc_payoffs.py:61-88
 // --------------------------------------------------------------------------------------------------------------------
+// General kernel (any mix of C / P / IC / IP): per-strike NaN-skipping counts, IEEE division for the inverse payoffs.
 template <typename Real>
 __global__ void __launch_bounds__(kThreads) payoff_kernel(const Real* __restrict__ x, const Real* __restrict__ q, long long n,
                                                          double ttm, double forward, const double* __restrict__ strikes,
@@ -368,14 +385,14 @@ __global__ void __launch_bounds__(kThreads) payoff_kernel(const Real* __restrict
   }
   // correnction = np.nanmean(spots_t) - forward
   const double corr = moments[0] / moments[1] - forward;
-  const double inv_ttm_is_qvar = variable_type == B200SV_Q_VAR ? 1.0 : 0.0;
+  const bool is_qvar = variable_type == B200SV_Q_VAR;
   double acc[3 * kStrikeChunk];
 #pragma unroll
   for (int c = 0; c < 3 * kStrikeChunk; ++c) acc[c] = 0.0;
   const long long stride = (long long)gridDim.x * kThreads;
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
     const double spot = forward * exp((double)x[i]) - corr;
-    const double under = inv_ttm_is_qvar != 0.0 ? (double)q[i] / ttm : spot;
+    const double under = is_qvar ? (double)q[i] / ttm : spot;
 #pragma unroll
     for (int c = 0; c < kStrikeChunk; ++c) {
       if (ty[c] >= 0) {
@@ -395,6 +412,73 @@ __global__ void __launch_bounds__(kThreads) payoff_kernel(const Real* __restrict
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int c = 0; c < 3 * kStrikeChunk; ++c) partials[(size_t)blockIdx.x * Kpad + 3 * j0 + c] = acc[c];
+  }
+}
+
+// Vanilla-only kernel ('C' / 'P' in every slot of the slice): pay = max(+-(U - K), 0) is never NaN (numpy's
+// where(greater(nan, K), ., 0.0) is 0.0 as well), so every path counts and the count is simply n; no division, no branches.
+// ~6 instructions per (path, strike) + one exp per (path, chunk); kPayoffUnroll loads in flight per thread.
+constexpr int kPayoffUnroll = 4;
+template <typename Real>
+__global__ void __launch_bounds__(kThreads) payoff_vanilla_kernel(const Real* __restrict__ x, const Real* __restrict__ q, long long n,
+                                                                 double ttm, double forward, const double* __restrict__ strikes,
+                                                                 const int8_t* __restrict__ types, int J, int variable_type,
+                                                                 const double* __restrict__ moments, double* __restrict__ partials,
+                                                                 int Kpad) {
+  __shared__ double red[2 * kStrikeChunk * kThreads / 32];
+  const int j0 = blockIdx.y * kStrikeChunk;
+  double sg[kStrikeChunk], nk[kStrikeChunk];      // pay = max(sg*U + nk, 0), nk = -sg*K
+#pragma unroll
+  for (int c = 0; c < kStrikeChunk; ++c) {
+    const int j = j0 + c;
+    const double sgn = (j < J && (types[j] & 1)) ? -1.0 : 1.0;
+    sg[c] = sgn;
+    nk[c] = j < J ? -sgn * strikes[j] : -INFINITY;   // unused slot: max(U - inf, 0) = 0
+  }
+  const double corr = moments[0] / moments[1] - forward;
+  const bool is_qvar = variable_type == B200SV_Q_VAR;
+  const double inv_ttm = 1.0 / ttm;
+  double acc[2 * kStrikeChunk];
+#pragma unroll
+  for (int c = 0; c < 2 * kStrikeChunk; ++c) acc[c] = 0.0;
+  auto accumulate = [&](double under) {
+#pragma unroll
+    for (int c = 0; c < kStrikeChunk; ++c) {
+      const double d = fma(sg[c], under, nk[c]);
+      const double pay = d > 0.0 ? d : 0.0;
+      acc[2 * c] += pay;
+      acc[2 * c + 1] = fma(pay, pay, acc[2 * c + 1]);
+    }
+  };
+  const long long stride = (long long)gridDim.x * kThreads;
+  long long i = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (!is_qvar) {
+    for (; i + (kPayoffUnroll - 1) * stride < n; i += kPayoffUnroll * stride) {
+      double xs[kPayoffUnroll];
+#pragma unroll
+      for (int u = 0; u < kPayoffUnroll; ++u) xs[u] = (double)x[i + u * stride];
+#pragma unroll
+      for (int u = 0; u < kPayoffUnroll; ++u) accumulate(forward * exp(xs[u]) - corr);
+    }
+    for (; i < n; i += stride) accumulate(forward * exp((double)x[i]) - corr);
+  } else {
+    for (; i < n; i += stride) accumulate((double)q[i] * inv_ttm);
+  }
+  block_sum<2 * kStrikeChunk, kThreads>(acc, red);
+  if (threadIdx.x == 0) {
+    // count of paths this CTA visited (same for every strike)
+    const long long first = (long long)blockIdx.x * kThreads;
+    long long cnt = 0;
+    if (first < n) {
+      const long long full_rounds = (n - first) / stride, rem = (n - first) % stride;
+      cnt = full_rounds * kThreads + (rem < kThreads ? rem : kThreads);
+    }
+#pragma unroll
+    for (int c = 0; c < kStrikeChunk; ++c) {
+      partials[(size_t)blockIdx.x * Kpad + 3 * (j0 + c) + 0] = acc[2 * c];
+      partials[(size_t)blockIdx.x * Kpad + 3 * (j0 + c) + 1] = acc[2 * c + 1];
+      partials[(size_t)blockIdx.x * Kpad + 3 * (j0 + c) + 2] = (double)cnt;
+    }
   }
 }
 
@@ -453,6 +537,20 @@ __global__ void exp_pair_kernel(const double* __restrict__ L, long long n, doubl
 // --------------------------------------------------------------------------------------------------------------------
 // host side
 // --------------------------------------------------------------------------------------------------------------------
+// cudaMallocAsync returns freed blocks to the OS at the next synchronisation unless the pool's release threshold is raised;
+// the chain entry points allocate GBs of path state per call, so keep it cached (set once per device).
+static void ensure_pool_threshold() {
+  static thread_local int done_for = -1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev == done_for) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long thr = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  done_for = dev;
+}
+
 static int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(-2, std::string(what) + ": " + cudaGetErrorString(e));
@@ -512,23 +610,35 @@ static int launch_slice(void* x, void* v, void* q, long long n, long long path_o
   return launch_slice_t<MODEL, float, true>(x, v, q, n, path_offset, init, v_init, nsteps, slice_index, forward, seed, lc, hc, moments_out, st);
 }
 
+// kinds: bit 0 = some 'C'/'P', bit 1 = some 'IC'/'IP' in this slice; 0 = unknown (device-level callers) -> general kernel
 template <typename Real>
 static int launch_payoff_t(const void* x, const void* q, long long n, double ttm, double forward, const double* strikes,
-                           const int8_t* types, int J, int variable_type, const double* moments, double* sums_out,
+                           const int8_t* types, int J, int variable_type, int kinds, const double* moments, double* sums_out,
                            cudaStream_t st) {
   const int chunks = (J + kStrikeChunk - 1) / kStrikeChunk;
   const int Kpad = 3 * kStrikeChunk * chunks;
-  Grid g = persistent_grid(payoff_kernel<Real>, kThreads, n);
+  const bool vanilla = kinds == 1;
+  Grid g = vanilla ? persistent_grid(payoff_vanilla_kernel<Real>, kThreads, n, kPayoffUnroll) : persistent_grid(payoff_kernel<Real>, kThreads, n);
   g.blocks = std::max(1, g.blocks / chunks);
   double* partials = nullptr;
   B200SV_CUDA(cudaMallocAsync(&partials, sizeof(double) * (size_t)Kpad * g.blocks, st));
-  payoff_kernel<Real><<<dim3(g.blocks, chunks), g.threads, 0, st>>>((const Real*)x, (const Real*)q, n, ttm, forward, strikes,
-                                                                      types, J, variable_type, moments, partials, Kpad);
+  if (vanilla)
+    payoff_vanilla_kernel<Real><<<dim3(g.blocks, chunks), g.threads, 0, st>>>((const Real*)x, (const Real*)q, n, ttm, forward, strikes,
+                                                                                types, J, variable_type, moments, partials, Kpad);
+  else
+    payoff_kernel<Real><<<dim3(g.blocks, chunks), g.threads, 0, st>>>((const Real*)x, (const Real*)q, n, ttm, forward, strikes,
+                                                                        types, J, variable_type, moments, partials, Kpad);
   if (int rc = check_launch("payoff_kernel")) return rc;
   reduce_partials_kernel<<<1, 256, 0, st>>>(partials, g.blocks, Kpad, 3 * J, sums_out);
   if (int rc = check_launch("reduce_partials_kernel")) return rc;
   B200SV_CUDA(cudaFreeAsync(partials, st));
   return 0;
+}
+
+static int payoff_kinds(const int8_t* types, int J) {
+  int k = 0;
+  for (int j = 0; j < J; ++j) k |= (types[j] >= 2) ? 2 : 1;
+  return k;
 }
 
 static int validate_chain(int M, const double* ttms, const int* offsets, const int8_t* types, int variable_type) {
@@ -558,6 +668,7 @@ static int mc_chain_host(const b200sv_logsv_params* lp, const b200sv_heston_para
   const int Jtot = offsets[M] - offsets[0];
   const size_t esz = (flags & B200SV_STATE_F32) ? 4 : 8;
   cudaStream_t st = 0;
+  ensure_pool_threshold();
   char *x = nullptr;
   double *d_strikes = nullptr, *d_out = nullptr, *d_mom = nullptr, *d_sums = nullptr;
   int8_t* d_types = nullptr;
@@ -591,9 +702,9 @@ static int mc_chain_host(const b200sv_logsv_params* lp, const b200sv_heston_para
     const int J = offsets[m + 1] - offsets[m], jo = offsets[m] - offsets[0];
     if (J == 0) continue;
     if (flags & B200SV_STATE_F32)
-      rc = launch_payoff_t<float>(x, q, nb_path, ttms[m], forwards[m], d_strikes + jo, d_types + jo, J, variable_type, d_mom, d_sums, st);
+      rc = launch_payoff_t<float>(x, q, nb_path, ttms[m], forwards[m], d_strikes + jo, d_types + jo, J, variable_type, payoff_kinds(types + offsets[m], J), d_mom, d_sums, st);
     else
-      rc = launch_payoff_t<double>(x, q, nb_path, ttms[m], forwards[m], d_strikes + jo, d_types + jo, J, variable_type, d_mom, d_sums, st);
+      rc = launch_payoff_t<double>(x, q, nb_path, ttms[m], forwards[m], d_strikes + jo, d_types + jo, J, variable_type, payoff_kinds(types + offsets[m], J), d_mom, d_sums, st);
     if (rc) break;
     payoff_finalize_kernel<<<(J + 127) / 128, 128, 0, st>>>(d_sums, J, discfactors[m], (double)nb_path, d_out + jo, d_out + Jalloc + jo);
     rc = check_launch("payoff_finalize_kernel");
@@ -620,6 +731,7 @@ static int terminal_host(const b200sv_logsv_params* lp, const b200sv_heston_para
   B200SV_REQUIRE(nb_path >= 1 && ttm > 0.0 && nb_steps_per_year >= 1, "nb_path, ttm, nb_steps_per_year must be positive");
   B200SV_REQUIRE(!(flags & B200SV_STATE_F32), "terminal values are returned as float64: use B200SV_STATE_F64");
   cudaStream_t st = 0;
+  ensure_pool_threshold();
   double *d = nullptr, *d_mom = nullptr;
   B200SV_CUDA(cudaMallocAsync(&d, sizeof(double) * 3 * (size_t)nb_path, st));
   B200SV_CUDA(cudaMallocAsync(&d_mom, sizeof(double) * 2, st));
@@ -716,15 +828,15 @@ int b200sv_dev_heston_slice(void* x, void* var, void* qvar, long long n_local, l
 }
 
 int b200sv_dev_payoff_sums(const void* x, const void* qvar, long long n_local, int flags, double ttm, double forward,
-                           const double* strikes, const int8_t* types, int J, int variable_type, const double* moments,
-                           double* sums_out, void* stream) {
+                           const double* strikes, const int8_t* types, int J, int variable_type, int payoff_kinds_hint,
+                           const double* moments, double* sums_out, void* stream) {
   B200SV_REQUIRE(x && strikes && types && moments && sums_out, "null pointer");
   B200SV_REQUIRE(J >= 1 && n_local >= 1, "J and n_local must be >= 1");
   if (variable_type != B200SV_LOG_RETURN && variable_type != B200SV_Q_VAR) return fail(-4, "variable_type not implemented");
   B200SV_REQUIRE(variable_type == B200SV_LOG_RETURN || qvar, "qvar required for Q_VAR");
   if (flags & B200SV_STATE_F32)
-    return launch_payoff_t<float>(x, qvar ? qvar : x, n_local, ttm, forward, strikes, types, J, variable_type, moments, sums_out, (cudaStream_t)stream);
-  return launch_payoff_t<double>(x, qvar ? qvar : x, n_local, ttm, forward, strikes, types, J, variable_type, moments, sums_out, (cudaStream_t)stream);
+    return launch_payoff_t<float>(x, qvar ? qvar : x, n_local, ttm, forward, strikes, types, J, variable_type, payoff_kinds_hint, moments, sums_out, (cudaStream_t)stream);
+  return launch_payoff_t<double>(x, qvar ? qvar : x, n_local, ttm, forward, strikes, types, J, variable_type, payoff_kinds_hint, moments, sums_out, (cudaStream_t)stream);
 }
 
 int b200sv_dev_payoff_finalize(const double* sums, int J, double discfactor, long long total_paths, double* prices_out,
@@ -835,7 +947,7 @@ int b200sv_mc_payoffs(const double* x, const double* qvar, long long N, double t
   B200SV_CUDA(cudaMemcpyAsync(dk, strikes, sizeof(double) * J, cudaMemcpyHostToDevice, st));
   B200SV_CUDA(cudaMemcpyAsync(dt_, types, J, cudaMemcpyHostToDevice, st));
   int rc = b200sv_dev_spot_moments(d, N, forward, d_mom, st);
-  if (rc == 0) rc = launch_payoff_t<double>(d, d + N, N, ttm, forward, dk, dt_, J, variable_type, d_mom, d_sums, st);
+  if (rc == 0) rc = launch_payoff_t<double>(d, d + N, N, ttm, forward, dk, dt_, J, variable_type, payoff_kinds(types, J), d_mom, d_sums, st);
   if (rc == 0) rc = b200sv_dev_payoff_finalize(d_sums, J, discfactor, N, d_out, d_out + J, st);
   if (rc == 0) {
     cudaError_t e = cudaMemcpyAsync(prices_out, d_out, sizeof(double) * J, cudaMemcpyDeviceToHost, st);

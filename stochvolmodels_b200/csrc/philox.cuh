@@ -19,13 +19,19 @@
 
 namespace b200sv {
 
+__device__ __forceinline__ void mulhilo32(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+  // one IMAD.WIDE.U32; written in PTX so the 64-bit product is split without zero-extension adds
+  asm("{\n\t.reg .u64 p;\n\tmul.wide.u32 p, %2, %3;\n\tmov.b64 {%1, %0}, p;\n\t}" : "=r"(hi), "=r"(lo) : "r"(a), "r"(b));
+}
+
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
-    const uint64_t p0 = (uint64_t)M0 * c.x;   // IMAD.WIDE.U32
-    const uint64_t p1 = (uint64_t)M1 * c.z;
-    c = make_uint4((uint32_t)(p1 >> 32) ^ c.y ^ k.x, (uint32_t)p1, (uint32_t)(p0 >> 32) ^ c.w ^ k.y, (uint32_t)p0);
+    uint32_t hi0, lo0, hi1, lo1;
+    mulhilo32(M0, c.x, hi0, lo0);
+    mulhilo32(M1, c.z, hi1, lo1);
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
     k.x += W0;
     k.y += W1;
   }
@@ -34,12 +40,14 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 
 // ---- float Box-Muller on the SFU -------------------------------------------------------------------
 __device__ __forceinline__ void box_muller_f32(uint32_t ra, uint32_t rb, float& z0, float& z1) {
-  const float u1 = fmaf(__uint2float_rn(ra), 2.3283064365386963e-10f, 1.1641532182693481e-10f);  // (0, 1]
-  // R = sqrt(-2 ln u1) = sqrt(-2 ln2 * lg2(u1))
-  const float rad = sqrtf(-1.3862943611198906f * __log2f(u1));
+  const float u1 = fmaf(__uint2float_rn(ra), 2.3283064365386963e-10f, 1.1641532182693481e-10f);  // (0, 1], >= 2^-33: never denormal
+  float lg, rad;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(u1));                                       // MUFU.LG2
+  // R = sqrt(-2 ln u1) = sqrt(-2 ln2 * lg2(u1));  MUFU.SQRT(0) = 0 (u1 == 1)
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(-1.3862943611198906f * lg));
   const float ang = __int2float_rn((int32_t)rb) * 1.4629180792671596e-09f;                        // pi * 2^-31 => [-pi, pi]
   float s, c;
-  __sincosf(ang, &s, &c);
+  __sincosf(ang, &s, &c);                                                                         // MUFU.SIN / MUFU.COS
   z0 = rad * c;
   z1 = rad * s;
 }

@@ -70,7 +70,7 @@ class CudaMcEngine:
                    c_void_p(self.moments.data_ptr()), self._stream())
         return self.moments
 
-    def payoff_sums(self, ttm: float, forward: float, strikes_dev, types_dev, J: int, variable_type: int):
+    def payoff_sums(self, ttm: float, forward: float, strikes_dev, types_dev, J: int, variable_type: int, kinds: int = 0):
         """LOCAL per-strike (sum, sum^2, count) given the GLOBAL moments in ``self.moments``; returns a view of 3*J doubles."""
         sums = self.sums[: 3 * J]
         if self.n_local == 0:
@@ -78,7 +78,7 @@ class CudaMcEngine:
             return sums
         C.call("b200sv_dev_payoff_sums", c_void_p(self.state[0].data_ptr()), c_void_p(self.state[2].data_ptr()), self.n_local,
                self.flags, float(ttm), float(forward), c_void_p(strikes_dev.data_ptr()), c_void_p(types_dev.data_ptr()), int(J),
-               int(variable_type), c_void_p(self.moments.data_ptr()), c_void_p(sums.data_ptr()), self._stream())
+               int(variable_type), int(kinds), c_void_p(self.moments.data_ptr()), c_void_p(sums.data_ptr()), self._stream())
         return sums
 
     def finalize(self, sums, J: int, discfactor: float, total_paths: int):
@@ -127,7 +127,8 @@ def mc_chain_distributed(model: str, params_c, ttms, forwards, discfactors, etas
             results.append((None, None))
             continue
         jo = int(offsets[m])
-        sums = eng.payoff_sums(float(ttms[m]), float(forwards[m]), strikes_dev[jo: jo + J], types_dev[jo: jo + J], J, variable_type)
+        kinds = int(np.bitwise_or.reduce(np.where(types[jo: jo + J] >= 2, 2, 1)))
+        sums = eng.payoff_sums(float(ttms[m]), float(forwards[m]), strikes_dev[jo: jo + J], types_dev[jo: jo + J], J, variable_type, kinds)
         if world > 1:
             dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)                 # exchange (2): 24*J bytes
         prices, stds = eng.finalize(sums, J, float(discfactors[m]), int(nb_path))

@@ -286,5 +286,83 @@ def main() -> None:
     print("golden fixtures written to", OUT)
 
 
+def reference_mc():
+    """Large-N Monte Carlo prices from the REFERENCE's own Numba stepper + payoff code (seeded through its ``set_seed``):
+    the statistical anchor for the GPU Philox path ("within 3 MC standard errors of the reference Numba CPU path").
+    The Euler scheme carries a discretisation bias against the Fourier price that is visible at these path counts
+    (|z| ~ 4 at 2e6 paths with ANY generator), so MC-vs-MC is the meaningful 3-SE comparison.
+    Paths are simulated in chunks (the reference materialises W0/W1[steps, paths]) and the payoffs are taken once on the
+    concatenated terminal states, so the forward re-centring is global exactly as in one big call."""
+    _import_reference()
+    import scipy
+    import numba
+    from stochvolmodels.pricers import logsv_pricer as lp
+    from stochvolmodels.pricers import heston_pricer as hp
+    from stochvolmodels.utils import mc_payoffs as mcp
+    from stochvolmodels.utils.funcs import set_seed
+    from stochvolmodels.data.sample_option_chains import get_btc_test_chain_data
+    versions = np.array([f"numpy={np.__version__}", f"scipy={scipy.__version__}", f"numba={numba.__version__}"])
+    K5 = np.array([0.8, 0.9, 1.0, 1.1, 1.2])
+    T5 = np.array(['P', 'P', 'C', 'C', 'C'])
+
+    def logsv_case(tag, p6, ttms, forwards, discfactors, strikes_ttms, types_ttms, n_per_year, nb_path, chunk, seed):
+        set_seed(seed)
+        M = len(ttms)
+        xs = [[] for _ in range(M)]
+        qs = [[] for _ in range(M)]
+        for c in range(nb_path // chunk):
+            x = np.zeros(chunk); q = np.zeros(chunk); s = p6[0] * np.ones(chunk); t0 = 0.0
+            for m, ttm in enumerate(ttms):
+                x, s, q = lp.simulate_logsv_x_vol_terminal(ttm=ttm - t0, x0=x, sigma0=s, qvar0=q, theta=p6[1], kappa1=p6[2], kappa2=p6[3],
+                                                           beta=p6[4], volvol=p6[5], nb_path=chunk, nb_steps_per_year=n_per_year)
+                t0 = ttm
+                xs[m].append(x.copy()); qs[m].append(q.copy())
+        out = dict(params=np.array(p6), ttms=ttms, forwards=forwards, discfactors=discfactors, n_per_year=np.array(n_per_year),
+                   nb_path=np.array(nb_path), seed=np.array(seed), nslices=np.array(M))
+        for m in range(M):
+            x, q = np.concatenate(xs[m]), np.concatenate(qs[m])
+            pr, se = mcp.compute_mc_vars_payoff(x0=x, sigma0=x, qvar0=q, ttm=ttms[m], forward=forwards[m], strikes_ttm=strikes_ttms[m],
+                                                optiontypes_ttm=types_ttms[m], discfactor=discfactors[m])
+            out[f"strikes_{m}"], out[f"types_{m}"], out[f"prices_{m}"], out[f"stderr_{m}"] = strikes_ttms[m], types_ttms[m], pr, se
+            out[f"mean_exp_x_{m}"] = np.array(np.mean(np.exp(x)))
+            out[f"mean_qvar_{m}"] = np.array(np.mean(q))
+            print("refmc", tag, m, pr[:3], se[:3])
+        np.savez(os.path.join(OUT, f"refmc_logsv_{tag}.npz"), versions=versions, **out)
+
+    which = [a.split("=")[1] for a in sys.argv if a.startswith("--case=")]
+    if not which or "quickstart" in which:
+        logsv_case("quickstart", (1.0, 1.0, 5.0, 5.0, 0.2, 2.0), np.array([0.25, 0.5]), np.ones(2), np.ones(2), (K5, K5), (T5, T5),
+                   252, 16_000_000, 500_000, 1234)
+    if not which or "btc" in which:
+        btc = get_btc_test_chain_data()
+        logsv_case("btc", (0.8376, 1.0413, 3.1844, 3.058, 0.1514, 1.8458), btc.ttms, btc.forwards, btc.discfactors,
+                   tuple(btc.strikes_ttms), tuple(btc.optiontypes_ttms), 252, 16_000_000, 500_000, 4321)
+    if which and "heston" not in which:
+        return
+
+    # Heston: reference stepper is hard-wired to 360 steps/yr
+    set_seed(99)
+    ttms = np.array([0.25, 1.0])
+    nb_path, chunk = 8_000_000, 250_000
+    xs = [[], []]
+    for c in range(nb_path // chunk):
+        x = np.zeros(chunk); q = np.zeros(chunk); v = 0.04 * np.ones(chunk); t0 = 0.0
+        for m, ttm in enumerate(ttms):
+            x, v, q = hp.simulate_heston_x_vol_terminal(ttm=ttm - t0, x0=x, var0=v, qvar0=q, theta=0.04, kappa=4.0, rho=-0.5, volvol=0.4,
+                                                        nb_path=chunk)
+            t0 = ttm
+            xs[m].append(x.copy())
+    out = dict(params=np.array([0.04, 0.04, 4.0, -0.5, 0.4]), ttms=ttms, nb_path=np.array(nb_path), nslices=np.array(2))
+    for m in range(2):
+        x = np.concatenate(xs[m])
+        pr, se = mcp.compute_mc_vars_payoff(x0=x, sigma0=x, qvar0=x, ttm=ttms[m], forward=1.0, strikes_ttm=K5, optiontypes_ttm=T5)
+        out[f"strikes_{m}"], out[f"types_{m}"], out[f"prices_{m}"], out[f"stderr_{m}"] = K5, T5, pr, se
+        print("refmc heston", m, pr, se)
+    np.savez(os.path.join(OUT, "refmc_heston_g4.npz"), versions=versions, **out)
+
+
 if __name__ == "__main__":
-    main()
+    if "--only-refmc" not in sys.argv:
+        main()
+    if "--skip-refmc" not in sys.argv:
+        reference_mc()
