@@ -19,6 +19,7 @@
 // All moment arithmetic is fp64 and every reduction has a fixed order => bitwise reproducible for a given launch shape.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "../../include/b200sv.h"
@@ -30,8 +31,15 @@ namespace b200sv {
 
 static thread_local long long g_launches = 0;
 constexpr int kThreads = 256;
+#ifndef B200SV_SLICE_PREFETCH
+#define B200SV_SLICE_PREFETCH 1     // issue the next Philox/Box-Muller call before the two fp64 steps of the current one
+#endif
+#ifndef B200SV_SLICE_THREADS
+#define B200SV_SLICE_THREADS 128
+#endif
+constexpr int kSliceThreads = B200SV_SLICE_THREADS;
 #ifndef B200SV_SLICE_MINBLOCKS
-#define B200SV_SLICE_MINBLOCKS 2   // resident CTAs / SM the slice kernel is register-budgeted for (tuned on B200, profiles/)
+#define B200SV_SLICE_MINBLOCKS 4   // resident CTAs / SM the slice kernel is register-budgeted for (tuned on B200, profiles/)
 #endif
 constexpr int kStrikeChunk = 8;
 
@@ -114,12 +122,15 @@ struct LogsvPath<double> {
     XM = 0.0;
   }
   __device__ __forceinline__ void step(double z0, double z1) {
+#if defined(B200SV_ABLATE) && (B200SV_ABLATE & 4)   // tuning only: no fp64 recursion, just consume the normals
+    XM = fma(z1, z0, XM);
+    return;
+#endif
     XM = fma(s, z0, XM);
-    double l = L + a0;
-    l = fma(a1, inv, l);
+    // noise + constant drift first (independent of sigma: off the critical path), then the two state-dependent terms
+    double l = L + fma(b0, z0, fma(b1, z1, a0));
     l = fma(a2, s, l);
-    l = fma(b0, z0, l);
-    l = fma(b1, z1, l);
+    l = fma(a1, inv, l);
     L = clamp_log(l);
     exp_pair(L, s, inv);
     A = fma(s, s, A);
@@ -149,11 +160,9 @@ struct LogsvPath<float> {
   }
   __device__ __forceinline__ void step(float z0, float z1) {
     XM = fmaf(s, z0, XM);
-    float l = L + a0;
-    l = fmaf(a1, inv, l);
+    float l = L + fmaf(b0, z0, fmaf(b1, z1, a0));
     l = fmaf(a2, s, l);
-    l = fmaf(b0, z0, l);
-    l = fmaf(b1, z1, l);
+    l = fmaf(a1, inv, l);
     L = fminf(fmaxf(l, -80.0f), 80.0f);
     s = __expf(L);
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(s));
@@ -212,12 +221,12 @@ struct SliceArgs {
 };
 
 template <typename Path, typename Consts, typename Real, bool GAUSS64>
-__global__ void __launch_bounds__(kThreads, B200SV_SLICE_MINBLOCKS) mc_slice_kernel(SliceArgs<Real> a, Consts consts) {
-  __shared__ double red[2 * kThreads / 32];
+__global__ void __launch_bounds__(kSliceThreads, B200SV_SLICE_MINBLOCKS) mc_slice_kernel(SliceArgs<Real> a, Consts consts) {
+  __shared__ double red[2 * kSliceThreads / 32];
   double acc[2] = {0.0, 0.0};
   Path p(consts);
-  const long long stride = (long long)gridDim.x * kThreads;
-  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < a.n; i += stride) {
+  const long long stride = (long long)gridDim.x * kSliceThreads;
+  for (long long i = (long long)blockIdx.x * kSliceThreads + threadIdx.x; i < a.n; i += stride) {
     if (a.init)
       p.load((Real)0, (Real)a.v_init, (Real)0);
     else
@@ -233,6 +242,7 @@ __global__ void __launch_bounds__(kThreads, B200SV_SLICE_MINBLOCKS) mc_slice_ker
       // one Philox call feeds two steps; the NEXT call is issued before the two fp64 steps of the current one so the
       // integer / SFU stream of the generator overlaps the fp64 stream of the recursion inside a warp
       const int ncalls = a.nsteps >> 1;
+#if B200SV_SLICE_PREFETCH
       Real n0, n1, n2, n3;
       rng.get2(0u, n0, n1, n2, n3);
       for (int c = 0; c < ncalls; ++c) {
@@ -246,6 +256,19 @@ __global__ void __launch_bounds__(kThreads, B200SV_SLICE_MINBLOCKS) mc_slice_ker
         n3 = m3;
       }
       if (a.nsteps & 1) p.step(n0, n1);
+#else
+      for (int c = 0; c < ncalls; ++c) {
+        Real n0, n1, n2, n3;
+        rng.get2((uint32_t)c, n0, n1, n2, n3);
+        p.step(n0, n1);
+        p.step(n2, n3);
+      }
+      if (a.nsteps & 1) {
+        Real n0, n1, n2, n3;
+        rng.get2((uint32_t)ncalls, n0, n1, n2, n3);
+        p.step(n0, n1);
+      }
+#endif
     }
     const Real xT = p.x();
     a.x[i] = xT;
@@ -258,7 +281,7 @@ __global__ void __launch_bounds__(kThreads, B200SV_SLICE_MINBLOCKS) mc_slice_ker
       acc[1] += 1.0;
     }
   }
-  block_sum<2, kThreads>(acc, red);
+  block_sum<2, kSliceThreads>(acc, red);
   if (threadIdx.x == 0) {
     a.partials[2 * blockIdx.x + 0] = acc[0];
     a.partials[2 * blockIdx.x + 1] = acc[1];
@@ -582,16 +605,30 @@ static int launch_slice_t(void* x, void* v, void* q, long long n, long long path
   a.forward = forward;
   Grid g;
   if constexpr (MODEL == 0)
-    g = persistent_grid(mc_slice_kernel<LogsvPath<Real>, LogsvConsts, Real, G64>, kThreads, n);
+    g = persistent_grid(mc_slice_kernel<LogsvPath<Real>, LogsvConsts, Real, G64>, kSliceThreads, n);
   else
-    g = persistent_grid(mc_slice_kernel<HestonPath<Real>, HestonConsts, Real, G64>, kThreads, n);
+    g = persistent_grid(mc_slice_kernel<HestonPath<Real>, HestonConsts, Real, G64>, kSliceThreads, n);
+  size_t dyn_smem = 0;
+#ifdef B200SV_TUNING   // occupancy sweep for profiles/: cap resident CTAs per SM with dynamic shared memory (tuning builds only)
+  if (const char* e = getenv("B200SV_DEBUG_BLOCKS_PER_SM")) {
+    const int bps = atoi(e);
+    if (bps > 0) {
+      dyn_smem = (size_t)(200 * 1024) / bps;
+      if constexpr (MODEL == 0)
+        cudaFuncSetAttribute(mc_slice_kernel<LogsvPath<Real>, LogsvConsts, Real, G64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
+      else
+        cudaFuncSetAttribute(mc_slice_kernel<HestonPath<Real>, HestonConsts, Real, G64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
+      g.blocks = (int)std::min<long long>((long long)148 * bps, (n + kSliceThreads - 1) / kSliceThreads);
+    }
+  }
+#endif
   double* partials = nullptr;
   B200SV_CUDA(cudaMallocAsync(&partials, sizeof(double) * 2 * g.blocks, st));
   a.partials = partials;
   if constexpr (MODEL == 0)
-    mc_slice_kernel<LogsvPath<Real>, LogsvConsts, Real, G64><<<g.blocks, g.threads, 0, st>>>(a, *lc);
+    mc_slice_kernel<LogsvPath<Real>, LogsvConsts, Real, G64><<<g.blocks, g.threads, dyn_smem, st>>>(a, *lc);
   else
-    mc_slice_kernel<HestonPath<Real>, HestonConsts, Real, G64><<<g.blocks, g.threads, 0, st>>>(a, *hc);
+    mc_slice_kernel<HestonPath<Real>, HestonConsts, Real, G64><<<g.blocks, g.threads, dyn_smem, st>>>(a, *hc);
   if (int rc = check_launch("mc_slice_kernel")) return rc;
   reduce_partials_kernel<<<1, 64, 0, st>>>(partials, g.blocks, 2, 2, moments_out);
   if (int rc = check_launch("reduce_partials_kernel")) return rc;

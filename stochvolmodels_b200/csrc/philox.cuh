@@ -93,10 +93,19 @@ struct StepNormals<Real, false> {
       : key(make_uint2((uint32_t)seed, (uint32_t)(seed >> 32))), plo((uint32_t)path), phi((uint32_t)(path >> 32)), slice(slice_) {}
   // two consecutive steps (2*call, 2*call+1) from one Philox call
   __device__ __forceinline__ void get2(uint32_t call, Real& a0, Real& a1, Real& b0, Real& b1) {
+#if defined(B200SV_ABLATE) && (B200SV_ABLATE & 1)   // tuning only: replace Philox by a trivial mix (NOT a valid generator)
+    uint4 r = make_uint4(plo * 0x9E3779B9u + call, phi ^ (call * 0x85EBCA6Bu), plo ^ (call * 0xC2B2AE35u), slice + call * 0x27D4EB2Fu);
+#else
     const uint4 r = philox4x32_10(make_uint4(plo, phi, call, slice), key);
+#endif
     float x0, x1, y0, y1;
+#if defined(B200SV_ABLATE) && (B200SV_ABLATE & 2)   // tuning only: no SFU, uniforms scaled to [-1.7, 1.7] (NOT normal)
+    x0 = __int2float_rn((int)r.x) * 8e-10f; x1 = __int2float_rn((int)r.y) * 8e-10f;
+    y0 = __int2float_rn((int)r.z) * 8e-10f; y1 = __int2float_rn((int)r.w) * 8e-10f;
+#else
     box_muller_f32(r.x, r.y, x0, x1);
     box_muller_f32(r.z, r.w, y0, y1);
+#endif
     a0 = (Real)x0;
     a1 = (Real)x1;
     b0 = (Real)y0;

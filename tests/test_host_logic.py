@@ -1,0 +1,150 @@
+"""CPU: host-side logic of the boundary (no GPU): time grid rule, chain flattening, validation and error conventions,
+default-step quirks, Black implied vols, path sharding."""
+import inspect
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+
+def test_set_time_grid_matches_reference_rule():
+    from stochvolmodels_b200.utils.funcs import set_time_grid
+    for ttm, n, S, dt in load_golden("time_grid.npz")["cases"]:
+        s2, dt2, grid = set_time_grid(ttm, int(n))
+        assert s2 == int(S) and dt2 == dt and grid.shape == (s2 + 1,)
+
+
+def test_flatten_chain_and_type_codes():
+    from stochvolmodels_b200 import _capi as C
+    off, k, t = C.flatten_chain([np.array([1.0, 2.0]), np.array([3.0])], [np.array(["C", "IP"]), np.array(["P"])])
+    assert off.tolist() == [0, 2, 3] and k.tolist() == [1.0, 2.0, 3.0] and t.tolist() == [C.CALL, C.INV_PUT, C.PUT]
+    assert t.dtype == np.int8 and off.dtype == np.int32
+    with pytest.raises(ValueError, match="payoff"):
+        C.encode_types(np.array(["X"]))
+    assert [a.tolist() for a in C.split_chain(np.arange(3.0), off)] == [[0.0, 1.0], [2.0]]
+
+
+def test_option_chain_validation_rules():
+    from stochvolmodels_b200 import OptionChain
+    K, T = np.array([0.9, 1.1]), np.array(["P", "C"])
+    ok = OptionChain(ttms=np.array([0.1, 0.2]), forwards=np.ones(2), strikes_ttms=[K, K], optiontypes_ttms=[T, T])
+    assert np.all(ok.discfactors == 1.0) and np.all(ok.discount_rates == 0.0)
+    with pytest.raises(ValueError, match="strictly increasing"):
+        OptionChain(ttms=np.array([0.2, 0.1]), forwards=np.ones(2), strikes_ttms=[K, K], optiontypes_ttms=[T, T])
+    with pytest.raises(ValueError, match="positive"):
+        OptionChain(ttms=np.array([0.1]), forwards=np.ones(1), strikes_ttms=[np.array([-1.0, 1.0])], optiontypes_ttms=[T])
+    with pytest.raises(ValueError, match="optiontypes"):
+        OptionChain(ttms=np.array([0.1]), forwards=np.ones(1), strikes_ttms=[K], optiontypes_ttms=[np.array(["P", "Z"])])
+    with pytest.raises(ValueError, match="same length"):
+        OptionChain(ttms=np.array([0.1, 0.2]), forwards=np.ones(2), strikes_ttms=[K], optiontypes_ttms=[T])
+    u = OptionChain.get_uniform_chain(ttms=np.array([0.25, 0.5]), ids=np.array(["3m", "6m"]), forwards=np.array([1.0, 1.0]),
+                                      strikes=np.array([0.8, 0.9, 1.0, 1.1, 1.2]))
+    assert u.optiontypes_ttms[0].tolist() == ["P", "P", "C", "C", "C"]          # np.where(K >= F, 'C', 'P'), option_chain.py:492
+    s = OptionChain.slice_to_chain(0.25, 1.0, K, T, discfactor=0.99)
+    assert s.ttms.tolist() == [0.25] and s.discfactors.tolist() == [0.99]
+
+
+def test_btc_chain_shape():
+    from stochvolmodels_b200 import get_btc_test_chain_data
+    c = get_btc_test_chain_data()
+    assert [len(k) for k in c.strikes_ttms] == [12, 13, 15, 9] and c.ttms.shape == (4,)
+    g = load_golden("logsv_fourier_btc.npz")
+    for m in range(4):
+        np.testing.assert_array_equal(c.strikes_ttms[m], g[f"strikes_{m}"])
+        np.testing.assert_array_equal(c.optiontypes_ttms[m], g[f"types_{m}"])
+    np.testing.assert_array_equal(c.ttms, g["ttms"])
+    np.testing.assert_array_equal(c.forwards, g["forwards"])
+
+
+def test_pricer_api_surface_matches_reference_signatures():
+    """names / defaults of the reference methods (pricers/logsv_pricer.py:345-377, 590-596; heston_pricer.py:52-96)."""
+    from stochvolmodels_b200 import HestonParams, HestonPricer, LogSvParams, LogSVPricer, ModelPricer, VariableType
+    assert issubclass(LogSVPricer, ModelPricer) and issubclass(HestonPricer, ModelPricer)
+    sig = inspect.signature(LogSVPricer.model_mc_price_chain)
+    assert sig.parameters["nb_path"].default == 100000 and sig.parameters["nb_steps"].default is None
+    assert sig.parameters["is_spot_measure"].default is True and sig.parameters["variable_type"].default == VariableType.LOG_RETURN
+    sig = inspect.signature(LogSVPricer.simulate_terminal_values)
+    assert sig.parameters["ttm"].default == 1.0 and sig.parameters["nb_path"].default == 100000
+    sig = inspect.signature(HestonPricer.model_mc_price_chain)
+    assert sig.parameters["nb_path"].default == 100000
+    for name in ("price_chain", "compute_chain_prices_with_vols", "compute_model_ivols_for_chain", "price_slice", "price_vanilla",
+                 "model_mc_price_chain", "simulate_terminal_values", "compute_mc_chain_implied_vols"):
+        assert callable(getattr(LogSVPricer, name)) and callable(getattr(HestonPricer, name))
+    p = LogSvParams(sigma0=0.2, theta=0.2, kappa1=1.0, kappa2=None)
+    assert p.kappa2 == 5.0                                              # kappa2=None -> kappa1/theta (logsv_params.py:92-93)
+    assert LogSvParams().get_vol_backbone_eta(0.3) == 1.0 and np.all(LogSvParams().get_vol_backbone_etas(np.array([0.1, 0.2])) == 1.0)
+    assert HestonParams().v0 == 0.04 and HestonParams().rho == -0.5
+    with pytest.raises(NotImplementedError):
+        ModelPricer.model_mc_price_chain(LogSVPricer(), None, None)
+
+
+def test_vol_backbone_lookup_is_equal_or_largest():
+    import pandas as pd
+    from stochvolmodels_b200 import LogSvParams
+    p = LogSvParams()
+    p.set_vol_backbone(pd.Series([0.9, 1.1], index=[0.1, 0.3]))
+    assert p.get_vol_backbone_eta(0.1) == 0.9 and p.get_vol_backbone_eta(0.2) == 1.1 and p.get_vol_backbone_eta(0.3) == 1.1
+
+
+def test_vol_scaler_and_phi_grid_host_side():
+    from stochvolmodels_b200.pricers.logsv_pricer import set_vol_scaler
+    from stochvolmodels_b200.utils.mgf_pricer import get_phi_grid
+    g = load_golden("grids.npz")
+    assert set_vol_scaler(1.0, np.array([0.25])) == float(g["vol_scaler_q_025"])
+    np.testing.assert_array_equal(get_phi_grid(True, 1000, 0.2041241452319315), g["phi_mma"])
+    np.testing.assert_array_equal(get_phi_grid(False, 1000, 0.2041241452319315), g["phi_inv"])
+
+
+def test_error_conventions_raised_before_any_gpu_work():
+    from stochvolmodels_b200 import engine, VariableType
+    with pytest.raises(NotImplementedError):
+        engine.variable_code(VariableType.SIGMA)
+    with pytest.raises(ValueError, match="not implemented"):
+        engine._check_fourier_types([np.array(["IC"])], True)
+    engine._check_fourier_types([np.array(["IC", "C", "P", "IP"])], False)      # inverse measure accepts C == IC, P == IP
+    with pytest.raises(ValueError):
+        engine.mc_flags("fp16", "fp32")
+    assert engine.mc_flags("fp64", "fp32") == 0 and engine.mc_flags("fp32", "fp64") == 3
+    assert engine.fresh_seed() != engine.fresh_seed()
+
+
+def test_fixed_randoms_helper_replays_and_leaves_global_state_untouched():
+    """reference tests/test_logsv_characterization.py:583-602."""
+    from stochvolmodels_b200.pricers.logsv_pricer import get_randoms_for_chain_valuation
+    np.random.seed(1)
+    before = np.random.get_state()[1].copy()
+    a = get_randoms_for_chain_valuation(np.array([0.1, 0.25]), nb_path=16, nb_steps_per_year=360, seed=10)
+    b = get_randoms_for_chain_valuation(np.array([0.1, 0.25]), nb_path=16, nb_steps_per_year=360, seed=10)
+    np.testing.assert_array_equal(np.random.get_state()[1], before)
+    for u, v in zip(a[0] + a[1], b[0] + b[1]):
+        np.testing.assert_array_equal(u, v)
+    assert a[0][0].shape == (37, 16) and a[0][1].shape == (55, 16) and a[2][0] == 0.1 / 37
+    g = load_golden("logsv_mc_fixed_g5_c1.npz")
+    W0s, _, dts = get_randoms_for_chain_valuation(g["ttms"], 10000, 252, 10)
+    np.testing.assert_array_equal(W0s[0][0, :3], g["W0_head"])
+    assert dts[0] == g["dts"][0]
+
+
+def test_black_implied_vols_round_trip_and_quickstart_values():
+    from stochvolmodels_b200.utils import bsm
+    K = np.array([0.6, 0.9, 1.0, 1.1, 1.6])
+    types = np.array(["P", "P", "C", "C", "C"])
+    for vol in (0.05, 0.2, 1.0, 2.5):
+        p = bsm.compute_bsm_vanilla_price(1.0, K, 0.5, vol, types, 0.97)
+        iv = bsm.infer_bsm_implied_vol(1.0, 0.5, K, p, types, 0.97)
+        good = p > 1e-14
+        np.testing.assert_allclose(iv[good], vol, rtol=1e-8)
+    # examples/getting_started/quickstart.py:43-46
+    np.testing.assert_allclose(bsm.infer_bsm_implied_vol(1.0, 0.25, [1.0], [0.197330882838064], ["C"]), 0.999577, rtol=5e-6)
+    np.testing.assert_allclose(bsm.infer_bsm_implied_vol(1.0, 0.5, [1.0], [0.275201697631672], ["C"]), 0.995757, rtol=5e-6)
+    assert np.isnan(bsm.infer_bsm_implied_vol(1.0, 0.5, [1.0], [1.5], ["C"]))[0]          # above the no-arbitrage bound
+
+
+def test_shard_paths_partitions_exactly():
+    from stochvolmodels_b200.multi_gpu import shard_paths
+    for n, w in ((100, 8), (7, 8), (10**8, 8), (12345, 3), (5, 1)):
+        parts = [shard_paths(n, w, r) for r in range(w)]
+        assert sum(p[0] for p in parts) == n
+        assert parts[0][1] == 0 and all(parts[r][1] == parts[r - 1][1] + parts[r - 1][0] for r in range(1, w))
+        assert max(p[0] for p in parts) - min(p[0] for p in parts) <= 1

@@ -1,0 +1,89 @@
+"""CPU: the N>1 path with torch.distributed (gloo, world_size 2): sharded chain MC == unsharded, on every rank."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import mc
+
+K5 = np.array([0.8, 0.9, 1.0, 1.1, 1.2])
+CASES = {
+    "logsv": dict(params=(0.8376, 1.0413, 3.1844, 3.058, 0.1514, 1.8458), ttms=np.array([0.1, 0.3]), fw=np.array([1.0, 1.02]),
+                  df=np.array([0.999, 0.99]), etas=np.array([0.9, 1.1]), spot=False,
+                  types=[np.array(["IP", "IP", "IC", "IC", "IC"]), np.array(["IP", "P", "C", "IC", "IC"])]),
+    "heston": dict(params=(0.04, 0.04, 4.0, -0.5, 0.4), ttms=np.array([0.1, 0.3]), fw=np.array([1.0, 1.02]), df=np.array([0.999, 0.99]),
+                   etas=None, spot=True, types=[np.array(["P", "P", "C", "C", "C"])] * 2),
+}
+N, NPY, SEED = 2001, 252, 77       # odd path count: ranks get 1001 / 1000
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _expected(model):
+    c = CASES[model]
+    steps = mc.chain_steps(c["ttms"], NPY)
+    Z = [mc.device_normals(SEED, np.arange(N), m, steps[m][0], "f64") for m in range(2)]
+    dts = [d for _, d in steps]
+    if model == "logsv":
+        return mc.logsv_mc_chain_fixed(c["params"], c["ttms"], c["fw"], c["df"], [K5, K5], c["types"], c["etas"], [z[0] for z in Z],
+                                       [z[1] for z in Z], dts, c["spot"], 1)
+    return mc.heston_mc_chain_fixed(c["params"], c["ttms"], c["fw"], c["df"], [K5, K5], c["types"], [z[0] for z in Z], [z[1] for z in Z], dts, 1)
+
+
+def _worker(rank, world, port, model, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import sys
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        from fake_engine import OracleEngine
+        from stochvolmodels_b200 import _capi as C, engine
+        from stochvolmodels_b200.multi_gpu import mc_chain_distributed
+        c = CASES[model]
+        pc = engine.logsv_params_c(*c["params"]) if model == "logsv" else engine.heston_params_c(*c["params"])
+        p, e = mc_chain_distributed(model, pc, c["ttms"], c["fw"], c["df"], c["etas"], [K5, K5], c["types"], N, NPY, c["spot"], C.LOG_RETURN,
+                                    SEED, C.GAUSS_F64, engine_factory=OracleEngine)
+        out[rank] = (p, e)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("model", ["logsv", "heston"])
+def test_sharded_chain_equals_unsharded_under_gloo(model):
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, port, model, out), nprocs=world, join=True)
+    pe, ee = _expected(model)
+    assert sorted(out.keys()) == [0, 1]
+    for rank in range(world):
+        p, e = out[rank]
+        for m in range(2):
+            np.testing.assert_allclose(p[m], pe[m], rtol=1e-11, atol=1e-14)     # only the fp64 summation order differs
+            np.testing.assert_allclose(e[m], ee[m], rtol=1e-9, atol=1e-14)
+    for m in range(2):                                                            # every rank returns the same numbers
+        np.testing.assert_array_equal(out[0][0][m], out[1][0][m])
+
+
+def test_unsharded_path_through_the_same_driver():
+    """world size 1 (no process group): the driver degenerates to the plain chain loop."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from fake_engine import OracleEngine
+    from stochvolmodels_b200 import _capi as C, engine
+    from stochvolmodels_b200.multi_gpu import mc_chain_distributed
+    c = CASES["logsv"]
+    p, e = mc_chain_distributed("logsv", engine.logsv_params_c(*c["params"]), c["ttms"], c["fw"], c["df"], c["etas"], [K5, K5], c["types"], N,
+                                NPY, c["spot"], C.LOG_RETURN, SEED, C.GAUSS_F64, engine_factory=OracleEngine)
+    pe, ee = _expected("logsv")
+    for m in range(2):
+        np.testing.assert_allclose(p[m], pe[m], rtol=1e-11, atol=1e-14)
+        np.testing.assert_allclose(e[m], ee[m], rtol=1e-9, atol=1e-14)
