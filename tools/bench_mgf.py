@@ -1,0 +1,38 @@
+"""Wall-clock of the Fourier route through the public API (host buffers in/out) on BASELINE config 3 (5 maturities x 21 strikes)
+and on the BTC chain, LogSV and Heston, with parity against the golden reference prices; oracle (CPU, vectorised numpy clone of
+the reference algorithm) timed next to it.  usage: python tools/bench_mgf.py"""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from oracle import mgf
+from stochvolmodels_b200 import HestonParams, HestonPricer, LogSvParams, LogSVPricer, LOGSV_BTC_PARAMS, OptionChain, get_btc_test_chain_data, _capi
+
+G = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+K21 = np.linspace(0.5, 1.5, 21); T21 = np.where(K21 >= 1.0, "C", "P")
+ttms5 = np.array([1.0 / 12.0, 0.25, 0.5, 0.75, 1.0])
+c3 = OptionChain(ttms=ttms5, forwards=np.ones(5), strikes_ttms=[K21] * 5, optiontypes_ttms=[T21] * 5)
+btc = get_btc_test_chain_data()
+Q = LogSvParams(1.0, 1.0, 5.0, 5.0, 0.2, 2.0)
+lib = _capi.load_library()
+
+def timed(f, reps=20):
+    f(); f()
+    ts = []
+    for _ in range(reps):
+        t = time.perf_counter(); out = f(); ts.append(time.perf_counter() - t)
+    return out, 1e3 * float(np.median(ts)), 1e3 * float(np.min(ts))
+
+for name, pricer, params, chain, gold in (("logsv c3 5x21", LogSVPricer(), Q, c3, "logsv_fourier_c3_5x21.npz"),
+                                          ("logsv btc 4x49", LogSVPricer(), LOGSV_BTC_PARAMS, btc, "logsv_fourier_btc.npz"),
+                                          ("heston c3 5x21", HestonPricer(), HestonParams(), c3, "heston_fourier_c3_5x21.npz")):
+    g = np.load(os.path.join(G, gold))
+    lib.b200sv_reset_launch_count()
+    prices, med, mn = timed(lambda: pricer.price_chain(chain, params))
+    M = len(chain.ttms)
+    rel = max(np.max(np.abs(prices[m] - g[f"prices_{m}"]) / np.maximum(np.abs(g[f"prices_{m}"]), 1e-12 * chain.forwards[m])) for m in range(M))
+    mask_rel = max(np.max(np.abs(prices[m] / g[f"prices_{m}"] - 1)[g[f"prices_{m}"] > 1e-6 * chain.forwards[m]]) for m in range(M))
+    print(f"{name:16s} GPU e2e median {med:8.3f} ms (min {mn:.3f})  max rel err vs reference golden {mask_rel:.2e}", flush=True)
+    if name.startswith("logsv"):
+        p6 = (params.sigma0, params.theta, params.kappa1, params.kappa2, params.beta, params.volvol)
+        _, omed, _ = timed(lambda: mgf.logsv_chain_prices(p6, chain.ttms, chain.forwards, chain.discfactors, chain.strikes_ttms, chain.optiontypes_ttms), reps=3)
+        print(f"{'':16s} CPU oracle (vectorised numpy RK45 clone) {omed:8.1f} ms; reference as shipped (scipy loop) ~2 s per maturity [SURVEY.md §6]")
