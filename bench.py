@@ -38,6 +38,7 @@ if ROOT not in sys.path:
 
 NB_STEPS_PER_YEAR = 582          # BTC chain maturity gaps -> 25 + 34 + 57 + 136 = 252 steps
 ALGO_BYTES_PER_PATH_STEP = 64.0
+SLICE_DRAM_BYTES_PER_PATH = 45.1  # measured: ncu --set full, profiles/r01_slice_kernel_ncu.txt (state read + write per launch)
 SEED = 10
 
 
@@ -67,7 +68,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -258,6 +259,7 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
+        # per launch: algorithmic bytes = 64 B x (n_local x S_m); achieved = sum of bytes / sum of CUDA-event durations of the slice launches
         achieved = ALGO_BYTES_PER_PATH_STEP * slice_path_steps / (slice_ms / 1e3) / 1e9
         same = bool(np.allclose(np.concatenate(prices_api), prices_dev[0], rtol=1e-12)) if world == 1 else None
         line = {"metric": "LogSV MC path-steps/sec", "value": value, "unit": "path-steps/s", "n_gpus": world, "steps": args.steps,
@@ -272,7 +274,10 @@ def main():
                         "api": "LogSVPricer.model_mc_price_chain (host numpy in/out through the C ABI)", "same_prices_as_device_arm": same},
                 "gpu_launches": launches,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "kernel": "mc_slice_kernel<LogsvPath>", "peak_source": peak_src,
+                             "traffic": SLICE_DRAM_BYTES_PER_PATH * n_local * len(slice_events) / max(args.steps, 1) / len(grid),
+                             "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum = 45.1 B per path per launch "
+                                               "(profiles/r01_slice_kernel_ncu.txt), scaled to this launch size",
+                             "kernel": "mc_slice_kernel<LogsvPath>", "peak_source": peak_src,
                              "algorithmic_bytes_per_path_step": ALGO_BYTES_PER_PATH_STEP,
                              "kernel_share_of_step": slice_ms / (1e3 * elapsed_s),
                              "note": "effective bandwidth of the reference's streaming dataflow; the fused kernel keeps state in registers"},

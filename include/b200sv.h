@@ -100,6 +100,12 @@ int b200sv_logsv_step_fixed(double* x, double* sigma, double* qvar, const double
 int b200sv_heston_step_fixed(double* x, double* var, double* qvar, const double* W0, const double* W1, int S,
                              long long N, double dt, const b200sv_heston_params* params);
 
+/* replaces simulate_vol_paths (pricers/logsv_pricer.py:870-947; LogSVPricer.simulate_vol_paths :561-587): the whole volatility
+ * path matrix sigma_t_out[(S+1)][nb_path] (row 0 = sigma0), S = int(ttm*n)+1.  brownians: optional host array [S][nb_path] of
+ * SCALED increments (the reference's `brownians`); NULL draws sqrt(dt)*Z from the device Philox stream.  Strict fp64. */
+int b200sv_logsv_vol_paths(const b200sv_logsv_params* params, double ttm, long long nb_path, int nb_steps_per_year,
+                           int is_spot_measure, uint64_t seed, const double* brownians, double* sigma_t_out);
+
 /* replaces compute_mc_vars_payoff (utils/mc_payoffs.py:10-88): forward re-centring with the nan-mean over all paths,
  * per-strike discounted nan-mean and nan-std/sqrt(N).  qvar may be NULL for B200SV_LOG_RETURN. */
 int b200sv_mc_payoffs(const double* x, const double* qvar, long long N, double ttm, double forward, const double* strikes,
@@ -157,22 +163,24 @@ int b200sv_debug_exp_pair(const double* L, long long n, double* out);
  * Fourier / MGF, host-level
  * ------------------------------------------------------------------------------------------------------------------ */
 
-/* replaces logsv_chain_pricer, LOG_RETURN branch (pricers/logsv_pricer.py:669-739): transform grid
+/* replaces logsv_chain_pricer (pricers/logsv_pricer.py:669-739), LOG_RETURN and Q_VAR branches: transform grid
  * (utils/mgf_pricer.py:11-34), per maturity the affine-expansion ODEs integrated with SciPy's RK45 control law
  * (pricers/logsv/affine_expansion.py:229-303, 492-529) carried across maturities, log-MGF contraction (:674-685)
  * and the Simpson/Fourier sums (utils/mgf_pricer.py:174-221).  vol_scaler <= 0 selects set_vol_scaler (:664-666).
- * P = grid size (reference: 1000).  Optional outputs (may be NULL): a_out [M][P][n] complex128 interleaved,
- * log_mgf_out [M][P] complex128 interleaved. */
+ * variable_type = B200SV_Q_VAR prices calls on the annualised quadratic variance on the psi grid -0.5 + 1j*linspace(0, 4000, P)
+ * (utils/mgf_pricer.py:37-47, :323-358; only 'C' payoffs, else -5) with phi = 0 (MMA) / 1 (inverse measure) (:79-85).
+ * P = grid size, <= 0 selects the reference's (1000 for LOG_RETURN, 40000 for Q_VAR).  Optional outputs (may be NULL):
+ * a_out [M][P][n] complex128 interleaved, log_mgf_out [M][P] complex128 interleaved. */
 int b200sv_logsv_price_chain(const b200sv_logsv_params* params, int M, const double* ttms, const double* forwards,
                              const double* discfactors, const double* etas, const int* offsets, const double* strikes,
-                             const int8_t* types, int is_spot_measure, int expansion_order, double vol_scaler, int P,
-                             double* prices_out, double* a_out, double* log_mgf_out);
+                             const int8_t* types, int is_spot_measure, int variable_type, int expansion_order,
+                             double vol_scaler, int P, double* prices_out, double* a_out, double* log_mgf_out);
 
-/* replaces heston_chain_pricer, LOG_RETURN branch (pricers/heston_pricer.py:217-282) with compute_heston_mgf_grid
+/* replaces heston_chain_pricer, LOG_RETURN and Q_VAR branches (pricers/heston_pricer.py:217-282) with compute_heston_mgf_grid
  * (:183-214).  vol_scaler <= 0 selects min(0.3, sqrt(v0*ttms[0])) (:234-235). */
 int b200sv_heston_price_chain(const b200sv_heston_params* params, int M, const double* ttms, const double* forwards,
                               const double* discfactors, const int* offsets, const double* strikes, const int8_t* types,
-                              double vol_scaler, int P, double* prices_out, double* log_mgf_out);
+                              int variable_type, double vol_scaler, int P, double* prices_out, double* log_mgf_out);
 
 /* replaces compute_logsv_a_mgf_grid, non-analytic branch (pricers/logsv/affine_expansion.py:570-685 -> solve_a_ode_grid
  * :492-529): phi, psi, a (in: A(0), out: A(dtau)), log_mgf_out are complex128 interleaved host arrays of P, P, P*n, P. */
@@ -187,6 +195,29 @@ int b200sv_heston_mgf_grid(const double* phi, const double* psi, int P, double d
 /* replaces vanilla_slice_pricer_with_mgf_grid (utils/mgf_pricer.py:174-221). */
 int b200sv_fourier_vanilla(const double* log_mgf, const double* phi, int P, double forward, const double* strikes,
                            const int8_t* types, int J, double discfactor, int is_spot_measure, double* prices_out);
+
+/* replaces slice_qvar_pricer_with_a_grid (utils/mgf_pricer.py:323-358): calls on annualised quadratic variance from the log-MGF on
+ * the psi grid; price = max(discfactor * S / ttm, 1e-10), S = nansum Re((dp/pi)/psi^2 * exp(K*ttm*psi + log_mgf)). */
+int b200sv_fourier_qvar(const double* log_mgf, const double* psi, int P, double ttm, const double* strikes,
+                        const int8_t* types, int J, double discfactor, double* prices_out);
+
+/* the sum of pdf_with_mgf_grid (utils/mgf_pricer.py:361-384): out[j] = nansum Re((dp/pi) * exp(z[j]*grid + log_mgf)); the caller
+ * applies z = (x - shift)/scale beforehand and the dx / scale factors afterwards (pricers/logsv_pricer.py:778-803). */
+int b200sv_fourier_pdf(const double* log_mgf, const double* grid, int P, const double* z, int J, double* out);
+
+/* replaces digital_slice_pricer_with_mgf_grid (utils/mgf_pricer.py:224-269). */
+int b200sv_fourier_digital(const double* log_mgf, const double* phi, int P, double forward, const double* strikes,
+                           const int8_t* types, int J, double discfactor, double* prices_out);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Black-76 implied volatilities (the step after every chain pricer in the reference's callers)
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* replaces option_chain.compute_model_ivols_from_chain_data (data/option_chain.py:327-346 -> third-party
+ * vanilla_option_pricers.infer_bsm_ivols_from_model_chain_prices): prices[] and ivols_out[] are flat in chain order
+ * (offsets[M]-offsets[0] entries).  'IC'/'IP' quotes are inverted like 'C'/'P'; prices outside the no-arbitrage bounds give NaN. */
+int b200sv_bsm_implied_vols(int M, const double* ttms, const double* forwards, const double* discfactors, const int* offsets,
+                            const double* strikes, const int8_t* types, const double* prices, double* ivols_out);
 
 #ifdef __cplusplus
 }

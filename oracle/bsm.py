@@ -1,10 +1,10 @@
-"""Black-76 prices and implied-volatility inversion on the host (numpy, vectorised).
+"""oracle.bsm -- Black-76 prices and implied-volatility inversion on the host (numpy).  TEST INFRASTRUCTURE ONLY: the checker of the
+CUDA kernel ``black_ivol_kernel`` (stochvolmodels_b200/csrc/ivol_kernels.cu), same bracketed bisection.
 
 In the reference this step is third-party: ``vanilla_option_pricers.infer_bsm_ivols_from_model_chain_prices`` called from
 ``data/option_chain.py:327-346``; that package is not part of the reference tree and is absent here, so bit-level parity
 with it is UNPINNED.  What the reference pins is satisfied by any correct inversion: the quickstart
 implied vols 0.999577 / 0.995757 (examples/getting_started/quickstart.py:44,46, rtol 5e-6) and flat-vol round trips.
-It is a "next" row of the scope table, kept on the host for now: J <= a few hundred per call.
 """
 from __future__ import annotations
 

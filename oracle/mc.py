@@ -227,3 +227,21 @@ def device_normals(seed: int, path_ids, slice_idx: int, nb_steps: int, gauss: st
     else:
         raise ValueError(gauss)
     return Z0, Z1
+
+
+def logsv_vol_paths(v0, theta, kappa1, kappa2, beta, volvol, W, dt, is_spot_measure=True):
+    """``simulate_vol_paths`` (pricers/logsv_pricer.py:925-947) with the scaled increments W[S, N] supplied:
+    sigma_t[(S+1), N], row 0 = v0; single normal per step with loading vartheta; adj = beta (no eta) under the inverse measure."""
+    n = W.shape[1]
+    sigma = v0 * np.ones(n)
+    adj = 0.0 if is_spot_measure else beta
+    vartheta2 = beta * beta + volvol * volvol
+    vartheta = np.sqrt(vartheta2)
+    L = np.log(sigma)
+    out = np.zeros((W.shape[0] + 1, n))
+    out[0] = sigma
+    for t, w1 in enumerate(W):
+        L = L + ((kappa1 * theta / sigma - kappa1) + kappa2 * (theta - sigma) + adj * sigma - 0.5 * vartheta2) * dt + vartheta * w1
+        sigma = np.exp(L)
+        out[t + 1] = sigma
+    return out

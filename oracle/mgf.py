@@ -374,3 +374,112 @@ def heston_chain_prices(params5, ttms, forwards, discfactors, strikes_ttms, type
         grids.append((log_mgf, a, b))
         t0 = ttm
     return (prices, grids) if return_grids else prices
+
+
+# --------------------------------------------------------------------------------------------
+# quadratic-variance options, densities, digitals
+# --------------------------------------------------------------------------------------------
+def psi_grid():
+    """``get_psi_grid`` (utils/mgf_pricer.py:37-47)."""
+    return -0.5 + 1j * np.linspace(0, 4000, 40000)
+
+
+def theta_grid():
+    """``get_theta_grid`` (utils/mgf_pricer.py:50-58)."""
+    return 0.0 + 1j * np.linspace(0, 600, 5000)
+
+
+def transform_var_grid(variable_type, is_spot_measure=True, vol_scaler=0.28):
+    """``get_transform_var_grid`` (utils/mgf_pricer.py:61-94); variable_type 1 LOG_RETURN, 2 Q_VAR, 3 SIGMA."""
+    if variable_type == 1:
+        phi = phi_grid(vol_scaler, is_spot_measure)
+        return phi, np.zeros_like(phi), np.zeros_like(phi)
+    if variable_type == 2:
+        psi = psi_grid()
+        return (np.zeros_like(psi) if is_spot_measure else np.ones_like(psi)), psi, np.zeros_like(psi)
+    if variable_type == 3:
+        th = theta_grid()
+        return np.zeros_like(th), np.zeros_like(th), th
+    raise NotImplementedError
+
+
+def qvar_slice_prices(log_mgf, psi, ttm, strikes, types, discfactor=1.0):
+    """``slice_qvar_pricer_with_a_grid`` (utils/mgf_pricer.py:323-358)."""
+    dp = legacy_simpson_weights(psi)
+    w = (dp / np.pi) / (psi * psi)
+    out = np.zeros(len(strikes))
+    for j, (k, ty) in enumerate(zip(strikes, types)):
+        if str(ty) != "C":
+            raise ValueError("not implemented")
+        s = np.nansum(np.real(w * np.exp((k * ttm) * psi + log_mgf)))
+        out[j] = np.maximum(discfactor * s / ttm, 1e-10)
+    return out
+
+
+def pdf_from_mgf(log_mgf, grid, space_grid, shift=0.0, scale=1.0):
+    """``pdf_with_mgf_grid`` (utils/mgf_pricer.py:361-384)."""
+    dp = legacy_simpson_weights(grid) / np.pi
+    z = (space_grid - shift) / scale
+    pdf = np.array([np.nansum(np.real(dp * np.exp(x * grid + log_mgf))) for x in z])
+    return (space_grid[1] - space_grid[0]) * pdf
+
+
+def digital_slice_prices(log_mgf, phi, forward, strikes, types, discfactor=1.0):
+    """``digital_slice_pricer_with_mgf_grid`` (utils/mgf_pricer.py:224-269)."""
+    dp = legacy_simpson_weights(phi)
+    all_calls = bool(np.all(np.real(phi) < 0.0))
+    w = -(dp / np.pi) / phi if all_calls else (dp / np.pi) / phi
+    out = np.zeros(len(strikes))
+    for j, (k, ty) in enumerate(zip(strikes, types)):
+        x = np.log(forward / k)
+        s = np.nansum(np.real(w * np.exp(-x * phi + log_mgf)))
+        ty = str(ty)
+        if ty == "C":
+            price = s if all_calls else 1.0 - s
+        elif ty == "P":
+            price = 1.0 - s if all_calls else s
+        else:
+            raise ValueError("not implemented")
+        out[j] = discfactor * price
+    return out
+
+
+def logsv_qvar_chain_prices(params6, ttms, discfactors, strikes_ttms, types_ttms, is_spot_measure=True, order=2, return_grids=False):
+    """``logsv_chain_pricer`` Q_VAR branch (pricers/logsv_pricer.py:669-731)."""
+    sigma0, theta, kappa1, kappa2, beta, volvol = params6
+    phi, psi, _ = transform_var_grid(2, is_spot_measure)
+    a = np.zeros((psi.shape[0], expansion_n(order)), dtype=np.complex128)
+    t0, prices, grids = 0.0, [], []
+    for m, ttm in enumerate(ttms):
+        a, lm = logsv_a_mgf_grid(ttm - t0, phi, psi, a, sigma0, theta, kappa1, kappa2, beta, volvol, is_spot_measure, order, 1.0)
+        prices.append(qvar_slice_prices(lm, psi, ttm, strikes_ttms[m], types_ttms[m], discfactors[m]))
+        grids.append((a.copy(), lm))
+        t0 = ttm
+    return (prices, grids) if return_grids else prices
+
+
+def logsv_pdf(params6, ttm, space_grid, variable_type=1, is_spot_measure=True, order=2):
+    """``logsv_pdfs`` (pricers/logsv_pricer.py:742-803)."""
+    sigma0, theta, kappa1, kappa2, beta, volvol = params6
+    vs = logsv_vol_scaler(sigma0, np.array([ttm]))
+    phi, psi, th = transform_var_grid(variable_type, is_spot_measure, vs)
+    a0 = np.zeros((phi.shape[0], expansion_n(order)), dtype=np.complex128)
+    if variable_type == 3:
+        a0[:, 1] = -th                     # get_init_conditions_a, affine_expansion.py:562-564
+    _, lm = logsv_a_mgf_grid(ttm, phi, psi, a0, sigma0, theta, kappa1, kappa2, beta, volvol, is_spot_measure, order, 1.0)
+    grid, shift, scale = ((phi, 0.0, 1.0), (psi, 0.0, 1.0 / ttm), (th, theta, 1.0))[variable_type - 1]
+    return pdf_from_mgf(lm, grid, space_grid, shift, scale) / scale
+
+
+def heston_qvar_chain_prices(params5, ttms, discfactors, strikes_ttms, types_ttms):
+    """``heston_chain_pricer`` Q_VAR branch (pricers/heston_pricer.py:217-282)."""
+    v0, theta, kappa, rho, volvol = params5
+    phi, psi, _ = transform_var_grid(2, True)
+    a = np.zeros_like(psi)
+    b = np.zeros_like(psi)
+    t0, prices = 0.0, []
+    for m, ttm in enumerate(ttms):
+        lm, a, b = heston_mgf_grid(v0, theta, kappa, volvol, rho, ttm - t0, phi, psi, a, b)
+        prices.append(qvar_slice_prices(lm, psi, ttm, strikes_ttms[m], types_ttms[m], discfactors[m]))
+        t0 = ttm
+    return prices

@@ -14,7 +14,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIBDIR, "libb200sv.so")
-SOURCES = ["mc_kernels.cu", "mgf_kernels.cu"]
+SOURCES = ["mc_kernels.cu", "mgf_kernels.cu", "ivol_kernels.cu"]
 HEADERS = ["common.cuh", "philox.cuh", "fastmath64.cuh", os.path.join("..", "..", "include", "b200sv.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]

@@ -55,6 +55,7 @@ SIGNATURES = {
     "b200sv_heston_terminal": [_hp, c_double, c_longlong, c_int, c_uint64, c_int, c_int, _dp, _dp, _dp],
     "b200sv_logsv_step_fixed": [_dp, _dp, _dp, _dp, _dp, c_int, c_longlong, c_double, _lp, c_double, c_int],
     "b200sv_heston_step_fixed": [_dp, _dp, _dp, _dp, _dp, c_int, c_longlong, c_double, _hp],
+    "b200sv_logsv_vol_paths": [_lp, c_double, c_longlong, c_int, c_int, c_uint64, _dp, _dp],
     "b200sv_mc_payoffs": [_dp, _dp, c_longlong, c_double, c_double, _dp, _i8p, c_int, c_double, c_int, _dp, _dp],
     "b200sv_device_normals": [c_uint64, c_longlong, c_longlong, c_int, c_int, c_int, _dp, _dp],
     "b200sv_dev_logsv_slice": [c_void_p, c_void_p, c_void_p, c_longlong, c_longlong, c_int, _lp, c_double, c_int, c_int, c_double,
@@ -69,8 +70,12 @@ SIGNATURES = {
     "b200sv_dev_heston_step_fixed": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_double, _hp, c_void_p],
     "b200sv_dev_spot_moments": [c_void_p, c_longlong, c_double, c_void_p, c_void_p],
     "b200sv_debug_exp_pair": [_dp, c_longlong, _dp],
-    "b200sv_logsv_price_chain": [_lp, c_int, _dp, _dp, _dp, _dp, _ip, _dp, _i8p, c_int, c_int, c_double, c_int, _dp, _dp, _dp],
-    "b200sv_heston_price_chain": [_hp, c_int, _dp, _dp, _dp, _ip, _dp, _i8p, c_double, c_int, _dp, _dp],
+    "b200sv_logsv_price_chain": [_lp, c_int, _dp, _dp, _dp, _dp, _ip, _dp, _i8p, c_int, c_int, c_int, c_double, c_int, _dp, _dp, _dp],
+    "b200sv_heston_price_chain": [_hp, c_int, _dp, _dp, _dp, _ip, _dp, _i8p, c_int, c_double, c_int, _dp, _dp],
+    "b200sv_fourier_qvar": [_dp, _dp, c_int, c_double, _dp, _i8p, c_int, c_double, _dp],
+    "b200sv_fourier_pdf": [_dp, _dp, c_int, _dp, c_int, _dp],
+    "b200sv_fourier_digital": [_dp, _dp, c_int, c_double, _dp, _i8p, c_int, c_double, _dp],
+    "b200sv_bsm_implied_vols": [c_int, _dp, _dp, _dp, _ip, _dp, _i8p, _dp, _dp],
     "b200sv_logsv_mgf_grid": [_dp, _dp, c_int, c_double, _dp, _lp, c_double, c_int, c_int, _dp],
     "b200sv_heston_mgf_grid": [_dp, _dp, c_int, c_double, _dp, _dp, _hp, _dp],
     "b200sv_fourier_vanilla": [_dp, _dp, c_int, c_double, _dp, _i8p, c_int, c_double, c_int, _dp],

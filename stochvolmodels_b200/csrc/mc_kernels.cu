@@ -366,6 +366,42 @@ __global__ void __launch_bounds__(kThreads) heston_step_fixed_kernel(double* __r
   }
 }
 
+// Full volatility paths sigma_t[(S+1)][N]: simulate_vol_paths (pricers/logsv_pricer.py:870-947).  One normal per step
+// (vartheta * w1), drift evaluated at the current step, reference evaluation order (it is plain numpy, no fastmath).
+// W != nullptr: caller-supplied SCALED increments [S][N] ("brownians"); else sqrt(dt) * Z0 of the device Philox stream
+// (gauss f64: call = step, first normal of the pair).  Output-bandwidth bound: 8 B written per path-step.
+__global__ void __launch_bounds__(kThreads) logsv_vol_paths_kernel(double* __restrict__ sigma_t, const double* __restrict__ W, int S,
+                                                                  long long N, LogsvRaw r, double v0, unsigned long long seed,
+                                                                  unsigned long long path_offset) {
+  const double sdt = __dsqrt_rn(r.dt);
+  const double vartheta2 = __dadd_rn(__dmul_rn(r.beta, r.beta), __dmul_rn(r.volvol, r.volvol));
+  const double vartheta = __dsqrt_rn(vartheta2);
+  const double k1theta = __dmul_rn(r.kappa1, r.theta);
+  const double half_vt2 = __dmul_rn(0.5, vartheta2);
+  const long long stride = (long long)gridDim.x * kThreads;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < N; i += stride) {
+    double si = v0;
+    double L = log(si);
+    sigma_t[i] = si;
+    StepNormals<double, true> rng(seed, path_offset + (unsigned long long)i, 0u);
+    for (int s = 0; s < S; ++s) {
+      double w1;
+      if (W) {
+        w1 = __ldg(W + (size_t)s * N + i);
+      } else {
+        double z0, z1;
+        rng.get((uint32_t)s, z0, z1);
+        w1 = __dmul_rn(sdt, z0);
+      }
+      double d = __dadd_rn(__dadd_rn(__ddiv_rn(k1theta, si), -r.kappa1), __dmul_rn(r.kappa2, __dadd_rn(r.theta, -si)));
+      d = __dadd_rn(__dadd_rn(d, __dmul_rn(r.adj, si)), -half_vt2);
+      L = __dadd_rn(__dadd_rn(L, __dmul_rn(d, r.dt)), __dmul_rn(vartheta, w1));
+      si = exp(L);
+      sigma_t[(size_t)(s + 1) * N + i] = si;
+    }
+  }
+}
+
 // (sum F e^x over non-NaN, count) partials for externally supplied states (b200sv_mc_payoffs)
 __global__ void __launch_bounds__(kThreads) spot_moments_kernel(const double* __restrict__ x, long long n, double forward,
                                                                double* __restrict__ partials) {
@@ -1038,6 +1074,39 @@ int b200sv_debug_exp_pair(const double* L, long long n, double* out /* 2n */) {
   cudaFreeAsync(dl, st);
   cudaFreeAsync(dout, st);
   B200SV_CUDA(cudaStreamSynchronize(st));
+  return rc;
+}
+
+int b200sv_logsv_vol_paths(const b200sv_logsv_params* params, double ttm, long long nb_path, int nb_steps_per_year, int is_spot_measure,
+                           uint64_t seed, const double* brownians, double* sigma_t_out) {
+  B200SV_REQUIRE(params && sigma_t_out, "null pointer");
+  B200SV_REQUIRE(nb_path >= 1 && ttm > 0.0 && nb_steps_per_year >= 1, "nb_path, ttm, nb_steps_per_year must be positive");
+  int S;
+  double dt;
+  time_grid(ttm, nb_steps_per_year, &S, &dt);
+  // adj = beta under the inverse measure, no eta (pricers/logsv_pricer.py:929-932)
+  LogsvRaw r{params->theta, params->kappa1, params->kappa2, params->beta, params->volvol, 1.0, is_spot_measure ? -1.0 : 1.0,
+             is_spot_measure ? 0.0 : params->beta, dt};
+  cudaStream_t st = 0;
+  ensure_pool_threshold();
+  double *d_out = nullptr, *d_w = nullptr;
+  const size_t ob = sizeof(double) * (size_t)(S + 1) * (size_t)nb_path, wb = sizeof(double) * (size_t)S * (size_t)nb_path;
+  B200SV_CUDA(cudaMallocAsync(&d_out, ob, st));
+  if (brownians) {
+    B200SV_CUDA(cudaMallocAsync(&d_w, wb, st));
+    B200SV_CUDA(cudaMemcpyAsync(d_w, brownians, wb, cudaMemcpyHostToDevice, st));
+  }
+  Grid g = persistent_grid(logsv_vol_paths_kernel, kThreads, nb_path);
+  logsv_vol_paths_kernel<<<g.blocks, g.threads, 0, st>>>(d_out, d_w, S, nb_path, r, params->sigma0, seed, 0ull);
+  int rc = check_launch("logsv_vol_paths_kernel");
+  if (rc == 0) {
+    cudaError_t e = cudaMemcpyAsync(sigma_t_out, d_out, ob, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) rc = fail(-2, std::string("D2H: ") + cudaGetErrorString(e));
+  }
+  cudaFreeAsync(d_out, st);
+  if (d_w) cudaFreeAsync(d_w, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (rc == 0 && e != cudaSuccess) rc = fail(-2, std::string("sync: ") + cudaGetErrorString(e));
   return rc;
 }
 

@@ -371,6 +371,53 @@ __global__ void __launch_bounds__(kFourierThreads) fourier_vanilla_kernel(const 
   }
 }
 
+// Generic Fourier sum  S = nansum_j Re( w_j * exp(coef * g_j + log_mgf_j) )  for the other inversion formulas of
+// utils/mgf_pricer.py: options on quadratic variance (:323-358), densities (:361-384), digitals (:224-269).
+enum { kModeQvar = 1, kModePdf = 2, kModeDigital = 3 };
+struct SumSpec {
+  double coef;        // QVAR: strike*ttm ; PDF: z = (x - shift)/scale ; DIGITAL: -ln(F/K)
+  double a, b;        // QVAR: a = discfactor, b = ttm ; DIGITAL: a = discfactor
+  int type, slice;
+};
+
+__global__ void __launch_bounds__(kFourierThreads) fourier_sum_kernel(const cd* __restrict__ log_mgf, const cd* __restrict__ grid, int P,
+                                                                     const SumSpec* __restrict__ specs, int mode, int all_calls,
+                                                                     double* __restrict__ out) {
+  __shared__ double red[kFourierThreads / 32];
+  const SumSpec sp = specs[blockIdx.x];
+  const cd* lm = log_mgf + (size_t)sp.slice * P;
+  const double h3 = (grid[1].im - grid[0].im) / 3.0;
+  double acc[1] = {0.0};
+  for (int j = threadIdx.x; j < P; j += kFourierThreads) {
+    const double wq = (j & 1) ? 4.0 : ((j == 0 || j == P - 1) ? 1.0 : 2.0);   // legacy Simpson, mgf_pricer.py:163-170
+    const double dp = h3 * wq;
+    const cd g = grid[j];
+    cd w;
+    if (mode == kModeQvar)
+      w = mk(dp / M_PI) / (g * g);                              // (dp/pi)/(psi*psi), :344
+    else if (mode == kModePdf)
+      w = mk(dp / M_PI);                                        // dp/pi, :374-376
+    else
+      w = all_calls ? -(mk(dp / M_PI) / g) : (mk(dp / M_PI) / g);   // -/+ (dp/pi)/phi, :241-246
+    const cd term = w * cexp_(sp.coef * g + lm[j]);
+    if (term.re == term.re) acc[0] += term.re;
+  }
+  block_sum<1, kFourierThreads>(acc, red);
+  if (threadIdx.x == 0) {
+    const double S = acc[0];
+    double r;
+    if (mode == kModeQvar)
+      r = fmax(sp.a * S / sp.b, 1e-10);                         // np.maximum(discfactor*option_price/ttm, 1e-10), :347
+    else if (mode == kModePdf)
+      r = S;
+    else {
+      const bool is_call = sp.type == B200SV_CALL;
+      r = sp.a * ((is_call == (all_calls != 0)) ? S : 1.0 - S);  // :251-264
+    }
+    out[blockIdx.x] = r;
+  }
+}
+
 // --------------------------------------------------------------------------------------------------------------------
 // host side
 // --------------------------------------------------------------------------------------------------------------------
@@ -396,6 +443,23 @@ static void build_phi(double vol_scaler, bool spot, int P, std::vector<double>& 
     phi[2 * i + 1] = (double)i * step;
   }
   phi[2 * (size_t)(P - 1) + 1] = stop;
+}
+
+// re + 1j*linspace(0, stop, P)  (get_psi_grid: -0.5 + 1j*linspace(0, 4000, 40000), utils/mgf_pricer.py:37-47)
+static void build_grid(double re, double stop, int P, std::vector<double>& g) {
+  g.resize(2 * (size_t)P);
+  const double step = stop / (double)(P - 1);
+  for (int i = 0; i < P; ++i) {
+    g[2 * i] = re;
+    g[2 * i + 1] = (double)i * step;
+  }
+  g[2 * (size_t)(P - 1) + 1] = stop;
+}
+
+static int check_qvar_types(const int8_t* types, int n) {
+  for (int j = 0; j < n; ++j)
+    if (types[j] != B200SV_CALL) return fail(-5, "not implemented");      // utils/mgf_pricer.py:349-358: only 'C'
+  return 0;
 }
 
 static int check_fourier_types(const int8_t* types, int n, bool spot) {
@@ -435,15 +499,18 @@ extern "C" {
 
 int b200sv_logsv_price_chain(const b200sv_logsv_params* params, int M, const double* ttms, const double* forwards,
                              const double* discfactors, const double* etas, const int* offsets, const double* strikes,
-                             const int8_t* types, int is_spot_measure, int expansion_order, double vol_scaler, int P,
-                             double* prices_out, double* a_out, double* log_mgf_out) {
+                             const int8_t* types, int is_spot_measure, int variable_type, int expansion_order,
+                             double vol_scaler, int P, double* prices_out, double* a_out, double* log_mgf_out) {
   B200SV_REQUIRE(params && ttms && forwards && discfactors && offsets && prices_out, "null pointer");
+  if (variable_type != B200SV_LOG_RETURN && variable_type != B200SV_Q_VAR) return fail(-4, "variable_type not implemented");   // logsv_pricer.py:733-734
+  const bool qvar = variable_type == B200SV_Q_VAR;
+  if (P <= 0) P = qvar ? 40000 : 1000;                                     // utils/mgf_pricer.py:13, :44
   B200SV_REQUIRE(M >= 1 && P >= 3, "M >= 1, P >= 3");
   if (expansion_order != B200SV_ORDER_FIRST && expansion_order != B200SV_ORDER_SECOND)
     return fail(-4, "expansion_order not implemented");                    // affine_expansion.py:680-681
   const bool spot = is_spot_measure != 0;
   const int Jtot = offsets[M] - offsets[0];
-  if (int rc = check_fourier_types(types + offsets[0], Jtot, spot)) return rc;
+  if (int rc = qvar ? check_qvar_types(types + offsets[0], Jtot) : check_fourier_types(types + offsets[0], Jtot, spot)) return rc;
   double t0 = 0.0, tmin = ttms[0];
   for (int m = 0; m < M; ++m) {
     B200SV_REQUIRE(ttms[m] > t0, "ttms must be positive and strictly increasing");
@@ -452,8 +519,15 @@ int b200sv_logsv_price_chain(const b200sv_logsv_params* params, int M, const dou
   }
   if (!(vol_scaler > 0.0)) vol_scaler = params->sigma0 * std::sqrt(std::min(tmin, 0.5 / 12.0));   // logsv_pricer.py:664-666
   const int N = expansion_order == B200SV_ORDER_FIRST ? 3 : 5;
-  std::vector<double> phi;
-  build_phi(vol_scaler, spot, P, phi);
+  std::vector<double> phi, psi;
+  if (!qvar) {
+    build_phi(vol_scaler, spot, P, phi);
+  } else {                                                                 // utils/mgf_pricer.py:79-85: psi grid, phi = 0 (MMA) | 1 (inverse)
+    build_grid(-0.5, 4000.0, P, psi);
+    phi.assign(2 * (size_t)P, 0.0);
+    if (!spot)
+      for (int i = 0; i < P; ++i) phi[2 * i] = 1.0;
+  }
   std::vector<ChainSpec> spec(M);
   t0 = 0.0;
   for (int m = 0; m < M; ++m) {
@@ -462,32 +536,43 @@ int b200sv_logsv_price_chain(const b200sv_logsv_params* params, int M, const dou
     t0 = ttms[m];
   }
   std::vector<StrikeSpec> ss(std::max(Jtot, 1));
+  std::vector<SumSpec> qs(std::max(Jtot, 1));
   for (int m = 0; m < M; ++m)
     for (int j = offsets[m]; j < offsets[m + 1]; ++j) {
       B200SV_REQUIRE(strikes[j] > 0.0, "strikes must be positive");
       ss[j - offsets[0]] = StrikeSpec{strikes[j], forwards[m], discfactors[m], (int)types[j], m};
+      qs[j - offsets[0]] = SumSpec{strikes[j] * ttms[m], discfactors[m], ttms[m], (int)types[j], m};
     }
   cudaStream_t st = 0;
-  DevBuf d_phi(st), d_spec(st), d_a(st), d_lm(st), d_ss(st), d_pr(st), d_stat(st);
+  DevBuf d_phi(st), d_psi(st), d_spec(st), d_a(st), d_lm(st), d_ss(st), d_pr(st), d_stat(st);
   B200SV_CUDA(d_phi.alloc(sizeof(cd) * P));
+  B200SV_CUDA(d_psi.alloc(sizeof(cd) * P));
+  if (qvar) B200SV_CUDA(cudaMemcpyAsync(d_psi.p, psi.data(), sizeof(cd) * P, cudaMemcpyHostToDevice, st));
   B200SV_CUDA(d_spec.alloc(sizeof(ChainSpec) * M));
   B200SV_CUDA(d_a.alloc(sizeof(cd) * (size_t)M * P * N));
   B200SV_CUDA(d_lm.alloc(sizeof(cd) * (size_t)M * P));
-  B200SV_CUDA(d_ss.alloc(sizeof(StrikeSpec) * ss.size()));
+  B200SV_CUDA(d_ss.alloc(std::max(sizeof(StrikeSpec), sizeof(SumSpec)) * ss.size()));
   B200SV_CUDA(d_pr.alloc(sizeof(double) * ss.size()));
   B200SV_CUDA(d_stat.alloc(sizeof(int) * P));
   B200SV_CUDA(cudaMemcpyAsync(d_phi.p, phi.data(), sizeof(cd) * P, cudaMemcpyHostToDevice, st));
   B200SV_CUDA(cudaMemcpyAsync(d_spec.p, spec.data(), sizeof(ChainSpec) * M, cudaMemcpyHostToDevice, st));
-  B200SV_CUDA(cudaMemcpyAsync(d_ss.p, ss.data(), sizeof(StrikeSpec) * ss.size(), cudaMemcpyHostToDevice, st));
+  if (qvar)
+    B200SV_CUDA(cudaMemcpyAsync(d_ss.p, qs.data(), sizeof(SumSpec) * qs.size(), cudaMemcpyHostToDevice, st));
+  else
+    B200SV_CUDA(cudaMemcpyAsync(d_ss.p, ss.data(), sizeof(StrikeSpec) * ss.size(), cudaMemcpyHostToDevice, st));
   const int tpb = mgf_block_threads(P), nb = (P + tpb - 1) / tpb;
   const double y = params->sigma0 - params->theta;
+  const cd* dpsi = qvar ? d_psi.as<cd>() : nullptr;
   if (N == 5)
-    logsv_mgf_kernel<5><<<nb, tpb, 0, st>>>(d_phi.as<cd>(), nullptr, P, M, d_spec.as<ChainSpec>(), nullptr, d_a.as<cd>(), d_lm.as<cd>(), y, d_stat.as<int>(), nullptr);
+    logsv_mgf_kernel<5><<<nb, tpb, 0, st>>>(d_phi.as<cd>(), dpsi, P, M, d_spec.as<ChainSpec>(), nullptr, d_a.as<cd>(), d_lm.as<cd>(), y, d_stat.as<int>(), nullptr);
   else
-    logsv_mgf_kernel<3><<<nb, tpb, 0, st>>>(d_phi.as<cd>(), nullptr, P, M, d_spec.as<ChainSpec>(), nullptr, d_a.as<cd>(), d_lm.as<cd>(), y, d_stat.as<int>(), nullptr);
+    logsv_mgf_kernel<3><<<nb, tpb, 0, st>>>(d_phi.as<cd>(), dpsi, P, M, d_spec.as<ChainSpec>(), nullptr, d_a.as<cd>(), d_lm.as<cd>(), y, d_stat.as<int>(), nullptr);
   if (int rc = launched("logsv_mgf_kernel")) return rc;
   if (Jtot > 0) {
-    fourier_vanilla_kernel<<<Jtot, kFourierThreads, 0, st>>>(d_lm.as<cd>(), d_phi.as<cd>(), P, d_ss.as<StrikeSpec>(), spot ? 1 : 0, 1, d_pr.as<double>());
+    if (qvar)
+      fourier_sum_kernel<<<Jtot, kFourierThreads, 0, st>>>(d_lm.as<cd>(), d_psi.as<cd>(), P, d_ss.as<SumSpec>(), kModeQvar, 0, d_pr.as<double>());
+    else
+      fourier_vanilla_kernel<<<Jtot, kFourierThreads, 0, st>>>(d_lm.as<cd>(), d_phi.as<cd>(), P, d_ss.as<StrikeSpec>(), spot ? 1 : 0, 1, d_pr.as<double>());
     if (int rc = launched("fourier_vanilla_kernel")) return rc;
     B200SV_CUDA(cudaMemcpyAsync(prices_out, d_pr.p, sizeof(double) * Jtot, cudaMemcpyDeviceToHost, st));
   }
@@ -499,14 +584,22 @@ int b200sv_logsv_price_chain(const b200sv_logsv_params* params, int M, const dou
 
 int b200sv_heston_price_chain(const b200sv_heston_params* params, int M, const double* ttms, const double* forwards,
                               const double* discfactors, const int* offsets, const double* strikes, const int8_t* types,
-                              double vol_scaler, int P, double* prices_out, double* log_mgf_out) {
+                              int variable_type, double vol_scaler, int P, double* prices_out, double* log_mgf_out) {
   B200SV_REQUIRE(params && ttms && forwards && discfactors && offsets && prices_out, "null pointer");
+  if (variable_type != B200SV_LOG_RETURN && variable_type != B200SV_Q_VAR) return fail(-4, "variable_type not implemented");   // heston_pricer.py:276-277
+  const bool qvar = variable_type == B200SV_Q_VAR;
+  if (P <= 0) P = qvar ? 40000 : 1000;
   B200SV_REQUIRE(M >= 1 && P >= 3, "M >= 1, P >= 3");
   const int Jtot = offsets[M] - offsets[0];
-  if (int rc = check_fourier_types(types + offsets[0], Jtot, true)) return rc;
+  if (int rc = qvar ? check_qvar_types(types + offsets[0], Jtot) : check_fourier_types(types + offsets[0], Jtot, true)) return rc;
   if (!(vol_scaler > 0.0)) vol_scaler = std::min(0.3, std::sqrt(params->v0 * ttms[0]));   // heston_pricer.py:234-235
-  std::vector<double> phi;
-  build_phi(vol_scaler, true, P, phi);
+  std::vector<double> phi, psi;
+  if (!qvar) {
+    build_phi(vol_scaler, true, P, phi);
+  } else {
+    build_grid(-0.5, 4000.0, P, psi);
+    phi.assign(2 * (size_t)P, 0.0);
+  }
   std::vector<double> dtaus(M);
   double t0 = 0.0;
   for (int m = 0; m < M; ++m) {
@@ -515,26 +608,37 @@ int b200sv_heston_price_chain(const b200sv_heston_params* params, int M, const d
     t0 = ttms[m];
   }
   std::vector<StrikeSpec> ss(std::max(Jtot, 1));
+  std::vector<SumSpec> qs(std::max(Jtot, 1));
   for (int m = 0; m < M; ++m)
     for (int j = offsets[m]; j < offsets[m + 1]; ++j) {
       B200SV_REQUIRE(strikes[j] > 0.0, "strikes must be positive");
       ss[j - offsets[0]] = StrikeSpec{strikes[j], forwards[m], discfactors[m], (int)types[j], m};
+      qs[j - offsets[0]] = SumSpec{strikes[j] * ttms[m], discfactors[m], ttms[m], (int)types[j], m};
     }
   cudaStream_t st = 0;
-  DevBuf d_phi(st), d_dt(st), d_lm(st), d_ss(st), d_pr(st);
+  DevBuf d_phi(st), d_psi(st), d_dt(st), d_lm(st), d_ss(st), d_pr(st);
   B200SV_CUDA(d_phi.alloc(sizeof(cd) * P));
+  B200SV_CUDA(d_psi.alloc(sizeof(cd) * P));
   B200SV_CUDA(d_dt.alloc(sizeof(double) * M));
   B200SV_CUDA(d_lm.alloc(sizeof(cd) * (size_t)M * P));
-  B200SV_CUDA(d_ss.alloc(sizeof(StrikeSpec) * ss.size()));
+  B200SV_CUDA(d_ss.alloc(std::max(sizeof(StrikeSpec), sizeof(SumSpec)) * ss.size()));
   B200SV_CUDA(d_pr.alloc(sizeof(double) * ss.size()));
   B200SV_CUDA(cudaMemcpyAsync(d_phi.p, phi.data(), sizeof(cd) * P, cudaMemcpyHostToDevice, st));
+  if (qvar) B200SV_CUDA(cudaMemcpyAsync(d_psi.p, psi.data(), sizeof(cd) * P, cudaMemcpyHostToDevice, st));
   B200SV_CUDA(cudaMemcpyAsync(d_dt.p, dtaus.data(), sizeof(double) * M, cudaMemcpyHostToDevice, st));
-  B200SV_CUDA(cudaMemcpyAsync(d_ss.p, ss.data(), sizeof(StrikeSpec) * ss.size(), cudaMemcpyHostToDevice, st));
+  if (qvar)
+    B200SV_CUDA(cudaMemcpyAsync(d_ss.p, qs.data(), sizeof(SumSpec) * qs.size(), cudaMemcpyHostToDevice, st));
+  else
+    B200SV_CUDA(cudaMemcpyAsync(d_ss.p, ss.data(), sizeof(StrikeSpec) * ss.size(), cudaMemcpyHostToDevice, st));
   const int tpb = mgf_block_threads(P), nb = (P + tpb - 1) / tpb;
-  heston_mgf_kernel<<<nb, tpb, 0, st>>>(d_phi.as<cd>(), nullptr, P, M, d_dt.as<double>(), *params, nullptr, nullptr, nullptr, nullptr, d_lm.as<cd>());
+  heston_mgf_kernel<<<nb, tpb, 0, st>>>(d_phi.as<cd>(), qvar ? d_psi.as<cd>() : nullptr, P, M, d_dt.as<double>(), *params, nullptr, nullptr,
+                                        nullptr, nullptr, d_lm.as<cd>());
   if (int rc = launched("heston_mgf_kernel")) return rc;
   if (Jtot > 0) {
-    fourier_vanilla_kernel<<<Jtot, kFourierThreads, 0, st>>>(d_lm.as<cd>(), d_phi.as<cd>(), P, d_ss.as<StrikeSpec>(), 1, 1, d_pr.as<double>());
+    if (qvar)
+      fourier_sum_kernel<<<Jtot, kFourierThreads, 0, st>>>(d_lm.as<cd>(), d_psi.as<cd>(), P, d_ss.as<SumSpec>(), kModeQvar, 0, d_pr.as<double>());
+    else
+      fourier_vanilla_kernel<<<Jtot, kFourierThreads, 0, st>>>(d_lm.as<cd>(), d_phi.as<cd>(), P, d_ss.as<StrikeSpec>(), 1, 1, d_pr.as<double>());
     if (int rc = launched("fourier_vanilla_kernel")) return rc;
     B200SV_CUDA(cudaMemcpyAsync(prices_out, d_pr.p, sizeof(double) * Jtot, cudaMemcpyDeviceToHost, st));
   }
@@ -631,6 +735,57 @@ int b200sv_fourier_vanilla(const double* log_mgf, const double* phi, int P, doub
   B200SV_CUDA(cudaMemcpyAsync(prices_out, d_pr.p, sizeof(double) * J, cudaMemcpyDeviceToHost, st));
   B200SV_CUDA(cudaStreamSynchronize(st));
   return 0;
+}
+
+// shared driver of the generic sums
+static int fourier_sum_host(const double* log_mgf, const double* grid, int P, const std::vector<SumSpec>& specs, int mode, int all_calls,
+                            double* out) {
+  const int J = (int)specs.size();
+  cudaStream_t st = 0;
+  DevBuf d_g(st), d_lm(st), d_ss(st), d_pr(st);
+  B200SV_CUDA(d_g.alloc(sizeof(cd) * P));
+  B200SV_CUDA(d_lm.alloc(sizeof(cd) * P));
+  B200SV_CUDA(d_ss.alloc(sizeof(SumSpec) * J));
+  B200SV_CUDA(d_pr.alloc(sizeof(double) * J));
+  B200SV_CUDA(cudaMemcpyAsync(d_g.p, grid, sizeof(cd) * P, cudaMemcpyHostToDevice, st));
+  B200SV_CUDA(cudaMemcpyAsync(d_lm.p, log_mgf, sizeof(cd) * P, cudaMemcpyHostToDevice, st));
+  B200SV_CUDA(cudaMemcpyAsync(d_ss.p, specs.data(), sizeof(SumSpec) * J, cudaMemcpyHostToDevice, st));
+  fourier_sum_kernel<<<J, kFourierThreads, 0, st>>>(d_lm.as<cd>(), d_g.as<cd>(), P, d_ss.as<SumSpec>(), mode, all_calls, d_pr.as<double>());
+  if (int rc = launched("fourier_sum_kernel")) return rc;
+  B200SV_CUDA(cudaMemcpyAsync(out, d_pr.p, sizeof(double) * J, cudaMemcpyDeviceToHost, st));
+  B200SV_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int b200sv_fourier_qvar(const double* log_mgf, const double* psi, int P, double ttm, const double* strikes, const int8_t* types, int J,
+                        double discfactor, double* prices_out) {
+  B200SV_REQUIRE(log_mgf && psi && strikes && types && prices_out, "null pointer");
+  B200SV_REQUIRE(P >= 3 && J >= 1 && ttm > 0.0, "P >= 3, J >= 1, ttm > 0");
+  if (int rc = check_qvar_types(types, J)) return rc;
+  std::vector<SumSpec> specs(J);
+  for (int j = 0; j < J; ++j) specs[j] = SumSpec{strikes[j] * ttm, discfactor, ttm, (int)types[j], 0};
+  return fourier_sum_host(log_mgf, psi, P, specs, kModeQvar, 0, prices_out);
+}
+
+int b200sv_fourier_pdf(const double* log_mgf, const double* grid, int P, const double* z, int J, double* out) {
+  B200SV_REQUIRE(log_mgf && grid && z && out, "null pointer");
+  B200SV_REQUIRE(P >= 3 && J >= 1, "P >= 3, J >= 1");
+  std::vector<SumSpec> specs(J);
+  for (int j = 0; j < J; ++j) specs[j] = SumSpec{z[j], 1.0, 1.0, 0, 0};
+  return fourier_sum_host(log_mgf, grid, P, specs, kModePdf, 0, out);
+}
+
+int b200sv_fourier_digital(const double* log_mgf, const double* phi, int P, double forward, const double* strikes, const int8_t* types,
+                           int J, double discfactor, double* prices_out) {
+  B200SV_REQUIRE(log_mgf && phi && strikes && types && prices_out, "null pointer");
+  B200SV_REQUIRE(P >= 3 && J >= 1, "P >= 3, J >= 1");
+  for (int j = 0; j < J; ++j)
+    if (types[j] != B200SV_CALL && types[j] != B200SV_PUT) return fail(-5, "not implemented");   // utils/mgf_pricer.py:265-266
+  bool all_neg = true;                                             // np.all(np.real(phi_grid) < 0.0), :241
+  for (int i = 0; i < P; ++i) all_neg = all_neg && (phi[2 * i] < 0.0);
+  std::vector<SumSpec> specs(J);
+  for (int j = 0; j < J; ++j) specs[j] = SumSpec{-std::log(forward / strikes[j]), discfactor, 1.0, (int)types[j], 0};
+  return fourier_sum_host(log_mgf, phi, P, specs, kModeDigital, all_neg ? 1 : 0, prices_out);
 }
 
 }  // extern "C"

@@ -12,8 +12,6 @@ from typing import List, Optional, Sequence
 
 import numpy as np
 
-from ..utils import bsm
-
 _VALID_TYPES = ("C", "P", "IC", "IP")
 
 
@@ -101,12 +99,12 @@ class OptionChain:
         return None
 
     def compute_model_ivols_from_chain_data(self, model_prices: Sequence[np.ndarray], forwards: np.ndarray = None) -> List[np.ndarray]:
-        """invert model prices to Black implied vols slice by slice (reference data/option_chain.py:327-346)."""
+        """invert model prices to Black implied vols for the whole chain in one GPU kernel launch (reference
+        data/option_chain.py:327-346 -> third-party ``vanilla_option_pricers``)."""
+        from .. import engine
         if forwards is None:
             forwards = self.forwards
-        return bsm.infer_bsm_ivols_from_model_chain_prices(ttms=self.ttms, forwards=forwards, discfactors=self.discfactors,
-                                                           strikes_ttms=self.strikes_ttms, optiontypes_ttms=self.optiontypes_ttms,
-                                                           model_prices_ttms=model_prices)
+        return engine.bsm_implied_vols(self.ttms, forwards, self.discfactors, self.strikes_ttms, self.optiontypes_ttms, model_prices)
 
 
 def get_btc_test_chain_data() -> OptionChain:

@@ -161,10 +161,21 @@ def _check_fourier_types(optiontypes_ttms, is_spot_measure: bool):
                 raise ValueError("not implemented")       # utils/mgf_pricer.py:206-219
 
 
+def _check_qvar_types(optiontypes_ttms):
+    for types in optiontypes_ttms:
+        for t in types:
+            if str(t) != "C":
+                raise ValueError("not implemented")       # utils/mgf_pricer.py:349-358
+
+
 def logsv_price_chain(params: C.LogsvParamsC, ttms, forwards, discfactors, etas, strikes_ttms, optiontypes_ttms,
                       is_spot_measure: bool = True, expansion_order: int = C.ORDER_SECOND, vol_scaler: Optional[float] = None,
-                      max_phi: int = 1000, return_grids: bool = False):
-    _check_fourier_types(optiontypes_ttms, is_spot_measure)
+                      max_phi: Optional[int] = None, return_grids: bool = False, variable_type: int = C.LOG_RETURN):
+    if variable_type == C.Q_VAR:
+        _check_qvar_types(optiontypes_ttms)
+    else:
+        _check_fourier_types(optiontypes_ttms, is_spot_measure)
+    max_phi = int(max_phi) if max_phi else (40000 if variable_type == C.Q_VAR else 1000)
     M, ttms, forwards, discfactors, offsets, strikes, types = _chain_arrays(ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms)
     etas = C.f64(np.ones(M) if etas is None else etas)
     n = 3 if expansion_order == C.ORDER_FIRST else 5
@@ -172,7 +183,7 @@ def logsv_price_chain(params: C.LogsvParamsC, ttms, forwards, discfactors, etas,
     a_out = np.empty((M, max_phi, n), dtype=np.complex128) if return_grids else None
     lm_out = np.empty((M, max_phi), dtype=np.complex128) if return_grids else None
     C.call("b200sv_logsv_price_chain", byref(params), M, C.dptr(ttms), C.dptr(forwards), C.dptr(discfactors), C.dptr(etas),
-           C.iptr(offsets), C.dptr(strikes), C.i8ptr(types), int(bool(is_spot_measure)), int(expansion_order),
+           C.iptr(offsets), C.dptr(strikes), C.i8ptr(types), int(bool(is_spot_measure)), int(variable_type), int(expansion_order),
            float(vol_scaler) if vol_scaler is not None else -1.0, int(max_phi), C.dptr(prices),
            a_out.ctypes.data_as(C._dp) if return_grids else None, lm_out.ctypes.data_as(C._dp) if return_grids else None)
     out = C.split_chain(prices, offsets)
@@ -180,14 +191,19 @@ def logsv_price_chain(params: C.LogsvParamsC, ttms, forwards, discfactors, etas,
 
 
 def heston_price_chain(params: C.HestonParamsC, ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms,
-                       vol_scaler: Optional[float] = None, max_phi: int = 1000, return_grids: bool = False):
-    _check_fourier_types(optiontypes_ttms, True)
+                       vol_scaler: Optional[float] = None, max_phi: Optional[int] = None, return_grids: bool = False,
+                       variable_type: int = C.LOG_RETURN):
+    if variable_type == C.Q_VAR:
+        _check_qvar_types(optiontypes_ttms)
+    else:
+        _check_fourier_types(optiontypes_ttms, True)
+    max_phi = int(max_phi) if max_phi else (40000 if variable_type == C.Q_VAR else 1000)
     M, ttms, forwards, discfactors, offsets, strikes, types = _chain_arrays(ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms)
     prices = np.empty(strikes.shape[0])
     lm_out = np.empty((M, max_phi), dtype=np.complex128) if return_grids else None
     C.call("b200sv_heston_price_chain", byref(params), M, C.dptr(ttms), C.dptr(forwards), C.dptr(discfactors), C.iptr(offsets),
-           C.dptr(strikes), C.i8ptr(types), float(vol_scaler) if vol_scaler is not None else -1.0, int(max_phi), C.dptr(prices),
-           lm_out.ctypes.data_as(C._dp) if return_grids else None)
+           C.dptr(strikes), C.i8ptr(types), int(variable_type), float(vol_scaler) if vol_scaler is not None else -1.0, int(max_phi),
+           C.dptr(prices), lm_out.ctypes.data_as(C._dp) if return_grids else None)
     out = C.split_chain(prices, offsets)
     return (out, lm_out) if return_grids else out
 
@@ -227,3 +243,58 @@ def fourier_vanilla(log_mgf, phi, forward, strikes, optiontypes, discfactor=1.0,
     C.call("b200sv_fourier_vanilla", log_mgf.ctypes.data_as(C._dp), phi.ctypes.data_as(C._dp), phi.shape[0], float(forward),
            C.dptr(strikes), C.i8ptr(types), J, float(discfactor), int(bool(is_spot_measure)), C.dptr(prices))
     return prices
+
+
+def fourier_qvar(log_mgf, psi, ttm, strikes, optiontypes, discfactor=1.0):
+    _check_qvar_types([optiontypes])
+    log_mgf, psi, strikes = C.c128(log_mgf), C.c128(psi), C.f64(strikes)
+    types = C.encode_types(optiontypes)
+    prices = np.empty(strikes.shape[0])
+    C.call("b200sv_fourier_qvar", log_mgf.ctypes.data_as(C._dp), psi.ctypes.data_as(C._dp), psi.shape[0], float(ttm), C.dptr(strikes),
+           C.i8ptr(types), strikes.shape[0], float(discfactor), C.dptr(prices))
+    return prices
+
+
+def fourier_pdf_sums(log_mgf, grid, z):
+    log_mgf, grid, z = C.c128(log_mgf), C.c128(grid), C.f64(z)
+    out = np.empty(z.shape[0])
+    C.call("b200sv_fourier_pdf", log_mgf.ctypes.data_as(C._dp), grid.ctypes.data_as(C._dp), grid.shape[0], C.dptr(z), z.shape[0], C.dptr(out))
+    return out
+
+
+def fourier_digital(log_mgf, phi, forward, strikes, optiontypes, discfactor=1.0):
+    for t in optiontypes:
+        if str(t) not in ("C", "P"):
+            raise ValueError("not implemented")           # utils/mgf_pricer.py:265-266
+    log_mgf, phi, strikes = C.c128(log_mgf), C.c128(phi), C.f64(strikes)
+    types = C.encode_types(optiontypes)
+    prices = np.empty(strikes.shape[0])
+    C.call("b200sv_fourier_digital", log_mgf.ctypes.data_as(C._dp), phi.ctypes.data_as(C._dp), phi.shape[0], float(forward), C.dptr(strikes),
+           C.i8ptr(types), strikes.shape[0], float(discfactor), C.dptr(prices))
+    return prices
+
+
+def bsm_implied_vols(ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms, prices_ttms):
+    """Black-76 implied vols of a whole chain in one kernel launch."""
+    M, ttms, forwards, discfactors, offsets, strikes, types = _chain_arrays(ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms)
+    prices = C.f64(np.concatenate([np.asarray(p, dtype=np.float64).ravel() for p in prices_ttms]))
+    if prices.shape[0] != strikes.shape[0]:
+        raise ValueError("model prices and strikes must have the same length")
+    ivols = np.empty(strikes.shape[0])
+    C.call("b200sv_bsm_implied_vols", M, C.dptr(ttms), C.dptr(forwards), C.dptr(discfactors), C.iptr(offsets), C.dptr(strikes),
+           C.i8ptr(types), C.dptr(prices), C.dptr(ivols))
+    return C.split_chain(ivols, offsets)
+
+
+def logsv_vol_paths(params: C.LogsvParamsC, ttm: float, nb_path: int, nb_steps_per_year: int, is_spot_measure: bool, seed: int,
+                    brownians=None):
+    from .utils.funcs import set_time_grid
+    nb_steps, _, grid_t = set_time_grid(ttm, nb_steps_per_year)
+    if brownians is not None:
+        brownians = C.f64(brownians)
+        if brownians.shape != (nb_steps, nb_path):
+            raise ValueError(f"brownians must have shape ({nb_steps}, {nb_path})")
+    sigma_t = np.empty((nb_steps + 1, nb_path))
+    C.call("b200sv_logsv_vol_paths", byref(params), float(ttm), int(nb_path), int(nb_steps_per_year), int(bool(is_spot_measure)),
+           int(seed) & 0xFFFFFFFFFFFFFFFF, C.dptr(brownians) if brownians is not None else None, C.dptr(sigma_t))
+    return sigma_t, grid_t

@@ -79,11 +79,12 @@ def heston_chain_pricer(v0: float, theta: float, kappa: float, volvol: float, rh
                         strikes_ttms, optiontypes_ttms, discfactors: np.ndarray,
                         variable_type: VariableType = VariableType.LOG_RETURN, vol_scaler: float = None, **kwargs) -> List[np.ndarray]:
     """Fourier chain pricer (reference :217-282), one fused GPU call for the chain."""
-    if getattr(variable_type, "value", variable_type) != 1:
-        raise NotImplementedError(f"variable_type={variable_type}")      # Q_VAR Fourier: SURVEY.md §8f #3
+    vt = getattr(variable_type, "value", variable_type)
+    if vt not in (1, 2):
+        raise NotImplementedError(f"variable_type={variable_type}")      # heston_pricer.py:276-277
     return engine.heston_price_chain(_params_c(v0, theta, kappa, rho, volvol), ttms, forwards, discfactors, strikes_ttms,
-                                     optiontypes_ttms, vol_scaler=vol_scaler, max_phi=int(kwargs.get("max_phi", 1000)),
-                                     return_grids=bool(kwargs.get("return_grids", False)))
+                                     optiontypes_ttms, vol_scaler=vol_scaler, max_phi=kwargs.get("max_phi"),
+                                     return_grids=bool(kwargs.get("return_grids", False)), variable_type=vt)
 
 
 def heston_mc_chain_pricer(ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms, v0: float, theta: float, kappa: float,

@@ -127,6 +127,16 @@ class LogSVPricer(ModelPricer):
                                      gauss=kwargs.get("gauss", "fp32"), distributed=kwargs.get("distributed", True))
 
     @timer
+    def simulate_vol_paths(self, params: LogSvParams, brownians: np.ndarray = None, ttm: float = 1.0, nb_path: int = 100000,
+                           is_spot_measure: bool = True, nb_steps: int = None, year_days: int = 360, **kwargs) -> Tuple[np.ndarray, np.ndarray]:
+        """volatility paths on the time grid, ``(sigma_t [nb_steps+1, nb_path], grid_t)`` (reference :561-587): note the reference
+        passes ``nb_steps or ceil(year_days*ttm)`` as the PER-YEAR rate of ``set_time_grid`` -- reproduced."""
+        nb_steps = nb_steps or int(np.ceil(year_days * ttm))
+        return simulate_vol_paths(ttm=ttm, v0=params.sigma0, theta=params.theta, kappa1=params.kappa1, kappa2=params.kappa2,
+                                  beta=params.beta, volvol=params.volvol, nb_path=nb_path, is_spot_measure=is_spot_measure,
+                                  nb_steps_per_year=nb_steps, brownians=brownians, seed=kwargs.get("seed"))
+
+    @timer
     def simulate_terminal_values(self, params: LogSvParams, ttm: float = 1.0, nb_path: int = 100000, is_spot_measure: bool = True,
                                  **kwargs) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
         """terminal (log-return, vol, quadratic variance), float64[nb_path] each; 360 steps/year and eta = 1 as in the
@@ -136,6 +146,14 @@ class LogSVPricer(ModelPricer):
                                              volvol=params.volvol, nb_path=nb_path, is_spot_measure=is_spot_measure,
                                              nb_steps_per_year=kwargs.get("nb_steps_per_year", 360), seed=kwargs.get("seed"),
                                              gauss=kwargs.get("gauss", "fp32"))
+
+
+def _pricer_logsv_pdfs(self, params: LogSvParams, ttm: float, space_grid: np.ndarray, **kwargs) -> np.ndarray:
+    """``LogSVPricer.logsv_pdfs`` (reference :613-637)."""
+    return logsv_pdfs(params=params, ttm=ttm, space_grid=space_grid, **kwargs)
+
+
+LogSVPricer.logsv_pdfs = _pricer_logsv_pdfs
 
 
 def set_vol_scaler(sigma0: float, ttm: float) -> float:
@@ -151,15 +169,43 @@ def logsv_chain_pricer(params: LogSvParams, ttms: np.ndarray, forwards: np.ndarr
     """Fourier chain pricer (reference :669-739): one fused GPU call for the whole chain -- transform grid, RK45 ODE solves of the
     affine expansion carried across maturities, log-MGF, Simpson sums.  ``return_grids=True`` additionally returns
     (a_t1 [M,P,n], log_mgf [M,P])."""
-    if variable_type != VariableType.LOG_RETURN and getattr(variable_type, "value", variable_type) != 1:
-        raise NotImplementedError       # Q_VAR Fourier route: SURVEY.md §8f #3; SIGMA: reference raises too (:733-734)
+    vt = getattr(variable_type, "value", variable_type)
+    if vt not in (1, 2):
+        raise NotImplementedError       # SIGMA: the reference raises too (:733-734)
     if is_stiff_solver or is_analytic:
         raise NotImplementedError("only the default RK45 branch is implemented on the GPU")
     order = _order_code(expansion_order)
     etas = np.array([params.get_vol_backbone_eta(tau=ttm) for ttm in ttms], dtype=float)
     return engine.logsv_price_chain(_params_c(params), ttms, forwards, discfactors, etas, strikes_ttms, optiontypes_ttms,
                                     is_spot_measure=is_spot_measure, expansion_order=order, vol_scaler=vol_scaler,
-                                    max_phi=int(kwargs.get("max_phi", 1000)), return_grids=bool(kwargs.get("return_grids", False)))
+                                    max_phi=kwargs.get("max_phi"), return_grids=bool(kwargs.get("return_grids", False)), variable_type=vt)
+
+
+def logsv_pdfs(params: LogSvParams, ttm: float, space_grid: np.ndarray, is_stiff_solver: bool = False, is_analytic: bool = False,
+               is_spot_measure: bool = True, expansion_order: ExpansionOrder = ExpansionOrder.SECOND,
+               variable_type: VariableType = VariableType.LOG_RETURN, vol_scaler: float = None) -> np.ndarray:
+    """model density of the log-return, the quadratic variance or the volatility on ``space_grid`` (reference :742-803): ODE grid
+    solve on the GPU from the variable's initial condition, then the Fourier density sums on the GPU."""
+    from ..utils import mgf_pricer as mgfp
+    from .logsv.affine_expansion import compute_logsv_a_mgf_grid
+    if vol_scaler is None:
+        vol_scaler = set_vol_scaler(sigma0=params.sigma0, ttm=ttm)
+    phi_grid, psi_grid, theta_grid = mgfp.get_transform_var_grid(variable_type=variable_type, is_spot_measure=is_spot_measure,
+                                                                 vol_scaler=vol_scaler)
+    _, log_mgf_grid = compute_logsv_a_mgf_grid(ttm=ttm, phi_grid=phi_grid, psi_grid=psi_grid, theta_grid=theta_grid, sigma0=params.sigma0,
+                                               theta=params.theta, kappa1=params.kappa1, kappa2=params.kappa2, beta=params.beta,
+                                               volvol=params.volvol, variable_type=variable_type, expansion_order=expansion_order,
+                                               is_stiff_solver=is_stiff_solver, is_analytic=is_analytic, is_spot_measure=is_spot_measure)
+    vt = getattr(variable_type, "value", variable_type)
+    if vt == 1:
+        grid, shift, scale = phi_grid, 0.0, 1.0
+    elif vt == 2:
+        grid, shift, scale = psi_grid, 0.0, 1.0 / ttm          # scaled by ttm (:785-788)
+    elif vt == 3:
+        grid, shift, scale = theta_grid, params.theta, 1.0
+    else:
+        raise NotImplementedError
+    return mgfp.pdf_with_mgf_grid(log_mgf_grid=log_mgf_grid, transform_var_grid=grid, space_grid=space_grid, shift=shift, scale=scale) / scale
 
 
 def logsv_mc_chain_pricer(ttms: np.ndarray, forwards: np.ndarray, discfactors: np.ndarray, strikes_ttms, optiontypes_ttms,
@@ -182,6 +228,15 @@ def logsv_mc_chain_pricer(ttms: np.ndarray, forwards: np.ndarray, discfactors: n
                                     engine.variable_code(variable_type), seed, flags)
     return engine.logsv_mc_chain(params_c, ttms, forwards, discfactors, vol_backbone_etas, strikes_ttms, optiontypes_ttms, nb_path,
                                  nb_steps_per_year, is_spot_measure, variable_type, seed, flags)
+
+
+def simulate_vol_paths(ttm: float, v0: float, theta: float, kappa1: float, kappa2: float, beta: float, volvol: float,
+                       is_spot_measure: bool = True, nb_path: int = 100000, nb_steps_per_year: int = 360, brownians: np.ndarray = None,
+                       seed: Optional[int] = None, **kwargs) -> Tuple[np.ndarray, np.ndarray]:
+    """full volatility paths (reference :870-947) on the GPU; ``brownians`` = pre-drawn SCALED increments [nb_steps, nb_path]."""
+    seed = engine.fresh_seed() if seed is None else int(seed)
+    return engine.logsv_vol_paths(engine.logsv_params_c(v0, theta, kappa1, kappa2, beta, volvol), ttm, nb_path, nb_steps_per_year,
+                                  is_spot_measure, seed, brownians)
 
 
 def simulate_logsv_x_vol_terminal(ttm: float, x0: np.ndarray, sigma0: np.ndarray, qvar0: np.ndarray, theta: float, kappa1: float,

@@ -17,12 +17,30 @@ def get_phi_grid(is_spot_measure: bool = True, max_phi: int = 1000, vol_scaler: 
     return real_phi + 1j * p
 
 
+def get_psi_grid() -> np.ndarray:
+    """transform grid for the quadratic variance: -1/2 + i*linspace(0, 4000, 40000) (utils/mgf_pricer.py:37-47)."""
+    return -0.5 + 1j * np.linspace(0, 4000, 40000)
+
+
+def get_theta_grid() -> np.ndarray:
+    """transform grid for the volatility: i*linspace(0, 600, 5000) (utils/mgf_pricer.py:50-58)."""
+    return 0.0 + 1j * np.linspace(0, 600, 5000)
+
+
 def get_transform_var_grid(variable_type: VariableType = VariableType.LOG_RETURN, is_spot_measure: bool = True, max_phi: int = 1000,
                            vol_scaler: float = 0.28, real_phi: float = None) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
-    """(phi, psi, theta) grids for LOG_RETURN (utils/mgf_pricer.py:61-77); Q_VAR / SIGMA grids are SURVEY.md §8f "next"."""
-    if variable_type == VariableType.LOG_RETURN:
+    """(phi, psi, theta) grids for Fourier inversion in each state variable (utils/mgf_pricer.py:61-94)."""
+    vt = getattr(variable_type, "value", variable_type)
+    if vt == 1:
         phi_grid = get_phi_grid(is_spot_measure=is_spot_measure, max_phi=max_phi, vol_scaler=vol_scaler, real_phi=real_phi)
         return phi_grid, np.zeros_like(phi_grid), np.zeros_like(phi_grid)
+    if vt == 2:
+        psi_grid = get_psi_grid()
+        phi_grid = np.zeros_like(psi_grid) if is_spot_measure else np.ones_like(psi_grid)
+        return phi_grid, psi_grid, np.zeros_like(psi_grid)
+    if vt == 3:
+        theta_grid = get_theta_grid()
+        return np.zeros_like(theta_grid), np.zeros_like(theta_grid), theta_grid
     raise NotImplementedError
 
 
@@ -31,3 +49,25 @@ def vanilla_slice_pricer_with_mgf_grid(log_mgf_grid: np.ndarray, phi_grid: np.nd
     """Simpson-weighted Fourier inversion for vanilla options on the GPU (utils/mgf_pricer.py:174-221): legacy weights on the
     even-length grid, nansum, MMA measure rejects 'IC'/'IP' with ``ValueError("not implemented")``."""
     return engine.fourier_vanilla(log_mgf_grid, phi_grid, forward, strikes, optiontypes, discfactor, is_spot_measure)
+
+
+def slice_qvar_pricer_with_a_grid(log_mgf_grid: np.ndarray, psi_grid: np.ndarray, ttm: float, strikes: np.ndarray, optiontypes: np.ndarray,
+                                  forward: float, discfactor: float = 1.0, is_spot_measure: bool = True) -> np.ndarray:
+    """calls on the annualised quadratic variance from the log-MGF on the psi grid, on the GPU (utils/mgf_pricer.py:323-358);
+    anything but 'C' raises ``ValueError("not implemented")``; ``forward`` is accepted and unused as in the reference."""
+    return engine.fourier_qvar(log_mgf_grid, psi_grid, ttm, strikes, optiontypes, discfactor)
+
+
+def digital_slice_pricer_with_mgf_grid(log_mgf_grid: np.ndarray, phi_grid: np.ndarray, forward: float, strikes: np.ndarray,
+                                       optiontypes: np.ndarray, discfactor: float = 1.0) -> np.ndarray:
+    """digital calls / puts on the spot from the log-MGF grid, on the GPU (utils/mgf_pricer.py:224-269)."""
+    return engine.fourier_digital(log_mgf_grid, phi_grid, forward, strikes, optiontypes, discfactor)
+
+
+def pdf_with_mgf_grid(log_mgf_grid: np.ndarray, transform_var_grid: np.ndarray, space_grid: np.ndarray, shift: float = 0.0,
+                      scale: float = 1.0) -> np.ndarray:
+    """density on ``space_grid`` by Fourier inversion of the log-MGF, sums on the GPU (utils/mgf_pricer.py:361-384)."""
+    space_grid = np.asarray(space_grid, dtype=np.float64)
+    z = (space_grid - shift) / scale
+    dx = space_grid[1] - space_grid[0]
+    return dx * engine.fourier_pdf_sums(log_mgf_grid, transform_var_grid, z)

@@ -361,7 +361,101 @@ def reference_mc():
     np.savez(os.path.join(OUT, "refmc_heston_g4.npz"), versions=versions, **out)
 
 
+def next_rows():
+    """SURVEY.md §8f #3: Q_VAR / density / digital Fourier routes (psi grid P = 40000, theta grid P = 5000)."""
+    _import_reference()
+    import scipy
+    import numba
+    from stochvolmodels.pricers import logsv_pricer as lp
+    from stochvolmodels.pricers import heston_pricer as hp
+    from stochvolmodels.pricers.logsv import affine_expansion as afe
+    from stochvolmodels.pricers.logsv.logsv_params import LogSvParams
+    from stochvolmodels.utils import mgf_pricer as mgfp
+    from stochvolmodels.utils.config import VariableType
+    versions = np.array([f"numpy={np.__version__}", f"scipy={scipy.__version__}", f"numba={numba.__version__}"])
+    Q = LogSvParams(sigma0=1.0, theta=1.0, kappa1=5.0, kappa2=5.0, beta=0.2, volvol=2.0)
+    p6 = np.array([1.0, 1.0, 5.0, 5.0, 0.2, 2.0])
+
+    # ---- LogSV options on quadratic variance, both measures (logsv_pricer.py:723-731 -> mgf_pricer.py:323-358)
+    ttms = np.array([0.25, 0.5])
+    kq = np.array([0.5, 0.8, 1.0, 1.2, 1.6])
+    tq = np.array(['C'] * 5)
+    for spot, tag in ((True, "mma"), (False, "inv")):
+        prices = lp.logsv_chain_pricer(params=Q, ttms=ttms, forwards=np.ones(2), discfactors=np.array([1.0, 0.98]),
+                                       strikes_ttms=(kq, kq), optiontypes_ttms=(tq, tq), is_spot_measure=spot,
+                                       variable_type=VariableType.Q_VAR)
+        phi, psi, theta = mgfp.get_transform_var_grid(variable_type=VariableType.Q_VAR, is_spot_measure=spot)
+        out = dict(params=p6, ttms=ttms, discfactors=np.array([1.0, 0.98]), strikes=kq, is_spot=np.array(spot), psi_head=psi[:4],
+                   psi_tail=psi[-2:], phi0=phi[0], npsi=np.array(psi.shape[0]))
+        a = np.zeros((psi.shape[0], 5), dtype=np.complex128)
+        t0 = 0.0
+        for m, ttm in enumerate(ttms):
+            a, lm = afe.compute_logsv_a_mgf_grid(ttm=ttm - t0, phi_grid=phi, psi_grid=psi, theta_grid=theta, a_t0=a,
+                                                 is_spot_measure=spot, **Q.to_dict())
+            t0 = ttm
+            out[f"a_sub_{m}"], out[f"log_mgf_sub_{m}"], out[f"prices_{m}"] = a[::40].copy(), lm[::40].copy(), np.asarray(prices[m])
+        np.savez(os.path.join(OUT, f"logsv_fourier_qvar_{tag}.npz"), versions=versions, **out)
+        print("qvar", tag, [np.asarray(p_) for p_ in prices])
+
+    # ---- densities (logsv_pricer.py:742-803 -> mgf_pricer.py:361-384)
+    grids = {"LOG_RETURN": np.linspace(-2.0, 1.5, 71), "Q_VAR": np.linspace(0.02, 3.0, 60), "SIGMA": np.linspace(0.05, 3.0, 60)}
+    out = dict(params=p6, ttm=np.array(0.25))
+    for vt in (VariableType.LOG_RETURN, VariableType.Q_VAR, VariableType.SIGMA):
+        pdf = lp.logsv_pdfs(params=Q, ttm=0.25, space_grid=grids[vt.name], variable_type=vt)
+        out[f"grid_{vt.name}"], out[f"pdf_{vt.name}"] = grids[vt.name], pdf
+        print("pdf", vt.name, pdf[:3], pdf.sum())
+    np.savez(os.path.join(OUT, "logsv_pdfs.npz"), versions=versions, **out)
+
+    # ---- Heston options on quadratic variance (heston_pricer.py:217-282 with Q_VAR)
+    prices = hp.heston_chain_pricer(v0=0.04, theta=0.04, kappa=4.0, volvol=0.4, rho=-0.5, ttms=ttms, forwards=np.ones(2),
+                                    strikes_ttms=(0.04 * kq, 0.04 * kq), optiontypes_ttms=(tq, tq), discfactors=np.array([1.0, 0.98]),
+                                    variable_type=VariableType.Q_VAR)
+    np.savez(os.path.join(OUT, "heston_fourier_qvar.npz"), versions=versions, params=np.array([0.04, 0.04, 4.0, -0.5, 0.4]), ttms=ttms,
+             discfactors=np.array([1.0, 0.98]), strikes=0.04 * kq, prices_0=np.asarray(prices[0]), prices_1=np.asarray(prices[1]))
+    print("heston qvar", [np.asarray(p_) for p_ in prices])
+
+    # ---- digitals on a closed-form lognormal MGF (mgf_pricer.py:224-269), both signs of Re(phi)
+    vol, ttm = 0.3, 0.4
+    K5 = np.array([0.8, 0.9, 1.0, 1.1, 1.2])
+    T5 = np.array(['P', 'P', 'C', 'C', 'C'])
+    for spot, tag in ((True, "neg"), (False, "pos")):
+        phi, _, _ = mgfp.get_transform_var_grid(variable_type=VariableType.LOG_RETURN, is_spot_measure=spot, vol_scaler=vol * np.sqrt(ttm))
+        log_mgf = 0.5 * vol * vol * ttm * (phi * phi + phi)
+        prices = mgfp.digital_slice_pricer_with_mgf_grid(log_mgf_grid=log_mgf, phi_grid=phi, forward=1.5, strikes=1.5 * K5,
+                                                         optiontypes=T5, discfactor=0.9)
+        np.savez(os.path.join(OUT, f"fourier_digital_{tag}.npz"), versions=versions, phi=phi, log_mgf=log_mgf, forward=np.array(1.5),
+                 strikes=1.5 * K5, types=T5, discfactor=np.array(0.9), prices=prices)
+        print("digital", tag, prices)
+
+
+def vol_paths():
+    """SURVEY.md §8f #4a: simulate_vol_paths with caller-supplied scaled increments (pricers/logsv_pricer.py:870-947)."""
+    _import_reference()
+    from stochvolmodels.pricers import logsv_pricer as lp
+    from stochvolmodels.utils.funcs import set_time_grid
+    out = {}
+    for tag, spot in (("mma", True), ("inv", False)):
+        S, dt, grid = set_time_grid(0.1, 360)
+        W = np.sqrt(dt) * np.random.RandomState(5).normal(0, 1, size=(S, 500))
+        sig, grid_t = lp.simulate_vol_paths(ttm=0.1, v0=0.8376, theta=1.0413, kappa1=3.1844, kappa2=3.058, beta=0.1514, volvol=1.8458,
+                                            is_spot_measure=spot, nb_path=500, nb_steps_per_year=360, brownians=W)
+        out[f"sigma_t_{tag}"], out[f"grid_t_{tag}"] = sig, grid_t
+    out["params"] = np.array([0.8376, 1.0413, 3.1844, 3.058, 0.1514, 1.8458])
+    # the class method: nb_steps=None -> per-year rate ceil(year_days*ttm) (logsv_pricer.py:574)
+    sig, grid_t = lp.LogSVPricer().simulate_vol_paths(params=lp.LOGSV_BTC_PARAMS, ttm=0.02, nb_path=4)
+    out["method_shape"] = np.array(sig.shape)
+    out["method_grid"] = grid_t
+    np.savez(os.path.join(OUT, "logsv_vol_paths.npz"), **out)
+    print("vol paths", out["sigma_t_mma"].shape, out["method_shape"])
+
+
 if __name__ == "__main__":
+    if "--only-volpaths" in sys.argv:
+        vol_paths()
+        sys.exit(0)
+    if "--only-next" in sys.argv:
+        next_rows()
+        sys.exit(0)
     if "--only-refmc" not in sys.argv:
         main()
     if "--skip-refmc" not in sys.argv:

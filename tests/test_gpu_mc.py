@@ -262,3 +262,24 @@ def test_path_offset_makes_shards_consistent(cuda_lib):
     np.testing.assert_array_equal(np.concatenate([a, b], axis=1), full)
     np.testing.assert_allclose(ma + mb, mfull, rtol=1e-13)
     assert mfull[1] == N
+
+
+def test_logsv_vol_paths_vs_reference_golden(cuda_lib):
+    """simulate_vol_paths (SURVEY.md §8f #4a): fixed increments == reference; Philox draws == oracle fed with the device normals."""
+    from stochvolmodels_b200 import LOGSV_BTC_PARAMS, LogSVPricer, engine, _capi as C
+    from stochvolmodels_b200.pricers.logsv_pricer import simulate_vol_paths
+    g = load_golden("logsv_vol_paths.npz")
+    S, dt = mc.set_time_grid(0.1, 360)
+    W = np.sqrt(dt) * np.random.RandomState(5).normal(0, 1, size=(S, 500))
+    for tag, spot in (("mma", True), ("inv", False)):
+        sig, grid_t = simulate_vol_paths(0.1, *g["params"], is_spot_measure=spot, nb_path=500, nb_steps_per_year=360, brownians=W)
+        np.testing.assert_allclose(sig, g[f"sigma_t_{tag}"], rtol=0, atol=1e-12)
+        np.testing.assert_array_equal(grid_t, g[f"grid_t_{tag}"])
+    sig, grid_t = LogSVPricer().simulate_vol_paths(params=LOGSV_BTC_PARAMS, ttm=0.02, nb_path=4, seed=1)
+    assert sig.shape == tuple(g["method_shape"]) and np.all(sig > 0) and np.all(sig[0] == LOGSV_BTC_PARAMS.sigma0)
+    np.testing.assert_array_equal(grid_t, g["method_grid"])
+    # Philox route: Z0 of the fp64 stream, slice 0
+    N, seed = 3000, 9
+    z0, _ = engine.device_normals(seed, 0, N, 0, S, C.GAUSS_F64)
+    sig, _ = simulate_vol_paths(0.1, *g["params"], nb_path=N, nb_steps_per_year=360, seed=seed)
+    np.testing.assert_allclose(sig, mc.logsv_vol_paths(*g["params"], np.sqrt(dt) * z0, dt, True), rtol=0, atol=1e-11)

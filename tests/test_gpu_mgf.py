@@ -121,3 +121,84 @@ def test_heston_pricer_api(cuda_lib):
     prices = HestonPricer().price_chain(chain, HestonParams(), variable_type=VariableType.LOG_RETURN, some_unknown_kwarg=1)
     for m in range(2):
         np.testing.assert_allclose(prices[m], g[f"prices_{m}"], rtol=1e-10, atol=1e-13)
+
+
+# ---- SURVEY.md §8f rows #1 and #3 -------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["mma", "inv"])
+def test_logsv_qvar_fourier_chain_vs_reference_golden(cuda_lib, tag):
+    """40,000 RK45 solves per maturity on the psi grid (the reference needs ~80 s per maturity)."""
+    from stochvolmodels_b200 import LogSvParams, VariableType
+    from stochvolmodels_b200.pricers.logsv_pricer import logsv_chain_pricer
+    g = load_golden(f"logsv_fourier_qvar_{tag}.npz")
+    K, T = g["strikes"], np.array(["C"] * len(g["strikes"]))
+    prices, a, lm = logsv_chain_pricer(LogSvParams(*g["params"]), g["ttms"], np.ones(2), g["discfactors"], [K, K], [T, T],
+                                       is_spot_measure=bool(g["is_spot"]), variable_type=VariableType.Q_VAR, return_grids=True)
+    assert a.shape == (2, 40000, 5)
+    for m in range(2):
+        np.testing.assert_allclose(a[m][::40], g[f"a_sub_{m}"], rtol=0, atol=1e-10)
+        np.testing.assert_allclose(lm[m][::40], g[f"log_mgf_sub_{m}"], rtol=0, atol=1e-10)
+        np.testing.assert_allclose(prices[m], g[f"prices_{m}"], rtol=1e-10)
+    with pytest.raises(ValueError, match="not implemented"):
+        logsv_chain_pricer(LogSvParams(*g["params"]), g["ttms"][:1], np.ones(1), np.ones(1), [K], [np.array(["P"] * 5)],
+                           variable_type=VariableType.Q_VAR)
+
+
+def test_logsv_pdfs_vs_reference_golden(cuda_lib):
+    from stochvolmodels_b200 import LogSvParams, LogSVPricer, VariableType
+    g = load_golden("logsv_pdfs.npz")
+    for vt in (VariableType.LOG_RETURN, VariableType.Q_VAR, VariableType.SIGMA):
+        pdf = LogSVPricer().logsv_pdfs(LogSvParams(*g["params"]), ttm=float(g["ttm"]), space_grid=g[f"grid_{vt.name}"], variable_type=vt)
+        np.testing.assert_allclose(pdf, g[f"pdf_{vt.name}"], rtol=1e-9, atol=1e-12)
+
+
+def test_heston_qvar_and_digitals_vs_reference_golden(cuda_lib):
+    from stochvolmodels_b200 import VariableType
+    from stochvolmodels_b200.pricers.heston_pricer import heston_chain_pricer
+    from stochvolmodels_b200.utils.mgf_pricer import digital_slice_pricer_with_mgf_grid, slice_qvar_pricer_with_a_grid
+    g = load_golden("heston_fourier_qvar.npz")
+    K, T = g["strikes"], np.array(["C"] * len(g["strikes"]))
+    v0, theta, kappa, rho, volvol = g["params"]
+    prices = heston_chain_pricer(v0, theta, kappa, volvol, rho, g["ttms"], np.ones(2), [K, K], [T, T], g["discfactors"], variable_type=VariableType.Q_VAR)
+    for m in range(2):
+        np.testing.assert_allclose(prices[m], g[f"prices_{m}"], rtol=1e-10, atol=1e-14)
+    for tag in ("neg", "pos"):
+        d = load_golden(f"fourier_digital_{tag}.npz")
+        p = digital_slice_pricer_with_mgf_grid(d["log_mgf"], d["phi"], float(d["forward"]), d["strikes"], d["types"], float(d["discfactor"]))
+        np.testing.assert_allclose(p, d["prices"], rtol=1e-12)
+    with pytest.raises(ValueError, match="not implemented"):
+        digital_slice_pricer_with_mgf_grid(d["log_mgf"], d["phi"], 1.5, d["strikes"][:1], np.array(["IC"]))
+    with pytest.raises(ValueError, match="not implemented"):
+        slice_qvar_pricer_with_a_grid(d["log_mgf"], d["phi"], 0.25, d["strikes"][:1], np.array(["P"]), 1.0)
+
+
+def test_gpu_black_implied_vols(cuda_lib):
+    """the chain inversion kernel == the host checker (same bisection) and the reference's pinned quickstart vols; round trips."""
+    from oracle import bsm
+    from stochvolmodels_b200 import OptionChain, engine
+    K = np.array([0.6, 0.9, 1.0, 1.1, 1.6])
+    types = np.array(["P", "P", "C", "IC", "C"])
+    ttms, fw, df = np.array([0.1, 0.5, 2.0]), np.array([1.0, 1.03, 0.97]), np.array([0.999, 0.97, 0.9])
+    vols = [0.05, 0.2, 1.5]
+    prices = [bsm.compute_bsm_vanilla_price(fw[m], K, ttms[m], vols[m], types, df[m]) for m in range(3)]
+    iv = engine.bsm_implied_vols(ttms, fw, df, [K] * 3, [types] * 3, prices)
+    host = bsm.infer_bsm_ivols_from_model_chain_prices(ttms, fw, df, [K] * 3, [types] * 3, prices)
+    for m in range(3):
+        good = prices[m] > 1e-14
+        np.testing.assert_allclose(iv[m][good], vols[m], rtol=1e-8)
+        np.testing.assert_allclose(iv[m], host[m], rtol=1e-12, equal_nan=True)
+    chain = OptionChain.slice_to_chain(0.25, 1.0, np.array([1.0, 1.0]), np.array(["C", "C"]))
+    out = chain.compute_model_ivols_from_chain_data([np.array([0.197330882838064, 1.5])])[0]
+    np.testing.assert_allclose(out[0], 0.999577, rtol=5e-6)            # examples/getting_started/quickstart.py:44
+    assert np.isnan(out[1])                                              # above the no-arbitrage bound
+
+
+def test_mc_chain_implied_vols_api(cuda_lib):
+    """ModelPricer.compute_mc_chain_implied_vols (reference model_pricer.py:216-241): 7 lists, bands ordered."""
+    from stochvolmodels_b200 import LogSvParams, LogSVPricer, OptionChain
+    chain = OptionChain(ttms=np.array([0.25, 0.5]), forwards=np.ones(2), strikes_ttms=[K5, K5], optiontypes_ttms=[T5, T5])
+    out = LogSVPricer().compute_mc_chain_implied_vols(chain, LogSvParams(1.0, 1.0, 5.0, 5.0, 0.2, 2.0), nb_path=200_000, nb_steps=252, seed=3)
+    assert len(out) == 7
+    prices, ups, downs, mid, up, down, ses = out
+    for m in range(2):
+        assert np.all(downs[m] <= prices[m]) and np.all(prices[m] <= ups[m])
+        assert np.all(down[m] <= mid[m] + 1e-12) and np.all(mid[m] <= up[m] + 1e-12) and np.all(np.abs(mid[m] - 1.0) < 0.1)

@@ -126,8 +126,8 @@ def test_fixed_randoms_helper_replays_and_leaves_global_state_untouched():
     assert dts[0] == g["dts"][0]
 
 
-def test_black_implied_vols_round_trip_and_quickstart_values():
-    from stochvolmodels_b200.utils import bsm
+def test_oracle_black_implied_vols_round_trip_and_quickstart_values():
+    from oracle import bsm
     K = np.array([0.6, 0.9, 1.0, 1.1, 1.6])
     types = np.array(["P", "P", "C", "C", "C"])
     for vol in (0.05, 0.2, 1.0, 2.5):

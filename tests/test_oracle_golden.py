@@ -205,3 +205,56 @@ def test_c_port_matches_numpy_oracle(model):
     for m in range(2):
         np.testing.assert_allclose(pc[m], p[m], rtol=1e-9, atol=1e-13)
         np.testing.assert_allclose(ec[m], e[m], rtol=1e-9, atol=1e-13)
+
+
+# ---- quadratic-variance options, densities, digitals ----------------------------------------------------
+@pytest.mark.parametrize("tag", ["mma", "inv"])
+def test_logsv_qvar_fourier_chain(tag):
+    g = load_golden(f"logsv_fourier_qvar_{tag}.npz")
+    psi = mgf.psi_grid()
+    assert psi.shape[0] == int(g["npsi"])
+    np.testing.assert_array_equal(psi[:4], g["psi_head"])
+    np.testing.assert_array_equal(psi[-2:], g["psi_tail"])
+    K, T = g["strikes"], np.array(["C"] * len(g["strikes"]))
+    prices, grids = mgf.logsv_qvar_chain_prices(g["params"], g["ttms"], g["discfactors"], [K, K], [T, T], bool(g["is_spot"]), 2, True)
+    for m in range(2):
+        np.testing.assert_allclose(grids[m][0][::40], g[f"a_sub_{m}"], rtol=0, atol=1e-10)
+        np.testing.assert_allclose(grids[m][1][::40], g[f"log_mgf_sub_{m}"], rtol=0, atol=1e-10)
+        np.testing.assert_allclose(prices[m], g[f"prices_{m}"], rtol=1e-10)
+    with pytest.raises(ValueError, match="not implemented"):
+        mgf.qvar_slice_prices(grids[0][1], psi, 0.25, K[:1], np.array(["P"]))
+
+
+def test_logsv_pdfs_three_variables():
+    g = load_golden("logsv_pdfs.npz")
+    for vt, name in ((1, "LOG_RETURN"), (2, "Q_VAR"), (3, "SIGMA")):
+        pdf = mgf.logsv_pdf(g["params"], float(g["ttm"]), g[f"grid_{name}"], vt)
+        np.testing.assert_allclose(pdf, g[f"pdf_{name}"], rtol=1e-9, atol=1e-12)
+
+
+def test_heston_qvar_fourier_chain():
+    g = load_golden("heston_fourier_qvar.npz")
+    K, T = g["strikes"], np.array(["C"] * len(g["strikes"]))
+    prices = mgf.heston_qvar_chain_prices(g["params"], g["ttms"], g["discfactors"], [K, K], [T, T])
+    for m in range(2):
+        np.testing.assert_allclose(prices[m], g[f"prices_{m}"], rtol=1e-10, atol=1e-14)
+
+
+@pytest.mark.parametrize("tag", ["neg", "pos"])
+def test_digital_fourier_sums(tag):
+    g = load_golden(f"fourier_digital_{tag}.npz")
+    p = mgf.digital_slice_prices(g["log_mgf"], g["phi"], float(g["forward"]), g["strikes"], g["types"], float(g["discfactor"]))
+    np.testing.assert_allclose(p, g["prices"], rtol=1e-12)
+
+
+def test_logsv_vol_paths():
+    g = load_golden("logsv_vol_paths.npz")
+    S, dt = mc.set_time_grid(0.1, 360)
+    W = np.sqrt(dt) * np.random.RandomState(5).normal(0, 1, size=(S, 500))
+    for tag, spot in (("mma", True), ("inv", False)):
+        sig = mc.logsv_vol_paths(*g["params"], W, dt, spot)
+        np.testing.assert_allclose(sig, g[f"sigma_t_{tag}"], rtol=0, atol=1e-14)
+    # LogSVPricer.simulate_vol_paths(ttm=0.02) passes ceil(360*0.02) = 8 as the PER-YEAR rate (logsv_pricer.py:574) => 1 step
+    assert tuple(g["method_shape"]) == (2, 4)
+    # the module function at 360 steps/yr gives 9 rows for ttm = 0.02 (reference tests/test_logsv_characterization.py:638-660)
+    assert mc.set_time_grid(0.02, 360)[0] + 1 == 9
