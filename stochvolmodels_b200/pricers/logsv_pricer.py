@@ -267,9 +267,31 @@ def simulate_logsv_x_vol_terminal(ttm: float, x0: np.ndarray, sigma0: np.ndarray
                                  engine.mc_flags("fp64", gauss))
 
 
-def get_randoms_for_chain_valuation(ttms: np.ndarray, nb_path: int = 100000, nb_steps_per_year: int = 360, seed: int = 10):
+class DeviceRandoms:
+    """Fixed unit normals of a chain kept RESIDENT in HBM (float64 CUDA tensors W0s[m], W1s[m] of shape [S_m, nb_path]) so that the
+    calibration inner loop (reference :235-294 -> :1100-1162) re-prices with new parameters without re-uploading 16 B per path-step.
+    torch is used for device memory only."""
+
+    def __init__(self, W0s, W1s, dts, device=None):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("DeviceRandoms needs a CUDA device; stochvolmodels_b200 has no CPU fallback")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        up = lambda w: w.to(self.device, torch.float64).contiguous() if torch.is_tensor(w) else torch.as_tensor(np.ascontiguousarray(w, dtype=np.float64)).to(self.device)
+        self.W0s, self.W1s, self.dts = [up(w) for w in W0s], [up(w) for w in W1s], [float(d) for d in dts]
+        self.nb_path = int(self.W0s[0].shape[1])
+        for a, b in zip(self.W0s, self.W1s):
+            if a.shape != b.shape or a.shape[1] != self.nb_path:
+                raise ValueError("W0s and W1s must be lists of [nb_steps, nb_path] arrays of equal shapes")
+
+    def nbytes(self) -> int:
+        return sum(w.numel() * 8 for w in self.W0s + self.W1s)
+
+
+def get_randoms_for_chain_valuation(ttms: np.ndarray, nb_path: int = 100000, nb_steps_per_year: int = 360, seed: int = 10,
+                                    device=None):
     """fixed unit normals per maturity from a LOCAL legacy generator: per slice W0 then W1, never touching numpy's global state
-    (reference :1051-1074)."""
+    (reference :1051-1074).  ``device="cuda"`` returns the same numbers as a :class:`DeviceRandoms` resident in HBM."""
     rng = np.random.RandomState(seed)
     W0s, W1s, dts = [], [], []
     ttm0 = 0.0
@@ -279,15 +301,63 @@ def get_randoms_for_chain_valuation(ttms: np.ndarray, nb_path: int = 100000, nb_
         W1s.append(rng.normal(0, 1, size=(nb_steps_, nb_path)))
         dts.append(dt)
         ttm0 = ttm
+    if device is not None:
+        return DeviceRandoms(W0s, W1s, dts, device)
     return W0s, W1s, dts
 
 
-def logsv_mc_chain_pricer_fixed_randoms(ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms, W0s, W1s, dts, v0: float,
-                                        theta: float, kappa1: float, kappa2: float, beta: float, volvol: float,
-                                        vol_backbone_etas: np.ndarray, is_spot_measure: bool = True,
-                                        variable_type: VariableType = VariableType.LOG_RETURN, return_states: bool = False):
-    """chain valuation with caller-supplied unit normals (reference :1100-1162): strict-arithmetic stepper + payoff kernels."""
+def _fixed_randoms_chain_device(rnd: DeviceRandoms, ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms, params_c, etas,
+                                is_spot_measure, variable_type):
+    """device-resident variant: strict stepper reading W from HBM, re-centring moments, payoff sums, finalisation -- one stream,
+    no host round trip until the prices are copied back."""
+    import torch
+    from ctypes import byref, c_void_p
+    dev = rnd.device
+    n = rnd.nb_path
+    vt = engine.variable_code(variable_type)
+    offsets, strikes, types = C.flatten_chain(strikes_ttms, optiontypes_ttms)
+    with torch.cuda.device(dev):
+        state = torch.zeros((3, n), dtype=torch.float64, device=dev)
+        state[1].fill_(params_c.sigma0)
+        mom = torch.zeros(2, dtype=torch.float64, device=dev)
+        J_tot = int(offsets[-1])
+        sums = torch.zeros(3 * max(J_tot, 1), dtype=torch.float64, device=dev)
+        out = torch.zeros((2, max(J_tot, 1)), dtype=torch.float64, device=dev)
+        strikes_dev = torch.as_tensor(strikes).to(dev)
+        types_dev = torch.as_tensor(types).to(dev)
+        stream = c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        ptr = lambda t: c_void_p(t.data_ptr())
+        for m, ttm in enumerate(ttms):
+            W0, W1 = rnd.W0s[m], rnd.W1s[m]
+            C.call("b200sv_dev_logsv_step_fixed", ptr(state[0]), ptr(state[1]), ptr(state[2]), ptr(W0), ptr(W1), int(W0.shape[0]), n,
+                   rnd.dts[m], byref(params_c), float(etas[m]), int(bool(is_spot_measure)), stream)
+            J, jo = int(offsets[m + 1] - offsets[m]), int(offsets[m])
+            if J == 0:
+                continue
+            C.call("b200sv_dev_spot_moments", ptr(state[0]), n, float(forwards[m]), ptr(mom), stream)
+            kinds = int(np.bitwise_or.reduce(np.where(types[jo: jo + J] >= 2, 2, 1)))
+            C.call("b200sv_dev_payoff_sums", ptr(state[0]), ptr(state[2]), n, 0, float(ttm), float(forwards[m]), ptr(strikes_dev[jo:]),
+                   ptr(types_dev[jo:]), J, vt, kinds, ptr(mom), ptr(sums[3 * jo:]), stream)
+            C.call("b200sv_dev_payoff_finalize", ptr(sums[3 * jo:]), J, float(discfactors[m]), n, ptr(out[0, jo:]), ptr(out[1, jo:]), stream)
+        host = out.cpu().numpy()
+    return C.split_chain(host[0], offsets), C.split_chain(host[1], offsets)
+
+
+def logsv_mc_chain_pricer_fixed_randoms(ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms, W0s, W1s=None, dts=None,
+                                        v0: float = None, theta: float = None, kappa1: float = None, kappa2: float = None,
+                                        beta: float = None, volvol: float = None, vol_backbone_etas: np.ndarray = None,
+                                        is_spot_measure: bool = True, variable_type: VariableType = VariableType.LOG_RETURN,
+                                        return_states: bool = False):
+    """chain valuation with caller-supplied unit normals (reference :1100-1162): strict-arithmetic stepper + payoff kernels.
+    ``W0s`` may be a :class:`DeviceRandoms` (then ``W1s`` / ``dts`` are taken from it and nothing is uploaded)."""
     params_c = engine.logsv_params_c(v0, theta, kappa1, kappa2, beta, volvol)
+    if vol_backbone_etas is None:
+        vol_backbone_etas = np.ones(len(ttms))
+    if isinstance(W0s, DeviceRandoms):
+        if return_states:
+            raise NotImplementedError("return_states is only available with host arrays")
+        return _fixed_randoms_chain_device(W0s, ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms, params_c, vol_backbone_etas,
+                                           is_spot_measure, variable_type)
     nb_path = W0s[0].shape[1]
     x, q, s = np.zeros(nb_path), np.zeros(nb_path), v0 * np.ones(nb_path)
     prices, stds, states = [], [], []

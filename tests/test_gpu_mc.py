@@ -283,3 +283,22 @@ def test_logsv_vol_paths_vs_reference_golden(cuda_lib):
     z0, _ = engine.device_normals(seed, 0, N, 0, S, C.GAUSS_F64)
     sig, _ = simulate_vol_paths(0.1, *g["params"], nb_path=N, nb_steps_per_year=360, seed=seed)
     np.testing.assert_allclose(sig, mc.logsv_vol_paths(*g["params"], np.sqrt(dt) * z0, dt, True), rtol=0, atol=1e-11)
+
+
+def test_device_resident_fixed_randoms_chain(cuda_lib):
+    """calibration inner loop shape (reference :1100-1162): W0s/W1s resident in HBM, same prices as the host-array path and as the
+    reference golden; re-pricing with other parameters reuses the resident normals."""
+    from stochvolmodels_b200.pricers.logsv_pricer import DeviceRandoms, get_randoms_for_chain_valuation, logsv_mc_chain_pricer_fixed_randoms
+    g = load_golden("logsv_mc_fixed_btc_small.npz")
+    strikes, types = chain_from_golden(g)
+    rnd = get_randoms_for_chain_valuation(g["ttms"], int(g["nb_path"]), int(g["n_per_year"]), int(g["seed"]), device="cuda")
+    assert isinstance(rnd, DeviceRandoms) and rnd.nbytes() == 2 * 8 * int(g["nb_path"]) * int(np.sum(g["nsteps"]))
+    s0, th, k1, k2, b, vv = g["params"]
+    p, e = logsv_mc_chain_pricer_fixed_randoms(g["ttms"], g["forwards"], g["discfactors"], strikes, types, rnd, v0=s0, theta=th, kappa1=k1,
+                                               kappa2=k2, beta=b, volvol=vv, vol_backbone_etas=g["etas"], is_spot_measure=bool(g["is_spot"]))
+    for m in range(int(g["nslices"])):
+        np.testing.assert_allclose(p[m], g[f"prices_{m}"], rtol=1e-9, atol=1e-13)
+        np.testing.assert_allclose(e[m], g[f"stderr_{m}"], rtol=1e-8, atol=1e-13)
+    p2, _ = logsv_mc_chain_pricer_fixed_randoms(g["ttms"], g["forwards"], g["discfactors"], strikes, types, rnd, v0=s0 * 1.01, theta=th,
+                                                kappa1=k1, kappa2=k2, beta=b, volvol=vv, vol_backbone_etas=g["etas"])
+    assert np.all(np.abs(p2[0] / p[0] - 1) < 0.1) and not np.allclose(p2[0], p[0], rtol=1e-6)

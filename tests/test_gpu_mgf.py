@@ -183,7 +183,7 @@ def test_gpu_black_implied_vols(cuda_lib):
     iv = engine.bsm_implied_vols(ttms, fw, df, [K] * 3, [types] * 3, prices)
     host = bsm.infer_bsm_ivols_from_model_chain_prices(ttms, fw, df, [K] * 3, [types] * 3, prices)
     for m in range(3):
-        good = prices[m] > 1e-14
+        good = prices[m] > 1e-8            # far-OTM quotes (price ~1e-12) are ill-conditioned: 1 ulp of price = 1e-5 of vol
         np.testing.assert_allclose(iv[m][good], vols[m], rtol=1e-8)
         np.testing.assert_allclose(iv[m], host[m], rtol=1e-12, equal_nan=True)
     chain = OptionChain.slice_to_chain(0.25, 1.0, np.array([1.0, 1.0]), np.array(["C", "C"]))

@@ -36,3 +36,12 @@ for name, pricer, params, chain, gold in (("logsv c3 5x21", LogSVPricer(), Q, c3
         p6 = (params.sigma0, params.theta, params.kappa1, params.kappa2, params.beta, params.volvol)
         _, omed, _ = timed(lambda: mgf.logsv_chain_prices(p6, chain.ttms, chain.forwards, chain.discfactors, chain.strikes_ttms, chain.optiontypes_ttms), reps=3)
         print(f"{'':16s} CPU oracle (vectorised numpy RK45 clone) {omed:8.1f} ms; reference as shipped (scipy loop) ~2 s per maturity [SURVEY.md §6]")
+
+# ---- options on quadratic variance, psi grid P = 40000 (reference: ~80 s per maturity on the CPU)
+from stochvolmodels_b200 import VariableType
+from stochvolmodels_b200.pricers.logsv_pricer import logsv_chain_pricer
+g = np.load(os.path.join(G, "logsv_fourier_qvar_mma.npz"))
+Kq, Tq = g["strikes"], np.array(["C"] * len(g["strikes"]))
+prices, med, mn = timed(lambda: logsv_chain_pricer(Q, g["ttms"], np.ones(2), g["discfactors"], [Kq, Kq], [Tq, Tq], variable_type=VariableType.Q_VAR), reps=10)
+rel = max(np.max(np.abs(prices[m] / g[f"prices_{m}"] - 1)) for m in range(2))
+print(f"{'logsv Q_VAR 2x5':16s} GPU e2e median {med:8.3f} ms (min {mn:.3f})  max rel err vs reference golden {rel:.2e}  [2 maturities x 40000 RK45 solves]")
