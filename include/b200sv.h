@@ -146,10 +146,12 @@ int b200sv_dev_payoff_finalize(const double* sums, int J, double discfactor, lon
 
 /* device-level twins of b200sv_logsv_step_fixed / b200sv_heston_step_fixed (all arrays on the device; W row-major [S][N]):
  * the calibration inner loop logsv_mc_chain_pricer_fixed_randoms (pricers/logsv_pricer.py:1100-1162) keeps W0s/W1s
- * resident in HBM across optimizer iterations and calls these per maturity. */
+ * resident in HBM across optimizer iterations and calls these per maturity.  fast != 0 selects the throughput variant of the
+ * LogSV stepper (the fused kernel's per-step update: folded constants, FMA, shared-polynomial exp pair; agrees with the strict
+ * kernel to ~1e-14), whose bound is the 16 B/path-step HBM stream of normals. */
 int b200sv_dev_logsv_step_fixed(double* x, double* sigma, double* qvar, const double* W0, const double* W1, int S,
                                 long long N, double dt, const b200sv_logsv_params* params, double eta,
-                                int is_spot_measure, void* stream);
+                                int is_spot_measure, int fast, void* stream);
 int b200sv_dev_heston_step_fixed(double* x, double* var, double* qvar, const double* W0, const double* W1, int S,
                                  long long N, double dt, const b200sv_heston_params* params, void* stream);
 

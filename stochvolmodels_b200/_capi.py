@@ -66,7 +66,7 @@ SIGNATURES = {
                                c_void_p, c_void_p, c_void_p],
     "b200sv_dev_payoff_finalize": [c_void_p, c_int, c_double, c_longlong, c_void_p, c_void_p, c_void_p],
     "b200sv_dev_logsv_step_fixed": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_double, _lp, c_double,
-                                    c_int, c_void_p],
+                                    c_int, c_int, c_void_p],
     "b200sv_dev_heston_step_fixed": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_double, _hp, c_void_p],
     "b200sv_dev_spot_moments": [c_void_p, c_longlong, c_double, c_void_p, c_void_p],
     "b200sv_debug_exp_pair": [_dp, c_longlong, _dp],

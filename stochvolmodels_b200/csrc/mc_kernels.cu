@@ -338,6 +338,25 @@ __global__ void __launch_bounds__(kThreads) logsv_step_fixed_kernel(double* __re
   }
 }
 
+// Throughput variant of the fixed-random stepper for the device-resident calibration loop: same normals from HBM, but the
+// per-step update of the fused kernel (LogsvPath<double>: folded constants, shared-polynomial exp pair, FMA) -- about half the
+// fp64 instructions of the strict kernel, so the 16 B/path-step HBM stream becomes the bound.  Agrees with the strict kernel to
+// ~1e-14 (tests/test_gpu_mc.py::test_device_resident_fixed_randoms_chain).
+__global__ void __launch_bounds__(kThreads) logsv_step_fixed_fast_kernel(double* __restrict__ x, double* __restrict__ sigma,
+                                                                        double* __restrict__ qvar, const double* __restrict__ W0,
+                                                                        const double* __restrict__ W1, int S, long long N,
+                                                                        LogsvConsts consts) {
+  LogsvPath<double> p(consts);
+  const long long stride = (long long)gridDim.x * kThreads;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < N; i += stride) {
+    p.load(x[i], sigma[i], qvar[i]);
+    for (int s = 0; s < S; ++s) p.step(__ldg(W0 + (size_t)s * N + i), __ldg(W1 + (size_t)s * N + i));
+    x[i] = p.x();
+    sigma[i] = p.sigma();
+    qvar[i] = p.q();
+  }
+}
+
 __global__ void __launch_bounds__(kThreads) heston_step_fixed_kernel(double* __restrict__ x, double* __restrict__ var,
                                                                     double* __restrict__ qvar, const double* __restrict__ W0,
                                                                     const double* __restrict__ W1, int S, long long N,
@@ -920,9 +939,15 @@ int b200sv_dev_payoff_finalize(const double* sums, int J, double discfactor, lon
 }
 
 int b200sv_dev_logsv_step_fixed(double* x, double* sigma, double* qvar, const double* W0, const double* W1, int S, long long N,
-                                double dt, const b200sv_logsv_params* params, double eta, int is_spot_measure, void* stream) {
+                                double dt, const b200sv_logsv_params* params, double eta, int is_spot_measure, int fast, void* stream) {
   B200SV_REQUIRE(x && sigma && qvar && W0 && W1 && params, "null pointer");
   B200SV_REQUIRE(S >= 0 && N >= 1 && dt > 0.0, "S, N, dt");
+  if (fast) {
+    const LogsvConsts c = make_logsv_consts(*params, eta, is_spot_measure != 0, dt);
+    Grid g = persistent_grid(logsv_step_fixed_fast_kernel, kThreads, N);
+    logsv_step_fixed_fast_kernel<<<g.blocks, g.threads, 0, (cudaStream_t)stream>>>(x, sigma, qvar, W0, W1, S, N, c);
+    return check_launch("logsv_step_fixed_fast_kernel");
+  }
   LogsvRaw r{params->theta, params->kappa1, params->kappa2, params->beta, params->volvol, eta,
              is_spot_measure ? -1.0 : 1.0, is_spot_measure ? 0.0 : params->beta * eta, dt};
   Grid g = persistent_grid(logsv_step_fixed_kernel, kThreads, N);
@@ -970,7 +995,7 @@ static int step_fixed_host(int model, double* x, double* v, double* q, const dou
     B200SV_CUDA(cudaMemcpyAsync(w, W0, wb, cudaMemcpyHostToDevice, st));
     B200SV_CUDA(cudaMemcpyAsync(w + (size_t)N * S, W1, wb, cudaMemcpyHostToDevice, st));
   }
-  int rc = model == 0 ? b200sv_dev_logsv_step_fixed(d, d + N, d + 2 * N, w, w + (size_t)N * S, S, N, dt, lp, eta, is_spot, st)
+  int rc = model == 0 ? b200sv_dev_logsv_step_fixed(d, d + N, d + 2 * N, w, w + (size_t)N * S, S, N, dt, lp, eta, is_spot, 0, st)
                       : b200sv_dev_heston_step_fixed(d, d + N, d + 2 * N, w, w + (size_t)N * S, S, N, dt, hp, st);
   if (rc == 0) {
     cudaError_t e = cudaMemcpyAsync(x, d, nb, cudaMemcpyDeviceToHost, st);

@@ -307,7 +307,7 @@ def get_randoms_for_chain_valuation(ttms: np.ndarray, nb_path: int = 100000, nb_
 
 
 def _fixed_randoms_chain_device(rnd: DeviceRandoms, ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms, params_c, etas,
-                                is_spot_measure, variable_type):
+                                is_spot_measure, variable_type, fast=True):
     """device-resident variant: strict stepper reading W from HBM, re-centring moments, payoff sums, finalisation -- one stream,
     no host round trip until the prices are copied back."""
     import torch
@@ -330,7 +330,7 @@ def _fixed_randoms_chain_device(rnd: DeviceRandoms, ttms, forwards, discfactors,
         for m, ttm in enumerate(ttms):
             W0, W1 = rnd.W0s[m], rnd.W1s[m]
             C.call("b200sv_dev_logsv_step_fixed", ptr(state[0]), ptr(state[1]), ptr(state[2]), ptr(W0), ptr(W1), int(W0.shape[0]), n,
-                   rnd.dts[m], byref(params_c), float(etas[m]), int(bool(is_spot_measure)), stream)
+                   rnd.dts[m], byref(params_c), float(etas[m]), int(bool(is_spot_measure)), int(bool(fast)), stream)
             J, jo = int(offsets[m + 1] - offsets[m]), int(offsets[m])
             if J == 0:
                 continue
@@ -347,9 +347,10 @@ def logsv_mc_chain_pricer_fixed_randoms(ttms, forwards, discfactors, strikes_ttm
                                         v0: float = None, theta: float = None, kappa1: float = None, kappa2: float = None,
                                         beta: float = None, volvol: float = None, vol_backbone_etas: np.ndarray = None,
                                         is_spot_measure: bool = True, variable_type: VariableType = VariableType.LOG_RETURN,
-                                        return_states: bool = False):
-    """chain valuation with caller-supplied unit normals (reference :1100-1162): strict-arithmetic stepper + payoff kernels.
-    ``W0s`` may be a :class:`DeviceRandoms` (then ``W1s`` / ``dts`` are taken from it and nothing is uploaded)."""
+                                        return_states: bool = False, fast: bool = True):
+    """chain valuation with caller-supplied unit normals (reference :1100-1162).  Host arrays go through the strict-arithmetic
+    stepper (reference evaluation order).  ``W0s`` may be a :class:`DeviceRandoms` (then ``W1s`` / ``dts`` are taken from it, nothing
+    is uploaded, and ``fast`` selects the throughput stepper, which agrees with the strict one to ~1e-14)."""
     params_c = engine.logsv_params_c(v0, theta, kappa1, kappa2, beta, volvol)
     if vol_backbone_etas is None:
         vol_backbone_etas = np.ones(len(ttms))
@@ -357,7 +358,7 @@ def logsv_mc_chain_pricer_fixed_randoms(ttms, forwards, discfactors, strikes_ttm
         if return_states:
             raise NotImplementedError("return_states is only available with host arrays")
         return _fixed_randoms_chain_device(W0s, ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms, params_c, vol_backbone_etas,
-                                           is_spot_measure, variable_type)
+                                           is_spot_measure, variable_type, fast)
     nb_path = W0s[0].shape[1]
     x, q, s = np.zeros(nb_path), np.zeros(nb_path), v0 * np.ones(nb_path)
     prices, stds, states = [], [], []

@@ -299,6 +299,11 @@ def test_device_resident_fixed_randoms_chain(cuda_lib):
     for m in range(int(g["nslices"])):
         np.testing.assert_allclose(p[m], g[f"prices_{m}"], rtol=1e-9, atol=1e-13)
         np.testing.assert_allclose(e[m], g[f"stderr_{m}"], rtol=1e-8, atol=1e-13)
+    ps, es = logsv_mc_chain_pricer_fixed_randoms(g["ttms"], g["forwards"], g["discfactors"], strikes, types, rnd, v0=s0, theta=th, kappa1=k1,
+                                                 kappa2=k2, beta=b, volvol=vv, vol_backbone_etas=g["etas"], fast=False)
+    for m in range(int(g["nslices"])):
+        np.testing.assert_allclose(ps[m], p[m], rtol=1e-11, atol=1e-13)          # throughput vs strict stepper
+        np.testing.assert_allclose(ps[m], g[f"prices_{m}"], rtol=1e-10, atol=1e-13)
     p2, _ = logsv_mc_chain_pricer_fixed_randoms(g["ttms"], g["forwards"], g["discfactors"], strikes, types, rnd, v0=s0 * 1.01, theta=th,
                                                 kappa1=k1, kappa2=k2, beta=b, volvol=vv, vol_backbone_etas=g["etas"])
     assert np.all(np.abs(p2[0] / p[0] - 1) < 0.1) and not np.allclose(p2[0], p[0], rtol=1e-6)
