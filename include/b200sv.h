@@ -40,8 +40,9 @@ enum { B200SV_ORDER_FIRST = 1, B200SV_ORDER_SECOND = 2 };
  * and widened (the draws are random inputs, not reference arithmetic).  B200SV_GAUSS_F64 draws them in fp64 as well;
  * B200SV_STATE_F32 keeps x / log-sigma / qvar in float registers (payoff moments stay fp64). */
 enum { B200SV_STATE_F64 = 0, B200SV_STATE_F32 = 1, B200SV_GAUSS_F32 = 0, B200SV_GAUSS_F64 = 2 };
-/* Heston variance scheme: reference floor-Euler (pricers/heston_pricer.py:369-379) */
-enum { B200SV_HESTON_EULER_FLOOR = 0 };
+/* Heston variance scheme: 0 = the reference's floor-Euler (pricers/heston_pricer.py:369-379, v = max(v, 1e-4)); 1 = opt-in Andersen (2008)
+ * quadratic-exponential scheme with central discretisation (BASELINE.json config 2 names it; the reference does not have it) */
+enum { B200SV_HESTON_EULER_FLOOR = 0, B200SV_HESTON_QE = 1 };
 
 /* pricers/logsv/logsv_params.py:35-83 LogSvParams (the six model floats; kappa2=None already mapped to kappa1/theta) */
 typedef struct {

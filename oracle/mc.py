@@ -245,3 +245,41 @@ def logsv_vol_paths(v0, theta, kappa1, kappa2, beta, volvol, W, dt, is_spot_meas
         sigma = np.exp(L)
         out[t + 1] = sigma
     return out
+
+
+def heston_qe_step_fixed(x, var, qvar, Z0, Z1, dt, theta, kappa, rho, volvol, psi_c=1.5):
+    """Andersen (2008) quadratic-exponential Heston step with central discretisation (gamma1 = gamma2 = 1/2), the opt-in
+    ``scheme="qe"`` of this repo (NOT in the reference; restated here as the checker of ``HestonPath::step_qe``).
+    Z0 drives the spot, Z1 the variance (U = Phi(Z1) in the exponential branch); qvar by the trapezoid rule."""
+    from scipy.special import ndtr
+    x = np.array(x, dtype=np.float64, copy=True)
+    v = np.array(var, dtype=np.float64, copy=True)
+    q = np.array(qvar, dtype=np.float64, copy=True)
+    e = np.exp(-kappa * dt)
+    m0 = theta * (1.0 - e)
+    s1 = volvol * volvol * e * (1.0 - e) / kappa
+    s0 = theta * volvol * volvol * (1.0 - e) * (1.0 - e) / (2.0 * kappa)
+    kre = kappa * rho / volvol
+    K0 = -rho * kappa * theta * dt / volvol
+    K1 = 0.5 * dt * (kre - 0.5) - rho / volvol
+    K2 = 0.5 * dt * (kre - 0.5) + rho / volvol
+    K3 = 0.5 * dt * (1.0 - rho * rho)
+    K4 = K3
+    for zx, zv in zip(Z0, Z1):
+        m = v * e + m0
+        s2 = v * s1 + s0
+        psi = s2 / (m * m)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ip = 2.0 / psi
+            b2 = ip - 1.0 + np.sqrt(ip) * np.sqrt(np.maximum(ip - 1.0, 0.0))
+            a = m / (1.0 + b2)
+            vq = a * (np.sqrt(b2) + zv) ** 2
+            p = (psi - 1.0) / (psi + 1.0)
+            beta = (1.0 - p) / m
+            u = ndtr(zv)
+            ve = np.where(u <= p, 0.0, np.log((1.0 - p) / (1.0 - u)) / beta)
+        vn = np.where(psi <= psi_c, vq, ve)
+        x = x + (K0 + K1 * v + K2 * vn + np.sqrt(K3 * v + K4 * vn) * zx)
+        q = q + 0.5 * dt * (v + vn)
+        v = vn
+    return x, v, q

@@ -20,7 +20,7 @@ CALL, PUT, INV_CALL, INV_PUT = 0, 1, 2, 3
 LOG_RETURN, Q_VAR, SIGMA = 1, 2, 3
 ORDER_FIRST, ORDER_SECOND = 1, 2
 STATE_F64, STATE_F32, GAUSS_F32, GAUSS_F64 = 0, 1, 0, 2
-HESTON_EULER_FLOOR = 0
+HESTON_EULER_FLOOR, HESTON_QE = 0, 1
 TYPE_CODES = {"C": CALL, "P": PUT, "IC": INV_CALL, "IP": INV_PUT}
 
 

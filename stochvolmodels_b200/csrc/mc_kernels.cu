@@ -65,6 +65,13 @@ struct HestonConsts {
   double theta;
   double c0;    // volvol * rho * sqrt(dt)
   double c1;    // volvol * sqrt(1 - rho^2) * sqrt(dt)
+  // opt-in Andersen (2008) quadratic-exponential scheme (B200SV_HESTON_QE), central discretisation gamma1 = gamma2 = 1/2
+  int qe;
+  double e;     // exp(-kappa dt)                     m  = v e + m0,  m0 = theta (1 - e)
+  double m0;
+  double s1;    // volvol^2 e (1 - e) / kappa         s2 = v s1 + s0
+  double s0;    // theta volvol^2 (1 - e)^2 / (2 kappa)
+  double K0, K1, K2, K3, K4;   // x' = x + K0 + K1 v + K2 v' + sqrt(K3 v + K4 v') Zx
 };
 
 static LogsvConsts make_logsv_consts(const b200sv_logsv_params& p, double eta, bool spot, double dt) {
@@ -83,9 +90,20 @@ static LogsvConsts make_logsv_consts(const b200sv_logsv_params& p, double eta, b
   return c;
 }
 
-static HestonConsts make_heston_consts(const b200sv_heston_params& p, double dt) {
+static HestonConsts make_heston_consts(const b200sv_heston_params& p, double dt, int scheme = B200SV_HESTON_EULER_FLOOR) {
   const double sdt = std::sqrt(dt);
   HestonConsts c;
+  c.qe = scheme == B200SV_HESTON_QE;
+  c.e = std::exp(-p.kappa * dt);
+  c.m0 = p.theta * (1.0 - c.e);
+  c.s1 = p.volvol * p.volvol * c.e * (1.0 - c.e) / p.kappa;
+  c.s0 = p.theta * p.volvol * p.volvol * (1.0 - c.e) * (1.0 - c.e) / (2.0 * p.kappa);
+  const double kre = p.kappa * p.rho / p.volvol;
+  c.K0 = -p.rho * p.kappa * p.theta * dt / p.volvol;
+  c.K1 = 0.5 * dt * (kre - 0.5) - p.rho / p.volvol;
+  c.K2 = 0.5 * dt * (kre - 0.5) + p.rho / p.volvol;
+  c.K3 = 0.5 * dt * (1.0 - p.rho * p.rho);
+  c.K4 = c.K3;
   c.hx = -0.5 * dt;
   c.sdt = sdt;
   c.dt = dt;
@@ -175,20 +193,54 @@ struct LogsvPath<float> {
 
 template <typename Real>
 struct HestonPath {
-  Real v, V, XM, x0, q0;
+  Real v, V, XM, x0, q0, xacc, qacc;
   Real hx, sdt, dt, kdt, theta, c0, c1;
+  Real e, m0, s1, s0, K0, K1, K2, K3, K4;
+  int qe;
   __device__ __forceinline__ HestonPath(const HestonConsts& c)
-      : hx((Real)c.hx), sdt((Real)c.sdt), dt((Real)c.dt), kdt((Real)c.kdt), theta((Real)c.theta), c0((Real)c.c0), c1((Real)c.c1) {}
+      : hx((Real)c.hx), sdt((Real)c.sdt), dt((Real)c.dt), kdt((Real)c.kdt), theta((Real)c.theta), c0((Real)c.c0), c1((Real)c.c1),
+        e((Real)c.e), m0((Real)c.m0), s1((Real)c.s1), s0((Real)c.s0), K0((Real)c.K0), K1((Real)c.K1), K2((Real)c.K2), K3((Real)c.K3),
+        K4((Real)c.K4), qe(c.qe) {}
   __device__ __forceinline__ void load(Real x_, Real v_, Real q_) {
     x0 = x_;
     v = v_;
     q0 = q_;
     V = (Real)0;
     XM = (Real)0;
+    xacc = (Real)0;
+    qacc = (Real)0;
+  }
+  // Andersen's QE step: moment-matched quadratic (psi <= 1.5) or exponential (psi > 1.5) variance draw, then the log-spot with the
+  // central discretisation.  z0 drives the spot, z1 the variance (U = Phi(z1) in the exponential branch).  Not in the reference
+  // (BASELINE.json names it): validated against the Heston Fourier price and the oracle restatement.
+  __device__ __forceinline__ void step_qe(Real zx, Real zv) {
+    const Real m = fma(v, e, m0);
+    const Real s2 = fma(v, s1, s0);
+    const Real psi = s2 / (m * m);
+    Real vn;
+    if (psi <= (Real)1.5) {
+      const Real ip = (Real)2 / psi;
+      const Real b2 = ip - (Real)1 + sqrt(ip) * sqrt(ip - (Real)1);
+      const Real a = m / ((Real)1 + b2);
+      const Real t = sqrt(b2) + zv;
+      vn = a * t * t;
+    } else {
+      const Real p = (psi - (Real)1) / (psi + (Real)1);
+      const Real beta = ((Real)1 - p) / m;
+      const Real u = (Real)normcdf((double)zv);
+      vn = u <= p ? (Real)0 : (Real)log((double)(((Real)1 - p) / ((Real)1 - u))) / beta;
+    }
+    xacc += K0 + K1 * v + K2 * vn + sqrt(K3 * v + K4 * vn) * zx;
+    qacc += (Real)0.5 * dt * (v + vn);
+    v = vn;
   }
   // pricers/heston_pricer.py:372-379 (floor-Euler): everything on the OLD variance, then v = max(v, 1e-4).
   // V = sum v_k, XM = sum sqrt(v_k) z0_k  =>  x_S = x_0 - 0.5*dt*V + sqrt(dt)*XM,  q_S = q_0 + dt*V.
   __device__ __forceinline__ void step(Real z0, Real z1) {
+    if (qe) {
+      step_qe(z0, z1);
+      return;
+    }
     const Real sig = sqrt(v);
     V += v;
     XM = fma(sig, z0, XM);
@@ -197,8 +249,8 @@ struct HestonPath {
     v = vn > (Real)1e-4 ? vn : (Real)1e-4;     // np.maximum(var0, 1e-4)
   }
   __device__ __forceinline__ Real sigma() const { return v; }
-  __device__ __forceinline__ Real x() const { return fma(sdt, XM, fma(hx, V, x0)); }
-  __device__ __forceinline__ Real q() const { return fma(dt, V, q0); }
+  __device__ __forceinline__ Real x() const { return fma(sdt, XM, fma(hx, V, x0)) + xacc; }
+  __device__ __forceinline__ Real q() const { return fma(dt, V, q0) + qacc; }
 };
 
 // --------------------------------------------------------------------------------------------------------------------
@@ -753,7 +805,7 @@ template <int MODEL>
 static int mc_chain_host(const b200sv_logsv_params* lp, const b200sv_heston_params* hp, int M, const double* ttms,
                          const double* forwards, const double* discfactors, const double* etas, const int* offsets,
                          const double* strikes, const int8_t* types, long long nb_path, int nb_steps_per_year, int is_spot,
-                         int variable_type, uint64_t seed, int flags, double* prices_out, double* stderr_out) {
+                         int variable_type, uint64_t seed, int flags, double* prices_out, double* stderr_out, int scheme = 0) {
   B200SV_REQUIRE(nb_path >= 1, "nb_path must be >= 1");
   B200SV_REQUIRE(nb_steps_per_year >= 1, "nb_steps_per_year must be >= 1");
   if (int rc = validate_chain(M, ttms, offsets, types, variable_type)) return rc;
@@ -787,7 +839,7 @@ static int mc_chain_host(const b200sv_logsv_params* lp, const b200sv_heston_para
       const LogsvConsts c = make_logsv_consts(*lp, etas ? etas[m] : 1.0, is_spot != 0, dt);
       rc = launch_slice<0>(x, v, q, nb_path, 0, m == 0, lp->sigma0, S, m, forwards[m], seed, flags, &c, nullptr, d_mom, st);
     } else {
-      const HestonConsts c = make_heston_consts(*hp, dt);
+      const HestonConsts c = make_heston_consts(*hp, dt, scheme);
       rc = launch_slice<1>(x, v, q, nb_path, 0, m == 0, hp->v0, S, m, forwards[m], seed, flags, nullptr, &c, d_mom, st);
     }
     if (rc) break;
@@ -819,7 +871,7 @@ static int mc_chain_host(const b200sv_logsv_params* lp, const b200sv_heston_para
 
 template <int MODEL>
 static int terminal_host(const b200sv_logsv_params* lp, const b200sv_heston_params* hp, double ttm, long long nb_path,
-                         int nb_steps_per_year, int is_spot, double eta, uint64_t seed, int flags, double* x, double* v, double* q) {
+                         int nb_steps_per_year, int is_spot, double eta, uint64_t seed, int flags, double* x, double* v, double* q, int scheme = 0) {
   B200SV_REQUIRE(nb_path >= 1 && ttm > 0.0 && nb_steps_per_year >= 1, "nb_path, ttm, nb_steps_per_year must be positive");
   B200SV_REQUIRE(!(flags & B200SV_STATE_F32), "terminal values are returned as float64: use B200SV_STATE_F64");
   cudaStream_t st = 0;
@@ -835,7 +887,7 @@ static int terminal_host(const b200sv_logsv_params* lp, const b200sv_heston_para
     const LogsvConsts c = make_logsv_consts(*lp, eta, is_spot != 0, dt);
     rc = launch_slice<0>(d, d + nb_path, d + 2 * nb_path, nb_path, 0, 1, lp->sigma0, S, 0, 1.0, seed, flags, &c, nullptr, d_mom, st);
   } else {
-    const HestonConsts c = make_heston_consts(*hp, dt);
+    const HestonConsts c = make_heston_consts(*hp, dt, scheme);
     rc = launch_slice<1>(d, d + nb_path, d + 2 * nb_path, nb_path, 0, 1, hp->v0, S, 0, 1.0, seed, flags, nullptr, &c, d_mom, st);
   }
   if (rc == 0) {
@@ -879,9 +931,9 @@ int b200sv_heston_mc_chain(const b200sv_heston_params* params, int M, const doub
                            long long nb_path, int nb_steps_per_year, int variable_type, uint64_t seed, int flags, int scheme,
                            double* prices_out, double* stderr_out) {
   B200SV_REQUIRE(params && ttms && forwards && discfactors && offsets && prices_out && stderr_out, "null pointer");
-  B200SV_REQUIRE(scheme == B200SV_HESTON_EULER_FLOOR, "unknown Heston scheme");
+  B200SV_REQUIRE(scheme == B200SV_HESTON_EULER_FLOOR || scheme == B200SV_HESTON_QE, "unknown Heston scheme");
   return mc_chain_host<1>(nullptr, params, M, ttms, forwards, discfactors, nullptr, offsets, strikes, types, nb_path,
-                          nb_steps_per_year, 1, variable_type, seed, flags, prices_out, stderr_out);
+                          nb_steps_per_year, 1, variable_type, seed, flags, prices_out, stderr_out, scheme);
 }
 
 int b200sv_logsv_terminal(const b200sv_logsv_params* params, double ttm, long long nb_path, int nb_steps_per_year,
@@ -893,8 +945,8 @@ int b200sv_logsv_terminal(const b200sv_logsv_params* params, double ttm, long lo
 int b200sv_heston_terminal(const b200sv_heston_params* params, double ttm, long long nb_path, int nb_steps_per_year,
                            uint64_t seed, int flags, int scheme, double* x, double* var, double* qvar) {
   B200SV_REQUIRE(params && x && var && qvar, "null pointer");
-  B200SV_REQUIRE(scheme == B200SV_HESTON_EULER_FLOOR, "unknown Heston scheme");
-  return terminal_host<1>(nullptr, params, ttm, nb_path, nb_steps_per_year, 1, 1.0, seed, flags, x, var, qvar);
+  B200SV_REQUIRE(scheme == B200SV_HESTON_EULER_FLOOR || scheme == B200SV_HESTON_QE, "unknown Heston scheme");
+  return terminal_host<1>(nullptr, params, ttm, nb_path, nb_steps_per_year, 1, 1.0, seed, flags, x, var, qvar, scheme);
 }
 
 // ---- device-level ---------------------------------------------------------------------------------------------------
@@ -913,8 +965,8 @@ int b200sv_dev_heston_slice(void* x, void* var, void* qvar, long long n_local, l
                             uint64_t seed, int flags, int scheme, double* moments_out, void* stream) {
   B200SV_REQUIRE(x && var && qvar && params && moments_out, "null pointer");
   B200SV_REQUIRE(n_local >= 1 && nsteps >= 1 && dt > 0.0, "n_local, nsteps, dt must be positive");
-  B200SV_REQUIRE(scheme == B200SV_HESTON_EULER_FLOOR, "unknown Heston scheme");
-  const HestonConsts c = make_heston_consts(*params, dt);
+  B200SV_REQUIRE(scheme == B200SV_HESTON_EULER_FLOOR || scheme == B200SV_HESTON_QE, "unknown Heston scheme");
+  const HestonConsts c = make_heston_consts(*params, dt, scheme);
   return launch_slice<1>(x, var, qvar, n_local, path_offset, init, params->v0, nsteps, slice_index, forward, seed, flags, nullptr,
                          &c, moments_out, (cudaStream_t)stream);
 }

@@ -31,13 +31,14 @@ def shard_paths(nb_path: int, world_size: int, rank: int) -> Tuple[int, int]:
 class CudaMcEngine:
     """Device-resident MC state + kernel launches on the current CUDA device (used for N>=1 ranks and by bench.py)."""
 
-    def __init__(self, model: str, params_c, n_local: int, path_offset: int, flags: int, max_strikes: int, device=None):
+    def __init__(self, model: str, params_c, n_local: int, path_offset: int, flags: int, max_strikes: int, device=None, scheme: int = 0):
         import torch
         if not torch.cuda.is_available():
             raise RuntimeError("CudaMcEngine needs a CUDA device; stochvolmodels_b200 has no CPU fallback")
         C.load_library()
         self.torch = torch
         self.model = model
+        self.scheme = int(scheme)
         self.params_c = params_c
         self.n_local, self.path_offset, self.flags = int(n_local), int(path_offset), int(flags)
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -66,7 +67,7 @@ class CudaMcEngine:
                    c_void_p(self.moments.data_ptr()), self._stream())
         else:
             C.call("b200sv_dev_heston_slice", x, v, q, self.n_local, self.path_offset, int(init), byref(self.params_c), int(nsteps),
-                   float(dt), int(m), float(forward), int(seed) & 0xFFFFFFFFFFFFFFFF, self.flags, C.HESTON_EULER_FLOOR,
+                   float(dt), int(m), float(forward), int(seed) & 0xFFFFFFFFFFFFFFFF, self.flags, self.scheme,
                    c_void_p(self.moments.data_ptr()), self._stream())
         return self.moments
 
@@ -91,7 +92,7 @@ class CudaMcEngine:
 
 def mc_chain_distributed(model: str, params_c, ttms, forwards, discfactors, etas, strikes_ttms, optiontypes_ttms, nb_path: int,
                          nb_steps_per_year: int, is_spot_measure: bool, variable_type: int, seed: int, flags: int,
-                         group=None, engine_factory: Optional[Callable] = None, return_engine: bool = False):
+                         group=None, engine_factory: Optional[Callable] = None, return_engine: bool = False, scheme: int = 0):
     """Chain MC with ``nb_path`` TOTAL paths split over the ranks of ``group`` (default: the world; works unsharded when
     torch.distributed is not initialised).  Every rank returns the same (prices, std errors) lists.
 
@@ -110,7 +111,7 @@ def mc_chain_distributed(model: str, params_c, ttms, forwards, discfactors, etas
     sizes = np.diff(offsets)
     Jmax = int(sizes.max()) if M else 0
     factory = engine_factory or CudaMcEngine
-    eng = factory(model, params_c, n_local, offset, flags, Jmax)
+    eng = factory(model, params_c, n_local, offset, flags, Jmax, scheme=scheme) if scheme else factory(model, params_c, n_local, offset, flags, Jmax)
     strikes_dev = eng.to_device(strikes, torch.float64)
     types_dev = eng.to_device(types, torch.int8)
     etas = np.ones(M) if etas is None else np.asarray(etas, dtype=np.float64)

@@ -39,6 +39,14 @@ def _params_c(v0, theta, kappa, rho, volvol) -> C.HestonParamsC:
     return engine.heston_params_c(v0, theta, kappa, rho, volvol)
 
 
+def _scheme_code(scheme) -> int:
+    """'euler_floor' (default = the reference's scheme) | 'qe' (opt-in Andersen quadratic-exponential; not in the reference)."""
+    codes = {"euler_floor": C.HESTON_EULER_FLOOR, "qe": C.HESTON_QE, C.HESTON_EULER_FLOOR: C.HESTON_EULER_FLOOR, C.HESTON_QE: C.HESTON_QE}
+    if scheme not in codes:
+        raise ValueError("scheme must be 'euler_floor' or 'qe'")
+    return codes[scheme]
+
+
 class HestonPricer(ModelPricer):
     """ModelPricer for the Heston model, Fourier + Monte Carlo routes on the GPU."""
 
@@ -57,7 +65,7 @@ class HestonPricer(ModelPricer):
                                       nb_path=nb_path, variable_type=variable_type,
                                       nb_steps_per_year=kwargs.get("nb_steps_per_year", 360), seed=kwargs.get("seed"),
                                       precision=kwargs.get("precision", "fp64"), gauss=kwargs.get("gauss", "fp32"),
-                                      distributed=kwargs.get("distributed", True))
+                                      distributed=kwargs.get("distributed", True), scheme=kwargs.get("scheme", "euler_floor"))
 
     @timer
     def simulate_terminal_values(self, params: HestonParams, ttm: float = 1.0, nb_path: int = 100000, x0: float = 0.0, **kwargs
@@ -66,7 +74,7 @@ class HestonPricer(ModelPricer):
         return simulate_heston_x_vol_terminal(ttm=ttm, x0=np.zeros(1), var0=params.v0 * np.ones(1), qvar0=np.zeros(1),
                                               theta=params.theta, kappa=params.kappa, rho=params.rho, volvol=params.volvol,
                                               nb_path=nb_path, nb_steps_per_year=kwargs.get("nb_steps_per_year", 360),
-                                              seed=kwargs.get("seed"), gauss=kwargs.get("gauss", "fp32"))
+                                              seed=kwargs.get("seed"), gauss=kwargs.get("gauss", "fp32"), scheme=kwargs.get("scheme", "euler_floor"))
 
 
 def compute_heston_mgf_grid(v0: float, theta: float, kappa: float, volvol: float, rho: float, ttm: float, phi_grid: np.ndarray,
@@ -90,7 +98,7 @@ def heston_chain_pricer(v0: float, theta: float, kappa: float, volvol: float, rh
 def heston_mc_chain_pricer(ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms, v0: float, theta: float, kappa: float,
                            rho: float, volvol: float, nb_path: int = 100000, variable_type: VariableType = VariableType.LOG_RETURN,
                            nb_steps_per_year: int = 360, seed: Optional[int] = None, precision: str = "fp64", gauss: str = "fp32",
-                           distributed: bool = True) -> Tuple[List[np.ndarray], List[np.ndarray]]:
+                           distributed: bool = True, scheme="euler_floor") -> Tuple[List[np.ndarray], List[np.ndarray]]:
     """chain MC under Heston (reference :285-331)."""
     from .logsv_pricer import _use_distributed
     params_c = _params_c(v0, theta, kappa, rho, volvol)
@@ -100,16 +108,16 @@ def heston_mc_chain_pricer(ttms, forwards, discfactors, strikes_ttms, optiontype
         from ..multi_gpu import mc_chain_distributed
         C.encode_types(np.concatenate([np.asarray(t) for t in optiontypes_ttms]))
         return mc_chain_distributed("heston", params_c, ttms, forwards, discfactors, None, strikes_ttms, optiontypes_ttms, nb_path,
-                                    nb_steps_per_year, True, engine.variable_code(variable_type), seed, flags)
+                                    nb_steps_per_year, True, engine.variable_code(variable_type), seed, flags, scheme=_scheme_code(scheme))
     return engine.heston_mc_chain(params_c, ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms, nb_path, nb_steps_per_year,
-                                  variable_type, seed, flags)
+                                  variable_type, seed, flags, _scheme_code(scheme))
 
 
 def simulate_heston_x_vol_terminal(ttm: float, x0: np.ndarray, var0: np.ndarray, qvar0: np.ndarray, theta: float, kappa: float,
                                    rho: float, volvol: float, nb_path: int = 100000, nb_steps_per_year: int = 360,
                                    W0: Optional[np.ndarray] = None, W1: Optional[np.ndarray] = None, dt: Optional[float] = None,
-                                   seed: Optional[int] = None, gauss: str = "fp32"):
-    """terminal (x, variance, qvar) by floor-Euler (reference :334-381).  ``W0, W1, dt`` (an extension: the reference has no
+                                   seed: Optional[int] = None, gauss: str = "fp32", scheme="euler_floor"):
+    """terminal (x, variance, qvar) by floor-Euler (reference :334-381; ``scheme="qe"`` opts into Andersen's QE).  ``W0, W1, dt`` (an extension: the reference has no
     fixed-random Heston entry) select the strict-arithmetic kernel."""
     if W0 is not None or W1 is not None:
         if W0 is None or W1 is None or dt is None:
@@ -124,4 +132,4 @@ def simulate_heston_x_vol_terminal(ttm: float, x0: np.ndarray, var0: np.ndarray,
         raise NotImplementedError("the fused kernel starts every path from (0, v0, 0); pass W0/W1/dt for per-path initial states")
     seed = engine.fresh_seed() if seed is None else int(seed)
     return engine.heston_terminal(_params_c(float(var0[0]), theta, kappa, rho, volvol), ttm, nb_path, nb_steps_per_year, seed,
-                                  engine.mc_flags("fp64", gauss))
+                                  engine.mc_flags("fp64", gauss), _scheme_code(scheme))

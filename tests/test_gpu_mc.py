@@ -307,3 +307,29 @@ def test_device_resident_fixed_randoms_chain(cuda_lib):
     p2, _ = logsv_mc_chain_pricer_fixed_randoms(g["ttms"], g["forwards"], g["discfactors"], strikes, types, rnd, v0=s0 * 1.01, theta=th,
                                                 kappa1=k1, kappa2=k2, beta=b, volvol=vv, vol_backbone_etas=g["etas"])
     assert np.all(np.abs(p2[0] / p[0] - 1) < 0.1) and not np.allclose(p2[0], p[0], rtol=1e-6)
+
+
+def test_heston_qe_scheme(cuda_lib):
+    """opt-in Andersen QE (BASELINE.json config 2; not in the reference): (i) terminal states == oracle restatement fed with the kernel's
+    normals, incl. a Feller-violating case that exercises the exponential branch; (ii) 1e6 paths x 252 steps (config 2 shape) within
+    3 SE of the reference's Heston Fourier price (golden G4) -- QE's discretisation bias is far below the MC error."""
+    from stochvolmodels_b200 import HestonParams, HestonPricer, OptionChain, _capi as C, engine
+    N, seed = 20000, 4321
+    for params, ttm, npy in (((0.04, 0.04, 4.0, -0.5, 0.4), 0.5, 100), ((0.01, 0.02, 1.0, -0.7, 1.0), 0.5, 50)):
+        S, dt = mc.set_time_grid(ttm, npy)
+        flags = engine.mc_flags("fp64", "fp64")
+        Z0, Z1 = engine.device_normals(seed, 0, N, 0, S, flags)
+        xo, vo, qo = mc.heston_qe_step_fixed(np.zeros(N), params[0] * np.ones(N), np.zeros(N), Z0, Z1, dt, params[1], params[2], params[3], params[4])
+        x, v, q = engine.heston_terminal(engine.heston_params_c(*params), ttm, N, npy, seed, flags, C.HESTON_QE)
+        np.testing.assert_allclose(x, xo, rtol=0, atol=1e-10)
+        np.testing.assert_allclose(v, vo, rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(q, qo, rtol=0, atol=1e-11)
+        assert v.min() >= 0.0
+    assert (vo == 0.0).any()                                   # the exponential branch produced exact zeros in the second case
+    g = load_golden("heston_fourier_g4.npz")
+    chain = OptionChain(ttms=np.array([1.0]), forwards=np.ones(1), strikes_ttms=[K5], optiontypes_ttms=[T5])
+    prices, ses = HestonPricer().model_mc_price_chain(chain, HestonParams(), nb_path=1_000_000, nb_steps_per_year=251, seed=17, scheme="qe")
+    z = (prices[0] - g["prices_1"]) / ses[0]
+    assert np.all(np.abs(z) < 3.0), z
+    with pytest.raises(ValueError):
+        HestonPricer().model_mc_price_chain(chain, HestonParams(), nb_path=1000, scheme="milstein")
