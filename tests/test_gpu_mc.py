@@ -333,3 +333,49 @@ def test_heston_qe_scheme(cuda_lib):
     assert np.all(np.abs(z) < 3.0), z
     with pytest.raises(ValueError):
         HestonPricer().model_mc_price_chain(chain, HestonParams(), nb_path=1000, scheme="milstein")
+
+
+def test_edge_cases_ragged_chain_many_strikes_single_step_tiny_path_counts(cuda_lib):
+    """ragged chain: a 21-strike slice (3 register chunks) with mixed inverse codes, an EMPTY slice (J = 0 through the C ABI), a
+    single-step slice (ttm gap * n < 1), path counts 1 / 33 / 257 (not multiples of the warp or CTA size), odd step counts."""
+    from stochvolmodels_b200 import engine
+    params = (0.8376, 1.0413, 3.1844, 3.058, 0.1514, 1.8458)
+    K21 = np.linspace(0.5, 1.5, 21)
+    T21 = np.array(["IP", "P", "IC", "C"] * 5 + ["IC"])
+    ttms = np.array([0.002, 0.05, 0.051, 0.2])           # 360/yr: steps 1, 18, 1, 54
+    fw, df = np.array([1.0, 1.01, 1.01, 1.02]), np.array([1.0, 0.999, 0.999, 0.99])
+    strikes = [K21, np.zeros(0), K5, K21[:9]]
+    types = [T21, np.zeros(0, dtype="<U2"), T5, T21[:9]]
+    steps = mc.chain_steps(ttms, 360)
+    assert [s for s, _ in steps] == [1, 18, 1, 54]
+    for N in (1, 33, 257, 5000):
+        for gauss in ("fp64", "fp32"):
+            flags = engine.mc_flags("fp64", gauss)
+            Z = [engine.device_normals(5, 0, N, m, steps[m][0], flags) for m in range(4)]
+            po, eo = mc.logsv_mc_chain_fixed(params, ttms, fw, df, [K21, K5[:0], K5, K21[:9]], [T21, T5[:0], T5, T21[:9]], np.ones(4),
+                                             [z[0] for z in Z], [z[1] for z in Z], [d for _, d in steps], False, 1)
+            pg, eg = engine.logsv_mc_chain(engine.logsv_params_c(*params), ttms, fw, df, None, strikes, types, N, 360, False, 1, 5, flags)
+            assert [len(p) for p in pg] == [21, 0, 5, 9]
+            for m in (0, 2, 3):
+                np.testing.assert_allclose(pg[m], po[m], rtol=1e-8, atol=1e-11)
+                # one-pass population variance (sum p^2 / n - mean^2): absolute floor sqrt(eps)*|mean|/sqrt(N), visible only when the
+                # sample variance is ~0 (N = 1); numpy's two-pass nanstd returns exactly 0 there (DESIGN.md §3.5)
+                np.testing.assert_allclose(eg[m], eo[m], rtol=1e-7, atol=1e-11 + 3e-8 * np.max(np.abs(po[m])) / np.sqrt(N))
+
+
+def test_qvar_payoffs_in_fused_chain(cuda_lib):
+    """MC options on quadratic variance through the fused chain (variable_type = Q_VAR): vanilla and general payoff kernels."""
+    from stochvolmodels_b200 import engine
+    params = (1.0, 1.0, 5.0, 5.0, 0.2, 2.0)
+    ttms, N = np.array([0.25, 0.5]), 20000
+    Kq = np.array([0.5, 0.8, 1.0, 1.2, 1.6])
+    steps = mc.chain_steps(ttms, 252)
+    flags = engine.mc_flags("fp64", "fp32")
+    Z = [engine.device_normals(3, 0, N, m, steps[m][0], flags) for m in range(2)]
+    for types in ([np.array(["C", "P", "C", "P", "C"])] * 2, [np.array(["C", "IC", "P", "IP", "C"])] * 2):
+        po, eo = mc.logsv_mc_chain_fixed(params, ttms, np.ones(2), np.ones(2), [Kq, Kq], types, np.ones(2), [z[0] for z in Z],
+                                         [z[1] for z in Z], [d for _, d in steps], True, mc.Q_VAR)
+        pg, eg = engine.logsv_mc_chain(engine.logsv_params_c(*params), ttms, np.ones(2), np.ones(2), None, [Kq, Kq], types, N, 252, True, 2, 3, flags)
+        for m in range(2):
+            np.testing.assert_allclose(pg[m], po[m], rtol=1e-9, atol=1e-12)
+            np.testing.assert_allclose(eg[m], eo[m], rtol=1e-8, atol=1e-12)
