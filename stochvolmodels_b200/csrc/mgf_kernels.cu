@@ -145,38 +145,51 @@ __device__ __forceinline__ void rhs(const cd (&A)[N], const LogsvModel& m, const
 // --------------------------------------------------------------------------------------------------------------------
 constexpr double kRtol = 1e-3, kAtol = 1e-6;   // solve_ivp defaults, affine_expansion.py:300-301 passes none
 
+// RMS norm of v / scale over complex moduli (scipy/integrate/_ivp/common.py:63-65); inv_scale = 1 / scale.
 template <int N>
-__device__ __forceinline__ double rms_scaled(const cd (&v)[N], const double (&scale)[N]) {
+__device__ __forceinline__ double rms_scaled(const cd (&v)[N], const double (&inv_scale)[N]) {
   double s = 0.0;
 #pragma unroll
   for (int k = 0; k < N; ++k) {
-    const double re = v[k].re / scale[k], im = v[k].im / scale[k];
+    const double re = v[k].re * inv_scale[k], im = v[k].im * inv_scale[k];
     s += re * re + im * im;
   }
-  return sqrt(s) / sqrt((double)N);
+  return sqrt(s) * rsqrt((double)N);
 }
+__device__ __forceinline__ double cmod(cd a) { return sqrt(a.re * a.re + a.im * a.im); }   // |a| (no overflow risk for these magnitudes)
+__device__ __forceinline__ double pow_m02(double e) { return exp(-0.2 * log(e)); }           // e^(-1/5), e > 0
+
+// Stage storage of one thread in shared memory: K[stage][component][thread] (16-byte elements, conflict-free across threads).
+// Keeping the 7 x N complex stages out of the register file leaves ptxas room to schedule the independent products of the
+// right-hand side in parallel: the kernel is latency-bound (one warp per SM), so ILP is what matters.
+template <int N, int TPB>
+struct StageStore {
+  cd* base;
+  __device__ __forceinline__ cd& at(int stage, int k) { return base[(stage * N + k) * TPB]; }
+};
 
 // returns 0 ok, 1 step size underflow (SciPy: TOO_SMALL_STEP -> solver fails, reference keeps the last accepted state)
-template <int N>
-__device__ int rk45(cd (&y)[N], double T, const LogsvModel& m, const Coef& c, int* nfev_out) {
-  constexpr double A21 = 1.0 / 5;
-  constexpr double A31 = 3.0 / 40, A32 = 9.0 / 40;
-  constexpr double A41 = 44.0 / 45, A42 = -56.0 / 15, A43 = 32.0 / 9;
-  constexpr double A51 = 19372.0 / 6561, A52 = -25360.0 / 2187, A53 = 64448.0 / 6561, A54 = -212.0 / 729;
-  constexpr double A61 = 9017.0 / 3168, A62 = -355.0 / 33, A63 = 46732.0 / 5247, A64 = 49.0 / 176, A65 = -5103.0 / 18656;
-  constexpr double B1 = 35.0 / 384, B3 = 500.0 / 1113, B4 = 125.0 / 192, B5 = -2187.0 / 6784, B6 = 11.0 / 84;
-  constexpr double E1 = -71.0 / 57600, E3 = 71.0 / 16695, E4 = -71.0 / 1920, E5 = 17253.0 / 339200, E6 = -22.0 / 525, E7 = 1.0 / 40;
+template <int N, int TPB>
+__device__ int rk45(cd (&y)[N], double T, const LogsvModel& m, const Coef& c, StageStore<N, TPB> K, int* nfev_out) {
+  constexpr double A[6][5] = {{0, 0, 0, 0, 0},
+                              {1.0 / 5, 0, 0, 0, 0},
+                              {3.0 / 40, 9.0 / 40, 0, 0, 0},
+                              {44.0 / 45, -56.0 / 15, 32.0 / 9, 0, 0},
+                              {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729, 0},
+                              {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656}};
+  constexpr double B[6] = {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84};
+  constexpr double E[7] = {-71.0 / 57600, 0, 71.0 / 16695, -71.0 / 1920, 17253.0 / 339200, -22.0 / 525, 1.0 / 40};
 
   cd f[N];
   rhs<N>(y, m, c, f);
   int nfev = 1;
-  double scale[N];
-  // ---- select_initial_step
+  double inv_scale[N];
+  // ---- select_initial_step (scipy/integrate/_ivp/common.py:109-134)
   double h_abs;
   {
 #pragma unroll
-    for (int k = 0; k < N; ++k) scale[k] = kAtol + cabs_(y[k]) * kRtol;
-    const double d0 = rms_scaled<N>(y, scale), d1 = rms_scaled<N>(f, scale);
+    for (int k = 0; k < N; ++k) inv_scale[k] = 1.0 / (kAtol + cmod(y[k]) * kRtol);
+    const double d0 = rms_scaled<N>(y, inv_scale), d1 = rms_scaled<N>(f, inv_scale);
     double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
     h0 = fmin(h0, T);
     cd y1[N], f1[N];
@@ -186,8 +199,8 @@ __device__ int rk45(cd (&y)[N], double T, const LogsvModel& m, const Coef& c, in
     ++nfev;
 #pragma unroll
     for (int k = 0; k < N; ++k) f1[k] = f1[k] - f[k];
-    const double d2 = rms_scaled<N>(f1, scale) / h0;
-    const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / fmax(d1, d2), 0.2);
+    const double d2 = rms_scaled<N>(f1, inv_scale) / h0;
+    const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : exp(0.2 * log(0.01 / fmax(d1, d2)));
     h_abs = fmin(fmin(100.0 * h0, h1), T);
   }
   double t = 0.0;
@@ -205,46 +218,53 @@ __device__ int rk45(cd (&y)[N], double T, const LogsvModel& m, const Coef& c, in
       if (t_new - T > 0.0) t_new = T;
       const double h = t_new - t;
       h_abs = fabs(h);
-      cd k2[N], k3[N], k4[N], k5[N], k6[N], k7[N], yt[N], yn[N];
+      cd yt[N], kn[N];
 #pragma unroll
-      for (int k = 0; k < N; ++k) yt[k] = y[k] + (f[k] * A21) * h;
-      rhs<N>(yt, m, c, k2);
+      for (int s = 1; s < 6; ++s) {            // rk_step (scipy/integrate/_ivp/rk.py:60-64): dy = (sum_j K_j a_sj) * h
 #pragma unroll
-      for (int k = 0; k < N; ++k) yt[k] = y[k] + (f[k] * A31 + k2[k] * A32) * h;
-      rhs<N>(yt, m, c, k3);
+        for (int k = 0; k < N; ++k) {
+          cd acc = f[k] * A[s][0];
 #pragma unroll
-      for (int k = 0; k < N; ++k) yt[k] = y[k] + (f[k] * A41 + k2[k] * A42 + k3[k] * A43) * h;
-      rhs<N>(yt, m, c, k4);
+          for (int jj = 1; jj < s; ++jj) acc = acc + K.at(jj, k) * A[s][jj];
+          yt[k] = y[k] + acc * h;
+        }
+        rhs<N>(yt, m, c, kn);
 #pragma unroll
-      for (int k = 0; k < N; ++k) yt[k] = y[k] + (f[k] * A51 + k2[k] * A52 + k3[k] * A53 + k4[k] * A54) * h;
-      rhs<N>(yt, m, c, k5);
+        for (int k = 0; k < N; ++k) K.at(s, k) = kn[k];
+      }
+      cd yn[N];
 #pragma unroll
-      for (int k = 0; k < N; ++k) yt[k] = y[k] + (f[k] * A61 + k2[k] * A62 + k3[k] * A63 + k4[k] * A64 + k5[k] * A65) * h;
-      rhs<N>(yt, m, c, k6);
+      for (int k = 0; k < N; ++k) {
+        cd acc = f[k] * B[0];
 #pragma unroll
-      for (int k = 0; k < N; ++k) yn[k] = y[k] + h * (f[k] * B1 + k3[k] * B3 + k4[k] * B4 + k5[k] * B5 + k6[k] * B6);
-      rhs<N>(yn, m, c, k7);
+        for (int jj = 2; jj < 6; ++jj) acc = acc + K.at(jj, k) * B[jj];      // B[1] = 0
+        yn[k] = y[k] + h * acc;
+      }
+      rhs<N>(yn, m, c, kn);                                                   // K[6] = f(t + h, y_new)
       nfev += 6;
       cd err[N];
 #pragma unroll
       for (int k = 0; k < N; ++k) {
-        scale[k] = kAtol + fmax(cabs_(y[k]), cabs_(yn[k])) * kRtol;
-        err[k] = (f[k] * E1 + k3[k] * E3 + k4[k] * E4 + k5[k] * E5 + k6[k] * E6 + k7[k] * E7) * h;
+        inv_scale[k] = 1.0 / (kAtol + fmax(cmod(y[k]), cmod(yn[k])) * kRtol);
+        cd acc = f[k] * E[0];
+#pragma unroll
+        for (int jj = 2; jj < 6; ++jj) acc = acc + K.at(jj, k) * E[jj];      // E[1] = 0
+        err[k] = (acc + kn[k] * E[6]) * h;
       }
-      const double en = rms_scaled<N>(err, scale);
+      const double en = rms_scaled<N>(err, inv_scale);
       if (en < 1.0) {
-        double factor = en == 0.0 ? 10.0 : fmin(10.0, 0.9 * pow(en, -0.2));
+        double factor = en == 0.0 ? 10.0 : fmin(10.0, 0.9 * pow_m02(en));
         if (rejected) factor = fmin(1.0, factor);
         h_abs *= factor;
         t = t_new;
 #pragma unroll
         for (int k = 0; k < N; ++k) {
           y[k] = yn[k];
-          f[k] = k7[k];     // FSAL
+          f[k] = kn[k];     // FSAL
         }
         break;
       }
-      h_abs *= fmax(0.2, 0.9 * pow(en, -0.2));
+      h_abs *= fmax(0.2, 0.9 * pow_m02(en));
       rejected = true;
     }
     if (status) break;
@@ -259,12 +279,14 @@ struct ChainSpec {   // per-maturity scalars (device array of M entries)
 };
 
 // one thread = one grid point through all M maturities.  a_io: [P][N] in (A(0)) ; a_out: [M][P][N]; log_mgf: [M][P]
-template <int N>
-__global__ void logsv_mgf_kernel(const cd* __restrict__ phi, const cd* __restrict__ psi, int P, int M,
+template <int N, int TPB>
+__global__ void __launch_bounds__(TPB) logsv_mgf_kernel(const cd* __restrict__ phi, const cd* __restrict__ psi, int P, int M,
                                  const ChainSpec* __restrict__ spec, const cd* __restrict__ a_in, cd* __restrict__ a_out,
                                  cd* __restrict__ log_mgf, double y, int* __restrict__ status, int* __restrict__ nfev) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ cd stage_smem[6 * N * TPB];
+  const int p = blockIdx.x * TPB + threadIdx.x;
   if (p >= P) return;
+  StageStore<N, TPB> K{stage_smem + threadIdx.x};
   cd A[N];
 #pragma unroll
   for (int k = 0; k < N; ++k) A[k] = a_in ? a_in[(size_t)p * N + k] : mk(0.0);
@@ -277,7 +299,7 @@ __global__ void logsv_mgf_kernel(const cd* __restrict__ phi, const cd* __restric
     const LogsvModel model = spec[mm].model;
     const Coef c = make_coef(model, ph, ps);
     int nfe = 0;
-    st |= rk45<N>(A, spec[mm].dtau, model, c, &nfe);
+    st |= rk45<N, TPB>(A, spec[mm].dtau, model, c, K, &nfe);
     nf += nfe;
     cd lm = mk(0.0);
 #pragma unroll
@@ -428,6 +450,18 @@ static int launched(const char* what) {
   return 0;
 }
 
+template <int N>
+static void launch_logsv_mgf(int tpb, int nb, cudaStream_t st, const cd* phi, const cd* psi, int P, int M, const ChainSpec* spec,
+                             const cd* a_in, cd* a_out, cd* lm, double y, int* status) {
+  switch (tpb) {
+    case 4: logsv_mgf_kernel<N, 4><<<nb, 4, 0, st>>>(phi, psi, P, M, spec, a_in, a_out, lm, y, status, nullptr); break;
+    case 8: logsv_mgf_kernel<N, 8><<<nb, 8, 0, st>>>(phi, psi, P, M, spec, a_in, a_out, lm, y, status, nullptr); break;
+    case 16: logsv_mgf_kernel<N, 16><<<nb, 16, 0, st>>>(phi, psi, P, M, spec, a_in, a_out, lm, y, status, nullptr); break;
+    case 32: logsv_mgf_kernel<N, 32><<<nb, 32, 0, st>>>(phi, psi, P, M, spec, a_in, a_out, lm, y, status, nullptr); break;
+    default: logsv_mgf_kernel<N, 64><<<nb, 64, 0, st>>>(phi, psi, P, M, spec, a_in, a_out, lm, y, status, nullptr); break;
+  }
+}
+
 static int mgf_block_threads(int P) {
   int t = 4;
   while (t < 64 && t * 148 < P) t <<= 1;
@@ -564,9 +598,9 @@ int b200sv_logsv_price_chain(const b200sv_logsv_params* params, int M, const dou
   const double y = params->sigma0 - params->theta;
   const cd* dpsi = qvar ? d_psi.as<cd>() : nullptr;
   if (N == 5)
-    logsv_mgf_kernel<5><<<nb, tpb, 0, st>>>(d_phi.as<cd>(), dpsi, P, M, d_spec.as<ChainSpec>(), nullptr, d_a.as<cd>(), d_lm.as<cd>(), y, d_stat.as<int>(), nullptr);
+    launch_logsv_mgf<5>(tpb, nb, st, d_phi.as<cd>(), dpsi, P, M, d_spec.as<ChainSpec>(), nullptr, d_a.as<cd>(), d_lm.as<cd>(), y, d_stat.as<int>());
   else
-    logsv_mgf_kernel<3><<<nb, tpb, 0, st>>>(d_phi.as<cd>(), dpsi, P, M, d_spec.as<ChainSpec>(), nullptr, d_a.as<cd>(), d_lm.as<cd>(), y, d_stat.as<int>(), nullptr);
+    launch_logsv_mgf<3>(tpb, nb, st, d_phi.as<cd>(), dpsi, P, M, d_spec.as<ChainSpec>(), nullptr, d_a.as<cd>(), d_lm.as<cd>(), y, d_stat.as<int>());
   if (int rc = launched("logsv_mgf_kernel")) return rc;
   if (Jtot > 0) {
     if (qvar)
@@ -672,9 +706,9 @@ int b200sv_logsv_mgf_grid(const double* phi, const double* psi, int P, double dt
   const double y = params->sigma0 - params->theta;
   const cd* dpsi = psi ? d_psi.as<cd>() : nullptr;
   if (N == 5)
-    logsv_mgf_kernel<5><<<nb, tpb, 0, st>>>(d_phi.as<cd>(), dpsi, P, 1, d_spec.as<ChainSpec>(), d_a0.as<cd>(), d_a1.as<cd>(), d_lm.as<cd>(), y, nullptr, nullptr);
+    launch_logsv_mgf<5>(tpb, nb, st, d_phi.as<cd>(), dpsi, P, 1, d_spec.as<ChainSpec>(), d_a0.as<cd>(), d_a1.as<cd>(), d_lm.as<cd>(), y, nullptr);
   else
-    logsv_mgf_kernel<3><<<nb, tpb, 0, st>>>(d_phi.as<cd>(), dpsi, P, 1, d_spec.as<ChainSpec>(), d_a0.as<cd>(), d_a1.as<cd>(), d_lm.as<cd>(), y, nullptr, nullptr);
+    launch_logsv_mgf<3>(tpb, nb, st, d_phi.as<cd>(), dpsi, P, 1, d_spec.as<ChainSpec>(), d_a0.as<cd>(), d_a1.as<cd>(), d_lm.as<cd>(), y, nullptr);
   if (int rc = launched("logsv_mgf_kernel")) return rc;
   B200SV_CUDA(cudaMemcpyAsync(a_inout, d_a1.p, sizeof(cd) * (size_t)P * N, cudaMemcpyDeviceToHost, st));
   B200SV_CUDA(cudaMemcpyAsync(log_mgf_out, d_lm.p, sizeof(cd) * P, cudaMemcpyDeviceToHost, st));
