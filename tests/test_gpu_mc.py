@@ -379,3 +379,30 @@ def test_qvar_payoffs_in_fused_chain(cuda_lib):
         for m in range(2):
             np.testing.assert_allclose(pg[m], po[m], rtol=1e-9, atol=1e-12)
             np.testing.assert_allclose(eg[m], eo[m], rtol=1e-8, atol=1e-12)
+
+
+def test_full_size_properties_1e8_paths(cuda_lib):
+    """BASELINE.json full size (1e8 paths x 252 steps, BTC chain) through size-independent properties: put-call parity is EXACT under the
+    forward re-centring (C - P = df (F - K) for every strike), prices are bitwise reproducible for a seed, monotone in strike, standard errors
+    scale as 1/sqrt(N), and every strike is within the north_star's 1e-3 (forward-normalised) of the reference Fourier price."""
+    from stochvolmodels_b200 import LOGSV_BTC_PARAMS, LogSVPricer, OptionChain, get_btc_test_chain_data
+    btc = get_btc_test_chain_data()
+    fourier = load_golden("logsv_fourier_btc.npz")
+    calls = OptionChain(ttms=btc.ttms, forwards=btc.forwards, strikes_ttms=btc.strikes_ttms, optiontypes_ttms=[np.array(["C"] * len(k)) for k in btc.strikes_ttms])
+    puts = OptionChain(ttms=btc.ttms, forwards=btc.forwards, strikes_ttms=btc.strikes_ttms, optiontypes_ttms=[np.array(["P"] * len(k)) for k in btc.strikes_ttms])
+    N = 100_000_000
+    pricer = LogSVPricer()
+    pc, ec = pricer.model_mc_price_chain(calls, LOGSV_BTC_PARAMS, nb_path=N, nb_steps=582, seed=42)
+    pp, ep = pricer.model_mc_price_chain(puts, LOGSV_BTC_PARAMS, nb_path=N, nb_steps=582, seed=42)
+    pm, em = pricer.model_mc_price_chain(btc, LOGSV_BTC_PARAMS, nb_path=N, nb_steps=582, seed=42)
+    pm2, _ = pricer.model_mc_price_chain(btc, LOGSV_BTC_PARAMS, nb_path=N, nb_steps=582, seed=42)
+    ps, es = pricer.model_mc_price_chain(btc, LOGSV_BTC_PARAMS, nb_path=N // 100, nb_steps=582, seed=42)
+    for m in range(4):
+        F, K = btc.forwards[m], btc.strikes_ttms[m]
+        np.testing.assert_allclose(pc[m] - pp[m], F - K, rtol=0, atol=2e-9 * F)            # exact parity (fp64 summation of 1e8 terms)
+        np.testing.assert_array_equal(pm[m], pm2[m])                                          # same seed => same bits
+        is_call = btc.optiontypes_ttms[m] == "C"
+        np.testing.assert_allclose(pm[m], np.where(is_call, pc[m], pp[m]), rtol=1e-12)         # mixed chain == per-type chains
+        assert np.all(np.diff(pc[m]) < 0) and np.all(np.diff(pp[m]) > 0)                       # monotone in strike
+        np.testing.assert_allclose(es[m] / em[m], 10.0, rtol=0.05)                             # SE ~ 1/sqrt(N)
+        assert np.all(np.abs(pm[m] - fourier[f"prices_{m}"]) / F < 1e-3)
