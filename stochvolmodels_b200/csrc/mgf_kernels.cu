@@ -116,8 +116,29 @@ __device__ __forceinline__ Coef make_coef(const LogsvModel& m, cd phi, cd psi) {
   return c;
 }
 
-template <int N>
-__device__ __forceinline__ void rhs(const cd (&A)[N], const LogsvModel& m, const Coef& c, cd (&out)[N]) {
+// The 14 phi/psi-dependent coefficients of one thread, parked in shared memory ([coef][thread]) like the RK stages: the kernel is
+// latency-bound, so register space is better spent on independent in-flight products than on long-lived constants.
+template <int TPB>
+struct CoefView {
+  const cd* base;
+  __device__ __forceinline__ cd at(int i) const { return base[i * TPB]; }
+};
+template <int TPB>
+__device__ __forceinline__ void store_coef(cd* base, const Coef& c) {
+  const cd v[14] = {c.l01, c.l11, c.l12, c.l21, c.l22, c.l23, c.l32, c.l33, c.l34, c.l43, c.l44, c.h0, c.h1, c.h2};
+#pragma unroll
+  for (int i = 0; i < 14; ++i) base[i * TPB] = v[i];
+}
+
+template <int N, int TPB>
+__device__ __forceinline__ void rhs(const cd (&A)[N], const LogsvModel& m, const CoefView<TPB>& cv, cd (&out)[N]) {
+  struct {
+    cd l01, l11, l12, l21, l22, l23, l32, l33, l34, l43, l44, h0, h1, h2;
+  } c;
+  c.l01 = cv.at(0); c.l11 = cv.at(1); c.l12 = cv.at(2); c.l21 = cv.at(3); c.l22 = cv.at(4); c.h0 = cv.at(11); c.h1 = cv.at(12); c.h2 = cv.at(13);
+  if constexpr (N == 5) {
+    c.l23 = cv.at(5); c.l32 = cv.at(6); c.l33 = cv.at(7); c.l34 = cv.at(8); c.l43 = cv.at(9); c.l44 = cv.at(10);
+  }
   const double v2 = m.v2, qv = m.qv, qv2 = m.qv2;
   const cd a1 = A[1], a2 = A[2];
   const cd a11 = a1 * a1, a12 = a1 * a2, a22 = a2 * a2;
@@ -143,6 +164,12 @@ __device__ __forceinline__ void rhs(const cd (&A)[N], const LogsvModel& m, const
 // SciPy RK45 clone (scipy/integrate/_ivp/rk.py:111-170 step loop, :14-69 stages, :538-552 tableau;
 //                   scipy/integrate/_ivp/common.py:63-65 norm, :109-134 select_initial_step)
 // --------------------------------------------------------------------------------------------------------------------
+__constant__ double c_A[6][5] = {{0, 0, 0, 0, 0},
+                                 {1.0 / 5, 0, 0, 0, 0},
+                                 {3.0 / 40, 9.0 / 40, 0, 0, 0},
+                                 {44.0 / 45, -56.0 / 15, 32.0 / 9, 0, 0},
+                                 {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729, 0},
+                                 {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656}};   // Dormand-Prince A (rk.py:542-549)
 constexpr double kRtol = 1e-3, kAtol = 1e-6;   // solve_ivp defaults, affine_expansion.py:300-301 passes none
 
 // RMS norm of v / scale over complex moduli (scipy/integrate/_ivp/common.py:63-65); inv_scale = 1 / scale.
@@ -170,7 +197,7 @@ struct StageStore {
 
 // returns 0 ok, 1 step size underflow (SciPy: TOO_SMALL_STEP -> solver fails, reference keeps the last accepted state)
 template <int N, int TPB>
-__device__ int rk45(cd (&y)[N], double T, const LogsvModel& m, const Coef& c, StageStore<N, TPB> K, int* nfev_out) {
+__device__ int rk45(cd (&y)[N], double T, const LogsvModel& m, const CoefView<TPB>& c, StageStore<N, TPB> K, int* nfev_out) {
   constexpr double A[6][5] = {{0, 0, 0, 0, 0},
                               {1.0 / 5, 0, 0, 0, 0},
                               {3.0 / 40, 9.0 / 40, 0, 0, 0},
@@ -180,8 +207,8 @@ __device__ int rk45(cd (&y)[N], double T, const LogsvModel& m, const Coef& c, St
   constexpr double B[6] = {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84};
   constexpr double E[7] = {-71.0 / 57600, 0, 71.0 / 16695, -71.0 / 1920, 17253.0 / 339200, -22.0 / 525, 1.0 / 40};
 
-  cd f[N];
-  rhs<N>(y, m, c, f);
+  cd f[N];                       // f(t, y): registers during the initial-step selection, then stage 0 of the shared-memory store
+  rhs<N, TPB>(y, m, c, f);
   int nfev = 1;
   double inv_scale[N];
   // ---- select_initial_step (scipy/integrate/_ivp/common.py:109-134)
@@ -195,7 +222,7 @@ __device__ int rk45(cd (&y)[N], double T, const LogsvModel& m, const Coef& c, St
     cd y1[N], f1[N];
 #pragma unroll
     for (int k = 0; k < N; ++k) y1[k] = y[k] + h0 * f[k];
-    rhs<N>(y1, m, c, f1);
+    rhs<N, TPB>(y1, m, c, f1);
     ++nfev;
 #pragma unroll
     for (int k = 0; k < N; ++k) f1[k] = f1[k] - f[k];
@@ -205,6 +232,8 @@ __device__ int rk45(cd (&y)[N], double T, const LogsvModel& m, const Coef& c, St
   }
   double t = 0.0;
   int status = 0;
+#pragma unroll
+  for (int k = 0; k < N; ++k) K.at(0, k) = f[k];
   for (int guard = 0; t < T && guard < 100000; ++guard) {
     const double min_step = 10.0 * (__longlong_as_double(__double_as_longlong(t) + 1) - t);   // 10*|nextafter(t, inf) - t|, t >= 0
     if (h_abs < min_step) h_abs = min_step;           // max_step = inf
@@ -219,34 +248,36 @@ __device__ int rk45(cd (&y)[N], double T, const LogsvModel& m, const Coef& c, St
       const double h = t_new - t;
       h_abs = fabs(h);
       cd yt[N], kn[N];
-#pragma unroll
+#pragma unroll 1
       for (int s = 1; s < 6; ++s) {            // rk_step (scipy/integrate/_ivp/rk.py:60-64): dy = (sum_j K_j a_sj) * h
+        // not unrolled on purpose: the fully unrolled body (5 inlined right-hand sides) is ~70 KB of SASS and the single resident
+        // warp per SM then stalls on instruction fetch; stages >= s still hold zeros / stale finite values and get coefficient 0
 #pragma unroll
         for (int k = 0; k < N; ++k) {
-          cd acc = f[k] * A[s][0];
+          cd acc = K.at(0, k) * c_A[s][0];
 #pragma unroll
-          for (int jj = 1; jj < s; ++jj) acc = acc + K.at(jj, k) * A[s][jj];
+          for (int jj = 1; jj < 5; ++jj) acc = acc + K.at(jj, k) * c_A[s][jj];
           yt[k] = y[k] + acc * h;
         }
-        rhs<N>(yt, m, c, kn);
+        rhs<N, TPB>(yt, m, c, kn);
 #pragma unroll
         for (int k = 0; k < N; ++k) K.at(s, k) = kn[k];
       }
       cd yn[N];
 #pragma unroll
       for (int k = 0; k < N; ++k) {
-        cd acc = f[k] * B[0];
+        cd acc = K.at(0, k) * B[0];
 #pragma unroll
         for (int jj = 2; jj < 6; ++jj) acc = acc + K.at(jj, k) * B[jj];      // B[1] = 0
         yn[k] = y[k] + h * acc;
       }
-      rhs<N>(yn, m, c, kn);                                                   // K[6] = f(t + h, y_new)
+      rhs<N, TPB>(yn, m, c, kn);                                                   // K[6] = f(t + h, y_new)
       nfev += 6;
       cd err[N];
 #pragma unroll
       for (int k = 0; k < N; ++k) {
         inv_scale[k] = 1.0 / (kAtol + fmax(cmod(y[k]), cmod(yn[k])) * kRtol);
-        cd acc = f[k] * E[0];
+        cd acc = K.at(0, k) * E[0];
 #pragma unroll
         for (int jj = 2; jj < 6; ++jj) acc = acc + K.at(jj, k) * E[jj];      // E[1] = 0
         err[k] = (acc + kn[k] * E[6]) * h;
@@ -260,7 +291,7 @@ __device__ int rk45(cd (&y)[N], double T, const LogsvModel& m, const Coef& c, St
 #pragma unroll
         for (int k = 0; k < N; ++k) {
           y[k] = yn[k];
-          f[k] = kn[k];     // FSAL
+          K.at(0, k) = kn[k];     // FSAL: K[6] of this step is K[0] of the next
         }
         break;
       }
@@ -284,9 +315,12 @@ __global__ void __launch_bounds__(TPB) logsv_mgf_kernel(const cd* __restrict__ p
                                  const ChainSpec* __restrict__ spec, const cd* __restrict__ a_in, cd* __restrict__ a_out,
                                  cd* __restrict__ log_mgf, double y, int* __restrict__ status, int* __restrict__ nfev) {
   __shared__ cd stage_smem[6 * N * TPB];
+  __shared__ cd coef_smem[14 * TPB];
   const int p = blockIdx.x * TPB + threadIdx.x;
   if (p >= P) return;
   StageStore<N, TPB> K{stage_smem + threadIdx.x};
+#pragma unroll
+  for (int i = 0; i < 6 * N; ++i) stage_smem[threadIdx.x + i * TPB] = mk(0.0);      // stages read with coefficient 0 must be finite
   cd A[N];
 #pragma unroll
   for (int k = 0; k < N; ++k) A[k] = a_in ? a_in[(size_t)p * N + k] : mk(0.0);
@@ -297,7 +331,8 @@ __global__ void __launch_bounds__(TPB) logsv_mgf_kernel(const cd* __restrict__ p
   int st = 0, nf = 0;
   for (int mm = 0; mm < M; ++mm) {
     const LogsvModel model = spec[mm].model;
-    const Coef c = make_coef(model, ph, ps);
+    store_coef<TPB>(coef_smem + threadIdx.x, make_coef(model, ph, ps));
+    const CoefView<TPB> c{coef_smem + threadIdx.x};
     int nfe = 0;
     st |= rk45<N, TPB>(A, spec[mm].dtau, model, c, K, &nfe);
     nf += nfe;

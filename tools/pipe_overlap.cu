@@ -5,7 +5,7 @@
 #include <cuda_runtime.h>
 constexpr int ITERS = 2048;
 template <int ND, int NI, int NM, int HL = 0>
-__global__ void k_mix(double* out, double a, double b, uint32_t m) {
+__global__ void k_mix(double* out, double a, double b, uint32_t m, uint32_t zero = 0) {
   double d[4]; uint32_t v[4]; float f[2];
   for (int c = 0; c < 4; ++c) { d[c] = threadIdx.x * 1e-3 + c; v[c] = threadIdx.x + c; }
   f[0] = 1.5f + threadIdx.x * 1e-3f; f[1] = 2.5f + threadIdx.x * 1e-3f;
@@ -16,7 +16,8 @@ __global__ void k_mix(double* out, double a, double b, uint32_t m) {
       if (k < NI) {
         uint32_t hi, lo;
         if (HL == 0) asm volatile("{\n\t.reg .u64 p;\n\tmul.wide.u32 p, %2, %3;\n\tmov.b64 {%1, %0}, p;\n\t}" : "=r"(hi), "=r"(lo) : "r"(v[k & 3]), "r"(m));
-        else { asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(hi) : "r"(v[k & 3]), "r"(m)); asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(lo) : "r"(v[k & 3]), "r"(m)); }
+        else if (HL == 1) { asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(hi) : "r"(v[k & 3]), "r"(m)); asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(lo) : "r"(v[k & 3]), "r"(m)); }
+        else { const uint32_t v2 = v[k & 3] + zero; asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(hi) : "r"(v[k & 3]), "r"(m)); asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(lo) : "r"(v2), "r"(m)); }
         v[k & 3] = hi ^ lo;
       }
       if (k < NM) asm volatile("lg2.approx.ftz.f32 %0, %0;" : "+f"(f[k & 1]));
@@ -46,6 +47,9 @@ int main() {
     float tdhl = timeit([&] { k_mix<26, 10, 0, 1><<<blocks, threads>>>((double*)buf, 1.0000001, 1e-9, 0xD2511F53u); });
     float tall = timeit([&] { k_mix<26, 10, 4, 1><<<blocks, threads>>>((double*)buf, 1.0000001, 1e-9, 0xD2511F53u); });
     printf("warps/SM %2d mul.hi+mul.lo instead of mul.wide: 10 pairs alone %.1f | with 26 DFMA %.1f | with DFMA and MUFU %.1f\n", wpsm, cyc(thl), cyc(tdhl), cyc(tall));
+    float t2 = timeit([&] { k_mix<0, 10, 0, 2><<<blocks, threads>>>((double*)buf, 1.0000001, 1e-9, 0xD2511F53u, 0u); });
+    float td2 = timeit([&] { k_mix<26, 10, 0, 2><<<blocks, threads>>>((double*)buf, 1.0000001, 1e-9, 0xD2511F53u, 0u); });
+    printf("warps/SM %2d UNFUSED IMAD.HI + IMAD (+IADD): 10 pairs alone %.1f | with 26 DFMA %.1f\n", wpsm, cyc(t2), cyc(td2));
     printf("warps/SM %2d pairs: DFMA+IMAD.WIDE %.1f (sum %.1f) | DFMA+MUFU %.1f (sum %.1f) | IMAD.WIDE+MUFU %.1f (sum %.1f)\n", wpsm, cyc(tdi),
            cyc(td) + cyc(ti), cyc(tdm), cyc(td) + cyc(tm), cyc(tim), cyc(ti) + cyc(tm));
     printf("warps/SM %2d: clk per iteration per warp-slot: 26 DFMA %.1f | 10 IMAD.WIDE %.1f | 4 MUFU %.1f | all three interleaved %.1f (sum %.1f, max %.1f)\n",
