@@ -147,6 +147,8 @@ def main():
     ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"])
     ap.add_argument("--gauss", default="fp32", choices=["fp32", "fp64"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "collective"],
+                    help="N>1: per-maturity moment exchange through NVLink peer memory inside the kernels (p2p) or NCCL all-reduce (collective)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -176,6 +178,9 @@ def main():
     offsets, strikes, types = C.flatten_chain(chain.strikes_ttms, chain.optiontypes_ttms)
     sizes = np.diff(offsets)
     eng = CudaMcEngine("logsv", _params_c(params), n_local, rank * n_local, flags, int(sizes.max()))
+    use_p2p = world > 1 and args.exchange == "p2p"     # the two per-maturity messages ride inside the kernels over NVLink peer memory
+    if use_p2p:
+        eng.enable_p2p()
     strikes_dev = eng.to_device(strikes, torch.float64)
     types_dev = eng.to_device(types, torch.int8)
     out_dev = torch.zeros((2, strikes.shape[0]), dtype=torch.float64, device=eng.device)
@@ -197,11 +202,11 @@ def main():
             if record:
                 e1.record()
                 slice_events.append((e0, e1, S))
-            if world > 1:
+            if world > 1 and not use_p2p:
                 dist.all_reduce(mom)
             J, jo = int(sizes[m]), int(offsets[m])
             sums = eng.payoff_sums(float(chain.ttms[m]), float(chain.forwards[m]), strikes_dev[jo: jo + J], types_dev[jo: jo + J], J, C.LOG_RETURN, 1)
-            if world > 1:
+            if world > 1 and not use_p2p:
                 dist.all_reduce(sums)
             p, s = eng.finalize(sums, J, float(chain.discfactors[m]), total_paths)
             out_dev[0, jo: jo + J].copy_(p)
@@ -240,7 +245,7 @@ def main():
     # ---------------- end-to-end arm: public API, host buffers ----------------
     pricer = LogSVPricer()
     api = lambda seed: pricer.model_mc_price_chain(chain, params, nb_path=total_paths, nb_steps=NB_STEPS_PER_YEAR, seed=seed,
-                                                   precision=args.precision, gauss=args.gauss)
+                                                   precision=args.precision, gauss=args.gauss, exchange=args.exchange)
     del eng
     torch.cuda.empty_cache()
     for w in range(min(args.warmup, 2)):
@@ -268,7 +273,9 @@ def main():
                 "config": {"workload": "LogSV MC, BTC chain 4 maturities x 49 strikes, 252 steps/path (nb_steps_per_year=582, "
                                        "slices 25+34+57+136), LOGSV_BTC_PARAMS", "paths_per_gpu": n_local, "paths_total": total_paths,
                            "state": args.precision, "gaussians": f"Philox4x32-10 + Box-Muller {args.gauss}",
-                           "parallelism": f"paths sharded over {world} GPU(s); 2 fp64 all-reduces (16 B, 24*J B) per maturity",
+                           "parallelism": f"paths sharded over {world} GPU(s); 2 fp64 exchanges (16 B, 24*J B) per maturity, "
+                                          + ("none needed at N=1" if world == 1 else ("fused into the reduction/payoff kernels over NVLink peer memory"
+                                                                                      if use_p2p else "NCCL all-reduce")),
                            "l2": "per-GPU state 3 x paths x 8 B >> 126 MB L2 (inputs larger than L2; no flush needed)"},
                 "e2e": {"value": e2e_value, "unit": "path-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "api": "LogSVPricer.model_mc_price_chain (host numpy in/out through the C ABI)", "same_prices_as_device_arm": same},

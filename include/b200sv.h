@@ -128,10 +128,11 @@ int b200sv_device_normals(uint64_t seed, long long path0, long long n, int slice
  * (sum over non-NaN paths of forward*exp(x), count of non-NaN paths) for THIS rank. */
 int b200sv_dev_logsv_slice(void* x, void* sigma, void* qvar, long long n_local, long long path_offset, int init,
                            const b200sv_logsv_params* params, double eta, int is_spot_measure, int nsteps, double dt,
-                           int slice_index, double forward, uint64_t seed, int flags, double* moments_out, void* stream);
+                           int slice_index, double forward, uint64_t seed, int flags, double* moments_out, void* p2p_ctx,
+                           void* stream);
 int b200sv_dev_heston_slice(void* x, void* var, void* qvar, long long n_local, long long path_offset, int init,
                             const b200sv_heston_params* params, int nsteps, double dt, int slice_index, double forward,
-                            uint64_t seed, int flags, int scheme, double* moments_out, void* stream);
+                            uint64_t seed, int flags, int scheme, double* moments_out, void* p2p_ctx, void* stream);
 
 /* per-strike payoff sums for local paths given the GLOBAL (all-reduced) re-centring moments[2]:
  * sums_out[3*J] (device) = (sum pay, sum pay^2, count non-NaN) per strike for THIS rank.
@@ -139,11 +140,25 @@ int b200sv_dev_heston_slice(void* x, void* var, void* qvar, long long n_local, l
  * 'C'/'P', bit 1: some 'IC'/'IP'; 1 selects the branch-free vanilla kernel, anything else (0 = unknown) the general one. */
 int b200sv_dev_payoff_sums(const void* x, const void* qvar, long long n_local, int flags, double ttm, double forward,
                            const double* strikes, const int8_t* types, int J, int variable_type, int payoff_kinds_hint,
-                           const double* moments, double* sums_out, void* stream);
+                           const double* moments, double* sums_out, void* p2p_ctx, void* stream);
 
 /* turn GLOBAL sums[3*J] into prices / std errors (device arrays of J): price = df*s1/n, se = df*sqrt(s2/n-(s1/n)^2)/sqrt(N). */
 int b200sv_dev_payoff_finalize(const double* sums, int J, double discfactor, long long total_paths, double* prices_out,
-                               double* stderr_out, void* stream);
+                               double* stderr_out, void* p2p_ctx, void* stream);
+
+/* Peer-memory exchange of the two per-maturity messages (csrc/p2p.cuh): with a non-NULL p2p_ctx the calls above fuse the exchange into
+ * their kernels instead of leaving it to the host's collective -- *_slice and *_payoff_sums PUBLISH their local values into every
+ * peer's mailbox over NVLink from the reduction kernel that produces them, *_payoff_sums and *_payoff_finalize GATHER the global values
+ * (summed in rank order) in their prologue; `moments` / `sums` arguments then carry this rank's local values only.  All ranks must
+ * issue the same sequence of calls (a publish whose predecessor was never gathered on this rank gets a flag-wait inserted, which keeps
+ * the double-buffered mailbox race-free when a maturity has no strikes or a rank has no paths).  create: allocates this rank's mailbox (max_values >= 3 * max strikes per slice) and returns a
+ * 64-byte CUDA IPC handle to all-gather among the ranks of the node; connect: maps the peers' mailboxes (handles in rank order). */
+int b200sv_p2p_create(int world, int rank, int max_values, void** ctx_out, unsigned char* handle_out);
+int b200sv_p2p_connect(void* p2p_ctx, const unsigned char* handles);
+int b200sv_p2p_destroy(void* p2p_ctx);
+/* standalone halves of an exchange (ranks without local paths; tests): publish K local values / gather the K global ones */
+int b200sv_dev_p2p_publish(void* p2p_ctx, const double* vals, int K, void* stream);
+int b200sv_dev_p2p_gather(void* p2p_ctx, int K, double* out, void* stream);
 
 /* device-level twins of b200sv_logsv_step_fixed / b200sv_heston_step_fixed (all arrays on the device; W row-major [S][N]):
  * the calibration inner loop logsv_mc_chain_pricer_fixed_randoms (pricers/logsv_pricer.py:1100-1162) keeps W0s/W1s

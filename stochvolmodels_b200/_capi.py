@@ -59,12 +59,17 @@ SIGNATURES = {
     "b200sv_mc_payoffs": [_dp, _dp, c_longlong, c_double, c_double, _dp, _i8p, c_int, c_double, c_int, _dp, _dp],
     "b200sv_device_normals": [c_uint64, c_longlong, c_longlong, c_int, c_int, c_int, _dp, _dp],
     "b200sv_dev_logsv_slice": [c_void_p, c_void_p, c_void_p, c_longlong, c_longlong, c_int, _lp, c_double, c_int, c_int, c_double,
-                               c_int, c_double, c_uint64, c_int, c_void_p, c_void_p],
+                               c_int, c_double, c_uint64, c_int, c_void_p, c_void_p, c_void_p],
     "b200sv_dev_heston_slice": [c_void_p, c_void_p, c_void_p, c_longlong, c_longlong, c_int, _hp, c_int, c_double, c_int, c_double,
-                                c_uint64, c_int, c_int, c_void_p, c_void_p],
+                                c_uint64, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "b200sv_dev_payoff_sums": [c_void_p, c_void_p, c_longlong, c_int, c_double, c_double, c_void_p, c_void_p, c_int, c_int, c_int,
-                               c_void_p, c_void_p, c_void_p],
-    "b200sv_dev_payoff_finalize": [c_void_p, c_int, c_double, c_longlong, c_void_p, c_void_p, c_void_p],
+                               c_void_p, c_void_p, c_void_p, c_void_p],
+    "b200sv_dev_payoff_finalize": [c_void_p, c_int, c_double, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p],
+    "b200sv_p2p_create": [c_int, c_int, c_int, POINTER(c_void_p), POINTER(ctypes.c_ubyte)],
+    "b200sv_p2p_connect": [c_void_p, POINTER(ctypes.c_ubyte)],
+    "b200sv_p2p_destroy": [c_void_p],
+    "b200sv_dev_p2p_publish": [c_void_p, c_void_p, c_int, c_void_p],
+    "b200sv_dev_p2p_gather": [c_void_p, c_int, c_void_p, c_void_p],
     "b200sv_dev_logsv_step_fixed": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_double, _lp, c_double,
                                     c_int, c_int, c_void_p],
     "b200sv_dev_heston_step_fixed": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_double, _hp, c_void_p],

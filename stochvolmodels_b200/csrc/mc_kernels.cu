@@ -25,6 +25,7 @@
 #include "../../include/b200sv.h"
 #include "common.cuh"
 #include "fastmath64.cuh"
+#include "p2p.cuh"
 #include "philox.cuh"
 
 namespace b200sv {
@@ -341,15 +342,38 @@ __global__ void __launch_bounds__(kSliceThreads, B200SV_SLICE_MINBLOCKS) mc_slic
 }
 
 // out[k] = sum_b partials[b*K + k] for k < K_out, fixed order: one warp per k, lanes stride over b, shuffle tree.
+// With a P2P context the same kernel PUBLISHES the K_out values into every peer's mailbox (stores to NVLink-mapped peer memory)
+// and then signals the epoch -- the producer half of the exchange, fused into the reduction that produces the values (p2p.cuh).
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __restrict__ partials, int nblk, int K, int K_out,
-                                                              double* __restrict__ out) {
+                                                              double* __restrict__ out, P2pPublish pub) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   for (int k = warp; k < K_out; k += nw) {
     double s = 0.0;
     for (int b = lane; b < nblk; b += 32) s += partials[(size_t)b * K + k];
     s = warp_sum(s);
-    if (lane == 0) out[k] = s;
+    if (lane == 0) {
+      out[k] = s;
+      if (pub.world) p2p_store(pub, k, s);
+    }
   }
+  if (pub.world) {
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) p2p_signal(pub);
+  }
+}
+
+// publish K values that are already final on this rank (ranks without local paths, tests)
+__global__ void p2p_publish_kernel(const double* __restrict__ vals, int K, P2pPublish pub) {
+  for (int k = threadIdx.x; k < K; k += blockDim.x) p2p_store(pub, k, vals ? vals[k] : 0.0);
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) p2p_signal(pub);
+}
+
+// gather K values of the current epoch into out[] (tests; the product consumes them inside the payoff / finalize kernels)
+__global__ void p2p_gather_kernel(P2pGather gat, int K, double* __restrict__ out) {
+  for (int k = threadIdx.x; k < K; k += blockDim.x) out[k] = p2p_gather(gat, k);
 }
 
 // --------------------------------------------------------------------------------------------------------------------
@@ -502,8 +526,9 @@ __global__ void __launch_bounds__(kThreads) payoff_kernel(const Real* __restrict
                                                          double ttm, double forward, const double* __restrict__ strikes,
                                                          const int8_t* __restrict__ types, int J, int variable_type,
                                                          const double* __restrict__ moments, double* __restrict__ partials,
-                                                         int Kpad /* = 3 * kStrikeChunk * gridDim.y */) {
+                                                         int Kpad /* = 3 * kStrikeChunk * gridDim.y */, P2pGather gat) {
   __shared__ double red[3 * kStrikeChunk * kThreads / 32];
+  __shared__ double sh_mom[2];
   const int j0 = blockIdx.y * kStrikeChunk;
   double kk[kStrikeChunk];
   int ty[kStrikeChunk];
@@ -513,8 +538,10 @@ __global__ void __launch_bounds__(kThreads) payoff_kernel(const Real* __restrict
     kk[c] = j < J ? strikes[j] : 0.0;
     ty[c] = j < J ? (int)types[j] : -1;
   }
-  // correnction = np.nanmean(spots_t) - forward
-  const double corr = moments[0] / moments[1] - forward;
+  // correnction = np.nanmean(spots_t) - forward; multi-GPU: the GLOBAL (sum, count) is gathered from the peers' mailbox writes here
+  if (threadIdx.x < 2) sh_mom[threadIdx.x] = gat.world ? p2p_gather(gat, threadIdx.x) : moments[threadIdx.x];
+  __syncthreads();
+  const double corr = sh_mom[0] / sh_mom[1] - forward;
   const bool is_qvar = variable_type == B200SV_Q_VAR;
   double acc[3 * kStrikeChunk];
 #pragma unroll
@@ -554,8 +581,9 @@ __global__ void __launch_bounds__(kThreads) payoff_vanilla_kernel(const Real* __
                                                                  double ttm, double forward, const double* __restrict__ strikes,
                                                                  const int8_t* __restrict__ types, int J, int variable_type,
                                                                  const double* __restrict__ moments, double* __restrict__ partials,
-                                                                 int Kpad) {
+                                                                 int Kpad, P2pGather gat) {
   __shared__ double red[2 * kStrikeChunk * kThreads / 32];
+  __shared__ double sh_mom[2];
   const int j0 = blockIdx.y * kStrikeChunk;
   double sg[kStrikeChunk], nk[kStrikeChunk];      // pay = max(sg*U + nk, 0), nk = -sg*K
 #pragma unroll
@@ -565,7 +593,9 @@ __global__ void __launch_bounds__(kThreads) payoff_vanilla_kernel(const Real* __
     sg[c] = sgn;
     nk[c] = j < J ? -sgn * strikes[j] : -INFINITY;   // unused slot: max(U - inf, 0) = 0
   }
-  const double corr = moments[0] / moments[1] - forward;
+  if (threadIdx.x < 2) sh_mom[threadIdx.x] = gat.world ? p2p_gather(gat, threadIdx.x) : moments[threadIdx.x];
+  __syncthreads();
+  const double corr = sh_mom[0] / sh_mom[1] - forward;
   const bool is_qvar = variable_type == B200SV_Q_VAR;
   const double inv_ttm = 1.0 / ttm;
   double acc[2 * kStrikeChunk];
@@ -613,10 +643,12 @@ __global__ void __launch_bounds__(kThreads) payoff_vanilla_kernel(const Real* __
 }
 
 __global__ void payoff_finalize_kernel(const double* __restrict__ sums, int J, double discfactor, double total_paths,
-                                       double* __restrict__ prices, double* __restrict__ stderrs) {
+                                       double* __restrict__ prices, double* __restrict__ stderrs, P2pGather gat) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= J) return;
-  const double s1 = sums[3 * j], s2 = sums[3 * j + 1], cnt = sums[3 * j + 2];
+  const double s1 = gat.world ? p2p_gather(gat, 3 * j) : sums[3 * j];
+  const double s2 = gat.world ? p2p_gather(gat, 3 * j + 1) : sums[3 * j + 1];
+  const double cnt = gat.world ? p2p_gather(gat, 3 * j + 2) : sums[3 * j + 2];
   const double mean = s1 / cnt;
   double var = s2 / cnt - mean * mean;
   var = var > 0.0 ? var : 0.0;
@@ -681,6 +713,45 @@ static void ensure_pool_threshold() {
   done_for = dev;
 }
 
+// host-side state of one rank's mailbox (p2p.cuh); created / connected through the b200sv_p2p_* entry points
+struct P2pCtx {
+  int world, rank, kmax;
+  char* mail;                    // own mailbox (cudaMalloc, IPC-exported)
+  char* peer[kMaxPeers];         // every rank's mailbox mapped into this process (peer[rank] == mail)
+  size_t vals_bytes;             // 2 * world * kmax * 8; flags follow
+  unsigned long long published;  // epoch of the last exchange this rank published
+  unsigned long long consumed;   // epoch of the last exchange this rank gathered
+  double* scratch;               // 1 double (tail of the own mailbox allocation): sink of the protocol-keeping gather below
+};
+static P2pGather make_gather(P2pCtx* c);
+__global__ void p2p_gather_kernel(P2pGather g, int K, double* __restrict__ out);
+// The double-buffer argument of p2p.cuh needs "publish e+1 only after gathering e" on every rank.  A caller that skips a gather (a
+// maturity without strikes, a rank without paths) gets it inserted here: a 1-thread kernel that waits for epoch e's flags.
+static P2pPublish make_publish(P2pCtx* c, cudaStream_t st) {
+  P2pPublish p{};
+  if (!c) return p;
+  if (c->consumed < c->published) p2p_gather_kernel<<<1, 32, 0, st>>>(make_gather(c), 1, c->scratch);
+  p.world = c->world;
+  p.epoch = ++c->published;
+  const int slot = (int)(p.epoch & 1ull);
+  for (int s = 0; s < c->world; ++s) {
+    p.peer_vals[s] = (double*)c->peer[s] + ((size_t)slot * c->world + c->rank) * c->kmax;
+    p.peer_flags[s] = (unsigned long long*)(c->peer[s] + c->vals_bytes) + (size_t)slot * c->world + c->rank;
+  }
+  return p;
+}
+static P2pGather make_gather(P2pCtx* c) {
+  P2pGather g{};
+  if (!c) return g;
+  g.world = c->world;
+  g.kmax = c->kmax;
+  g.epoch = c->consumed = c->published;
+  const int slot = (int)(g.epoch & 1ull);
+  g.vals = (const double*)c->mail + (size_t)slot * c->world * c->kmax;
+  g.flags = (const unsigned long long*)(c->mail + c->vals_bytes) + (size_t)slot * c->world;
+  return g;
+}
+
 static int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(-2, std::string(what) + ": " + cudaGetErrorString(e));
@@ -697,7 +768,7 @@ static void time_grid(double ttm, int n_per_year, int* S, double* dt) {
 template <int MODEL, typename Real, bool G64>
 static int launch_slice_t(void* x, void* v, void* q, long long n, long long path_offset, int init, double v_init, int nsteps,
                           int slice_index, double forward, uint64_t seed, const LogsvConsts* lc, const HestonConsts* hc,
-                          double* moments_out, cudaStream_t st) {
+                          double* moments_out, cudaStream_t st, P2pCtx* p2p = nullptr) {
   SliceArgs<Real> a;
   a.x = (Real*)x;
   a.v = (Real*)v;
@@ -737,7 +808,7 @@ static int launch_slice_t(void* x, void* v, void* q, long long n, long long path
   else
     mc_slice_kernel<HestonPath<Real>, HestonConsts, Real, G64><<<g.blocks, g.threads, dyn_smem, st>>>(a, *hc);
   if (int rc = check_launch("mc_slice_kernel")) return rc;
-  reduce_partials_kernel<<<1, 64, 0, st>>>(partials, g.blocks, 2, 2, moments_out);
+  reduce_partials_kernel<<<1, 64, 0, st>>>(partials, g.blocks, 2, 2, moments_out, make_publish(p2p, st));   // exchange #1 (producer)
   if (int rc = check_launch("reduce_partials_kernel")) return rc;
   B200SV_CUDA(cudaFreeAsync(partials, st));
   return 0;
@@ -746,19 +817,21 @@ static int launch_slice_t(void* x, void* v, void* q, long long n, long long path
 template <int MODEL>
 static int launch_slice(void* x, void* v, void* q, long long n, long long path_offset, int init, double v_init, int nsteps,
                         int slice_index, double forward, uint64_t seed, int flags, const LogsvConsts* lc, const HestonConsts* hc,
-                        double* moments_out, cudaStream_t st) {
+                        double* moments_out, cudaStream_t st, P2pCtx* p2p = nullptr) {
   const bool f32 = flags & B200SV_STATE_F32, g64 = flags & B200SV_GAUSS_F64;
-  if (!f32 && !g64) return launch_slice_t<MODEL, double, false>(x, v, q, n, path_offset, init, v_init, nsteps, slice_index, forward, seed, lc, hc, moments_out, st);
-  if (!f32 && g64) return launch_slice_t<MODEL, double, true>(x, v, q, n, path_offset, init, v_init, nsteps, slice_index, forward, seed, lc, hc, moments_out, st);
-  if (f32 && !g64) return launch_slice_t<MODEL, float, false>(x, v, q, n, path_offset, init, v_init, nsteps, slice_index, forward, seed, lc, hc, moments_out, st);
-  return launch_slice_t<MODEL, float, true>(x, v, q, n, path_offset, init, v_init, nsteps, slice_index, forward, seed, lc, hc, moments_out, st);
+  if (!f32 && !g64) return launch_slice_t<MODEL, double, false>(x, v, q, n, path_offset, init, v_init, nsteps, slice_index, forward, seed, lc, hc, moments_out, st, p2p);
+  if (!f32 && g64) return launch_slice_t<MODEL, double, true>(x, v, q, n, path_offset, init, v_init, nsteps, slice_index, forward, seed, lc, hc, moments_out, st, p2p);
+  if (f32 && !g64) return launch_slice_t<MODEL, float, false>(x, v, q, n, path_offset, init, v_init, nsteps, slice_index, forward, seed, lc, hc, moments_out, st, p2p);
+  return launch_slice_t<MODEL, float, true>(x, v, q, n, path_offset, init, v_init, nsteps, slice_index, forward, seed, lc, hc, moments_out, st, p2p);
 }
 
 // kinds: bit 0 = some 'C'/'P', bit 1 = some 'IC'/'IP' in this slice; 0 = unknown (device-level callers) -> general kernel
 template <typename Real>
 static int launch_payoff_t(const void* x, const void* q, long long n, double ttm, double forward, const double* strikes,
                            const int8_t* types, int J, int variable_type, int kinds, const double* moments, double* sums_out,
-                           cudaStream_t st) {
+                           cudaStream_t st, P2pCtx* p2p = nullptr) {
+  if (p2p && 3 * J > p2p->kmax) return fail(-1, "P2P mailbox too small for this slice (max_values < 3*J)");
+  const P2pGather gat = make_gather(p2p);      // exchange #1 (consumer): the global re-centring moments
   const int chunks = (J + kStrikeChunk - 1) / kStrikeChunk;
   const int Kpad = 3 * kStrikeChunk * chunks;
   const bool vanilla = kinds == 1;
@@ -768,12 +841,12 @@ static int launch_payoff_t(const void* x, const void* q, long long n, double ttm
   B200SV_CUDA(cudaMallocAsync(&partials, sizeof(double) * (size_t)Kpad * g.blocks, st));
   if (vanilla)
     payoff_vanilla_kernel<Real><<<dim3(g.blocks, chunks), g.threads, 0, st>>>((const Real*)x, (const Real*)q, n, ttm, forward, strikes,
-                                                                                types, J, variable_type, moments, partials, Kpad);
+                                                                                types, J, variable_type, moments, partials, Kpad, gat);
   else
     payoff_kernel<Real><<<dim3(g.blocks, chunks), g.threads, 0, st>>>((const Real*)x, (const Real*)q, n, ttm, forward, strikes,
-                                                                        types, J, variable_type, moments, partials, Kpad);
+                                                                        types, J, variable_type, moments, partials, Kpad, gat);
   if (int rc = check_launch("payoff_kernel")) return rc;
-  reduce_partials_kernel<<<1, 256, 0, st>>>(partials, g.blocks, Kpad, 3 * J, sums_out);
+  reduce_partials_kernel<<<1, 256, 0, st>>>(partials, g.blocks, Kpad, 3 * J, sums_out, make_publish(p2p, st));   // exchange #2 (producer)
   if (int rc = check_launch("reduce_partials_kernel")) return rc;
   B200SV_CUDA(cudaFreeAsync(partials, st));
   return 0;
@@ -850,7 +923,7 @@ static int mc_chain_host(const b200sv_logsv_params* lp, const b200sv_heston_para
     else
       rc = launch_payoff_t<double>(x, q, nb_path, ttms[m], forwards[m], d_strikes + jo, d_types + jo, J, variable_type, payoff_kinds(types + offsets[m], J), d_mom, d_sums, st);
     if (rc) break;
-    payoff_finalize_kernel<<<(J + 127) / 128, 128, 0, st>>>(d_sums, J, discfactors[m], (double)nb_path, d_out + jo, d_out + Jalloc + jo);
+    payoff_finalize_kernel<<<(J + 127) / 128, 128, 0, st>>>(d_sums, J, discfactors[m], (double)nb_path, d_out + jo, d_out + Jalloc + jo, P2pGather{});
     rc = check_launch("payoff_finalize_kernel");
   }
   if (rc == 0 && Jtot > 0) {
@@ -952,41 +1025,43 @@ int b200sv_heston_terminal(const b200sv_heston_params* params, double ttm, long 
 // ---- device-level ---------------------------------------------------------------------------------------------------
 int b200sv_dev_logsv_slice(void* x, void* sigma, void* qvar, long long n_local, long long path_offset, int init,
                            const b200sv_logsv_params* params, double eta, int is_spot_measure, int nsteps, double dt,
-                           int slice_index, double forward, uint64_t seed, int flags, double* moments_out, void* stream) {
+                           int slice_index, double forward, uint64_t seed, int flags, double* moments_out, void* p2p, void* stream) {
   B200SV_REQUIRE(x && sigma && qvar && params && moments_out, "null pointer");
   B200SV_REQUIRE(n_local >= 1 && nsteps >= 1 && dt > 0.0, "n_local, nsteps, dt must be positive");
   const LogsvConsts c = make_logsv_consts(*params, eta, is_spot_measure != 0, dt);
   return launch_slice<0>(x, sigma, qvar, n_local, path_offset, init, params->sigma0, nsteps, slice_index, forward, seed, flags,
-                         &c, nullptr, moments_out, (cudaStream_t)stream);
+                         &c, nullptr, moments_out, (cudaStream_t)stream, (P2pCtx*)p2p);
 }
 
 int b200sv_dev_heston_slice(void* x, void* var, void* qvar, long long n_local, long long path_offset, int init,
                             const b200sv_heston_params* params, int nsteps, double dt, int slice_index, double forward,
-                            uint64_t seed, int flags, int scheme, double* moments_out, void* stream) {
+                            uint64_t seed, int flags, int scheme, double* moments_out, void* p2p, void* stream) {
   B200SV_REQUIRE(x && var && qvar && params && moments_out, "null pointer");
   B200SV_REQUIRE(n_local >= 1 && nsteps >= 1 && dt > 0.0, "n_local, nsteps, dt must be positive");
   B200SV_REQUIRE(scheme == B200SV_HESTON_EULER_FLOOR || scheme == B200SV_HESTON_QE, "unknown Heston scheme");
   const HestonConsts c = make_heston_consts(*params, dt, scheme);
   return launch_slice<1>(x, var, qvar, n_local, path_offset, init, params->v0, nsteps, slice_index, forward, seed, flags, nullptr,
-                         &c, moments_out, (cudaStream_t)stream);
+                         &c, moments_out, (cudaStream_t)stream, (P2pCtx*)p2p);
 }
 
 int b200sv_dev_payoff_sums(const void* x, const void* qvar, long long n_local, int flags, double ttm, double forward,
                            const double* strikes, const int8_t* types, int J, int variable_type, int payoff_kinds_hint,
-                           const double* moments, double* sums_out, void* stream) {
+                           const double* moments, double* sums_out, void* p2p, void* stream) {
   B200SV_REQUIRE(x && strikes && types && moments && sums_out, "null pointer");
   B200SV_REQUIRE(J >= 1 && n_local >= 1, "J and n_local must be >= 1");
   if (variable_type != B200SV_LOG_RETURN && variable_type != B200SV_Q_VAR) return fail(-4, "variable_type not implemented");
   B200SV_REQUIRE(variable_type == B200SV_LOG_RETURN || qvar, "qvar required for Q_VAR");
   if (flags & B200SV_STATE_F32)
-    return launch_payoff_t<float>(x, qvar ? qvar : x, n_local, ttm, forward, strikes, types, J, variable_type, payoff_kinds_hint, moments, sums_out, (cudaStream_t)stream);
-  return launch_payoff_t<double>(x, qvar ? qvar : x, n_local, ttm, forward, strikes, types, J, variable_type, payoff_kinds_hint, moments, sums_out, (cudaStream_t)stream);
+    return launch_payoff_t<float>(x, qvar ? qvar : x, n_local, ttm, forward, strikes, types, J, variable_type, payoff_kinds_hint, moments, sums_out, (cudaStream_t)stream, (P2pCtx*)p2p);
+  return launch_payoff_t<double>(x, qvar ? qvar : x, n_local, ttm, forward, strikes, types, J, variable_type, payoff_kinds_hint, moments, sums_out, (cudaStream_t)stream, (P2pCtx*)p2p);
 }
 
 int b200sv_dev_payoff_finalize(const double* sums, int J, double discfactor, long long total_paths, double* prices_out,
-                               double* stderr_out, void* stream) {
+                               double* stderr_out, void* p2p, void* stream) {
   B200SV_REQUIRE(sums && prices_out && stderr_out && J >= 1, "null pointer / J");
-  payoff_finalize_kernel<<<(J + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, J, discfactor, (double)total_paths, prices_out, stderr_out);
+  // exchange #2 (consumer): with a P2P context the global sums are gathered from the mailbox, `sums` holds this rank's local ones
+  payoff_finalize_kernel<<<(J + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, J, discfactor, (double)total_paths, prices_out, stderr_out,
+                                                                            make_gather((P2pCtx*)p2p));
   return check_launch("payoff_finalize_kernel");
 }
 
@@ -1024,7 +1099,7 @@ int b200sv_dev_spot_moments(const double* x, long long n, double forward, double
   B200SV_CUDA(cudaMallocAsync(&partials, sizeof(double) * 2 * g.blocks, st));
   spot_moments_kernel<<<g.blocks, g.threads, 0, st>>>(x, n, forward, partials);
   if (int rc = check_launch("spot_moments_kernel")) return rc;
-  reduce_partials_kernel<<<1, 64, 0, st>>>(partials, g.blocks, 2, 2, moments_out);
+  reduce_partials_kernel<<<1, 64, 0, st>>>(partials, g.blocks, 2, 2, moments_out, P2pPublish{});
   if (int rc = check_launch("reduce_partials_kernel")) return rc;
   B200SV_CUDA(cudaFreeAsync(partials, st));
   return 0;
@@ -1098,7 +1173,7 @@ int b200sv_mc_payoffs(const double* x, const double* qvar, long long N, double t
   B200SV_CUDA(cudaMemcpyAsync(dt_, types, J, cudaMemcpyHostToDevice, st));
   int rc = b200sv_dev_spot_moments(d, N, forward, d_mom, st);
   if (rc == 0) rc = launch_payoff_t<double>(d, d + N, N, ttm, forward, dk, dt_, J, variable_type, payoff_kinds(types, J), d_mom, d_sums, st);
-  if (rc == 0) rc = b200sv_dev_payoff_finalize(d_sums, J, discfactor, N, d_out, d_out + J, st);
+  if (rc == 0) rc = b200sv_dev_payoff_finalize(d_sums, J, discfactor, N, d_out, d_out + J, nullptr, st);
   if (rc == 0) {
     cudaError_t e = cudaMemcpyAsync(prices_out, d_out, sizeof(double) * J, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(stderr_out, d_out + J, sizeof(double) * J, cudaMemcpyDeviceToHost, st);
@@ -1185,6 +1260,76 @@ int b200sv_logsv_vol_paths(const b200sv_logsv_params* params, double ttm, long l
   cudaError_t e = cudaStreamSynchronize(st);
   if (rc == 0 && e != cudaSuccess) rc = fail(-2, std::string("sync: ") + cudaGetErrorString(e));
   return rc;
+}
+
+// ---- P2P mailbox (p2p.cuh) -----------------------------------------------------------------------------------------------
+int b200sv_p2p_create(int world, int rank, int max_values, void** ctx_out, unsigned char* handle_out /* 64 bytes */) {
+  B200SV_REQUIRE(ctx_out && handle_out, "null pointer");
+  B200SV_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world && max_values >= 2, "world <= 8, 0 <= rank < world, max_values >= 2");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  P2pCtx* c = new P2pCtx();
+  c->world = world;
+  c->rank = rank;
+  c->kmax = max_values;
+  c->vals_bytes = sizeof(double) * 2 * (size_t)world * max_values;
+  c->published = c->consumed = 0;
+  const size_t flags_bytes = sizeof(unsigned long long) * 2 * (size_t)world;
+  const size_t total = c->vals_bytes + flags_bytes + sizeof(double);
+  cudaError_t e = cudaMalloc((void**)&c->mail, total);
+  if (e == cudaSuccess) e = cudaMemset(c->mail, 0, total);
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, c->mail);
+  if (e != cudaSuccess) {
+    delete c;
+    return fail(-2, std::string("b200sv_p2p_create: ") + cudaGetErrorString(e));
+  }
+  for (int s = 0; s < kMaxPeers; ++s) c->peer[s] = nullptr;
+  c->peer[rank] = c->mail;
+  c->scratch = (double*)(c->mail + c->vals_bytes + flags_bytes);
+  memcpy(handle_out, &h, 64);
+  *ctx_out = c;
+  return 0;
+}
+
+int b200sv_p2p_connect(void* ctx, const unsigned char* handles /* world x 64 bytes, rank order */) {
+  B200SV_REQUIRE(ctx && handles, "null pointer");
+  P2pCtx* c = (P2pCtx*)ctx;
+  for (int s = 0; s < c->world; ++s) {
+    if (s == c->rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + 64 * (size_t)s, 64);
+    void* p = nullptr;
+    B200SV_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->peer[s] = (char*)p;
+  }
+  return 0;
+}
+
+int b200sv_p2p_destroy(void* ctx) {
+  if (!ctx) return 0;
+  P2pCtx* c = (P2pCtx*)ctx;
+  cudaDeviceSynchronize();
+  for (int s = 0; s < c->world; ++s)
+    if (s != c->rank && c->peer[s]) cudaIpcCloseMemHandle(c->peer[s]);
+  cudaFree(c->mail);
+  delete c;
+  return 0;
+}
+
+int b200sv_dev_p2p_publish(void* ctx, const double* vals, int K, void* stream) {
+  B200SV_REQUIRE(ctx && K >= 1, "null pointer / K");
+  P2pCtx* c = (P2pCtx*)ctx;
+  B200SV_REQUIRE(K <= c->kmax, "K exceeds the mailbox size");
+  p2p_publish_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(vals, K, make_publish(c, (cudaStream_t)stream));
+  return check_launch("p2p_publish_kernel");
+}
+
+int b200sv_dev_p2p_gather(void* ctx, int K, double* out, void* stream) {
+  B200SV_REQUIRE(ctx && out && K >= 1, "null pointer / K");
+  P2pCtx* c = (P2pCtx*)ctx;
+  B200SV_REQUIRE(K <= c->kmax, "K exceeds the mailbox size");
+  p2p_gather_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(make_gather(c), K, out);
+  return check_launch("p2p_gather_kernel");
 }
 
 }  // extern "C"

@@ -4,6 +4,10 @@ The path shards naturally: state never leaves its GPU; per matu
 both tiny all-reduces of fp64 moments:
     (1) [sum F*exp(x), count]               -> forward re-centring  (utils/mc_payoffs.py:61-63)
     (2) [sum pay, sum pay^2, count] x J     -> prices / standard errors (:85-88)
+Default exchange on GPUs (``exchange="p2p"``): the two messages travel through NVLink peer memory INSIDE the kernels that produce and
+consume them (csrc/p2p.cuh: mailbox stores from the partial-reduction kernel, acquire-spin + rank-ordered sum in the payoff / finalize
+kernel prologues) -- no collective launch, no host synchronisation.  ``exchange="collective"`` uses ``torch.distributed.all_reduce``
+(NCCL; gloo in the CPU tests).
 torch is plumbing only: device memory (``torch.empty``), the current CUDA stream, and ``torch.distributed`` (NCCL over
 NVLink on GPUs, gloo in the CPU tests).  All arithmetic is in libb200sv kernels, called through the device-level C ABI
 (``b200sv_dev_*``) with raw pointers.  Because the Philox counter is the global path id, prices do not depend on the number of
@@ -28,6 +32,49 @@ def shard_paths(nb_path: int, world_size: int, rank: int) -> Tuple[int, int]:
     return n_local, offset
 
 
+# (group id, device index) -> (ctx, capacity): mailboxes are created once per process group and reused by every chain call, so that the
+# per-call cost of the P2P exchange is zero host work (cudaMalloc + IPC mapping happen on first use only)
+_P2P_CACHE = {}
+_P2P_MIN_VALUES = 3 * 512
+
+
+def p2p_context(torch, device, group=None, min_values: int = 0):
+    """this rank's libb200sv mailbox context for ``group`` (created, IPC-exchanged and mapped on first use; COLLECTIVE on first use and
+    whenever ``min_values`` outgrows the cached capacity -- every rank of the group must call it with the same arguments)."""
+    import ctypes
+    import torch.distributed as dist
+    key = (id(group) if group is not None else 0, torch.device(device).index)
+    hit = _P2P_CACHE.get(key)
+    if hit is not None and hit[1] >= min_values:
+        return hit[0]
+    if hit is not None:
+        torch.cuda.synchronize(device)
+        dist.barrier(group)               # nobody is still spinning on the mailbox that is about to go
+        C.call("b200sv_p2p_destroy", hit[0])
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    cap = max(int(min_values), _P2P_MIN_VALUES)
+    ctx = c_void_p()
+    handle = (ctypes.c_ubyte * 64)()
+    with torch.cuda.device(device):
+        C.call("b200sv_p2p_create", world, rank, cap, ctypes.byref(ctx), handle)
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        blob = (ctypes.c_ubyte * (64 * world)).from_buffer_copy(b"".join(handles))
+        C.call("b200sv_p2p_connect", ctx, blob)
+    dist.barrier(group)                   # nobody publishes before every mailbox is mapped everywhere
+    _P2P_CACHE[key] = (ctx, cap)
+    return ctx
+
+
+def release_p2p():
+    """unmap and free every cached mailbox (call on all ranks before destroy_process_group; optional -- process exit frees them)."""
+    import torch
+    for ctx, _ in _P2P_CACHE.values():
+        torch.cuda.synchronize()
+        C.call("b200sv_p2p_destroy", ctx)
+    _P2P_CACHE.clear()
+
+
 class CudaMcEngine:
     """Device-resident MC state + kernel launches on the current CUDA device (used for N>=1 ranks and by bench.py)."""
 
@@ -48,6 +95,11 @@ class CudaMcEngine:
         self.sums = torch.zeros(3 * max(max_strikes, 1), dtype=torch.float64, device=self.device)
         self.out = torch.zeros(2 * max(max_strikes, 1), dtype=torch.float64, device=self.device)
         self.cap = max(max_strikes, 1)
+        self.p2p = None          # libb200sv P2P mailbox context (void*), see enable_p2p
+
+    def enable_p2p(self, group=None):
+        """attach this rank's (cached) peer-memory mailbox for ``group``; collective call."""
+        self.p2p = p2p_context(self.torch, self.device, group, 3 * self.cap)
 
     def _stream(self):
         return c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
@@ -60,15 +112,17 @@ class CudaMcEngine:
         x, v, q = (c_void_p(self.state[i].data_ptr()) for i in range(3))
         if self.n_local == 0:
             self.moments.zero_()
+            if self.p2p is not None:      # a rank without paths still takes part in the exchange
+                C.call("b200sv_dev_p2p_publish", self.p2p, c_void_p(self.moments.data_ptr()), 2, self._stream())
             return self.moments
         if self.model == "logsv":
             C.call("b200sv_dev_logsv_slice", x, v, q, self.n_local, self.path_offset, int(init), byref(self.params_c), float(eta),
                    int(bool(is_spot)), int(nsteps), float(dt), int(m), float(forward), int(seed) & 0xFFFFFFFFFFFFFFFF, self.flags,
-                   c_void_p(self.moments.data_ptr()), self._stream())
+                   c_void_p(self.moments.data_ptr()), self.p2p, self._stream())
         else:
             C.call("b200sv_dev_heston_slice", x, v, q, self.n_local, self.path_offset, int(init), byref(self.params_c), int(nsteps),
                    float(dt), int(m), float(forward), int(seed) & 0xFFFFFFFFFFFFFFFF, self.flags, self.scheme,
-                   c_void_p(self.moments.data_ptr()), self._stream())
+                   c_void_p(self.moments.data_ptr()), self.p2p, self._stream())
         return self.moments
 
     def payoff_sums(self, ttm: float, forward: float, strikes_dev, types_dev, J: int, variable_type: int, kinds: int = 0):
@@ -76,23 +130,26 @@ class CudaMcEngine:
         sums = self.sums[: 3 * J]
         if self.n_local == 0:
             sums.zero_()
+            if self.p2p is not None:
+                C.call("b200sv_dev_p2p_publish", self.p2p, c_void_p(sums.data_ptr()), 3 * J, self._stream())
             return sums
         C.call("b200sv_dev_payoff_sums", c_void_p(self.state[0].data_ptr()), c_void_p(self.state[2].data_ptr()), self.n_local,
                self.flags, float(ttm), float(forward), c_void_p(strikes_dev.data_ptr()), c_void_p(types_dev.data_ptr()), int(J),
-               int(variable_type), int(kinds), c_void_p(self.moments.data_ptr()), c_void_p(sums.data_ptr()), self._stream())
+               int(variable_type), int(kinds), c_void_p(self.moments.data_ptr()), c_void_p(sums.data_ptr()), self.p2p, self._stream())
         return sums
 
     def finalize(self, sums, J: int, discfactor: float, total_paths: int):
         """GLOBAL sums -> (prices, std errors) device views of J doubles each."""
         prices, stds = self.out[:J], self.out[self.cap: self.cap + J]
         C.call("b200sv_dev_payoff_finalize", c_void_p(sums.data_ptr()), int(J), float(discfactor), int(total_paths),
-               c_void_p(prices.data_ptr()), c_void_p(stds.data_ptr()), self._stream())
+               c_void_p(prices.data_ptr()), c_void_p(stds.data_ptr()), self.p2p, self._stream())
         return prices, stds
 
 
 def mc_chain_distributed(model: str, params_c, ttms, forwards, discfactors, etas, strikes_ttms, optiontypes_ttms, nb_path: int,
                          nb_steps_per_year: int, is_spot_measure: bool, variable_type: int, seed: int, flags: int,
-                         group=None, engine_factory: Optional[Callable] = None, return_engine: bool = False, scheme: int = 0):
+                         group=None, engine_factory: Optional[Callable] = None, return_engine: bool = False, scheme: int = 0,
+                         exchange: Optional[str] = None):
     """Chain MC with ``nb_path`` TOTAL paths split over the ranks of ``group`` (default: the world; works unsharded when
     torch.distributed is not initialised).  Every rank returns the same (prices, std errors) lists.
 
@@ -112,6 +169,14 @@ def mc_chain_distributed(model: str, params_c, ttms, forwards, discfactors, etas
     Jmax = int(sizes.max()) if M else 0
     factory = engine_factory or CudaMcEngine
     eng = factory(model, params_c, n_local, offset, flags, Jmax, scheme=scheme) if scheme else factory(model, params_c, n_local, offset, flags, Jmax)
+    # exchange mode: P2P mailbox on CUDA engines of a multi-rank group unless the caller asks for the collective
+    if exchange is None:
+        exchange = "p2p" if (world > 1 and hasattr(eng, "enable_p2p") and world <= 8) else "collective"
+    if exchange not in ("p2p", "collective"):
+        raise ValueError("exchange must be 'p2p' or 'collective'")
+    use_p2p = exchange == "p2p" and world > 1
+    if use_p2p:
+        eng.enable_p2p(group)
     strikes_dev = eng.to_device(strikes, torch.float64)
     types_dev = eng.to_device(types, torch.int8)
     etas = np.ones(M) if etas is None else np.asarray(etas, dtype=np.float64)
@@ -121,7 +186,7 @@ def mc_chain_distributed(model: str, params_c, ttms, forwards, discfactors, etas
         nsteps, dt, _ = set_time_grid(ttms[m] - t0, nb_steps_per_year)
         t0 = ttms[m]
         moments = eng.simulate_slice(m, m == 0, nsteps, dt, float(etas[m]), is_spot_measure, float(forwards[m]), seed)
-        if world > 1:
+        if world > 1 and not use_p2p:
             dist.all_reduce(moments, op=dist.ReduceOp.SUM, group=group)              # exchange (1): 16 bytes
         J = int(sizes[m])
         if J == 0:
@@ -130,7 +195,7 @@ def mc_chain_distributed(model: str, params_c, ttms, forwards, discfactors, etas
         jo = int(offsets[m])
         kinds = int(np.bitwise_or.reduce(np.where(types[jo: jo + J] >= 2, 2, 1)))
         sums = eng.payoff_sums(float(ttms[m]), float(forwards[m]), strikes_dev[jo: jo + J], types_dev[jo: jo + J], J, variable_type, kinds)
-        if world > 1:
+        if world > 1 and not use_p2p:
             dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)                 # exchange (2): 24*J bytes
         prices, stds = eng.finalize(sums, J, float(discfactors[m]), int(nb_path))
         results.append((prices.clone(), stds.clone()))

@@ -65,7 +65,8 @@ class HestonPricer(ModelPricer):
                                       nb_path=nb_path, variable_type=variable_type,
                                       nb_steps_per_year=kwargs.get("nb_steps_per_year", 360), seed=kwargs.get("seed"),
                                       precision=kwargs.get("precision", "fp64"), gauss=kwargs.get("gauss", "fp32"),
-                                      distributed=kwargs.get("distributed", True), scheme=kwargs.get("scheme", "euler_floor"))
+                                      distributed=kwargs.get("distributed", True), scheme=kwargs.get("scheme", "euler_floor"),
+                                      exchange=kwargs.get("exchange"))
 
     @timer
     def simulate_terminal_values(self, params: HestonParams, ttm: float = 1.0, nb_path: int = 100000, x0: float = 0.0, **kwargs
@@ -98,7 +99,7 @@ def heston_chain_pricer(v0: float, theta: float, kappa: float, volvol: float, rh
 def heston_mc_chain_pricer(ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms, v0: float, theta: float, kappa: float,
                            rho: float, volvol: float, nb_path: int = 100000, variable_type: VariableType = VariableType.LOG_RETURN,
                            nb_steps_per_year: int = 360, seed: Optional[int] = None, precision: str = "fp64", gauss: str = "fp32",
-                           distributed: bool = True, scheme="euler_floor") -> Tuple[List[np.ndarray], List[np.ndarray]]:
+                           distributed: bool = True, scheme="euler_floor", exchange: Optional[str] = None) -> Tuple[List[np.ndarray], List[np.ndarray]]:
     """chain MC under Heston (reference :285-331)."""
     from .logsv_pricer import _use_distributed
     params_c = _params_c(v0, theta, kappa, rho, volvol)
@@ -108,7 +109,7 @@ def heston_mc_chain_pricer(ttms, forwards, discfactors, strikes_ttms, optiontype
         from ..multi_gpu import mc_chain_distributed
         C.encode_types(np.concatenate([np.asarray(t) for t in optiontypes_ttms]))
         return mc_chain_distributed("heston", params_c, ttms, forwards, discfactors, None, strikes_ttms, optiontypes_ttms, nb_path,
-                                    nb_steps_per_year, True, engine.variable_code(variable_type), seed, flags, scheme=_scheme_code(scheme))
+                                    nb_steps_per_year, True, engine.variable_code(variable_type), seed, flags, scheme=_scheme_code(scheme), exchange=exchange)
     return engine.heston_mc_chain(params_c, ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms, nb_path, nb_steps_per_year,
                                   variable_type, seed, flags, _scheme_code(scheme))
 

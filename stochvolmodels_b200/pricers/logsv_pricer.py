@@ -124,7 +124,8 @@ class LogSVPricer(ModelPricer):
                                      is_spot_measure=is_spot_measure, variable_type=variable_type, nb_path=nb_path,
                                      nb_steps_per_year=nb_steps or int(360 * np.max(option_chain.ttms)) + 1,
                                      seed=kwargs.get("seed"), precision=kwargs.get("precision", "fp64"),
-                                     gauss=kwargs.get("gauss", "fp32"), distributed=kwargs.get("distributed", True))
+                                     gauss=kwargs.get("gauss", "fp32"), distributed=kwargs.get("distributed", True),
+                                     exchange=kwargs.get("exchange"))
 
     @timer
     def simulate_vol_paths(self, params: LogSvParams, brownians: np.ndarray = None, ttm: float = 1.0, nb_path: int = 100000,
@@ -212,8 +213,8 @@ def logsv_mc_chain_pricer(ttms: np.ndarray, forwards: np.ndarray, discfactors: n
                           v0: float, theta: float, kappa1: float, kappa2: float, beta: float, volvol: float,
                           vol_backbone_etas: np.ndarray, is_spot_measure: bool = True, nb_path: int = 100000,
                           nb_steps_per_year: int = 360, variable_type: VariableType = VariableType.LOG_RETURN,
-                          seed: Optional[int] = None, precision: str = "fp64", gauss: str = "fp32", distributed: bool = True
-                          ) -> Tuple[List[np.ndarray], List[np.ndarray]]:
+                          seed: Optional[int] = None, precision: str = "fp64", gauss: str = "fp32", distributed: bool = True,
+                          exchange: Optional[str] = None) -> Tuple[List[np.ndarray], List[np.ndarray]]:
     """chain MC (reference :806-867): every maturity is simulated from the terminal state of the previous one by the fused
     stepper, followed by forward-recentred payoff moments.  Under an initialised torch.distributed world ``nb_path`` is the
     TOTAL path count, sharded over the ranks (two fp64 all-reduces per maturity)."""
@@ -225,7 +226,7 @@ def logsv_mc_chain_pricer(ttms: np.ndarray, forwards: np.ndarray, discfactors: n
         C.encode_types(np.concatenate([np.asarray(t) for t in optiontypes_ttms]))
         return mc_chain_distributed("logsv", params_c, ttms, forwards, discfactors, vol_backbone_etas, strikes_ttms,
                                     optiontypes_ttms, nb_path, nb_steps_per_year, is_spot_measure,
-                                    engine.variable_code(variable_type), seed, flags)
+                                    engine.variable_code(variable_type), seed, flags, exchange=exchange)
     return engine.logsv_mc_chain(params_c, ttms, forwards, discfactors, vol_backbone_etas, strikes_ttms, optiontypes_ttms, nb_path,
                                  nb_steps_per_year, is_spot_measure, variable_type, seed, flags)
 
@@ -337,8 +338,8 @@ def _fixed_randoms_chain_device(rnd: DeviceRandoms, ttms, forwards, discfactors,
             C.call("b200sv_dev_spot_moments", ptr(state[0]), n, float(forwards[m]), ptr(mom), stream)
             kinds = int(np.bitwise_or.reduce(np.where(types[jo: jo + J] >= 2, 2, 1)))
             C.call("b200sv_dev_payoff_sums", ptr(state[0]), ptr(state[2]), n, 0, float(ttm), float(forwards[m]), ptr(strikes_dev[jo:]),
-                   ptr(types_dev[jo:]), J, vt, kinds, ptr(mom), ptr(sums[3 * jo:]), stream)
-            C.call("b200sv_dev_payoff_finalize", ptr(sums[3 * jo:]), J, float(discfactors[m]), n, ptr(out[0, jo:]), ptr(out[1, jo:]), stream)
+                   ptr(types_dev[jo:]), J, vt, kinds, ptr(mom), ptr(sums[3 * jo:]), None, stream)
+            C.call("b200sv_dev_payoff_finalize", ptr(sums[3 * jo:]), J, float(discfactors[m]), n, ptr(out[0, jo:]), ptr(out[1, jo:]), None, stream)
         host = out.cpu().numpy()
     return C.split_chain(host[0], offsets), C.split_chain(host[1], offsets)
 

@@ -253,7 +253,7 @@ def test_path_offset_makes_shards_consistent(cuda_lib):
         st = torch.empty((3, n), dtype=torch.float64, device="cuda")
         mom = torch.zeros(2, dtype=torch.float64, device="cuda")
         C.call("b200sv_dev_logsv_slice", c_void_p(st[0].data_ptr()), c_void_p(st[1].data_ptr()), c_void_p(st[2].data_ptr()), n, off, 1,
-               byref(pc), 1.0, 1, 64, 0.25 / 64, 0, 1.0, 10, 0, c_void_p(mom.data_ptr()), c_void_p(torch.cuda.current_stream().cuda_stream))
+               byref(pc), 1.0, 1, 64, 0.25 / 64, 0, 1.0, 10, 0, c_void_p(mom.data_ptr()), None, c_void_p(torch.cuda.current_stream().cuda_stream))
         torch.cuda.synchronize()
         return st.cpu().numpy(), mom.cpu().numpy()
     full, mfull = run(N, 0)

@@ -15,13 +15,46 @@ chain = get_btc_test_chain_data()
 N = 4_000_001
 ok = True
 for name, pricer, params, kw in (("logsv", LogSVPricer(), LOGSV_BTC_PARAMS, dict(nb_steps=252)), ("heston", HestonPricer(), HestonParams(v0=0.8, theta=1.0, kappa=2.0, rho=0.0, volvol=2.0), {})):
-    p_d, e_d = pricer.model_mc_price_chain(chain, params, nb_path=N, seed=123, **kw)                       # sharded over `world` GPUs
+    p_d, e_d = pricer.model_mc_price_chain(chain, params, nb_path=N, seed=123, **kw)                       # sharded, peer-memory exchange
+    p_c, e_c = pricer.model_mc_price_chain(chain, params, nb_path=N, seed=123, exchange="collective", **kw)  # sharded, NCCL all-reduce
+    same = all(np.array_equal(a, b) for a, b in zip(p_d, p_c)) and all(np.array_equal(a, b) for a, b in zip(e_d, e_c))
+    if rank == 0:
+        print(f"{name}: p2p exchange == NCCL exchange bitwise: {same}", flush=True)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, np.concatenate(p_d).tobytes())
+    ok &= all(g == gathered[0] for g in gathered)            # every rank holds the same bits
     p_s, e_s = pricer.model_mc_price_chain(chain, params, nb_path=N, seed=123, distributed=False, **kw)    # this rank alone
     rel_p = max(np.max(np.abs(a / b - 1)) for a, b in zip(p_d, p_s))
     rel_e = max(np.max(np.abs(a / b - 1)) for a, b in zip(e_d, e_s))
     if rank == 0:
         print(f"{name}: world={world} N={N} max rel diff prices {rel_p:.2e} stderr {rel_e:.2e}", flush=True)
     ok &= rel_p < 1e-12 and rel_e < 1e-10
+
+# ragged corner cases through the peer-memory exchange: a maturity without strikes, fewer paths than ranks (ranks without paths),
+# IC/IP payoffs (general payoff kernel), and many repeated calls (epoch wrap of the double-buffered mailbox)
+from stochvolmodels_b200.pricers.logsv_pricer import logsv_mc_chain_pricer
+P = LOGSV_BTC_PARAMS
+rag = dict(ttms=np.array([0.1, 0.2, 0.4]), forwards=np.array([1.0, 1.0, 1.0]), discfactors=np.array([1.0, 0.99, 0.98]),
+           strikes_ttms=[np.array([0.9, 1.0, 1.1]), np.zeros(0), np.array([0.8, 1.2])],
+           optiontypes_ttms=[np.array(["C", "IP", "P"]), np.array([], dtype="<U2"), np.array(["IC", "C"])],
+           v0=P.sigma0, theta=P.theta, kappa1=P.kappa1, kappa2=P.kappa2, beta=P.beta, volvol=P.volvol, vol_backbone_etas=np.ones(3),
+           nb_steps_per_year=100)
+for n in (world - 1, 3 * world + 1, 200_003):
+    if n < 1:
+        continue
+    for rep in range(3):
+        a, ea = logsv_mc_chain_pricer(nb_path=n, seed=7 + rep, **rag)
+        b, eb = logsv_mc_chain_pricer(nb_path=n, seed=7 + rep, distributed=False, **rag)
+        d = max(np.max(np.abs(x - y)) for x, y in zip(a, b) if x.size)
+        good = d < 1e-12 and all(np.all(np.isfinite(x)) for x in a)
+        ok &= good
+        if rank == 0 and (rep == 0 or not good):
+            print(f"ragged chain N={n}: max abs diff vs single GPU {d:.2e} finite={good}", flush=True)
+flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+ok = bool(flag.item() > 0.5)
+from stochvolmodels_b200.multi_gpu import release_p2p
 dist.barrier()
+release_p2p()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

@@ -16,7 +16,7 @@ mom = torch.zeros(2, dtype=torch.float64, device="cuda")
 stream = c_void_p(torch.cuda.current_stream().cuda_stream)
 def run(seed):
     C.call("b200sv_dev_logsv_slice", c_void_p(st[0].data_ptr()), c_void_p(st[1].data_ptr()), c_void_p(st[2].data_ptr()), n, 0, 1,
-           byref(pc), 1.0, 1, S, 0.25 / S, 0, 1.0, seed, flags, c_void_p(mom.data_ptr()), stream)
+           byref(pc), 1.0, 1, S, 0.25 / S, 0, 1.0, seed, flags, c_void_p(mom.data_ptr()), None, stream)
 for w in range(3):
     run(w)
 torch.cuda.synchronize()
