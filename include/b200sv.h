@@ -200,6 +200,22 @@ int b200sv_heston_price_chain(const b200sv_heston_params* params, int M, const d
                               const double* discfactors, const int* offsets, const double* strikes, const int8_t* types,
                               int variable_type, double vol_scaler, int P, double* prices_out, double* log_mgf_out);
 
+/* B parameter sets on ONE chain in one pass -- the objective of the calibration drivers and its finite-difference gradient:
+ * _LogSvCalibrationObjective.__call__ (pricers/logsv_pricer.py:234-294: compute_model_ivols_for_chain = logsv_chain_pricer +
+ * option_chain.compute_model_ivols_from_chain_data), which scipy SLSQP evaluates n+1 times per iteration, one parameter set at a time.
+ * params[B]; etas[B*M] (NULL = 1); prices_out[B*J], ivols_out[B*J] (NULL = skip the fused Black-76 inversion), J = offsets[M]-offsets[0],
+ * row b in chain order.  vol_scaler <= 0: each set gets its own default grid sigma0_b*sqrt(min(min ttm, 1/24)) (:664-666).
+ * LOG_RETURN only.  Row b equals b200sv_logsv_price_chain(params[b]) (+ b200sv_bsm_implied_vols) bit for bit. */
+int b200sv_logsv_price_chain_batch(const b200sv_logsv_params* params, int B, int M, const double* ttms, const double* forwards,
+                                   const double* discfactors, const double* etas, const int* offsets, const double* strikes,
+                                   const int8_t* types, int is_spot_measure, int expansion_order, double vol_scaler, int P,
+                                   double* prices_out, double* ivols_out);
+
+/* same for Heston: the objective of HestonPricer.calibrate_model_params_to_chain (pricers/heston_pricer.py:111-180). */
+int b200sv_heston_price_chain_batch(const b200sv_heston_params* params, int B, int M, const double* ttms, const double* forwards,
+                                    const double* discfactors, const int* offsets, const double* strikes, const int8_t* types,
+                                    double vol_scaler, int P, double* prices_out, double* ivols_out);
+
 /* replaces compute_logsv_a_mgf_grid, non-analytic branch (pricers/logsv/affine_expansion.py:570-685 -> solve_a_ode_grid
  * :492-529): phi, psi, a (in: A(0), out: A(dtau)), log_mgf_out are complex128 interleaved host arrays of P, P, P*n, P. */
 int b200sv_logsv_mgf_grid(const double* phi, const double* psi, int P, double dtau, double* a_inout,

@@ -77,6 +77,8 @@ SIGNATURES = {
     "b200sv_debug_exp_pair": [_dp, c_longlong, _dp],
     "b200sv_logsv_price_chain": [_lp, c_int, _dp, _dp, _dp, _dp, _ip, _dp, _i8p, c_int, c_int, c_int, c_double, c_int, _dp, _dp, _dp],
     "b200sv_heston_price_chain": [_hp, c_int, _dp, _dp, _dp, _ip, _dp, _i8p, c_int, c_double, c_int, _dp, _dp],
+    "b200sv_logsv_price_chain_batch": [_lp, c_int, c_int, _dp, _dp, _dp, _dp, _ip, _dp, _i8p, c_int, c_int, c_double, c_int, _dp, _dp],
+    "b200sv_heston_price_chain_batch": [_hp, c_int, c_int, _dp, _dp, _dp, _ip, _dp, _i8p, c_double, c_int, _dp, _dp],
     "b200sv_fourier_qvar": [_dp, _dp, c_int, c_double, _dp, _i8p, c_int, c_double, _dp],
     "b200sv_fourier_pdf": [_dp, _dp, c_int, _dp, c_int, _dp],
     "b200sv_fourier_digital": [_dp, _dp, c_int, c_double, _dp, _i8p, c_int, c_double, _dp],

@@ -11,6 +11,7 @@
 
 #include "../../include/b200sv.h"
 #include "common.cuh"
+#include "black.cuh"
 
 extern "C" void b200sv_internal_count_launch(void);
 
@@ -21,29 +22,11 @@ struct QuoteSpec {
   int type;
 };
 
-__device__ __forceinline__ double black_call(double F, double K, double sdev) {
-  const double d1 = log(F / K) / sdev + 0.5 * sdev;
-  return F * normcdf(d1) - K * normcdf(d1 - sdev);
-}
-
 __global__ void black_ivol_kernel(const QuoteSpec* __restrict__ q, int n, double* __restrict__ ivols) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const QuoteSpec s = q[i];
-  const double p = s.price / s.discfactor;
-  const bool is_call = (s.type == B200SV_CALL || s.type == B200SV_INV_CALL);
-  const double c = is_call ? p : p + (s.forward - s.strike);            // put-call parity: work on the call
-  const double intrinsic = fmax(s.forward - s.strike, 0.0);
-  const bool ok = (c > intrinsic) && (c < s.forward) && isfinite(c);
-  const double srt = sqrt(s.ttm);
-  double a = 1e-8, b = 10.0;
-  for (int it = 0; it < 80; ++it) {
-    const double mid = 0.5 * (a + b);
-    const bool up = black_call(s.forward, s.strike, mid * srt) < c;
-    a = up ? mid : a;
-    b = up ? b : mid;
-  }
-  ivols[i] = ok ? 0.5 * (a + b) : NAN;
+  ivols[i] = black_implied_vol(s.forward, s.strike, s.ttm, s.discfactor, s.price, s.type);
 }
 
 }  // namespace b200sv

@@ -21,6 +21,7 @@
 
 #include "../../include/b200sv.h"
 #include "common.cuh"
+#include "black.cuh"
 
 extern "C" void b200sv_internal_count_launch(void);
 
@@ -310,14 +311,26 @@ struct ChainSpec {   // per-maturity scalars (device array of M entries)
 };
 
 // one thread = one grid point through all M maturities.  a_io: [P][N] in (A(0)) ; a_out: [M][P][N]; log_mgf: [M][P]
+// blockIdx.y = parameter set of a batch (b200sv_logsv_price_chain_batch): spec[b][M], yb[b], phi[b][P] (phi_stride = P) or one shared
+// grid (phi_stride = 0), outputs [b][M][P]...
 template <int N, int TPB>
 __global__ void __launch_bounds__(TPB) logsv_mgf_kernel(const cd* __restrict__ phi, const cd* __restrict__ psi, int P, int M,
                                  const ChainSpec* __restrict__ spec, const cd* __restrict__ a_in, cd* __restrict__ a_out,
-                                 cd* __restrict__ log_mgf, double y, int* __restrict__ status, int* __restrict__ nfev) {
+                                 cd* __restrict__ log_mgf, double y, int* __restrict__ status, int* __restrict__ nfev,
+                                 const double* __restrict__ yb = nullptr, int phi_stride = 0) {
   __shared__ cd stage_smem[6 * N * TPB];
   __shared__ cd coef_smem[14 * TPB];
   const int p = blockIdx.x * TPB + threadIdx.x;
   if (p >= P) return;
+  if (gridDim.y > 1 || yb) {
+    const size_t b = blockIdx.y;
+    spec += b * M;
+    phi += b * (size_t)phi_stride;
+    a_out += b * (size_t)M * P * N;
+    log_mgf += b * (size_t)M * P;
+    if (status) status += b * (size_t)P;
+    if (yb) y = yb[b];
+  }
   StageStore<N, TPB> K{stage_smem + threadIdx.x};
 #pragma unroll
   for (int i = 0; i < 6 * N; ++i) stage_smem[threadIdx.x + i * TPB] = mk(0.0);      // stages read with coefficient 0 must be finite
@@ -354,9 +367,15 @@ __global__ void __launch_bounds__(TPB) logsv_mgf_kernel(const cd* __restrict__ p
 __global__ void heston_mgf_kernel(const cd* __restrict__ phi, const cd* __restrict__ psi, int P, int M,
                                   const double* __restrict__ dtaus, b200sv_heston_params hp, const cd* __restrict__ a_in,
                                   const cd* __restrict__ b_in, cd* __restrict__ a_out, cd* __restrict__ b_out,
-                                  cd* __restrict__ log_mgf) {
+                                  cd* __restrict__ log_mgf, const b200sv_heston_params* __restrict__ hpb = nullptr, int phi_stride = 0) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
+  if (hpb) {                                       // batch of parameter sets (b200sv_heston_price_chain_batch): blockIdx.y = set
+    const size_t b = blockIdx.y;
+    hp = hpb[b];
+    phi += b * (size_t)phi_stride;
+    log_mgf += b * (size_t)M * P;
+  }
   const cd ph = phi[p], ps = psi ? psi[p] : mk(0.0);
   cd a = a_in ? a_in[p] : mk(0.0), b = b_in ? b_in[p] : mk(0.0);
   const double vv2 = hp.volvol * hp.volvol;
@@ -387,16 +406,20 @@ struct StrikeSpec {
   double strike, forward, discfactor;
   int type;     // B200SV_CALL ..
   int slice;    // which log_mgf row
+  double ttm;   // only for the fused Black inversion of the batched pricers
+  int grid;     // which phi row (batched pricers with per-set grids), else 0
 };
 
 constexpr int kFourierThreads = 256;
 
 __global__ void __launch_bounds__(kFourierThreads) fourier_vanilla_kernel(const cd* __restrict__ log_mgf, const cd* __restrict__ phi,
                                                                          int P, const StrikeSpec* __restrict__ specs,
-                                                                         int is_spot, int half_re, double* __restrict__ prices) {
+                                                                         int is_spot, int half_re, double* __restrict__ prices,
+                                                                         double* __restrict__ ivols = nullptr) {
   __shared__ double red[kFourierThreads / 32];
   const StrikeSpec sp = specs[blockIdx.x];
   const cd* lm = log_mgf + (size_t)sp.slice * P;
+  phi += (size_t)sp.grid * P;
   const double x = log(sp.forward / sp.strike);
   const double h3 = (phi[1].im - phi[0].im) / 3.0;
   double acc[1] = {0.0};
@@ -425,6 +448,8 @@ __global__ void __launch_bounds__(kFourierThreads) fourier_vanilla_kernel(const 
     else
       price = (sp.type == B200SV_CALL || sp.type == B200SV_INV_CALL) ? F * df * (1.0 - capped) : F * df * (exp(-x) - capped);
     prices[blockIdx.x] = price;
+    // calibration objective: the Black inversion that follows every chain pricing (option_chain.py:327-346), fused
+    if (ivols) ivols[blockIdx.x] = black_implied_vol(F, K, sp.ttm, df, price, sp.type);
   }
 }
 
@@ -487,13 +512,15 @@ static int launched(const char* what) {
 
 template <int N>
 static void launch_logsv_mgf(int tpb, int nb, cudaStream_t st, const cd* phi, const cd* psi, int P, int M, const ChainSpec* spec,
-                             const cd* a_in, cd* a_out, cd* lm, double y, int* status) {
+                             const cd* a_in, cd* a_out, cd* lm, double y, int* status, int B = 1, const double* yb = nullptr,
+                             int phi_stride = 0) {
+  const dim3 grid(nb, B);
   switch (tpb) {
-    case 4: logsv_mgf_kernel<N, 4><<<nb, 4, 0, st>>>(phi, psi, P, M, spec, a_in, a_out, lm, y, status, nullptr); break;
-    case 8: logsv_mgf_kernel<N, 8><<<nb, 8, 0, st>>>(phi, psi, P, M, spec, a_in, a_out, lm, y, status, nullptr); break;
-    case 16: logsv_mgf_kernel<N, 16><<<nb, 16, 0, st>>>(phi, psi, P, M, spec, a_in, a_out, lm, y, status, nullptr); break;
-    case 32: logsv_mgf_kernel<N, 32><<<nb, 32, 0, st>>>(phi, psi, P, M, spec, a_in, a_out, lm, y, status, nullptr); break;
-    default: logsv_mgf_kernel<N, 64><<<nb, 64, 0, st>>>(phi, psi, P, M, spec, a_in, a_out, lm, y, status, nullptr); break;
+    case 4: logsv_mgf_kernel<N, 4><<<grid, 4, 0, st>>>(phi, psi, P, M, spec, a_in, a_out, lm, y, status, nullptr, yb, phi_stride); break;
+    case 8: logsv_mgf_kernel<N, 8><<<grid, 8, 0, st>>>(phi, psi, P, M, spec, a_in, a_out, lm, y, status, nullptr, yb, phi_stride); break;
+    case 16: logsv_mgf_kernel<N, 16><<<grid, 16, 0, st>>>(phi, psi, P, M, spec, a_in, a_out, lm, y, status, nullptr, yb, phi_stride); break;
+    case 32: logsv_mgf_kernel<N, 32><<<grid, 32, 0, st>>>(phi, psi, P, M, spec, a_in, a_out, lm, y, status, nullptr, yb, phi_stride); break;
+    default: logsv_mgf_kernel<N, 64><<<grid, 64, 0, st>>>(phi, psi, P, M, spec, a_in, a_out, lm, y, status, nullptr, yb, phi_stride); break;
   }
 }
 
@@ -609,7 +636,7 @@ int b200sv_logsv_price_chain(const b200sv_logsv_params* params, int M, const dou
   for (int m = 0; m < M; ++m)
     for (int j = offsets[m]; j < offsets[m + 1]; ++j) {
       B200SV_REQUIRE(strikes[j] > 0.0, "strikes must be positive");
-      ss[j - offsets[0]] = StrikeSpec{strikes[j], forwards[m], discfactors[m], (int)types[j], m};
+      ss[j - offsets[0]] = StrikeSpec{strikes[j], forwards[m], discfactors[m], (int)types[j], m, ttms[m], 0};
       qs[j - offsets[0]] = SumSpec{strikes[j] * ttms[m], discfactors[m], ttms[m], (int)types[j], m};
     }
   cudaStream_t st = 0;
@@ -681,7 +708,7 @@ int b200sv_heston_price_chain(const b200sv_heston_params* params, int M, const d
   for (int m = 0; m < M; ++m)
     for (int j = offsets[m]; j < offsets[m + 1]; ++j) {
       B200SV_REQUIRE(strikes[j] > 0.0, "strikes must be positive");
-      ss[j - offsets[0]] = StrikeSpec{strikes[j], forwards[m], discfactors[m], (int)types[j], m};
+      ss[j - offsets[0]] = StrikeSpec{strikes[j], forwards[m], discfactors[m], (int)types[j], m, ttms[m], 0};
       qs[j - offsets[0]] = SumSpec{strikes[j] * ttms[m], discfactors[m], ttms[m], (int)types[j], m};
     }
   cudaStream_t st = 0;
@@ -712,6 +739,133 @@ int b200sv_heston_price_chain(const b200sv_heston_params* params, int M, const d
     B200SV_CUDA(cudaMemcpyAsync(prices_out, d_pr.p, sizeof(double) * Jtot, cudaMemcpyDeviceToHost, st));
   }
   if (log_mgf_out) B200SV_CUDA(cudaMemcpyAsync(log_mgf_out, d_lm.p, sizeof(cd) * (size_t)M * P, cudaMemcpyDeviceToHost, st));
+  B200SV_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+/* ---- batched chain pricers: B parameter sets on one chain in one pass (calibration objective + its finite-difference gradient) ---- */
+static int chain_batch_common(int B, int M, const double* ttms, const double* forwards, const double* discfactors, const int* offsets,
+                              const double* strikes, const int8_t* types, bool spot, int P, std::vector<double>& dtaus,
+                              std::vector<StrikeSpec>& ss, bool per_set_grid) {
+  B200SV_REQUIRE(B >= 1 && B <= 65535 && M >= 1 && P >= 3, "1 <= B <= 65535, M >= 1, P >= 3");
+  const int Jtot = offsets[M] - offsets[0];
+  B200SV_REQUIRE(Jtot >= 1, "the chain has no strikes");
+  if (int rc = check_fourier_types(types + offsets[0], Jtot, spot)) return rc;
+  dtaus.resize(M);
+  double t0 = 0.0;
+  for (int m = 0; m < M; ++m) {
+    B200SV_REQUIRE(ttms[m] > t0, "ttms must be positive and strictly increasing");
+    dtaus[m] = ttms[m] - t0;
+    t0 = ttms[m];
+  }
+  ss.resize((size_t)B * Jtot);
+  for (int b = 0; b < B; ++b)
+    for (int m = 0; m < M; ++m)
+      for (int j = offsets[m]; j < offsets[m + 1]; ++j) {
+        B200SV_REQUIRE(strikes[j] > 0.0, "strikes must be positive");
+        ss[(size_t)b * Jtot + (j - offsets[0])] = StrikeSpec{strikes[j], forwards[m], discfactors[m], (int)types[j], b * M + m, ttms[m], per_set_grid ? b : 0};
+      }
+  return 0;
+}
+
+int b200sv_logsv_price_chain_batch(const b200sv_logsv_params* params, int B, int M, const double* ttms, const double* forwards,
+                                   const double* discfactors, const double* etas, const int* offsets, const double* strikes,
+                                   const int8_t* types, int is_spot_measure, int expansion_order, double vol_scaler, int P,
+                                   double* prices_out, double* ivols_out) {
+  B200SV_REQUIRE(params && ttms && forwards && discfactors && offsets && strikes && types && prices_out, "null pointer");
+  if (P <= 0) P = 1000;
+  if (expansion_order != B200SV_ORDER_FIRST && expansion_order != B200SV_ORDER_SECOND) return fail(-4, "expansion_order not implemented");
+  const bool spot = is_spot_measure != 0;
+  const bool per_set_grid = !(vol_scaler > 0.0);      // default scaler depends on sigma0 of each set (logsv_pricer.py:664-666)
+  std::vector<double> dtaus;
+  std::vector<StrikeSpec> ss;
+  if (int rc = chain_batch_common(B, M, ttms, forwards, discfactors, offsets, strikes, types, spot, P, dtaus, ss, per_set_grid)) return rc;
+  const int Jtot = offsets[M] - offsets[0], N = expansion_order == B200SV_ORDER_FIRST ? 3 : 5;
+  const double tmin = *std::min_element(ttms, ttms + M);
+  const int G = per_set_grid ? B : 1;
+  std::vector<double> phi, one;
+  for (int g = 0; g < G; ++g) {
+    build_phi(per_set_grid ? params[g].sigma0 * std::sqrt(std::min(tmin, 0.5 / 12.0)) : vol_scaler, spot, P, one);
+    phi.insert(phi.end(), one.begin(), one.end());
+  }
+  std::vector<ChainSpec> spec((size_t)B * M);
+  std::vector<double> yb(B);
+  for (int b = 0; b < B; ++b) {
+    yb[b] = params[b].sigma0 - params[b].theta;
+    for (int m = 0; m < M; ++m) spec[(size_t)b * M + m] = ChainSpec{dtaus[m], make_model(params[b], etas ? etas[(size_t)b * M + m] : 1.0, spot)};
+  }
+  cudaStream_t st = 0;
+  DevBuf d_phi(st), d_spec(st), d_y(st), d_a(st), d_lm(st), d_ss(st), d_pr(st), d_iv(st);
+  const size_t nq = (size_t)B * Jtot;
+  B200SV_CUDA(d_phi.alloc(sizeof(cd) * (size_t)G * P));
+  B200SV_CUDA(d_spec.alloc(sizeof(ChainSpec) * spec.size()));
+  B200SV_CUDA(d_y.alloc(sizeof(double) * B));
+  B200SV_CUDA(d_a.alloc(sizeof(cd) * (size_t)B * M * P * N));
+  B200SV_CUDA(d_lm.alloc(sizeof(cd) * (size_t)B * M * P));
+  B200SV_CUDA(d_ss.alloc(sizeof(StrikeSpec) * nq));
+  B200SV_CUDA(d_pr.alloc(sizeof(double) * nq));
+  B200SV_CUDA(d_iv.alloc(sizeof(double) * nq));
+  B200SV_CUDA(cudaMemcpyAsync(d_phi.p, phi.data(), sizeof(cd) * (size_t)G * P, cudaMemcpyHostToDevice, st));
+  B200SV_CUDA(cudaMemcpyAsync(d_spec.p, spec.data(), sizeof(ChainSpec) * spec.size(), cudaMemcpyHostToDevice, st));
+  B200SV_CUDA(cudaMemcpyAsync(d_y.p, yb.data(), sizeof(double) * B, cudaMemcpyHostToDevice, st));
+  B200SV_CUDA(cudaMemcpyAsync(d_ss.p, ss.data(), sizeof(StrikeSpec) * nq, cudaMemcpyHostToDevice, st));
+  const long long threads = (long long)B * P;
+  const int tpb = mgf_block_threads((int)std::min<long long>(threads, 1 << 30)), nb = (P + tpb - 1) / tpb;
+  if (N == 5)
+    launch_logsv_mgf<5>(tpb, nb, st, d_phi.as<cd>(), nullptr, P, M, d_spec.as<ChainSpec>(), nullptr, d_a.as<cd>(), d_lm.as<cd>(), 0.0, nullptr, B,
+                        d_y.as<double>(), per_set_grid ? P : 0);
+  else
+    launch_logsv_mgf<3>(tpb, nb, st, d_phi.as<cd>(), nullptr, P, M, d_spec.as<ChainSpec>(), nullptr, d_a.as<cd>(), d_lm.as<cd>(), 0.0, nullptr, B,
+                        d_y.as<double>(), per_set_grid ? P : 0);
+  if (int rc = launched("logsv_mgf_kernel")) return rc;
+  fourier_vanilla_kernel<<<(unsigned)nq, kFourierThreads, 0, st>>>(d_lm.as<cd>(), d_phi.as<cd>(), P, d_ss.as<StrikeSpec>(), spot ? 1 : 0, 1,
+                                                                    d_pr.as<double>(), ivols_out ? d_iv.as<double>() : nullptr);
+  if (int rc = launched("fourier_vanilla_kernel")) return rc;
+  B200SV_CUDA(cudaMemcpyAsync(prices_out, d_pr.p, sizeof(double) * nq, cudaMemcpyDeviceToHost, st));
+  if (ivols_out) B200SV_CUDA(cudaMemcpyAsync(ivols_out, d_iv.p, sizeof(double) * nq, cudaMemcpyDeviceToHost, st));
+  B200SV_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int b200sv_heston_price_chain_batch(const b200sv_heston_params* params, int B, int M, const double* ttms, const double* forwards,
+                                    const double* discfactors, const int* offsets, const double* strikes, const int8_t* types,
+                                    double vol_scaler, int P, double* prices_out, double* ivols_out) {
+  B200SV_REQUIRE(params && ttms && forwards && discfactors && offsets && strikes && types && prices_out, "null pointer");
+  if (P <= 0) P = 1000;
+  const bool per_set_grid = !(vol_scaler > 0.0);      // default scaler depends on v0 of each set (heston_pricer.py:234-235)
+  std::vector<double> dtaus;
+  std::vector<StrikeSpec> ss;
+  if (int rc = chain_batch_common(B, M, ttms, forwards, discfactors, offsets, strikes, types, true, P, dtaus, ss, per_set_grid)) return rc;
+  const int Jtot = offsets[M] - offsets[0];
+  const int G = per_set_grid ? B : 1;
+  std::vector<double> phi, one;
+  for (int g = 0; g < G; ++g) {
+    build_phi(per_set_grid ? std::min(0.3, std::sqrt(params[g].v0 * ttms[0])) : vol_scaler, true, P, one);
+    phi.insert(phi.end(), one.begin(), one.end());
+  }
+  cudaStream_t st = 0;
+  DevBuf d_phi(st), d_hp(st), d_dt(st), d_lm(st), d_ss(st), d_pr(st), d_iv(st);
+  const size_t nq = (size_t)B * Jtot;
+  B200SV_CUDA(d_phi.alloc(sizeof(cd) * (size_t)G * P));
+  B200SV_CUDA(d_hp.alloc(sizeof(b200sv_heston_params) * B));
+  B200SV_CUDA(d_dt.alloc(sizeof(double) * M));
+  B200SV_CUDA(d_lm.alloc(sizeof(cd) * (size_t)B * M * P));
+  B200SV_CUDA(d_ss.alloc(sizeof(StrikeSpec) * nq));
+  B200SV_CUDA(d_pr.alloc(sizeof(double) * nq));
+  B200SV_CUDA(d_iv.alloc(sizeof(double) * nq));
+  B200SV_CUDA(cudaMemcpyAsync(d_phi.p, phi.data(), sizeof(cd) * (size_t)G * P, cudaMemcpyHostToDevice, st));
+  B200SV_CUDA(cudaMemcpyAsync(d_hp.p, params, sizeof(b200sv_heston_params) * B, cudaMemcpyHostToDevice, st));
+  B200SV_CUDA(cudaMemcpyAsync(d_dt.p, dtaus.data(), sizeof(double) * M, cudaMemcpyHostToDevice, st));
+  B200SV_CUDA(cudaMemcpyAsync(d_ss.p, ss.data(), sizeof(StrikeSpec) * nq, cudaMemcpyHostToDevice, st));
+  const int tpb = 64, nb = (P + tpb - 1) / tpb;
+  heston_mgf_kernel<<<dim3(nb, B), tpb, 0, st>>>(d_phi.as<cd>(), nullptr, P, M, d_dt.as<double>(), params[0], nullptr, nullptr, nullptr, nullptr,
+                                                 d_lm.as<cd>(), d_hp.as<b200sv_heston_params>(), per_set_grid ? P : 0);
+  if (int rc = launched("heston_mgf_kernel")) return rc;
+  fourier_vanilla_kernel<<<(unsigned)nq, kFourierThreads, 0, st>>>(d_lm.as<cd>(), d_phi.as<cd>(), P, d_ss.as<StrikeSpec>(), 1, 1, d_pr.as<double>(),
+                                                                    ivols_out ? d_iv.as<double>() : nullptr);
+  if (int rc = launched("fourier_vanilla_kernel")) return rc;
+  B200SV_CUDA(cudaMemcpyAsync(prices_out, d_pr.p, sizeof(double) * nq, cudaMemcpyDeviceToHost, st));
+  if (ivols_out) B200SV_CUDA(cudaMemcpyAsync(ivols_out, d_iv.p, sizeof(double) * nq, cudaMemcpyDeviceToHost, st));
   B200SV_CUDA(cudaStreamSynchronize(st));
   return 0;
 }
@@ -788,7 +942,7 @@ int b200sv_fourier_vanilla(const double* log_mgf, const double* phi, int P, doub
   const bool spot = is_spot_measure != 0;
   if (int rc = check_fourier_types(types, J, spot)) return rc;
   std::vector<StrikeSpec> ss(J);
-  for (int j = 0; j < J; ++j) ss[j] = StrikeSpec{strikes[j], forward, discfactor, (int)types[j], 0};
+  for (int j = 0; j < J; ++j) ss[j] = StrikeSpec{strikes[j], forward, discfactor, (int)types[j], 0, 1.0, 0};
   cudaStream_t st = 0;
   DevBuf d_phi(st), d_lm(st), d_ss(st), d_pr(st);
   B200SV_CUDA(d_phi.alloc(sizeof(cd) * P));

@@ -8,7 +8,7 @@ reference's validation rules (data/option_chain.py:147-215) and constructors ``s
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import List, Optional, Sequence
+from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -97,6 +97,27 @@ class OptionChain:
         if self.bid_ivs is not None and self.ask_ivs is not None:
             return [0.5 * (b + a) for b, a in zip(self.bid_ivs, self.ask_ivs)]
         return None
+
+    def get_chain_data_as_xy(self) -> Tuple[tuple, List[np.ndarray]]:
+        """(x, y) for model calibration: chain inputs and mid implied vols (reference data/option_chain.py:318-325)."""
+        mid_vols = [0.5 * (b + a) for b, a in zip(self.bid_ivs, self.ask_ivs)]
+        return (self.ttms, self.forwards, self.discfactors, self.strikes_ttms, self.optiontypes_ttms), mid_vols
+
+    def get_chain_atm_vols(self) -> np.ndarray:
+        """mid vol of each slice interpolated to the forward (reference :281-286)."""
+        return np.array([np.interp(x=f, xp=k, fp=y) for f, k, y in zip(self.forwards, self.strikes_ttms, self.get_mid_vols())])
+
+    def get_chain_vegas(self, is_unit_ttm_vega: bool = False) -> List[np.ndarray]:
+        """Black-76 vegas F*n(d1)*sqrt(T) at the mid vols, one array per slice -- the calibration weights of Eq. (6.3) (reference
+        :263-279 -> third-party ``vanilla_option_pricers.bsm.compute_bsm_vegas_ttms``, absent from the reference tree; host-side
+        arithmetic on a handful of quotes, normalised per slice by the caller)."""
+        ttms = np.ones_like(self.ttms) if is_unit_ttm_vega else self.ttms
+        out = []
+        for ttm, forward, strikes, vols in zip(ttms, self.forwards, self.strikes_ttms, self.get_mid_vols()):
+            sdev = vols * np.sqrt(ttm)
+            d1 = np.log(forward / strikes) / sdev + 0.5 * sdev
+            out.append(forward * np.exp(-0.5 * d1 * d1) / np.sqrt(2.0 * np.pi) * np.sqrt(ttm))
+        return out
 
     def compute_model_ivols_from_chain_data(self, model_prices: Sequence[np.ndarray], forwards: np.ndarray = None) -> List[np.ndarray]:
         """invert model prices to Black implied vols for the whole chain in one GPU kernel launch (reference

@@ -208,6 +208,43 @@ def heston_price_chain(params: C.HestonParamsC, ttms, forwards, discfactors, str
     return (out, lm_out) if return_grids else out
 
 
+def logsv_price_chain_batch(params_list: Sequence[C.LogsvParamsC], ttms, forwards, discfactors, etas, strikes_ttms, optiontypes_ttms,
+                            is_spot_measure: bool = True, expansion_order: int = C.ORDER_SECOND, vol_scaler: Optional[float] = None,
+                            max_phi: int = 1000, with_ivols: bool = True):
+    """B parameter sets on one chain in one pass -> (prices [B, J], ivols [B, J] | None); ``etas`` is [B, M] or None."""
+    _check_fourier_types(optiontypes_ttms, bool(is_spot_measure))
+    M, ttms, forwards, discfactors, offsets, strikes, types = _chain_arrays(ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms)
+    B = len(params_list)
+    arr = (C.LogsvParamsC * B)(*params_list)
+    etas_c = None
+    if etas is not None:
+        etas_c = np.ascontiguousarray(etas, dtype=np.float64)
+        if etas_c.shape != (B, M):
+            raise ValueError(f"etas must have shape ({B}, {M})")
+    prices = np.empty((B, strikes.shape[0]))
+    ivols = np.empty((B, strikes.shape[0])) if with_ivols else None
+    C.call("b200sv_logsv_price_chain_batch", arr, B, M, C.dptr(ttms), C.dptr(forwards), C.dptr(discfactors),
+           C.dptr(etas_c) if etas_c is not None else None, C.iptr(offsets), C.dptr(strikes), C.i8ptr(types), int(bool(is_spot_measure)),
+           int(expansion_order), float(vol_scaler) if vol_scaler is not None else -1.0, int(max_phi), C.dptr(prices),
+           C.dptr(ivols) if with_ivols else None)
+    return prices, ivols
+
+
+def heston_price_chain_batch(params_list: Sequence[C.HestonParamsC], ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms,
+                             vol_scaler: Optional[float] = None, max_phi: int = 1000, with_ivols: bool = True):
+    """B Heston parameter sets on one chain in one pass -> (prices [B, J], ivols [B, J] | None)."""
+    _check_fourier_types(optiontypes_ttms, True)
+    M, ttms, forwards, discfactors, offsets, strikes, types = _chain_arrays(ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms)
+    B = len(params_list)
+    arr = (C.HestonParamsC * B)(*params_list)
+    prices = np.empty((B, strikes.shape[0]))
+    ivols = np.empty((B, strikes.shape[0])) if with_ivols else None
+    C.call("b200sv_heston_price_chain_batch", arr, B, M, C.dptr(ttms), C.dptr(forwards), C.dptr(discfactors), C.iptr(offsets),
+           C.dptr(strikes), C.i8ptr(types), float(vol_scaler) if vol_scaler is not None else -1.0, int(max_phi), C.dptr(prices),
+           C.dptr(ivols) if with_ivols else None)
+    return prices, ivols
+
+
 def logsv_mgf_grid(phi, psi, dtau: float, a_t0, params: C.LogsvParamsC, eta: float, is_spot_measure: bool, expansion_order: int):
     phi = C.c128(phi)
     psi = C.c128(psi) if psi is not None else None

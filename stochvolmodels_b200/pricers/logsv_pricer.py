@@ -13,7 +13,8 @@ RNG and exposes no seed; default = OS entropy), ``precision`` ('fp64' | 'fp32'),
 (shard ``nb_path`` over the ranks of an initialised ``torch.distributed`` world; default True when one exists).
 Unknown kwargs are accepted and ignored on both routes, as in the reference (:349, :376, :681).
 
-Calibration (:105-333, :441-558) and the rough-vol route (:1164-1232) are callers / neighbours of the hot path and out of scope.
+``LogSVPricer.calibrate_model_params_to_chain`` (:441-558) runs on the batched GPU chain pricer (pricers/calibration.py); the
+rough-vol route (:1164-1232) is a neighbour of the hot path and out of scope.
 """
 from __future__ import annotations
 
@@ -27,6 +28,7 @@ from .. import engine
 from ..data.option_chain import OptionChain
 from ..utils.config import VariableType
 from ..utils.funcs import set_time_grid, timer
+from .calibration import CalibrationEngine, ConstraintsType, LogsvModelCalibrationType, calibrate_logsv
 from .logsv.affine_expansion import ExpansionOrder, _order_code
 from .model_pricer import ModelParams, ModelPricer
 
@@ -107,6 +109,29 @@ class LogSVPricer(ModelPricer):
         return logsv_chain_pricer(params=params, ttms=option_chain.ttms, forwards=option_chain.forwards,
                                   discfactors=option_chain.discfactors, strikes_ttms=option_chain.strikes_ttms,
                                   optiontypes_ttms=option_chain.optiontypes_ttms, is_spot_measure=is_spot_measure, **kwargs)
+
+    def set_vol_scaler(self, option_chain: OptionChain) -> float:
+        """transform-grid scaler from the first slice's ATM vol (reference :436-439)."""
+        return set_vol_scaler(sigma0=option_chain.get_chain_atm_vols()[0], ttm=option_chain.ttms[0])
+
+    @timer
+    def calibrate_model_params_to_chain(self, option_chain: OptionChain, params0: LogSvParams,
+                                        params_min: Optional[LogSvParams] = None, params_max: Optional[LogSvParams] = None,
+                                        is_vega_weighted: bool = True, is_unit_ttm_vega: bool = False,
+                                        model_calibration_type: LogsvModelCalibrationType = LogsvModelCalibrationType.PARAMS5,
+                                        constraints_type: ConstraintsType = ConstraintsType.UNCONSTRAINT,
+                                        calibration_engine: CalibrationEngine = CalibrationEngine.ANALYTIC,
+                                        nb_path: int = 100000, nb_steps: int = 360, seed: int = 10, **kwargs) -> LogSvParams:
+        """fit model parameters to the chain's mid implied vols: vega-weighted squared vol errors (Eq. (6.3)) minimised by SLSQP under
+        ``constraints_type`` (reference :441-558; same arguments, bounds and return type).  The objective and its finite-difference
+        gradient are ONE batched GPU call per optimizer evaluation (pricers/calibration.py).  ``return_info=True`` also returns
+        {fun, nit, nb_batches, x}."""
+        params_min = params_min or LogSvParams(sigma0=0.1, theta=0.1, kappa1=0.25, kappa2=0.25, beta=-3.0, volvol=0.2)
+        params_max = params_max or LogSvParams(sigma0=1.5, theta=1.5, kappa1=10.0, kappa2=10.0, beta=3.0, volvol=3.0)
+        return calibrate_logsv(self, option_chain, params0, params_min, params_max, is_vega_weighted, is_unit_ttm_vega,
+                               model_calibration_type, constraints_type, calibration_engine, nb_path, nb_steps, seed,
+                               is_spot_measure=kwargs.get("is_spot_measure", True), disp=bool(kwargs.get("disp", False)),
+                               return_info=bool(kwargs.get("return_info", False)), fd_step=kwargs.get("fd_step"))
 
     @timer
     def model_mc_price_chain(self, option_chain: OptionChain, params: LogSvParams, is_spot_measure: bool = True,

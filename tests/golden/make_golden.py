@@ -449,7 +449,89 @@ def vol_paths():
     print("vol paths", out["sigma_t_mma"].shape, out["method_shape"])
 
 
+def calibration() -> None:
+    """goldens for the calibration drivers: the reference's own ``calibrate_model_params_to_chain`` (SLSQP, scipy
+    finite differences, CPU pricer) on a synthetic market generated by the reference pricer.  The third-party Black helpers the
+    reference imports (``vanilla_option_pricers.bsm``: implied vols, vegas) are absent from the reference tree; a shim built on
+    ``oracle/bsm.py`` stands in for them, so these goldens pin the DRIVER + PRICER, not the third-party inversion.
+    Run:  python tests/golden/make_golden.py --only-calib"""
+    import types
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+    from oracle import bsm as obsm
+    shim = types.ModuleType("vanilla_option_pricers.bsm")
+    shim.infer_bsm_ivols_from_model_chain_prices = obsm.infer_bsm_ivols_from_model_chain_prices
+
+    def compute_bsm_vegas_ttms(ttms, forwards, strikes_ttms, optiontypes_ttms, vols_ttms):
+        out = []
+        for ttm, forward, strikes, vols in zip(ttms, forwards, strikes_ttms, vols_ttms):
+            sdev = vols * np.sqrt(ttm)
+            d1 = np.log(forward / strikes) / sdev + 0.5 * sdev
+            out.append(forward * np.exp(-0.5 * d1 * d1) / np.sqrt(2.0 * np.pi) * np.sqrt(ttm))
+        return out
+    shim.compute_bsm_vegas_ttms = compute_bsm_vegas_ttms
+    pkg = MagicMock()          # the reference does `import vanilla_option_pricers as bsm`: the two functions it needs live on the package
+    pkg.infer_bsm_ivols_from_model_chain_prices = shim.infer_bsm_ivols_from_model_chain_prices
+    pkg.compute_bsm_vegas_ttms = shim.compute_bsm_vegas_ttms
+    sys.modules["vanilla_option_pricers"] = pkg
+    sys.modules["vanilla_option_pricers.bsm"] = shim
+    sys.modules["vanilla_option_pricers.bachelier"] = MagicMock()
+    _import_reference()
+    import time
+    from stochvolmodels.pricers import logsv_pricer as lp
+    from stochvolmodels.pricers import heston_pricer as hp
+    from stochvolmodels.pricers.logsv.logsv_params import LogSvParams
+    from stochvolmodels.data.option_chain import OptionChain
+
+    ttms = np.array([1.0 / 12.0, 0.25])
+    forwards = np.array([1.0, 1.0])
+    K = np.array([0.8, 0.9, 1.0, 1.1, 1.2])
+    types_ = np.array(["P", "P", "C", "C", "C"])
+
+    def chain_with(vols):
+        return OptionChain(ttms=ttms, ids=np.array(["1m", "3m"]), forwards=forwards, strikes_ttms=[K, K], optiontypes_ttms=[types_, types_],
+                           bid_ivs=[v.copy() for v in vols], ask_ivs=[v.copy() for v in vols])
+
+    flat = chain_with([0.8 * np.ones(5), 0.8 * np.ones(5)])
+    # ---- LogSV, PARAMS4, analytic engine
+    truth = LogSvParams(sigma0=0.9, theta=1.0, kappa1=4.0, kappa2=4.0, beta=0.3, volvol=1.5)
+    pricer = lp.LogSVPricer()
+    market = pricer.compute_model_ivols_for_chain(option_chain=flat, params=truth, vol_scaler=pricer.set_vol_scaler(option_chain=flat))
+    chain = chain_with([np.asarray(v) for v in market])
+    start = LogSvParams(sigma0=0.8, theta=0.9, kappa1=4.0, kappa2=4.0, beta=0.1, volvol=1.2)
+    t = time.time()
+    fit = pricer.calibrate_model_params_to_chain(option_chain=chain, params0=start,
+                                                 model_calibration_type=lp.LogsvModelCalibrationType.PARAMS4,
+                                                 constraints_type=lp.ConstraintsType.UNCONSTRAINT)
+    secs = time.time() - t
+    fit_vols = pricer.compute_model_ivols_for_chain(option_chain=chain, params=fit, vol_scaler=pricer.set_vol_scaler(option_chain=chain))
+    print("logsv fit", fit, f"{secs:.1f}s")
+    np.savez(os.path.join(OUT, "calib_logsv_params4.npz"), ttms=ttms, forwards=forwards, strikes=K, types=types_,
+             market_vols=np.array(market), truth=np.array([truth.sigma0, truth.theta, truth.kappa1, truth.kappa2, truth.beta, truth.volvol]),
+             start=np.array([start.sigma0, start.theta, start.kappa1, start.kappa2, start.beta, start.volvol]),
+             fit=np.array([fit.sigma0, fit.theta, fit.kappa1, fit.kappa2, fit.beta, fit.volvol]), fit_vols=np.array(fit_vols),
+             vol_scaler=np.array(pricer.set_vol_scaler(option_chain=chain)), ref_seconds=np.array(secs))
+    # ---- Heston
+    htruth = hp.HestonParams(v0=0.7, theta=0.9, kappa=3.0, rho=-0.3, volvol=1.2)
+    hpr = hp.HestonPricer()
+    hmarket = hpr.compute_model_ivols_for_chain(option_chain=flat, params=htruth)
+    hchain = chain_with([np.asarray(v) for v in hmarket])
+    hstart = hp.HestonParams(v0=0.5, theta=0.7, kappa=2.0, rho=-0.1, volvol=1.0)
+    t = time.time()
+    hfit = hpr.calibrate_model_params_to_chain(option_chain=hchain, params0=hstart)
+    hsecs = time.time() - t
+    hfit_vols = hpr.compute_model_ivols_for_chain(option_chain=hchain, params=hfit)
+    print("heston fit", hfit, f"{hsecs:.1f}s")
+    np.savez(os.path.join(OUT, "calib_heston.npz"), ttms=ttms, forwards=forwards, strikes=K, types=types_, market_vols=np.array(hmarket),
+             truth=np.array([htruth.v0, htruth.theta, htruth.kappa, htruth.rho, htruth.volvol]),
+             start=np.array([hstart.v0, hstart.theta, hstart.kappa, hstart.rho, hstart.volvol]),
+             fit=np.array([hfit.v0, hfit.theta, hfit.kappa, hfit.rho, hfit.volvol]), fit_vols=np.array(hfit_vols), ref_seconds=np.array(hsecs))
+
+
+
 if __name__ == "__main__":
+    if "--only-calib" in sys.argv:
+        calibration()
+        sys.exit(0)
     if "--only-volpaths" in sys.argv:
         vol_paths()
         sys.exit(0)
