@@ -138,9 +138,10 @@ class CudaMcEngine:
                int(variable_type), int(kinds), c_void_p(self.moments.data_ptr()), c_void_p(sums.data_ptr()), self.p2p, self._stream())
         return sums
 
-    def finalize(self, sums, J: int, discfactor: float, total_paths: int):
-        """GLOBAL sums -> (prices, std errors) device views of J doubles each."""
-        prices, stds = self.out[:J], self.out[self.cap: self.cap + J]
+    def finalize(self, sums, J: int, discfactor: float, total_paths: int, prices=None, stds=None):
+        """GLOBAL sums -> (prices, std errors) device views of J doubles each (written into ``prices`` / ``stds`` when given)."""
+        if prices is None:
+            prices, stds = self.out[:J], self.out[self.cap: self.cap + J]
         C.call("b200sv_dev_payoff_finalize", c_void_p(sums.data_ptr()), int(J), float(discfactor), int(total_paths),
                c_void_p(prices.data_ptr()), c_void_p(stds.data_ptr()), self.p2p, self._stream())
         return prices, stds
@@ -180,6 +181,9 @@ def mc_chain_distributed(model: str, params_c, ttms, forwards, discfactors, etas
     strikes_dev = eng.to_device(strikes, torch.float64)
     types_dev = eng.to_device(types, torch.int8)
     etas = np.ones(M) if etas is None else np.asarray(etas, dtype=np.float64)
+    Jtot = int(offsets[-1])
+    chain_out = hasattr(eng, "torch")          # CUDA engine: results stay on the device until ONE copy at the end of the chain
+    out_dev = eng.torch.zeros((2, max(Jtot, 1)), dtype=eng.torch.float64, device=eng.device) if chain_out else None
     results = []
     t0 = 0.0
     for m in range(M):
@@ -197,13 +201,24 @@ def mc_chain_distributed(model: str, params_c, ttms, forwards, discfactors, etas
         sums = eng.payoff_sums(float(ttms[m]), float(forwards[m]), strikes_dev[jo: jo + J], types_dev[jo: jo + J], J, variable_type, kinds)
         if world > 1 and not use_p2p:
             dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)                 # exchange (2): 24*J bytes
-        prices, stds = eng.finalize(sums, J, float(discfactors[m]), int(nb_path))
-        results.append((prices.clone(), stds.clone()))
+        if chain_out:
+            eng.finalize(sums, J, float(discfactors[m]), int(nb_path), out_dev[0, jo: jo + J], out_dev[1, jo: jo + J])
+            results.append((jo, J))
+        else:
+            prices, stds = eng.finalize(sums, J, float(discfactors[m]), int(nb_path))
+            results.append((prices.clone(), stds.clone()))
     prices_out: List[np.ndarray] = []
     stds_out: List[np.ndarray] = []
-    for p, s in results:
-        prices_out.append(p.cpu().numpy() if p is not None else np.zeros(0))
-        stds_out.append(s.cpu().numpy() if s is not None else np.zeros(0))
+    if chain_out:
+        host = out_dev.cpu().numpy()
+        for r in results:
+            jo, J = r if r[0] is not None else (0, 0)
+            prices_out.append(host[0, jo: jo + J].copy())
+            stds_out.append(host[1, jo: jo + J].copy())
+    else:
+        for p, s in results:
+            prices_out.append(p.cpu().numpy() if p is not None else np.zeros(0))
+            stds_out.append(s.cpu().numpy() if s is not None else np.zeros(0))
     if return_engine:
         return prices_out, stds_out, eng
     return prices_out, stds_out

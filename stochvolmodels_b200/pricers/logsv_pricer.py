@@ -302,7 +302,7 @@ class DeviceRandoms:
         import torch
         if not torch.cuda.is_available():
             raise RuntimeError("DeviceRandoms needs a CUDA device; stochvolmodels_b200 has no CPU fallback")
-        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.device = torch.device(f"cuda:{torch.cuda.current_device()}" if device is None or device is True else device)
         up = lambda w: w.to(self.device, torch.float64).contiguous() if torch.is_tensor(w) else torch.as_tensor(np.ascontiguousarray(w, dtype=np.float64)).to(self.device)
         self.W0s, self.W1s, self.dts = [up(w) for w in W0s], [up(w) for w in W1s], [float(d) for d in dts]
         self.nb_path = int(self.W0s[0].shape[1])
