@@ -180,7 +180,14 @@ def main():
     eng = CudaMcEngine("logsv", _params_c(params), n_local, rank * n_local, flags, int(sizes.max()))
     use_p2p = world > 1 and args.exchange == "p2p"     # the two per-maturity messages ride inside the kernels over NVLink peer memory
     if use_p2p:
-        eng.enable_p2p()
+        from stochvolmodels_b200.multi_gpu import P2pUnavailable
+        try:
+            eng.enable_p2p()
+        except P2pUnavailable as e:          # raised on every rank together; the NCCL exchange is the same arithmetic
+            if rank == 0:
+                print(f"bench.py: peer-memory exchange unavailable ({e}); using NCCL all-reduces", file=sys.stderr)
+            use_p2p = False
+            args.exchange = "collective"
     strikes_dev = eng.to_device(strikes, torch.float64)
     types_dev = eng.to_device(types, torch.int8)
     out_dev = torch.zeros((2, strikes.shape[0]), dtype=torch.float64, device=eng.device)

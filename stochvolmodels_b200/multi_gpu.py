@@ -55,15 +55,34 @@ def p2p_context(torch, device, group=None, min_values: int = 0):
     cap = max(int(min_values), _P2P_MIN_VALUES)
     ctx = c_void_p()
     handle = (ctypes.c_ubyte * 64)()
+    error = None
     with torch.cuda.device(device):
-        C.call("b200sv_p2p_create", world, rank, cap, ctypes.byref(ctx), handle)
+        try:
+            C.call("b200sv_p2p_create", world, rank, cap, ctypes.byref(ctx), handle)
+        except C.B200svError as e:       # keep taking part in the collectives below so that every rank reaches the same verdict
+            error = e
         handles = [None] * world
-        dist.all_gather_object(handles, bytes(handle), group=group)
-        blob = (ctypes.c_ubyte * (64 * world)).from_buffer_copy(b"".join(handles))
-        C.call("b200sv_p2p_connect", ctx, blob)
-    dist.barrier(group)                   # nobody publishes before every mailbox is mapped everywhere
+        dist.all_gather_object(handles, None if error else bytes(handle), group=group)
+        if error is None and all(h is not None for h in handles):
+            try:
+                C.call("b200sv_p2p_connect", ctx, (ctypes.c_ubyte * (64 * world)).from_buffer_copy(b"".join(handles)))
+            except C.B200svError as e:   # e.g. no peer access / IPC not permitted between these devices
+                error = e
+        elif error is None:
+            error = C.B200svError(-2, "a peer could not create its mailbox")
+    verdicts = [None] * world
+    dist.all_gather_object(verdicts, None if error is None else str(error), group=group)   # also: nobody publishes before all are mapped
+    failed = [v for v in verdicts if v is not None]
+    if failed:
+        if ctx:
+            C.call("b200sv_p2p_destroy", ctx)
+        raise P2pUnavailable(failed[0])
     _P2P_CACHE[key] = (ctx, cap)
     return ctx
+
+
+class P2pUnavailable(RuntimeError):
+    """peer-memory mailboxes cannot be set up between the ranks of this group (raised on EVERY rank of the group)."""
 
 
 def release_p2p():
@@ -171,13 +190,19 @@ def mc_chain_distributed(model: str, params_c, ttms, forwards, discfactors, etas
     factory = engine_factory or CudaMcEngine
     eng = factory(model, params_c, n_local, offset, flags, Jmax, scheme=scheme) if scheme else factory(model, params_c, n_local, offset, flags, Jmax)
     # exchange mode: P2P mailbox on CUDA engines of a multi-rank group unless the caller asks for the collective
+    explicit_p2p = exchange == "p2p"
     if exchange is None:
         exchange = "p2p" if (world > 1 and hasattr(eng, "enable_p2p") and world <= 8) else "collective"
     if exchange not in ("p2p", "collective"):
         raise ValueError("exchange must be 'p2p' or 'collective'")
     use_p2p = exchange == "p2p" and world > 1
     if use_p2p:
-        eng.enable_p2p(group)
+        try:
+            eng.enable_p2p(group)
+        except P2pUnavailable:            # every rank gets this together: all switch to the collective, or all re-raise
+            if explicit_p2p:
+                raise
+            use_p2p = False
     strikes_dev = eng.to_device(strikes, torch.float64)
     types_dev = eng.to_device(types, torch.int8)
     etas = np.ones(M) if etas is None else np.asarray(etas, dtype=np.float64)
