@@ -80,6 +80,20 @@ int b200sv_heston_mc_chain(const b200sv_heston_params* params, int M, const doub
                            long long nb_path, int nb_steps_per_year, int variable_type, uint64_t seed, int flags,
                            int scheme, double* prices_out, double* stderr_out);
 
+/* B parameter sets through the fused chain Monte Carlo in ONE call, all on the SAME Philox seed (common random numbers): the objective of
+ * CalibrationEngine.MC (pricers/logsv_pricer.py:251-266 -- there: pre-drawn fixed normals W0s/W1s re-used across optimizer iterations;
+ * here the counter-based generator re-draws the identical normals for every set, so nothing is stored or streamed).  params[B],
+ * etas[B*M] (NULL = 1); prices_out / stderr_out / ivols_out are [B][J] in chain order (ivols_out may be NULL; Black-76 inversion fused into
+ * the finalisation kernel).  LOG_RETURN payoffs.  Row b equals b200sv_logsv_mc_chain(params[b], seed) bit for bit. */
+int b200sv_logsv_mc_chain_batch(const b200sv_logsv_params* params, int B, int M, const double* ttms, const double* forwards,
+                                const double* discfactors, const double* etas, const int* offsets, const double* strikes,
+                                const int8_t* types, long long nb_path, int nb_steps_per_year, int is_spot_measure, uint64_t seed,
+                                int flags, double* prices_out, double* stderr_out, double* ivols_out);
+int b200sv_heston_mc_chain_batch(const b200sv_heston_params* params, int B, int M, const double* ttms, const double* forwards,
+                                 const double* discfactors, const int* offsets, const double* strikes, const int8_t* types,
+                                 long long nb_path, int nb_steps_per_year, uint64_t seed, int flags, int scheme, double* prices_out,
+                                 double* stderr_out, double* ivols_out);
+
 /* replaces LogSVPricer.simulate_terminal_values (pricers/logsv_pricer.py:590-611) -> simulate_logsv_x_vol_terminal.
  * x, sigma, qvar: nb_path doubles each (host, out). */
 int b200sv_logsv_terminal(const b200sv_logsv_params* params, double ttm, long long nb_path, int nb_steps_per_year,

@@ -51,6 +51,8 @@ _hp = POINTER(HestonParamsC)
 SIGNATURES = {
     "b200sv_logsv_mc_chain": [_lp, c_int, _dp, _dp, _dp, _dp, _ip, _dp, _i8p, c_longlong, c_int, c_int, c_int, c_uint64, c_int, _dp, _dp],
     "b200sv_heston_mc_chain": [_hp, c_int, _dp, _dp, _dp, _ip, _dp, _i8p, c_longlong, c_int, c_int, c_uint64, c_int, c_int, _dp, _dp],
+    "b200sv_logsv_mc_chain_batch": [_lp, c_int, c_int, _dp, _dp, _dp, _dp, _ip, _dp, _i8p, c_longlong, c_int, c_int, c_uint64, c_int, _dp, _dp, _dp],
+    "b200sv_heston_mc_chain_batch": [_hp, c_int, c_int, _dp, _dp, _dp, _ip, _dp, _i8p, c_longlong, c_int, c_uint64, c_int, c_int, _dp, _dp, _dp],
     "b200sv_logsv_terminal": [_lp, c_double, c_longlong, c_int, c_int, c_double, c_uint64, c_int, _dp, _dp, _dp],
     "b200sv_heston_terminal": [_hp, c_double, c_longlong, c_int, c_uint64, c_int, c_int, _dp, _dp, _dp],
     "b200sv_logsv_step_fixed": [_dp, _dp, _dp, _dp, _dp, c_int, c_longlong, c_double, _lp, c_double, c_int],

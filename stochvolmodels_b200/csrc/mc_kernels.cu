@@ -26,6 +26,7 @@
 #include "common.cuh"
 #include "fastmath64.cuh"
 #include "p2p.cuh"
+#include "black.cuh"
 #include "philox.cuh"
 
 namespace b200sv {
@@ -642,8 +643,16 @@ __global__ void __launch_bounds__(kThreads) payoff_vanilla_kernel(const Real* __
   }
 }
 
+// optional fused Black-76 inversion of the prices just assembled (batched calibration objective): needs strikes/types/forward/ttm
+struct IvolSpec {
+  const double* strikes;
+  const int8_t* types;
+  double forward, ttm;
+  double* ivols;       // nullptr: skip
+};
+
 __global__ void payoff_finalize_kernel(const double* __restrict__ sums, int J, double discfactor, double total_paths,
-                                       double* __restrict__ prices, double* __restrict__ stderrs, P2pGather gat) {
+                                       double* __restrict__ prices, double* __restrict__ stderrs, P2pGather gat, IvolSpec iv = IvolSpec{}) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= J) return;
   const double s1 = gat.world ? p2p_gather(gat, 3 * j) : sums[3 * j];
@@ -654,6 +663,7 @@ __global__ void payoff_finalize_kernel(const double* __restrict__ sums, int J, d
   var = var > 0.0 ? var : 0.0;
   prices[j] = discfactor * mean;                               // discfactor*np.nanmean(payoff)
   stderrs[j] = discfactor * sqrt(var) / sqrt(total_paths);     // discfactor*np.nanstd(payoff) / sqrt(x0.shape[0])
+  if (iv.ivols) iv.ivols[j] = black_implied_vol(iv.forward, iv.strikes[j], iv.ttm, discfactor, discfactor * mean, iv.types[j]);
 }
 
 // --------------------------------------------------------------------------------------------------------------------
@@ -878,7 +888,11 @@ template <int MODEL>
 static int mc_chain_host(const b200sv_logsv_params* lp, const b200sv_heston_params* hp, int M, const double* ttms,
                          const double* forwards, const double* discfactors, const double* etas, const int* offsets,
                          const double* strikes, const int8_t* types, long long nb_path, int nb_steps_per_year, int is_spot,
-                         int variable_type, uint64_t seed, int flags, double* prices_out, double* stderr_out, int scheme = 0) {
+                         int variable_type, uint64_t seed, int flags, double* prices_out, double* stderr_out, int scheme = 0, int B = 1,
+                         double* ivols_out = nullptr) {
+  // B > 1: lp / hp point to B parameter sets, etas to [B][M], outputs to [B][Jtot]; the sets run back to back on one stream with the SAME
+  // seed (common random numbers => a smooth objective in the parameters), no host synchronisation until the single copy back
+  B200SV_REQUIRE(B >= 1, "B must be >= 1");
   B200SV_REQUIRE(nb_path >= 1, "nb_path must be >= 1");
   B200SV_REQUIRE(nb_steps_per_year >= 1, "nb_steps_per_year must be >= 1");
   if (int rc = validate_chain(M, ttms, offsets, types, variable_type)) return rc;
@@ -894,41 +908,48 @@ static int mc_chain_host(const b200sv_logsv_params* lp, const b200sv_heston_para
   const int Jalloc = std::max(Jtot, 1);
   B200SV_CUDA(cudaMallocAsync(&d_strikes, sizeof(double) * Jalloc, st));
   B200SV_CUDA(cudaMallocAsync(&d_types, Jalloc, st));
-  B200SV_CUDA(cudaMallocAsync(&d_out, sizeof(double) * 2 * Jalloc, st));
+  const size_t out_stride = (size_t)3 * Jalloc;                 // per set: prices, std errors, implied vols
+  B200SV_CUDA(cudaMallocAsync(&d_out, sizeof(double) * out_stride * B, st));
   B200SV_CUDA(cudaMallocAsync(&d_mom, sizeof(double) * 2, st));
   B200SV_CUDA(cudaMallocAsync(&d_sums, sizeof(double) * 3 * Jalloc, st));
   if (Jtot > 0) {
     B200SV_CUDA(cudaMemcpyAsync(d_strikes, strikes + offsets[0], sizeof(double) * Jtot, cudaMemcpyHostToDevice, st));
     B200SV_CUDA(cudaMemcpyAsync(d_types, types + offsets[0], Jtot, cudaMemcpyHostToDevice, st));
   }
-  double t0 = 0.0;
   int rc = 0;
-  for (int m = 0; m < M && rc == 0; ++m) {
-    int S;
-    double dt;
-    time_grid(ttms[m] - t0, nb_steps_per_year, &S, &dt);
-    t0 = ttms[m];
-    if (MODEL == 0) {
-      const LogsvConsts c = make_logsv_consts(*lp, etas ? etas[m] : 1.0, is_spot != 0, dt);
-      rc = launch_slice<0>(x, v, q, nb_path, 0, m == 0, lp->sigma0, S, m, forwards[m], seed, flags, &c, nullptr, d_mom, st);
-    } else {
-      const HestonConsts c = make_heston_consts(*hp, dt, scheme);
-      rc = launch_slice<1>(x, v, q, nb_path, 0, m == 0, hp->v0, S, m, forwards[m], seed, flags, nullptr, &c, d_mom, st);
+  for (int b = 0; b < B && rc == 0; ++b) {
+    double* out_b = d_out + out_stride * b;
+    double t0 = 0.0;
+    for (int m = 0; m < M && rc == 0; ++m) {
+      int S;
+      double dt;
+      time_grid(ttms[m] - t0, nb_steps_per_year, &S, &dt);
+      t0 = ttms[m];
+      if (MODEL == 0) {
+        const LogsvConsts c = make_logsv_consts(lp[b], etas ? etas[(size_t)b * M + m] : 1.0, is_spot != 0, dt);
+        rc = launch_slice<0>(x, v, q, nb_path, 0, m == 0, lp[b].sigma0, S, m, forwards[m], seed, flags, &c, nullptr, d_mom, st);
+      } else {
+        const HestonConsts c = make_heston_consts(hp[b], dt, scheme);
+        rc = launch_slice<1>(x, v, q, nb_path, 0, m == 0, hp[b].v0, S, m, forwards[m], seed, flags, nullptr, &c, d_mom, st);
+      }
+      if (rc) break;
+      const int J = offsets[m + 1] - offsets[m], jo = offsets[m] - offsets[0];
+      if (J == 0) continue;
+      if (flags & B200SV_STATE_F32)
+        rc = launch_payoff_t<float>(x, q, nb_path, ttms[m], forwards[m], d_strikes + jo, d_types + jo, J, variable_type, payoff_kinds(types + offsets[m], J), d_mom, d_sums, st);
+      else
+        rc = launch_payoff_t<double>(x, q, nb_path, ttms[m], forwards[m], d_strikes + jo, d_types + jo, J, variable_type, payoff_kinds(types + offsets[m], J), d_mom, d_sums, st);
+      if (rc) break;
+      const IvolSpec iv{d_strikes + jo, d_types + jo, forwards[m], ttms[m], ivols_out ? out_b + 2 * Jalloc + jo : nullptr};
+      payoff_finalize_kernel<<<(J + 127) / 128, 128, 0, st>>>(d_sums, J, discfactors[m], (double)nb_path, out_b + jo, out_b + Jalloc + jo, P2pGather{}, iv);
+      rc = check_launch("payoff_finalize_kernel");
     }
-    if (rc) break;
-    const int J = offsets[m + 1] - offsets[m], jo = offsets[m] - offsets[0];
-    if (J == 0) continue;
-    if (flags & B200SV_STATE_F32)
-      rc = launch_payoff_t<float>(x, q, nb_path, ttms[m], forwards[m], d_strikes + jo, d_types + jo, J, variable_type, payoff_kinds(types + offsets[m], J), d_mom, d_sums, st);
-    else
-      rc = launch_payoff_t<double>(x, q, nb_path, ttms[m], forwards[m], d_strikes + jo, d_types + jo, J, variable_type, payoff_kinds(types + offsets[m], J), d_mom, d_sums, st);
-    if (rc) break;
-    payoff_finalize_kernel<<<(J + 127) / 128, 128, 0, st>>>(d_sums, J, discfactors[m], (double)nb_path, d_out + jo, d_out + Jalloc + jo, P2pGather{});
-    rc = check_launch("payoff_finalize_kernel");
   }
-  if (rc == 0 && Jtot > 0) {
-    cudaError_t e = cudaMemcpyAsync(prices_out, d_out, sizeof(double) * Jtot, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(stderr_out, d_out + Jalloc, sizeof(double) * Jtot, cudaMemcpyDeviceToHost, st);
+  for (int b = 0; b < B && rc == 0 && Jtot > 0; ++b) {
+    const double* out_b = d_out + out_stride * b;
+    cudaError_t e = cudaMemcpyAsync(prices_out + (size_t)b * Jtot, out_b, sizeof(double) * Jtot, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(stderr_out + (size_t)b * Jtot, out_b + Jalloc, sizeof(double) * Jtot, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && ivols_out) e = cudaMemcpyAsync(ivols_out + (size_t)b * Jtot, out_b + 2 * Jalloc, sizeof(double) * Jtot, cudaMemcpyDeviceToHost, st);
     if (e != cudaSuccess) rc = fail(-2, std::string("D2H: ") + cudaGetErrorString(e));
   }
   cudaFreeAsync(x, st);
@@ -1007,6 +1028,25 @@ int b200sv_heston_mc_chain(const b200sv_heston_params* params, int M, const doub
   B200SV_REQUIRE(scheme == B200SV_HESTON_EULER_FLOOR || scheme == B200SV_HESTON_QE, "unknown Heston scheme");
   return mc_chain_host<1>(nullptr, params, M, ttms, forwards, discfactors, nullptr, offsets, strikes, types, nb_path,
                           nb_steps_per_year, 1, variable_type, seed, flags, prices_out, stderr_out, scheme);
+}
+
+int b200sv_logsv_mc_chain_batch(const b200sv_logsv_params* params, int B, int M, const double* ttms, const double* forwards,
+                                const double* discfactors, const double* etas, const int* offsets, const double* strikes,
+                                const int8_t* types, long long nb_path, int nb_steps_per_year, int is_spot_measure, uint64_t seed,
+                                int flags, double* prices_out, double* stderr_out, double* ivols_out) {
+  B200SV_REQUIRE(params && ttms && forwards && discfactors && offsets && prices_out && stderr_out, "null pointer");
+  return mc_chain_host<0>(params, nullptr, M, ttms, forwards, discfactors, etas, offsets, strikes, types, nb_path, nb_steps_per_year,
+                          is_spot_measure, B200SV_LOG_RETURN, seed, flags, prices_out, stderr_out, 0, B, ivols_out);
+}
+
+int b200sv_heston_mc_chain_batch(const b200sv_heston_params* params, int B, int M, const double* ttms, const double* forwards,
+                                 const double* discfactors, const int* offsets, const double* strikes, const int8_t* types,
+                                 long long nb_path, int nb_steps_per_year, uint64_t seed, int flags, int scheme, double* prices_out,
+                                 double* stderr_out, double* ivols_out) {
+  B200SV_REQUIRE(params && ttms && forwards && discfactors && offsets && prices_out && stderr_out, "null pointer");
+  B200SV_REQUIRE(scheme == B200SV_HESTON_EULER_FLOOR || scheme == B200SV_HESTON_QE, "unknown Heston scheme");
+  return mc_chain_host<1>(nullptr, params, M, ttms, forwards, discfactors, nullptr, offsets, strikes, types, nb_path, nb_steps_per_year, 1,
+                          B200SV_LOG_RETURN, seed, flags, prices_out, stderr_out, scheme, B, ivols_out);
 }
 
 int b200sv_logsv_terminal(const b200sv_logsv_params* params, double ttm, long long nb_path, int nb_steps_per_year,

@@ -79,6 +79,42 @@ def heston_mc_chain(params: C.HestonParamsC, ttms, forwards, discfactors, strike
     return C.split_chain(prices, offsets), C.split_chain(stds, offsets)
 
 
+def logsv_mc_chain_batch(params_list: Sequence[C.LogsvParamsC], ttms, forwards, discfactors, etas, strikes_ttms, optiontypes_ttms,
+                         nb_path: int, nb_steps_per_year: int, is_spot_measure: bool, seed: int, flags: int, with_ivols: bool = True):
+    """B parameter sets through the fused chain MC on the SAME seed in one call -> (prices, std errors, ivols | None), each [B, J]."""
+    M, ttms, forwards, discfactors, offsets, strikes, types = _chain_arrays(ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms)
+    B = len(params_list)
+    arr = (C.LogsvParamsC * B)(*params_list)
+    etas_c = None
+    if etas is not None:
+        etas_c = np.ascontiguousarray(etas, dtype=np.float64)
+        if etas_c.shape != (B, M):
+            raise ValueError(f"etas must have shape ({B}, {M})")
+    J = strikes.shape[0]
+    prices, stds = np.empty((B, J)), np.empty((B, J))
+    ivols = np.empty((B, J)) if with_ivols else None
+    C.call("b200sv_logsv_mc_chain_batch", arr, B, M, C.dptr(ttms), C.dptr(forwards), C.dptr(discfactors),
+           C.dptr(etas_c) if etas_c is not None else None, C.iptr(offsets), C.dptr(strikes), C.i8ptr(types), int(nb_path),
+           int(nb_steps_per_year), int(bool(is_spot_measure)), int(seed) & 0xFFFFFFFFFFFFFFFF, int(flags), C.dptr(prices), C.dptr(stds),
+           C.dptr(ivols) if with_ivols else None)
+    return prices, stds, ivols
+
+
+def heston_mc_chain_batch(params_list: Sequence[C.HestonParamsC], ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms,
+                          nb_path: int, nb_steps_per_year: int, seed: int, flags: int, scheme: int = C.HESTON_EULER_FLOOR,
+                          with_ivols: bool = True):
+    M, ttms, forwards, discfactors, offsets, strikes, types = _chain_arrays(ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms)
+    B = len(params_list)
+    arr = (C.HestonParamsC * B)(*params_list)
+    J = strikes.shape[0]
+    prices, stds = np.empty((B, J)), np.empty((B, J))
+    ivols = np.empty((B, J)) if with_ivols else None
+    C.call("b200sv_heston_mc_chain_batch", arr, B, M, C.dptr(ttms), C.dptr(forwards), C.dptr(discfactors), C.iptr(offsets), C.dptr(strikes),
+           C.i8ptr(types), int(nb_path), int(nb_steps_per_year), int(seed) & 0xFFFFFFFFFFFFFFFF, int(flags), int(scheme), C.dptr(prices),
+           C.dptr(stds), C.dptr(ivols) if with_ivols else None)
+    return prices, stds, ivols
+
+
 def logsv_terminal(params: C.LogsvParamsC, ttm: float, nb_path: int, nb_steps_per_year: int, is_spot_measure: bool, eta: float,
                    seed: int, flags: int):
     x, s, q = np.empty(nb_path), np.empty(nb_path), np.empty(nb_path)

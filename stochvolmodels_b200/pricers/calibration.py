@@ -12,7 +12,11 @@ and the Black inversion fused, one launch pair, one D2H copy), so the objective 
 SLSQP's own default (``eps = 1.4901161193847656e-08``, absolute, flipped at an upper bound), so the gradient is the number scipy would
 have computed from the same objective.
 
-The MC engine (:251-266) prices each of the n+1 sets with the device-resident fixed normals (``DeviceRandoms``).
+The MC engine (:251-266) has two sources of fixed normals: ``mc_randoms="numpy"`` (default) draws them exactly as the reference does
+(``np.random.RandomState(seed)``, :1051-1074), keeps them resident in HBM (``DeviceRandoms``) and prices each of the n+1 sets with the
+fixed-random stepper -- the same objective values as the reference for the same seed; ``mc_randoms="philox"`` prices the n+1 sets in one
+``b200sv_logsv_mc_chain_batch`` call in which the counter-based generator re-draws identical normals for every set (nothing stored or
+streamed; statistically equivalent objective, different sample).
 """
 from __future__ import annotations
 
@@ -203,7 +207,7 @@ def build_logsv_constraints(codec: LogSvParameterCodec, constraints_type: Constr
 def calibrate_logsv(pricer, option_chain, params0, params_min, params_max, is_vega_weighted: bool, is_unit_ttm_vega: bool,
                     model_calibration_type: LogsvModelCalibrationType, constraints_type: ConstraintsType,
                     calibration_engine: CalibrationEngine, nb_path: int, nb_steps: int, seed: int, is_spot_measure: bool = True,
-                    disp: bool = False, return_info: bool = False, fd_step: Optional[float] = None):
+                    disp: bool = False, return_info: bool = False, fd_step: Optional[float] = None, mc_randoms: str = "numpy"):
     from .logsv_pricer import (DeviceRandoms, _fixed_randoms_chain_device, _params_c, get_randoms_for_chain_valuation)
     if model_calibration_type == LogsvModelCalibrationType.PARAMS_WITH_VARSWAP_FIT:
         raise NotImplementedError("PARAMS_WITH_VARSWAP_FIT needs the vol-moments backbone fit (pricers/logsv/vol_moments_ode.py), out of scope")
@@ -223,7 +227,19 @@ def calibrate_logsv(pricer, option_chain, params0, params_min, params_max, is_ve
                                                       etas, option_chain.strikes_ttms, option_chain.optiontypes_ttms,
                                                       is_spot_measure=is_spot_measure, vol_scaler=vol_scaler)
             return ivols
+    elif calibration_engine == CalibrationEngine.MC and mc_randoms == "philox":
+        flags = engine.mc_flags("fp64", "fp32")
+
+        def batch_vols(points: np.ndarray) -> np.ndarray:
+            sets = [codec.parse(p) for p in points]
+            etas = np.array([s.get_vol_backbone_etas(ttms=ttms) for s in sets], dtype=float)
+            _, _, ivols = engine.logsv_mc_chain_batch([_params_c(s) for s in sets], ttms, option_chain.forwards, option_chain.discfactors, etas,
+                                                      option_chain.strikes_ttms, option_chain.optiontypes_ttms, nb_path, nb_steps,
+                                                      is_spot_measure, seed, flags)
+            return ivols
     elif calibration_engine == CalibrationEngine.MC:
+        if mc_randoms != "numpy":
+            raise ValueError("mc_randoms must be 'numpy' or 'philox'")
         rnd = get_randoms_for_chain_valuation(ttms=ttms, nb_path=nb_path, nb_steps_per_year=nb_steps, seed=seed, device=True)
         assert isinstance(rnd, DeviceRandoms)
 

@@ -131,7 +131,8 @@ class LogSVPricer(ModelPricer):
         return calibrate_logsv(self, option_chain, params0, params_min, params_max, is_vega_weighted, is_unit_ttm_vega,
                                model_calibration_type, constraints_type, calibration_engine, nb_path, nb_steps, seed,
                                is_spot_measure=kwargs.get("is_spot_measure", True), disp=bool(kwargs.get("disp", False)),
-                               return_info=bool(kwargs.get("return_info", False)), fd_step=kwargs.get("fd_step"))
+                               return_info=bool(kwargs.get("return_info", False)), fd_step=kwargs.get("fd_step"),
+                               mc_randoms=kwargs.get("mc_randoms", "numpy"))
 
     @timer
     def model_mc_price_chain(self, option_chain: OptionChain, params: LogSvParams, is_spot_measure: bool = True,

@@ -166,3 +166,49 @@ def test_logsv_calibration_mc_engine_recovers_own_market(cuda_lib):
     fit_prices, _ = _fixed_randoms_chain_device(rnd, ttms, fw, np.ones(2), [K5, K5], [T5, T5], _params_c(fit), np.ones(2), True, 1, True)
     fit_vols = flat.compute_model_ivols_from_chain_data(fit_prices)
     np.testing.assert_allclose(np.array(fit_vols), np.array(vols), atol=5e-3)
+
+
+def test_mc_chain_batch_rows_equal_single_calls_bitwise(cuda_lib):
+    """b200sv_*_mc_chain_batch: row b == the single-set fused chain on the same seed; fused ivols == separate Black inversion."""
+    from stochvolmodels_b200 import _capi as C, engine
+    ttms, fw, df = np.array([0.1, 0.3]), np.array([1.0, 1.01]), np.array([1.0, 0.99])
+    strikes, types = [K5, K5[:3]], [T5, T5[:3]]
+    sets = _sets()[:4]
+    etas = np.array([[1.0, 0.9]] * 4) * np.linspace(0.9, 1.1, 4)[:, None]
+    flags = engine.mc_flags("fp64", "fp32")
+    for spot in (True, False):
+        p, e, iv = engine.logsv_mc_chain_batch([engine.logsv_params_c(*s) for s in sets], ttms, fw, df, etas, strikes, types, 100_000, 360, spot, 42, flags)
+        for b, s in enumerate(sets):
+            ps, es = engine.logsv_mc_chain(engine.logsv_params_c(*s), ttms, fw, df, etas[b], strikes, types, 100_000, 360, spot, 1, 42, flags)
+            np.testing.assert_array_equal(p[b], np.concatenate(ps))
+            np.testing.assert_array_equal(e[b], np.concatenate(es))
+            np.testing.assert_array_equal(iv[b], np.concatenate(engine.bsm_implied_vols(ttms, fw, df, strikes, types, ps)))
+    hsets = [np.array([0.6, 0.8, 3.0, -0.3, 1.1]) * f for f in (1.0, 1.1, 0.9)]
+    for scheme in (C.HESTON_EULER_FLOOR, C.HESTON_QE):
+        p, e, iv = engine.heston_mc_chain_batch([engine.heston_params_c(*s) for s in hsets], ttms, fw, df, strikes, types, 100_000, 360, 7, flags, scheme)
+        for b, s in enumerate(hsets):
+            ps, es = engine.heston_mc_chain(engine.heston_params_c(*s), ttms, fw, df, strikes, types, 100_000, 360, 1, 7, flags, scheme)
+            np.testing.assert_array_equal(p[b], np.concatenate(ps))
+            np.testing.assert_array_equal(iv[b], np.concatenate(engine.bsm_implied_vols(ttms, fw, df, strikes, types, ps)))
+
+
+def test_logsv_calibration_mc_engine_philox_common_random_numbers(cuda_lib):
+    """MC engine on the counter-based generator: the market is produced by the same seed, so the objective has an exact zero at the
+    generating parameters and SLSQP must find (near) it; one batched call per evaluation."""
+    from stochvolmodels_b200 import CalibrationEngine, LogSvParams, LogSVPricer, LogsvModelCalibrationType, OptionChain, engine
+    from stochvolmodels_b200.pricers.logsv_pricer import _params_c
+    ttms, fw = np.array([1.0 / 12.0, 0.25]), np.ones(2)
+    truth = LogSvParams(sigma0=0.9, theta=1.0, kappa1=4.0, kappa2=4.0, beta=0.3, volvol=1.5)
+    _, _, iv = engine.logsv_mc_chain_batch([_params_c(truth)], ttms, fw, np.ones(2), None, [K5, K5], [T5, T5], 200_000, 360, True, 10,
+                                           engine.mc_flags("fp64", "fp32"))
+    vols = [iv[0, :5].copy(), iv[0, 5:].copy()]
+    chain = OptionChain(ttms=ttms, forwards=fw, strikes_ttms=[K5, K5], optiontypes_ttms=[T5, T5], ids=np.array(["a", "b"]),
+                        bid_ivs=vols, ask_ivs=[v.copy() for v in vols])
+    start = LogSvParams(sigma0=0.8, theta=0.9, kappa1=4.0, kappa2=4.0, beta=0.1, volvol=1.2)
+    fit, info = LogSVPricer().calibrate_model_params_to_chain(chain, start, model_calibration_type=LogsvModelCalibrationType.PARAMS4,
+                                                              calibration_engine=CalibrationEngine.MC, nb_path=200_000, nb_steps=360, seed=10,
+                                                              mc_randoms="philox", return_info=True)
+    assert info["fun"] < 1e-5
+    _, _, fit_iv = engine.logsv_mc_chain_batch([_params_c(fit)], ttms, fw, np.ones(2), None, [K5, K5], [T5, T5], 200_000, 360, True, 10,
+                                               engine.mc_flags("fp64", "fp32"))
+    np.testing.assert_allclose(fit_iv[0], iv[0], atol=5e-3)

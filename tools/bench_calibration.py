@@ -42,5 +42,16 @@ for ctype in (LogsvModelCalibrationType.PARAMS4, LogsvModelCalibrationType.PARAM
     dt = time.perf_counter() - t
     print(f"calibration {ctype.name}: {dt * 1e3:.1f} ms, {info['nit']} SLSQP iterations, {info['nb_batches']} batched GPU evaluations, "
           f"objective {info['fun']:.2e}; fit {fit.to_str()}")
+# MC engine: numpy normals resident in HBM vs Philox common random numbers (one batched call per evaluation)
+from stochvolmodels_b200 import CalibrationEngine
+for rnd in ("numpy", "philox"):
+    kw = dict(model_calibration_type=LogsvModelCalibrationType.PARAMS4, calibration_engine=CalibrationEngine.MC, nb_path=100000, nb_steps=360,
+              seed=10, mc_randoms=rnd)
+    pricer.calibrate_model_params_to_chain(cm, start, **kw)
+    t = time.perf_counter()
+    fit, info = pricer.calibrate_model_params_to_chain(cm, start, return_info=True, **kw)
+    dt = time.perf_counter() - t
+    print(f"calibration PARAMS4, MC engine 1e5 paths, {rnd} normals: {dt * 1e3:.1f} ms ({info['nit']} iterations, {info['nb_batches']} evaluations of 5 "
+          f"chains, objective {info['fun']:.2e}); fit {fit.to_str()}")
 print("# reference: one objective evaluation = one CPU chain pricing = 7.6 s on this chain (profiles/r01_mgf_bench.txt); SLSQP needs "
       "(n+1) per iteration")
