@@ -19,7 +19,7 @@ for name, pricer, params, kw in (("logsv", LogSVPricer(), LOGSV_BTC_PARAMS, dict
     p_c, e_c = pricer.model_mc_price_chain(chain, params, nb_path=N, seed=123, exchange="collective", **kw)  # sharded, NCCL all-reduce
     same = all(np.array_equal(a, b) for a, b in zip(p_d, p_c)) and all(np.array_equal(a, b) for a, b in zip(e_d, e_c))
     if rank == 0:
-        print(f"{name}: p2p exchange == NCCL exchange bitwise: {same}", flush=True)
+        print(f"{name}: p2p exchange == NCCL exchange bitwise: {same}" + ("" if world == 2 else "  (only expected at 2 ranks: NCCL sums in its own order)"), flush=True)
     gathered = [None] * world
     dist.all_gather_object(gathered, np.concatenate(p_d).tobytes())
     ok &= all(g == gathered[0] for g in gathered)            # every rank holds the same bits
