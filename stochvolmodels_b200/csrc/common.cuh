@@ -80,4 +80,19 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double* smem /* NV * 
   __syncthreads();
 }
 
+// cudaMallocAsync returns freed blocks to the OS at the next synchronisation unless the pool's release threshold is raised;
+// the chain entry points allocate GBs of path state per call, so keep it cached (set once per device).
+inline void ensure_pool_threshold() {
+  static thread_local int done_for = -1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev == done_for) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long thr = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  done_for = dev;
+}
+
+
 }  // namespace b200sv

@@ -46,6 +46,7 @@ extern "C" int b200sv_bsm_implied_vols(int M, const double* ttms, const double* 
       q[j - offsets[0]] = QuoteSpec{forwards[m], strikes[j], ttms[m], discfactors[m], prices[j - offsets[0]], (int)types[j]};
     }
   cudaStream_t st = 0;
+  ensure_pool_threshold();
   QuoteSpec* dq = nullptr;
   double* dv = nullptr;
   B200SV_CUDA(cudaMallocAsync(&dq, sizeof(QuoteSpec) * n, st));

@@ -709,20 +709,6 @@ __global__ void exp_pair_kernel(const double* __restrict__ L, long long n, doubl
 // --------------------------------------------------------------------------------------------------------------------
 // host side
 // --------------------------------------------------------------------------------------------------------------------
-// cudaMallocAsync returns freed blocks to the OS at the next synchronisation unless the pool's release threshold is raised;
-// the chain entry points allocate GBs of path state per call, so keep it cached (set once per device).
-static void ensure_pool_threshold() {
-  static thread_local int done_for = -1;
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev == done_for) return;
-  cudaMemPool_t pool;
-  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-    unsigned long long thr = ~0ull;
-    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-  }
-  done_for = dev;
-}
-
 // host-side state of one rank's mailbox (p2p.cuh); created / connected through the b200sv_p2p_* entry points
 struct P2pCtx {
   int world, rank, kmax;

@@ -17,6 +17,7 @@
 // A second kernel does the Simpson-weighted Fourier sums, one CTA per strike, fixed-order fp64 reduction.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "../../include/b200sv.h"
@@ -362,6 +363,222 @@ __global__ void __launch_bounds__(TPB) logsv_mgf_kernel(const cd* __restrict__ p
 }
 
 // --------------------------------------------------------------------------------------------------------------------
+// Lane-parallel variant for the latency regime (one chain, P = 1000): the N components of A are spread over N lanes of a group of LPP
+// lanes (8 for N = 5, 4 for N = 3), so one Runge-Kutta stage costs each lane ONE row of A'MA + LA + H (<= 6 quadratic + 4 linear terms)
+// instead of all N rows -- about a third of the dependent instruction stream of the thread-per-point kernel, which is what bounds a
+// single chain pricing (one resident warp per SM).  The stage vector is exchanged through shared memory (one 16-byte store, <= 5 loads,
+// __syncwarp); each lane keeps its own 7 stage derivatives in registers.  Step-size control is replicated in every lane of a point from
+// an error norm summed in component order, i.e. the same accepted steps as the thread-per-point kernel; all points of a warp iterate
+// together (finished points idle) so the warp-level barriers stay converged.  Row k accumulates its terms in the order of rhs<>().
+// --------------------------------------------------------------------------------------------------------------------
+template <int N>
+struct LaneRow {        // row k of the right-hand side in table form
+  cd l[4];              // linear coefficients (complex; real ones carry im = 0)
+  double q[6];          // quadratic coefficients (already doubled for off-diagonal pairs)
+  cd h;
+  int li[4], qi[6], qj[6];
+  int nl, nq;
+};
+
+template <int N>
+__device__ __forceinline__ LaneRow<N> make_lane_row(int k, const LogsvModel& m, cd phi, cd psi) {
+  const Coef c = make_coef(m, phi, psi);
+  const double v2 = m.v2, qv = m.qv, qv2 = m.qv2;
+  LaneRow<N> r;
+  // padding entries: coefficient 0 on a component every row already depends on (rows 0-3: A1, row 4: A3), so that a non-finite value
+  // cannot enter a row through a padded term unless the row is non-finite anyway
+  const int pad = k == 4 ? 3 : 1;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) { r.l[t] = mk(0.0); r.li[t] = pad; }
+#pragma unroll
+  for (int t = 0; t < 6; ++t) { r.q[t] = 0.0; r.qi[t] = pad; r.qj[t] = pad; }
+  r.h = mk(0.0);
+  r.nl = r.nq = 0;
+  auto Q = [&](double coef, int i, int j) { r.q[r.nq] = coef; r.qi[r.nq] = i; r.qj[r.nq] = j; ++r.nq; };
+  auto L = [&](cd coef, int i) { r.l[r.nl] = coef; r.li[r.nl] = i; ++r.nl; };
+  // same term order as rhs<>() above (affine_expansion.py:139-183)
+  if (k == 0) {
+    Q(0.5 * qv2, 1, 1); L(c.l01, 1); L(mk(qv2), 2); r.h = c.h0;
+  } else if (k == 1) {
+    Q(qv, 1, 1); Q(2.0 * qv2, 1, 2); L(c.l11, 1); L(c.l12, 2);
+    if (N == 5) L(mk(3.0 * qv2), 3);
+    r.h = c.h1;
+  } else if (k == 2) {
+    Q(0.5 * v2, 1, 1); Q(2.0 * qv2, 2, 2); Q(4.0 * qv, 1, 2);
+    if (N == 5) Q(3.0 * qv2, 1, 3);
+    L(c.l21, 1); L(c.l22, 2);
+    if (N == 5) { L(c.l23, 3); L(mk(6.0 * qv2), 4); }
+    r.h = c.h2;
+  } else if (k == 3) {
+    Q(4.0 * qv, 2, 2); Q(2.0 * v2, 1, 2); Q(6.0 * qv, 1, 3); Q(4.0 * qv2, 1, 4); Q(6.0 * qv2, 2, 3);
+    L(c.l32, 2); L(c.l33, 3); L(c.l34, 4);
+  } else if (k == 4) {
+    Q(2.0 * v2, 2, 2); Q(4.5 * qv2, 3, 3); Q(3.0 * v2, 1, 3); Q(8.0 * qv, 1, 4); Q(12.0 * qv, 2, 3); Q(8.0 * qv2, 2, 4);
+    L(c.l43, 3); L(c.l44, 4);
+  }
+  return r;
+}
+
+// f_k(Y) for this lane's row; Y = the point's stage vector in shared memory.  Branch-free: rows shorter than 6 + 4 terms are padded with
+// zero coefficients on an entry the row already reads (make_lane_row), so every lane of the warp runs the same instruction stream.
+template <int N>
+__device__ __forceinline__ cd lane_rhs(const LaneRow<N>& r, const cd* __restrict__ Y) {
+  cd acc = r.q[0] * (Y[r.qi[0]] * Y[r.qj[0]]);
+#pragma unroll
+  for (int t = 1; t < (N == 5 ? 6 : 3); ++t) acc = acc + r.q[t] * (Y[r.qi[t]] * Y[r.qj[t]]);
+#pragma unroll
+  for (int t = 0; t < (N == 5 ? 4 : 2); ++t) acc = acc + r.l[t] * Y[r.li[t]];
+  return acc + r.h;
+}
+
+constexpr int kLaneWarpsPerBlock = 1;
+
+template <int N>
+__global__ void __launch_bounds__(32 * kLaneWarpsPerBlock, 1) logsv_mgf_lanes_kernel(
+    const cd* __restrict__ phi, const cd* __restrict__ psi, int P, int M, const ChainSpec* __restrict__ spec, const cd* __restrict__ a_in,
+    cd* __restrict__ a_out, cd* __restrict__ log_mgf, double y, int* __restrict__ status_out, const double* __restrict__ yb, int phi_stride) {
+  constexpr int LPP = N == 5 ? 8 : 4;             // lanes per grid point
+  constexpr int PPW = 32 / LPP;                   // points per warp
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr double B[6] = {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84};
+  constexpr double E[7] = {-71.0 / 57600, 0, 71.0 / 16695, -71.0 / 1920, 17253.0 / 339200, -22.0 / 525, 1.0 / 40};
+  constexpr double A[6][5] = {{0, 0, 0, 0, 0},
+                              {1.0 / 5, 0, 0, 0, 0},
+                              {3.0 / 40, 9.0 / 40, 0, 0, 0},
+                              {44.0 / 45, -56.0 / 15, 32.0 / 9, 0, 0},
+                              {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729, 0},
+                              {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656}};
+  __shared__ cd Ysh[kLaneWarpsPerBlock][PPW][N];
+  __shared__ double Nsh[kLaneWarpsPerBlock][PPW][N];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int g = lane / LPP, k = lane % LPP;        // point within the warp, component
+  const int p = (blockIdx.x * kLaneWarpsPerBlock + wib) * PPW + g;
+  {
+    const size_t b = blockIdx.y;
+    spec += b * M;
+    phi += b * (size_t)phi_stride;
+    a_out += b * (size_t)M * P * N;
+    log_mgf += b * (size_t)M * P;
+    if (status_out) status_out += b * (size_t)P;
+    if (yb) y = yb[b];
+  }
+  const bool valid = p < P, comp = k < N, mine = valid && comp;
+  const int pc = valid ? p : P - 1;                // out-of-range groups shadow the last point (never stored)
+  const int kc = comp ? k : 0;
+  cd* Y = &Ysh[wib][g][0];
+  double* Nn = &Nsh[wib][g][0];
+  const cd ph = phi[pc], ps = psi ? psi[pc] : mk(0.0);
+  cd yk = a_in ? a_in[(size_t)pc * N + kc] : mk(0.0);
+  const double y2 = y * y;
+  const double ys[5] = {1.0, y, y2, y2 * y, y2 * y2};
+  int st_all = 0;
+
+  // sum over the point's components, in component order, of this lane's value (identical in every lane of the point)
+  auto point_norm = [&](cd v, double inv_scale) -> double {
+    const double re = v.re * inv_scale, im = v.im * inv_scale;
+    __syncwarp(FULL);
+    if (comp) Nn[k] = re * re + im * im;
+    __syncwarp(FULL);
+    double s = 0.0;
+#pragma unroll
+    for (int c = 0; c < N; ++c) s += Nn[c];
+    return sqrt(s) * rsqrt((double)N);
+  };
+  // f_k at the point's vector whose k-th entry is `mine_k`
+  auto eval = [&](const LaneRow<N>& row, cd mine_k) -> cd {
+    __syncwarp(FULL);
+    if (comp) Y[k] = mine_k;
+    __syncwarp(FULL);
+    return lane_rhs<N>(row, Y);
+  };
+
+  for (int mm = 0; mm < M; ++mm) {
+    const LogsvModel model = spec[mm].model;
+    const double T = spec[mm].dtau;
+    const LaneRow<N> row = make_lane_row<N>(kc, model, ph, ps);
+    cd K[7];
+    K[0] = eval(row, yk);
+    double h_abs;
+    {   // select_initial_step (scipy/integrate/_ivp/common.py:109-134)
+      const double inv_scale = 1.0 / (kAtol + cmod(yk) * kRtol);
+      const double d0 = point_norm(yk, inv_scale), d1 = point_norm(K[0], inv_scale);
+      double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+      h0 = fmin(h0, T);
+      const cd f1 = eval(row, yk + h0 * K[0]);
+      const double d2 = point_norm(f1 - K[0], inv_scale) / h0;
+      const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : exp(0.2 * log(0.01 / fmax(d1, d2)));
+      h_abs = fmin(fmin(100.0 * h0, h1), T);
+    }
+    double t = 0.0, min_step = 0.0;
+    bool done = !(t < T), in_step = false, rejected = false;
+    int status = 0;
+    for (int guard = 0; guard < 1000000 && __any_sync(FULL, !done); ++guard) {
+      if (!done && !in_step) {                      // head of the outer loop of rk.py:111-170
+        min_step = 10.0 * (__longlong_as_double(__double_as_longlong(t) + 1) - t);
+        if (h_abs < min_step) h_abs = min_step;
+        rejected = false;
+        in_step = true;
+      }
+      if (!done && h_abs < min_step) {
+        status = 1;
+        done = true;
+      }
+      double t_new = t + h_abs;
+      if (t_new - T > 0.0) t_new = T;
+      const double h = t_new - t;
+      if (!done) h_abs = fabs(h);
+#pragma unroll
+      for (int s = 1; s < 6; ++s) {
+        cd acc = K[0] * A[s][0];
+#pragma unroll
+        for (int jj = 1; jj < 5; ++jj)
+          if (jj < s) acc = acc + K[jj] * A[s][jj];
+        K[s] = eval(row, yk + acc * h);
+      }
+      cd acc = K[0] * B[0];
+#pragma unroll
+      for (int jj = 2; jj < 6; ++jj) acc = acc + K[jj] * B[jj];
+      const cd yn = yk + h * acc;
+      K[6] = eval(row, yn);
+      const double inv_scale = 1.0 / (kAtol + fmax(cmod(yk), cmod(yn)) * kRtol);
+      cd e = K[0] * E[0];
+#pragma unroll
+      for (int jj = 2; jj < 6; ++jj) e = e + K[jj] * E[jj];
+      const cd err = (e + K[6] * E[6]) * h;
+      const double en = point_norm(err, inv_scale);
+      if (!done) {
+        if (en < 1.0) {
+          double factor = en == 0.0 ? 10.0 : fmin(10.0, 0.9 * pow_m02(en));
+          if (rejected) factor = fmin(1.0, factor);
+          h_abs *= factor;
+          t = t_new;
+          yk = yn;
+          K[0] = K[6];                               // FSAL
+          in_step = false;
+          done = !(t < T);
+        } else {
+          h_abs *= fmax(0.2, 0.9 * pow_m02(en));
+          rejected = true;
+        }
+      }
+    }
+    st_all |= status;
+    // outputs of this maturity: a_t1 and log_mgf = sum_k A_k ys_k in component order (affine_expansion.py:674-685)
+    __syncwarp(FULL);
+    if (comp) Y[k] = yk;
+    __syncwarp(FULL);
+    if (mine) a_out[((size_t)mm * P + p) * N + k] = yk;
+    if (valid && k == 0) {
+      cd lm = mk(0.0);
+#pragma unroll
+      for (int c = 0; c < N; ++c) lm = lm + Y[c] * ys[c];
+      log_mgf[(size_t)mm * P + p] = lm;
+    }
+  }
+  if (status_out && valid && k == 0) status_out[p] = st_all;
+}
+
+// --------------------------------------------------------------------------------------------------------------------
 // Heston closed form: pricers/heston_pricer.py:199-214, chained over maturities with (a, b) carried in registers
 // --------------------------------------------------------------------------------------------------------------------
 __global__ void heston_mgf_kernel(const cd* __restrict__ phi, const cd* __restrict__ psi, int P, int M,
@@ -510,10 +727,28 @@ static int launched(const char* what) {
   return 0;
 }
 
+// Latency regime (few grid points in total): lane-parallel kernel; throughput regime (batches, the 40000-point psi grid): one thread per
+// point.  B200SV_MGF_LANES=0/1 overrides the choice (A/B timing in tools/bench_mgf.py).
+static bool use_lane_kernel(long long points) {
+  static const int forced = [] {
+    const char* e = getenv("B200SV_MGF_LANES");
+    return e ? atoi(e) : -1;
+  }();
+  if (forced >= 0) return forced != 0;
+  return points <= 8192;
+}
+
 template <int N>
 static void launch_logsv_mgf(int tpb, int nb, cudaStream_t st, const cd* phi, const cd* psi, int P, int M, const ChainSpec* spec,
                              const cd* a_in, cd* a_out, cd* lm, double y, int* status, int B = 1, const double* yb = nullptr,
                              int phi_stride = 0) {
+  if (use_lane_kernel((long long)P * B)) {
+    constexpr int PPW = 32 / (N == 5 ? 8 : 4);
+    const int per_block = PPW * kLaneWarpsPerBlock;
+    logsv_mgf_lanes_kernel<N><<<dim3((P + per_block - 1) / per_block, B), 32 * kLaneWarpsPerBlock, 0, st>>>(phi, psi, P, M, spec, a_in, a_out, lm, y,
+                                                                                                      status, yb, phi_stride);
+    return;
+  }
   const dim3 grid(nb, B);
   switch (tpb) {
     case 4: logsv_mgf_kernel<N, 4><<<grid, 4, 0, st>>>(phi, psi, P, M, spec, a_in, a_out, lm, y, status, nullptr, yb, phi_stride); break;
@@ -640,6 +875,7 @@ int b200sv_logsv_price_chain(const b200sv_logsv_params* params, int M, const dou
       qs[j - offsets[0]] = SumSpec{strikes[j] * ttms[m], discfactors[m], ttms[m], (int)types[j], m};
     }
   cudaStream_t st = 0;
+  ensure_pool_threshold();
   DevBuf d_phi(st), d_psi(st), d_spec(st), d_a(st), d_lm(st), d_ss(st), d_pr(st), d_stat(st);
   B200SV_CUDA(d_phi.alloc(sizeof(cd) * P));
   B200SV_CUDA(d_psi.alloc(sizeof(cd) * P));
@@ -712,6 +948,7 @@ int b200sv_heston_price_chain(const b200sv_heston_params* params, int M, const d
       qs[j - offsets[0]] = SumSpec{strikes[j] * ttms[m], discfactors[m], ttms[m], (int)types[j], m};
     }
   cudaStream_t st = 0;
+  ensure_pool_threshold();
   DevBuf d_phi(st), d_psi(st), d_dt(st), d_lm(st), d_ss(st), d_pr(st);
   B200SV_CUDA(d_phi.alloc(sizeof(cd) * P));
   B200SV_CUDA(d_psi.alloc(sizeof(cd) * P));
@@ -795,6 +1032,7 @@ int b200sv_logsv_price_chain_batch(const b200sv_logsv_params* params, int B, int
     for (int m = 0; m < M; ++m) spec[(size_t)b * M + m] = ChainSpec{dtaus[m], make_model(params[b], etas ? etas[(size_t)b * M + m] : 1.0, spot)};
   }
   cudaStream_t st = 0;
+  ensure_pool_threshold();
   DevBuf d_phi(st), d_spec(st), d_y(st), d_a(st), d_lm(st), d_ss(st), d_pr(st), d_iv(st);
   const size_t nq = (size_t)B * Jtot;
   B200SV_CUDA(d_phi.alloc(sizeof(cd) * (size_t)G * P));
@@ -844,6 +1082,7 @@ int b200sv_heston_price_chain_batch(const b200sv_heston_params* params, int B, i
     phi.insert(phi.end(), one.begin(), one.end());
   }
   cudaStream_t st = 0;
+  ensure_pool_threshold();
   DevBuf d_phi(st), d_hp(st), d_dt(st), d_lm(st), d_ss(st), d_pr(st), d_iv(st);
   const size_t nq = (size_t)B * Jtot;
   B200SV_CUDA(d_phi.alloc(sizeof(cd) * (size_t)G * P));
@@ -880,6 +1119,7 @@ int b200sv_logsv_mgf_grid(const double* phi, const double* psi, int P, double dt
   const int N = expansion_order == B200SV_ORDER_FIRST ? 3 : 5;
   ChainSpec spec{dtau, make_model(*params, eta, is_spot_measure != 0)};
   cudaStream_t st = 0;
+  ensure_pool_threshold();
   DevBuf d_phi(st), d_psi(st), d_spec(st), d_a0(st), d_a1(st), d_lm(st);
   B200SV_CUDA(d_phi.alloc(sizeof(cd) * P));
   B200SV_CUDA(d_psi.alloc(sizeof(cd) * P));
@@ -910,6 +1150,7 @@ int b200sv_heston_mgf_grid(const double* phi, const double* psi, int P, double d
   B200SV_REQUIRE(phi && a_inout && b_inout && params && log_mgf_out, "null pointer");
   B200SV_REQUIRE(P >= 1 && dtau > 0.0, "P >= 1, dtau > 0");
   cudaStream_t st = 0;
+  ensure_pool_threshold();
   DevBuf d_phi(st), d_psi(st), d_dt(st), d_a(st), d_b(st), d_a1(st), d_b1(st), d_lm(st);
   B200SV_CUDA(d_phi.alloc(sizeof(cd) * P));
   B200SV_CUDA(d_psi.alloc(sizeof(cd) * P));
@@ -944,6 +1185,7 @@ int b200sv_fourier_vanilla(const double* log_mgf, const double* phi, int P, doub
   std::vector<StrikeSpec> ss(J);
   for (int j = 0; j < J; ++j) ss[j] = StrikeSpec{strikes[j], forward, discfactor, (int)types[j], 0, 1.0, 0};
   cudaStream_t st = 0;
+  ensure_pool_threshold();
   DevBuf d_phi(st), d_lm(st), d_ss(st), d_pr(st);
   B200SV_CUDA(d_phi.alloc(sizeof(cd) * P));
   B200SV_CUDA(d_lm.alloc(sizeof(cd) * P));
@@ -965,6 +1207,7 @@ static int fourier_sum_host(const double* log_mgf, const double* grid, int P, co
                             double* out) {
   const int J = (int)specs.size();
   cudaStream_t st = 0;
+  ensure_pool_threshold();
   DevBuf d_g(st), d_lm(st), d_ss(st), d_pr(st);
   B200SV_CUDA(d_g.alloc(sizeof(cd) * P));
   B200SV_CUDA(d_lm.alloc(sizeof(cd) * P));

@@ -43,6 +43,23 @@ def test_logsv_batch_rows_equal_single_calls_bitwise(cuda_lib, vol_scaler, spot)
     np.testing.assert_array_equal(p1[0], np.concatenate(single))
 
 
+def test_lane_parallel_and_thread_per_point_ode_kernels_agree(cuda_lib):
+    """a 12-set batch (12000 grid points: thread-per-point kernel) against single calls (1000 points: lane-parallel kernel): the two
+    kernels take the same accepted steps and differ only in the last bits of the right-hand side's sums."""
+    from stochvolmodels_b200 import engine
+    ttms, fw, df = np.array([0.1, 0.3, 0.7]), np.array([1.0, 1.01, 1.02]), np.array([1.0, 0.99, 0.98])
+    strikes, types = [K5, K5, K5], [T5, T5, T5]
+    rng = np.random.RandomState(11)
+    base = np.array([1.0, 1.0, 5.0, 5.0, 0.2, 2.0])
+    sets = [base * (1.0 + 0.2 * rng.uniform(-1, 1, 6)) for _ in range(12)]
+    for order in (2, 1):
+        prices, _ = engine.logsv_price_chain_batch([engine.logsv_params_c(*s) for s in sets], ttms, fw, df, None, strikes, types,
+                                                   expansion_order=order, vol_scaler=0.2)
+        for b in (0, 5, 11):
+            single = engine.logsv_price_chain(engine.logsv_params_c(*sets[b]), ttms, fw, df, np.ones(3), strikes, types, True, order, 0.2, 1000, False)
+            np.testing.assert_allclose(prices[b], np.concatenate(single), rtol=1e-12, atol=1e-15)
+
+
 def test_heston_batch_rows_equal_single_calls_bitwise(cuda_lib):
     from stochvolmodels_b200 import engine
     ttms, fw, df = np.array([0.1, 0.3]), np.array([1.0, 1.01]), np.array([1.0, 0.99])

@@ -18,7 +18,7 @@ for B in (1, 6, 32, 128, 512, 2048):
     sets = [engine.logsv_params_c(*(base * (1 + 0.05 * rng.uniform(-1, 1, 6)))) for _ in range(B)]
     call = lambda: engine.logsv_price_chain_batch(sets, chain.ttms, chain.forwards, chain.discfactors, None, chain.strikes_ttms,
                                                   chain.optiontypes_ttms, vol_scaler=0.17)
-    for _ in range(3):
+    for _ in range(10 if B <= 128 else 3):
         call()
     ts = []
     for _ in range(20 if B <= 512 else 5):
