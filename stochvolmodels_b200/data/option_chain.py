@@ -119,6 +119,35 @@ class OptionChain:
             out.append(forward * np.exp(-0.5 * d1 * d1) / np.sqrt(2.0 * np.pi) * np.sqrt(ttm))
         return out
 
+    def get_slice_varswap_strikes(self, floor_with_atm_vols: bool = True):
+        """variance-swap VOL per maturity by static replication from the quoted strip (reference data/option_chain.py:402-426 with
+        utils/var_swap_pricer.py:8-56): K_var = (2/T) sum_i dk_i O(K_i)/K_i^2 - (F/K_atm - 1)^2 / T with Black mid prices O (puts below
+        the forward, calls above), centred strike spacings, floored with the ATM vol.  Host arithmetic; returns a pandas Series."""
+        import pandas as pd
+        from scipy.special import ndtr
+        out = np.zeros_like(self.ttms)
+        for m, (ttm, forward, strikes, vols, types) in enumerate(zip(self.ttms, self.forwards, self.strikes_ttms, self.get_mid_vols(),
+                                                                      self.optiontypes_ttms)):
+            sdev = vols * np.sqrt(ttm)
+            d1 = np.log(forward / strikes) / sdev + 0.5 * sdev
+            calls = forward * ndtr(d1) - strikes * ndtr(d1 - sdev)
+            prices = np.where(np.asarray(types) == "P", calls - (forward - strikes), calls)
+            is_put = np.asarray(types) == "P"
+            # the reference joins the put and call strips on strike and picks puts below / calls at-or-above the forward
+            table = pd.concat([pd.Series(prices[is_put], index=strikes[is_put], name="puts"),
+                               pd.Series(prices[~is_put], index=strikes[~is_put], name="calls")], axis=1).sort_index()
+            k = table.index.to_numpy()
+            dk = np.empty_like(k)
+            dk[0], dk[-1] = k[1] - k[0], k[-1] - k[-2]
+            dk[1:-1] = 0.5 * (k[2:] - k[:-2])
+            below = k < forward
+            strip = np.where(below, table["puts"].to_numpy(), table["calls"].to_numpy())
+            k_atm = k[~below][0]
+            out[m] = np.sqrt((2.0 * np.nansum(dk * strip / np.square(k)) - np.square(forward / k_atm - 1.0)) / ttm)
+        if floor_with_atm_vols:
+            out = np.maximum(self.get_chain_atm_vols(), out)
+        return pd.Series(out, index=self.ttms)
+
     def compute_model_ivols_from_chain_data(self, model_prices: Sequence[np.ndarray], forwards: np.ndarray = None) -> List[np.ndarray]:
         """invert model prices to Black implied vols for the whole chain in one GPU kernel launch (reference
         data/option_chain.py:327-346 -> third-party ``vanilla_option_pricers``)."""

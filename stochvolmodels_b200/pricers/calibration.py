@@ -37,7 +37,7 @@ class LogsvModelCalibrationType(Enum):
     PARAMS4 = 1                  # sigma0, theta, beta, volvol; kappa1, kappa2 fixed
     PARAMS5 = 2                  # sigma0, theta, kappa1, beta, volvol; kappa2 = kappa1 / theta
     PARAMS6 = 3
-    PARAMS_WITH_VARSWAP_FIT = 4  # needs the vol-moments ODE backbone fit (out of scope here)
+    PARAMS_WITH_VARSWAP_FIT = 4  # beta, volvol; the eta backbone is re-fitted to the chain's variance-swap strikes at every point
 
 
 class ConstraintsType(Enum):
@@ -152,10 +152,16 @@ class LogSvParameterCodec:
     params_min: "LogSvParams"
     params_max: "LogSvParams"
     calibration_type: LogsvModelCalibrationType
+    varswap_strikes: object = None          # pandas Series (PARAMS_WITH_VARSWAP_FIT only)
 
     def parse(self, pars: np.ndarray):
+        from .logsv.vol_moments import fit_vol_backbone_to_varswaps
         from .logsv_pricer import LogSvParams
         p0 = self.params0
+        if self.calibration_type == LogsvModelCalibrationType.PARAMS_WITH_VARSWAP_FIT:
+            out = LogSvParams(sigma0=p0.sigma0, theta=p0.theta, kappa1=p0.kappa1, kappa2=p0.kappa2, beta=pars[0], volvol=pars[1])
+            out.set_vol_backbone(fit_vol_backbone_to_varswaps(out, self.varswap_strikes))     # reference :145-160
+            return out
         if self.calibration_type == LogsvModelCalibrationType.PARAMS4:
             out = LogSvParams(sigma0=pars[0], theta=pars[1], kappa1=p0.kappa1, kappa2=p0.kappa2, beta=pars[2], volvol=pars[3])
         elif self.calibration_type == LogsvModelCalibrationType.PARAMS5:
@@ -171,6 +177,8 @@ class LogSvParameterCodec:
             names = ("sigma0", "theta", "beta", "volvol")
         elif self.calibration_type == LogsvModelCalibrationType.PARAMS5:
             names = ("sigma0", "theta", "kappa1", "beta", "volvol")
+        elif self.calibration_type == LogsvModelCalibrationType.PARAMS_WITH_VARSWAP_FIT:
+            names = ("beta", "volvol")
         else:
             raise NotImplementedError(f"{self.calibration_type}")
         return (np.array([getattr(p0, n) for n in names], dtype=float),
@@ -209,13 +217,13 @@ def calibrate_logsv(pricer, option_chain, params0, params_min, params_max, is_ve
                     calibration_engine: CalibrationEngine, nb_path: int, nb_steps: int, seed: int, is_spot_measure: bool = True,
                     disp: bool = False, return_info: bool = False, fd_step: Optional[float] = None, mc_randoms: str = "numpy"):
     from .logsv_pricer import (DeviceRandoms, _fixed_randoms_chain_device, _params_c, get_randoms_for_chain_valuation)
-    if model_calibration_type == LogsvModelCalibrationType.PARAMS_WITH_VARSWAP_FIT:
-        raise NotImplementedError("PARAMS_WITH_VARSWAP_FIT needs the vol-moments backbone fit (pricers/logsv/vol_moments_ode.py), out of scope")
     vol_scaler = pricer.set_vol_scaler(option_chain=option_chain)
     _, market_vols_ttms = option_chain.get_chain_data_as_xy()
     market_vols = to_flat_np_array(market_vols_ttms)
     weights = calibration_weights(option_chain, market_vols, is_vega_weighted, is_unit_ttm_vega)
-    codec = LogSvParameterCodec(params0, params_min, params_max, model_calibration_type)
+    varswap_strikes = (option_chain.get_slice_varswap_strikes(floor_with_atm_vols=True)
+                       if model_calibration_type == LogsvModelCalibrationType.PARAMS_WITH_VARSWAP_FIT else None)
+    codec = LogSvParameterCodec(params0, params_min, params_max, model_calibration_type, varswap_strikes)
     p0, bounds = codec.initial_and_bounds()
     ttms = option_chain.ttms
 

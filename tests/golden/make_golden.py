@@ -469,9 +469,14 @@ def calibration() -> None:
             out.append(forward * np.exp(-0.5 * d1 * d1) / np.sqrt(2.0 * np.pi) * np.sqrt(ttm))
         return out
     shim.compute_bsm_vegas_ttms = compute_bsm_vegas_ttms
+
+    def compute_bsm_vanilla_slice_prices(ttm, forward, strikes, vols, optiontypes, discfactor=1.0):
+        return np.array([obsm.compute_bsm_vanilla_price(forward, k, ttm, v, str(t), discfactor) for k, v, t in zip(strikes, vols, optiontypes)])
+    shim.compute_bsm_vanilla_slice_prices = compute_bsm_vanilla_slice_prices
     pkg = MagicMock()          # the reference does `import vanilla_option_pricers as bsm`: the two functions it needs live on the package
     pkg.infer_bsm_ivols_from_model_chain_prices = shim.infer_bsm_ivols_from_model_chain_prices
     pkg.compute_bsm_vegas_ttms = shim.compute_bsm_vegas_ttms
+    pkg.compute_bsm_vanilla_slice_prices = shim.compute_bsm_vanilla_slice_prices
     sys.modules["vanilla_option_pricers"] = pkg
     sys.modules["vanilla_option_pricers.bsm"] = shim
     sys.modules["vanilla_option_pricers.bachelier"] = MagicMock()
@@ -510,6 +515,40 @@ def calibration() -> None:
              start=np.array([start.sigma0, start.theta, start.kappa1, start.kappa2, start.beta, start.volvol]),
              fit=np.array([fit.sigma0, fit.theta, fit.kappa1, fit.kappa2, fit.beta, fit.volvol]), fit_vols=np.array(fit_vols),
              vol_scaler=np.array(pricer.set_vol_scaler(option_chain=chain)), ref_seconds=np.array(secs))
+    # ---- LogSV, PARAMS_WITH_VARSWAP_FIT (beta, volvol; eta backbone re-fitted to the chain's var-swap strikes at every point)
+    if "--skip-varswap" not in sys.argv:
+        from stochvolmodels.pricers.logsv import vol_moments_ode as vmo
+        K9 = np.linspace(0.6, 1.4, 9)
+        T9 = np.where(K9 >= 1.0, "C", "P")
+        ttms3 = np.array([0.04, 0.25, 0.5])
+
+        def chain9(vols):
+            return OptionChain(ttms=ttms3, ids=np.array(["2w", "3m", "6m"]), forwards=np.ones(3), strikes_ttms=[K9] * 3, optiontypes_ttms=[T9] * 3,
+                               bid_ivs=[v.copy() for v in vols], ask_ivs=[v.copy() for v in vols])
+        flat9 = chain9([0.8 * np.ones(9)] * 3)
+        market9 = pricer.compute_model_ivols_for_chain(option_chain=flat9, params=truth, vol_scaler=pricer.set_vol_scaler(option_chain=flat9))
+        c9 = chain9([np.asarray(v) * s for v, s in zip(market9, (1.05, 1.0, 0.97))])        # tilt the term structure so that eta != 1
+        vs = c9.get_slice_varswap_strikes(floor_with_atm_vols=True)
+        vs_raw = c9.get_slice_varswap_strikes(floor_with_atm_vols=False)
+        start2 = LogSvParams(sigma0=0.9, theta=1.0, kappa1=4.0, kappa2=4.0, beta=0.1, volvol=1.2)
+        eta0 = vmo.fit_model_vol_backbone_to_varswaps(log_sv_params=start2, varswap_strikes=vs)
+        moments = np.array([vmo.compute_analytic_vol_moments(params=start2, t=t_, n_terms=4) for t_ in (0.0, 0.04, 0.5, 2.0)])
+        int_moments = np.array([vmo.compute_analytic_vol_moments(params=start2, t=t_, n_terms=4, is_qvar=True) for t_ in (0.04, 0.5, 2.0)])
+        qvars = np.array([vmo.compute_analytic_qvar(params=start2, ttm=t_) for t_ in (0.0, 0.04, 0.25, 0.5, 2.0)])
+        t = time.time()
+        fit2 = pricer.calibrate_model_params_to_chain(option_chain=c9, params0=start2,
+                                                      model_calibration_type=lp.LogsvModelCalibrationType.PARAMS_WITH_VARSWAP_FIT)
+        secs2 = time.time() - t
+        fit2_vols = pricer.compute_model_ivols_for_chain(option_chain=c9, params=fit2, vol_scaler=pricer.set_vol_scaler(option_chain=c9))
+        print("logsv varswap fit", fit2, f"{secs2:.1f}s")
+        np.savez(os.path.join(OUT, "calib_logsv_varswap.npz"), ttms=ttms3, forwards=np.ones(3), strikes=K9, types=T9,
+                 market_vols=np.array([np.asarray(v) for v in c9.get_mid_vols()]), start=np.array([0.9, 1.0, 4.0, 4.0, 0.1, 1.2]),
+                 varswap_strikes=vs.to_numpy(), varswap_strikes_raw=vs_raw.to_numpy(), eta_start=eta0.to_numpy(),
+                 lambda4=start2.get_vol_moments_lambda(n_terms=4), moments=moments, int_moments=int_moments, qvars=qvars,
+                 fit=np.array([fit2.sigma0, fit2.theta, fit2.kappa1, fit2.kappa2, fit2.beta, fit2.volvol]),
+                 fit_eta=fit2.vol_backbone.to_numpy(), fit_vols=np.array(fit2_vols), ref_seconds=np.array(secs2))
+        if "--only-varswap" in sys.argv:
+            return
     # ---- Heston
     htruth = hp.HestonParams(v0=0.7, theta=0.9, kappa=3.0, rho=-0.3, volvol=1.2)
     hpr = hp.HestonPricer()

@@ -22,8 +22,12 @@ def test_codec_params4_and_params5():
     np.testing.assert_array_equal(x0, [0.8, 0.9, 4.0, 0.1, 1.2])
     q = c5.parse(np.array([0.5, 0.8, 2.0, 0.7, 0.9]))
     assert q.kappa2 == 2.0 / 0.8                      # kappa2=None -> kappa1/theta (logsv_params.py:92-93)
+    cv = cal.LogSvParameterCodec(p0, lo, hi, cal.LogsvModelCalibrationType.PARAMS_WITH_VARSWAP_FIT)
+    x0, b = cv.initial_and_bounds()
+    np.testing.assert_array_equal(x0, [0.1, 1.2])
+    assert b == ((-3.0, 3.0), (0.2, 3.0))
     with pytest.raises(NotImplementedError):
-        cal.LogSvParameterCodec(p0, lo, hi, cal.LogsvModelCalibrationType.PARAMS_WITH_VARSWAP_FIT).initial_and_bounds()
+        cal.LogSvParameterCodec(p0, lo, hi, cal.LogsvModelCalibrationType.PARAMS6).initial_and_bounds()
 
 
 def test_constraints_match_theorem_3_7():
@@ -115,3 +119,35 @@ def test_validate_optimization_result():
     R.x = np.array([0.5])
     with pytest.raises(cal.CalibrationError, match="wrong shape"):
         cal.validate_optimization_result(R, b)
+
+
+def _varswap_chain(g):
+    vols = [np.asarray(v) for v in g["market_vols"]]
+    M = len(g["ttms"])
+    return OptionChain(ttms=g["ttms"], ids=np.array([f"{t:0.2f}" for t in g["ttms"]]), forwards=g["forwards"], strikes_ttms=[g["strikes"]] * M,
+                       optiontypes_ttms=[g["types"]] * M, bid_ivs=vols, ask_ivs=[v.copy() for v in vols])
+
+
+def test_vol_moments_varswap_strikes_and_backbone_vs_reference_golden():
+    """host pieces of PARAMS_WITH_VARSWAP_FIT against the reference's own outputs (tests/golden/make_golden.py --only-calib):
+    Lambda matrix, moments, integrated moments, expected quadratic variance, replicated var-swap strikes, fitted eta backbone."""
+    from conftest import load_golden
+    from stochvolmodels_b200.pricers.logsv import vol_moments as vm
+    g = load_golden("calib_logsv_varswap.npz")
+    p = LogSvParams(*g["start"])
+    np.testing.assert_allclose(vm.vol_moments_generator(p, 4), g["lambda4"], rtol=1e-15, atol=0)
+    np.testing.assert_allclose([vm.vol_moments(p, t, 4) for t in (0.0, 0.04, 0.5, 2.0)], g["moments"], rtol=1e-11, atol=1e-14)
+    np.testing.assert_allclose([vm.vol_moments(p, t, 4, integrated=True) for t in (0.04, 0.5, 2.0)], g["int_moments"], rtol=1e-10, atol=1e-14)
+    np.testing.assert_allclose([vm.expected_qvar(p, t) for t in (0.0, 0.04, 0.25, 0.5, 2.0)], g["qvars"], rtol=1e-11)
+    chain = _varswap_chain(g)
+    np.testing.assert_allclose(chain.get_slice_varswap_strikes(False).to_numpy(), g["varswap_strikes_raw"], rtol=1e-12)
+    vs = chain.get_slice_varswap_strikes(True)
+    np.testing.assert_allclose(vs.to_numpy(), g["varswap_strikes"], rtol=1e-12)
+    eta = vm.fit_vol_backbone_to_varswaps(p, vs)
+    np.testing.assert_allclose(eta.to_numpy(), g["eta_start"], rtol=1e-10)
+    np.testing.assert_array_equal(eta.index.to_numpy(), g["ttms"])
+    # the codec attaches the refitted backbone to every parsed point
+    codec = cal.LogSvParameterCodec(p, p, p, cal.LogsvModelCalibrationType.PARAMS_WITH_VARSWAP_FIT, vs)
+    q = codec.parse(np.array([0.1, 1.2]))
+    np.testing.assert_allclose(q.get_vol_backbone_etas(g["ttms"]), g["eta_start"], rtol=1e-10)
+    assert (q.sigma0, q.theta, q.kappa1, q.kappa2) == (p.sigma0, p.theta, p.kappa1, p.kappa2)

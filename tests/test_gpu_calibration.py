@@ -145,6 +145,30 @@ def test_logsv_calibration_vs_reference_driver(cuda_lib):
     assert info2["fun"] == pytest.approx(info["fun"], rel=1e-2)
 
 
+def test_logsv_varswap_fit_calibration_vs_reference_driver(cuda_lib):
+    """PARAMS_WITH_VARSWAP_FIT: (beta, volvol) with the eta backbone re-fitted at every optimizer point, against the reference's run."""
+    from stochvolmodels_b200 import LogSvParams, LogSVPricer, LogsvModelCalibrationType
+    g = load_golden("calib_logsv_varswap.npz")
+    M = len(g["ttms"])
+    from stochvolmodels_b200 import OptionChain
+    vols = [np.asarray(v) for v in g["market_vols"]]
+    chain = OptionChain(ttms=g["ttms"], ids=np.array([f"{t:0.2f}" for t in g["ttms"]]), forwards=g["forwards"], strikes_ttms=[g["strikes"]] * M,
+                        optiontypes_ttms=[g["types"]] * M, bid_ivs=vols, ask_ivs=[v.copy() for v in vols])
+    pricer = LogSVPricer()
+    market = g["market_vols"].ravel()
+    ref_fit = LogSvParams(*g["fit"])
+    ref_fit.set_vol_backbone(__import__("pandas").Series(g["fit_eta"], index=g["ttms"]))
+    ref_vols = np.array(pricer.compute_model_ivols_for_chain(chain, ref_fit, vol_scaler=pricer.set_vol_scaler(chain)))
+    np.testing.assert_allclose(ref_vols, g["fit_vols"], rtol=0, atol=1e-9)          # same objective at the reference's optimum
+    f_ref = _objective(chain, g["fit_vols"].ravel(), market)
+    fit, info = pricer.calibrate_model_params_to_chain(chain, LogSvParams(*g["start"]),
+                                                       model_calibration_type=LogsvModelCalibrationType.PARAMS_WITH_VARSWAP_FIT, return_info=True)
+    assert (fit.sigma0, fit.theta, fit.kappa1, fit.kappa2) == tuple(g["start"][:4])
+    assert info["fun"] <= 1.05 * f_ref + 1e-9
+    np.testing.assert_allclose([fit.beta, fit.volvol], g["fit"][4:], atol=3e-2)
+    np.testing.assert_allclose(fit.get_vol_backbone_etas(g["ttms"]), g["fit_eta"], rtol=2e-2)
+
+
 def test_heston_calibration_vs_reference_driver(cuda_lib):
     from stochvolmodels_b200 import HestonParams, HestonPricer
     g = load_golden("calib_heston.npz")
