@@ -100,7 +100,9 @@ def cpu_port_rate(chain, params, budget_s: float, nthreads: int = 0):
     """time the C port (all host threads) on a bounded sample of the SAME workload; returns (path_steps/s, paths, seconds, threads)."""
     from oracle import cport
     p6 = (params.sigma0, params.theta, params.kappa1, params.kappa2, params.beta, params.volvol)
-    threads = cport.num_threads() if nthreads <= 0 else nthreads
+    # all host threads this process may run on -- NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to its workers, which would
+    # silently turn the N>1 reference arm into a single-core run (measured: 1.9e7 instead of 1.5e8 path-steps/s)
+    threads = (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)) if nthreads <= 0 else nthreads
     run = lambda n: cport.mc_chain("logsv", p6, chain.ttms, chain.forwards, chain.discfactors, None, chain.strikes_ttms,
                                    chain.optiontypes_ttms, n, NB_STEPS_PER_YEAR, True, 1, SEED, "f64", nthreads=threads)
     n0 = 20_000 * threads
