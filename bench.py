@@ -44,9 +44,12 @@ SEED = 10
 
 def workload():
     from stochvolmodels_b200 import LOGSV_BTC_PARAMS, get_btc_test_chain_data
-    from oracle.mc import chain_steps
+    from stochvolmodels_b200.utils.funcs import set_time_grid
     chain = get_btc_test_chain_data()
-    steps = [s for s, _ in chain_steps(chain.ttms, NB_STEPS_PER_YEAR)]
+    steps, t0 = [], 0.0
+    for ttm in chain.ttms:
+        steps.append(set_time_grid(ttm - t0, NB_STEPS_PER_YEAR)[0])
+        t0 = ttm
     return chain, LOGSV_BTC_PARAMS, steps
 
 
