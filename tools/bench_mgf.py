@@ -1,10 +1,9 @@
 """Wall-clock of the Fourier route through the public API (host buffers in/out) on BASELINE config 3 (5 maturities x 21 strikes)
-and on the BTC chain, LogSV and Heston, with parity against the golden reference prices; oracle (CPU, vectorised numpy clone of
-the reference algorithm) timed next to it.  usage: python tools/bench_mgf.py"""
+and on the BTC chain, LogSV and Heston, with parity against the golden reference prices (reference CPU timings: SURVEY.md §6 and
+profiles/r01_mgf_bench.txt).  usage: python tools/bench_mgf.py"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
-from oracle import mgf
 from stochvolmodels_b200 import HestonParams, HestonPricer, LogSvParams, LogSVPricer, LOGSV_BTC_PARAMS, OptionChain, get_btc_test_chain_data, _capi
 
 G = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
@@ -32,10 +31,6 @@ for name, pricer, params, chain, gold in (("logsv c3 5x21", LogSVPricer(), Q, c3
     rel = max(np.max(np.abs(prices[m] - g[f"prices_{m}"]) / np.maximum(np.abs(g[f"prices_{m}"]), 1e-12 * chain.forwards[m])) for m in range(M))
     mask_rel = max(np.max(np.abs(prices[m] / g[f"prices_{m}"] - 1)[g[f"prices_{m}"] > 1e-6 * chain.forwards[m]]) for m in range(M))
     print(f"{name:16s} GPU e2e median {med:8.3f} ms (min {mn:.3f})  max rel err vs reference golden {mask_rel:.2e}", flush=True)
-    if name.startswith("logsv"):
-        p6 = (params.sigma0, params.theta, params.kappa1, params.kappa2, params.beta, params.volvol)
-        _, omed, _ = timed(lambda: mgf.logsv_chain_prices(p6, chain.ttms, chain.forwards, chain.discfactors, chain.strikes_ttms, chain.optiontypes_ttms), reps=3)
-        print(f"{'':16s} CPU oracle (vectorised numpy RK45 clone) {omed:8.1f} ms; reference as shipped (scipy loop) ~2 s per maturity [SURVEY.md §6]")
 
 # ---- options on quadratic variance, psi grid P = 40000 (reference: ~80 s per maturity on the CPU)
 from stochvolmodels_b200 import VariableType
