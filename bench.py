@@ -302,11 +302,11 @@ def main():
                              "note": "effective bandwidth of the reference's streaming dataflow; the fused kernel keeps state in registers, so "
                                      "frac > 1 means the HBM roofline is not what binds it: see compute_bound",
                              # what does bind it (one ncu --set full capture of this kernel per change, not measured in this run)
-                             "compute_bound": {"source": "profiles/r01_slice_kernel_ncu.txt (capture r1g) + profiles/r01_pipe_overlap.txt",
-                                               "issue_slots_busy": 0.52, "fp64_pipe": 0.386, "xu_pipe": 0.354, "fma_heavy_pipe": 0.322,
-                                               "alu_pipe": 0.292, "dram_throughput": 0.011,
-                                               "warp_instructions_per_path_step": 71.9 / 32,
-                                               "clk_per_warp_step_per_smsp": {"measured": 136, "instruction_mix_floor": "105-135"}}},
+                             "compute_bound": {"source": "profiles/r01_slice_kernel_ncu.txt (capture r1n) + profiles/r01_pipe_overlap.txt",
+                                               "issue_slots_busy": 0.586, "fp64_pipe": 0.326, "xu_pipe": 0.408, "fma_heavy_pipe": 0.419,
+                                               "alu_pipe": 0.378, "dram_throughput": 0.013,
+                                               "warp_instructions_per_path_step": 70.2 / 32,
+                                               "clk_per_warp_step_per_smsp": {"measured": 120}}},
                 "clocks": clocks}
         # second half of BASELINE.json's metric: price error of the timed MC chain against the Fourier reference (our GPU Fourier route,
         # itself within 1e-10 of the reference CPU path, tests/test_gpu_mgf.py); every one of the 49 strikes

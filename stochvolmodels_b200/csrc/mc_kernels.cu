@@ -277,6 +277,7 @@ struct SliceArgs {
 template <typename Path, typename Consts, typename Real, bool GAUSS64>
 __global__ void __launch_bounds__(kSliceThreads, B200SV_SLICE_MINBLOCKS) mc_slice_kernel(SliceArgs<Real> a, Consts consts) {
   __shared__ double red[2 * kSliceThreads / 32];
+  exp_table_init();
   double acc[2] = {0.0, 0.0};
   Path p(consts);
   const long long stride = (long long)gridDim.x * kSliceThreads;
@@ -423,6 +424,7 @@ __global__ void __launch_bounds__(kThreads) logsv_step_fixed_fast_kernel(double*
                                                                         double* __restrict__ qvar, const double* __restrict__ W0,
                                                                         const double* __restrict__ W1, int S, long long N,
                                                                         LogsvConsts consts) {
+  exp_table_init();
   LogsvPath<double> p(consts);
   const long long stride = (long long)gridDim.x * kThreads;
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < N; i += stride) {
@@ -698,6 +700,7 @@ __global__ void device_normals_kernel(unsigned long long seed, unsigned long lon
 
 // exp_pair self-test kernel (tests): out[2i] = exp(L), out[2i+1] = exp(-L)
 __global__ void exp_pair_kernel(const double* __restrict__ L, long long n, double* __restrict__ out) {
+  exp_table_init();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double a, b;
