@@ -196,6 +196,8 @@ def mc_chain_distributed(model: str, params_c, ttms, forwards, discfactors, etas
     if exchange not in ("p2p", "collective"):
         raise ValueError("exchange must be 'p2p' or 'collective'")
     use_p2p = exchange == "p2p" and world > 1
+    if use_p2p and not hasattr(eng, "enable_p2p"):
+        raise ValueError("exchange='p2p' needs an engine with a peer-memory mailbox (CudaMcEngine); use exchange='collective'")
     if use_p2p:
         try:
             eng.enable_p2p(group)

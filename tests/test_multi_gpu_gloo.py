@@ -51,6 +51,17 @@ def _worker(rank, world, port, model, out):
         pc = engine.logsv_params_c(*c["params"]) if model == "logsv" else engine.heston_params_c(*c["params"])
         p, e = mc_chain_distributed(model, pc, c["ttms"], c["fw"], c["df"], c["etas"], [K5, K5], c["types"], N, NPY, c["spot"], C.LOG_RETURN,
                                     SEED, C.GAUSS_F64, engine_factory=OracleEngine)
+        # an engine without a peer-memory mailbox takes the collective by default, accepts it explicitly, refuses exchange="p2p"
+        p2, _ = mc_chain_distributed(model, pc, c["ttms"], c["fw"], c["df"], c["etas"], [K5, K5], c["types"], N, NPY, c["spot"], C.LOG_RETURN,
+                                     SEED, C.GAUSS_F64, engine_factory=OracleEngine, exchange="collective")
+        assert all(np.array_equal(a, b) for a, b in zip(p, p2))
+        for bad, exc in (("p2p", ValueError), ("ring", ValueError)):
+            try:
+                mc_chain_distributed(model, pc, c["ttms"], c["fw"], c["df"], c["etas"], [K5, K5], c["types"], N, NPY, c["spot"], C.LOG_RETURN,
+                                     SEED, C.GAUSS_F64, engine_factory=OracleEngine, exchange=bad)
+                raise AssertionError(f"exchange={bad!r} was accepted")
+            except exc:
+                pass
         out[rank] = (p, e)
     finally:
         dist.destroy_process_group()
