@@ -87,3 +87,25 @@ class ModelPricer(ABC):
         ivols_up = option_chain.compute_model_ivols_from_chain_data(model_prices=ups)
         ivols_down = option_chain.compute_model_ivols_from_chain_data(model_prices=downs)
         return model_prices_ttms, ups, downs, ivols_mid, ivols_up, ivols_down, option_std_ttms
+
+    # ---- densities ----------------------------------------------------------------------------------------------------------
+    def get_log_return_mc_pdf(self, ttm: float, params: ModelParams, x_grid: np.ndarray, nb_path: int = 100000) -> np.ndarray:
+        """normalised Gaussian-KDE histogram of simulated terminal log-returns on ``x_grid`` (reference :243-265): NaN and |value| > 1e16
+        samples are counted, reported on stdout with the reference's wording and dropped.  Host post-processing of GPU samples.
+        The reference hands the whole return value of ``simulate_terminal_values`` to the filter, which only works for pricers that
+        return one array; a (log-return, vol, qvar) tuple -- what LogSVPricer / HestonPricer return -- is reduced to its log-returns."""
+        from scipy import stats
+        t_values = self.simulate_terminal_values(ttm=ttm, params=params, nb_path=nb_path)
+        if isinstance(t_values, tuple):
+            t_values = t_values[0]
+        t_values = np.asarray(t_values, dtype=float)
+        cut_off = 1e16
+        nans = np.isnan(t_values)
+        pos = ~nans & (t_values > cut_off)
+        neg = ~nans & (t_values < -cut_off)
+        print(f"in mc: num -inf = {np.sum(neg)}, num +inf = {np.sum(pos)}, num nans = {np.sum(nans)}")
+        z = stats.gaussian_kde(t_values[~(nans | pos | neg)])(x_grid)
+        return z / np.nansum(z)
+
+    def compute_logreturn_pdf(self, params: ModelParams, **kwargs) -> np.ndarray:
+        raise NotImplementedError("must be implemented in parent class")

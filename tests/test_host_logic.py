@@ -148,3 +148,32 @@ def test_shard_paths_partitions_exactly():
         assert sum(p[0] for p in parts) == n
         assert parts[0][1] == 0 and all(parts[r][1] == parts[r - 1][1] + parts[r - 1][0] for r in range(1, w))
         assert max(p[0] for p in parts) - min(p[0] for p in parts) <= 1
+
+
+def test_model_pricer_mc_pdf_and_default_interfaces():
+    """ModelPricer contract of the reference's tests/test_model_calibration_contracts.py:121-157 on a host-only toy pricer."""
+    import pytest
+    from stochvolmodels_b200 import ModelParams, ModelPricer
+
+    class Flat(ModelPricer):
+        def price_chain(self, option_chain, params, **kwargs):
+            return [np.zeros(1)]
+
+        def simulate_terminal_values(self, ttm, params, nb_path):
+            return np.array([np.nan, np.inf, -np.inf, -0.2, -0.1, 0.0, 0.1, 0.2])
+
+    import io, contextlib
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        density = Flat().get_log_return_mc_pdf(ttm=0.25, params=ModelParams(), x_grid=np.linspace(-0.5, 0.5, 51), nb_path=8)
+    assert np.all(np.isfinite(density)) and np.all(density >= 0.0) and abs(np.sum(density) - 1.0) < 1e-14
+    out = buf.getvalue()
+    assert "num -inf = 1" in out and "num +inf = 1" in out and "num nans = 1" in out
+
+    class PriceOnly(ModelPricer):
+        def price_chain(self, option_chain, params, **kwargs):
+            return [np.zeros(1)]
+    for call in (lambda p: p.model_mc_price_chain(None, None), lambda p: p.calibrate_model_params_to_chain(None),
+                 lambda p: p.simulate_vol_paths(None), lambda p: p.simulate_terminal_values(None), lambda p: p.compute_logreturn_pdf(None)):
+        with pytest.raises(NotImplementedError):
+            call(PriceOnly())
