@@ -48,3 +48,35 @@ def compute_logsv_a_mgf_grid(ttm: float, phi_grid: np.ndarray, psi_grid: np.ndar
             a_t0[:, 1] = -theta_grid      # affine_expansion.py:562-564
     params = engine.logsv_params_c(sigma0, theta, kappa1, kappa2, beta, volvol)
     return engine.logsv_mgf_grid(phi_grid, psi_grid, ttm, a_t0, params, vol_backbone_eta, is_spot_measure, order)
+
+
+def get_init_conditions_a(phi_grid: np.ndarray, psi_grid: np.ndarray, theta_grid: np.ndarray, n_terms: int,
+                          variable_type: VariableType = VariableType.LOG_RETURN) -> np.ndarray:
+    """A(0) over the transform grid (affine_expansion.py:532-567): zeros, except that the volatility transform puts -Theta into the
+    second coefficient."""
+    vt = getattr(variable_type, "value", variable_type)
+    if vt == VariableType.LOG_RETURN.value:
+        return np.zeros((phi_grid.shape[0], n_terms), dtype=np.complex128)
+    if vt == VariableType.Q_VAR.value:
+        return np.zeros((psi_grid.shape[0], n_terms), dtype=np.complex128)
+    if vt == VariableType.SIGMA.value:
+        a_t0 = np.zeros((theta_grid.shape[0], n_terms), dtype=np.complex128)
+        a_t0[:, 1] = -theta_grid
+        return a_t0
+    raise NotImplementedError
+
+
+def solve_a_ode_grid(phi_grid: np.ndarray, psi_grid: np.ndarray, ttm: float, theta: float, kappa1: float, kappa2: float, beta: float,
+                     volvol: float, is_spot_measure: bool = True, a_t0: Optional[np.ndarray] = None, is_stiff_solver: bool = False,
+                     expansion_order: ExpansionOrder = ExpansionOrder.FIRST, vol_backbone_eta: float = 1.0) -> np.ndarray:
+    """A(ttm) for every grid point from A(0) = ``a_t0`` (affine_expansion.py:492-529: a Python loop of ``solve_ivp`` calls there, one
+    GPU launch here; same default ``expansion_order`` = FIRST as the reference function)."""
+    if is_stiff_solver:
+        raise NotImplementedError("only the default RK45 branch is implemented on the GPU")
+    order = _order_code(expansion_order)
+    if a_t0 is None:
+        a_t0 = np.zeros((phi_grid.shape[0], get_expansion_n(ExpansionOrder(order))), dtype=np.complex128)
+    # the log-MGF contraction needs sigma0 - theta; it is discarded here, so any finite sigma0 does
+    a_t1, _ = engine.logsv_mgf_grid(phi_grid, psi_grid, ttm, a_t0, engine.logsv_params_c(theta, theta, kappa1, kappa2, beta, volvol),
+                                    vol_backbone_eta, is_spot_measure, order)
+    return a_t1

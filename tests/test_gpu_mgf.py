@@ -53,6 +53,13 @@ def test_single_maturity_grid_entry_points(cuda_lib):
     np.testing.assert_allclose(lm0, 0.0, atol=1e-14)
     with pytest.raises(NotImplementedError):
         compute_logsv_a_mgf_grid(0.25, phi, z, z, s0, th, k1, k2, b, vv, expansion_order=ExpansionOrder.ZERO)
+    # solve_a_ode_grid / get_init_conditions_a: the two steps compute_logsv_a_mgf_grid is made of in the reference (:492-567)
+    from stochvolmodels_b200 import VariableType
+    from stochvolmodels_b200.pricers.logsv.affine_expansion import get_init_conditions_a, solve_a_ode_grid
+    a0 = get_init_conditions_a(phi, z, z, 5, VariableType.LOG_RETURN)
+    assert a0.shape == (phi.shape[0], 5) and not a0.any()
+    np.testing.assert_array_equal(get_init_conditions_a(phi, z, phi, 3, VariableType.SIGMA)[:, 1], -phi)
+    np.testing.assert_array_equal(solve_a_ode_grid(phi, z, 0.25, th, k1, k2, b, vv, a_t0=a0, expansion_order=ExpansionOrder.SECOND), a1)
     h = load_golden("heston_fourier_g4.npz")
     v0, theta, kappa, rho, volvol = h["params"]
     lm, a, bb = compute_heston_mgf_grid(v0, theta, kappa, volvol, rho, 0.25, h["phi"], np.zeros_like(h["phi"]))
