@@ -170,6 +170,11 @@ int b200sv_dev_payoff_finalize(const double* sums, int J, double discfactor, lon
 int b200sv_p2p_create(int world, int rank, int max_values, void** ctx_out, unsigned char* handle_out);
 int b200sv_p2p_connect(void* p2p_ctx, const unsigned char* handles);
 int b200sv_p2p_destroy(void* p2p_ctx);
+/* A gather that waits longer than the spin limit (default 2^24 polls of ~200 ns, ~3 s) poisons its value with NaN and sets bit r (the
+ * peer that never published) of the context's status word.  b200sv_p2p_status synchronises `stream`, returns the word and clears it: a
+ * host must call it after the chain's copy back and treat non-zero as an error (multi_gpu.mc_chain_distributed raises P2pTimeout). */
+int b200sv_p2p_set_spin_limit(void* p2p_ctx, unsigned int spins);
+int b200sv_p2p_status(void* p2p_ctx, unsigned int* status_out, void* stream);
 /* standalone halves of an exchange (ranks without local paths; tests): publish K local values / gather the K global ones */
 int b200sv_dev_p2p_publish(void* p2p_ctx, const double* vals, int K, void* stream);
 int b200sv_dev_p2p_gather(void* p2p_ctx, int K, double* out, void* stream);

@@ -15,7 +15,6 @@ CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIBDIR, "libb200sv.so")
 SOURCES = ["mc_kernels.cu", "mgf_kernels.cu", "ivol_kernels.cu"]
-HEADERS = ["common.cuh", "philox.cuh", "fastmath64.cuh", os.path.join("..", "..", "include", "b200sv.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 
@@ -31,7 +30,9 @@ def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
+    import glob
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + glob.glob(os.path.join(CSRC, "*.cuh")) \
+        + [os.path.join(PKG, "..", "include", "b200sv.h"), os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

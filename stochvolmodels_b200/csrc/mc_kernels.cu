@@ -721,6 +721,8 @@ struct P2pCtx {
   unsigned long long published;  // epoch of the last exchange this rank published
   unsigned long long consumed;   // epoch of the last exchange this rank gathered
   double* scratch;               // 1 double (tail of the own mailbox allocation): sink of the protocol-keeping gather below
+  unsigned int* status;          // 1 word after scratch: timeout bits set by p2p_gather (p2p.cuh)
+  unsigned int spin_limit;
 };
 static P2pGather make_gather(P2pCtx* c);
 __global__ void p2p_gather_kernel(P2pGather g, int K, double* __restrict__ out);
@@ -745,6 +747,8 @@ static P2pGather make_gather(P2pCtx* c) {
   g.world = c->world;
   g.kmax = c->kmax;
   g.epoch = c->consumed = c->published;
+  g.spin_limit = c->spin_limit;
+  g.status = c->status;
   const int slot = (int)(g.epoch & 1ull);
   g.vals = (const double*)c->mail + (size_t)slot * c->world * c->kmax;
   g.flags = (const unsigned long long*)(c->mail + c->vals_bytes) + (size_t)slot * c->world;
@@ -1303,7 +1307,7 @@ int b200sv_p2p_create(int world, int rank, int max_values, void** ctx_out, unsig
   c->vals_bytes = sizeof(double) * 2 * (size_t)world * max_values;
   c->published = c->consumed = 0;
   const size_t flags_bytes = sizeof(unsigned long long) * 2 * (size_t)world;
-  const size_t total = c->vals_bytes + flags_bytes + sizeof(double);
+  const size_t total = c->vals_bytes + flags_bytes + 2 * sizeof(double);
   cudaError_t e = cudaMalloc((void**)&c->mail, total);
   if (e == cudaSuccess) e = cudaMemset(c->mail, 0, total);
   cudaIpcMemHandle_t h;
@@ -1315,6 +1319,8 @@ int b200sv_p2p_create(int world, int rank, int max_values, void** ctx_out, unsig
   for (int s = 0; s < kMaxPeers; ++s) c->peer[s] = nullptr;
   c->peer[rank] = c->mail;
   c->scratch = (double*)(c->mail + c->vals_bytes + flags_bytes);
+  c->status = (unsigned int*)(c->scratch + 1);
+  c->spin_limit = kSpinLimit;
   memcpy(handle_out, &h, 64);
   *ctx_out = c;
   return 0;
@@ -1342,6 +1348,23 @@ int b200sv_p2p_destroy(void* ctx) {
     if (s != c->rank && c->peer[s]) cudaIpcCloseMemHandle(c->peer[s]);
   cudaFree(c->mail);
   delete c;
+  return 0;
+}
+
+int b200sv_p2p_set_spin_limit(void* ctx, unsigned int spins) {
+  B200SV_REQUIRE(ctx && spins >= 1, "null pointer / spins");
+  ((P2pCtx*)ctx)->spin_limit = spins;
+  return 0;
+}
+
+// timeout bits of the exchanges since the last call (bit r: peer r did not publish within the spin limit); synchronises `stream` first
+int b200sv_p2p_status(void* ctx, unsigned int* status_out, void* stream) {
+  B200SV_REQUIRE(ctx && status_out, "null pointer");
+  P2pCtx* c = (P2pCtx*)ctx;
+  cudaStream_t st = (cudaStream_t)stream;
+  B200SV_CUDA(cudaMemcpyAsync(status_out, c->status, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+  B200SV_CUDA(cudaStreamSynchronize(st));
+  if (*status_out) B200SV_CUDA(cudaMemsetAsync(c->status, 0, sizeof(unsigned int), st));
   return 0;
 }
 

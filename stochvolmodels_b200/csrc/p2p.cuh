@@ -10,8 +10,9 @@
 //       of any collective algorithm.
 // No NCCL launch, no host synchronisation, no extra kernel: the 16 B (moments) and 24*J B (payoff sums) messages ride inside the
 // compute kernels.  Double buffering is safe because a rank publishes epoch e+2 only after it consumed e+1, which needed every rank to
-// have published e+1, which each does only after consuming e.  A spin that exceeds kSpinLimit poisons the result with NaN instead of
-// hanging the GPU.
+// have published e+1, which each does only after consuming e.  A spin that exceeds the context's spin limit poisons the result with NaN
+// AND sets bit r of the mailbox's status word instead of hanging the GPU; the host reads the word after the chain's copy back
+// (b200sv_p2p_status) and raises -- a timed-out exchange is an error, never a silent NaN price.
 #pragma once
 #include <cstdint>
 
@@ -31,6 +32,8 @@ struct P2pGather {             // by value into the consumer kernel; world == 0:
   const unsigned long long* flags;               // &my_mailbox.flags[slot][0]
   int world, kmax;
   unsigned long long epoch;
+  unsigned int spin_limit;                       // x ~200 ns backoff; b200sv_p2p_set_spin_limit
+  unsigned int* status;                          // device word in the own mailbox: bit r set <=> peer r never published (timeout)
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
@@ -42,7 +45,7 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-constexpr unsigned int kSpinLimit = 1u << 24;      // x ~200 ns backoff ~ 3 s
+constexpr unsigned int kSpinLimit = 1u << 24;      // default: x ~200 ns backoff ~ 3 s
 
 // value k of the exchange, summed over ranks in rank order (call from any thread; spins until every rank has published)
 __device__ __forceinline__ double p2p_gather(const P2pGather& g, int k) {
@@ -51,7 +54,10 @@ __device__ __forceinline__ double p2p_gather(const P2pGather& g, int k) {
     unsigned int spins = 0;
     while (ld_acquire_sys(g.flags + r) < g.epoch) {
       __nanosleep(200);
-      if (++spins > kSpinLimit) return __longlong_as_double(0x7ff8000000000000ll);   // peer never arrived: poison, do not hang
+      if (++spins > g.spin_limit) {     // peer never arrived: poison the value, RECORD it (the host raises after the chain's copy back)
+        atomicOr(g.status, 1u << r);
+        return __longlong_as_double(0x7ff8000000000000ll);
+      }
     }
     s += __ldcg(g.vals + (size_t)r * g.kmax + k);
   }

@@ -61,28 +61,36 @@ class CalibrationError(RuntimeError):
 
 
 def validate_optimization_result(result, bounds) -> np.ndarray:
-    """finite, in-bounds optimizer vector or ``CalibrationError`` (reference pricers/model_pricer.py:48-80)."""
-    message = str(getattr(result, "message", "no optimizer message"))
-    if not bool(getattr(result, "success", False)):
-        raise CalibrationError(f"Calibration failed: {message}")
-    raw = getattr(result, "x", None)
-    if raw is None:
-        raise CalibrationError(f"Calibration returned no parameter vector: {message}")
+    """the optimizer's vector as float64[len(bounds)], or ``CalibrationError`` naming what is wrong with it.
+
+    Same acceptance rule and error wording as the reference's guard (pricers/model_pricer.py:48-80: success flag, numeric 1-d vector
+    of the right length, finite, inside the bounds up to 1e-10) -- callers match on the message text."""
+    note = str(getattr(result, "message", "no optimizer message"))
+
+    def reject(what: str, cause=None):
+        raise CalibrationError(f"Calibration {what}: {note}") from cause
+
+    if not getattr(result, "success", False):
+        reject("failed")
+    x = getattr(result, "x", None)
+    if x is None:
+        reject("returned no parameter vector")
     try:
-        values = np.asarray(raw, dtype=float)
-    except (TypeError, ValueError) as error:
-        raise CalibrationError(f"Calibration returned a non-numeric parameter vector: {message}") from error
-    if values.ndim != 1 or values.size != len(bounds):
-        raise CalibrationError(f"Calibration returned a parameter vector with the wrong shape: {message}")
-    if not np.all(np.isfinite(values)):
-        raise CalibrationError(f"Calibration returned non-finite parameters: {message}")
-    tol = 1.0e-10
-    for value, (lower, upper) in zip(values, bounds):
-        if lower is not None and value < lower - tol:
-            raise CalibrationError(f"Calibration returned parameters below bounds: {message}")
-        if upper is not None and value > upper + tol:
-            raise CalibrationError(f"Calibration returned parameters above bounds: {message}")
-    return values
+        x = np.array(x, dtype=np.float64, copy=True)
+    except (TypeError, ValueError) as exc:
+        reject("returned a non-numeric parameter vector", exc)
+    if x.shape != (len(bounds),):
+        reject("returned a parameter vector with the wrong shape")
+    if not np.isfinite(x).all():
+        reject("returned non-finite parameters")
+    slack = 1.0e-10
+    lo = np.array([-np.inf if b[0] is None else b[0] for b in bounds], dtype=np.float64)
+    hi = np.array([np.inf if b[1] is None else b[1] for b in bounds], dtype=np.float64)
+    if (x < lo - slack).any():
+        reject("returned parameters below bounds")
+    if (x > hi + slack).any():
+        reject("returned parameters above bounds")
+    return x
 
 
 def calibration_weights(option_chain, market_vols: np.ndarray, is_vega_weighted: bool, is_unit_ttm_vega: bool) -> np.ndarray:
@@ -168,7 +176,8 @@ class LogSvParameterCodec:
             out = LogSvParams(sigma0=pars[0], theta=pars[1], kappa1=pars[2], kappa2=None, beta=pars[3], volvol=pars[4])
         else:
             raise NotImplementedError(f"{self.calibration_type}")
-        out.vol_backbone = p0.vol_backbone
+        # no vol_backbone on the trial point: the reference codec (logsv_pricer.py:112-137) builds PARAMS4 / PARAMS5 candidates without
+        # one, so eta = 1 during the fit and the fitted object carries none, whatever params0 holds
         return out
 
     def initial_and_bounds(self) -> Tuple[np.ndarray, Tuple[Tuple[float, float], ...]]:

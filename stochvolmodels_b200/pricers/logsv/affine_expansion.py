@@ -44,7 +44,7 @@ def compute_logsv_a_mgf_grid(ttm: float, phi_grid: np.ndarray, psi_grid: np.ndar
     n = get_expansion_n(ExpansionOrder(order))
     if a_t0 is None:
         a_t0 = np.zeros((phi_grid.shape[0], n), dtype=np.complex128)
-        if variable_type == VariableType.SIGMA:
+        if getattr(variable_type, "value", variable_type) == VariableType.SIGMA.value:   # by value: the reference's own enum duck-types
             a_t0[:, 1] = -theta_grid      # affine_expansion.py:562-564
     params = engine.logsv_params_c(sigma0, theta, kappa1, kappa2, beta, volvol)
     return engine.logsv_mgf_grid(phi_grid, psi_grid, ttm, a_t0, params, vol_backbone_eta, is_spot_measure, order)

@@ -174,13 +174,9 @@ class LogSVPricer(ModelPricer):
                                              nb_steps_per_year=kwargs.get("nb_steps_per_year", 360), seed=kwargs.get("seed"),
                                              gauss=kwargs.get("gauss", "fp32"))
 
-
-def _pricer_logsv_pdfs(self, params: LogSvParams, ttm: float, space_grid: np.ndarray, **kwargs) -> np.ndarray:
-    """``LogSVPricer.logsv_pdfs`` (reference :613-637)."""
-    return logsv_pdfs(params=params, ttm=ttm, space_grid=space_grid, **kwargs)
-
-
-LogSVPricer.logsv_pdfs = _pricer_logsv_pdfs
+    def logsv_pdfs(self, params: LogSvParams, ttm: float, space_grid: np.ndarray, **kwargs) -> np.ndarray:
+        """model density of log-return / quadratic variance / volatility on ``space_grid`` (reference :613-637)."""
+        return logsv_pdfs(params=params, ttm=ttm, space_grid=space_grid, **kwargs)
 
 
 def set_vol_scaler(sigma0: float, ttm: float) -> float:
