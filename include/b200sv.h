@@ -39,7 +39,10 @@ enum { B200SV_ORDER_FIRST = 1, B200SV_ORDER_SECOND = 2 };
 /* MC arithmetic flags (bit-or).  Default 0 = fp64 state arithmetic, Gaussians drawn by a float Box-Muller on the SFU
  * and widened (the draws are random inputs, not reference arithmetic).  B200SV_GAUSS_F64 draws them in fp64 as well;
  * B200SV_STATE_F32 keeps x / log-sigma / qvar in float registers (payoff moments stay fp64). */
-enum { B200SV_STATE_F64 = 0, B200SV_STATE_F32 = 1, B200SV_GAUSS_F32 = 0, B200SV_GAUSS_F64 = 2 };
+enum { B200SV_STATE_F64 = 0, B200SV_STATE_F32 = 1, B200SV_GAUSS_F32 = 0, B200SV_GAUSS_F64 = 2,
+       /* check mode: the DEFAULT stream's 32-bit uniforms pushed through the fp64 Box-Muller (paired with the default mode path by path,
+        * so that price differences isolate the SFU approximation error of the float draws; tests/test_gpu_gauss_bias.py) */
+       B200SV_GAUSS_F64_PAIRED = 4 };
 /* Heston variance scheme: 0 = the reference's floor-Euler (pricers/heston_pricer.py:369-379, v = max(v, 1e-4)); 1 = opt-in Andersen (2008)
  * quadratic-exponential scheme with central discretisation (BASELINE.json config 2 names it; the reference does not have it) */
 enum { B200SV_HESTON_EULER_FLOOR = 0, B200SV_HESTON_QE = 1 };
@@ -195,6 +198,8 @@ int b200sv_dev_spot_moments(const double* x, long long n, double forward, double
 
 /* test hook: out[2i] = exp(L[i]), out[2i+1] = exp(-L[i]) through the stepper's shared-polynomial exp pair (host arrays). */
 int b200sv_debug_exp_pair(const double* L, long long n, double* out);
+/* same for the variant the stepper runs on its table-unit state: out[2i] = exp(Ls[i] ln2/256), out[2i+1] = exp(-Ls[i] ln2/256) */
+int b200sv_debug_exp_pair_scaled(const double* Ls, long long n, double* out);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Fourier / MGF, host-level

@@ -42,7 +42,7 @@ static inline void step_normals(uint64_t seed, uint64_t path, uint32_t slice, ui
   uint32_t c[4] = {(uint32_t)path, (uint32_t)(path >> 32), gauss64 ? step : step >> 1, slice};
   philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
   if (gauss64) {
-    const double u1 = 2.0 - u52(c[0], c[1]), u2 = u52(c[2], c[3]) - 1.0;
+    const double u1 = 2.0 - u52(c[0], c[1] | 1u), u2 = u52(c[2], c[3]) - 1.0;   /* lowest bit forced: u1 < 1 (gauss64.cuh) */
     const double rad = sqrt(-2.0 * log(u1));
     *z0 = rad * cos(2.0 * M_PI * u2);
     *z1 = rad * sin(2.0 * M_PI * u2);

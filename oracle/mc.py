@@ -188,8 +188,11 @@ def device_normals(seed: int, path_ids, slice_idx: int, nb_steps: int, gauss: st
 
     Counter layout (``philox.cuh``): key = (seed_lo, seed_hi); counter = (path_lo, path_hi, call, slice).
 
-    gauss="f64": one call per step s (call = s); u1 = 2 - d(r0,r1) in (0,1], u2 = d(r2,r3) - 1 in [0,1);
+    gauss="f64": one call per step s (call = s); u1 = 2 - d(r0,r1|1) in (0,1) (the lowest mantissa bit is forced to 1 so that
+                 u1 < 1 and R > 0, gauss64.cuh), u2 = d(r2,r3) - 1 in [0,1);
                  Z0 = R cos(2 pi u2), Z1 = R sin(2 pi u2), R = sqrt(-2 ln u1).
+    gauss="f64_paired": the f32 stream's words and layout evaluated in float64: u1 = (ra + 1/2) 2^-32, angle = 2 pi rb 2^-32
+                 (the device's check mode B200SV_GAUSS_F64_PAIRED).
     gauss="f32": one call per TWO steps (call = s // 2); even step uses (r0, r1), odd step (r2, r3);
                  u1 = fma(float(ra), 2^-32, 2^-33), angle = float(int32(rb)) * pi * 2^-31, float32 Box-Muller:
                  Z0 = R cos(angle), Z1 = R sin(angle).  The device uses MUFU approximations (lg2/sin/cos), so this variant
@@ -205,7 +208,7 @@ def device_normals(seed: int, path_ids, slice_idx: int, nb_steps: int, gauss: st
     if gauss == "f64":
         for s in range(nb_steps):
             r0, r1, r2, r3 = philox4x32_10(plo, phi, np.uint64(s), np.uint64(slice_idx), k0, k1)
-            u1 = 2.0 - _u52(r0, r1)
+            u1 = 2.0 - _u52(r0, r1 | np.uint64(1))
             u2 = _u52(r2, r3) - 1.0
             rad = np.sqrt(-2.0 * np.log(u1))
             Z0[s] = rad * np.cos(2.0 * np.pi * u2)
@@ -224,6 +227,18 @@ def device_normals(seed: int, path_ids, slice_idx: int, nb_steps: int, gauss: st
                 ang = rb.view(np.int32).astype(f32) * f32(np.pi * 2.0 ** -31)      # [-pi, pi]
                 Z0[s] = (rad * np.cos(ang)).astype(np.float64)
                 Z1[s] = (rad * np.sin(ang)).astype(np.float64)
+    elif gauss == "f64_paired":
+        for c in range((nb_steps + 1) // 2):
+            r = philox4x32_10(plo, phi, np.uint64(c), np.uint64(slice_idx), k0, k1)
+            for half in range(2):
+                s = 2 * c + half
+                if s >= nb_steps:
+                    break
+                ra, rb = r[2 * half].astype(np.float64), r[2 * half + 1].astype(np.float64)
+                rad = np.sqrt(-2.0 * np.log((ra + 0.5) * 2.0 ** -32))
+                ang = 2.0 * np.pi * (rb * 2.0 ** -32)
+                Z0[s] = rad * np.cos(ang)
+                Z1[s] = rad * np.sin(ang)
     else:
         raise ValueError(gauss)
     return Z0, Z1

@@ -19,7 +19,7 @@ LIB_PATH = os.environ.get("B200SV_LIB") or os.path.join(_PKG, "lib", "libb200sv.
 CALL, PUT, INV_CALL, INV_PUT = 0, 1, 2, 3
 LOG_RETURN, Q_VAR, SIGMA = 1, 2, 3
 ORDER_FIRST, ORDER_SECOND = 1, 2
-STATE_F64, STATE_F32, GAUSS_F32, GAUSS_F64 = 0, 1, 0, 2
+STATE_F64, STATE_F32, GAUSS_F32, GAUSS_F64, GAUSS_F64_PAIRED = 0, 1, 0, 2, 4
 HESTON_EULER_FLOOR, HESTON_QE = 0, 1
 TYPE_CODES = {"C": CALL, "P": PUT, "IC": INV_CALL, "IP": INV_PUT}
 
@@ -79,6 +79,7 @@ SIGNATURES = {
     "b200sv_dev_heston_step_fixed": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_double, _hp, c_void_p],
     "b200sv_dev_spot_moments": [c_void_p, c_longlong, c_double, c_void_p, c_void_p],
     "b200sv_debug_exp_pair": [_dp, c_longlong, _dp],
+    "b200sv_debug_exp_pair_scaled": [_dp, c_longlong, _dp],
     "b200sv_logsv_price_chain": [_lp, c_int, _dp, _dp, _dp, _dp, _ip, _dp, _i8p, c_int, c_int, c_int, c_double, c_int, _dp, _dp, _dp],
     "b200sv_heston_price_chain": [_hp, c_int, _dp, _dp, _dp, _ip, _dp, _i8p, c_int, c_double, c_int, _dp, _dp],
     "b200sv_logsv_price_chain_batch": [_lp, c_int, c_int, _dp, _dp, _dp, _dp, _ip, _dp, _i8p, c_int, c_int, c_double, c_int, _dp, _dp],

@@ -57,6 +57,7 @@ struct LogsvConsts {   // all dt / sqrt(dt) factors folded in on the host (fp64)
   double b0;    // beta * sqrt(dt)
   double b1;    // volvol * sqrt(dt)
   double cq;    // 0.5 * eta^2 * dt                  q  += cq * (sigma_old^2 + sigma_new^2)
+  double a0s, a1s, a2s, b0s, b1s;   // a0..b1 in table units (x 256/ln2): the fp64 stepper carries Ls = L * 256/ln2 (fastmath64.cuh)
 };
 
 struct HestonConsts {
@@ -89,6 +90,11 @@ static LogsvConsts make_logsv_consts(const b200sv_logsv_params& p, double eta, b
   c.b0 = p.beta * sdt;
   c.b1 = p.volvol * sdt;
   c.cq = 0.5 * eta * eta * dt;
+  c.a0s = c.a0 * kLogScale;
+  c.a1s = c.a1 * kLogScale;
+  c.a2s = c.a2 * kLogScale;
+  c.b0s = c.b0 * kLogScale;
+  c.b1s = c.b1 * kLogScale;
   return c;
 }
 
@@ -124,23 +130,30 @@ struct LogsvPath;
 //   XM = sum_{k=0..S-1} sigma_k z0_k (martingale part of x, old sigma)
 // from which  x_S = x_0 + cx*(sigma_0^2 + A - sigma_S^2) + ce*XM          [sum_k cx*sigma_k^2 + ce*sigma_k*z0_k]
 //             q_S = q_0 + cq*(sigma_0^2 + 2A - sigma_S^2)                 [sum_k cq*(sigma_k^2 + sigma_{k+1}^2)]
-// (logsv_pricer.py:1041-1045 summed over the slice).  1/sigma = exp(-L) comes from the shared polynomial.
+// (logsv_pricer.py:1041-1045 summed over the slice).  The log-vol is carried in table units Ls = L * 256/ln2 so that sigma = exp(L) and
+// 1/sigma = exp(-L) come out of exp_pair_scaled (11 fp64 instructions, fastmath64.cuh); 18 fp64-pipe instructions per step in all.
+// Range guard: step<false> only RECORDS |Ls| > kLogScaledMax (|L| > 699.997: one LOP3 + one ISETP.OR per step); a path that ever trips
+// it is re-run by the kernel with step<true>, which clamps every step -- the result is the clamped recursion for every path, the common
+// case pays 2 integer instructions instead of 5 + 2.
 template <>
 struct LogsvPath<double> {
-  double L, s, inv, A, XM, x0, q0, s2_first;
+  double Ls, s, inv, A, XM, x0, q0, s2_first;
   double cx, ce, a0, a1, a2, b0, b1, cq;
+  bool bad;
   __device__ __forceinline__ LogsvPath(const LogsvConsts& c)
-      : cx(c.cx), ce(c.ce), a0(c.a0), a1(c.a1), a2(c.a2), b0(c.b0), b1(c.b1), cq(c.cq) {}
+      : cx(c.cx), ce(c.ce), a0(c.a0s), a1(c.a1s), a2(c.a2s), b0(c.b0s), b1(c.b1s), cq(c.cq), bad(false) {}
   __device__ __forceinline__ void load(double x_, double sigma0, double q_) {
     x0 = x_;
     q0 = q_;
-    L = clamp_log(log(sigma0));    // vol_var = np.log(sigma0), logsv_pricer.py:1039
-    exp_pair(L, s, inv);
+    Ls = clamp_log_scaled(clamp_log(log(sigma0)) * kLogScale);    // vol_var = np.log(sigma0), logsv_pricer.py:1039
+    exp_pair_scaled(Ls, s, inv);
     s = sigma0;                    // keep the loaded sigma itself for the first step
     s2_first = s * s;
     A = 0.0;
     XM = 0.0;
+    bad = false;
   }
+  template <bool SAFE>
   __device__ __forceinline__ void step(double z0, double z1) {
 #if defined(B200SV_ABLATE) && (B200SV_ABLATE & 4)   // tuning only: no fp64 recursion, just consume the normals
     XM = fma(z1, z0, XM);
@@ -148,13 +161,18 @@ struct LogsvPath<double> {
 #endif
     XM = fma(s, z0, XM);
     // noise + constant drift first (independent of sigma: off the critical path), then the two state-dependent terms
-    double l = L + fma(b0, z0, fma(b1, z1, a0));
+    double l = Ls + fma(b0, z0, fma(b1, z1, a0));
     l = fma(a2, s, l);
     l = fma(a1, inv, l);
-    L = clamp_log(l);
-    exp_pair(L, s, inv);
+    if constexpr (SAFE)
+      l = clamp_log_scaled(l);
+    else
+      bad |= log_scaled_out_of_range(l);
+    Ls = l;
+    exp_pair_scaled(Ls, s, inv);
     A = fma(s, s, A);
   }
+  __device__ __forceinline__ bool overflowed() const { return bad; }
   __device__ __forceinline__ double sigma() const { return s; }
   __device__ __forceinline__ double x() const { return fma(ce, XM, fma(cx, (s2_first - s * s) + A, x0)); }
   __device__ __forceinline__ double q() const { return fma(cq, (s2_first - s * s) + 2.0 * A, q0); }
@@ -178,6 +196,7 @@ struct LogsvPath<float> {
     A = 0.0f;
     XM = 0.0f;
   }
+  template <bool SAFE>
   __device__ __forceinline__ void step(float z0, float z1) {
     XM = fmaf(s, z0, XM);
     float l = L + fmaf(b0, z0, fmaf(b1, z1, a0));
@@ -188,6 +207,7 @@ struct LogsvPath<float> {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(s));
     A = fmaf(s, s, A);
   }
+  __device__ __forceinline__ bool overflowed() const { return false; }   // L is clamped every step
   __device__ __forceinline__ float sigma() const { return s; }
   __device__ __forceinline__ float x() const { return fmaf(ce, XM, fmaf(cx, (s2_first - s * s) + A, x0)); }
   __device__ __forceinline__ float q() const { return fmaf(cq, (s2_first - s * s) + 2.0f * A, q0); }
@@ -238,6 +258,7 @@ struct HestonPath {
   }
   // pricers/heston_pricer.py:372-379 (floor-Euler): everything on the OLD variance, then v = max(v, 1e-4).
   // V = sum v_k, XM = sum sqrt(v_k) z0_k  =>  x_S = x_0 - 0.5*dt*V + sqrt(dt)*XM,  q_S = q_0 + dt*V.
+  template <bool SAFE>
   __device__ __forceinline__ void step(Real z0, Real z1) {
     if (qe) {
       step_qe(z0, z1);
@@ -250,6 +271,7 @@ struct HestonPath {
     vn = fma(sig, fma(c0, z0, c1 * z1), vn);
     v = vn > (Real)1e-4 ? vn : (Real)1e-4;     // np.maximum(var0, 1e-4)
   }
+  __device__ __forceinline__ bool overflowed() const { return false; }
   __device__ __forceinline__ Real sigma() const { return v; }
   __device__ __forceinline__ Real x() const { return fma(sdt, XM, fma(hx, V, x0)) + xacc; }
   __device__ __forceinline__ Real q() const { return fma(dt, V, q0) + qacc; }
@@ -274,56 +296,91 @@ struct SliceArgs {
   double* partials;   // [gridDim.x][2]
 };
 
-template <typename Path, typename Consts, typename Real, bool GAUSS64>
+// advance one path through the slice, drawing its normals in the order philox.cuh defines.  SAFE = clamp the log-vol every step (re-run
+// of a path whose fast pass left the representable range); !SAFE = the production loop with the generator software-pipelined one call
+// ahead of the fp64 recursion (the integer / SFU stream of call c+1 overlaps the fp64 stream of call c inside a warp).
+template <bool SAFE, typename Path, typename Real, int GAUSS>
+__device__ __forceinline__ void run_slice_steps(Path& p, StepNormals<Real, GAUSS>& rng, int nsteps) {
+  if constexpr (GAUSS == kGaussF64) {
+    if constexpr (SAFE || !B200SV_SLICE_PREFETCH) {
+      for (int s = 0; s < nsteps; ++s) {
+        Real z0, z1;
+        rng.get((uint32_t)s, z0, z1);
+        p.template step<SAFE>(z0, z1);
+      }
+    } else {
+      Real n0, n1;
+      rng.get(0u, n0, n1);
+#pragma unroll 1
+      for (int s = 0; s < nsteps; ++s) {
+        Real m0, m1;
+        rng.get((uint32_t)(s + 1), m0, m1);
+        p.template step<SAFE>(n0, n1);
+        n0 = m0;
+        n1 = m1;
+      }
+    }
+  } else {
+    // one Philox call feeds two steps
+    const int ncalls = nsteps >> 1;
+    if constexpr (SAFE || !B200SV_SLICE_PREFETCH) {
+      for (int c = 0; c < ncalls; ++c) {
+        Real n0, n1, n2, n3;
+        rng.get2((uint32_t)c, n0, n1, n2, n3);
+        p.template step<SAFE>(n0, n1);
+        p.template step<SAFE>(n2, n3);
+      }
+      if (nsteps & 1) {
+        Real n0, n1, n2, n3;
+        rng.get2((uint32_t)ncalls, n0, n1, n2, n3);
+        p.template step<SAFE>(n0, n1);
+      }
+    } else {
+      Real n0, n1, n2, n3, m0, m1, m2, m3;
+      rng.get2(0u, n0, n1, n2, n3);
+      int c = 0;
+#pragma unroll 1
+      for (; c + 2 <= ncalls; c += 2) {     // two calls = four steps per iteration: the n / m register sets swap roles, no moves
+        rng.get2((uint32_t)(c + 1), m0, m1, m2, m3);
+        p.template step<SAFE>(n0, n1);
+        p.template step<SAFE>(n2, n3);
+        rng.get2((uint32_t)(c + 2), n0, n1, n2, n3);
+        p.template step<SAFE>(m0, m1);
+        p.template step<SAFE>(m2, m3);
+      }
+      if (c < ncalls) {
+        rng.get2((uint32_t)(c + 1), m0, m1, m2, m3);
+        p.template step<SAFE>(n0, n1);
+        p.template step<SAFE>(n2, n3);
+        n0 = m0;
+        n1 = m1;
+      }
+      if (nsteps & 1) p.template step<SAFE>(n0, n1);
+    }
+  }
+}
+
+template <typename Path, typename Consts, typename Real, int GAUSS>
 __global__ void __launch_bounds__(kSliceThreads, B200SV_SLICE_MINBLOCKS) mc_slice_kernel(SliceArgs<Real> a, Consts consts) {
   __shared__ double red[2 * kSliceThreads / 32];
   exp_table_init();
+  if constexpr (GAUSS != kGaussF32) gauss64_table_init();
   double acc[2] = {0.0, 0.0};
   Path p(consts);
   const long long stride = (long long)gridDim.x * kSliceThreads;
   for (long long i = (long long)blockIdx.x * kSliceThreads + threadIdx.x; i < a.n; i += stride) {
-    if (a.init)
-      p.load((Real)0, (Real)a.v_init, (Real)0);
-    else
-      p.load(a.x[i], a.v[i], a.q[i]);
-    StepNormals<Real, GAUSS64> rng(a.seed, a.path_offset + (unsigned long long)i, a.slice);
-    if constexpr (GAUSS64) {
-      for (int s = 0; s < a.nsteps; ++s) {
-        Real z0, z1;
-        rng.get((uint32_t)s, z0, z1);
-        p.step(z0, z1);
-      }
-    } else {
-      // one Philox call feeds two steps; the NEXT call is issued before the two fp64 steps of the current one so the
-      // integer / SFU stream of the generator overlaps the fp64 stream of the recursion inside a warp
-      const int ncalls = a.nsteps >> 1;
-#if B200SV_SLICE_PREFETCH
-      Real n0, n1, n2, n3;
-      rng.get2(0u, n0, n1, n2, n3);
-      for (int c = 0; c < ncalls; ++c) {
-        Real m0, m1, m2, m3;
-        rng.get2((uint32_t)(c + 1), m0, m1, m2, m3);
-        p.step(n0, n1);
-        p.step(n2, n3);
-        n0 = m0;
-        n1 = m1;
-        n2 = m2;
-        n3 = m3;
-      }
-      if (a.nsteps & 1) p.step(n0, n1);
-#else
-      for (int c = 0; c < ncalls; ++c) {
-        Real n0, n1, n2, n3;
-        rng.get2((uint32_t)c, n0, n1, n2, n3);
-        p.step(n0, n1);
-        p.step(n2, n3);
-      }
-      if (a.nsteps & 1) {
-        Real n0, n1, n2, n3;
-        rng.get2((uint32_t)ncalls, n0, n1, n2, n3);
-        p.step(n0, n1);
-      }
-#endif
+    Real xi = (Real)0, vi = (Real)a.v_init, qi = (Real)0;
+    if (!a.init) {
+      xi = a.x[i];
+      vi = a.v[i];
+      qi = a.q[i];
+    }
+    p.load(xi, vi, qi);
+    StepNormals<Real, GAUSS> rng(a.seed, a.path_offset + (unsigned long long)i, a.slice);
+    run_slice_steps<false>(p, rng, a.nsteps);
+    if (p.overflowed()) {      // rare: |log sigma| left [-700, 700] somewhere on this path -> redo it with the per-step clamp
+      p.load(xi, vi, qi);
+      run_slice_steps<true>(p, rng, a.nsteps);
     }
     const Real xT = p.x();
     a.x[i] = xT;
@@ -429,7 +486,7 @@ __global__ void __launch_bounds__(kThreads) logsv_step_fixed_fast_kernel(double*
   const long long stride = (long long)gridDim.x * kThreads;
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < N; i += stride) {
     p.load(x[i], sigma[i], qvar[i]);
-    for (int s = 0; s < S; ++s) p.step(__ldg(W0 + (size_t)s * N + i), __ldg(W1 + (size_t)s * N + i));
+    for (int s = 0; s < S; ++s) p.step<true>(__ldg(W0 + (size_t)s * N + i), __ldg(W1 + (size_t)s * N + i));
     x[i] = p.x();
     sigma[i] = p.sigma();
     qvar[i] = p.q();
@@ -476,12 +533,13 @@ __global__ void __launch_bounds__(kThreads) logsv_vol_paths_kernel(double* __res
   const double vartheta = __dsqrt_rn(vartheta2);
   const double k1theta = __dmul_rn(r.kappa1, r.theta);
   const double half_vt2 = __dmul_rn(0.5, vartheta2);
+  gauss64_table_init();
   const long long stride = (long long)gridDim.x * kThreads;
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < N; i += stride) {
     double si = v0;
     double L = log(si);
     sigma_t[i] = si;
-    StepNormals<double, true> rng(seed, path_offset + (unsigned long long)i, 0u);
+    StepNormals<double, kGaussF64> rng(seed, path_offset + (unsigned long long)i, 0u);
     for (int s = 0; s < S; ++s) {
       double w1;
       if (W) {
@@ -671,13 +729,14 @@ __global__ void payoff_finalize_kernel(const double* __restrict__ sums, int J, d
 // --------------------------------------------------------------------------------------------------------------------
 // debug / parity export of the normals the fused kernel draws
 // --------------------------------------------------------------------------------------------------------------------
-template <bool GAUSS64>
+template <int GAUSS>
 __global__ void device_normals_kernel(unsigned long long seed, unsigned long long path0, long long n, unsigned int slice,
                                       int nsteps, double* __restrict__ z0, double* __restrict__ z1) {
+  if constexpr (GAUSS != kGaussF32) gauss64_table_init();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  StepNormals<double, GAUSS64> rng(seed, path0 + (unsigned long long)i, slice);
-  if constexpr (GAUSS64) {
+  StepNormals<double, GAUSS> rng(seed, path0 + (unsigned long long)i, slice);
+  if constexpr (GAUSS == kGaussF64) {
     for (int s = 0; s < nsteps; ++s) {
       double a, b;
       rng.get((uint32_t)s, a, b);
@@ -705,6 +764,17 @@ __global__ void exp_pair_kernel(const double* __restrict__ L, long long n, doubl
   if (i >= n) return;
   double a, b;
   exp_pair(L[i], a, b);
+  out[2 * i] = a;
+  out[2 * i + 1] = b;
+}
+
+// the stepper's variant on table units: out[2i] = exp(Ls ln2/256), out[2i+1] = exp(-Ls ln2/256), |Ls| clamped like the stepper does
+__global__ void exp_pair_scaled_kernel(const double* __restrict__ Ls, long long n, double* __restrict__ out) {
+  exp_table_init();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double a, b;
+  exp_pair_scaled(clamp_log_scaled(Ls[i]), a, b);
   out[2 * i] = a;
   out[2 * i + 1] = b;
 }
@@ -768,7 +838,7 @@ static void time_grid(double ttm, int n_per_year, int* S, double* dt) {
   *dt = (*S == 1) ? ttm : ttm / (double)(*S);   // linspace sets the LAST point to `stop` exactly; with S == 1 y[1] is that point
 }
 
-template <int MODEL, typename Real, bool G64>
+template <int MODEL, typename Real, int G64>
 static int launch_slice_t(void* x, void* v, void* q, long long n, long long path_offset, int init, double v_init, int nsteps,
                           int slice_index, double forward, uint64_t seed, const LogsvConsts* lc, const HestonConsts* hc,
                           double* moments_out, cudaStream_t st, P2pCtx* p2p = nullptr) {
@@ -817,15 +887,29 @@ static int launch_slice_t(void* x, void* v, void* q, long long n, long long path
   return 0;
 }
 
+// B200SV_GAUSS_* bits -> GaussMode (philox.cuh); -1 = contradictory
+static int gauss_mode(int flags) {
+  const bool g64 = flags & B200SV_GAUSS_F64, paired = flags & B200SV_GAUSS_F64_PAIRED;
+  if (g64 && paired) return -1;
+  return paired ? kGaussF64Paired : (g64 ? kGaussF64 : kGaussF32);
+}
+
 template <int MODEL>
 static int launch_slice(void* x, void* v, void* q, long long n, long long path_offset, int init, double v_init, int nsteps,
                         int slice_index, double forward, uint64_t seed, int flags, const LogsvConsts* lc, const HestonConsts* hc,
                         double* moments_out, cudaStream_t st, P2pCtx* p2p = nullptr) {
-  const bool f32 = flags & B200SV_STATE_F32, g64 = flags & B200SV_GAUSS_F64;
-  if (!f32 && !g64) return launch_slice_t<MODEL, double, false>(x, v, q, n, path_offset, init, v_init, nsteps, slice_index, forward, seed, lc, hc, moments_out, st, p2p);
-  if (!f32 && g64) return launch_slice_t<MODEL, double, true>(x, v, q, n, path_offset, init, v_init, nsteps, slice_index, forward, seed, lc, hc, moments_out, st, p2p);
-  if (f32 && !g64) return launch_slice_t<MODEL, float, false>(x, v, q, n, path_offset, init, v_init, nsteps, slice_index, forward, seed, lc, hc, moments_out, st, p2p);
-  return launch_slice_t<MODEL, float, true>(x, v, q, n, path_offset, init, v_init, nsteps, slice_index, forward, seed, lc, hc, moments_out, st, p2p);
+  const bool f32 = flags & B200SV_STATE_F32;
+  const int g = gauss_mode(flags);
+  if (g < 0) return fail(-1, "invalid argument: B200SV_GAUSS_F64 and B200SV_GAUSS_F64_PAIRED are mutually exclusive");
+#define B200SV_SLICE_CASE(REAL, G) \
+  return launch_slice_t<MODEL, REAL, G>(x, v, q, n, path_offset, init, v_init, nsteps, slice_index, forward, seed, lc, hc, moments_out, st, p2p)
+  if (!f32 && g == kGaussF32) B200SV_SLICE_CASE(double, kGaussF32);
+  if (!f32 && g == kGaussF64) B200SV_SLICE_CASE(double, kGaussF64);
+  if (!f32 && g == kGaussF64Paired) B200SV_SLICE_CASE(double, kGaussF64Paired);
+  if (f32 && g == kGaussF32) B200SV_SLICE_CASE(float, kGaussF32);
+  if (f32 && g == kGaussF64) B200SV_SLICE_CASE(float, kGaussF64);
+  return fail(-1, "invalid argument: the paired Gaussian check mode needs fp64 state");
+#undef B200SV_SLICE_CASE
 }
 
 // kinds: bit 0 = some 'C'/'P', bit 1 = some 'IC'/'IP' in this slice; 0 = unknown (device-level callers) -> general kernel
@@ -1230,10 +1314,14 @@ int b200sv_device_normals(uint64_t seed, long long path0, long long n, int slice
   const size_t nb = sizeof(double) * (size_t)n * nsteps;
   B200SV_CUDA(cudaMallocAsync(&d, 2 * nb, st));
   const int blocks = (int)((n + 127) / 128);
-  if (flags & B200SV_GAUSS_F64)
-    device_normals_kernel<true><<<blocks, 128, 0, st>>>(seed, (unsigned long long)path0, n, (unsigned)slice, nsteps, d, d + (size_t)n * nsteps);
+  const int g = gauss_mode(flags);
+  B200SV_REQUIRE(g >= 0, "B200SV_GAUSS_F64 and B200SV_GAUSS_F64_PAIRED are mutually exclusive");
+  if (g == kGaussF64)
+    device_normals_kernel<kGaussF64><<<blocks, 128, 0, st>>>(seed, (unsigned long long)path0, n, (unsigned)slice, nsteps, d, d + (size_t)n * nsteps);
+  else if (g == kGaussF64Paired)
+    device_normals_kernel<kGaussF64Paired><<<blocks, 128, 0, st>>>(seed, (unsigned long long)path0, n, (unsigned)slice, nsteps, d, d + (size_t)n * nsteps);
   else
-    device_normals_kernel<false><<<blocks, 128, 0, st>>>(seed, (unsigned long long)path0, n, (unsigned)slice, nsteps, d, d + (size_t)n * nsteps);
+    device_normals_kernel<kGaussF32><<<blocks, 128, 0, st>>>(seed, (unsigned long long)path0, n, (unsigned)slice, nsteps, d, d + (size_t)n * nsteps);
   int rc = check_launch("device_normals_kernel");
   if (rc == 0) {
     cudaError_t e = cudaMemcpyAsync(z0, d, nb, cudaMemcpyDeviceToHost, st);
@@ -1243,6 +1331,22 @@ int b200sv_device_normals(uint64_t seed, long long path0, long long n, int slice
   cudaFreeAsync(d, st);
   cudaError_t e = cudaStreamSynchronize(st);
   if (rc == 0 && e != cudaSuccess) rc = fail(-2, std::string("sync: ") + cudaGetErrorString(e));
+  return rc;
+}
+
+int b200sv_debug_exp_pair_scaled(const double* Ls, long long n, double* out /* 2n */) {
+  B200SV_REQUIRE(Ls && out && n >= 1, "null pointer / n");
+  cudaStream_t st = 0;
+  double *dl = nullptr, *dout = nullptr;
+  B200SV_CUDA(cudaMallocAsync(&dl, sizeof(double) * n, st));
+  B200SV_CUDA(cudaMallocAsync(&dout, sizeof(double) * 2 * n, st));
+  B200SV_CUDA(cudaMemcpyAsync(dl, Ls, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  exp_pair_scaled_kernel<<<(int)((n + 127) / 128), 128, 0, st>>>(dl, n, dout);
+  int rc = check_launch("exp_pair_scaled_kernel");
+  if (rc == 0) B200SV_CUDA(cudaMemcpyAsync(out, dout, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, st));
+  cudaFreeAsync(dl, st);
+  cudaFreeAsync(dout, st);
+  B200SV_CUDA(cudaStreamSynchronize(st));
   return rc;
 }
 

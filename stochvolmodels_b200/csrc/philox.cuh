@@ -8,16 +8,21 @@
 //   key     = (seed_lo, seed_hi)
 //   counter = (path_lo, path_hi, call, slice)       path = GLOBAL path id => results independent of the
 //                                                   GPU count / grid / block size
-//   gauss f64: call = step;      u1 = 2 - d(r0,r1) in (0,1], u2 = d(r2,r3) - 1 in [0,1),
+//   gauss f64: call = step;      u1 = 2 - d(r0,r1|1) in (0,1), u2 = d(r2,r3) - 1 in [0,1),
 //                                d(hi,lo) = double with exponent 0x3FF and mantissa (hi>>12):lo
-//                                Z0 = R cos(2 pi u2), Z1 = R sin(2 pi u2), R = sqrt(-2 ln u1)
+//                                Z0 = R cos(2 pi u2), Z1 = R sin(2 pi u2), R = sqrt(-2 ln u1)      (gauss64.cuh: table + polynomial fp64)
 //   gauss f32: call = step / 2;  even step uses (r0,r1), odd step (r2,r3);
 //                                u1 = fma(float(ra), 2^-32, 2^-33) in (0,1], angle = int32(rb) * pi * 2^-31
 //                                float Box-Muller through the SFU (lg2 / sin / cos approx), widened to Real
+//   gauss f64 paired (check mode): the f32 stream's words and layout, u1 = (ra + 1/2) 2^-32 and the same angle evaluated in fp64
 #pragma once
 #include <cstdint>
 
+#include "gauss64.cuh"
+
 namespace b200sv {
+
+enum GaussMode { kGaussF32 = 0, kGaussF64 = 1, kGaussF64Paired = 2 };
 
 __device__ __forceinline__ void mulhilo32(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
   // one IMAD.WIDE.U32; written in PTX so the 64-bit product is split without zero-extension adds
@@ -52,26 +57,12 @@ __device__ __forceinline__ void box_muller_f32(uint32_t ra, uint32_t rb, float& 
   z1 = rad * s;
 }
 
-// ---- double Box-Muller ------------------------------------------------------------------------------
-__device__ __forceinline__ double u52(uint32_t hi, uint32_t lo) {   // [1, 2)
-  return __hiloint2double((int)(0x3FF00000u | (hi >> 12)), (int)lo);
-}
-__device__ __forceinline__ void box_muller_f64(uint4 r, double& z0, double& z1) {
-  const double u1 = 2.0 - u52(r.x, r.y);   // (0, 1]
-  const double u2 = u52(r.z, r.w) - 1.0;   // [0, 1)
-  const double rad = sqrt(-2.0 * log(u1));
-  double s, c;
-  sincospi(2.0 * u2, &s, &c);
-  z0 = rad * c;
-  z1 = rad * s;
-}
-
 // Per-path generator that hands out one (Z0, Z1) pair per time step in the order defined above.
-template <typename Real, bool GAUSS64>
+template <typename Real, int MODE>
 struct StepNormals;
 
 template <typename Real>
-struct StepNormals<Real, true> {
+struct StepNormals<Real, kGaussF64> {
   uint2 key;
   uint32_t plo, phi, slice;
   __device__ __forceinline__ StepNormals(uint64_t seed, uint64_t path, uint32_t slice_)
@@ -79,14 +70,14 @@ struct StepNormals<Real, true> {
   // one step
   __device__ __forceinline__ void get(uint32_t step, Real& z0, Real& z1) {
     double a, b;
-    box_muller_f64(philox4x32_10(make_uint4(plo, phi, step, slice), key), a, b);
+    box_muller_f64_fast(philox4x32_10(make_uint4(plo, phi, step, slice), key), a, b);
     z0 = (Real)a;
     z1 = (Real)b;
   }
 };
 
-template <typename Real>
-struct StepNormals<Real, false> {
+template <typename Real, int MODE>
+struct StepNormals {            // kGaussF32 and kGaussF64Paired: two steps per Philox call
   uint2 key;
   uint32_t plo, phi, slice;
   __device__ __forceinline__ StepNormals(uint64_t seed, uint64_t path, uint32_t slice_)
@@ -98,6 +89,16 @@ struct StepNormals<Real, false> {
 #else
     const uint4 r = philox4x32_10(make_uint4(plo, phi, call, slice), key);
 #endif
+    if constexpr (MODE == kGaussF64Paired) {
+      double x0, x1, y0, y1;
+      box_muller_f64_u32(r.x, r.y, x0, x1);
+      box_muller_f64_u32(r.z, r.w, y0, y1);
+      a0 = (Real)x0;
+      a1 = (Real)x1;
+      b0 = (Real)y0;
+      b1 = (Real)y1;
+      return;
+    }
     float x0, x1, y0, y1;
 #if defined(B200SV_ABLATE) && (B200SV_ABLATE & 2)   // tuning only: no SFU, uniforms scaled to [-1.7, 1.7] (NOT normal)
     x0 = __int2float_rn((int)r.x) * 8e-10f; x1 = __int2float_rn((int)r.y) * 8e-10f;

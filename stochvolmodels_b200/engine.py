@@ -21,12 +21,13 @@ def fresh_seed() -> int:
 
 
 def mc_flags(precision: str = "fp64", gauss: str = "fp32") -> int:
-    """precision: 'fp64' (default) | 'fp32' state arithmetic; gauss: 'fp32' (default, SFU Box-Muller) | 'fp64'."""
+    """precision: 'fp64' (default) | 'fp32' state arithmetic; gauss: 'fp32' (default, SFU Box-Muller) | 'fp64' (fp64 Box-Muller on
+    52-bit uniforms) | 'fp64_paired' (check mode: the default stream's 32-bit uniforms through the fp64 Box-Muller)."""
     if precision not in ("fp64", "fp32"):
         raise ValueError("precision must be 'fp64' or 'fp32'")
-    if gauss not in ("fp32", "fp64"):
-        raise ValueError("gauss must be 'fp32' or 'fp64'")
-    return (C.STATE_F32 if precision == "fp32" else C.STATE_F64) | (C.GAUSS_F64 if gauss == "fp64" else C.GAUSS_F32)
+    if gauss not in ("fp32", "fp64", "fp64_paired"):
+        raise ValueError("gauss must be 'fp32', 'fp64' or 'fp64_paired'")
+    return (C.STATE_F32 if precision == "fp32" else C.STATE_F64) | {"fp32": C.GAUSS_F32, "fp64": C.GAUSS_F64, "fp64_paired": C.GAUSS_F64_PAIRED}[gauss]
 
 
 def variable_code(variable_type) -> int:
@@ -185,6 +186,14 @@ def debug_exp_pair(L):
     L = C.f64(L)
     out = np.empty(2 * L.shape[0])
     C.call("b200sv_debug_exp_pair", C.dptr(L), L.shape[0], C.dptr(out))
+    return out[0::2].copy(), out[1::2].copy()
+
+
+def debug_exp_pair_scaled(Ls):
+    """(exp(Ls ln2/256), exp(-Ls ln2/256)) through the variant the fp64 stepper runs on its table-unit log-vol state."""
+    Ls = C.f64(Ls)
+    out = np.empty(2 * Ls.shape[0])
+    C.call("b200sv_debug_exp_pair_scaled", C.dptr(Ls), Ls.shape[0], C.dptr(out))
     return out[0::2].copy(), out[1::2].copy()
 
 

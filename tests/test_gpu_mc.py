@@ -37,6 +37,20 @@ def test_exp_pair_accuracy(cuda_lib):
     assert rel_p.max() < 4.5e-16 and rel_m.max() < 4.5e-16, (rel_p.max(), rel_m.max())
 
 
+def test_exp_pair_scaled_accuracy(cuda_lib):
+    """the stepper's exp pair on table units Ls = L*256/ln2, against exp in extended precision of the SAME argument Ls*ln2/256"""
+    from stochvolmodels_b200 import engine
+    rs = np.random.RandomState(1)
+    Ls = np.concatenate([np.linspace(-11000, 11000, 200001), rs.normal(0, 700, 100000), rs.uniform(-258530, 258530, 50000),
+                         [0.0, 0.5, -0.5, 1.5, 255.5, 256.0, -256.5, 258530.0, -258530.0, 1e-300, 3e5, -1e9]])
+    ep, em = engine.debug_exp_pair_scaled(Ls)
+    ld = np.longdouble
+    arg = np.clip(Ls, -258530.0, 258530.0).astype(ld) * (np.log(ld(2)) / ld(256))
+    rel_p = np.abs((ep.astype(ld) / np.exp(arg) - 1).astype(float))
+    rel_m = np.abs((em.astype(ld) / np.exp(-arg) - 1).astype(float))
+    assert rel_p.max() < 4.5e-16 and rel_m.max() < 4.5e-16, (rel_p.max(), rel_m.max())
+
+
 @pytest.mark.parametrize("tag", ["g5_c1", "inverse_eta", "btc_small", "qvar"])
 def test_logsv_fixed_randoms_vs_reference_golden(cuda_lib, tag):
     """b200sv_logsv_step_fixed + b200sv_mc_payoffs == logsv_mc_chain_pricer_fixed_randoms of the reference."""
@@ -108,6 +122,12 @@ def test_device_normals_match_oracle_restatement(cuda_lib):
         o0, o1 = mc.device_normals(10, ids, slice_idx, nsteps, "f32")
         np.testing.assert_allclose(z0, o0, rtol=0, atol=2e-5)          # SFU lg2/sin/cos vs libm float
         np.testing.assert_allclose(z1, o1, rtol=0, atol=2e-5)
+        p0, p1 = engine.device_normals(10, int(ids[0]), ids.shape[0], slice_idx, nsteps, C.GAUSS_F64_PAIRED)
+        o0, o1 = mc.device_normals(10, ids, slice_idx, nsteps, "f64_paired")
+        np.testing.assert_allclose(p0, o0, rtol=0, atol=5e-15)         # same 32-bit uniforms, fp64 arithmetic
+        np.testing.assert_allclose(p1, o1, rtol=0, atol=5e-15)
+        np.testing.assert_allclose(z0, p0, rtol=0, atol=2e-5)          # ... which the SFU float draws approximate
+        np.testing.assert_allclose(z1, p1, rtol=0, atol=2e-5)
     z = np.concatenate([a.ravel() for a in engine.device_normals(99, 0, 1 << 20, 0, 4, C.GAUSS_F32)])
     n = z.size
     assert abs(z.mean()) < 4 / np.sqrt(n) and abs(z.var() - 1) < 4 * np.sqrt(2 / n) and abs(np.mean(z ** 4) - 3) < 4 * np.sqrt(96 / n)
