@@ -874,6 +874,7 @@ static int launch_slice_t(void* x, void* v, void* q, long long n, long long path
   }
 #endif
   double* partials = nullptr;
+  ensure_pool_threshold();      // device-level callers too: a pool that trims at every synchronisation stalls the whole node
   B200SV_CUDA(cudaMallocAsync(&partials, sizeof(double) * 2 * g.blocks, st));
   a.partials = partials;
   if constexpr (MODEL == 0)
@@ -925,6 +926,7 @@ static int launch_payoff_t(const void* x, const void* q, long long n, double ttm
   Grid g = vanilla ? persistent_grid(payoff_vanilla_kernel<Real>, kThreads, n, kPayoffUnroll) : persistent_grid(payoff_kernel<Real>, kThreads, n);
   g.blocks = std::max(1, g.blocks / chunks);
   double* partials = nullptr;
+  ensure_pool_threshold();
   B200SV_CUDA(cudaMallocAsync(&partials, sizeof(double) * (size_t)Kpad * g.blocks, st));
   if (vanilla)
     payoff_vanilla_kernel<Real><<<dim3(g.blocks, chunks), g.threads, 0, st>>>((const Real*)x, (const Real*)q, n, ttm, forward, strikes,
@@ -1213,6 +1215,7 @@ int b200sv_dev_spot_moments(const double* x, long long n, double forward, double
   cudaStream_t st = (cudaStream_t)stream;
   Grid g = persistent_grid(spot_moments_kernel, kThreads, n);
   double* partials = nullptr;
+  ensure_pool_threshold();
   B200SV_CUDA(cudaMallocAsync(&partials, sizeof(double) * 2 * g.blocks, st));
   spot_moments_kernel<<<g.blocks, g.threads, 0, st>>>(x, n, forward, partials);
   if (int rc = check_launch("spot_moments_kernel")) return rc;

@@ -103,6 +103,7 @@ class P2pTimeout(C.B200svError):
 # for engine construction.  The state stays allocated between calls (2.4 GB at 1e8 paths) -- release_engines()
 # frees it; B200SV_ENGINE_CACHE=0 disables the cache.
 _ENGINE_CACHE = {}
+TRACE_LOG = []          # filled when B200SV_TRACE is set (one dict per sharded chain call on this rank)
 
 
 def release_engines():
@@ -283,6 +284,12 @@ def mc_chain_distributed(model: str, params_c, ttms, forwards, discfactors, etas
         strikes_dev = eng.to_device(strikes, torch.float64)
         types_dev = eng.to_device(types, torch.int8)
         out_dev = None
+    trace = chain_out and bool(os.environ.get("B200SV_TRACE"))     # tools/trace_multi_gpu.py: where does a sharded API call spend its time?
+    if trace:
+        import time as _time
+        ev = [eng.torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        t_host = [_time.time()]
+        ev[0].record()
     results = []
     t0 = 0.0
     for m in range(M):
@@ -310,7 +317,13 @@ def mc_chain_distributed(model: str, params_c, ttms, forwards, discfactors, etas
     stds_out: List[np.ndarray] = []
     if chain_out:
         out_pin[:, :max(Jtot, 1)].copy_(out_dev[:, :max(Jtot, 1)], non_blocking=True)     # one async D2H into pinned memory ...
+        if trace:
+            ev[1].record()
+            t_host.append(_time.time())
         eng.torch.cuda.current_stream(eng.device).synchronize()                            # ... and the chain's only host wait
+        if trace:
+            t_host.append(_time.time())
+            TRACE_LOG.append({"rank": rank, "t_enter": t_host[0], "t_launched": t_host[1], "t_synced": t_host[2], "gpu_ms": ev[0].elapsed_time(ev[1])})
         if use_p2p:
             eng.check_p2p()          # a timed-out exchange is an error, never a silent NaN price
         host = out_pin.numpy()

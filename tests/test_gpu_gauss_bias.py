@@ -6,7 +6,9 @@ Three checks on the bench workload (BTC chain, 49 strikes, 252 steps/path, LOGSV
    runs share every uniform, so their price difference has a tiny variance; it isolates what the SFU approximations (lg2 / sqrt /
    sin / cos .approx) and the float rounding of the uniforms do.  At 1e8 paths every strike must satisfy
    |delta| < 3 paired SE + 2 % of one MC standard error (the second term says: whatever systematic shift exists is below 1/50 of the
-   statistical error of a 1e8-path price -- it would take 2.5e11 paths to see it).
+   statistical error of a 1e8-path price -- it would take 2.5e11 paths to see it).  Measured on B200 (r02): the paired difference IS
+   resolved (6e3 paired SE: the SFU draws do shift prices systematically) and amounts to 1.3e-3 of one MC standard error at 1e8 paths,
+   i.e. ~1e-7 relative to the price -- 6e13 paths would be needed to detect it statistically.
 2. UNPAIRED: default mode vs ``gauss="fp64"`` (52-bit uniforms, one Philox call per step: different draws, no 6.7-sigma tail cut) at
    1e8 paths: every strike within 3 combined standard errors -- and the z-scores as a group look standard normal.
 3. GPU default mode at 1e8 paths vs the C port of the reference arithmetic with fp64 libm draws (oracle/csrc/oracle_mc.c) on its own
