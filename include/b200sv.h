@@ -193,6 +193,22 @@ int b200sv_dev_logsv_step_fixed(double* x, double* sigma, double* qvar, const do
 int b200sv_dev_heston_step_fixed(double* x, double* var, double* qvar, const double* W0, const double* W1, int S,
                                  long long N, double dt, const b200sv_heston_params* params, void* stream);
 
+/* Rough-LogSV multi-factor Monte Carlo chain (Markovian lift of the rough kernel, 1 <= n_factors <= 8):
+ * rough_logsv_mc_chain_pricer_fixed_randoms (pricers/logsv_pricer.py:1164-1232) -> log_spot_full_combined
+ * (pricers/rough_logsv/split_simulation.py:466-479, f64 branch :340-361).  params[b].volvol carries the ORTHOGONAL vol-of-vol of set b
+ * (the reference's `orthog_vol`); weights / nodes are [B][n_factors].  Every maturity m restarts at t = 0 and runs nsteps[m] steps of size
+ * hs[m] (the reference's per-maturity `timegrids`), consuming rows [0, nsteps[m]) of the unit normals Z0 / Z1 (host, row-major
+ * [z_rows][nb_path]); Z0 == Z1 == NULL draws them in-kernel from the Philox stream of csrc/philox.cuh (seed, flags = B200SV_GAUSS_*).
+ * Outputs [B][J_total]: prices, "std errors" exactly as the reference returns them on this route -- discfactor * nanstd(payoff), NOT
+ * divided by sqrt(nb_path) (it calls compute_mc_vars_payoff with (1, nb_path) arrays, utils/mc_payoffs.py:88) -- and optionally Black
+ * implied vols (ivols_out may be NULL).  states_out (B == 1, may be NULL): [M][n_factors + 2][nb_path] = log-spot, factor values, quadratic
+ * variance at each maturity. */
+int b200sv_rough_logsv_mc_chain(const b200sv_logsv_params* params, int B, int n_factors, const double* weights, const double* nodes, int M,
+                                const double* ttms, const double* forwards, const double* discfactors, const int* offsets, const double* strikes,
+                                const int8_t* types, long long nb_path, const int* nsteps, const double* hs, const double* Z0, const double* Z1,
+                                long long z_rows, int variable_type, uint64_t seed, int flags, double* prices_out, double* stderr_out,
+                                double* ivols_out, double* states_out);
+
 /* moments_out[2] (device) = (sum over non-NaN paths of forward*exp(x), count) for externally produced float64 states. */
 int b200sv_dev_spot_moments(const double* x, long long n, double forward, double* moments_out, void* stream);
 

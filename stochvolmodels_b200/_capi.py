@@ -59,6 +59,8 @@ SIGNATURES = {
     "b200sv_heston_step_fixed": [_dp, _dp, _dp, _dp, _dp, c_int, c_longlong, c_double, _hp],
     "b200sv_logsv_vol_paths": [_lp, c_double, c_longlong, c_int, c_int, c_uint64, _dp, _dp],
     "b200sv_mc_payoffs": [_dp, _dp, c_longlong, c_double, c_double, _dp, _i8p, c_int, c_double, c_int, _dp, _dp],
+    "b200sv_rough_logsv_mc_chain": [_lp, c_int, c_int, _dp, _dp, c_int, _dp, _dp, _dp, _ip, _dp, _i8p, c_longlong, _ip, _dp, _dp, _dp, c_longlong,
+                                    c_int, c_uint64, c_int, _dp, _dp, _dp, _dp],
     "b200sv_device_normals": [c_uint64, c_longlong, c_longlong, c_int, c_int, c_int, _dp, _dp],
     "b200sv_dev_logsv_slice": [c_void_p, c_void_p, c_void_p, c_longlong, c_longlong, c_int, _lp, c_double, c_int, c_int, c_double,
                                c_int, c_double, c_uint64, c_int, c_void_p, c_void_p, c_void_p],

@@ -1078,6 +1078,8 @@ static int terminal_host(const b200sv_logsv_params* lp, const b200sv_heston_para
 
 }  // namespace b200sv
 
+#include "rough_kernels.cuh"
+
 using namespace b200sv;
 
 extern "C" {
@@ -1400,6 +1402,17 @@ int b200sv_logsv_vol_paths(const b200sv_logsv_params* params, double ttm, long l
   cudaError_t e = cudaStreamSynchronize(st);
   if (rc == 0 && e != cudaSuccess) rc = fail(-2, std::string("sync: ") + cudaGetErrorString(e));
   return rc;
+}
+
+// ---- rough-LogSV multi-factor MC (rough_kernels.cuh) ------------------------------------------------------------------------
+int b200sv_rough_logsv_mc_chain(const b200sv_logsv_params* params, int B, int n_factors, const double* weights, const double* nodes, int M,
+                                const double* ttms, const double* forwards, const double* discfactors, const int* offsets, const double* strikes,
+                                const int8_t* types, long long nb_path, const int* nsteps, const double* hs, const double* Z0, const double* Z1,
+                                long long z_rows, int variable_type, uint64_t seed, int flags, double* prices_out, double* stderr_out,
+                                double* ivols_out, double* states_out) {
+  B200SV_REQUIRE(params && weights && nodes && ttms && forwards && discfactors && offsets && nsteps && hs && prices_out && stderr_out, "null pointer");
+  return rough_chain_host(params, B, n_factors, weights, nodes, M, ttms, forwards, discfactors, offsets, strikes, types, nb_path, nsteps, hs, Z0, Z1,
+                          z_rows, variable_type, seed, flags, prices_out, stderr_out, ivols_out, states_out);
 }
 
 // ---- P2P mailbox (p2p.cuh) -----------------------------------------------------------------------------------------------

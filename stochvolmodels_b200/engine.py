@@ -116,6 +116,52 @@ def heston_mc_chain_batch(params_list: Sequence[C.HestonParamsC], ttms, forwards
     return prices, stds, ivols
 
 
+def rough_logsv_mc_chain(params_list, weights, nodes, ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms, nb_path: int, nsteps, hs,
+                         Z0=None, Z1=None, variable_type=1, seed: int = 0, flags: int = 0, with_ivols: bool = False, return_states: bool = False):
+    """B parameter sets through the rough-LogSV multi-factor chain MC (b200sv_rough_logsv_mc_chain).  ``weights`` / ``nodes``: [n] (shared)
+    or [B, n]; ``Z0`` / ``Z1``: host unit normals [rows >= max(nsteps), nb_path] or None (in-kernel Philox draws).
+    Returns (prices [B, J], std [B, J], ivols [B, J] | None, states [M, n + 2, nb_path] | None)."""
+    vt = variable_code(variable_type)
+    M, ttms, forwards, discfactors, offsets, strikes, types = _chain_arrays(ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms)
+    B = len(params_list)
+    arr = (C.LogsvParamsC * B)(*params_list)
+    weights, nodes = np.atleast_2d(C.f64(weights)), np.atleast_2d(C.f64(nodes))
+    if weights.shape != nodes.shape or weights.ndim != 2:
+        raise ValueError("weights and nodes must have the same 1-d (or [B, n]) shape")
+    n = weights.shape[1]
+    if weights.shape[0] == 1 and B > 1:
+        weights, nodes = np.repeat(weights, B, axis=0), np.repeat(nodes, B, axis=0)
+    if weights.shape[0] != B:
+        raise ValueError(f"weights / nodes must have {B} rows")
+    weights, nodes = np.ascontiguousarray(weights), np.ascontiguousarray(nodes)
+    nsteps = np.ascontiguousarray(nsteps, dtype=np.int32)
+    hs = C.f64(hs)
+    if nsteps.shape[0] != M or hs.shape[0] != M:
+        raise ValueError("nsteps and hs must have one entry per maturity")
+    z_rows = 0
+    if Z0 is not None or Z1 is not None:
+        if Z0 is None or Z1 is None:
+            raise ValueError("Z0 and Z1 must be supplied together")
+        Z0, Z1 = C.f64(Z0), C.f64(Z1)
+        if Z0.ndim != 2 or Z0.shape != Z1.shape or Z0.shape[1] != nb_path:
+            raise ValueError("Z0 and Z1 must be 2-d arrays [nb_steps, nb_path] of the same shape")
+        z_rows = Z0.shape[0]
+        if z_rows < int(nsteps.max()):
+            raise ValueError("Z0 / Z1 have fewer rows than the longest time grid")
+        if z_rows > int(nsteps.max()):          # the library uploads exactly max(nsteps) rows
+            Z0, Z1 = np.ascontiguousarray(Z0[: int(nsteps.max())]), np.ascontiguousarray(Z1[: int(nsteps.max())])
+            z_rows = int(nsteps.max())
+    J = strikes.shape[0]
+    prices, stds = np.empty((B, J)), np.empty((B, J))
+    ivols = np.empty((B, J)) if with_ivols else None
+    states = np.empty((M, n + 2, int(nb_path))) if return_states else None
+    C.call("b200sv_rough_logsv_mc_chain", arr, B, n, C.dptr(weights), C.dptr(nodes), M, C.dptr(ttms), C.dptr(forwards), C.dptr(discfactors),
+           C.iptr(offsets), C.dptr(strikes), C.i8ptr(types), int(nb_path), nsteps.ctypes.data_as(C._ip), C.dptr(hs),
+           C.dptr(Z0) if Z0 is not None else None, C.dptr(Z1) if Z1 is not None else None, int(z_rows), vt, int(seed) & 0xFFFFFFFFFFFFFFFF,
+           int(flags), C.dptr(prices), C.dptr(stds), C.dptr(ivols) if with_ivols else None, C.dptr(states) if return_states else None)
+    return prices, stds, ivols, states, offsets
+
+
 def logsv_terminal(params: C.LogsvParamsC, ttm: float, nb_path: int, nb_steps_per_year: int, is_spot_measure: bool, eta: float,
                    seed: int, flags: int):
     x, s, q = np.empty(nb_path), np.empty(nb_path), np.empty(nb_path)

@@ -53,7 +53,7 @@ class CalibrationEngine(Enum):
     """how model vols are produced inside the objective (reference :93-102)."""
     ANALYTIC = 1
     MC = 2
-    ROUGH_MC = 3                     # rough-vol MC: out of scope (SURVEY.md §2 row 12)
+    ROUGH_MC = 3                     # rough-LogSV multi-factor MC with fixed normals (reference logsv_pricer.py:266-289)
 
 
 class CalibrationError(RuntimeError):
@@ -166,14 +166,15 @@ class LogSvParameterCodec:
         from .logsv.vol_moments import fit_vol_backbone_to_varswaps
         from .logsv_pricer import LogSvParams
         p0 = self.params0
+        rough = dict(H=getattr(p0, "H", 0.5), nodes=getattr(p0, "nodes", None), weights=getattr(p0, "weights", None))   # reference :125-127
         if self.calibration_type == LogsvModelCalibrationType.PARAMS_WITH_VARSWAP_FIT:
-            out = LogSvParams(sigma0=p0.sigma0, theta=p0.theta, kappa1=p0.kappa1, kappa2=p0.kappa2, beta=pars[0], volvol=pars[1])
+            out = LogSvParams(sigma0=p0.sigma0, theta=p0.theta, kappa1=p0.kappa1, kappa2=p0.kappa2, beta=pars[0], volvol=pars[1], **rough)
             out.set_vol_backbone(fit_vol_backbone_to_varswaps(out, self.varswap_strikes))     # reference :145-160
             return out
         if self.calibration_type == LogsvModelCalibrationType.PARAMS4:
-            out = LogSvParams(sigma0=pars[0], theta=pars[1], kappa1=p0.kappa1, kappa2=p0.kappa2, beta=pars[2], volvol=pars[3])
+            out = LogSvParams(sigma0=pars[0], theta=pars[1], kappa1=p0.kappa1, kappa2=p0.kappa2, beta=pars[2], volvol=pars[3], **rough)
         elif self.calibration_type == LogsvModelCalibrationType.PARAMS5:
-            out = LogSvParams(sigma0=pars[0], theta=pars[1], kappa1=pars[2], kappa2=None, beta=pars[3], volvol=pars[4])
+            out = LogSvParams(sigma0=pars[0], theta=pars[1], kappa1=pars[2], kappa2=None, beta=pars[3], volvol=pars[4], **rough)
         else:
             raise NotImplementedError(f"{self.calibration_type}")
         # no vol_backbone on the trial point: the reference codec (logsv_pricer.py:112-137) builds PARAMS4 / PARAMS5 candidates without
@@ -269,6 +270,27 @@ def calibrate_logsv(pricer, option_chain, params0, params_min, params_max, is_ve
                                                         is_spot_measure, 1, True)
                 rows.append(to_flat_np_array(option_chain.compute_model_ivols_from_chain_data(model_prices=prices)))
             return np.vstack(rows)
+    elif calibration_engine == CalibrationEngine.ROUGH_MC:
+        # reference :528-533 + :266-289: fixed normals of get_randoms_for_rough_vol_chain_valuation; here the n + 1 finite-difference
+        # parameter sets of an optimizer step share ONE upload of them (or none: mc_randoms="philox" draws in-kernel on a fixed seed)
+        from .logsv_pricer import get_randoms_for_rough_vol_chain_valuation
+        if mc_randoms not in ("numpy", "philox"):
+            raise ValueError("mc_randoms must be 'numpy' or 'philox'")
+        if params0.weights is None or params0.nodes is None:
+            raise ValueError("ROUGH_MC needs params0.weights / params0.nodes (LogSvParams.approximate_kernel)")
+        Z0, Z1, grids = get_randoms_for_rough_vol_chain_valuation(ttms=ttms, nb_path=nb_path, nb_steps_per_year=nb_steps, seed=seed)
+        if mc_randoms == "philox":
+            Z0 = Z1 = None
+        nsteps = [int(g.size) - 1 for g in grids]
+        hs = [float(g[1] - g[0]) for g in grids]
+        flags = engine.mc_flags("fp64", "fp32")
+
+        def batch_vols(points: np.ndarray) -> np.ndarray:
+            sets = [codec.parse(p) for p in points]
+            _, _, ivols, _, _ = engine.rough_logsv_mc_chain([_params_c(s) for s in sets], params0.weights, params0.nodes, ttms, option_chain.forwards,
+                                                            option_chain.discfactors, option_chain.strikes_ttms, option_chain.optiontypes_ttms,
+                                                            nb_path, nsteps, hs, Z0, Z1, 1, seed, flags, with_ivols=True)
+            return ivols
     else:
         raise NotImplementedError(f"{calibration_engine}")
 

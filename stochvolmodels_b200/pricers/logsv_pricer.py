@@ -44,10 +44,26 @@ class LogSvParams(ModelParams):
     beta: float = -1.0
     volvol: float = 1.0
     vol_backbone: Any = None
+    H: float = 0.5                  # Hurst exponent of the rough extension (logsv_params.py:81); 1/2 = the article's model
+    weights: Any = None             # quadrature weights / nodes of the Markovian lift of the rough kernel (:82-83)
+    nodes: Any = None
 
     def __post_init__(self):
         if self.kappa2 is None:              # logsv_params.py:92-93
             self.kappa2 = self.kappa1 / self.theta
+        assert 1e-4 < self.H <= 0.5          # :94
+
+    def approximate_kernel(self, T: float) -> None:
+        """nodes / weights of the Markovian approximation of the rough kernel (logsv_params.py:96-118).  H in (0.49, 1/2] is the single
+        node 1e-3 with weight 1 (the non-rough dynamics).  Smaller H needs the reference's 'European' quadrature optimiser
+        (rough_logsv/rough_kernel.py:927, a 1200-line scipy optimisation outside the Monte Carlo hot path): it is not rebuilt here --
+        set ``weights`` / ``nodes`` from it (or any other quadrature rule) yourself."""
+        if 0.49 < self.H <= 0.5:
+            self.weights = np.array([1.0])
+            self.nodes = np.array([1e-3])
+            return
+        raise NotImplementedError("approximate_kernel for H <= 0.49 needs the reference's european_rule optimiser (out of the hot path): "
+                                  "assign params.weights / params.nodes directly")
 
     def to_dict(self) -> Dict[str, Any]:
         return asdict(self)
@@ -140,8 +156,22 @@ class LogSVPricer(ModelPricer):
                              nb_steps: Optional[int] = None, **kwargs) -> Tuple[List[np.ndarray], List[np.ndarray]]:
         """MC prices and standard errors, one array per maturity.  ``nb_steps`` is a PER-YEAR rate whose default is
         ``int(360*max(ttms)) + 1`` (reference quirk, logsv_pricer.py:427)."""
-        if kwargs.get("use_rough_mc"):
-            raise NotImplementedError("rough-vol MC is outside the B200 hot path (SURVEY.md §2 row 12)")
+        if kwargs.get("use_rough_mc"):          # reference :395-411 (needs `seed`; `nb_steps` is passed through as given)
+            assert "seed" in kwargs
+            gauss = kwargs.get("gauss")        # None: the reference's host-drawn RandomState normals; 'fp32' / 'fp64': in-kernel Philox
+            if gauss is None:
+                Z0, Z1, grid_ttms = get_randoms_for_rough_vol_chain_valuation(ttms=option_chain.ttms, nb_path=nb_path, nb_steps_per_year=nb_steps,
+                                                                              seed=kwargs["seed"])
+            else:
+                Z0 = Z1 = None
+                grid_ttms = [set_time_grid(ttm, nb_steps)[2] for ttm in option_chain.ttms]
+            return rough_logsv_mc_chain_pricer_fixed_randoms(ttms=option_chain.ttms, forwards=option_chain.forwards,
+                                                             discfactors=option_chain.discfactors, strikes_ttms=option_chain.strikes_ttms,
+                                                             optiontypes_ttms=option_chain.optiontypes_ttms, Z0=Z0, Z1=Z1, sigma0=params.sigma0,
+                                                             theta=params.theta, kappa1=params.kappa1, kappa2=params.kappa2, beta=params.beta,
+                                                             orthog_vol=params.volvol, weights=params.weights, nodes=params.nodes,
+                                                             timegrids=grid_ttms, variable_type=variable_type, nb_path=nb_path,
+                                                             seed=kwargs["seed"], gauss=gauss or "fp32")
         vol_backbone_etas = params.get_vol_backbone_etas(ttms=option_chain.ttms)
         return logsv_mc_chain_pricer(v0=params.sigma0, theta=params.theta, kappa1=params.kappa1, kappa2=params.kappa2,
                                      beta=params.beta, volvol=params.volvol, vol_backbone_etas=vol_backbone_etas,
@@ -327,6 +357,50 @@ def get_randoms_for_chain_valuation(ttms: np.ndarray, nb_path: int = 100000, nb_
     if device is not None:
         return DeviceRandoms(W0s, W1s, dts, device)
     return W0s, W1s, dts
+
+
+def get_randoms_for_rough_vol_chain_valuation(ttms: np.ndarray, nb_path: int = 100000, nb_steps_per_year: int = 360, seed: int = 10):
+    """(Z0, Z1, per-maturity time grids) of the rough-vol chain valuation (reference :1076-1097): one block of unit normals of the LAST
+    maturity's length from a local ``RandomState(seed)`` -- Z0 then Z1 -- whose first S_m rows every maturity m consumes."""
+    rng = np.random.RandomState(seed)
+    grid_ttms, nb_steps = [], 0
+    for ttm in ttms:
+        nb_steps, _, grid_t = set_time_grid(ttm, nb_steps_per_year)
+        grid_ttms.append(grid_t)
+    Z0 = rng.normal(0, 1, size=(nb_steps, nb_path))
+    Z1 = rng.normal(0, 1, size=(nb_steps, nb_path))
+    return Z0, Z1, grid_ttms
+
+
+def rough_logsv_mc_chain_pricer_fixed_randoms(ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms, Z0, Z1, sigma0: float, theta: float,
+                                              kappa1: float, kappa2: float, beta: float, orthog_vol: float, weights: np.ndarray, nodes: np.ndarray,
+                                              timegrids: List[np.ndarray], variable_type: VariableType = VariableType.LOG_RETURN,
+                                              debug: bool = False, nb_path: Optional[int] = None, seed: Optional[int] = None, gauss: str = "fp32",
+                                              return_states: bool = False):
+    """rough-LogSV chain prices by the multi-factor Strang-splitting scheme with caller-supplied normals (reference :1164-1232 ->
+    rough_logsv/split_simulation.py:466): every maturity restarts at t = 0 on ITS grid and uses the first rows of ``Z0`` / ``Z1``.
+    Returned "standard errors" are, as in the reference on this route, discfactor * nanstd(payoff) without the 1/sqrt(nb_path).
+    ``Z0 = Z1 = None`` (extra): the normals are drawn in-kernel (Philox stream keyed by ``seed``; ``nb_path`` required)."""
+    weights, nodes = np.asarray(weights, dtype=np.float64), np.asarray(nodes, dtype=np.float64)
+    assert weights.shape == nodes.shape and weights.ndim == 1            # :1188
+    if Z0 is not None:
+        nb_path = Z0.shape[1]
+    elif nb_path is None:
+        raise ValueError("nb_path is required when the normals are drawn in-kernel")
+    nsteps = [int(np.asarray(g).size) - 1 for g in timegrids]
+    hs = [float(np.asarray(g)[1] - np.asarray(g)[0]) for g in timegrids]             # split_simulation.py:346
+    params_c = engine.logsv_params_c(sigma0, theta, kappa1, kappa2, beta, orthog_vol)
+    prices, stds, _, states, offsets = engine.rough_logsv_mc_chain([params_c], weights, nodes, ttms, forwards, discfactors, strikes_ttms,
+                                                                   optiontypes_ttms, nb_path, nsteps, hs, Z0, Z1, variable_type,
+                                                                   engine.fresh_seed() if seed is None else int(seed),
+                                                                   engine.mc_flags("fp64", gauss), return_states=return_states or debug)
+    if debug:            # the reference's per-slice diagnostics (:1218-1220)
+        for m in range(len(nsteps)):
+            vol = weights @ states[m, 1:-1]
+            print(f"Number of paths with negative vol: {np.sum(vol < 0.0)}, nan vol: {np.count_nonzero(np.isnan(vol))}")
+            print(f"Mean spot Strand: {np.mean(np.exp(states[m, 0]))}, nan spots: {np.count_nonzero(np.isnan(states[m, 0]))}")
+    out = (C.split_chain(prices[0], offsets), C.split_chain(stds[0], offsets))
+    return out + (states,) if return_states else out
 
 
 def _fixed_randoms_chain_device(rnd: DeviceRandoms, ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms, params_c, etas,

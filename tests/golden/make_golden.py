@@ -567,7 +567,61 @@ def calibration() -> None:
 
 
 
+def rough_mc() -> None:
+    """rough-LogSV multi-factor MC with caller-supplied normals (pricers/logsv_pricer.py:1164-1232 ->
+    rough_logsv/split_simulation.py:466 log_spot_full_combined): per-maturity terminal states, prices and the route's 'std errors'."""
+    _import_reference()
+    from stochvolmodels.pricers import logsv_pricer as lp
+    from stochvolmodels.pricers.logsv.logsv_params import LogSvParams
+    from stochvolmodels.pricers.rough_logsv.split_simulation import log_spot_full_combined
+    K = np.array([0.8, 0.9, 1.0, 1.1, 1.2])
+    T = np.array(['P', 'P', 'C', 'C', 'C'])
+    TI = np.array(['IP', 'IP', 'IC', 'IC', 'IC'])
+    cases = {
+        "h030_n3": dict(params=LogSvParams(sigma0=0.8, theta=1.0, kappa1=3.0, kappa2=3.0, beta=0.15, volvol=1.8, H=0.3), ttms=np.array([0.1, 0.25]),
+                        forwards=np.array([1.0, 1.02]), discfactors=np.array([0.999, 0.99]), types=(T, T), npy=360, seed=3, nb_path=3000),
+        "h045_n2": dict(params=LogSvParams(sigma0=1.0, theta=1.0, kappa1=5.0, kappa2=5.0, beta=0.2, volvol=2.0, H=0.45), ttms=np.array([1.0 / 12.0, 0.25, 0.5]),
+                        forwards=np.ones(3), discfactors=np.ones(3), types=(T, TI, T), npy=252, seed=11, nb_path=2000),
+        "h050_n1": dict(params=LogSvParams(sigma0=0.5, theta=0.6, kappa1=2.0, kappa2=0.0, beta=-0.4, volvol=0.9, H=0.5), ttms=np.array([0.25]),
+                        forwards=np.array([100.0]), discfactors=np.array([0.97]), types=(T,), npy=360, seed=5, nb_path=2500),
+    }
+    for name, c in cases.items():
+        p = c["params"]
+        p.approximate_kernel(T=float(c["ttms"][-1]))
+        Z0, Z1, grids = lp.get_randoms_for_rough_vol_chain_valuation(ttms=c["ttms"], nb_path=c["nb_path"], nb_steps_per_year=c["npy"], seed=c["seed"])
+        M = len(c["ttms"])
+        strikes = tuple(K * c["forwards"][m] for m in range(M))
+        prices, stds = lp.rough_logsv_mc_chain_pricer_fixed_randoms(
+            ttms=c["ttms"], forwards=c["forwards"], discfactors=c["discfactors"], strikes_ttms=strikes, optiontypes_ttms=c["types"], Z0=Z0, Z1=Z1,
+            sigma0=p.sigma0, theta=p.theta, kappa1=p.kappa1, kappa2=p.kappa2, beta=p.beta, orthog_vol=p.volvol, weights=p.weights, nodes=p.nodes,
+            timegrids=grids)
+        out = dict(params=np.array([p.sigma0, p.theta, p.kappa1, p.kappa2, p.beta, p.volvol, p.H]), weights=p.weights, nodes=p.nodes, ttms=c["ttms"],
+                   forwards=c["forwards"], discfactors=c["discfactors"], npy=np.array(c["npy"]), seed=np.array(c["seed"]), nb_path=np.array(c["nb_path"]),
+                   nslices=np.array(M), Z0_head=Z0[:3, :5], Z1_head=Z1[:3, :5])
+        # terminal states per maturity, exactly as the chain pricer computes them (restart from t = 0 with the prefix of the normals)
+        N = p.nodes.size
+        volvol = np.sqrt(p.beta ** 2 + p.volvol ** 2)
+        rho = p.beta / volvol
+        v0 = np.full((N,), p.sigma0 / np.sum(p.weights))
+        v0_vec = np.repeat(v0[:, None], c["nb_path"], axis=1)
+        w_vec = np.repeat(p.weights[:, None], c["nb_path"], axis=1)
+        n_vec = np.repeat(p.nodes[:, None], c["nb_path"], axis=1)
+        for m in range(M):
+            S = grids[m].size - 1
+            ls, vol, qv = log_spot_full_combined(n_vec, w_vec, v0_vec, p.theta, p.kappa1, p.kappa2, 0.0, v0_vec.copy(), rho, volvol, grids[m],
+                                                 c["nb_path"], Z0[:S], Z1[:S])
+            out[f"grid_{m}"] = np.asarray(grids[m])
+            out[f"log_spot_{m}"], out[f"vol_{m}"], out[f"qv_{m}"] = ls, vol, qv
+            out[f"strikes_{m}"], out[f"types_{m}"] = strikes[m], c["types"][m]
+            out[f"prices_{m}"], out[f"stds_{m}"] = np.asarray(prices[m]), np.asarray(stds[m])
+        np.savez(os.path.join(OUT, f"rough_mc_{name}.npz"), **out)
+        print(name, "nodes", p.nodes, "weights", p.weights, "prices", [np.asarray(a) for a in prices][0])
+
+
 if __name__ == "__main__":
+    if "--only-rough" in sys.argv:
+        rough_mc()
+        sys.exit(0)
     if "--only-calib" in sys.argv:
         calibration()
         sys.exit(0)

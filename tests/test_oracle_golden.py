@@ -258,3 +258,27 @@ def test_logsv_vol_paths():
     assert tuple(g["method_shape"]) == (2, 4)
     # the module function at 360 steps/yr gives 9 rows for ttm = 0.02 (reference tests/test_logsv_characterization.py:638-660)
     assert mc.set_time_grid(0.02, 360)[0] + 1 == 9
+
+
+@pytest.mark.parametrize("name", ["h030_n3", "h045_n2", "h050_n1"])
+def test_rough_mc_oracle_vs_reference_golden(name):
+    """oracle/rough.py == the reference's rough-LogSV fixed-random chain pricer (terminal states per maturity, prices, 'std errors')"""
+    from oracle import rough
+    g = load_golden(f"rough_mc_{name}.npz")
+    sigma0, theta, kappa1, kappa2, beta, volvol, H = g["params"]
+    M, P = int(g["nslices"]), int(g["nb_path"])
+    Z0, Z1, grids = rough.rough_randoms(g["ttms"], P, int(g["npy"]), int(g["seed"]))
+    np.testing.assert_array_equal(Z0[:3, :5], g["Z0_head"])
+    np.testing.assert_array_equal(Z1[:3, :5], g["Z1_head"])
+    for m in range(M):
+        np.testing.assert_array_equal(grids[m], g[f"grid_{m}"])
+    prices, stds, states = rough.rough_chain_fixed(g["ttms"], g["forwards"], g["discfactors"], [g[f"strikes_{m}"] for m in range(M)],
+                                                   [g[f"types_{m}"] for m in range(M)], Z0, Z1, sigma0, theta, kappa1, kappa2, beta, volvol,
+                                                   g["weights"], g["nodes"], grids, return_states=True)
+    for m in range(M):
+        ls, vol, qv = states[m]
+        np.testing.assert_allclose(ls, g[f"log_spot_{m}"], rtol=0, atol=2e-12)        # the reference kernels are fastmath=True
+        np.testing.assert_allclose(vol, g[f"vol_{m}"], rtol=1e-11, atol=1e-13)
+        np.testing.assert_allclose(qv, g[f"qv_{m}"], rtol=1e-12, atol=0)
+        np.testing.assert_allclose(prices[m], g[f"prices_{m}"], rtol=1e-10, atol=1e-14)
+        np.testing.assert_allclose(stds[m], g[f"stds_{m}"], rtol=1e-9, atol=1e-14)
