@@ -4,8 +4,9 @@
 // data/option_chain.py:327-346 right after every price_chain / model_mc_price_chain in compute_chain_prices_with_vols,
 // model_pricer.py:109-120, and compute_mc_chain_implied_vols, :216-241).  That package is not in the reference tree, so bit-level
 // parity with it is unpinned; what the reference pins -- the quickstart vols 0.999577 / 0.995757 and flat-vol
-// round trips -- holds for any correct inversion.  One thread per quote: bracketed bisection on the OTM-equivalent call price
-// (80 halvings of [1e-8, 10], identical to the checker oracle/bsm.py so the two agree to the last bits), fp64 normcdf.
+// round trips -- holds for any correct inversion; the reference's own assertions about the step (flat-vol recovery 1e-10, chain round trip
+// 2e-10, single-option round trip 2e-12, slice / vanilla self-consistency 1e-12) are ported in tests/test_gpu_ivol_pins.py.  One thread per
+// quote: safeguarded Newton in total-vol space (black.cuh), fp64 normcdf; the checker oracle/bsm.py is an independent 80-step bisection.
 #include <cmath>
 #include <vector>
 

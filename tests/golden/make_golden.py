@@ -616,6 +616,22 @@ def rough_mc() -> None:
             out[f"prices_{m}"], out[f"stds_{m}"] = np.asarray(prices[m]), np.asarray(stds[m])
         np.savez(os.path.join(OUT, f"rough_mc_{name}.npz"), **out)
         print(name, "nodes", p.nodes, "weights", p.weights, "prices", [np.asarray(a) for a in prices][0])
+    # the reference's OWN regression fixture for this path (tests/test_rough_logsv_pricer_regression.py: BTC chain, H = 0.1, 10000 paths,
+    # seed 10, rtol 1e-7): expected prices copied from its .npz, plus the kernel nodes / weights its european_rule produces (the
+    # quadrature optimiser is host set-up code outside the hot path and is not rebuilt in the B200 package)
+    from stochvolmodels.data.sample_option_chains import get_btc_test_chain_data
+    chain = get_btc_test_chain_data()
+    p = LogSvParams(sigma0=0.377, theta=0.347, kappa1=1.29, kappa2=1.93, beta=2.45, volvol=1.81)
+    p.H = 0.1
+    p.approximate_kernel(T=chain.ttms[-1])
+    ref = np.load(os.path.join(os.path.dirname(REF_SRC), "src", "stochvolmodels", "tests", "test_rough_logsv_pricer_regression",
+                               "test_rough_logsv_pricer_pricing_regression.npz"))
+    out = dict(params=np.array([p.sigma0, p.theta, p.kappa1, p.kappa2, p.beta, p.volvol, p.H]), weights=p.weights, nodes=p.nodes,
+               nb_path=np.array(10000), npy=np.array(360), seed=np.array(10), nslices=np.array(len(chain.ttms)))
+    for m in range(len(chain.ttms)):
+        out[f"expected_prices_{m}"] = ref[f"option_prices_ttm_{m}"]
+    np.savez(os.path.join(OUT, "rough_mc_reference_regression.npz"), **out)
+    print("reference regression fixture: nodes", p.nodes, "weights", p.weights)
 
 
 if __name__ == "__main__":

@@ -282,3 +282,17 @@ def test_rough_mc_oracle_vs_reference_golden(name):
         np.testing.assert_allclose(qv, g[f"qv_{m}"], rtol=1e-12, atol=0)
         np.testing.assert_allclose(prices[m], g[f"prices_{m}"], rtol=1e-10, atol=1e-14)
         np.testing.assert_allclose(stds[m], g[f"stds_{m}"], rtol=1e-9, atol=1e-14)
+
+
+def test_rough_mc_oracle_vs_the_references_own_regression_fixture():
+    """the reference's own known-answer vector for this path (tests/test_rough_logsv_pricer_regression.py, rtol 1e-7): BTC chain, H = 0.1"""
+    from oracle import rough
+    from stochvolmodels_b200 import get_btc_test_chain_data
+    g = load_golden("rough_mc_reference_regression.npz")
+    chain = get_btc_test_chain_data()
+    sigma0, theta, kappa1, kappa2, beta, volvol, H = g["params"]
+    Z0, Z1, grids = rough.rough_randoms(chain.ttms, int(g["nb_path"]), int(g["npy"]), int(g["seed"]))
+    prices, _ = rough.rough_chain_fixed(chain.ttms, chain.forwards, chain.discfactors, chain.strikes_ttms, chain.optiontypes_ttms, Z0, Z1, sigma0, theta,
+                                        kappa1, kappa2, beta, volvol, g["weights"], g["nodes"], grids)
+    for m in range(int(g["nslices"])):
+        np.testing.assert_allclose(prices[m], g[f"expected_prices_{m}"], rtol=1e-7, atol=0)
