@@ -100,10 +100,14 @@ def test_single_option_round_trip_2e12(cuda_lib):
     iv = np.array([v[0] for v in iv])
     tv = V * np.sqrt(T)
     d1 = np.log(F / K) / tv + 0.5 * tv
-    vega_rel = np.exp(-0.5 * d1 * d1) * np.sqrt(T) * F / np.array([p[0] for p in prices]).clip(1e-300)     # d price / d vol relative to the price
-    well = vega_rel > 1e-2
-    assert well.mean() > 0.9
+    # conditioning: the input price carries an ABSOLUTE rounding error ~1e-16 F (it is F N(d1) - K N(d2)), so d vol = 1e-16 F / vega
+    vega = F * np.exp(-0.5 * d1 * d1) / np.sqrt(2.0 * np.pi) * np.sqrt(T)
+    well = vega / F > 2e-3
+    assert well.mean() > 0.5
     np.testing.assert_allclose(iv[well], V[well], rtol=0.0, atol=2.0e-12)
+    # everywhere else the inversion still returns the vol to the accuracy the quote allows
+    rest = ~well & (np.array([p[0] for p in prices]) > 1e-10) & np.isfinite(iv)
+    assert np.all(np.abs(iv[rest] - V[rest]) < 5e-15 * F[rest] / vega[rest] + 1e-13)
 
 
 def test_quickstart_vanilla_vol(cuda_lib):
