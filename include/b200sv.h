@@ -262,6 +262,17 @@ int b200sv_logsv_mgf_grid(const double* phi, const double* psi, int P, double dt
                           const b200sv_logsv_params* params, double eta, int is_spot_measure, int expansion_order,
                           double* log_mgf_out);
 
+/* func_a_ode_quadratic_terms (pricers/logsv/affine_expansion.py:67-184): the dense coefficient tensors of A' = A^T M^(k) A + L A + H for
+ * P transform points, n = 3 (FIRST) or 5 (SECOND): M_out complex [P][n][n][n] (symmetric in the last two indices), L_out [P][n][n],
+ * H_out [P][n], interleaved (re, im).  psi may be NULL (zeros).  Parity entry: the pricing kernels integrate the same rows in sparse form. */
+int b200sv_logsv_ode_terms(const double* phi, const double* psi, int P, const b200sv_logsv_params* params, double eta, int is_spot_measure,
+                           int expansion_order, double* M_out, double* L_out, double* H_out);
+/* func_rhs (affine_expansion.py:187-205) evaluated by the production right-hand side at A [P][n] complex -> rhs_out [P][n] complex. */
+int b200sv_logsv_ode_rhs(const double* phi, const double* psi, int P, const double* A, const b200sv_logsv_params* params, double eta,
+                         int is_spot_measure, int expansion_order, double* rhs_out);
+/* func_rhs with the reference's own signature (caller-supplied dense complex tensors M [n][n][n], L [n][n], H [n]; A [P][n]) */
+int b200sv_ode_rhs_dense(const double* A, int P, int n, const double* M, const double* L, const double* H, double* rhs_out);
+
 /* replaces compute_heston_mgf_grid (pricers/heston_pricer.py:183-214); a, b in/out complex128[P]. */
 int b200sv_heston_mgf_grid(const double* phi, const double* psi, int P, double dtau, double* a_inout, double* b_inout,
                            const b200sv_heston_params* params, double* log_mgf_out);

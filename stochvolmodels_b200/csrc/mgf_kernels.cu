@@ -759,6 +759,68 @@ static void launch_logsv_mgf(int tpb, int nb, cudaStream_t st, const cd* phi, co
   }
 }
 
+// dense M / L / H of affine_expansion.py:139-184 from the row tables (parity entry b200sv_logsv_ode_terms)
+template <int N>
+__global__ void logsv_ode_terms_kernel(const cd* __restrict__ phi, const cd* __restrict__ psi, int P, LogsvModel m, cd* __restrict__ M_out,
+                                       cd* __restrict__ L_out, cd* __restrict__ H_out) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const cd ph = phi[p], ps = psi ? psi[p] : mk(0.0);
+  cd* Mo = M_out + (size_t)p * N * N * N;
+  cd* Lo = L_out + (size_t)p * N * N;
+  for (int i = 0; i < N * N * N; ++i) Mo[i] = mk(0.0);
+  for (int i = 0; i < N * N; ++i) Lo[i] = mk(0.0);
+  for (int k = 0; k < N; ++k) {
+    const LaneRow<N> r = make_lane_row<N>(k, m, ph, ps);
+    for (int t = 0; t < r.nq; ++t) {
+      const int i = r.qi[t], j = r.qj[t];
+      if (i == j) {
+        Mo[(k * N + i) * N + i] = mk(r.q[t]);
+      } else {          // the row tables carry off-diagonal pairs doubled: A_i A_j (M_ij + M_ji)
+        Mo[(k * N + i) * N + j] = mk(0.5 * r.q[t]);
+        Mo[(k * N + j) * N + i] = mk(0.5 * r.q[t]);
+      }
+    }
+    for (int t = 0; t < r.nl; ++t) Lo[k * N + r.li[t]] = r.l[t];
+    H_out[(size_t)p * N + k] = r.h;
+  }
+}
+
+// func_rhs (affine_expansion.py:187-205) through the production right-hand side
+template <int N>
+__global__ void logsv_ode_rhs_kernel(const cd* __restrict__ phi, const cd* __restrict__ psi, int P, LogsvModel m, const cd* __restrict__ A_in,
+                                     cd* __restrict__ rhs_out) {
+  __shared__ cd coef_smem[14 * 64];
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  store_coef<64>(coef_smem + threadIdx.x, make_coef(m, phi[p], psi ? psi[p] : mk(0.0)));
+  const CoefView<64> c{coef_smem + threadIdx.x};
+  cd A[N], out[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) A[k] = A_in[(size_t)p * N + k];
+  rhs<N, 64>(A, m, c, out);
+#pragma unroll
+  for (int k = 0; k < N; ++k) rhs_out[(size_t)p * N + k] = out[k];
+}
+
+// func_rhs with caller-supplied dense tensors (the reference signature): rhs[p][k] = A_p^T M[k] A_p + (L A_p)[k] + H[k]
+__global__ void ode_rhs_dense_kernel(const cd* __restrict__ A, int P, int n, const cd* __restrict__ M, const cd* __restrict__ L,
+                                     const cd* __restrict__ H, cd* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P * n) return;
+  const int p = idx / n, k = idx % n;
+  const cd* a = A + (size_t)p * n;
+  cd acc = mk(0.0);
+  for (int i = 0; i < n; ++i) {          // A^T M[k] A: row-by-row, as numpy's A0.T @ M[n_] @ A0 contracts (vector-matrix, then dot)
+    cd row = mk(0.0);
+    for (int j = 0; j < n; ++j) row = row + a[j] * M[((size_t)k * n + j) * n + i];
+    acc = acc + row * a[i];
+  }
+  cd lin = mk(0.0);
+  for (int j = 0; j < n; ++j) lin = lin + L[(size_t)k * n + j] * a[j];
+  out[idx] = (acc + lin) + H[k];
+}
+
 static int mgf_block_threads(int P) {
   int t = 4;
   while (t < 64 && t * 148 < P) t <<= 1;
@@ -1141,6 +1203,91 @@ int b200sv_logsv_mgf_grid(const double* phi, const double* psi, int P, double dt
   if (int rc = launched("logsv_mgf_kernel")) return rc;
   B200SV_CUDA(cudaMemcpyAsync(a_inout, d_a1.p, sizeof(cd) * (size_t)P * N, cudaMemcpyDeviceToHost, st));
   B200SV_CUDA(cudaMemcpyAsync(log_mgf_out, d_lm.p, sizeof(cd) * P, cudaMemcpyDeviceToHost, st));
+  B200SV_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// func_a_ode_quadratic_terms (pricers/logsv/affine_expansion.py:67-184) for a grid of transform points: the dense tensors the reference
+// builds per point -- M [n][n][n] (symmetric in the last two indices), L [n][n], H [n], complex -- written from the SAME row tables
+// (make_lane_row / make_coef) the ODE kernels integrate with, and func_rhs (:187-205) evaluated with the production rhs<>() at given A.
+// Parity entry points: nothing on the pricing path needs the dense tensors.
+int b200sv_logsv_ode_terms(const double* phi, const double* psi, int P, const b200sv_logsv_params* params, double eta, int is_spot_measure,
+                           int expansion_order, double* M_out, double* L_out, double* H_out) {
+  B200SV_REQUIRE(phi && params && M_out && L_out && H_out, "null pointer");
+  B200SV_REQUIRE(P >= 1, "P >= 1");
+  if (expansion_order != B200SV_ORDER_FIRST && expansion_order != B200SV_ORDER_SECOND) return fail(-4, "expansion_order not implemented");
+  const int N = expansion_order == B200SV_ORDER_FIRST ? 3 : 5;
+  const LogsvModel model = make_model(*params, eta, is_spot_measure != 0);
+  cudaStream_t st = 0;
+  ensure_pool_threshold();
+  DevBuf d_phi(st), d_psi(st), d_M(st), d_L(st), d_H(st);
+  const size_t nM = (size_t)P * N * N * N, nL = (size_t)P * N * N, nH = (size_t)P * N;
+  B200SV_CUDA(d_phi.alloc(sizeof(cd) * P));
+  B200SV_CUDA(d_psi.alloc(sizeof(cd) * P));
+  B200SV_CUDA(d_M.alloc(sizeof(cd) * nM));
+  B200SV_CUDA(d_L.alloc(sizeof(cd) * nL));
+  B200SV_CUDA(d_H.alloc(sizeof(cd) * nH));
+  B200SV_CUDA(cudaMemcpyAsync(d_phi.p, phi, sizeof(cd) * P, cudaMemcpyHostToDevice, st));
+  if (psi) B200SV_CUDA(cudaMemcpyAsync(d_psi.p, psi, sizeof(cd) * P, cudaMemcpyHostToDevice, st));
+  const cd* dpsi = psi ? d_psi.as<cd>() : nullptr;
+  if (N == 5)
+    logsv_ode_terms_kernel<5><<<(P + 63) / 64, 64, 0, st>>>(d_phi.as<cd>(), dpsi, P, model, d_M.as<cd>(), d_L.as<cd>(), d_H.as<cd>());
+  else
+    logsv_ode_terms_kernel<3><<<(P + 63) / 64, 64, 0, st>>>(d_phi.as<cd>(), dpsi, P, model, d_M.as<cd>(), d_L.as<cd>(), d_H.as<cd>());
+  if (int rc = launched("logsv_ode_terms_kernel")) return rc;
+  B200SV_CUDA(cudaMemcpyAsync(M_out, d_M.p, sizeof(cd) * nM, cudaMemcpyDeviceToHost, st));
+  B200SV_CUDA(cudaMemcpyAsync(L_out, d_L.p, sizeof(cd) * nL, cudaMemcpyDeviceToHost, st));
+  B200SV_CUDA(cudaMemcpyAsync(H_out, d_H.p, sizeof(cd) * nH, cudaMemcpyDeviceToHost, st));
+  B200SV_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int b200sv_logsv_ode_rhs(const double* phi, const double* psi, int P, const double* A, const b200sv_logsv_params* params, double eta,
+                         int is_spot_measure, int expansion_order, double* rhs_out) {
+  B200SV_REQUIRE(phi && A && params && rhs_out, "null pointer");
+  B200SV_REQUIRE(P >= 1, "P >= 1");
+  if (expansion_order != B200SV_ORDER_FIRST && expansion_order != B200SV_ORDER_SECOND) return fail(-4, "expansion_order not implemented");
+  const int N = expansion_order == B200SV_ORDER_FIRST ? 3 : 5;
+  const LogsvModel model = make_model(*params, eta, is_spot_measure != 0);
+  cudaStream_t st = 0;
+  ensure_pool_threshold();
+  DevBuf d_phi(st), d_psi(st), d_A(st), d_R(st);
+  B200SV_CUDA(d_phi.alloc(sizeof(cd) * P));
+  B200SV_CUDA(d_psi.alloc(sizeof(cd) * P));
+  B200SV_CUDA(d_A.alloc(sizeof(cd) * (size_t)P * N));
+  B200SV_CUDA(d_R.alloc(sizeof(cd) * (size_t)P * N));
+  B200SV_CUDA(cudaMemcpyAsync(d_phi.p, phi, sizeof(cd) * P, cudaMemcpyHostToDevice, st));
+  if (psi) B200SV_CUDA(cudaMemcpyAsync(d_psi.p, psi, sizeof(cd) * P, cudaMemcpyHostToDevice, st));
+  B200SV_CUDA(cudaMemcpyAsync(d_A.p, A, sizeof(cd) * (size_t)P * N, cudaMemcpyHostToDevice, st));
+  const cd* dpsi = psi ? d_psi.as<cd>() : nullptr;
+  if (N == 5)
+    logsv_ode_rhs_kernel<5><<<(P + 63) / 64, 64, 0, st>>>(d_phi.as<cd>(), dpsi, P, model, d_A.as<cd>(), d_R.as<cd>());
+  else
+    logsv_ode_rhs_kernel<3><<<(P + 63) / 64, 64, 0, st>>>(d_phi.as<cd>(), dpsi, P, model, d_A.as<cd>(), d_R.as<cd>());
+  if (int rc = launched("logsv_ode_rhs_kernel")) return rc;
+  B200SV_CUDA(cudaMemcpyAsync(rhs_out, d_R.p, sizeof(cd) * (size_t)P * N, cudaMemcpyDeviceToHost, st));
+  B200SV_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int b200sv_ode_rhs_dense(const double* A, int P, int n, const double* M, const double* L, const double* H, double* rhs_out) {
+  B200SV_REQUIRE(A && M && L && H && rhs_out, "null pointer");
+  B200SV_REQUIRE(P >= 1 && n >= 1 && n <= 16, "P >= 1, 1 <= n <= 16");
+  cudaStream_t st = 0;
+  ensure_pool_threshold();
+  DevBuf d_A(st), d_M(st), d_L(st), d_H(st), d_R(st);
+  B200SV_CUDA(d_A.alloc(sizeof(cd) * (size_t)P * n));
+  B200SV_CUDA(d_M.alloc(sizeof(cd) * (size_t)n * n * n));
+  B200SV_CUDA(d_L.alloc(sizeof(cd) * (size_t)n * n));
+  B200SV_CUDA(d_H.alloc(sizeof(cd) * n));
+  B200SV_CUDA(d_R.alloc(sizeof(cd) * (size_t)P * n));
+  B200SV_CUDA(cudaMemcpyAsync(d_A.p, A, sizeof(cd) * (size_t)P * n, cudaMemcpyHostToDevice, st));
+  B200SV_CUDA(cudaMemcpyAsync(d_M.p, M, sizeof(cd) * (size_t)n * n * n, cudaMemcpyHostToDevice, st));
+  B200SV_CUDA(cudaMemcpyAsync(d_L.p, L, sizeof(cd) * (size_t)n * n, cudaMemcpyHostToDevice, st));
+  B200SV_CUDA(cudaMemcpyAsync(d_H.p, H, sizeof(cd) * n, cudaMemcpyHostToDevice, st));
+  ode_rhs_dense_kernel<<<(P * n + 127) / 128, 128, 0, st>>>(d_A.as<cd>(), P, n, d_M.as<cd>(), d_L.as<cd>(), d_H.as<cd>(), d_R.as<cd>());
+  if (int rc = launched("ode_rhs_dense_kernel")) return rc;
+  B200SV_CUDA(cudaMemcpyAsync(rhs_out, d_R.p, sizeof(cd) * (size_t)P * n, cudaMemcpyDeviceToHost, st));
   B200SV_CUDA(cudaStreamSynchronize(st));
   return 0;
 }

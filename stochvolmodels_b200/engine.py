@@ -235,6 +235,46 @@ def debug_exp_pair(L):
     return out[0::2].copy(), out[1::2].copy()
 
 
+def _c128(a):
+    return np.ascontiguousarray(a, dtype=np.complex128)
+
+
+def logsv_ode_terms(phi_grid, psi_grid, params: C.LogsvParamsC, eta: float, is_spot_measure: bool, order: int):
+    """dense (M [P,n,n,n], L [P,n,n], H [P,n]) of the coefficient ODEs over a transform grid (b200sv_logsv_ode_terms)."""
+    phi = _c128(np.atleast_1d(phi_grid))
+    psi = None if psi_grid is None else _c128(np.atleast_1d(psi_grid))
+    P, n = phi.shape[0], (3 if order == 1 else 5)
+    M, L, H = np.empty((P, n, n, n), np.complex128), np.empty((P, n, n), np.complex128), np.empty((P, n), np.complex128)
+    as_d = lambda a: a.view(np.float64).ctypes.data_as(C._dp)
+    C.call("b200sv_logsv_ode_terms", as_d(phi), as_d(psi) if psi is not None else None, P, byref(params), float(eta), int(bool(is_spot_measure)),
+           int(order), as_d(M), as_d(L), as_d(H))
+    return M, L, H
+
+
+def logsv_ode_rhs(phi_grid, psi_grid, A, params: C.LogsvParamsC, eta: float, is_spot_measure: bool, order: int):
+    """right-hand side A'MA + LA + H at A [P, n] through the production device function (b200sv_logsv_ode_rhs)."""
+    phi, A = _c128(np.atleast_1d(phi_grid)), _c128(np.atleast_2d(A))
+    psi = None if psi_grid is None else _c128(np.atleast_1d(psi_grid))
+    out = np.empty_like(A)
+    as_d = lambda a: a.view(np.float64).ctypes.data_as(C._dp)
+    C.call("b200sv_logsv_ode_rhs", as_d(phi), as_d(psi) if psi is not None else None, phi.shape[0], as_d(A), byref(params), float(eta),
+           int(bool(is_spot_measure)), int(order), as_d(out))
+    return out
+
+
+def ode_rhs_dense(A, M, L, H):
+    """func_rhs with caller-supplied dense tensors: A [P, n] (or [n]) -> rhs of the same shape (b200sv_ode_rhs_dense)."""
+    A0 = _c128(A)
+    A2, M, L, H = np.atleast_2d(A0), _c128(M), _c128(L), _c128(H)
+    n = A2.shape[1]
+    if M.shape != (n, n, n) or L.shape != (n, n) or H.shape != (n,):
+        raise ValueError("M, L, H must have shapes (n, n, n), (n, n), (n,)")
+    out = np.empty_like(A2)
+    as_d = lambda a: a.view(np.float64).ctypes.data_as(C._dp)
+    C.call("b200sv_ode_rhs_dense", as_d(A2), A2.shape[0], n, as_d(M), as_d(L), as_d(H), as_d(out))
+    return out.reshape(A0.shape)
+
+
 def debug_exp_pair_scaled(Ls):
     """(exp(Ls ln2/256), exp(-Ls ln2/256)) through the variant the fp64 stepper runs on its table-unit log-vol state."""
     Ls = C.f64(Ls)

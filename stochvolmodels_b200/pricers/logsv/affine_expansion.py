@@ -29,6 +29,22 @@ def _order_code(expansion_order) -> int:
     return v
 
 
+def func_a_ode_quadratic_terms(theta: float, kappa1: float, kappa2: float, beta: float, volvol: float, phi: complex, psi: complex,
+                               is_spot_measure: bool = True, expansion_order: ExpansionOrder = ExpansionOrder.FIRST,
+                               vol_backbone_eta: float = 1.0) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """(M, L, H) of the coefficient ODEs A' = A^T M^(k) A + L A + H, Eqs. (4.17)/(4.25) (affine_expansion.py:67-184; same default order
+    FIRST as the reference): dense complex tensors [n,n,n], [n,n], [n] written on the GPU from the row tables the ODE kernels integrate."""
+    order = _order_code(expansion_order)
+    M, L, H = engine.logsv_ode_terms(np.array([phi]), np.array([psi]), engine.logsv_params_c(theta, theta, kappa1, kappa2, beta, volvol),
+                                     vol_backbone_eta, is_spot_measure, order)
+    return M[0], L[0], H[0]
+
+
+def func_rhs(t: float, A0: np.ndarray, M, L: np.ndarray, H: np.ndarray) -> np.ndarray:
+    """right-hand side of the coefficient ODE system, Eq. (4.14), with caller-supplied (M, L, H) (affine_expansion.py:187-205; ``t`` unused)."""
+    return engine.ode_rhs_dense(A0, np.asarray(M), L, H)
+
+
 def compute_logsv_a_mgf_grid(ttm: float, phi_grid: np.ndarray, psi_grid: np.ndarray, theta_grid: np.ndarray, sigma0: float,
                              theta: float, kappa1: float, kappa2: float, beta: float, volvol: float,
                              variable_type: VariableType = VariableType.LOG_RETURN,

@@ -210,3 +210,27 @@ def test_mc_chain_implied_vols_api(cuda_lib):
     for m in range(2):
         assert np.all(downs[m] <= prices[m]) and np.all(prices[m] <= ups[m])
         assert np.all(down[m] <= mid[m] + 1e-12) and np.all(mid[m] <= up[m] + 1e-12) and np.all(np.abs(mid[m] - 1.0) < 0.1)
+
+
+def test_ode_terms_and_rhs_vs_reference_golden(cuda_lib):
+    """func_a_ode_quadratic_terms / func_rhs (affine_expansion.py:67-205) on the GPU against the reference's own outputs (mlh.npz: FIRST and
+    SECOND order, both measures, eta != 1, psi != 0): dense M / L / H from the kernels' row tables, the dense rhs, and the production
+    sparse rhs<>() -- all three must tell the same story."""
+    from stochvolmodels_b200 import engine
+    from stochvolmodels_b200.pricers.logsv.affine_expansion import ExpansionOrder, func_a_ode_quadratic_terms, func_rhs
+    g = load_golden("mlh.npz")
+    theta, kappa1, kappa2, beta, volvol = g["params"]
+    for k in range(int(g["ncases"])):
+        order, spot, eta, pr, pi, sr, si = g[f"case{k}_in"]
+        phi, psi = complex(pr, pi), complex(sr, si)
+        M, L, H = func_a_ode_quadratic_terms(theta, kappa1, kappa2, beta, volvol, phi, psi, is_spot_measure=bool(spot),
+                                             expansion_order=ExpansionOrder(int(order)), vol_backbone_eta=eta)
+        np.testing.assert_allclose(M, g[f"case{k}_M"], rtol=0, atol=5e-15)
+        np.testing.assert_allclose(L, g[f"case{k}_L"], rtol=1e-15, atol=5e-15)
+        np.testing.assert_allclose(H, g[f"case{k}_H"], rtol=1e-15, atol=5e-15)
+        n = M.shape[0]
+        A = (np.arange(1, n + 1) * (0.1 - 0.05j)).astype(np.complex128)
+        np.testing.assert_allclose(func_rhs(0.0, A, g[f"case{k}_M"], g[f"case{k}_L"], g[f"case{k}_H"]), g[f"case{k}_rhs"], rtol=1e-14, atol=1e-14)
+        fast = engine.logsv_ode_rhs(np.array([phi]), np.array([psi]), A[None, :], engine.logsv_params_c(theta, theta, kappa1, kappa2, beta, volvol),
+                                    eta, bool(spot), int(order))
+        np.testing.assert_allclose(fast[0], g[f"case{k}_rhs"], rtol=1e-14, atol=1e-14)
