@@ -57,7 +57,22 @@ typedef struct {
   double v0, theta, kappa, rho, volvol;
 } b200sv_heston_params;
 
+/* pricers/hawkes_jd_pricer.py:41-65 HawkesJDParams (the sixteen model floats, in the order of the dataclass with lambda_p / lambda_m moved next
+ * to their intensities' parameters as listed here) */
+typedef struct {
+  double mu, sigma, shift_p, mean_p, shift_m, mean_m;
+  double lambda_p, theta_p, kappa_p, beta1_p, beta2_p;
+  double lambda_m, theta_m, kappa_m, beta1_m, beta2_m;
+} b200sv_hawkes_params;
+
 const char* b200sv_last_error(void);
+/* CUDA stream (cudaStream_t as void*) on which the calling thread's HOST-LEVEL calls enqueue their copies and kernels and on which they
+ * synchronise before returning; NULL (the default) = the legacy default stream.  Thread-local, like the error string: calls from different
+ * threads on different streams run concurrently.  (SURVEY.md 8b asked for a stream on every call; the device-level b200sv_dev_* calls take it
+ * as an argument, the host-level ones -- what a ctypes / cgo / JNI binding of the reference's functions binds -- take it from here so that
+ * their signatures stay the reference's argument lists.) */
+int b200sv_set_stream(void* stream);
+void* b200sv_get_stream(void);
 int b200sv_version(void);
 /* number of this library's kernels launched by the calling thread since the last reset (bench "gpu_launches") */
 long long b200sv_launch_count(void);
@@ -104,6 +119,11 @@ int b200sv_logsv_terminal(const b200sv_logsv_params* params, double ttm, long lo
                           double* qvar);
 
 /* replaces HestonPricer.simulate_terminal_values (pricers/heston_pricer.py:90-108). */
+/* the same with PER-PATH initial arrays (pricers/logsv_pricer.py:1007-1020 accepts length-nb_path x0 / sigma0 / qvar0): in/out host arrays;
+ * slice_index = Philox sub-stream (0 for a fresh start; m for the m-th consecutive call on one seed, as the chain pricer numbers its slices) */
+int b200sv_logsv_terminal_from_state(const b200sv_logsv_params* params, double ttm, long long nb_path, int nb_steps_per_year, int is_spot_measure,
+                                     double eta, uint64_t seed, int flags, int slice_index, double* x_inout, double* sigma_inout,
+                                     double* qvar_inout);
 int b200sv_heston_terminal(const b200sv_heston_params* params, double ttm, long long nb_path, int nb_steps_per_year,
                            uint64_t seed, int flags, int scheme, double* x, double* var, double* qvar);
 
@@ -208,6 +228,25 @@ int b200sv_rough_logsv_mc_chain(const b200sv_logsv_params* params, int B, int n_
                                 const int8_t* types, long long nb_path, const int* nsteps, const double* hs, const double* Z0, const double* Z1,
                                 long long z_rows, int variable_type, uint64_t seed, int flags, double* prices_out, double* stderr_out,
                                 double* ivols_out, double* states_out);
+
+/* Hawkes jump-diffusion Monte Carlo (pricers/hawkes_jd_pricer.py): 1800 steps per year (:752), state (x, lambda_p, lambda_m).
+ * b200sv_hawkesjd_mc_chain   = hawkesjd_mc_chain_pricer (:644-715): chained slices, forward-recentred payoffs on x; in-kernel draws (Philox;
+ *                              flags = B200SV_GAUSS_* for the normals, the jump clocks and sizes come from 32-bit uniforms through fp64 logs).
+ * b200sv_hawkesjd_terminal   = simulate_hawkesjd_terminal (:718-779) with in-kernel draws; use_initial_arrays != 0: the three host arrays hold the
+ *                              per-path initial state (in/out), else every path starts from (0, lambda_p, lambda_m) and the arrays are outputs.
+ * b200sv_hawkesjd_step_fixed = the same update on caller-supplied inputs in the reference's own form, row-major [S][N] host arrays:
+ *                              W0 = sqrt(dt) z, U_P / U_M = -ln(U)/dt, J_P / J_M = shift +- mean Exp(1) (:753-757) -- reference evaluation order,
+ *                              no FMA contraction (parity entry).
+ * b200sv_hawkesjd_device_draws exports, in that same form, what the in-kernel generator draws for paths [path0, path0 + n) of a slice. */
+int b200sv_hawkesjd_mc_chain(const b200sv_hawkes_params* params, int M, const double* ttms, const double* forwards, const double* discfactors,
+                             const int* offsets, const double* strikes, const int8_t* types, long long nb_path, int variable_type, uint64_t seed,
+                             int flags, double* prices_out, double* stderr_out);
+int b200sv_hawkesjd_terminal(const b200sv_hawkes_params* params, double ttm, long long nb_path, uint64_t seed, int flags, int slice_index,
+                             int use_initial_arrays, double* x_inout, double* lambda_p_inout, double* lambda_m_inout);
+int b200sv_hawkesjd_step_fixed(double* x, double* lambda_p, double* lambda_m, const double* W0, const double* U_P, const double* U_M,
+                               const double* J_P, const double* J_M, int S, long long N, double dt, const b200sv_hawkes_params* params);
+int b200sv_hawkesjd_device_draws(uint64_t seed, long long path0, long long n, int slice, int S, double dt, const b200sv_hawkes_params* params,
+                                 int flags, double* W0, double* U_P, double* U_M, double* J_P, double* J_M);
 
 /* moments_out[2] (device) = (sum over non-NaN paths of forward*exp(x), count) for externally produced float64 states. */
 int b200sv_dev_spot_moments(const double* x, long long n, double forward, double* moments_out, void* stream);

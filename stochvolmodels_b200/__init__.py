@@ -3,6 +3,7 @@ behind the reference's Pricer API.  See DESIGN.md / INTEGRATION.md.  There is no
 ``lib/libb200sv.so`` (built by ``python -m stochvolmodels_b200._build``) and a CUDA device."""
 from .data.option_chain import OptionChain, get_btc_test_chain_data
 from .pricers.calibration import CalibrationEngine, CalibrationError, ConstraintsType, LogsvModelCalibrationType
+from .pricers.hawkes_jd_pricer import HawkesJDParams, HawkesJDPricer
 from .pricers.heston_pricer import BTC_HESTON_PARAMS, HestonParams, HestonPricer
 from .pricers.logsv.affine_expansion import ExpansionOrder
 from .pricers.logsv_pricer import LOGSV_BTC_PARAMS, LogSvParams, LogSVPricer
@@ -10,5 +11,5 @@ from .pricers.model_pricer import ModelParams, ModelPricer
 from .utils.config import OptionType, VariableType
 
 __version__ = "0.1.0"
-__all__ = ["OptionChain", "get_btc_test_chain_data", "HestonParams", "HestonPricer", "BTC_HESTON_PARAMS", "ExpansionOrder",
+__all__ = ["HawkesJDParams", "HawkesJDPricer", "OptionChain", "get_btc_test_chain_data", "HestonParams", "HestonPricer", "BTC_HESTON_PARAMS", "ExpansionOrder",
            "LogSvParams", "LogSVPricer", "CalibrationEngine", "CalibrationError", "ConstraintsType", "LogsvModelCalibrationType", "LOGSV_BTC_PARAMS", "ModelParams", "ModelPricer", "OptionType", "VariableType"]

@@ -41,11 +41,18 @@ class B200svError(RuntimeError):
         self.message = message
 
 
+class HawkesParamsC(ctypes.Structure):
+    """b200sv_hawkes_params"""
+    _fields_ = [(k, c_double) for k in ("mu", "sigma", "shift_p", "mean_p", "shift_m", "mean_m", "lambda_p", "theta_p", "kappa_p", "beta1_p", "beta2_p",
+                                        "lambda_m", "theta_m", "kappa_m", "beta1_m", "beta2_m")]
+
+
 _dp = POINTER(c_double)
 _ip = POINTER(c_int)
 _i8p = POINTER(c_int8)
 _lp = POINTER(LogsvParamsC)
 _hp = POINTER(HestonParamsC)
+_kp = POINTER(HawkesParamsC)
 
 # name -> argtypes; every symbol declared in include/b200sv.h must be listed here (tests/test_capi_symbols.py checks it)
 SIGNATURES = {
@@ -54,6 +61,8 @@ SIGNATURES = {
     "b200sv_logsv_mc_chain_batch": [_lp, c_int, c_int, _dp, _dp, _dp, _dp, _ip, _dp, _i8p, c_longlong, c_int, c_int, c_uint64, c_int, _dp, _dp, _dp],
     "b200sv_heston_mc_chain_batch": [_hp, c_int, c_int, _dp, _dp, _dp, _ip, _dp, _i8p, c_longlong, c_int, c_uint64, c_int, c_int, _dp, _dp, _dp],
     "b200sv_logsv_terminal": [_lp, c_double, c_longlong, c_int, c_int, c_double, c_uint64, c_int, _dp, _dp, _dp],
+    "b200sv_logsv_terminal_from_state": [_lp, c_double, c_longlong, c_int, c_int, c_double, c_uint64, c_int, c_int, _dp, _dp, _dp],
+    "b200sv_set_stream": [c_void_p],
     "b200sv_heston_terminal": [_hp, c_double, c_longlong, c_int, c_uint64, c_int, c_int, _dp, _dp, _dp],
     "b200sv_logsv_step_fixed": [_dp, _dp, _dp, _dp, _dp, c_int, c_longlong, c_double, _lp, c_double, c_int],
     "b200sv_heston_step_fixed": [_dp, _dp, _dp, _dp, _dp, c_int, c_longlong, c_double, _hp],
@@ -61,6 +70,10 @@ SIGNATURES = {
     "b200sv_mc_payoffs": [_dp, _dp, c_longlong, c_double, c_double, _dp, _i8p, c_int, c_double, c_int, _dp, _dp],
     "b200sv_rough_logsv_mc_chain": [_lp, c_int, c_int, _dp, _dp, c_int, _dp, _dp, _dp, _ip, _dp, _i8p, c_longlong, _ip, _dp, _dp, _dp, c_longlong,
                                     c_int, c_uint64, c_int, _dp, _dp, _dp, _dp],
+    "b200sv_hawkesjd_mc_chain": [_kp, c_int, _dp, _dp, _dp, _ip, _dp, _i8p, c_longlong, c_int, c_uint64, c_int, _dp, _dp],
+    "b200sv_hawkesjd_terminal": [_kp, c_double, c_longlong, c_uint64, c_int, c_int, c_int, _dp, _dp, _dp],
+    "b200sv_hawkesjd_step_fixed": [_dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, c_int, c_longlong, c_double, _kp],
+    "b200sv_hawkesjd_device_draws": [c_uint64, c_longlong, c_longlong, c_int, c_int, c_double, _kp, c_int, _dp, _dp, _dp, _dp, _dp],
     "b200sv_device_normals": [c_uint64, c_longlong, c_longlong, c_int, c_int, c_int, _dp, _dp],
     "b200sv_dev_logsv_slice": [c_void_p, c_void_p, c_void_p, c_longlong, c_longlong, c_int, _lp, c_double, c_int, c_int, c_double,
                                c_int, c_double, c_uint64, c_int, c_void_p, c_void_p, c_void_p],
@@ -102,6 +115,7 @@ _MISC = {
     "b200sv_version": ([], c_int),
     "b200sv_launch_count": ([], c_longlong),
     "b200sv_reset_launch_count": ([], None),
+    "b200sv_get_stream": ([], c_void_p),
 }
 
 _lib = None

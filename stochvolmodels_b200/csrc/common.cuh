@@ -19,6 +19,11 @@ inline int fail(int code, const std::string& msg) {
   return code;
 }
 
+// The stream every HOST-LEVEL entry point of the calling thread works on: b200sv_set_stream (include/b200sv.h).  Defined once in
+// mc_kernels.cu; the other translation units reach it through these accessors (one shared library, one thread-local).
+cudaStream_t& current_stream_ref();
+inline cudaStream_t current_stream() { return current_stream_ref(); }
+
 #define B200SV_CUDA(call)                                                                           \
   do {                                                                                              \
     cudaError_t e__ = (call);                                                                       \

@@ -46,7 +46,7 @@ extern "C" int b200sv_bsm_implied_vols(int M, const double* ttms, const double* 
       if (types[j] < 0 || types[j] > 3) return fail(-3, "unknown option payoff code");
       q[j - offsets[0]] = QuoteSpec{forwards[m], strikes[j], ttms[m], discfactors[m], prices[j - offsets[0]], (int)types[j]};
     }
-  cudaStream_t st = 0;
+  cudaStream_t st = current_stream();
   ensure_pool_threshold();
   QuoteSpec* dq = nullptr;
   double* dv = nullptr;

@@ -32,6 +32,10 @@
 namespace b200sv {
 
 static thread_local long long g_launches = 0;
+cudaStream_t& current_stream_ref() {
+  static thread_local cudaStream_t st = nullptr;
+  return st;
+}
 constexpr int kThreads = 256;
 #ifndef B200SV_SLICE_PREFETCH
 #define B200SV_SLICE_PREFETCH 1     // issue the next Philox/Box-Muller call before the two fp64 steps of the current one
@@ -977,7 +981,7 @@ static int mc_chain_host(const b200sv_logsv_params* lp, const b200sv_heston_para
   if (int rc = validate_chain(M, ttms, offsets, types, variable_type)) return rc;
   const int Jtot = offsets[M] - offsets[0];
   const size_t esz = (flags & B200SV_STATE_F32) ? 4 : 8;
-  cudaStream_t st = 0;
+  cudaStream_t st = current_stream();
   ensure_pool_threshold();
   char *x = nullptr;
   double *d_strikes = nullptr, *d_out = nullptr, *d_mom = nullptr, *d_sums = nullptr;
@@ -1047,7 +1051,7 @@ static int terminal_host(const b200sv_logsv_params* lp, const b200sv_heston_para
                          int nb_steps_per_year, int is_spot, double eta, uint64_t seed, int flags, double* x, double* v, double* q, int scheme = 0) {
   B200SV_REQUIRE(nb_path >= 1 && ttm > 0.0 && nb_steps_per_year >= 1, "nb_path, ttm, nb_steps_per_year must be positive");
   B200SV_REQUIRE(!(flags & B200SV_STATE_F32), "terminal values are returned as float64: use B200SV_STATE_F64");
-  cudaStream_t st = 0;
+  cudaStream_t st = current_stream();
   ensure_pool_threshold();
   double *d = nullptr, *d_mom = nullptr;
   B200SV_CUDA(cudaMallocAsync(&d, sizeof(double) * 3 * (size_t)nb_path, st));
@@ -1079,6 +1083,7 @@ static int terminal_host(const b200sv_logsv_params* lp, const b200sv_heston_para
 }  // namespace b200sv
 
 #include "rough_kernels.cuh"
+#include "hawkes_kernels.cuh"
 
 using namespace b200sv;
 
@@ -1086,6 +1091,12 @@ extern "C" {
 
 const char* b200sv_last_error(void) { return last_error().c_str(); }
 int b200sv_version(void) { return B200SV_VERSION; }
+// stream of the calling thread's host-level calls (like cublasSetStream; NULL = the legacy default stream)
+int b200sv_set_stream(void* stream) {
+  current_stream_ref() = (cudaStream_t)stream;
+  return 0;
+}
+void* b200sv_get_stream(void) { return (void*)current_stream(); }
 long long b200sv_launch_count(void) { return g_launches; }
 void b200sv_reset_launch_count(void) { g_launches = 0; }
 
@@ -1134,6 +1145,42 @@ int b200sv_logsv_terminal(const b200sv_logsv_params* params, double ttm, long lo
                           int is_spot_measure, double eta, uint64_t seed, int flags, double* x, double* sigma, double* qvar) {
   B200SV_REQUIRE(params && x && sigma && qvar, "null pointer");
   return terminal_host<0>(params, nullptr, ttm, nb_path, nb_steps_per_year, is_spot_measure, eta, seed, flags, x, sigma, qvar);
+}
+
+// simulate_logsv_x_vol_terminal with PER-PATH initial arrays and in-kernel draws (pricers/logsv_pricer.py:1007-1020 accepts length-N x0 / sigma0 /
+// qvar0): the three arrays are uploaded, advanced by the fused kernel (init = 0) and copied back in place.  slice_index selects the Philox
+// sub-stream (counter word 3), so that successive calls on the same seed continue with fresh normals like the chain pricer's slices.
+int b200sv_logsv_terminal_from_state(const b200sv_logsv_params* params, double ttm, long long nb_path, int nb_steps_per_year, int is_spot_measure,
+                                     double eta, uint64_t seed, int flags, int slice_index, double* x_inout, double* sigma_inout,
+                                     double* qvar_inout) {
+  B200SV_REQUIRE(params && x_inout && sigma_inout && qvar_inout, "null pointer");
+  B200SV_REQUIRE(nb_path >= 1 && ttm > 0.0 && nb_steps_per_year >= 1 && slice_index >= 0, "nb_path, ttm, nb_steps_per_year must be positive");
+  B200SV_REQUIRE(!(flags & B200SV_STATE_F32), "terminal values are returned as float64: use B200SV_STATE_F64");
+  cudaStream_t st = current_stream();
+  ensure_pool_threshold();
+  double *d = nullptr, *d_mom = nullptr;
+  const size_t nb = sizeof(double) * (size_t)nb_path;
+  B200SV_CUDA(cudaMallocAsync(&d, 3 * nb, st));
+  B200SV_CUDA(cudaMallocAsync(&d_mom, sizeof(double) * 2, st));
+  B200SV_CUDA(cudaMemcpyAsync(d, x_inout, nb, cudaMemcpyHostToDevice, st));
+  B200SV_CUDA(cudaMemcpyAsync(d + nb_path, sigma_inout, nb, cudaMemcpyHostToDevice, st));
+  B200SV_CUDA(cudaMemcpyAsync(d + 2 * nb_path, qvar_inout, nb, cudaMemcpyHostToDevice, st));
+  int S;
+  double dt;
+  time_grid(ttm, nb_steps_per_year, &S, &dt);
+  const LogsvConsts c = make_logsv_consts(*params, eta, is_spot_measure != 0, dt);
+  int rc = launch_slice<0>(d, d + nb_path, d + 2 * nb_path, nb_path, 0, 0, params->sigma0, S, slice_index, 1.0, seed, flags, &c, nullptr, d_mom, st);
+  if (rc == 0) {
+    cudaError_t e = cudaMemcpyAsync(x_inout, d, nb, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(sigma_inout, d + nb_path, nb, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(qvar_inout, d + 2 * nb_path, nb, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) rc = fail(-2, std::string("D2H: ") + cudaGetErrorString(e));
+  }
+  cudaFreeAsync(d, st);
+  cudaFreeAsync(d_mom, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (rc == 0 && e != cudaSuccess) rc = fail(-2, std::string("sync: ") + cudaGetErrorString(e));
+  return rc;
 }
 
 int b200sv_heston_terminal(const b200sv_heston_params* params, double ttm, long long nb_path, int nb_steps_per_year,
@@ -1232,7 +1279,7 @@ static int step_fixed_host(int model, double* x, double* v, double* q, const dou
                            double dt, const b200sv_logsv_params* lp, double eta, int is_spot, const b200sv_heston_params* hp) {
   B200SV_REQUIRE(x && v && q && (S == 0 || (W0 && W1)), "null pointer");
   B200SV_REQUIRE(S >= 0 && N >= 1 && dt > 0.0, "S, N, dt");
-  cudaStream_t st = 0;
+  cudaStream_t st = current_stream();
   double *d = nullptr, *w = nullptr;
   const size_t nb = sizeof(double) * (size_t)N, wb = sizeof(double) * (size_t)N * (size_t)std::max(S, 1);
   B200SV_CUDA(cudaMallocAsync(&d, 3 * nb, st));
@@ -1279,7 +1326,7 @@ int b200sv_mc_payoffs(const double* x, const double* qvar, long long N, double t
     if (types[j] < 0 || types[j] > 3) return fail(-3, "unknown option payoff code");
   if (variable_type != B200SV_LOG_RETURN && variable_type != B200SV_Q_VAR) return fail(-4, "variable_type not implemented");
   B200SV_REQUIRE(variable_type == B200SV_LOG_RETURN || qvar, "qvar required for Q_VAR");
-  cudaStream_t st = 0;
+  cudaStream_t st = current_stream();
   double *d = nullptr, *dk = nullptr, *d_mom = nullptr, *d_sums = nullptr, *d_out = nullptr;
   int8_t* dt_ = nullptr;
   const size_t nb = sizeof(double) * (size_t)N;
@@ -1314,7 +1361,7 @@ int b200sv_mc_payoffs(const double* x, const double* qvar, long long N, double t
 
 int b200sv_device_normals(uint64_t seed, long long path0, long long n, int slice, int nsteps, int flags, double* z0, double* z1) {
   B200SV_REQUIRE(z0 && z1 && n >= 1 && nsteps >= 1, "null pointer / sizes");
-  cudaStream_t st = 0;
+  cudaStream_t st = current_stream();
   double* d = nullptr;
   const size_t nb = sizeof(double) * (size_t)n * nsteps;
   B200SV_CUDA(cudaMallocAsync(&d, 2 * nb, st));
@@ -1341,7 +1388,7 @@ int b200sv_device_normals(uint64_t seed, long long path0, long long n, int slice
 
 int b200sv_debug_exp_pair_scaled(const double* Ls, long long n, double* out /* 2n */) {
   B200SV_REQUIRE(Ls && out && n >= 1, "null pointer / n");
-  cudaStream_t st = 0;
+  cudaStream_t st = current_stream();
   double *dl = nullptr, *dout = nullptr;
   B200SV_CUDA(cudaMallocAsync(&dl, sizeof(double) * n, st));
   B200SV_CUDA(cudaMallocAsync(&dout, sizeof(double) * 2 * n, st));
@@ -1357,7 +1404,7 @@ int b200sv_debug_exp_pair_scaled(const double* Ls, long long n, double* out /* 2
 
 int b200sv_debug_exp_pair(const double* L, long long n, double* out /* 2n */) {
   B200SV_REQUIRE(L && out && n >= 1, "null pointer / n");
-  cudaStream_t st = 0;
+  cudaStream_t st = current_stream();
   double *dl = nullptr, *dout = nullptr;
   B200SV_CUDA(cudaMallocAsync(&dl, sizeof(double) * n, st));
   B200SV_CUDA(cudaMallocAsync(&dout, sizeof(double) * 2 * n, st));
@@ -1381,7 +1428,7 @@ int b200sv_logsv_vol_paths(const b200sv_logsv_params* params, double ttm, long l
   // adj = beta under the inverse measure, no eta (pricers/logsv_pricer.py:929-932)
   LogsvRaw r{params->theta, params->kappa1, params->kappa2, params->beta, params->volvol, 1.0, is_spot_measure ? -1.0 : 1.0,
              is_spot_measure ? 0.0 : params->beta, dt};
-  cudaStream_t st = 0;
+  cudaStream_t st = current_stream();
   ensure_pool_threshold();
   double *d_out = nullptr, *d_w = nullptr;
   const size_t ob = sizeof(double) * (size_t)(S + 1) * (size_t)nb_path, wb = sizeof(double) * (size_t)S * (size_t)nb_path;
@@ -1413,6 +1460,109 @@ int b200sv_rough_logsv_mc_chain(const b200sv_logsv_params* params, int B, int n_
   B200SV_REQUIRE(params && weights && nodes && ttms && forwards && discfactors && offsets && nsteps && hs && prices_out && stderr_out, "null pointer");
   return rough_chain_host(params, B, n_factors, weights, nodes, M, ttms, forwards, discfactors, offsets, strikes, types, nb_path, nsteps, hs, Z0, Z1,
                           z_rows, variable_type, seed, flags, prices_out, stderr_out, ivols_out, states_out);
+}
+
+// ---- Hawkes jump-diffusion MC (hawkes_kernels.cuh) ---------------------------------------------------------------------------
+int b200sv_hawkesjd_mc_chain(const b200sv_hawkes_params* params, int M, const double* ttms, const double* forwards, const double* discfactors,
+                             const int* offsets, const double* strikes, const int8_t* types, long long nb_path, int variable_type, uint64_t seed,
+                             int flags, double* prices_out, double* stderr_out) {
+  B200SV_REQUIRE(params && ttms && forwards && discfactors && offsets && prices_out && stderr_out, "null pointer");
+  return hawkes_chain_host(params, M, ttms, forwards, discfactors, offsets, strikes, types, nb_path, variable_type, seed, flags, prices_out,
+                           stderr_out, nullptr);
+}
+
+int b200sv_hawkesjd_terminal(const b200sv_hawkes_params* params, double ttm, long long nb_path, uint64_t seed, int flags, int slice_index,
+                             int use_initial_arrays, double* x_inout, double* lambda_p_inout, double* lambda_m_inout) {
+  B200SV_REQUIRE(params && x_inout && lambda_p_inout && lambda_m_inout, "null pointer");
+  B200SV_REQUIRE(nb_path >= 1 && ttm > 0.0 && slice_index >= 0, "nb_path, ttm must be positive");
+  cudaStream_t st = current_stream();
+  ensure_pool_threshold();
+  double *d = nullptr, *d_mom = nullptr;
+  const size_t nb = sizeof(double) * (size_t)nb_path;
+  B200SV_CUDA(cudaMallocAsync(&d, 3 * nb, st));
+  B200SV_CUDA(cudaMallocAsync(&d_mom, sizeof(double) * 2, st));
+  if (use_initial_arrays) {
+    B200SV_CUDA(cudaMemcpyAsync(d, x_inout, nb, cudaMemcpyHostToDevice, st));
+    B200SV_CUDA(cudaMemcpyAsync(d + nb_path, lambda_p_inout, nb, cudaMemcpyHostToDevice, st));
+    B200SV_CUDA(cudaMemcpyAsync(d + 2 * nb_path, lambda_m_inout, nb, cudaMemcpyHostToDevice, st));
+  }
+  int S;
+  double dt;
+  time_grid(ttm, kHawkesStepsPerYear, &S, &dt);
+  int rc = launch_hawkes_slice(d, d + nb_path, d + 2 * nb_path, nb_path, 0, use_initial_arrays ? 0 : 1, *params, S, dt, slice_index, 1.0, seed, flags,
+                               d_mom, st);
+  if (rc == 0) {
+    cudaError_t e = cudaMemcpyAsync(x_inout, d, nb, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(lambda_p_inout, d + nb_path, nb, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(lambda_m_inout, d + 2 * nb_path, nb, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) rc = fail(-2, std::string("D2H: ") + cudaGetErrorString(e));
+  }
+  cudaFreeAsync(d, st);
+  cudaFreeAsync(d_mom, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (rc == 0 && e != cudaSuccess) rc = fail(-2, std::string("sync: ") + cudaGetErrorString(e));
+  return rc;
+}
+
+int b200sv_hawkesjd_step_fixed(double* x, double* lambda_p, double* lambda_m, const double* W0, const double* U_P, const double* U_M,
+                               const double* J_P, const double* J_M, int S, long long N, double dt, const b200sv_hawkes_params* params) {
+  B200SV_REQUIRE(x && lambda_p && lambda_m && params && (S == 0 || (W0 && U_P && U_M && J_P && J_M)), "null pointer");
+  B200SV_REQUIRE(S >= 0 && N >= 1 && dt > 0.0, "S, N, dt");
+  cudaStream_t st = current_stream();
+  ensure_pool_threshold();
+  double *d = nullptr, *w = nullptr;
+  const size_t nb = sizeof(double) * (size_t)N, wb = sizeof(double) * (size_t)N * (size_t)std::max(S, 1), wn = (size_t)N * (size_t)std::max(S, 1);
+  B200SV_CUDA(cudaMallocAsync(&d, 3 * nb, st));
+  B200SV_CUDA(cudaMallocAsync(&w, 5 * wb, st));
+  B200SV_CUDA(cudaMemcpyAsync(d, x, nb, cudaMemcpyHostToDevice, st));
+  B200SV_CUDA(cudaMemcpyAsync(d + N, lambda_p, nb, cudaMemcpyHostToDevice, st));
+  B200SV_CUDA(cudaMemcpyAsync(d + 2 * N, lambda_m, nb, cudaMemcpyHostToDevice, st));
+  const double* src[5] = {W0, U_P, U_M, J_P, J_M};
+  if (S > 0)
+    for (int k = 0; k < 5; ++k) B200SV_CUDA(cudaMemcpyAsync(w + k * wn, src[k], wb, cudaMemcpyHostToDevice, st));
+  Grid g = persistent_grid(hawkes_step_fixed_kernel, kThreads, N);
+  hawkes_step_fixed_kernel<<<g.blocks, g.threads, 0, st>>>(d, d + N, d + 2 * N, w, w + wn, w + 2 * wn, w + 3 * wn, w + 4 * wn, S, N,
+                                                            make_hawkes_consts(*params, dt));
+  int rc = check_launch("hawkes_step_fixed_kernel");
+  if (rc == 0) {
+    cudaError_t e = cudaMemcpyAsync(x, d, nb, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(lambda_p, d + N, nb, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(lambda_m, d + 2 * N, nb, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) rc = fail(-2, std::string("D2H: ") + cudaGetErrorString(e));
+  }
+  cudaFreeAsync(d, st);
+  cudaFreeAsync(w, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (rc == 0 && e != cudaSuccess) rc = fail(-2, std::string("sync: ") + cudaGetErrorString(e));
+  return rc;
+}
+
+int b200sv_hawkesjd_device_draws(uint64_t seed, long long path0, long long n, int slice, int S, double dt, const b200sv_hawkes_params* params,
+                                 int flags, double* W0, double* U_P, double* U_M, double* J_P, double* J_M) {
+  B200SV_REQUIRE(params && W0 && U_P && U_M && J_P && J_M && n >= 1 && S >= 1 && dt > 0.0, "null pointer / sizes");
+  const int g = gauss_mode(flags);
+  B200SV_REQUIRE(g == kGaussF32 || g == kGaussF64, "gauss flags");
+  cudaStream_t st = current_stream();
+  ensure_pool_threshold();
+  double* d = nullptr;
+  const size_t wn = (size_t)n * S;
+  B200SV_CUDA(cudaMallocAsync(&d, sizeof(double) * 5 * wn, st));
+  const HawkesConsts c = make_hawkes_consts(*params, dt);
+  const int blocks = (int)((n + 127) / 128);
+  if (g == kGaussF64)
+    hawkes_device_draws_kernel<kGaussF64><<<blocks, 128, 0, st>>>(seed, (unsigned long long)path0, n, (unsigned)slice, S, c, d, d + wn, d + 2 * wn, d + 3 * wn, d + 4 * wn);
+  else
+    hawkes_device_draws_kernel<kGaussF32><<<blocks, 128, 0, st>>>(seed, (unsigned long long)path0, n, (unsigned)slice, S, c, d, d + wn, d + 2 * wn, d + 3 * wn, d + 4 * wn);
+  int rc = check_launch("hawkes_device_draws_kernel");
+  double* dst[5] = {W0, U_P, U_M, J_P, J_M};
+  for (int k = 0; k < 5 && rc == 0; ++k) {
+    cudaError_t e = cudaMemcpyAsync(dst[k], d + k * wn, sizeof(double) * wn, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) rc = fail(-2, std::string("D2H: ") + cudaGetErrorString(e));
+  }
+  cudaFreeAsync(d, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (rc == 0 && e != cudaSuccess) rc = fail(-2, std::string("sync: ") + cudaGetErrorString(e));
+  return rc;
 }
 
 // ---- P2P mailbox (p2p.cuh) -----------------------------------------------------------------------------------------------

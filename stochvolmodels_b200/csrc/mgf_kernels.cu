@@ -936,7 +936,7 @@ int b200sv_logsv_price_chain(const b200sv_logsv_params* params, int M, const dou
       ss[j - offsets[0]] = StrikeSpec{strikes[j], forwards[m], discfactors[m], (int)types[j], m, ttms[m], 0};
       qs[j - offsets[0]] = SumSpec{strikes[j] * ttms[m], discfactors[m], ttms[m], (int)types[j], m};
     }
-  cudaStream_t st = 0;
+  cudaStream_t st = current_stream();
   ensure_pool_threshold();
   DevBuf d_phi(st), d_psi(st), d_spec(st), d_a(st), d_lm(st), d_ss(st), d_pr(st), d_stat(st);
   B200SV_CUDA(d_phi.alloc(sizeof(cd) * P));
@@ -1009,7 +1009,7 @@ int b200sv_heston_price_chain(const b200sv_heston_params* params, int M, const d
       ss[j - offsets[0]] = StrikeSpec{strikes[j], forwards[m], discfactors[m], (int)types[j], m, ttms[m], 0};
       qs[j - offsets[0]] = SumSpec{strikes[j] * ttms[m], discfactors[m], ttms[m], (int)types[j], m};
     }
-  cudaStream_t st = 0;
+  cudaStream_t st = current_stream();
   ensure_pool_threshold();
   DevBuf d_phi(st), d_psi(st), d_dt(st), d_lm(st), d_ss(st), d_pr(st);
   B200SV_CUDA(d_phi.alloc(sizeof(cd) * P));
@@ -1093,7 +1093,7 @@ int b200sv_logsv_price_chain_batch(const b200sv_logsv_params* params, int B, int
     yb[b] = params[b].sigma0 - params[b].theta;
     for (int m = 0; m < M; ++m) spec[(size_t)b * M + m] = ChainSpec{dtaus[m], make_model(params[b], etas ? etas[(size_t)b * M + m] : 1.0, spot)};
   }
-  cudaStream_t st = 0;
+  cudaStream_t st = current_stream();
   ensure_pool_threshold();
   DevBuf d_phi(st), d_spec(st), d_y(st), d_a(st), d_lm(st), d_ss(st), d_pr(st), d_iv(st);
   const size_t nq = (size_t)B * Jtot;
@@ -1143,7 +1143,7 @@ int b200sv_heston_price_chain_batch(const b200sv_heston_params* params, int B, i
     build_phi(per_set_grid ? std::min(0.3, std::sqrt(params[g].v0 * ttms[0])) : vol_scaler, true, P, one);
     phi.insert(phi.end(), one.begin(), one.end());
   }
-  cudaStream_t st = 0;
+  cudaStream_t st = current_stream();
   ensure_pool_threshold();
   DevBuf d_phi(st), d_hp(st), d_dt(st), d_lm(st), d_ss(st), d_pr(st), d_iv(st);
   const size_t nq = (size_t)B * Jtot;
@@ -1180,7 +1180,7 @@ int b200sv_logsv_mgf_grid(const double* phi, const double* psi, int P, double dt
     return fail(-4, "expansion_order not implemented");
   const int N = expansion_order == B200SV_ORDER_FIRST ? 3 : 5;
   ChainSpec spec{dtau, make_model(*params, eta, is_spot_measure != 0)};
-  cudaStream_t st = 0;
+  cudaStream_t st = current_stream();
   ensure_pool_threshold();
   DevBuf d_phi(st), d_psi(st), d_spec(st), d_a0(st), d_a1(st), d_lm(st);
   B200SV_CUDA(d_phi.alloc(sizeof(cd) * P));
@@ -1218,7 +1218,7 @@ int b200sv_logsv_ode_terms(const double* phi, const double* psi, int P, const b2
   if (expansion_order != B200SV_ORDER_FIRST && expansion_order != B200SV_ORDER_SECOND) return fail(-4, "expansion_order not implemented");
   const int N = expansion_order == B200SV_ORDER_FIRST ? 3 : 5;
   const LogsvModel model = make_model(*params, eta, is_spot_measure != 0);
-  cudaStream_t st = 0;
+  cudaStream_t st = current_stream();
   ensure_pool_threshold();
   DevBuf d_phi(st), d_psi(st), d_M(st), d_L(st), d_H(st);
   const size_t nM = (size_t)P * N * N * N, nL = (size_t)P * N * N, nH = (size_t)P * N;
@@ -1249,7 +1249,7 @@ int b200sv_logsv_ode_rhs(const double* phi, const double* psi, int P, const doub
   if (expansion_order != B200SV_ORDER_FIRST && expansion_order != B200SV_ORDER_SECOND) return fail(-4, "expansion_order not implemented");
   const int N = expansion_order == B200SV_ORDER_FIRST ? 3 : 5;
   const LogsvModel model = make_model(*params, eta, is_spot_measure != 0);
-  cudaStream_t st = 0;
+  cudaStream_t st = current_stream();
   ensure_pool_threshold();
   DevBuf d_phi(st), d_psi(st), d_A(st), d_R(st);
   B200SV_CUDA(d_phi.alloc(sizeof(cd) * P));
@@ -1273,7 +1273,7 @@ int b200sv_logsv_ode_rhs(const double* phi, const double* psi, int P, const doub
 int b200sv_ode_rhs_dense(const double* A, int P, int n, const double* M, const double* L, const double* H, double* rhs_out) {
   B200SV_REQUIRE(A && M && L && H && rhs_out, "null pointer");
   B200SV_REQUIRE(P >= 1 && n >= 1 && n <= 16, "P >= 1, 1 <= n <= 16");
-  cudaStream_t st = 0;
+  cudaStream_t st = current_stream();
   ensure_pool_threshold();
   DevBuf d_A(st), d_M(st), d_L(st), d_H(st), d_R(st);
   B200SV_CUDA(d_A.alloc(sizeof(cd) * (size_t)P * n));
@@ -1296,7 +1296,7 @@ int b200sv_heston_mgf_grid(const double* phi, const double* psi, int P, double d
                            const b200sv_heston_params* params, double* log_mgf_out) {
   B200SV_REQUIRE(phi && a_inout && b_inout && params && log_mgf_out, "null pointer");
   B200SV_REQUIRE(P >= 1 && dtau > 0.0, "P >= 1, dtau > 0");
-  cudaStream_t st = 0;
+  cudaStream_t st = current_stream();
   ensure_pool_threshold();
   DevBuf d_phi(st), d_psi(st), d_dt(st), d_a(st), d_b(st), d_a1(st), d_b1(st), d_lm(st);
   B200SV_CUDA(d_phi.alloc(sizeof(cd) * P));
@@ -1331,7 +1331,7 @@ int b200sv_fourier_vanilla(const double* log_mgf, const double* phi, int P, doub
   if (int rc = check_fourier_types(types, J, spot)) return rc;
   std::vector<StrikeSpec> ss(J);
   for (int j = 0; j < J; ++j) ss[j] = StrikeSpec{strikes[j], forward, discfactor, (int)types[j], 0, 1.0, 0};
-  cudaStream_t st = 0;
+  cudaStream_t st = current_stream();
   ensure_pool_threshold();
   DevBuf d_phi(st), d_lm(st), d_ss(st), d_pr(st);
   B200SV_CUDA(d_phi.alloc(sizeof(cd) * P));
@@ -1353,7 +1353,7 @@ int b200sv_fourier_vanilla(const double* log_mgf, const double* phi, int P, doub
 static int fourier_sum_host(const double* log_mgf, const double* grid, int P, const std::vector<SumSpec>& specs, int mode, int all_calls,
                             double* out) {
   const int J = (int)specs.size();
-  cudaStream_t st = 0;
+  cudaStream_t st = current_stream();
   ensure_pool_threshold();
   DevBuf d_g(st), d_lm(st), d_ss(st), d_pr(st);
   B200SV_CUDA(d_g.alloc(sizeof(cd) * P));

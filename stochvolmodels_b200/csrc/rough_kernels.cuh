@@ -225,7 +225,7 @@ static int rough_chain_host(const b200sv_logsv_params* params, int B, int n, con
   }
   B200SV_REQUIRE(!Z0 || z_rows >= Smax, "Z0 / Z1 have fewer rows than the longest grid");
   const int Jtot = offsets[M] - offsets[0], Jalloc = std::max(Jtot, 1);
-  cudaStream_t st = 0;
+  cudaStream_t st = current_stream();
   ensure_pool_threshold();
   const size_t P = (size_t)nb_path;
   double *d_state = nullptr, *d_z = nullptr, *d_strikes = nullptr, *d_out = nullptr, *d_mom = nullptr, *d_sums = nullptr;

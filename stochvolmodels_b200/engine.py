@@ -170,6 +170,23 @@ def logsv_terminal(params: C.LogsvParamsC, ttm: float, nb_path: int, nb_steps_pe
     return x, s, q
 
 
+def logsv_terminal_from_state(params: C.LogsvParamsC, x0, sigma0, qvar0, ttm: float, nb_steps_per_year: int, is_spot_measure: bool, eta: float,
+                              seed: int, flags: int, slice_index: int = 0):
+    """fused Philox stepper from PER-PATH initial arrays (b200sv_logsv_terminal_from_state); returns fresh (x, sigma, qvar) arrays."""
+    x, s, q = (np.array(a, dtype=np.float64, copy=True, order="C") for a in (x0, sigma0, qvar0))
+    if not (x.shape == s.shape == q.shape and x.ndim == 1):
+        raise ValueError("x0, sigma0, qvar0 must be 1-d arrays of one length")
+    C.call("b200sv_logsv_terminal_from_state", byref(params), float(ttm), int(x.shape[0]), int(nb_steps_per_year), int(bool(is_spot_measure)),
+           float(eta), int(seed) & 0xFFFFFFFFFFFFFFFF, int(flags), int(slice_index), C.dptr(x), C.dptr(s), C.dptr(q))
+    return x, s, q
+
+
+def set_stream(stream) -> None:
+    """CUDA stream (int / ctypes pointer / torch.cuda.Stream) for this thread's host-level library calls; None = the default stream."""
+    ptr = getattr(stream, "cuda_stream", stream)
+    C.call("b200sv_set_stream", ptr)
+
+
 def heston_terminal(params: C.HestonParamsC, ttm: float, nb_path: int, nb_steps_per_year: int, seed: int, flags: int,
                     scheme: int = C.HESTON_EULER_FLOOR):
     x, v, q = np.empty(nb_path), np.empty(nb_path), np.empty(nb_path)

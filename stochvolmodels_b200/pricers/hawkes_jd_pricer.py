@@ -1,0 +1,161 @@
+"""HawkesJDPricer on B200: the Monte Carlo route of the reference's ``pricers/hawkes_jd_pricer.py``.
+
+* ``HawkesJDParams``                          (hawkes_jd_pricer.py:41-119)
+* ``HawkesJDPricer.model_mc_price_chain``     (:156-171) -> ``hawkesjd_mc_chain_pricer`` (:644-715)
+* ``HawkesJDPricer.simulate_terminal_values`` (:193-224) -> ``simulate_hawkesjd_terminal`` (:718-779)
+
+The reference draws every random input from numpy's process-global generator; here they are drawn in-kernel from the Philox stream keyed
+by an explicit ``seed`` (default: OS entropy).  ``simulate_hawkesjd_terminal`` additionally accepts the five input blocks
+(``W0, U_P, U_M, J_P, J_M`` in the reference's own form) and then reproduces the reference arithmetic operation by operation.
+
+The Fourier route of this model (a 3-equation Riccati system per transform point, :480-640) and its calibration are outside the scope
+contract (SURVEY.md §8 names the Hawkes *Monte Carlo*): ``price_chain`` raises ``NotImplementedError``.
+"""
+from __future__ import annotations
+
+from ctypes import byref
+from dataclasses import asdict, dataclass
+from typing import Any, Dict, List, Optional, Tuple
+
+import numpy as np
+
+from .. import _capi as C
+from .. import engine
+from ..data.option_chain import OptionChain
+from ..utils.config import VariableType
+from ..utils.funcs import set_time_grid, timer
+from .model_pricer import ModelParams, ModelPricer
+
+_KEYS = tuple(k for k, _ in C.HawkesParamsC._fields_)
+STEPS_PER_YEAR = 5 * 360          # hawkes_jd_pricer.py:752 "need small dt step for large intensities"
+
+
+@dataclass
+class HawkesJDParams(ModelParams):
+    """parameters of the 2-factor Hawkes jump-diffusion, annualised (reference :41-65, same defaults)"""
+    mu: float = 0.0
+    sigma: float = 0.45
+    shift_p: float = 0.06
+    mean_p: float = 0.03
+    shift_m: float = -0.06
+    mean_m: float = -0.03
+    lambda_p: float = 6.55
+    theta_p: float = 6.55
+    kappa_p: float = 22.29
+    beta1_p: float = 76.0
+    beta2_p: float = -67.58
+    lambda_m: float = 8.50
+    theta_m: float = 8.50
+    kappa_m: float = 29.0
+    beta1_m: float = 104.55
+    beta2_m: float = -109.6
+    risk_premia_gamma: Optional[float] = None
+
+    def __post_init__(self):
+        self.compensator_p = np.exp(self.shift_p) / (1.0 - self.mean_p) - 1.0
+        self.compensator_m = np.exp(self.shift_m) / (1.0 - self.mean_m) - 1.0
+
+    def to_dict(self) -> Dict[str, Any]:
+        return asdict(self)
+
+    @property
+    def exp_jump_p(self) -> float:
+        return self.shift_p + self.mean_p
+
+    @property
+    def exp_jump_m(self) -> float:
+        return self.shift_m + self.mean_m
+
+    @property
+    def jump1_cond(self) -> float:
+        """stationarity margin of the positive-jump intensity (:87-96)"""
+        return self.kappa_p - self.beta1_p * self.exp_jump_p - self.beta2_p * self.exp_jump_m
+
+    @property
+    def jump2_cond(self) -> float:
+        return self.kappa_m - self.beta2_m * self.exp_jump_m - self.beta1_m * self.exp_jump_p
+
+
+def _params_c(**kw) -> C.HawkesParamsC:
+    return C.HawkesParamsC(*[float(kw[k]) for k in _KEYS])
+
+
+class HawkesJDPricer(ModelPricer):
+    """ModelPricer for the Hawkes jump-diffusion model: Monte Carlo route on the GPU."""
+
+    def price_chain(self, option_chain: OptionChain, params: HawkesJDParams, is_spot_measure: bool = True, **kwargs) -> List[np.ndarray]:
+        raise NotImplementedError("the Fourier route of the Hawkes jump-diffusion model is outside the B200 hot-path scope (SURVEY.md §8); "
+                                  "use model_mc_price_chain")
+
+    @timer
+    def model_mc_price_chain(self, option_chain: OptionChain, params: HawkesJDParams, nb_path: int = 100000, **kwargs
+                             ) -> Tuple[List[np.ndarray], List[np.ndarray]]:
+        d = params.to_dict()
+        d.pop("risk_premia_gamma", None)
+        return hawkesjd_mc_chain_pricer(ttms=option_chain.ttms, forwards=option_chain.forwards, discfactors=option_chain.discfactors,
+                                        strikes_ttms=option_chain.strikes_ttms, optiontypes_ttms=option_chain.optiontypes_ttms, nb_path=nb_path,
+                                        seed=kwargs.get("seed"), gauss=kwargs.get("gauss", "fp32"),
+                                        variable_type=kwargs.get("variable_type", VariableType.LOG_RETURN), **d)
+
+    @timer
+    def simulate_terminal_values(self, params: HawkesJDParams, ttm: float = 1.0, nb_path: int = 100000, is_spot_measure: bool = True, **kwargs
+                                 ) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        d = {k: v for k, v in params.to_dict().items() if k in _KEYS and k not in ("lambda_p", "lambda_m")}
+        return simulate_hawkesjd_terminal(ttm=ttm, x0=np.zeros(1), lambda_p0=params.lambda_p * np.ones(1), lambda_m0=params.lambda_m * np.ones(1),
+                                          nb_path=nb_path, seed=kwargs.get("seed"), gauss=kwargs.get("gauss", "fp32"), **d)
+
+
+def hawkesjd_mc_chain_pricer(ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms, lambda_p: float, lambda_m: float, mu: float, sigma: float,
+                             shift_p: float, mean_p: float, shift_m: float, mean_m: float, theta_p: float, kappa_p: float, beta1_p: float,
+                             beta2_p: float, theta_m: float, kappa_m: float, beta1_m: float, beta2_m: float, risk_premia_gamma: float = 0.0,
+                             nb_path: int = 100000, variable_type: VariableType = VariableType.LOG_RETURN, seed: Optional[int] = None,
+                             gauss: str = "fp32") -> Tuple[List[np.ndarray], List[np.ndarray]]:
+    """chain prices and standard errors by simulating the jump-diffusion (reference :644-715): the terminal (x, lambda_p, lambda_m) of slice m
+    seeds slice m+1; payoffs are forward-recentred on x (utils/mc_payoffs.py)."""
+    vt = engine.variable_code(variable_type)
+    M, ttms, forwards, discfactors, offsets, strikes, types = engine._chain_arrays(ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms)
+    pc = _params_c(**locals())
+    prices, stds = np.empty(strikes.shape[0]), np.empty(strikes.shape[0])
+    C.call("b200sv_hawkesjd_mc_chain", byref(pc), M, C.dptr(ttms), C.dptr(forwards), C.dptr(discfactors), C.iptr(offsets), C.dptr(strikes),
+           C.i8ptr(types), int(nb_path), vt, (engine.fresh_seed() if seed is None else int(seed)) & 0xFFFFFFFFFFFFFFFF, engine.mc_flags("fp64", gauss),
+           C.dptr(prices), C.dptr(stds))
+    return C.split_chain(prices, offsets), C.split_chain(stds, offsets)
+
+
+def simulate_hawkesjd_terminal(ttm: float, x0: np.ndarray, lambda_p0: np.ndarray, lambda_m0: np.ndarray, mu: float, sigma: float, shift_p: float,
+                               mean_p: float, shift_m: float, mean_m: float, theta_p: float, kappa_p: float, beta1_p: float, beta2_p: float,
+                               theta_m: float, kappa_m: float, beta1_m: float, beta2_m: float, nb_path: int = 100000, seed: Optional[int] = None,
+                               gauss: str = "fp32", slice_index: int = 0, inputs=None) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """terminal (log-return, lambda_p, lambda_m) with both Hawkes intensities evolving jointly (reference :718-779).  Length-1 initial
+    arrays broadcast as in the reference (:742-750: x0 -> zeros, intensities -> constants).  ``inputs = (W0, U_P, U_M, J_P, J_M)`` (extra;
+    [nb_steps, nb_path] each, in the form :753-757 builds them) runs the strict kernel on caller-supplied draws."""
+    x0, lambda_p0, lambda_m0 = np.atleast_1d(x0), np.atleast_1d(lambda_p0), np.atleast_1d(lambda_m0)
+    for a in (x0, lambda_p0, lambda_m0):
+        assert a.shape[0] in (1, nb_path)
+    x = np.zeros(nb_path) if x0.shape[0] == 1 else np.array(x0, dtype=np.float64)
+    lp = lambda_p0 * np.ones(nb_path) if lambda_p0.shape[0] == 1 else np.array(lambda_p0, dtype=np.float64)
+    lm = lambda_m0 * np.ones(nb_path) if lambda_m0.shape[0] == 1 else np.array(lambda_m0, dtype=np.float64)
+    x, lp, lm = (np.ascontiguousarray(a, dtype=np.float64) for a in (x, lp, lm))
+    pc = _params_c(lambda_p=float(lp[0]), lambda_m=float(lm[0]), **{k: v for k, v in locals().items() if k in _KEYS})
+    nb_steps, dt, _ = set_time_grid(ttm=ttm, nb_steps_per_year=STEPS_PER_YEAR)
+    if inputs is not None:
+        blocks = [C.f64(b) for b in inputs]
+        if len(blocks) != 5 or any(b.shape != (nb_steps, nb_path) for b in blocks):
+            raise ValueError(f"inputs must be five arrays of shape ({nb_steps}, {nb_path})")
+        C.call("b200sv_hawkesjd_step_fixed", C.dptr(x), C.dptr(lp), C.dptr(lm), *[C.dptr(b) for b in blocks], nb_steps, nb_path, dt, byref(pc))
+        return x, lp, lm
+    const_start = x0.shape[0] == 1 and lambda_p0.shape[0] == 1 and lambda_m0.shape[0] == 1
+    C.call("b200sv_hawkesjd_terminal", byref(pc), float(ttm), int(nb_path), (engine.fresh_seed() if seed is None else int(seed)) & 0xFFFFFFFFFFFFFFFF,
+           engine.mc_flags("fp64", gauss), int(slice_index), 0 if const_start else 1, C.dptr(x), C.dptr(lp), C.dptr(lm))
+    return x, lp, lm
+
+
+def hawkesjd_device_draws(seed: int, path0: int, n: int, slice_index: int, ttm: float, gauss: str = "fp32", **params):
+    """(W0, U_P, U_M, J_P, J_M, dt): what the in-kernel generator draws for paths [path0, path0 + n) of a slice of length ``ttm``, in the
+    reference's form (test / diagnostics hook)."""
+    pc = _params_c(**{**{k: 0.0 for k in _KEYS}, **params})
+    S, dt, _ = set_time_grid(ttm=ttm, nb_steps_per_year=STEPS_PER_YEAR)
+    out = [np.empty((S, n)) for _ in range(5)]
+    C.call("b200sv_hawkesjd_device_draws", int(seed) & 0xFFFFFFFFFFFFFFFF, int(path0), int(n), int(slice_index), S, dt, byref(pc),
+           engine.mc_flags("fp64", gauss), *[C.dptr(o) for o in out])
+    return (*out, dt)

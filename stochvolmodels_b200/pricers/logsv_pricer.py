@@ -296,12 +296,13 @@ def simulate_logsv_x_vol_terminal(ttm: float, x0: np.ndarray, sigma0: np.ndarray
                                   kappa2: float, beta: float, volvol: float, vol_backbone_eta: float = 1.0,
                                   is_spot_measure: bool = True, nb_path: int = 100000, nb_steps_per_year: int = 360,
                                   W0: Optional[np.ndarray] = None, W1: Optional[np.ndarray] = None, dt: Optional[float] = None,
-                                  seed: Optional[int] = None, gauss: str = "fp32") -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+                                  seed: Optional[int] = None, gauss: str = "fp32", slice_index: int = 0) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
     """terminal (x, sigma, qvar) after ``ttm`` (reference :950-1047).
 
     With ``W0, W1, dt`` (unit normals [nb_steps, nb_path]) the strict fixed-random kernel reproduces the reference arithmetic
-    (fp64, reference evaluation order, no FMA contraction).  Without them the fused Philox kernel is used and the initial state
-    must be the length-1 broadcast form the reference's own callers use (constant sigma0, zero x0 / qvar0)."""
+    (fp64, reference evaluation order, no FMA contraction).  Without them the fused Philox kernel draws the normals; the initial state is
+    either the length-1 broadcast form or per-path arrays of length ``nb_path``, as in the reference (:1007-1020).  ``slice_index`` (extra)
+    selects the Philox sub-stream so that a chain of calls on one seed does not reuse normals."""
     if W0 is not None or W1 is not None:
         if W0 is None or W1 is None or dt is None:
             raise ValueError("W0, W1 and dt must be supplied together")
@@ -310,14 +311,20 @@ def simulate_logsv_x_vol_terminal(ttm: float, x0: np.ndarray, sigma0: np.ndarray
     x0, sigma0, qvar0 = np.atleast_1d(x0), np.atleast_1d(sigma0), np.atleast_1d(qvar0)
     for a in (x0, sigma0, qvar0):
         assert a.shape[0] in (1, nb_path)            # :1007-1020
-    x_ok = x0.shape[0] == 1 or not np.any(x0)            # a length-1 x0 / qvar0 is replaced by zeros in the reference (:1007-1015)
-    q_ok = qvar0.shape[0] == 1 or not np.any(qvar0)
-    if not (x_ok and q_ok and np.all(sigma0 == sigma0[0])):
-        raise NotImplementedError("the fused kernel starts every path from (0, sigma0, 0); pass W0/W1/dt for per-path initial states")
-    params_c = engine.logsv_params_c(float(sigma0[0]), theta, kappa1, kappa2, beta, volvol)
     seed = engine.fresh_seed() if seed is None else int(seed)
-    return engine.logsv_terminal(params_c, ttm, nb_path, nb_steps_per_year, is_spot_measure, vol_backbone_eta, seed,
-                                 engine.mc_flags("fp64", gauss))
+    flags = engine.mc_flags("fp64", gauss)
+    x_bcast = x0.shape[0] == 1 or not np.any(x0)         # a length-1 x0 / qvar0 is replaced by zeros in the reference (:1007-1015)
+    q_bcast = qvar0.shape[0] == 1 or not np.any(qvar0)
+    if x_bcast and q_bcast and np.all(sigma0 == sigma0[0]):
+        # the form the reference's own callers use: every path starts from (0, sigma0, 0) -- no state upload
+        params_c = engine.logsv_params_c(float(sigma0[0]), theta, kappa1, kappa2, beta, volvol)
+        return engine.logsv_terminal(params_c, ttm, nb_path, nb_steps_per_year, is_spot_measure, vol_backbone_eta, seed, flags)
+    # per-path initial state (:1007-1020): length-1 inputs broadcast as the reference does (x0 -> zeros, qvar0 -> zeros, sigma0 -> constant)
+    xs = np.zeros(nb_path) if x0.shape[0] == 1 else x0
+    qs = np.zeros(nb_path) if qvar0.shape[0] == 1 else qvar0
+    ss = sigma0 * np.ones(nb_path) if sigma0.shape[0] == 1 else sigma0
+    params_c = engine.logsv_params_c(float(ss[0]), theta, kappa1, kappa2, beta, volvol)
+    return engine.logsv_terminal_from_state(params_c, xs, ss, qs, ttm, nb_steps_per_year, is_spot_measure, vol_backbone_eta, seed, flags, slice_index)
 
 
 class DeviceRandoms:

@@ -634,7 +634,62 @@ def rough_mc() -> None:
     print("reference regression fixture: nodes", p.nodes, "weights", p.weights)
 
 
+def hawkes_mc() -> None:
+    """Hawkes jump-diffusion MC (pricers/hawkes_jd_pricer.py:644-779).  The reference draws from numpy's GLOBAL legacy generator, so each case
+    is run after np.random.seed(seed): RandomState(seed) re-draws the same arrays in the same order (W0 normal, U_P, U_M uniform(1e-16, 1),
+    J_P, J_M exponential; one block of shape (S, N) each per simulate call)."""
+    _import_reference()
+    from stochvolmodels.pricers import hawkes_jd_pricer as hj
+    from stochvolmodels.data.sample_option_chains import get_btc_test_chain_data
+    K = np.array([0.8, 0.9, 1.0, 1.1, 1.2])
+    T = np.array(['P', 'P', 'C', 'C', 'C'])
+    out = {}
+    # (a) terminal values, default (BTC-like) parameters and a second set with mu != 0 and per-path initial state
+    for name, params, ttm, N, seed, init in (("dflt", hj.HawkesJDParams(), 0.1, 3000, 21, None),
+                                             ("drift", hj.HawkesJDParams(mu=0.05, sigma=0.3, shift_p=0.04, mean_p=0.05, shift_m=-0.03, mean_m=-0.06, lambda_p=12.0,
+                                                                         theta_p=9.0, kappa_p=15.0, beta1_p=40.0, beta2_p=-30.0, lambda_m=10.0, theta_m=11.0,
+                                                                         kappa_m=20.0, beta1_m=50.0, beta2_m=-60.0), 0.05, 2000, 22, 5)):
+        d = params.to_dict()
+        d.pop("risk_premia_gamma", None)
+        if init is None:
+            x0, lp0, lm0 = np.zeros(N), params.lambda_p * np.ones(N), params.lambda_m * np.ones(N)
+        else:
+            rs = np.random.RandomState(init)
+            x0, lp0, lm0 = rs.normal(0, 0.05, N), params.lambda_p * np.exp(rs.normal(0, 0.2, N)), params.lambda_m * np.exp(rs.normal(0, 0.2, N))
+        np.random.seed(seed)
+        kw = {k: v for k, v in d.items() if k not in ("lambda_p", "lambda_m")}
+        x, lp, lm = hj.simulate_hawkesjd_terminal(ttm=ttm, x0=x0.copy(), lambda_p0=lp0.copy(), lambda_m0=lm0.copy(), nb_path=N, **kw)
+        out.update({f"{name}_params": np.array([d[k] for k in HAWKES_KEYS]), f"{name}_ttm": np.array(ttm), f"{name}_N": np.array(N),
+                    f"{name}_seed": np.array(seed), f"{name}_x0": x0, f"{name}_lp0": lp0, f"{name}_lm0": lm0, f"{name}_x": x, f"{name}_lp": lp,
+                    f"{name}_lm": lm})
+    # (b) chain pricer on two maturities
+    params = hj.HawkesJDParams()
+    ttms, fw, df = np.array([0.05, 0.12]), np.array([1.0, 1.01]), np.array([0.999, 0.995])
+    np.random.seed(33)
+    prices, stds = hj.HawkesJDPricer().model_mc_price_chain.__wrapped__(hj.HawkesJDPricer(), _chain(ttms, fw, df, K, T), params, nb_path=4000) \
+        if hasattr(hj.HawkesJDPricer.model_mc_price_chain, "__wrapped__") else hj.HawkesJDPricer().model_mc_price_chain(_chain(ttms, fw, df, K, T), params, nb_path=4000)
+    out.update(chain_ttms=ttms, chain_forwards=fw, chain_discfactors=df, chain_strikes=K, chain_types=T, chain_seed=np.array(33), chain_N=np.array(4000),
+               chain_params=np.array([params.to_dict()[k] for k in HAWKES_KEYS]),
+               chain_prices=np.array([np.asarray(p) for p in prices]), chain_stds=np.array([np.asarray(p) for p in stds]))
+    np.savez(os.path.join(OUT, "hawkes_mc.npz"), keys=np.array(HAWKES_KEYS), **out)
+    print("hawkes chain prices", out["chain_prices"])
+
+
+HAWKES_KEYS = ("mu", "sigma", "shift_p", "mean_p", "shift_m", "mean_m", "lambda_p", "theta_p", "kappa_p", "beta1_p", "beta2_p", "lambda_m", "theta_m",
+               "kappa_m", "beta1_m", "beta2_m")
+
+
+def _chain(ttms, fw, df, K, T):
+    from stochvolmodels.data.option_chain import OptionChain
+    from numba.typed import List
+    return OptionChain(ttms=ttms, forwards=fw, discfactors=df, strikes_ttms=List([K * f for f in fw]), optiontypes_ttms=List([T for _ in fw]),
+                       ids=np.array([f"{t:0.2f}" for t in ttms]))
+
+
 if __name__ == "__main__":
+    if "--only-hawkes" in sys.argv:
+        hawkes_mc()
+        sys.exit(0)
     if "--only-rough" in sys.argv:
         rough_mc()
         sys.exit(0)

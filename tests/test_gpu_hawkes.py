@@ -1,0 +1,91 @@
+"""Hawkes jump-diffusion Monte Carlo on the GPU against the reference goldens and the numpy oracle.
+
+tests/golden/hawkes_mc.npz = outputs of the UNMODIFIED reference (pricers/hawkes_jd_pricer.py:644-779) after np.random.seed(seed); the
+oracle re-draws the same legacy-generator blocks, the strict GPU kernel consumes them and must reproduce the reference operation by
+operation; the fused kernel (in-kernel Philox draws) is checked against the oracle on the draws it exports."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle import hawkes
+
+pytestmark = pytest.mark.gpu
+
+
+def test_strict_kernel_vs_reference_golden_terminal_states(cuda_lib):
+    from stochvolmodels_b200.pricers.hawkes_jd_pricer import simulate_hawkesjd_terminal
+    g = load_golden("hawkes_mc.npz")
+    for name in ("dflt", "drift"):
+        params = dict(zip(hawkes.KEYS, g[f"{name}_params"]))
+        N, ttm = int(g[f"{name}_N"]), float(g[f"{name}_ttm"])
+        blk = hawkes.draw_inputs(np.random.RandomState(int(g[f"{name}_seed"])), ttm, N, params["shift_p"], params["mean_p"], params["shift_m"], params["mean_m"])
+        kw = {k: v for k, v in params.items() if k not in ("lambda_p", "lambda_m")}
+        x, lp, lm = simulate_hawkesjd_terminal(ttm=ttm, x0=g[f"{name}_x0"], lambda_p0=g[f"{name}_lp0"], lambda_m0=g[f"{name}_lm0"], nb_path=N,
+                                               inputs=blk[:5], **kw)
+        np.testing.assert_allclose(x, g[f"{name}_x"], rtol=0, atol=1e-13)
+        np.testing.assert_allclose(lp, g[f"{name}_lp"], rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(lm, g[f"{name}_lm"], rtol=1e-12, atol=1e-12)
+        xo, lpo, lmo = hawkes.step_fixed(g[f"{name}_x0"], g[f"{name}_lp0"], g[f"{name}_lm0"], *blk, **params)
+        np.testing.assert_array_equal(x, xo)              # IEEE operation by operation: bit-identical to the numpy restatement
+        np.testing.assert_array_equal(lp, lpo)
+        np.testing.assert_array_equal(lm, lmo)
+        assert np.any(lp != g[f"{name}_lp0"]) and np.max(np.abs(x)) > 0.05           # jumps did fire
+
+
+@pytest.mark.parametrize("gauss", ["fp32", "fp64"])
+def test_fused_kernel_vs_oracle_on_its_own_draws(cuda_lib, gauss):
+    """chain prices of the in-kernel-draw kernel == oracle chain on the exported draws (two slices: the second continues from the first's
+    state on Philox sub-stream 1); terminal states path by path"""
+    from stochvolmodels_b200 import HawkesJDParams, HawkesJDPricer, OptionChain
+    from stochvolmodels_b200.pricers.hawkes_jd_pricer import hawkesjd_device_draws, simulate_hawkesjd_terminal
+    p = HawkesJDParams(mu=0.02, sigma=0.4, lambda_p=9.0, lambda_m=11.0)
+    d = {k: v for k, v in p.to_dict().items() if k in hawkes.KEYS}
+    N, seed = 6000, 123
+    ttms, fw, df = np.array([0.04, 0.1]), np.array([1.0, 1.01]), np.array([0.999, 0.99])
+    K = np.array([0.85, 0.95, 1.0, 1.05, 1.15]); T = np.array(["P", "P", "C", "C", "IC"])
+    chain = OptionChain(ttms=ttms, forwards=fw, discfactors=df, strikes_ttms=[K, K * 1.01], optiontypes_ttms=[T, T])
+    pg, eg = HawkesJDPricer().model_mc_price_chain(chain, p, nb_path=N, seed=seed, gauss=gauss)
+    inputs, t0 = [], 0.0
+    for m, ttm in enumerate(ttms):
+        inputs.append(hawkesjd_device_draws(seed, 0, N, m, ttm - t0, gauss=gauss, **d))
+        t0 = ttm
+    po, eo = hawkes.chain_prices(d, ttms, fw, df, chain.strikes_ttms, chain.optiontypes_ttms, N, inputs=inputs)
+    for m in range(2):
+        np.testing.assert_allclose(pg[m], po[m], rtol=1e-12, atol=1e-15)
+        np.testing.assert_allclose(eg[m], eo[m], rtol=1e-10, atol=1e-15)
+    # terminal values API: constant start, then per-path continuation
+    x, lp, lm = HawkesJDPricer().simulate_terminal_values(p, ttm=0.04, nb_path=N, seed=seed, gauss=gauss)
+    xo, lpo, lmo = hawkes.step_fixed(np.zeros(N), p.lambda_p * np.ones(N), p.lambda_m * np.ones(N), *inputs[0], **d)
+    np.testing.assert_array_equal(x, xo)
+    np.testing.assert_array_equal(lp, lpo)
+    kw = {k: v for k, v in d.items() if k not in ("lambda_p", "lambda_m")}
+    x2, lp2, lm2 = simulate_hawkesjd_terminal(ttm=0.06, x0=x, lambda_p0=lp, lambda_m0=lm, nb_path=N, seed=seed, gauss=gauss, slice_index=1, **kw)
+    xo2, lpo2, lmo2 = hawkes.step_fixed(xo, lpo, lmo, *inputs[1], **d)
+    np.testing.assert_array_equal(x2, xo2)
+    np.testing.assert_array_equal(lm2, lmo2)
+    # the draws themselves: uniform clocks, exponential sizes, unit-variance increments
+    W0, U_P, U_M, J_P, J_M, dt = inputs[1]
+    n = W0.size
+    assert abs(W0.mean()) < 4 * np.sqrt(dt / n) and abs(W0.var() / dt - 1) < 4 * np.sqrt(2 / n)
+    assert abs((U_P * dt).mean() - 1) < 4 / np.sqrt(n) and abs((U_M * dt).mean() - 1) < 4 / np.sqrt(n)
+    assert abs((J_P - p.shift_p).mean() / p.mean_p - 1) < 4 / np.sqrt(n) and np.all(J_P >= p.shift_p) and np.all(J_M <= p.shift_m)
+
+
+def test_chain_prices_within_mc_error_of_reference_mc_golden(cuda_lib):
+    """statistical agreement with the reference's own MC sample (4000 paths, golden) using 2e6 GPU paths: |diff| < 4 combined SE"""
+    from stochvolmodels_b200 import HawkesJDParams, HawkesJDPricer, OptionChain
+    g = load_golden("hawkes_mc.npz")
+    params = HawkesJDParams(**dict(zip(hawkes.KEYS, g["chain_params"])))
+    M = g["chain_ttms"].shape[0]
+    chain = OptionChain(ttms=g["chain_ttms"], forwards=g["chain_forwards"], discfactors=g["chain_discfactors"],
+                        strikes_ttms=[g["chain_strikes"] * f for f in g["chain_forwards"]], optiontypes_ttms=[g["chain_types"]] * M)
+    p, e = HawkesJDPricer().model_mc_price_chain(chain, params, nb_path=2_000_000, seed=5)
+    for m in range(M):
+        z = (p[m] - g["chain_prices"][m]) / np.sqrt(e[m] ** 2 + g["chain_stds"][m] ** 2)
+        assert np.all(np.abs(z) < 4.0), z
+    # martingale check: E[exp(x_T)] = exp(mu T) under the compensated dynamics
+    x, _, _ = HawkesJDPricer().simulate_terminal_values(params, ttm=0.1, nb_path=2_000_000, seed=6)
+    m1 = np.exp(x)
+    assert abs(m1.mean() - np.exp(params.mu * 0.1)) < 4 * m1.std() / np.sqrt(x.size)
+    with pytest.raises(NotImplementedError):
+        HawkesJDPricer().price_chain(chain, params)

@@ -426,3 +426,56 @@ def test_full_size_properties_1e8_paths(cuda_lib):
         assert np.all(np.diff(pc[m]) < 0) and np.all(np.diff(pp[m]) > 0)                       # monotone in strike
         np.testing.assert_allclose(es[m] / em[m], 10.0, rtol=0.05)                             # SE ~ 1/sqrt(N)
         assert np.all(np.abs(pm[m] - fourier[f"prices_{m}"]) / F < 1e-3)
+
+
+def test_terminal_values_from_per_path_initial_arrays(cuda_lib):
+    """simulate_logsv_x_vol_terminal with length-N x0 / sigma0 / qvar0 and in-kernel draws (reference :1007-1020): equals the oracle stepper
+    fed with the kernel's own normals; a two-leg continuation (slice 0 then slice 1 from the first leg's state) equals the chain pricer's
+    own slice sequence."""
+    from stochvolmodels_b200 import _capi as C, engine
+    from stochvolmodels_b200.pricers.logsv_pricer import simulate_logsv_x_vol_terminal
+    N, npy, seed = 6000, 252, 77
+    theta, kappa1, kappa2, beta, volvol = 1.0413, 3.1844, 3.058, 0.1514, 1.8458
+    rs = np.random.RandomState(3)
+    x0, s0, q0 = rs.normal(0, 0.1, N), np.exp(rs.normal(-0.2, 0.3, N)), rs.uniform(0, 0.05, N)
+    ttm = 0.2
+    S, dt = mc.set_time_grid(ttm, npy)
+    for gauss, flag in (("fp64", C.GAUSS_F64), ("fp32", C.GAUSS_F32)):
+        x, s, q = simulate_logsv_x_vol_terminal(ttm=ttm, x0=x0, sigma0=s0, qvar0=q0, theta=theta, kappa1=kappa1, kappa2=kappa2, beta=beta, volvol=volvol,
+                                                vol_backbone_eta=0.9, is_spot_measure=False, nb_path=N, nb_steps_per_year=npy, seed=seed, gauss=gauss)
+        Z0, Z1 = engine.device_normals(seed, 0, N, 0, S, flag)
+        xo, so, qo = mc.logsv_step_fixed(x0.copy(), s0.copy(), q0.copy(), Z0, Z1, dt, theta, kappa1, kappa2, beta, volvol, 0.9, False)
+        np.testing.assert_allclose(x, xo, rtol=0, atol=2e-11)
+        np.testing.assert_allclose(s, so, rtol=2e-11, atol=0)
+        np.testing.assert_allclose(q, qo, rtol=2e-11, atol=1e-14)
+    assert x0[0] != x[0] and np.all(x0 == np.asarray(x0))                      # inputs untouched
+    # continuation: leg 2 on sub-stream 1 from the state of leg 1 == oracle on the slice-1 normals
+    x2, s2, q2 = simulate_logsv_x_vol_terminal(ttm=ttm, x0=x, sigma0=s, qvar0=q, theta=theta, kappa1=kappa1, kappa2=kappa2, beta=beta, volvol=volvol,
+                                               vol_backbone_eta=0.9, is_spot_measure=False, nb_path=N, nb_steps_per_year=npy, seed=seed, gauss="fp32",
+                                               slice_index=1)
+    Z0, Z1 = engine.device_normals(seed, 0, N, 1, S, C.GAUSS_F32)
+    xo, so, qo = mc.logsv_step_fixed(x.copy(), s.copy(), q.copy(), Z0, Z1, dt, theta, kappa1, kappa2, beta, volvol, 0.9, False)
+    np.testing.assert_allclose(x2, xo, rtol=0, atol=2e-11)
+    np.testing.assert_allclose(s2, so, rtol=2e-11, atol=0)
+
+
+def test_host_level_calls_follow_set_stream(cuda_lib):
+    """b200sv_set_stream: host-level calls run on the caller's stream (same results; the call synchronises that stream before returning)."""
+    import torch
+    from stochvolmodels_b200 import LogSvParams, LogSVPricer, OptionChain, engine
+    chain = OptionChain(ttms=np.array([0.25]), forwards=np.ones(1), strikes_ttms=[K5], optiontypes_ttms=[T5])
+    p = LogSvParams(1.0, 1.0, 5.0, 5.0, 0.2, 2.0)
+    base = LogSVPricer().model_mc_price_chain(chain, p, nb_path=50_000, nb_steps=252, seed=9)
+    fourier = LogSVPricer().price_chain(chain, p)
+    st = torch.cuda.Stream()
+    engine.set_stream(st)
+    try:
+        assert cuda_lib.b200sv_get_stream() == st.cuda_stream
+        on_stream = LogSVPricer().model_mc_price_chain(chain, p, nb_path=50_000, nb_steps=252, seed=9)
+        fourier2 = LogSVPricer().price_chain(chain, p)
+    finally:
+        engine.set_stream(None)
+    assert not cuda_lib.b200sv_get_stream()
+    np.testing.assert_array_equal(on_stream[0][0], base[0][0])
+    np.testing.assert_array_equal(on_stream[1][0], base[1][0])
+    np.testing.assert_array_equal(fourier2[0], fourier[0])

@@ -177,3 +177,21 @@ def test_model_pricer_mc_pdf_and_default_interfaces():
                  lambda p: p.simulate_vol_paths(None), lambda p: p.simulate_terminal_values(None), lambda p: p.compute_logreturn_pdf(None)):
         with pytest.raises(NotImplementedError):
             call(PriceOnly())
+
+
+def test_non_default_ode_branches_refuse_loudly():
+    """``is_stiff_solver=True`` (SciPy BDF, affine_expansion.py:229-303) and ``is_analytic=True`` (semi-analytic fixed-point branch, :306-384)
+    are NOT rebuilt on the GPU (BDF's variable-order Newton/LU control law cannot be cloned to the reference's own 1e-10 bar
+    at reasonable cost, and the semi-analytic branch returns NaN on both flagship parameter sets in the reference itself).  The drop-in
+    contract for an unsupported branch is a loud NotImplementedError naming the branch -- never a silent switch to RK45."""
+    from stochvolmodels_b200 import LogSvParams, LogSVPricer, OptionChain
+    from stochvolmodels_b200.pricers.logsv.affine_expansion import compute_logsv_a_mgf_grid, solve_a_ode_grid
+    chain = OptionChain(ttms=np.array([0.25]), forwards=np.ones(1), strikes_ttms=[np.array([1.0])], optiontypes_ttms=[np.array(["C"])])
+    p = LogSvParams(1.0, 1.0, 5.0, 5.0, 0.2, 2.0)
+    for kw in ({"is_stiff_solver": True}, {"is_analytic": True}):
+        with pytest.raises(NotImplementedError, match="RK45"):
+            LogSVPricer().price_chain(chain, p, **kw)
+        with pytest.raises(NotImplementedError, match="RK45"):
+            compute_logsv_a_mgf_grid(0.25, np.array([-0.5 + 1j]), np.zeros(1, complex), np.zeros(1, complex), 1.0, 1.0, 5.0, 5.0, 0.2, 2.0, **kw)
+    with pytest.raises(NotImplementedError, match="RK45"):
+        solve_a_ode_grid(np.array([-0.5 + 1j]), np.zeros(1, complex), 0.25, 1.0, 5.0, 5.0, 0.2, 2.0, is_stiff_solver=True)

@@ -296,3 +296,25 @@ def test_rough_mc_oracle_vs_the_references_own_regression_fixture():
                                         kappa1, kappa2, beta, volvol, g["weights"], g["nodes"], grids)
     for m in range(int(g["nslices"])):
         np.testing.assert_allclose(prices[m], g[f"expected_prices_{m}"], rtol=1e-7, atol=0)
+
+
+def test_hawkes_mc_oracle_vs_reference_golden():
+    """oracle/hawkes.py == the reference's Hawkes jump-diffusion MC on the same legacy-generator draws (terminal states, chain prices)"""
+    from oracle import hawkes
+    g = load_golden("hawkes_mc.npz")
+    for name in ("dflt", "drift"):
+        params = dict(zip(hawkes.KEYS, g[f"{name}_params"]))
+        rng = np.random.RandomState(int(g[f"{name}_seed"]))
+        blk = hawkes.draw_inputs(rng, float(g[f"{name}_ttm"]), int(g[f"{name}_N"]), params["shift_p"], params["mean_p"], params["shift_m"], params["mean_m"])
+        x, lp, lm = hawkes.step_fixed(g[f"{name}_x0"], g[f"{name}_lp0"], g[f"{name}_lm0"], *blk, **params)
+        np.testing.assert_allclose(x, g[f"{name}_x"], rtol=0, atol=1e-13)
+        np.testing.assert_allclose(lp, g[f"{name}_lp"], rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(lm, g[f"{name}_lm"], rtol=1e-12, atol=1e-12)
+    params = dict(zip(hawkes.KEYS, g["chain_params"]))
+    M = g["chain_ttms"].shape[0]
+    strikes = [g["chain_strikes"] * f for f in g["chain_forwards"]]
+    prices, stds = hawkes.chain_prices(params, g["chain_ttms"], g["chain_forwards"], g["chain_discfactors"], strikes, [g["chain_types"]] * M,
+                                       int(g["chain_N"]), rng=np.random.RandomState(int(g["chain_seed"])))
+    for m in range(M):
+        np.testing.assert_allclose(prices[m], g["chain_prices"][m], rtol=1e-11, atol=1e-15)
+        np.testing.assert_allclose(stds[m], g["chain_stds"][m], rtol=1e-10, atol=1e-15)
