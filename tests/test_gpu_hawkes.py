@@ -59,7 +59,7 @@ def test_fused_kernel_vs_oracle_on_its_own_draws(cuda_lib, gauss):
     np.testing.assert_array_equal(x, xo)
     np.testing.assert_array_equal(lp, lpo)
     kw = {k: v for k, v in d.items() if k not in ("lambda_p", "lambda_m")}
-    x2, lp2, lm2 = simulate_hawkesjd_terminal(ttm=0.06, x0=x, lambda_p0=lp, lambda_m0=lm, nb_path=N, seed=seed, gauss=gauss, slice_index=1, **kw)
+    x2, lp2, lm2 = simulate_hawkesjd_terminal(ttm=ttms[1] - ttms[0], x0=x, lambda_p0=lp, lambda_m0=lm, nb_path=N, seed=seed, gauss=gauss, slice_index=1, **kw)
     xo2, lpo2, lmo2 = hawkes.step_fixed(xo, lpo, lmo, *inputs[1], **d)
     np.testing.assert_array_equal(x2, xo2)
     np.testing.assert_array_equal(lm2, lmo2)
