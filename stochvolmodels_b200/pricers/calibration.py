@@ -17,6 +17,11 @@ The MC engine (:251-266) has two sources of fixed normals: ``mc_randoms="numpy"`
 fixed-random stepper -- the same objective values as the reference for the same seed; ``mc_randoms="philox"`` prices the n+1 sets in one
 ``b200sv_logsv_mc_chain_batch`` call in which the counter-based generator re-draws identical normals for every set (nothing stored or
 streamed; statistically equivalent objective, different sample).
+
+Quotes whose model price falls outside the no-arbitrage bounds have no implied vol: the GPU inversion returns NaN for them and the
+objective's ``nansum`` (the reference's own reduction, :292-294) leaves them out of that evaluation, exactly as the reference does with the NaNs
+of its third-party inverter.  Which quotes that inverter would flag is not pinned (the package is absent); ``BatchedObjective``
+counts the skipped quotes per evaluation in ``nan_quotes`` so that a caller can see when a fit was driven by a shrinking set of quotes.
 """
 from __future__ import annotations
 
@@ -111,6 +116,7 @@ class BatchedObjective:
     bounds: Sequence[Tuple[float, float]]
     eps: float = SLSQP_EPS
     nb_batches: int = 0
+    nan_quotes: int = 0          # quotes without an implied vol at the LAST evaluation point (dropped there by nansum, as in the reference)
     _x: Optional[np.ndarray] = None
     _f: float = np.nan
     _g: Optional[np.ndarray] = None
@@ -129,8 +135,10 @@ class BatchedObjective:
             return
         h = self.steps(x)
         pts = np.vstack([x[None, :], x[None, :] + np.diag(h)])
-        f = self.values(self.batch_vols(pts))
+        vols = self.batch_vols(pts)
+        f = self.values(vols)
         self.nb_batches += 1
+        self.nan_quotes = int(np.count_nonzero(np.isnan(vols[0])))
         self._x, self._f, self._g = x.copy(), float(f[0]), (f[1:] - f[0]) / h
 
     def fun(self, x: np.ndarray, *args) -> float:
@@ -298,7 +306,8 @@ def calibrate_logsv(pricer, option_chain, params0, params_min, params_max, is_ve
     x, result = run_slsqp(objective, p0, bounds, build_logsv_constraints(codec, constraints_type), disp=disp)
     fit = codec.parse(x)
     if return_info:
-        return fit, {"fun": float(result.fun), "nit": int(result.nit), "nb_batches": objective.nb_batches, "x": x}
+        return fit, {"fun": float(result.fun), "nit": int(result.nit), "nb_batches": objective.nb_batches, "x": x,
+                     "nan_quotes": objective.nan_quotes}
     return fit
 
 
