@@ -41,12 +41,12 @@ constexpr int kThreads = 256;
 #define B200SV_SLICE_PREFETCH 1     // issue the next Philox/Box-Muller call before the two fp64 steps of the current one
 #endif
 #ifndef B200SV_SLICE_THREADS
-#define B200SV_SLICE_THREADS 128
+#define B200SV_SLICE_THREADS 256
 #endif
 constexpr int kSliceThreads = B200SV_SLICE_THREADS;
 #ifndef B200SV_SLICE_MINBLOCKS
-#define B200SV_SLICE_MINBLOCKS 4   // resident CTAs / SM the slice kernel is register-budgeted for (tuned on B200, profiles/)
-#endif
+#define B200SV_SLICE_MINBLOCKS 2   // resident CTAs / SM the slice kernel is register-budgeted for.  Tuned on B200 (profiles/r02_occupancy.txt):
+#endif                             // 16 warps/SM as 2 x 256 threads 352 Gpath-steps/s, 4 x 128 345, 3 x 128 345, 5 x 128 (96 regs) 330, 6 x 128 319
 constexpr int kStrikeChunk = 8;
 
 // --------------------------------------------------------------------------------------------------------------------
@@ -217,7 +217,9 @@ struct LogsvPath<float> {
   __device__ __forceinline__ float q() const { return fmaf(cq, (s2_first - s * s) + 2.0f * A, q0); }
 };
 
-template <typename Real>
+// QE = compile-time scheme switch: the floor-Euler kernel carries none of the quadratic-exponential code (a runtime flag inside the step
+// cost the reference scheme 6 % through registers and instruction-cache footprint)
+template <typename Real, bool QE = false>
 struct HestonPath {
   Real v, V, XM, x0, q0, xacc, qacc;
   Real hx, sdt, dt, kdt, theta, c0, c1;
@@ -242,21 +244,27 @@ struct HestonPath {
   __device__ __forceinline__ void step_qe(Real zx, Real zv) {
     const Real m = fma(v, e, m0);
     const Real s2 = fma(v, s1, s0);
-    const Real psi = s2 / (m * m);
+    const Real mm = m * m;
     Real vn;
-    if (psi <= (Real)1.5) {
-      const Real ip = (Real)2 / psi;
-      const Real b2 = ip - (Real)1 + sqrt(ip) * sqrt(ip - (Real)1);
-      const Real a = m / ((Real)1 + b2);
-      const Real t = sqrt(b2) + zv;
-      vn = a * t * t;
+    if (s2 <= (Real)1.5 * mm) {          // psi = s2 / m^2 <= 1.5, tested without the division
+      // 2/psi = 2 m^2 / s2;  b^2 = 2/psi - 1 + sqrt(2/psi) sqrt(2/psi - 1) with the two roots merged (2/psi >= 4/3: both factors positive);
+      // fp64 divisions and square roots through MUFU seeds + Newton / Householder steps (fastmath64.cuh, gauss64.cuh): <= 2 ulp, a third of
+      // the instructions of the IEEE routines -- the QE step is 3 divisions + 4 roots in its textbook form, 2 + 3 here
+      const Real ip = (Real)2 * fast_div(mm, s2);
+      const Real t = ip - (Real)1;
+      const Real b2 = t + fast_sqrt(ip * t);
+      const Real a = fast_div(m, (Real)1 + b2);
+      const Real r = fast_sqrt(b2) + zv;
+      vn = a * r * r;
     } else {
+      const Real psi = s2 / mm;
       const Real p = (psi - (Real)1) / (psi + (Real)1);
       const Real beta = ((Real)1 - p) / m;
       const Real u = (Real)normcdf((double)zv);
       vn = u <= p ? (Real)0 : (Real)log((double)(((Real)1 - p) / ((Real)1 - u))) / beta;
     }
-    xacc += K0 + K1 * v + K2 * vn + sqrt(K3 * v + K4 * vn) * zx;
+    const Real arg = K3 * v + K4 * vn;
+    xacc += K0 + K1 * v + K2 * vn + (arg > (Real)0 ? fast_sqrt(arg) : (Real)0) * zx;
     qacc += (Real)0.5 * dt * (v + vn);
     v = vn;
   }
@@ -264,7 +272,7 @@ struct HestonPath {
   // V = sum v_k, XM = sum sqrt(v_k) z0_k  =>  x_S = x_0 - 0.5*dt*V + sqrt(dt)*XM,  q_S = q_0 + dt*V.
   template <bool SAFE>
   __device__ __forceinline__ void step(Real z0, Real z1) {
-    if (qe) {
+    if constexpr (QE) {
       step_qe(z0, z1);
       return;
     }
@@ -858,11 +866,14 @@ static int launch_slice_t(void* x, void* v, void* q, long long n, long long path
   a.slice = (unsigned int)slice_index;
   a.seed = seed;
   a.forward = forward;
+  const bool qe = MODEL == 1 && hc->qe;
   Grid g;
   if constexpr (MODEL == 0)
     g = persistent_grid(mc_slice_kernel<LogsvPath<Real>, LogsvConsts, Real, G64>, kSliceThreads, n);
+  else if (qe)
+    g = persistent_grid(mc_slice_kernel<HestonPath<Real, true>, HestonConsts, Real, G64>, kSliceThreads, n);
   else
-    g = persistent_grid(mc_slice_kernel<HestonPath<Real>, HestonConsts, Real, G64>, kSliceThreads, n);
+    g = persistent_grid(mc_slice_kernel<HestonPath<Real, false>, HestonConsts, Real, G64>, kSliceThreads, n);
   size_t dyn_smem = 0;
 #ifdef B200SV_TUNING   // occupancy sweep for profiles/: cap resident CTAs per SM with dynamic shared memory (tuning builds only)
   if (const char* e = getenv("B200SV_DEBUG_BLOCKS_PER_SM")) {
@@ -871,8 +882,6 @@ static int launch_slice_t(void* x, void* v, void* q, long long n, long long path
       dyn_smem = (size_t)(200 * 1024) / bps;
       if constexpr (MODEL == 0)
         cudaFuncSetAttribute(mc_slice_kernel<LogsvPath<Real>, LogsvConsts, Real, G64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
-      else
-        cudaFuncSetAttribute(mc_slice_kernel<HestonPath<Real>, HestonConsts, Real, G64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
       g.blocks = (int)std::min<long long>((long long)148 * bps, (n + kSliceThreads - 1) / kSliceThreads);
     }
   }
@@ -883,8 +892,10 @@ static int launch_slice_t(void* x, void* v, void* q, long long n, long long path
   a.partials = partials;
   if constexpr (MODEL == 0)
     mc_slice_kernel<LogsvPath<Real>, LogsvConsts, Real, G64><<<g.blocks, g.threads, dyn_smem, st>>>(a, *lc);
+  else if (qe)
+    mc_slice_kernel<HestonPath<Real, true>, HestonConsts, Real, G64><<<g.blocks, g.threads, dyn_smem, st>>>(a, *hc);
   else
-    mc_slice_kernel<HestonPath<Real>, HestonConsts, Real, G64><<<g.blocks, g.threads, dyn_smem, st>>>(a, *hc);
+    mc_slice_kernel<HestonPath<Real, false>, HestonConsts, Real, G64><<<g.blocks, g.threads, dyn_smem, st>>>(a, *hc);
   if (int rc = check_launch("mc_slice_kernel")) return rc;
   reduce_partials_kernel<<<1, 64, 0, st>>>(partials, g.blocks, 2, 2, moments_out, make_publish(p2p, st));   // exchange #1 (producer)
   if (int rc = check_launch("reduce_partials_kernel")) return rc;
