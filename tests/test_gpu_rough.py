@@ -57,6 +57,28 @@ def test_rough_chain_vs_the_references_own_regression_fixture(cuda_lib):
         np.testing.assert_allclose(prices[m], g[f"expected_prices_{m}"], rtol=1e-7, atol=0)
 
 
+def test_rough_fixed_random_pricer_is_finite_and_deterministic(cuda_lib):
+    """port of the reference's tests/test_rough_logsv_characterization.py::test_rough_fixed_random_pricer_is_finite_and_deterministic
+    (H = 0.1 -> three factors; the nodes / weights are the reference optimiser's output for this fixture, stored in the regression golden)"""
+    from stochvolmodels_b200 import OptionChain
+    from stochvolmodels_b200.pricers.logsv_pricer import get_randoms_for_rough_vol_chain_valuation, rough_logsv_mc_chain_pricer_fixed_randoms
+    g = load_golden("rough_mc_reference_regression.npz")
+    chain = OptionChain.slice_to_chain(ttm=0.05, forward=1.0, strikes=np.array([0.95, 1.0, 1.05]), optiontypes=np.array(["P", "C", "C"]), id="rough")
+    z0, z1, grids = get_randoms_for_rough_vol_chain_valuation(chain.ttms, nb_path=128, nb_steps_per_year=100, seed=123)
+
+    def price():
+        return rough_logsv_mc_chain_pricer_fixed_randoms(ttms=chain.ttms, forwards=chain.forwards, discfactors=chain.discfactors,
+                                                         strikes_ttms=chain.strikes_ttms, optiontypes_ttms=chain.optiontypes_ttms, Z0=z0, Z1=z1,
+                                                         sigma0=0.2, theta=0.2, kappa1=2.0, kappa2=8.0, beta=-0.2, orthog_vol=0.3,
+                                                         weights=g["weights"], nodes=g["nodes"], timegrids=grids)
+    p1, e1 = price()
+    p2, e2 = price()
+    assert np.asarray(p1[0]).shape == (3,)
+    assert np.all(np.isfinite(p1[0])) and np.all(np.isfinite(e1[0])) and np.all(np.asarray(e1[0]) >= 0.0)
+    np.testing.assert_array_equal(p1[0], p2[0])
+    np.testing.assert_array_equal(e1[0], e2[0])
+
+
 def test_rough_qvar_payoffs_and_bad_vol_reset_vs_oracle(cuda_lib):
     """Q_VAR payoffs, and a configuration that drives the weighted vol through zero so that the reference's reset-to-1e-6 branch
     (split_simulation.py:310-312) is exercised: GPU == numpy oracle on the same normals."""

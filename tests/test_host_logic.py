@@ -195,3 +195,33 @@ def test_non_default_ode_branches_refuse_loudly():
             compute_logsv_a_mgf_grid(0.25, np.array([-0.5 + 1j]), np.zeros(1, complex), np.zeros(1, complex), 1.0, 1.0, 5.0, 5.0, 0.2, 2.0, **kw)
     with pytest.raises(NotImplementedError, match="RK45"):
         solve_a_ode_grid(np.array([-0.5 + 1j]), np.zeros(1, complex), 0.25, 1.0, 5.0, 5.0, 0.2, 2.0, is_stiff_solver=True)
+
+
+def test_rough_random_grid_replays_seed_and_has_aligned_shapes():
+    """port of the reference's tests/test_rough_logsv_characterization.py::test_rough_random_grid_replays_seed_and_has_aligned_shapes:
+    local RandomState (global numpy state untouched), Z0 / Z1 of the LAST maturity's length, grids end at the maturities"""
+    from stochvolmodels_b200.pricers.logsv_pricer import get_randoms_for_rough_vol_chain_valuation
+    kwargs = dict(ttms=np.array([0.05, 0.1]), nb_path=16, nb_steps_per_year=100, seed=123)
+    np.random.seed(91)
+    expected_global_draw = np.random.random()
+    np.random.seed(91)
+    z0a, z1a, ga = get_randoms_for_rough_vol_chain_valuation(**kwargs)
+    actual_global_draw = np.random.random()
+    z0b, z1b, gb = get_randoms_for_rough_vol_chain_valuation(**kwargs)
+    assert z0a.shape == z1a.shape == (11, 16)
+    np.testing.assert_array_equal(z0a, z0b)
+    np.testing.assert_array_equal(z1a, z1b)
+    assert len(ga) == len(gb) == 2
+    for a, b in zip(ga, gb):
+        np.testing.assert_array_equal(a, b)
+        assert a[0] == 0.0
+    np.testing.assert_allclose([g[-1] for g in ga], kwargs["ttms"], rtol=0.0, atol=0.0)
+    np.testing.assert_allclose(actual_global_draw, expected_global_draw, rtol=0.0, atol=0.0)
+    # H = 1/2 kernel: the single node of the reference (logsv_params.py:110-113), deterministic
+    from stochvolmodels_b200 import LogSvParams
+    p, q = LogSvParams(H=0.5), LogSvParams(H=0.5)
+    p.approximate_kernel(T=0.05); q.approximate_kernel(T=0.05)
+    assert p.nodes.shape == p.weights.shape == (1,) and np.all(p.weights > 0) and np.all(p.nodes >= 0)
+    np.testing.assert_array_equal(p.nodes, q.nodes)
+    with pytest.raises(AssertionError):
+        LogSvParams(H=0.7)
