@@ -175,13 +175,16 @@ def i8ptr(a: np.ndarray):
 
 
 def encode_types(optiontypes) -> np.ndarray:
-    """'C','P','IC','IP' -> int8 codes; unknown code -> ValueError like utils/mc_payoffs.py:83-84 / utils/mgf_pricer.py:212."""
-    out = np.empty(len(optiontypes), dtype=np.int8)
-    for i, t in enumerate(optiontypes):
-        code = TYPE_CODES.get(str(t))
-        if code is None:
-            raise ValueError("unknown option payoff code")
-        out[i] = code
+    """'C','P','IC','IP' -> int8 codes; unknown code -> ValueError like utils/mc_payoffs.py:83-84 / utils/mgf_pricer.py:212.
+    Vectorised (four array comparisons): the marshalling of a 49-strike chain is part of the latency of a small MC call."""
+    a = np.asarray(optiontypes)
+    if a.dtype.kind != "U":
+        a = np.array([str(t) for t in np.atleast_1d(a).ravel()], dtype="U8").reshape(np.shape(a))
+    out = np.full(a.shape, -1, dtype=np.int8)
+    for name, code in TYPE_CODES.items():
+        out[a == name] = code
+    if out.size and out.min() < 0:
+        raise ValueError("unknown option payoff code")
     return out
 
 
@@ -191,7 +194,7 @@ def flatten_chain(strikes_ttms, optiontypes_ttms):
     offsets = np.zeros(len(sizes) + 1, dtype=np.int32)
     offsets[1:] = np.cumsum(sizes)
     strikes = f64(np.concatenate([np.asarray(s, dtype=np.float64).ravel() for s in strikes_ttms])) if sizes else np.zeros(0)
-    types = np.concatenate([encode_types(t) for t in optiontypes_ttms]) if sizes else np.zeros(0, dtype=np.int8)
+    types = encode_types(np.concatenate([np.asarray(t).ravel() for t in optiontypes_ttms])) if sizes else np.zeros(0, dtype=np.int8)
     if strikes.shape[0] != types.shape[0]:
         raise ValueError("strikes and option types must have the same length")
     return offsets, strikes, np.ascontiguousarray(types, dtype=np.int8)
