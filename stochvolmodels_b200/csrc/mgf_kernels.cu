@@ -821,6 +821,123 @@ __global__ void ode_rhs_dense_kernel(const cd* __restrict__ A, int P, int n, con
   out[idx] = (acc + lin) + H[k];
 }
 
+// --------------------------------------------------------------------------------------------------------------------
+// semi-analytic branch: solve_analytic_ode_for_a (pricers/logsv/affine_expansion.py:306-384), is_analytic=True
+// --------------------------------------------------------------------------------------------------------------------
+// The reference steps A' = A^T M A + L A + H on a business-day grid (nb_steps = ceil(260 dtau)): the linear part exactly -- through
+// eig(L), v diag(exp(w dt)) v^-1 and v diag((exp(w dt) - 1)/w) v^-1 with the zero eigenvalue's entry set to 0 -- and the quadratic part by
+// 10 unchecked fixed-point sweeps per step, quadratic term times plain dt; row 0 of the right-hand side is (H_0 + quad_0) dt.
+// Here the two matrices are formed WITHOUT an eigendecomposition: v diag(e^{w dt}) v^-1 = expm(L dt) =: E, and because column 0 of L is zero
+// (nothing depends on A_0) the null eigenvector is e_0, so rows 1.. of the second matrix equal rows 1.. of Psi = int_0^dt e^{L s} ds
+// (the projector that the reference removes has only row 0, and row 0 is overwritten anyway).  E and Psi come from a degree-18 Taylor series
+// of the scaled matrix and s doublings  Psi_{2h} = (I + E_h) Psi_h,  E_{2h} = E_h^2  -- 5x5 complex products in thread-local memory, once per
+// (grid point, maturity).  Agreement with the reference's LAPACK route is limited by the conditioning of ITS eigenvector matrix (1e-10 on
+// the goldens).  vol_backbone_eta is ignored on this branch as in the reference (:340-348: not passed to func_a_ode_quadratic_terms).
+template <int N>
+__device__ void cmat_mul(const cd (&A)[N][N], const cd (&B)[N][N], cd (&C)[N][N]) {
+  for (int i = 0; i < N; ++i)
+    for (int j = 0; j < N; ++j) {
+      cd acc = mk(0.0);
+      for (int k = 0; k < N; ++k) acc = acc + A[i][k] * B[k][j];
+      C[i][j] = acc;
+    }
+}
+
+template <int N>
+__global__ void __launch_bounds__(64) logsv_mgf_analytic_kernel(const cd* __restrict__ phi, const cd* __restrict__ psi, int P, LogsvModel m, double dtau,
+                                                                int year_days, const cd* __restrict__ a_in, cd* __restrict__ a_out,
+                                                                cd* __restrict__ log_mgf, double y) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const cd ph = phi[p], ps = psi ? psi[p] : mk(0.0);
+  const int nb_steps = (int)ceil((double)year_days * dtau);
+  const double dt = dtau / (double)nb_steps;
+  // rows of the system (the same tables the RK45 kernels integrate) -> dense L, H
+  LaneRow<N> rows[N];
+  cd L[N][N], H[N];
+  for (int i = 0; i < N; ++i)
+    for (int j = 0; j < N; ++j) L[i][j] = mk(0.0);
+  double nrm = 0.0;
+  for (int k = 0; k < N; ++k) {
+    rows[k] = make_lane_row<N>(k, m, ph, ps);
+    for (int t = 0; t < rows[k].nl; ++t) L[k][rows[k].li[t]] = rows[k].l[t];
+    H[k] = rows[k].h;
+    double rs = 0.0;
+    for (int j = 0; j < N; ++j) rs += cabs_(L[k][j]);
+    nrm = fmax(nrm, rs);
+  }
+  // scaling: ||L h||_inf <= 1/2
+  int sq = 0;
+  double h = dt;
+  while (nrm * h > 0.5 && sq < 40) {
+    h *= 0.5;
+    ++sq;
+  }
+  cd X[N][N], E[N][N], Psi[N][N], T1[N][N], T2[N][N];
+  for (int i = 0; i < N; ++i)
+    for (int j = 0; j < N; ++j) {
+      X[i][j] = h * L[i][j];
+      E[i][j] = mk(i == j ? 1.0 : 0.0);
+      Psi[i][j] = mk(i == j ? h : 0.0);
+      T1[i][j] = E[i][j];                     // running term X^k / k!
+    }
+  for (int k = 1; k <= 18; ++k) {             // E = sum X^k/k!,  Psi = h sum X^k/(k+1)!
+    cmat_mul<N>(T1, X, T2);
+    for (int i = 0; i < N; ++i)
+      for (int j = 0; j < N; ++j) {
+        T1[i][j] = (1.0 / k) * T2[i][j];
+        E[i][j] = E[i][j] + T1[i][j];
+        Psi[i][j] = Psi[i][j] + (h / (k + 1)) * T1[i][j];
+      }
+  }
+  for (int d = 0; d < sq; ++d) {              // doubling
+    for (int i = 0; i < N; ++i)
+      for (int j = 0; j < N; ++j) T1[i][j] = E[i][j] + mk(i == j ? 1.0 : 0.0);
+    cmat_mul<N>(T1, Psi, T2);
+    cmat_mul<N>(E, E, T1);
+    for (int i = 0; i < N; ++i)
+      for (int j = 0; j < N; ++j) {
+        Psi[i][j] = T2[i][j];
+        E[i][j] = T1[i][j];
+      }
+  }
+  cd g[N];                                    // rows 1.. of (m_rhs @ H)
+  for (int k = 0; k < N; ++k) {
+    cd acc = mk(0.0);
+    for (int j = 0; j < N; ++j) acc = acc + Psi[k][j] * H[j];
+    g[k] = acc;
+  }
+  cd a[N], fp[N], q[N];
+  for (int k = 0; k < N; ++k) a[k] = a_in[(size_t)p * N + k];
+  for (int t = 0; t < nb_steps; ++t) {
+    for (int k = 0; k < N; ++k) fp[k] = a[k];
+    cd Ea[N];
+    for (int k = 0; k < N; ++k) {
+      cd acc = mk(0.0);
+      for (int j = 0; j < N; ++j) acc = acc + E[k][j] * a[j];
+      Ea[k] = acc;
+    }
+    for (int it = 0; it < 10; ++it) {         // nfp = 10, no convergence test (:365)
+      for (int k = 0; k < N; ++k) {
+        cd acc = mk(0.0);
+        for (int u = 0; u < rows[k].nq; ++u) acc = acc + rows[k].q[u] * (fp[rows[k].qi[u]] * fp[rows[k].qj[u]]);
+        q[k] = acc;
+      }
+      fp[0] = Ea[0] + dt * (H[0] + q[0]);
+      for (int k = 1; k < N; ++k) fp[k] = Ea[k] + (g[k] + dt * q[k]);
+    }
+    for (int k = 0; k < N; ++k) a[k] = fp[k];
+  }
+  double yk = 1.0;
+  cd lm = mk(0.0);
+  for (int k = 0; k < N; ++k) {
+    a_out[(size_t)p * N + k] = a[k];
+    lm = lm + yk * a[k];
+    yk *= y;
+  }
+  log_mgf[p] = lm;
+}
+
 static int mgf_block_threads(int P) {
   int t = 4;
   while (t < 64 && t * 148 < P) t <<= 1;
@@ -1288,6 +1405,38 @@ int b200sv_ode_rhs_dense(const double* A, int P, int n, const double* M, const d
   ode_rhs_dense_kernel<<<(P * n + 127) / 128, 128, 0, st>>>(d_A.as<cd>(), P, n, d_M.as<cd>(), d_L.as<cd>(), d_H.as<cd>(), d_R.as<cd>());
   if (int rc = launched("ode_rhs_dense_kernel")) return rc;
   B200SV_CUDA(cudaMemcpyAsync(rhs_out, d_R.p, sizeof(cd) * (size_t)P * n, cudaMemcpyDeviceToHost, st));
+  B200SV_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// compute_logsv_a_mgf_grid(is_analytic=True): the semi-analytic branch over a transform grid (affine_expansion.py:388-470 -> :306-384)
+int b200sv_logsv_mgf_grid_analytic(const double* phi, const double* psi, int P, double dtau, double* a_inout, const b200sv_logsv_params* params,
+                                   int is_spot_measure, int expansion_order, int year_days, double* log_mgf_out) {
+  B200SV_REQUIRE(phi && a_inout && params && log_mgf_out, "null pointer");
+  B200SV_REQUIRE(P >= 1 && dtau > 0.0 && year_days >= 1, "P >= 1, dtau > 0, year_days >= 1");
+  if (expansion_order != B200SV_ORDER_FIRST && expansion_order != B200SV_ORDER_SECOND) return fail(-4, "expansion_order not implemented");
+  const int N = expansion_order == B200SV_ORDER_FIRST ? 3 : 5;
+  const LogsvModel model = make_model(*params, 1.0, is_spot_measure != 0);      // eta is ignored on this branch (reference :340-348)
+  cudaStream_t st = current_stream();
+  ensure_pool_threshold();
+  DevBuf d_phi(st), d_psi(st), d_a0(st), d_a1(st), d_lm(st);
+  B200SV_CUDA(d_phi.alloc(sizeof(cd) * P));
+  B200SV_CUDA(d_psi.alloc(sizeof(cd) * P));
+  B200SV_CUDA(d_a0.alloc(sizeof(cd) * (size_t)P * N));
+  B200SV_CUDA(d_a1.alloc(sizeof(cd) * (size_t)P * N));
+  B200SV_CUDA(d_lm.alloc(sizeof(cd) * P));
+  B200SV_CUDA(cudaMemcpyAsync(d_phi.p, phi, sizeof(cd) * P, cudaMemcpyHostToDevice, st));
+  if (psi) B200SV_CUDA(cudaMemcpyAsync(d_psi.p, psi, sizeof(cd) * P, cudaMemcpyHostToDevice, st));
+  B200SV_CUDA(cudaMemcpyAsync(d_a0.p, a_inout, sizeof(cd) * (size_t)P * N, cudaMemcpyHostToDevice, st));
+  const cd* dpsi = psi ? d_psi.as<cd>() : nullptr;
+  const double y = params->sigma0 - params->theta;
+  if (N == 5)
+    logsv_mgf_analytic_kernel<5><<<(P + 63) / 64, 64, 0, st>>>(d_phi.as<cd>(), dpsi, P, model, dtau, year_days, d_a0.as<cd>(), d_a1.as<cd>(), d_lm.as<cd>(), y);
+  else
+    logsv_mgf_analytic_kernel<3><<<(P + 63) / 64, 64, 0, st>>>(d_phi.as<cd>(), dpsi, P, model, dtau, year_days, d_a0.as<cd>(), d_a1.as<cd>(), d_lm.as<cd>(), y);
+  if (int rc = launched("logsv_mgf_analytic_kernel")) return rc;
+  B200SV_CUDA(cudaMemcpyAsync(a_inout, d_a1.p, sizeof(cd) * (size_t)P * N, cudaMemcpyDeviceToHost, st));
+  B200SV_CUDA(cudaMemcpyAsync(log_mgf_out, d_lm.p, sizeof(cd) * P, cudaMemcpyDeviceToHost, st));
   B200SV_CUDA(cudaStreamSynchronize(st));
   return 0;
 }

@@ -51,11 +51,12 @@ def compute_logsv_a_mgf_grid(ttm: float, phi_grid: np.ndarray, psi_grid: np.ndar
                              expansion_order: ExpansionOrder = ExpansionOrder.SECOND, a_t0: Optional[np.ndarray] = None,
                              is_stiff_solver: bool = False, is_analytic: bool = False, is_spot_measure: bool = True,
                              vol_backbone_eta: float = 1.0, **kwargs) -> Tuple[np.ndarray, np.ndarray]:
-    """(a_t1, log_mgf) over the transform grid, one RK45 (SciPy control law) ODE solve per grid point on the GPU
-    (affine_expansion.py:570-685 -> :492-529).  The BDF (``is_stiff_solver``) and semi-analytic (``is_analytic``) branches are
-    not the default path and are not rebuilt (SURVEY.md §8f #4)."""
-    if is_stiff_solver or is_analytic:
-        raise NotImplementedError("only the default RK45 branch is implemented on the GPU")
+    """(a_t1, log_mgf) over the transform grid, one ODE solve per grid point on the GPU (affine_expansion.py:570-685): the default RK45 branch
+    with SciPy's control law (:492-529), or with ``is_analytic=True`` the semi-analytic branch (business-day steps, exact linear part,
+    10 fixed-point sweeps for the quadratic part, :306-470; ``vol_backbone_eta`` is ignored there, as in the reference).  The BDF branch
+    (``is_stiff_solver``) is not rebuilt and refuses loudly."""
+    if is_stiff_solver and not is_analytic:
+        raise NotImplementedError("is_stiff_solver=True (SciPy BDF) is not implemented on the GPU: use the default RK45 branch or is_analytic=True")
     order = _order_code(expansion_order)
     n = get_expansion_n(ExpansionOrder(order))
     if a_t0 is None:
@@ -63,7 +64,21 @@ def compute_logsv_a_mgf_grid(ttm: float, phi_grid: np.ndarray, psi_grid: np.ndar
         if getattr(variable_type, "value", variable_type) == VariableType.SIGMA.value:   # by value: the reference's own enum duck-types
             a_t0[:, 1] = -theta_grid      # affine_expansion.py:562-564
     params = engine.logsv_params_c(sigma0, theta, kappa1, kappa2, beta, volvol)
+    if is_analytic:            # takes precedence over is_stiff_solver, as in the reference (:643-654)
+        return engine.logsv_mgf_grid_analytic(phi_grid, psi_grid, ttm, a_t0, params, is_spot_measure, order)
     return engine.logsv_mgf_grid(phi_grid, psi_grid, ttm, a_t0, params, vol_backbone_eta, is_spot_measure, order)
+
+
+def solve_analytic_ode_grid_phi(phi_grid: np.ndarray, psi_grid: np.ndarray, ttm: float, theta: float, kappa1: float, kappa2: float, beta: float,
+                                volvol: float, is_spot_measure: bool = True, a_t0: Optional[np.ndarray] = None,
+                                expansion_order: ExpansionOrder = ExpansionOrder.FIRST, year_days: int = 260) -> np.ndarray:
+    """A(ttm) over the grid by the semi-analytic scheme (affine_expansion.py:388-470 -> solve_analytic_ode_for_a :306-384)"""
+    order = _order_code(expansion_order)
+    if a_t0 is None:
+        a_t0 = np.zeros((phi_grid.shape[0], get_expansion_n(ExpansionOrder(order))), dtype=np.complex128)
+    a_t1, _ = engine.logsv_mgf_grid_analytic(phi_grid, psi_grid, ttm, a_t0, engine.logsv_params_c(theta, theta, kappa1, kappa2, beta, volvol),
+                                             is_spot_measure, order, year_days)
+    return a_t1
 
 
 def get_init_conditions_a(phi_grid: np.ndarray, psi_grid: np.ndarray, theta_grid: np.ndarray, n_terms: int,
@@ -88,7 +103,7 @@ def solve_a_ode_grid(phi_grid: np.ndarray, psi_grid: np.ndarray, ttm: float, the
     """A(ttm) for every grid point from A(0) = ``a_t0`` (affine_expansion.py:492-529: a Python loop of ``solve_ivp`` calls there, one
     GPU launch here; same default ``expansion_order`` = FIRST as the reference function)."""
     if is_stiff_solver:
-        raise NotImplementedError("only the default RK45 branch is implemented on the GPU")
+        raise NotImplementedError("is_stiff_solver=True (SciPy BDF) is not implemented on the GPU: use the default RK45 branch")
     order = _order_code(expansion_order)
     if a_t0 is None:
         a_t0 = np.zeros((phi_grid.shape[0], get_expansion_n(ExpansionOrder(order))), dtype=np.complex128)

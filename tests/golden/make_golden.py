@@ -634,6 +634,45 @@ def rough_mc() -> None:
     print("reference regression fixture: nodes", p.nodes, "weights", p.weights)
 
 
+def analytic_branch() -> None:
+    """semi-analytic ODE branch (is_analytic=True): solve_analytic_ode_grid_phi (pricers/logsv/affine_expansion.py:388-470) and the chain pricer on
+    parameter sets where the reference's fixed-point iteration converges (it returns NaN prices for the quickstart / BTC sets at SECOND order)."""
+    _import_reference()
+    from stochvolmodels.pricers import logsv_pricer as lp
+    from stochvolmodels.pricers.logsv import affine_expansion as afe
+    from stochvolmodels.pricers.logsv.logsv_params import LogSvParams
+    from stochvolmodels.utils import mgf_pricer as mgfp
+    from stochvolmodels.utils.config import VariableType
+    K = np.array([0.8, 0.9, 1.0, 1.1, 1.2])
+    T = np.array(['P', 'P', 'C', 'C', 'C'])
+    TI = np.array(['IP', 'IP', 'IC', 'IC', 'IC'])
+    cases = {"quick_first": (LogSvParams(1.0, 1.0, 5.0, 5.0, 0.2, 2.0), afe.ExpansionOrder.FIRST, True, T),
+             "mild_second": (LogSvParams(0.2, 0.2, 1.0, 2.5, -0.3, 0.4), afe.ExpansionOrder.SECOND, True, T),
+             "mild2_second_inverse": (LogSvParams(0.3, 0.25, 2.0, 4.0, -0.2, 0.6), afe.ExpansionOrder.SECOND, False, TI),
+             "quick_second_nan": (LogSvParams(1.0, 1.0, 5.0, 5.0, 0.2, 2.0), afe.ExpansionOrder.SECOND, True, T)}
+    ttms = np.array([0.1, 0.25, 0.5])
+    out = {}
+    for name, (p, order, spot, types) in cases.items():
+        vol_scaler = lp.set_vol_scaler(sigma0=p.sigma0, ttm=np.min(ttms))
+        phi, psi, theta_grid = mgfp.get_transform_var_grid(variable_type=VariableType.LOG_RETURN, is_spot_measure=spot, vol_scaler=vol_scaler)
+        a_t0 = np.zeros((phi.shape[0], afe.get_expansion_n(order)), dtype=np.complex128)
+        t0 = 0.0
+        for m, ttm in enumerate(ttms):
+            a_t0, lm = afe.compute_logsv_a_mgf_grid(ttm=ttm - t0, phi_grid=phi, psi_grid=psi, theta_grid=theta_grid, a_t0=a_t0, is_analytic=True,
+                                                    expansion_order=order, is_spot_measure=spot, sigma0=p.sigma0, theta=p.theta, kappa1=p.kappa1,
+                                                    kappa2=p.kappa2, beta=p.beta, volvol=p.volvol)
+            out[f"{name}_a_{m}"], out[f"{name}_lm_{m}"] = a_t0[::8], lm[::8]          # every 8th grid point (the prices pin the whole grid)
+            t0 = ttm
+        prices = lp.logsv_chain_pricer(params=p, ttms=ttms, forwards=np.ones(3), discfactors=np.array([0.999, 0.99, 0.98]), strikes_ttms=(K, K, K),
+                                       optiontypes_ttms=(types, types, types), is_analytic=True, expansion_order=order, is_spot_measure=spot)
+        out[f"{name}_prices"] = np.array([np.asarray(x) for x in prices])
+        out[f"{name}_params"] = np.array([p.sigma0, p.theta, p.kappa1, p.kappa2, p.beta, p.volvol, order.value, float(spot)])
+        out[f"{name}_types"] = types
+        out[f"{name}_phi"] = phi
+        print(name, out[f"{name}_prices"][1])
+    np.savez_compressed(os.path.join(OUT, "logsv_analytic_branch.npz"), ttms=ttms, strikes=K, discfactors=np.array([0.999, 0.99, 0.98]), **out)
+
+
 def hawkes_mc() -> None:
     """Hawkes jump-diffusion MC (pricers/hawkes_jd_pricer.py:644-779).  The reference draws from numpy's GLOBAL legacy generator, so each case
     is run after np.random.seed(seed): RandomState(seed) re-draws the same arrays in the same order (W0 normal, U_P, U_M uniform(1e-16, 1),
@@ -687,6 +726,9 @@ def _chain(ttms, fw, df, K, T):
 
 
 if __name__ == "__main__":
+    if "--only-analytic" in sys.argv:
+        analytic_branch()
+        sys.exit(0)
     if "--only-hawkes" in sys.argv:
         hawkes_mc()
         sys.exit(0)

@@ -234,3 +234,35 @@ def test_ode_terms_and_rhs_vs_reference_golden(cuda_lib):
         fast = engine.logsv_ode_rhs(np.array([phi]), np.array([psi]), A[None, :], engine.logsv_params_c(theta, theta, kappa1, kappa2, beta, volvol),
                                     eta, bool(spot), int(order))
         np.testing.assert_allclose(fast[0], g[f"case{k}_rhs"], rtol=1e-14, atol=1e-14)
+
+
+@pytest.mark.parametrize("name", ["quick_first", "mild_second", "mild2_second_inverse"])
+def test_semi_analytic_branch_vs_reference_golden(cuda_lib, name):
+    """is_analytic=True (solve_analytic_ode_for_a, affine_expansion.py:306-384): a_t1 / log_mgf carried over three maturities and the chain
+    prices against the reference's own outputs.  The reference forms exp(L dt) through LAPACK eig + inv, the kernel through a scaled Taylor
+    series -- they agree to the conditioning of the reference's eigenvector matrix (measured <= 1e-9 on these sets)."""
+    from stochvolmodels_b200 import LogSvParams, LogSVPricer, OptionChain
+    from stochvolmodels_b200.pricers.logsv.affine_expansion import ExpansionOrder
+    g = load_golden("logsv_analytic_branch.npz")
+    sigma0, theta, k1, k2, beta, vv, order, spot = g[f"{name}_params"]
+    p = LogSvParams(sigma0, theta, k1, k2, beta, vv)
+    K, types, ttms = g["strikes"], g[f"{name}_types"], g["ttms"]
+    chain = OptionChain(ttms=ttms, forwards=np.ones(3), strikes_ttms=[K] * 3, optiontypes_ttms=[types] * 3, discfactors=g["discfactors"])
+    prices, grids = LogSVPricer().price_chain(chain, p, is_analytic=True, expansion_order=ExpansionOrder(int(order)), is_spot_measure=bool(spot),
+                                              return_grids=True)
+    for m in range(3):
+        a, lm = grids[m]
+        np.testing.assert_allclose(a[::8], g[f"{name}_a_{m}"], rtol=1e-8, atol=1e-10)
+        np.testing.assert_allclose(lm[::8], g[f"{name}_lm_{m}"], rtol=1e-8, atol=1e-10)
+        np.testing.assert_allclose(prices[m], g[f"{name}_prices"][m], rtol=1e-8, atol=1e-12)
+
+
+def test_semi_analytic_branch_diverges_where_the_reference_does(cuda_lib):
+    """quickstart parameters at SECOND order: the reference's unchecked fixed-point iteration blows up and it returns NaN for every strike;
+    the drop-in does the same (non-finite prices), it does not silently fall back to RK45"""
+    from stochvolmodels_b200 import LogSvParams, LogSVPricer, OptionChain
+    g = load_golden("logsv_analytic_branch.npz")
+    assert np.all(np.isnan(g["quick_second_nan_prices"]))
+    chain = OptionChain(ttms=g["ttms"], forwards=np.ones(3), strikes_ttms=[g["strikes"]] * 3, optiontypes_ttms=[g["quick_second_nan_types"]] * 3)
+    prices = LogSVPricer().price_chain(chain, LogSvParams(1.0, 1.0, 5.0, 5.0, 0.2, 2.0), is_analytic=True)
+    assert not np.any(np.isfinite(np.concatenate(prices)))
