@@ -483,3 +483,40 @@ def heston_qvar_chain_prices(params5, ttms, discfactors, strikes_ttms, types_ttm
         prices.append(qvar_slice_prices(lm, psi, ttm, strikes_ttms[m], types_ttms[m], discfactors[m]))
         t0 = ttm
     return prices
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# semi-analytic branch (is_analytic=True)
+# ---------------------------------------------------------------------------------------------------------------------------------
+def logsv_analytic_a_grid(dtau, phi, psi, a_t0, theta, kappa1, kappa2, beta, volvol, is_spot_measure=True, order=2, year_days=260):
+    """``solve_analytic_ode_grid_phi`` / ``solve_analytic_ode_for_a`` (pricers/logsv/affine_expansion.py:306-470), restated WITHOUT the
+    eigendecomposition, the way the CUDA kernel does it: ``v diag(exp(w dt)) v^-1 = expm(L dt)``; column 0 of L is zero, so the reference's
+    ``v diag((exp(w dt) - 1)/w, with the zero eigenvalue's entry := 0) v^-1`` equals ``int_0^dt exp(L s) ds`` in rows 1.. (its row 0 is
+    overwritten by (H_0 + quad_0) dt).  Business-day steps, 10 fixed-point sweeps per step, eta = 1.  Pinned by
+    tests/golden/logsv_analytic_branch.npz (outputs of the reference's LAPACK route)."""
+    from scipy.linalg import expm
+    n = expansion_n(order)
+    nb_steps = int(np.ceil(year_days * dtau))
+    dt = dtau / nb_steps
+    out = np.empty((phi.shape[0], n), dtype=np.complex128)
+    for p in range(phi.shape[0]):
+        M, L, H = logsv_mlh(theta, kappa1, kappa2, beta, volvol, complex(phi[p]), complex(psi[p]), is_spot_measure, order, 1.0)
+        aug = np.zeros((2 * n, 2 * n), dtype=np.complex128)          # expm([[L, I], [0, 0]] dt) = [[E, Psi], [0, I]]
+        aug[:n, :n] = L * dt
+        aug[:n, n:] = np.eye(n) * dt
+        big = expm(aug)
+        E, Psi = big[:n, :n], big[:n, n:]
+        g = Psi @ H
+        a = np.array(a_t0[p], dtype=np.complex128)
+        with np.errstate(all="ignore"):
+            for _ in range(nb_steps):
+                Ea = E @ a
+                fp = a
+                for _ in range(10):
+                    quad = np.array([fp @ M[k] @ fp for k in range(n)])
+                    rhs = g + quad * dt
+                    rhs[0] = (H[0] + quad[0]) * dt
+                    fp = Ea + rhs
+                a = fp
+        out[p] = a
+    return out

@@ -661,7 +661,8 @@ def analytic_branch() -> None:
             a_t0, lm = afe.compute_logsv_a_mgf_grid(ttm=ttm - t0, phi_grid=phi, psi_grid=psi, theta_grid=theta_grid, a_t0=a_t0, is_analytic=True,
                                                     expansion_order=order, is_spot_measure=spot, sigma0=p.sigma0, theta=p.theta, kappa1=p.kappa1,
                                                     kappa2=p.kappa2, beta=p.beta, volvol=p.volvol)
-            out[f"{name}_a_{m}"], out[f"{name}_lm_{m}"] = a_t0[::8], lm[::8]          # every 8th grid point (the prices pin the whole grid)
+            # every 8th grid point (the prices pin the whole grid); COPIES: the reference updates a_t0 in place across maturities (:487-488)
+            out[f"{name}_a_{m}"], out[f"{name}_lm_{m}"] = a_t0[::8].copy(), lm[::8].copy()
             t0 = ttm
         prices = lp.logsv_chain_pricer(params=p, ttms=ttms, forwards=np.ones(3), discfactors=np.array([0.999, 0.99, 0.98]), strikes_ttms=(K, K, K),
                                        optiontypes_ttms=(types, types, types), is_analytic=True, expansion_order=order, is_spot_measure=spot)

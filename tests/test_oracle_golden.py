@@ -318,3 +318,18 @@ def test_hawkes_mc_oracle_vs_reference_golden():
     for m in range(M):
         np.testing.assert_allclose(prices[m], g["chain_prices"][m], rtol=1e-11, atol=1e-15)
         np.testing.assert_allclose(stds[m], g["chain_stds"][m], rtol=1e-10, atol=1e-15)
+
+
+@pytest.mark.parametrize("name", ["quick_first", "mild_second", "mild2_second_inverse"])
+def test_semi_analytic_branch_oracle_vs_reference_golden(name):
+    """the eig-free restatement of the semi-analytic branch == the reference's LAPACK route (every 8th grid point, three carried maturities)"""
+    g = load_golden("logsv_analytic_branch.npz")
+    sigma0, theta, k1, k2, beta, vv, order, spot = g[f"{name}_params"]
+    phi = g[f"{name}_phi"][::8]
+    n = mgf.expansion_n(int(order))
+    a = np.zeros((phi.shape[0], n), dtype=np.complex128)
+    t0 = 0.0
+    for m, ttm in enumerate(g["ttms"]):
+        a = mgf.logsv_analytic_a_grid(ttm - t0, phi, np.zeros_like(phi), a, theta, k1, k2, beta, vv, bool(spot), int(order))
+        np.testing.assert_allclose(a, g[f"{name}_a_{m}"], rtol=1e-8, atol=1e-10)
+        t0 = ttm
