@@ -171,3 +171,38 @@ def test_rough_mc_calibration_engine(cuda_lib):
     fit_vols = flat.compute_model_ivols_from_chain_data(model_prices=pricer.model_mc_price_chain(flat, fit, nb_path=N, nb_steps=npy, use_rough_mc=True, seed=seed)[0])
     assert max(np.max(np.abs(a - b)) for a, b in zip(fit_vols, vols)) < 3e-3
     assert fit.H == 0.45 and fit.weights is w
+
+
+def test_rough_and_hawkes_edge_cases(cuda_lib):
+    """ragged chain with an EMPTY slice, a single path, a single-step grid, 8 factors (the kernel's maximum) and a refused 9th; Hawkes with an
+    empty slice and one path -- no crashes, finite outputs of the right shapes, errors where the boundary promises them"""
+    from stochvolmodels_b200 import HawkesJDParams, HawkesJDPricer, OptionChain
+    from stochvolmodels_b200._capi import B200svError
+    from stochvolmodels_b200.pricers.logsv_pricer import get_randoms_for_rough_vol_chain_valuation, rough_logsv_mc_chain_pricer_fixed_randoms
+    ttms = np.array([0.002, 0.05, 0.1])                       # first grid: int(0.002 * 100) + 1 = 1 step
+    K = [np.array([0.9, 1.0, 1.1]), np.zeros(0), np.array([1.0])]
+    T = [np.array(["P", "C", "IC"]), np.zeros(0, dtype="U2"), np.array(["IP"])]
+    for P in (1, 33):
+        Z0, Z1, grids = get_randoms_for_rough_vol_chain_valuation(ttms, nb_path=P, nb_steps_per_year=100, seed=2)
+        assert grids[0].size == 2
+        for n in (1, 8):
+            w, x = np.full(n, 1.0 / n), np.geomspace(1e-3, 50.0, n)
+            kw = dict(ttms=ttms, forwards=np.ones(3), discfactors=np.ones(3), strikes_ttms=K, optiontypes_ttms=T, Z0=Z0, Z1=Z1, sigma0=0.4, theta=0.5,
+                      kappa1=2.0, kappa2=1.0, beta=-0.2, orthog_vol=0.6, weights=w, nodes=x, timegrids=grids)
+            p, e = rough_logsv_mc_chain_pricer_fixed_randoms(**kw)
+            po, eo = rough.rough_chain_fixed(ttms, np.ones(3), np.ones(3), K, T, Z0, Z1, 0.4, 0.5, 2.0, 1.0, -0.2, 0.6, w, x, grids)
+            assert [a.shape for a in p] == [(3,), (0,), (1,)] and [a.shape for a in e] == [(3,), (0,), (1,)]
+            for m in (0, 2):
+                np.testing.assert_allclose(p[m], po[m], rtol=1e-10, atol=1e-14)
+                np.testing.assert_allclose(e[m], eo[m], rtol=1e-8, atol=1e-13)
+    with pytest.raises((B200svError, ValueError)):
+        rough_logsv_mc_chain_pricer_fixed_randoms(**{**kw, "weights": np.full(9, 1.0 / 9), "nodes": np.geomspace(1e-3, 50.0, 9)})
+    with pytest.raises(ValueError):
+        rough_logsv_mc_chain_pricer_fixed_randoms(**{**kw, "Z1": None})
+    with pytest.raises(ValueError, match="unknown option payoff code"):
+        rough_logsv_mc_chain_pricer_fixed_randoms(**{**kw, "optiontypes_ttms": [np.array(["P", "C", "X"]), T[1], T[2]]})
+    chain = OptionChain(ttms=np.array([0.01, 0.03]), forwards=np.ones(2), strikes_ttms=[np.zeros(0), np.array([0.95, 1.05])],
+                        optiontypes_ttms=[np.zeros(0, dtype="U2"), np.array(["P", "C"])])
+    for P in (1, 257):
+        p, e = HawkesJDPricer().model_mc_price_chain(chain, HawkesJDParams(), nb_path=P, seed=4)
+        assert p[0].shape == (0,) and p[1].shape == (2,) and np.all(np.isfinite(p[1])) and np.all(e[1] >= 0.0)
