@@ -1179,8 +1179,10 @@ static int launch_chain_coop(int gauss, const CoopArgs& args, const void* d_spec
 // profiles/r02_coop_chain.txt: 1e4 paths 0.18 vs 0.24 ms, 1e6 paths 0.75 vs 0.76 ms) and loses 5-6 % at >= 1e7 paths, where its 128-register
 // budget (slice + payoff phases in one kernel) costs more than 20 launches: it serves nb_path <= kCoopMaxPaths.
 // B200SV_CHAIN_COOP=0 / 1 forces the multi-launch / cooperative driver (A/B measurements, tests).
-constexpr long long kCoopMaxPaths = 4000000;
-static bool use_coop_chain(int flags, long long nb_path) {
+constexpr long long kCoopMaxPaths = 4000000;        // LogSV
+constexpr long long kCoopMaxPathsHeston = 500000;   // Heston's cheaper step leaves less to hide the fused kernel's register budget behind: 1e6 paths
+                                                    // 0.926 (cooperative) vs 0.890 ms (20 launches)
+static bool use_coop_chain(int flags, long long nb_path, bool heston = false) {
   if (flags & B200SV_STATE_F32) return false;
   const int g = gauss_mode(flags);
   if (g != kGaussF32 && g != kGaussF64) return false;
@@ -1192,7 +1194,7 @@ static bool use_coop_chain(int flags, long long nb_path) {
     if (!coop) return 0;
     return e ? (e[0] == '0' ? 0 : 2) : 1;      // 0 never, 1 by size, 2 always
   }();
-  return mode == 2 || (mode == 1 && nb_path <= kCoopMaxPaths);
+  return mode == 2 || (mode == 1 && nb_path <= (heston ? kCoopMaxPathsHeston : kCoopMaxPaths));
 }
 
 // Small-chain fast path: ONE stream-ordered allocation, ONE host-to-device copy (strikes, types and the per-maturity specs of all B sets in
@@ -1314,7 +1316,7 @@ static int mc_chain_host(const b200sv_logsv_params* lp, const b200sv_heston_para
   B200SV_REQUIRE(nb_path >= 1, "nb_path must be >= 1");
   B200SV_REQUIRE(nb_steps_per_year >= 1, "nb_steps_per_year must be >= 1");
   if (int rc = validate_chain(M, ttms, offsets, types, variable_type)) return rc;
-  if (use_coop_chain(flags, nb_path))
+  if (use_coop_chain(flags, nb_path, MODEL == 1))
     return mc_chain_host_coop<MODEL>(lp, hp, M, ttms, forwards, discfactors, etas, offsets, strikes, types, nb_path, nb_steps_per_year, is_spot,
                                      variable_type, seed, flags, prices_out, stderr_out, scheme, B, ivols_out);
   const int Jtot = offsets[M] - offsets[0];
