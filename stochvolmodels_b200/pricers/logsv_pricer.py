@@ -260,6 +260,11 @@ def _logsv_chain_pricer_analytic(params, ttms, forwards, discfactors, strikes_tt
         else:
             prices.append(mgfp.slice_qvar_pricer_with_a_grid(log_mgf_grid=log_mgf, psi_grid=psi_grid, ttm=ttm, forward=forward, strikes=strikes,
                                                              optiontypes=types, discfactor=discfactor, is_spot_measure=is_spot_measure))
+        if not np.all(np.isfinite(log_mgf)):
+            # the branch's unchecked fixed-point sweeps have diverged on part of the grid (the reference: quickstart / BTC parameters at
+            # SECOND order).  The reference's Fourier sum is an njit(fastmath=True) nansum, which does not skip the NaNs it is fed and
+            # returns NaN for every strike; a NaN-skipping sum over the surviving grid points would be a finite but meaningless number.
+            prices[-1] = np.full(np.asarray(strikes).shape, np.nan)
         grids.append((a_t0, log_mgf))
         ttm0 = ttm
     return (prices, grids) if return_grids else prices

@@ -258,11 +258,18 @@ def test_semi_analytic_branch_vs_reference_golden(cuda_lib, name):
 
 
 def test_semi_analytic_branch_diverges_where_the_reference_does(cuda_lib):
-    """quickstart parameters at SECOND order: the reference's unchecked fixed-point iteration blows up and it returns NaN for every strike;
-    the drop-in does the same (non-finite prices), it does not silently fall back to RK45"""
+    """quickstart parameters at SECOND order: the reference's unchecked fixed-point sweeps blow up beyond |phi| ~ 16 and it returns NaN for
+    every strike.  The drop-in agrees with it on the convergent part of the grid, is non-finite in the divergent tail as well (which grid
+    points of a chaotic iteration end up inf vs NaN is not comparable), and returns NaN prices -- it does not silently fall back to RK45."""
     from stochvolmodels_b200 import LogSvParams, LogSVPricer, OptionChain
     g = load_golden("logsv_analytic_branch.npz")
     assert np.all(np.isnan(g["quick_second_nan_prices"]))
     chain = OptionChain(ttms=g["ttms"], forwards=np.ones(3), strikes_ttms=[g["strikes"]] * 3, optiontypes_ttms=[g["quick_second_nan_types"]] * 3)
-    prices = LogSVPricer().price_chain(chain, LogSvParams(1.0, 1.0, 5.0, 5.0, 0.2, 2.0), is_analytic=True)
-    assert not np.any(np.isfinite(np.concatenate(prices)))
+    prices, grids = LogSVPricer().price_chain(chain, LogSvParams(1.0, 1.0, 5.0, 5.0, 0.2, 2.0), is_analytic=True, return_grids=True)
+    assert np.all(np.isnan(np.concatenate(prices)))
+    for m in range(3):
+        ref, lm = g[f"quick_second_nan_lm_{m}"], grids[m][1][::8]
+        first_bad = int(np.argmin(np.isfinite(ref)))
+        assert first_bad > 40
+        np.testing.assert_allclose(lm[: first_bad - 8], ref[: first_bad - 8], rtol=1e-6, atol=1e-8)      # converged region
+        assert not np.all(np.isfinite(lm[first_bad:]))                                                     # diverged tail

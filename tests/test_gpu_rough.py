@@ -201,8 +201,11 @@ def test_rough_and_hawkes_edge_cases(cuda_lib):
         rough_logsv_mc_chain_pricer_fixed_randoms(**{**kw, "Z1": None})
     with pytest.raises(ValueError, match="unknown option payoff code"):
         rough_logsv_mc_chain_pricer_fixed_randoms(**{**kw, "optiontypes_ttms": [np.array(["P", "C", "X"]), T[1], T[2]]})
-    chain = OptionChain(ttms=np.array([0.01, 0.03]), forwards=np.ones(2), strikes_ttms=[np.zeros(0), np.array([0.95, 1.05])],
-                        optiontypes_ttms=[np.zeros(0, dtype="U2"), np.array(["P", "C"])])
+    # Hawkes: an empty slice through the function-level entry (OptionChain itself rejects empty slices, like the reference's), 1 / 257 paths
+    from stochvolmodels_b200.pricers.hawkes_jd_pricer import hawkesjd_mc_chain_pricer
+    d = {k: v for k, v in HawkesJDParams().to_dict().items() if k != "risk_premia_gamma"}
     for P in (1, 257):
-        p, e = HawkesJDPricer().model_mc_price_chain(chain, HawkesJDParams(), nb_path=P, seed=4)
+        p, e = hawkesjd_mc_chain_pricer(ttms=np.array([0.01, 0.03]), forwards=np.ones(2), discfactors=np.ones(2),
+                                        strikes_ttms=[np.zeros(0), np.array([0.95, 1.05])],
+                                        optiontypes_ttms=[np.zeros(0, dtype="U2"), np.array(["P", "C"])], nb_path=P, seed=4, **d)
         assert p[0].shape == (0,) and p[1].shape == (2,) and np.all(np.isfinite(p[1])) and np.all(e[1] >= 0.0)
