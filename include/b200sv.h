@@ -198,6 +198,8 @@ int b200sv_p2p_destroy(void* p2p_ctx);
  * host must call it after the chain's copy back and treat non-zero as an error (multi_gpu.mc_chain_distributed raises P2pTimeout). */
 int b200sv_p2p_set_spin_limit(void* p2p_ctx, unsigned int spins);
 int b200sv_p2p_status(void* p2p_ctx, unsigned int* status_out, void* stream);
+/* test hook: pretend a publish was issued that never arrives, so that the next gather runs into the spin limit */
+int b200sv_debug_p2p_lose_publish(void* p2p_ctx);
 /* standalone halves of an exchange (ranks without local paths; tests): publish K local values / gather the K global ones */
 int b200sv_dev_p2p_publish(void* p2p_ctx, const double* vals, int K, void* stream);
 int b200sv_dev_p2p_gather(void* p2p_ctx, int K, double* out, void* stream);

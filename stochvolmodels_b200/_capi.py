@@ -87,6 +87,7 @@ SIGNATURES = {
     "b200sv_p2p_destroy": [c_void_p],
     "b200sv_p2p_set_spin_limit": [c_void_p, ctypes.c_uint],
     "b200sv_p2p_status": [c_void_p, POINTER(ctypes.c_uint), c_void_p],
+    "b200sv_debug_p2p_lose_publish": [c_void_p],
     "b200sv_dev_p2p_publish": [c_void_p, c_void_p, c_int, c_void_p],
     "b200sv_dev_p2p_gather": [c_void_p, c_int, c_void_p, c_void_p],
     "b200sv_dev_logsv_step_fixed": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_double, _lp, c_double,

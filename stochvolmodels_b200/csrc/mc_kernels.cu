@@ -1978,6 +1978,14 @@ int b200sv_p2p_status(void* ctx, unsigned int* status_out, void* stream) {
   return 0;
 }
 
+// test hook: account for a publish that never happens (a peer that died / never arrived) -- the next gather on this context waits for an epoch
+// nobody signals and must run into the spin limit: poisoned values + status bit, never a hang
+int b200sv_debug_p2p_lose_publish(void* ctx) {
+  B200SV_REQUIRE(ctx, "null pointer");
+  ++((P2pCtx*)ctx)->published;
+  return 0;
+}
+
 int b200sv_dev_p2p_publish(void* ctx, const double* vals, int K, void* stream) {
   B200SV_REQUIRE(ctx && K >= 1, "null pointer / K");
   P2pCtx* c = (P2pCtx*)ctx;

@@ -86,6 +86,44 @@ def test_fused_exchange_equals_plain_path_bitwise(cuda_lib, kinds, types):
     C.call("b200sv_p2p_destroy", small)
 
 
+def test_gather_timeout_is_an_error_not_a_silent_nan(cuda_lib):
+    """a peer that never publishes used to poison the prices with a quiet NaN.  Now the gather sets a status word that the host
+    reads after the chain's copy back: b200sv_p2p_status reports the missing rank, CudaMcEngine.check_p2p raises P2pTimeout; the spin limit is
+    configurable (2000 polls here: the test takes milliseconds, not the default 3 s)."""
+    import torch
+    from stochvolmodels_b200 import _capi as C, engine
+    from stochvolmodels_b200.multi_gpu import CudaMcEngine, P2pTimeout
+    ctx = _mailbox(C, cap=16)
+    C.call("b200sv_p2p_set_spin_limit", ctx, 2000)
+    st = c_void_p(torch.cuda.current_stream().cuda_stream)
+    out = torch.zeros(4, dtype=torch.float64, device="cuda")
+    status = ctypes.c_uint(7)
+    C.call("b200sv_p2p_status", ctx, byref(status), st)
+    assert status.value == 0
+    vals = torch.ones(4, dtype=torch.float64, device="cuda")
+    C.call("b200sv_dev_p2p_publish", ctx, c_void_p(vals.data_ptr()), 4, st)          # a healthy exchange first
+    C.call("b200sv_dev_p2p_gather", ctx, 4, c_void_p(out.data_ptr()), st)
+    C.call("b200sv_p2p_status", ctx, byref(status), st)
+    assert status.value == 0 and np.all(out.cpu().numpy() == 1.0)
+    C.call("b200sv_debug_p2p_lose_publish", ctx)                                     # the "peer" (rank 0 of world 1) never arrives
+    C.call("b200sv_dev_p2p_gather", ctx, 4, c_void_p(out.data_ptr()), st)
+    C.call("b200sv_p2p_status", ctx, byref(status), st)
+    assert status.value == 1 and np.all(np.isnan(out.cpu().numpy()))                 # bit 0 = rank 0 missing; values poisoned
+    C.call("b200sv_p2p_status", ctx, byref(status), st)
+    assert status.value == 0                                                         # reading clears it
+    # the Python driver's check: an engine whose exchange timed out raises instead of returning NaN prices
+    eng = CudaMcEngine("logsv", engine.logsv_params_c(*Q), 1000, 0, 0, 5)
+    eng.p2p = ctx
+    eng.check_p2p()                                                                   # clean: no raise
+    C.call("b200sv_debug_p2p_lose_publish", ctx)
+    sums = torch.zeros(15, dtype=torch.float64, device="cuda")
+    eng.finalize(sums, 5, 1.0, 1000)                                                  # gathers the (never published) global sums
+    with pytest.raises(P2pTimeout, match="rank"):
+        eng.check_p2p()
+    eng.p2p = None
+    C.call("b200sv_p2p_destroy", ctx)
+
+
 def test_two_gpu_exchange_vs_nccl_and_single_gpu(cuda_lib):
     import torch
     if torch.cuda.device_count() < 2:
