@@ -308,6 +308,10 @@ int b200sv_logsv_mgf_grid(const double* phi, const double* psi, int P, double dt
  * a_inout complex [P][n] in/out, log_mgf_out complex [P]; vol_backbone_eta is ignored on this branch, as in the reference. */
 int b200sv_logsv_mgf_grid_analytic(const double* phi, const double* psi, int P, double dtau, double* a_inout, const b200sv_logsv_params* params,
                                    int is_spot_measure, int expansion_order, int year_days, double* log_mgf_out);
+/* compute_logsv_a_mgf_grid(is_stiff_solver=True): solve_ivp(method="BDF", jac=func_rhs_jac) per grid point (pricers/logsv/affine_expansion.py:229-303) --
+ * a clone of SciPy's BDF control law (scipy 1.18.1 _ivp/bdf.py), default rtol 1e-3 / atol 1e-6.  Same arrays as b200sv_logsv_mgf_grid. */
+int b200sv_logsv_mgf_grid_bdf(const double* phi, const double* psi, int P, double dtau, double* a_inout, const b200sv_logsv_params* params,
+                              double eta, int is_spot_measure, int expansion_order, double* log_mgf_out);
 /* func_a_ode_quadratic_terms (pricers/logsv/affine_expansion.py:67-184): the dense coefficient tensors of A' = A^T M^(k) A + L A + H for
  * P transform points, n = 3 (FIRST) or 5 (SECOND): M_out complex [P][n][n][n] (symmetric in the last two indices), L_out [P][n][n],
  * H_out [P][n], interleaved (re, im).  psi may be NULL (zeros).  Parity entry: the pricing kernels integrate the same rows in sparse form. */

@@ -520,3 +520,24 @@ def logsv_analytic_a_grid(dtau, phi, psi, a_t0, theta, kappa1, kappa2, beta, vol
                 a = fp
         out[p] = a
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# stiff branch (is_stiff_solver=True)
+# ---------------------------------------------------------------------------------------------------------------------------------
+def logsv_bdf_a_grid(dtau, phi, psi, a_t0, theta, kappa1, kappa2, beta, volvol, is_spot_measure=True, order=2, eta=1.0, return_stats=False):
+    """``solve_ode_for_a(is_stiff_solver=True)`` over a grid (pricers/logsv/affine_expansion.py:229-303, 492-529): SciPy's own
+    ``solve_ivp(method='BDF', jac=func_rhs_jac)`` (default rtol 1e-3 / atol 1e-6) per grid point on the restated M, L, H.  The third-party
+    arithmetic here IS the reference's (scipy 1.18.1, scipy/integrate/_ivp/bdf.py): the oracle calls it, the CUDA kernel clones its control law."""
+    from scipy.integrate import solve_ivp
+    n = expansion_n(order)
+    out = np.empty((phi.shape[0], n), dtype=np.complex128)
+    stats = []
+    for p in range(phi.shape[0]):
+        M, L, H = logsv_mlh(theta, kappa1, kappa2, beta, volvol, complex(phi[p]), complex(psi[p]), is_spot_measure, order, eta)
+        fun = lambda t, A: np.array([A @ M[k] @ A for k in range(n)]) + L @ A + H
+        jac = lambda t, A: np.array([2.0 * M[k] @ A for k in range(n)]) + L
+        sol = solve_ivp(fun=fun, t_span=(0.0, dtau), y0=np.array(a_t0[p], dtype=np.complex128), method="BDF", jac=jac)
+        out[p] = sol.y[:, -1]
+        stats.append((sol.nfev, sol.njev, sol.nlu, sol.t.size - 1))
+    return (out, np.array(stats)) if return_stats else out

@@ -106,6 +106,7 @@ SIGNATURES = {
     "b200sv_bsm_implied_vols": [c_int, _dp, _dp, _dp, _ip, _dp, _i8p, _dp, _dp],
     "b200sv_logsv_mgf_grid": [_dp, _dp, c_int, c_double, _dp, _lp, c_double, c_int, c_int, _dp],
     "b200sv_logsv_mgf_grid_analytic": [_dp, _dp, c_int, c_double, _dp, _lp, c_int, c_int, c_int, _dp],
+    "b200sv_logsv_mgf_grid_bdf": [_dp, _dp, c_int, c_double, _dp, _lp, c_double, c_int, c_int, _dp],
     "b200sv_logsv_ode_terms": [_dp, _dp, c_int, _lp, c_double, c_int, c_int, _dp, _dp, _dp],
     "b200sv_logsv_ode_rhs": [_dp, _dp, c_int, _dp, _lp, c_double, c_int, c_int, _dp],
     "b200sv_ode_rhs_dense": [_dp, c_int, c_int, _dp, _dp, _dp, _dp],

@@ -938,6 +938,344 @@ __global__ void __launch_bounds__(64) logsv_mgf_analytic_kernel(const cd* __rest
   log_mgf[p] = lm;
 }
 
+// --------------------------------------------------------------------------------------------------------------------
+// stiff branch: solve_ivp(method="BDF", jac=func_rhs_jac) as used by solve_ode_for_a(is_stiff_solver=True) (affine_expansion.py:229-303)
+// --------------------------------------------------------------------------------------------------------------------
+// A clone of the CONTROL LAW of scipy.integrate.BDF (scipy 1.18.1, scipy/integrate/_ivp/bdf.py:14-60, 186-230, 317-455; select_initial_step
+// with order 1, common.py:68-134; rtol 1e-3 / atol 1e-6): variable order 1..5 NDF with quasi-constant step size, the differences array D and
+// its rescaling matrices (change_D), simplified Newton with at most 4 iterations on an LU of I - c J that is KEPT across steps and across
+// error rejections (bdf.py resets it only when the step size changes for other reasons), Jacobian refreshed only after a failed Newton
+// solve, order selection from the three error norms after order + 1 equal steps.  Parity with the reference means reproducing its accepted
+// steps, so every branch of the step routine is mirrored; floating-point differences (LAPACK's blocked zgetrf / BLAS dot products vs the
+// scalar loops here) stay at the 1e-15 level because the decisions are thresholds on norms (tests: 1e-10 against the reference goldens).
+// One thread = one grid point; D (8 x N complex), J and LU live in thread-local memory -- this is the reference's non-default branch, 1000
+// independent stiff solves of ~30 steps each, not a throughput path.
+template <int N>
+struct BdfState {
+  cd D[8][N];
+  cd J[N][N], LU[N][N];
+  int piv[N];
+  bool lu_valid;
+};
+
+__device__ __forceinline__ double cabs1(cd a) { return fabs(a.re) + fabs(a.im); }     // LAPACK izamax's magnitude
+
+template <int N>
+__device__ void bdf_lu_factor(BdfState<N>& s, double c) {             // LU of I - c J, partial pivoting (zgetrf semantics)
+  for (int i = 0; i < N; ++i)
+    for (int j = 0; j < N; ++j) s.LU[i][j] = mk(i == j ? 1.0 : 0.0) - c * s.J[i][j];
+  for (int k = 0; k < N; ++k) {
+    int p = k;
+    double best = cabs1(s.LU[k][k]);
+    for (int i = k + 1; i < N; ++i) {
+      const double v = cabs1(s.LU[i][k]);
+      if (v > best) {
+        best = v;
+        p = i;
+      }
+    }
+    s.piv[k] = p;
+    if (p != k)
+      for (int j = 0; j < N; ++j) {
+        const cd t = s.LU[k][j];
+        s.LU[k][j] = s.LU[p][j];
+        s.LU[p][j] = t;
+      }
+    const cd inv = mk(1.0) / s.LU[k][k];
+    for (int i = k + 1; i < N; ++i) {
+      s.LU[i][k] = s.LU[i][k] * inv;
+      for (int j = k + 1; j < N; ++j) s.LU[i][j] = s.LU[i][j] - s.LU[i][k] * s.LU[k][j];
+    }
+  }
+  s.lu_valid = true;
+}
+
+template <int N>
+__device__ void bdf_lu_solve(const BdfState<N>& s, cd (&b)[N]) {
+  for (int k = 0; k < N; ++k) {
+    const int p = s.piv[k];
+    if (p != k) {
+      const cd t = b[k];
+      b[k] = b[p];
+      b[p] = t;
+    }
+  }
+  for (int i = 1; i < N; ++i)
+    for (int j = 0; j < i; ++j) b[i] = b[i] - s.LU[i][j] * b[j];
+  for (int i = N - 1; i >= 0; --i) {
+    for (int j = i + 1; j < N; ++j) b[i] = b[i] - s.LU[i][j] * b[j];
+    b[i] = b[i] / s.LU[i][i];
+  }
+}
+
+// func_rhs_jac (affine_expansion.py:208-225): J = 2 M[k] A + L, from the row tables
+template <int N>
+__device__ void bdf_jacobian(BdfState<N>& s, const cd (&A)[N], const LogsvModel& m, cd phi, cd psi) {
+  for (int k = 0; k < N; ++k) {
+    for (int j = 0; j < N; ++j) s.J[k][j] = mk(0.0);
+    const LaneRow<N> r = make_lane_row<N>(k, m, phi, psi);
+    for (int t = 0; t < r.nq; ++t) {
+      const int i = r.qi[t], j = r.qj[t];
+      if (i == j) {
+        s.J[k][i] = s.J[k][i] + (2.0 * r.q[t]) * A[i];
+      } else {                       // the tables carry off-diagonal pairs doubled: q A_i A_j with q = M_ij + M_ji
+        s.J[k][i] = s.J[k][i] + r.q[t] * A[j];
+        s.J[k][j] = s.J[k][j] + r.q[t] * A[i];
+      }
+    }
+    for (int t = 0; t < r.nl; ++t) s.J[k][r.li[t]] = s.J[k][r.li[t]] + r.l[t];
+  }
+}
+
+// change_D (bdf.py:28-33): D[:order+1] <- (R U)^T D[:order+1],  R = compute_R(order, factor), U = compute_R(order, 1)
+template <int N>
+__device__ void bdf_change_D(BdfState<N>& s, int order, double factor) {
+  double R[6][6], U[6][6], RU[6][6];
+  for (int j = 0; j <= order; ++j) {
+    R[0][j] = 1.0;
+    U[0][j] = 1.0;
+  }
+  for (int i = 1; i <= order; ++i) {
+    R[i][0] = 0.0;                  // M[i][0] = 0 => cumprod is 0 from row 1 on
+    U[i][0] = 0.0;
+    for (int j = 1; j <= order; ++j) {
+      R[i][j] = R[i - 1][j] * (((double)(i - 1) - factor * (double)j) / (double)i);
+      U[i][j] = U[i - 1][j] * (((double)(i - 1) - (double)j) / (double)i);
+    }
+  }
+  for (int i = 0; i <= order; ++i)
+    for (int j = 0; j <= order; ++j) {
+      double acc = 0.0;
+      for (int k = 0; k <= order; ++k) acc += R[i][k] * U[k][j];
+      RU[i][j] = acc;
+    }
+  cd Dn[6][N];
+  for (int i = 0; i <= order; ++i)
+    for (int c = 0; c < N; ++c) {
+      cd acc = mk(0.0);
+      for (int k = 0; k <= order; ++k) acc = acc + RU[k][i] * s.D[k][c];
+      Dn[i][c] = acc;
+    }
+  for (int i = 0; i <= order; ++i)
+    for (int c = 0; c < N; ++c) s.D[i][c] = Dn[i][c];
+}
+
+template <int N>
+__device__ double bdf_norm_scaled(const cd (&v)[N], const double (&scale)[N]) {       // norm(v / scale) = ||.||_2 / sqrt(n)
+  double acc = 0.0;
+  for (int k = 0; k < N; ++k) {
+    const double re = v[k].re / scale[k], im = v[k].im / scale[k];
+    acc += re * re + im * im;
+  }
+  return sqrt(acc) / sqrt((double)N);
+}
+
+// returns 0 ok, 1 step size underflow (TOO_SMALL_STEP: the reference keeps the last accepted state)
+template <int N, int TPB>
+__device__ int bdf_integrate(cd (&y)[N], double T, const LogsvModel& m, const CoefView<TPB>& c, cd phi, cd psi, BdfState<N>& s) {
+  const double gamma[6] = {0.0, 1.0, 1.5, 1.5 + 1.0 / 3.0, 1.5 + 1.0 / 3.0 + 0.25, 1.5 + 1.0 / 3.0 + 0.25 + 0.2};
+  const double kappa[6] = {0.0, -0.1850, -1.0 / 9.0, -0.0823, -0.0415, 0.0};
+  double alpha[6], error_const[7];
+  for (int i = 0; i < 6; ++i) {
+    alpha[i] = (1.0 - kappa[i]) * gamma[i];
+    error_const[i] = kappa[i] * gamma[i] + 1.0 / (double)(i + 1);
+  }
+  const double newton_tol = 0.03;       // max(10 EPS / rtol, min(0.03, sqrt(rtol)))
+  cd f[N];
+  rhs<N, TPB>(y, m, c, f);
+  double h_abs;
+  {  // select_initial_step(order = 1)
+    double scale[N];
+    for (int k = 0; k < N; ++k) scale[k] = kAtol + cmod(y[k]) * kRtol;
+    const double d0 = bdf_norm_scaled<N>(y, scale), d1 = bdf_norm_scaled<N>(f, scale);
+    double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+    h0 = fmin(h0, T);
+    cd y1[N], f1[N];
+    for (int k = 0; k < N; ++k) y1[k] = y[k] + h0 * f[k];
+    rhs<N, TPB>(y1, m, c, f1);
+    for (int k = 0; k < N; ++k) f1[k] = f1[k] - f[k];
+    const double d2 = bdf_norm_scaled<N>(f1, scale) / h0;
+    const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : sqrt(0.01 / fmax(d1, d2));
+    h_abs = fmin(fmin(100.0 * h0, h1), T);
+  }
+  bdf_jacobian<N>(s, y, m, phi, psi);
+  for (int i = 0; i < 8; ++i)
+    for (int k = 0; k < N; ++k) s.D[i][k] = mk(0.0);
+  for (int k = 0; k < N; ++k) {
+    s.D[0][k] = y[k];
+    s.D[1][k] = h_abs * f[k];
+  }
+  int order = 1, n_equal_steps = 0;
+  s.lu_valid = false;
+  double t = 0.0;
+  for (int guard = 0; t < T && guard < 100000; ++guard) {
+    // ---- _step_impl (bdf.py:317-455)
+    const double min_step = 10.0 * (__longlong_as_double(__double_as_longlong(t) + 1) - t);
+    if (h_abs < min_step) {
+      bdf_change_D<N>(s, order, min_step / h_abs);
+      h_abs = min_step;
+      n_equal_steps = 0;
+    }
+    bool current_jac = false;
+    bool accepted = false;
+    double t_new = t, safety = 0.0, error_norm = 0.0;
+    double scale[N];
+    cd y_new[N], d[N];
+    while (!accepted) {
+      if (h_abs < min_step) return 1;
+      t_new = t + h_abs;
+      if (t_new - T > 0.0) {
+        t_new = T;
+        bdf_change_D<N>(s, order, fabs(t_new - t) / h_abs);
+        n_equal_steps = 0;
+        s.lu_valid = false;
+      }
+      const double h = t_new - t;
+      h_abs = fabs(h);
+      cd y_predict[N], psi_v[N];
+      for (int k = 0; k < N; ++k) {
+        cd acc = s.D[0][k];
+        for (int i = 1; i <= order; ++i) acc = acc + s.D[i][k];
+        y_predict[k] = acc;
+        scale[k] = kAtol + kRtol * cmod(acc);
+        cd ps = mk(0.0);
+        for (int i = 1; i <= order; ++i) ps = ps + gamma[i] * s.D[i][k];
+        psi_v[k] = mk(ps.re / alpha[order], ps.im / alpha[order]);      // numpy divides (dot(...) / alpha[order]): no reciprocal multiply
+      }
+      const double cc = h / alpha[order];
+      bool converged = false;
+      int n_iter = 0;
+      while (!converged) {
+        if (!s.lu_valid) bdf_lu_factor<N>(s, cc);
+        // ---- solve_bdf_system (bdf.py:36-72)
+        for (int k = 0; k < N; ++k) {
+          d[k] = mk(0.0);
+          y_new[k] = y_predict[k];
+        }
+        double dy_norm_old = -1.0;
+        for (int k_it = 0; k_it < 4; ++k_it) {
+          cd fn[N];
+          rhs<N, TPB>(y_new, m, c, fn);
+          bool finite = true;
+          for (int k = 0; k < N; ++k) finite = finite && isfinite(fn[k].re) && isfinite(fn[k].im);
+          if (!finite) break;
+          cd dy[N];
+          for (int k = 0; k < N; ++k) dy[k] = (cc * fn[k] - psi_v[k]) - d[k];
+          bdf_lu_solve<N>(s, dy);
+          const double dy_norm = bdf_norm_scaled<N>(dy, scale);
+          const bool have_rate = dy_norm_old >= 0.0;
+          const double rate = have_rate ? dy_norm / dy_norm_old : 0.0;
+          if (have_rate && (rate >= 1.0 || pow(rate, (double)(4 - k_it)) / (1.0 - rate) * dy_norm > newton_tol)) break;
+          for (int k = 0; k < N; ++k) {
+            y_new[k] = y_new[k] + dy[k];
+            d[k] = d[k] + dy[k];
+          }
+          n_iter = k_it + 1;
+          if (dy_norm == 0.0 || (have_rate && rate / (1.0 - rate) * dy_norm < newton_tol)) {
+            converged = true;
+            break;
+          }
+          dy_norm_old = dy_norm;
+        }
+        if (!converged) {
+          if (current_jac) break;
+          bdf_jacobian<N>(s, y_predict, m, phi, psi);
+          s.lu_valid = false;
+          current_jac = true;
+        }
+      }
+      if (!converged) {
+        h_abs *= 0.5;
+        bdf_change_D<N>(s, order, 0.5);
+        n_equal_steps = 0;
+        s.lu_valid = false;
+        continue;
+      }
+      safety = 0.9 * (2.0 * 4.0 + 1.0) / (2.0 * 4.0 + (double)n_iter);
+      for (int k = 0; k < N; ++k) scale[k] = kAtol + kRtol * cmod(y_new[k]);
+      cd err[N];
+      for (int k = 0; k < N; ++k) err[k] = error_const[order] * d[k];
+      error_norm = bdf_norm_scaled<N>(err, scale);
+      if (error_norm > 1.0) {
+        const double factor = fmax(0.2, safety * pow(error_norm, -1.0 / (double)(order + 1)));
+        h_abs *= factor;
+        bdf_change_D<N>(s, order, factor);
+        n_equal_steps = 0;            // LU is deliberately NOT invalidated here (bdf.py:398-403)
+      } else {
+        accepted = true;
+      }
+    }
+    ++n_equal_steps;
+    t = t_new;
+    for (int k = 0; k < N; ++k) {
+      y[k] = y_new[k];
+      s.D[order + 2][k] = d[k] - s.D[order + 1][k];
+      s.D[order + 1][k] = d[k];
+    }
+    for (int i = order; i >= 0; --i)
+      for (int k = 0; k < N; ++k) s.D[i][k] = s.D[i][k] + s.D[i + 1][k];
+    if (n_equal_steps < order + 1) continue;
+    double en[3];
+    {
+      cd e[N];
+      if (order > 1) {
+        for (int k = 0; k < N; ++k) e[k] = error_const[order - 1] * s.D[order][k];
+        en[0] = bdf_norm_scaled<N>(e, scale);
+      } else {
+        en[0] = INFINITY;
+      }
+      en[1] = error_norm;
+      if (order < 5) {
+        for (int k = 0; k < N; ++k) e[k] = error_const[order + 1] * s.D[order + 2][k];
+        en[2] = bdf_norm_scaled<N>(e, scale);
+      } else {
+        en[2] = INFINITY;
+      }
+    }
+    double factors[3], best = -1.0;
+    int arg = 0;
+    for (int i = 0; i < 3; ++i) {
+      factors[i] = pow(en[i], -1.0 / (double)(order + i));     // 0 -> inf, inf -> 0 (numpy with divide='ignore')
+      if (factors[i] > best) {                                   // np.argmax: first maximum
+        best = factors[i];
+        arg = i;
+      }
+    }
+    order += arg - 1;
+    const double factor = fmin(10.0, safety * best);
+    h_abs *= factor;
+    bdf_change_D<N>(s, order, factor);
+    n_equal_steps = 0;
+    s.lu_valid = false;
+  }
+  return 0;
+}
+
+template <int N>
+__global__ void __launch_bounds__(64) logsv_mgf_bdf_kernel(const cd* __restrict__ phi, const cd* __restrict__ psi, int P, LogsvModel m, double dtau,
+                                                           const cd* __restrict__ a_in, cd* __restrict__ a_out, cd* __restrict__ log_mgf, double y,
+                                                           int* __restrict__ status) {
+  __shared__ cd coef_smem[14 * 64];
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const cd ph = phi[p], ps = psi ? psi[p] : mk(0.0);
+  store_coef<64>(coef_smem + threadIdx.x, make_coef(m, ph, ps));
+  const CoefView<64> c{coef_smem + threadIdx.x};
+  cd A[N];
+  for (int k = 0; k < N; ++k) A[k] = a_in[(size_t)p * N + k];
+  BdfState<N> st;
+  const int rc = bdf_integrate<N, 64>(A, dtau, m, c, ph, ps, st);
+  if (status) status[p] = rc;
+  double yk = 1.0;
+  cd lm = mk(0.0);
+  for (int k = 0; k < N; ++k) {
+    a_out[(size_t)p * N + k] = A[k];
+    lm = lm + yk * A[k];
+    yk *= y;
+  }
+  log_mgf[p] = lm;
+}
+
 static int mgf_block_threads(int P) {
   int t = 4;
   while (t < 64 && t * 148 < P) t <<= 1;
@@ -1435,6 +1773,38 @@ int b200sv_logsv_mgf_grid_analytic(const double* phi, const double* psi, int P, 
   else
     logsv_mgf_analytic_kernel<3><<<(P + 63) / 64, 64, 0, st>>>(d_phi.as<cd>(), dpsi, P, model, dtau, year_days, d_a0.as<cd>(), d_a1.as<cd>(), d_lm.as<cd>(), y);
   if (int rc = launched("logsv_mgf_analytic_kernel")) return rc;
+  B200SV_CUDA(cudaMemcpyAsync(a_inout, d_a1.p, sizeof(cd) * (size_t)P * N, cudaMemcpyDeviceToHost, st));
+  B200SV_CUDA(cudaMemcpyAsync(log_mgf_out, d_lm.p, sizeof(cd) * P, cudaMemcpyDeviceToHost, st));
+  B200SV_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// compute_logsv_a_mgf_grid(is_stiff_solver=True): SciPy's BDF control law per grid point (affine_expansion.py:229-303)
+int b200sv_logsv_mgf_grid_bdf(const double* phi, const double* psi, int P, double dtau, double* a_inout, const b200sv_logsv_params* params,
+                              double eta, int is_spot_measure, int expansion_order, double* log_mgf_out) {
+  B200SV_REQUIRE(phi && a_inout && params && log_mgf_out, "null pointer");
+  B200SV_REQUIRE(P >= 1 && dtau > 0.0, "P >= 1, dtau > 0");
+  if (expansion_order != B200SV_ORDER_FIRST && expansion_order != B200SV_ORDER_SECOND) return fail(-4, "expansion_order not implemented");
+  const int N = expansion_order == B200SV_ORDER_FIRST ? 3 : 5;
+  const LogsvModel model = make_model(*params, eta, is_spot_measure != 0);
+  cudaStream_t st = current_stream();
+  ensure_pool_threshold();
+  DevBuf d_phi(st), d_psi(st), d_a0(st), d_a1(st), d_lm(st);
+  B200SV_CUDA(d_phi.alloc(sizeof(cd) * P));
+  B200SV_CUDA(d_psi.alloc(sizeof(cd) * P));
+  B200SV_CUDA(d_a0.alloc(sizeof(cd) * (size_t)P * N));
+  B200SV_CUDA(d_a1.alloc(sizeof(cd) * (size_t)P * N));
+  B200SV_CUDA(d_lm.alloc(sizeof(cd) * P));
+  B200SV_CUDA(cudaMemcpyAsync(d_phi.p, phi, sizeof(cd) * P, cudaMemcpyHostToDevice, st));
+  if (psi) B200SV_CUDA(cudaMemcpyAsync(d_psi.p, psi, sizeof(cd) * P, cudaMemcpyHostToDevice, st));
+  B200SV_CUDA(cudaMemcpyAsync(d_a0.p, a_inout, sizeof(cd) * (size_t)P * N, cudaMemcpyHostToDevice, st));
+  const cd* dpsi = psi ? d_psi.as<cd>() : nullptr;
+  const double y = params->sigma0 - params->theta;
+  if (N == 5)
+    logsv_mgf_bdf_kernel<5><<<(P + 63) / 64, 64, 0, st>>>(d_phi.as<cd>(), dpsi, P, model, dtau, d_a0.as<cd>(), d_a1.as<cd>(), d_lm.as<cd>(), y, nullptr);
+  else
+    logsv_mgf_bdf_kernel<3><<<(P + 63) / 64, 64, 0, st>>>(d_phi.as<cd>(), dpsi, P, model, dtau, d_a0.as<cd>(), d_a1.as<cd>(), d_lm.as<cd>(), y, nullptr);
+  if (int rc = launched("logsv_mgf_bdf_kernel")) return rc;
   B200SV_CUDA(cudaMemcpyAsync(a_inout, d_a1.p, sizeof(cd) * (size_t)P * N, cudaMemcpyDeviceToHost, st));
   B200SV_CUDA(cudaMemcpyAsync(log_mgf_out, d_lm.p, sizeof(cd) * P, cudaMemcpyDeviceToHost, st));
   B200SV_CUDA(cudaStreamSynchronize(st));

@@ -407,6 +407,21 @@ def logsv_mgf_grid(phi, psi, dtau: float, a_t0, params: C.LogsvParamsC, eta: flo
     return a, lm
 
 
+def logsv_mgf_grid_bdf(phi, psi, dtau: float, a_t0, params: C.LogsvParamsC, eta: float, is_spot_measure: bool, expansion_order: int):
+    """stiff branch (is_stiff_solver=True: SciPy's BDF control law) over a transform grid: (a_t1 [P, n], log_mgf [P])"""
+    phi = C.c128(phi)
+    psi = C.c128(psi) if psi is not None else None
+    P = phi.shape[0]
+    n = 3 if expansion_order == C.ORDER_FIRST else 5
+    a = np.array(C.c128(a_t0), copy=True)
+    if a.shape != (P, n):
+        raise ValueError(f"a_t0 must have shape ({P}, {n})")
+    lm = np.empty(P, dtype=np.complex128)
+    C.call("b200sv_logsv_mgf_grid_bdf", phi.ctypes.data_as(C._dp), psi.ctypes.data_as(C._dp) if psi is not None else None, P, float(dtau),
+           a.ctypes.data_as(C._dp), byref(params), float(eta), int(bool(is_spot_measure)), int(expansion_order), lm.ctypes.data_as(C._dp))
+    return a, lm
+
+
 def logsv_mgf_grid_analytic(phi, psi, dtau: float, a_t0, params: C.LogsvParamsC, is_spot_measure: bool, expansion_order: int, year_days: int = 260):
     """semi-analytic branch (is_analytic=True) over a transform grid: (a_t1 [P, n], log_mgf [P])"""
     phi = C.c128(phi)

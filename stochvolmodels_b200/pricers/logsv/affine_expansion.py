@@ -53,10 +53,8 @@ def compute_logsv_a_mgf_grid(ttm: float, phi_grid: np.ndarray, psi_grid: np.ndar
                              vol_backbone_eta: float = 1.0, **kwargs) -> Tuple[np.ndarray, np.ndarray]:
     """(a_t1, log_mgf) over the transform grid, one ODE solve per grid point on the GPU (affine_expansion.py:570-685): the default RK45 branch
     with SciPy's control law (:492-529), or with ``is_analytic=True`` the semi-analytic branch (business-day steps, exact linear part,
-    10 fixed-point sweeps for the quadratic part, :306-470; ``vol_backbone_eta`` is ignored there, as in the reference).  The BDF branch
-    (``is_stiff_solver``) is not rebuilt and refuses loudly."""
-    if is_stiff_solver and not is_analytic:
-        raise NotImplementedError("is_stiff_solver=True (SciPy BDF) is not implemented on the GPU: use the default RK45 branch or is_analytic=True")
+    10 fixed-point sweeps for the quadratic part, :306-470; ``vol_backbone_eta`` is ignored there, as in the reference), or with
+    ``is_stiff_solver=True`` SciPy's BDF control law with the analytic Jacobian (:229-303)."""
     order = _order_code(expansion_order)
     n = get_expansion_n(ExpansionOrder(order))
     if a_t0 is None:
@@ -66,6 +64,8 @@ def compute_logsv_a_mgf_grid(ttm: float, phi_grid: np.ndarray, psi_grid: np.ndar
     params = engine.logsv_params_c(sigma0, theta, kappa1, kappa2, beta, volvol)
     if is_analytic:            # takes precedence over is_stiff_solver, as in the reference (:643-654)
         return engine.logsv_mgf_grid_analytic(phi_grid, psi_grid, ttm, a_t0, params, is_spot_measure, order)
+    if is_stiff_solver:
+        return engine.logsv_mgf_grid_bdf(phi_grid, psi_grid, ttm, a_t0, params, vol_backbone_eta, is_spot_measure, order)
     return engine.logsv_mgf_grid(phi_grid, psi_grid, ttm, a_t0, params, vol_backbone_eta, is_spot_measure, order)
 
 
@@ -102,12 +102,11 @@ def solve_a_ode_grid(phi_grid: np.ndarray, psi_grid: np.ndarray, ttm: float, the
                      expansion_order: ExpansionOrder = ExpansionOrder.FIRST, vol_backbone_eta: float = 1.0) -> np.ndarray:
     """A(ttm) for every grid point from A(0) = ``a_t0`` (affine_expansion.py:492-529: a Python loop of ``solve_ivp`` calls there, one
     GPU launch here; same default ``expansion_order`` = FIRST as the reference function)."""
-    if is_stiff_solver:
-        raise NotImplementedError("is_stiff_solver=True (SciPy BDF) is not implemented on the GPU: use the default RK45 branch")
     order = _order_code(expansion_order)
     if a_t0 is None:
         a_t0 = np.zeros((phi_grid.shape[0], get_expansion_n(ExpansionOrder(order))), dtype=np.complex128)
     # the log-MGF contraction needs sigma0 - theta; it is discarded here, so any finite sigma0 does
-    a_t1, _ = engine.logsv_mgf_grid(phi_grid, psi_grid, ttm, a_t0, engine.logsv_params_c(theta, theta, kappa1, kappa2, beta, volvol),
-                                    vol_backbone_eta, is_spot_measure, order)
+    solver = engine.logsv_mgf_grid_bdf if is_stiff_solver else engine.logsv_mgf_grid
+    a_t1, _ = solver(phi_grid, psi_grid, ttm, a_t0, engine.logsv_params_c(theta, theta, kappa1, kappa2, beta, volvol), vol_backbone_eta,
+                     is_spot_measure, order)
     return a_t1

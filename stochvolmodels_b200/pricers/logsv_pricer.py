@@ -225,22 +225,21 @@ def logsv_chain_pricer(params: LogSvParams, ttms: np.ndarray, forwards: np.ndarr
     vt = getattr(variable_type, "value", variable_type)
     if vt not in (1, 2):
         raise NotImplementedError       # SIGMA: the reference raises too (:733-734)
-    if is_stiff_solver and not is_analytic:
-        raise NotImplementedError("is_stiff_solver=True (SciPy BDF) is not implemented on the GPU: use the default RK45 branch or is_analytic=True")
     order = _order_code(expansion_order)
-    if is_analytic:
-        return _logsv_chain_pricer_analytic(params, ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms, is_spot_measure, expansion_order,
-                                            variable_type, vol_scaler, bool(kwargs.get("return_grids", False)))
+    if is_analytic or is_stiff_solver:
+        return _logsv_chain_pricer_branch(params, ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms, is_spot_measure, expansion_order,
+                                          variable_type, vol_scaler, bool(kwargs.get("return_grids", False)), is_analytic, is_stiff_solver)
     etas = np.array([params.get_vol_backbone_eta(tau=ttm) for ttm in ttms], dtype=float)
     return engine.logsv_price_chain(_params_c(params), ttms, forwards, discfactors, etas, strikes_ttms, optiontypes_ttms,
                                     is_spot_measure=is_spot_measure, expansion_order=order, vol_scaler=vol_scaler,
                                     max_phi=kwargs.get("max_phi"), return_grids=bool(kwargs.get("return_grids", False)), variable_type=vt)
 
 
-def _logsv_chain_pricer_analytic(params, ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms, is_spot_measure, expansion_order, variable_type,
-                                 vol_scaler, return_grids):
-    """the chain loop of the reference (:699-737) on the semi-analytic branch (``is_analytic=True``): per maturity one grid solve carried on
-    ``a_t0`` and one Fourier sum, both on the GPU.  Not fused into a single call like the default branch -- it is a non-default route."""
+def _logsv_chain_pricer_branch(params, ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms, is_spot_measure, expansion_order, variable_type,
+                               vol_scaler, return_grids, is_analytic, is_stiff_solver):
+    """the chain loop of the reference (:699-737) on its two non-default ODE branches (``is_analytic=True``: semi-analytic scheme;
+    ``is_stiff_solver=True``: SciPy's BDF control law): per maturity one grid solve carried on ``a_t0`` and one Fourier sum, both on the
+    GPU.  Not fused into a single call like the default RK45 branch."""
     from ..utils import mgf_pricer as mgfp
     from .logsv.affine_expansion import compute_logsv_a_mgf_grid, get_expansion_n
     if vol_scaler is None:
@@ -251,9 +250,10 @@ def _logsv_chain_pricer_analytic(params, ttms, forwards, discfactors, strikes_tt
     vt = getattr(variable_type, "value", variable_type)
     for ttm, forward, strikes, types, discfactor in zip(ttms, forwards, strikes_ttms, optiontypes_ttms, discfactors):
         a_t0, log_mgf = compute_logsv_a_mgf_grid(ttm=ttm - ttm0, phi_grid=phi_grid, psi_grid=psi_grid, theta_grid=theta_grid, a_t0=a_t0,
-                                                 is_analytic=True, expansion_order=expansion_order, is_spot_measure=is_spot_measure,
-                                                 sigma0=params.sigma0, theta=params.theta, kappa1=params.kappa1, kappa2=params.kappa2,
-                                                 beta=params.beta, volvol=params.volvol, variable_type=variable_type)
+                                                 is_analytic=is_analytic, is_stiff_solver=is_stiff_solver, expansion_order=expansion_order,
+                                                 is_spot_measure=is_spot_measure, sigma0=params.sigma0, theta=params.theta, kappa1=params.kappa1,
+                                                 kappa2=params.kappa2, beta=params.beta, volvol=params.volvol, variable_type=variable_type,
+                                                 vol_backbone_eta=params.get_vol_backbone_eta(tau=ttm))
         if vt == 1:
             prices.append(mgfp.vanilla_slice_pricer_with_mgf_grid(log_mgf_grid=log_mgf, phi_grid=phi_grid, forward=forward, strikes=strikes,
                                                                   optiontypes=types, discfactor=discfactor, is_spot_measure=is_spot_measure))

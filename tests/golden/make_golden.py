@@ -674,6 +674,45 @@ def analytic_branch() -> None:
     np.savez_compressed(os.path.join(OUT, "logsv_analytic_branch.npz"), ttms=ttms, strikes=K, discfactors=np.array([0.999, 0.99, 0.98]), **out)
 
 
+def bdf_branch() -> None:
+    """stiff branch (is_stiff_solver=True): solve_ivp(method='BDF', jac=func_rhs_jac) per grid point (pricers/logsv/affine_expansion.py:229-303).
+    a_t1 / log_mgf on every 8th grid point for three parameter sets (two carried maturities), full-grid chain prices for one."""
+    _import_reference()
+    from stochvolmodels.pricers import logsv_pricer as lp
+    from stochvolmodels.pricers.logsv import affine_expansion as afe
+    from stochvolmodels.pricers.logsv.logsv_params import LogSvParams
+    from stochvolmodels.utils import mgf_pricer as mgfp
+    from stochvolmodels.utils.config import VariableType
+    K = np.array([0.8, 0.9, 1.0, 1.1, 1.2])
+    T = np.array(['P', 'P', 'C', 'C', 'C'])
+    cases = {"quick_second": (LogSvParams(1.0, 1.0, 5.0, 5.0, 0.2, 2.0), afe.ExpansionOrder.SECOND, True, 1.0),
+             "btc_second_inverse_eta": (LogSvParams(0.8376, 1.0413, 3.1844, 3.058, 0.1514, 1.8458), afe.ExpansionOrder.SECOND, False, 0.9),
+             "mild_first": (LogSvParams(0.2, 0.2, 1.0, 2.5, -0.3, 0.4), afe.ExpansionOrder.FIRST, True, 1.0)}
+    ttms = np.array([0.1, 0.35])
+    out = {}
+    for name, (p, order, spot, eta) in cases.items():
+        vol_scaler = lp.set_vol_scaler(sigma0=p.sigma0, ttm=np.min(ttms))
+        phi, psi, theta_grid = mgfp.get_transform_var_grid(variable_type=VariableType.LOG_RETURN, is_spot_measure=spot, vol_scaler=vol_scaler)
+        phi, psi, theta_grid = phi[::8], psi[::8], theta_grid[::8]
+        a_t0 = np.zeros((phi.shape[0], afe.get_expansion_n(order)), dtype=np.complex128)
+        t0 = 0.0
+        for m, ttm in enumerate(ttms):
+            a_t0, lm = afe.compute_logsv_a_mgf_grid(ttm=ttm - t0, phi_grid=phi, psi_grid=psi, theta_grid=theta_grid, a_t0=a_t0, is_stiff_solver=True,
+                                                    expansion_order=order, is_spot_measure=spot, sigma0=p.sigma0, theta=p.theta, kappa1=p.kappa1,
+                                                    kappa2=p.kappa2, beta=p.beta, volvol=p.volvol, vol_backbone_eta=eta)
+            out[f"{name}_a_{m}"], out[f"{name}_lm_{m}"] = a_t0.copy(), lm.copy()
+            t0 = ttm
+        out[f"{name}_params"] = np.array([p.sigma0, p.theta, p.kappa1, p.kappa2, p.beta, p.volvol, order.value, float(spot), eta])
+        out[f"{name}_phi"] = phi
+        print(name, "done", np.abs(a_t0).max())
+    p = cases["quick_second"][0]
+    prices = lp.logsv_chain_pricer(params=p, ttms=ttms, forwards=np.ones(2), discfactors=np.array([0.999, 0.99]), strikes_ttms=(K, K),
+                                   optiontypes_ttms=(T, T), is_stiff_solver=True)
+    out["quick_second_prices"] = np.array([np.asarray(x) for x in prices])
+    print("prices", out["quick_second_prices"])
+    np.savez_compressed(os.path.join(OUT, "logsv_bdf_branch.npz"), ttms=ttms, strikes=K, types=T, discfactors=np.array([0.999, 0.99]), **out)
+
+
 def hawkes_mc() -> None:
     """Hawkes jump-diffusion MC (pricers/hawkes_jd_pricer.py:644-779).  The reference draws from numpy's GLOBAL legacy generator, so each case
     is run after np.random.seed(seed): RandomState(seed) re-draws the same arrays in the same order (W0 normal, U_P, U_M uniform(1e-16, 1),
@@ -727,6 +766,9 @@ def _chain(ttms, fw, df, K, T):
 
 
 if __name__ == "__main__":
+    if "--only-bdf" in sys.argv:
+        bdf_branch()
+        sys.exit(0)
     if "--only-analytic" in sys.argv:
         analytic_branch()
         sys.exit(0)

@@ -273,3 +273,42 @@ def test_semi_analytic_branch_diverges_where_the_reference_does(cuda_lib):
         assert first_bad > 40
         np.testing.assert_allclose(lm[: first_bad - 8], ref[: first_bad - 8], rtol=1e-6, atol=1e-8)      # converged region
         assert not np.all(np.isfinite(lm[first_bad:]))                                                     # diverged tail
+
+
+@pytest.mark.parametrize("name", ["quick_second", "btc_second_inverse_eta", "mild_first"])
+def test_bdf_branch_vs_reference_golden(cuda_lib, name):
+    """is_stiff_solver=True: the CUDA clone of SciPy's BDF control law against the reference's own outputs (solve_ivp(method='BDF',
+    jac=func_rhs_jac) per grid point, affine_expansion.py:229-303): a_t1 and log_mgf on 125 grid points carried over two maturities.
+    Reproducing the reference here means reproducing its accepted steps, order changes and Newton iteration counts."""
+    from stochvolmodels_b200.pricers.logsv.affine_expansion import ExpansionOrder, compute_logsv_a_mgf_grid
+    g = load_golden("logsv_bdf_branch.npz")
+    sigma0, theta, k1, k2, beta, vv, order, spot, eta = g[f"{name}_params"]
+    phi = g[f"{name}_phi"]
+    a = np.zeros((phi.shape[0], 3 if int(order) == 1 else 5), dtype=np.complex128)
+    t0 = 0.0
+    for m, ttm in enumerate(g["ttms"]):
+        a, lm = compute_logsv_a_mgf_grid(ttm - t0, phi, np.zeros_like(phi), np.zeros_like(phi), sigma0, theta, k1, k2, beta, vv, a_t0=a,
+                                         is_stiff_solver=True, expansion_order=ExpansionOrder(int(order)), is_spot_measure=bool(spot),
+                                         vol_backbone_eta=eta)
+        np.testing.assert_allclose(a, g[f"{name}_a_{m}"], rtol=1e-10, atol=1e-11)
+        np.testing.assert_allclose(lm, g[f"{name}_lm_{m}"], rtol=1e-10, atol=1e-11)
+        t0 = ttm
+
+
+def test_bdf_branch_chain_prices_and_oracle(cuda_lib):
+    """full-grid chain prices on the stiff branch vs the reference (quickstart parameters), and the kernel vs SciPy's BDF itself on a grid
+    the goldens do not cover (Q_VAR transform variable psi != 0, inverse measure)"""
+    from oracle import mgf as omgf
+    from stochvolmodels_b200 import LogSvParams, LogSVPricer, OptionChain
+    from stochvolmodels_b200.pricers.logsv.affine_expansion import ExpansionOrder, solve_a_ode_grid
+    g = load_golden("logsv_bdf_branch.npz")
+    chain = OptionChain(ttms=g["ttms"], forwards=np.ones(2), strikes_ttms=[g["strikes"]] * 2, optiontypes_ttms=[g["types"]] * 2, discfactors=g["discfactors"])
+    prices = LogSVPricer().price_chain(chain, LogSvParams(1.0, 1.0, 5.0, 5.0, 0.2, 2.0), is_stiff_solver=True)
+    for m in range(2):
+        np.testing.assert_allclose(prices[m], g["quick_second_prices"][m], rtol=1e-10, atol=0)
+    psi = -0.5 + 1j * np.linspace(0, 400, 60)
+    phi = np.ones_like(psi)
+    a_gpu = solve_a_ode_grid(phi, psi, 0.3, 1.0413, 3.1844, 3.058, 0.1514, 1.8458, is_spot_measure=False, is_stiff_solver=True,
+                             expansion_order=ExpansionOrder.SECOND, vol_backbone_eta=1.1)
+    a_ref = omgf.logsv_bdf_a_grid(0.3, phi, psi, np.zeros((60, 5), complex), 1.0413, 3.1844, 3.058, 0.1514, 1.8458, False, 2, 1.1)
+    np.testing.assert_allclose(a_gpu, a_ref, rtol=1e-10, atol=1e-11)

@@ -179,21 +179,6 @@ def test_model_pricer_mc_pdf_and_default_interfaces():
             call(PriceOnly())
 
 
-def test_bdf_branch_refuses_loudly():
-    """``is_stiff_solver=True`` (SciPy BDF, affine_expansion.py:229-303) is NOT rebuilt on the GPU (its parity bar is SciPy's
-    variable-order Newton/LU control law).  The drop-in contract for an unsupported branch is a loud NotImplementedError naming the branch --
-    never a silent switch to RK45.  (``is_analytic=True`` takes precedence over it, as in the reference, and IS implemented.)"""
-    from stochvolmodels_b200 import LogSvParams, LogSVPricer, OptionChain
-    from stochvolmodels_b200.pricers.logsv.affine_expansion import compute_logsv_a_mgf_grid, solve_a_ode_grid
-    chain = OptionChain(ttms=np.array([0.25]), forwards=np.ones(1), strikes_ttms=[np.array([1.0])], optiontypes_ttms=[np.array(["C"])])
-    p = LogSvParams(1.0, 1.0, 5.0, 5.0, 0.2, 2.0)
-    with pytest.raises(NotImplementedError, match="BDF"):
-        LogSVPricer().price_chain(chain, p, is_stiff_solver=True)
-    with pytest.raises(NotImplementedError, match="BDF"):
-        compute_logsv_a_mgf_grid(0.25, np.array([-0.5 + 1j]), np.zeros(1, complex), np.zeros(1, complex), 1.0, 1.0, 5.0, 5.0, 0.2, 2.0, is_stiff_solver=True)
-    with pytest.raises(NotImplementedError, match="BDF"):
-        solve_a_ode_grid(np.array([-0.5 + 1j]), np.zeros(1, complex), 0.25, 1.0, 5.0, 5.0, 0.2, 2.0, is_stiff_solver=True)
-
 def test_rough_random_grid_replays_seed_and_has_aligned_shapes():
     """port of the reference's tests/test_rough_logsv_characterization.py::test_rough_random_grid_replays_seed_and_has_aligned_shapes:
     local RandomState (global numpy state untouched), Z0 / Z1 of the LAST maturity's length, grids end at the maturities"""

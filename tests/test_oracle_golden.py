@@ -333,3 +333,17 @@ def test_semi_analytic_branch_oracle_vs_reference_golden(name):
         a = mgf.logsv_analytic_a_grid(ttm - t0, phi, np.zeros_like(phi), a, theta, k1, k2, beta, vv, bool(spot), int(order))
         np.testing.assert_allclose(a, g[f"{name}_a_{m}"], rtol=1e-8, atol=1e-10)
         t0 = ttm
+
+
+@pytest.mark.parametrize("name", ["quick_second", "btc_second_inverse_eta", "mild_first"])
+def test_bdf_branch_oracle_vs_reference_golden(name):
+    """SciPy BDF on the restated right-hand side / Jacobian == the reference's is_stiff_solver=True branch (every 8th grid point, 2 maturities)"""
+    g = load_golden("logsv_bdf_branch.npz")
+    sigma0, theta, k1, k2, beta, vv, order, spot, eta = g[f"{name}_params"]
+    phi = g[f"{name}_phi"]
+    a = np.zeros((phi.shape[0], mgf.expansion_n(int(order))), dtype=np.complex128)
+    t0 = 0.0
+    for m, ttm in enumerate(g["ttms"]):
+        a = mgf.logsv_bdf_a_grid(ttm - t0, phi, np.zeros_like(phi), a, theta, k1, k2, beta, vv, bool(spot), int(order), eta)
+        np.testing.assert_allclose(a, g[f"{name}_a_{m}"], rtol=1e-11, atol=1e-12)
+        t0 = ttm
