@@ -234,6 +234,25 @@ def test_logsv_mc_btc_chain_within_3se_of_reference_mc(cuda_lib):
         assert np.all(np.abs(prices[m] - fourier[f"prices_{m}"]) / chain.forwards[m] < 1e-3)
 
 
+def test_logsv_mc_btc_chain_strict_3se_at_1e8_paths(cuda_lib):
+    """the north_star's bar without softening: every one of the 49 strikes of the BTC chain within 3 (combined) MC standard errors of the
+    reference's own Numba MC (golden: 16e6 reference paths), with the GPU estimate at 1e8 paths (its own error is 2.5x smaller than the
+    reference sample's), default arithmetic (fp64 state, float draws) and the all-fp64 mode; abs error vs the reference Fourier prices <= 1e-3 F"""
+    from stochvolmodels_b200 import LOGSV_BTC_PARAMS, LogSVPricer, get_btc_test_chain_data
+    ref = load_golden("refmc_logsv_btc.npz")
+    fourier = load_golden("logsv_fourier_btc.npz")
+    chain = get_btc_test_chain_data()
+    for gauss, seed in (("fp32", 10), ("fp64", 11)):
+        prices, ses = LogSVPricer().model_mc_price_chain(chain, LOGSV_BTC_PARAMS, nb_path=100_000_000, nb_steps=252, seed=seed, gauss=gauss)
+        zmax = 0.0
+        for m in range(4):
+            z = np.abs(prices[m] - ref[f"prices_{m}"]) / np.sqrt(ses[m] ** 2 + ref[f"stderr_{m}"] ** 2)
+            zmax = max(zmax, float(z.max()))
+            assert np.all(z < 3.0), (gauss, m, z)
+            assert np.all(np.abs(prices[m] - fourier[f"prices_{m}"]) / chain.forwards[m] < 1e-3)
+        print(f"BTC chain, 1e8 GPU paths ({gauss} draws) vs 16e6-path reference Numba MC: max z over 49 strikes = {zmax:.2f}")
+
+
 def test_heston_mc_within_3se_of_reference_mc(cuda_lib):
     from stochvolmodels_b200 import HestonParams, HestonPricer, OptionChain
     ref = load_golden("refmc_heston_g4.npz")
