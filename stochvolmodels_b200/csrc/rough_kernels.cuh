@@ -12,7 +12,7 @@
 //
 // One thread = one path for the whole grid; the n factor values live in registers (template on n), the only HBM traffic is the two
 // normals per step in the fixed-random mode (16 B / path-step, coalesced [S][P] rows) or nothing at all in the Philox mode, plus the
-// terminal state.  ~110 fp64 instructions per step at n = 3 (8 RK4 slopes, one exp, one sqrt, one division): fp64-pipe bound.
+// terminal state.  ~160 fp64 instructions per step at n = 3 (8 RK4 slopes, one table exponential, one MUFU-seeded sqrt): fp64-pipe bound.
 // The reference kernels are compiled fastmath=True, so its own evaluation order is not fixed; agreement with it is 1e-12.
 #pragma once
 
@@ -110,7 +110,8 @@ struct RoughPath {
     for (int i = 0; i < N; ++i) u[i] = v[i];
     drift(c, u, c.half_h);
     const double yw = wsum_of(c, u);
-    const double Yh = yw * exp(fma(c.vv, z0 * c.sqrt_h, -0.5 * c.vv * c.vv * c.h));     // diffus_sde_solve_f64 (:240-243)
+    const double ex = clamp_log(fma(c.vv, z0 * c.sqrt_h, -0.5 * c.vv * c.vv * c.h));
+    const double Yh = yw * exp_table(ex);                                               // diffus_sde_solve_f64 (:240-243)
     const double Q = c.w_inv * (Yh - yw);
 #pragma unroll
     for (int i = 0; i < N; ++i) u[i] += Q;
@@ -130,7 +131,7 @@ struct RoughPath {
                           (c.kappa1 - c.kappa2 * c.theta) * (0.5 * vw + 0.5 * volw_h) + c.kappa2 * (0.5 * sq_vw + 0.5 * sq_vhw)) *
                          c.h;
     const double term2 = 0.5 * c.h * sq_vw + 0.5 * c.h * sq_vhw;
-    ls = ls - 0.5 * term2 + c.rho * term1 + c.rho_comp * sqrt(term2) * z1;
+    ls = ls - 0.5 * term2 + c.rho * term1 + c.rho_comp * (term2 > 0.0 ? fast_sqrt(term2) : sqrt(term2)) * z1;
     y = fma(0.5 * c.h, sq_vw + sq_vhw, y);
 #pragma unroll
     for (int i = 0; i < N; ++i) v[i] = u[i];
@@ -145,6 +146,7 @@ __global__ void __launch_bounds__(kThreads) rough_logsv_kernel(double* __restric
                                                               double* __restrict__ qv_out, const double* __restrict__ Z0,
                                                               const double* __restrict__ Z1, int S, long long P, RoughConsts c,
                                                               unsigned long long seed, unsigned long long path_offset) {
+  exp_table_init();
   if constexpr (GAUSS != kGaussF32) gauss64_table_init();
   const long long stride = (long long)gridDim.x * kThreads;
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < P; i += stride) {
