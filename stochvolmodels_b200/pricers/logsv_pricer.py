@@ -197,7 +197,18 @@ class LogSVPricer(ModelPricer):
     def simulate_terminal_values(self, params: LogSvParams, ttm: float = 1.0, nb_path: int = 100000, is_spot_measure: bool = True,
                                  **kwargs) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
         """terminal (log-return, vol, quadratic variance), float64[nb_path] each; 360 steps/year and eta = 1 as in the
-        reference (:600-610)."""
+        reference (:600-610).  Under an initialised ``torch.distributed`` world (one process per GPU) every rank simulates and returns ITS
+        contiguous shard of the ``nb_path`` global path ids (no collective; concatenating the shards in rank order gives the
+        single-GPU arrays); ``path_range=(offset, n_local)`` selects a shard explicitly, ``distributed=False`` switches sharding off."""
+        path_range = kwargs.get("path_range")
+        if path_range is None and _use_distributed(kwargs):
+            import torch.distributed as dist
+            from ..multi_gpu import shard_paths
+            n_local, offset = shard_paths(nb_path, dist.get_world_size(), dist.get_rank())
+            path_range = (offset, n_local)
+        if path_range is not None:
+            return _terminal_values_shard(params, ttm, int(path_range[0]), int(path_range[1]), is_spot_measure,
+                                          kwargs.get("nb_steps_per_year", 360), kwargs.get("seed"), kwargs.get("gauss", "fp32"))
         return simulate_logsv_x_vol_terminal(ttm=ttm, x0=np.zeros(1), sigma0=params.sigma0 * np.ones(1), qvar0=np.zeros(1),
                                              theta=params.theta, kappa1=params.kappa1, kappa2=params.kappa2, beta=params.beta,
                                              volvol=params.volvol, nb_path=nb_path, is_spot_measure=is_spot_measure,
@@ -326,6 +337,20 @@ def simulate_vol_paths(ttm: float, v0: float, theta: float, kappa1: float, kappa
     seed = engine.fresh_seed() if seed is None else int(seed)
     return engine.logsv_vol_paths(engine.logsv_params_c(v0, theta, kappa1, kappa2, beta, volvol), ttm, nb_path, nb_steps_per_year,
                                   is_spot_measure, seed, brownians)
+
+
+def _terminal_values_shard(params, ttm, offset, n_local, is_spot_measure, nb_steps_per_year, seed, gauss):
+    """paths [offset, offset + n_local) of the global Philox stream on the current CUDA device (device-level slice call, state copied back)"""
+    from ..multi_gpu import CudaMcEngine
+    if seed is None:
+        raise ValueError("a sharded simulation needs an explicit seed (every rank must draw from the same stream)")
+    if n_local == 0:
+        return np.zeros(0), np.zeros(0), np.zeros(0)
+    eng = CudaMcEngine("logsv", _params_c(params), n_local, offset, engine.mc_flags("fp64", gauss), 1)
+    nb_steps, dt, _ = set_time_grid(ttm, nb_steps_per_year)
+    eng.simulate_slice(0, True, nb_steps, dt, 1.0, is_spot_measure, 1.0, int(seed))
+    host = eng.state.cpu().numpy()
+    return host[0].copy(), host[1].copy(), host[2].copy()
 
 
 def simulate_logsv_x_vol_terminal(ttm: float, x0: np.ndarray, sigma0: np.ndarray, qvar0: np.ndarray, theta: float, kappa1: float,

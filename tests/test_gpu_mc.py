@@ -498,3 +498,16 @@ def test_host_level_calls_follow_set_stream(cuda_lib):
     np.testing.assert_array_equal(on_stream[0][0], base[0][0])
     np.testing.assert_array_equal(on_stream[1][0], base[1][0])
     np.testing.assert_array_equal(fourier2[0], fourier[0])
+
+
+def test_terminal_values_shards_concatenate_to_the_single_gpu_arrays(cuda_lib):
+    """simulate_terminal_values beyond one GPU returns per-GPU shards of the global path ids; three uneven shards == one run"""
+    from stochvolmodels_b200 import LogSvParams, LogSVPricer
+    from stochvolmodels_b200.multi_gpu import shard_paths
+    p, N = LogSvParams(*Q), 100_003
+    full = LogSVPricer().simulate_terminal_values(p, ttm=0.3, nb_path=N, seed=21, distributed=False)
+    parts = [LogSVPricer().simulate_terminal_values(p, ttm=0.3, nb_path=N, seed=21, path_range=shard_paths(N, 3, r)[::-1]) for r in range(3)]
+    for k in range(3):
+        np.testing.assert_array_equal(np.concatenate([part[k] for part in parts]), full[k])
+    with pytest.raises(ValueError):
+        LogSVPricer().simulate_terminal_values(p, ttm=0.3, nb_path=N, path_range=(0, 10))
