@@ -23,6 +23,7 @@
 #include "../../include/b200sv.h"
 #include "common.cuh"
 #include "black.cuh"
+#include "fastmath64.cuh"
 
 extern "C" void b200sv_internal_count_launch(void);
 
@@ -174,6 +175,11 @@ __constant__ double c_A[6][5] = {{0, 0, 0, 0, 0},
                                  {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656}};   // Dormand-Prince A (rk.py:542-549)
 constexpr double kRtol = 1e-3, kAtol = 1e-6;   // solve_ivp defaults, affine_expansion.py:300-301 passes none
 
+// Step-size control arithmetic of the RK45 clone (error scale, RMS norm): MUFU-seeded reciprocal / square root with Newton refinement
+// (<= 2 ulp, fastmath64.cuh) instead of the IEEE sequences with their slow-path branches -- these sit on the dependent chain of every
+// step attempt.  Moduli below 1e-145 count as 0 (the scale is atol + |a| rtol with atol = 1e-6: identical result).
+__device__ __forceinline__ double ctrl_sqrt(double s) { return s < 1e-290 ? 0.0 : fast_sqrt(s); }
+__device__ __forceinline__ double ctrl_rcp(double x) { return fast_div(1.0, x); }     // x >= atol
 // RMS norm of v / scale over complex moduli (scipy/integrate/_ivp/common.py:63-65); inv_scale = 1 / scale.
 template <int N>
 __device__ __forceinline__ double rms_scaled(const cd (&v)[N], const double (&inv_scale)[N]) {
@@ -183,10 +189,23 @@ __device__ __forceinline__ double rms_scaled(const cd (&v)[N], const double (&in
     const double re = v[k].re * inv_scale[k], im = v[k].im * inv_scale[k];
     s += re * re + im * im;
   }
-  return sqrt(s) * rsqrt((double)N);
+  return ctrl_sqrt(s) * (N == 5 ? 0.44721359549995793 : 0.57735026918962576);   // / sqrt(N)
 }
-__device__ __forceinline__ double cmod(cd a) { return sqrt(a.re * a.re + a.im * a.im); }   // |a| (no overflow risk for these magnitudes)
-__device__ __forceinline__ double pow_m02(double e) { return exp(-0.2 * log(e)); }           // e^(-1/5), e > 0
+__device__ __forceinline__ double cmod(cd a) { return ctrl_sqrt(a.re * a.re + a.im * a.im); }   // |a| (no overflow risk for these magnitudes)
+// e^(-1/5), e > 0, for the step-size factor 0.9 e^(-1/5) clipped to [0.2, 10]: SFU single-precision seed + two Newton steps on x^-5 = e
+// (x <- x (1.2 - 0.2 e x^5), quadratic: 1e-6 -> 3e-12 -> 1 ulp) instead of exp(-0.2 log e).  Outside [1e-30, 1e30] the clipped factor
+// does not depend on e, so e is clamped for the float seed; NaN propagates (fmax(0.2, NaN) = 0.2 as before).
+__device__ __forceinline__ double pow_m02(double e) {
+  const double ec = e != e ? e : fmin(fmax(e, 1e-30), 1e30);
+  double x = (double)__powf((float)ec, -0.2f);
+  const double c = 0.2 * ec;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const double x2 = x * x;
+    x = x * fma(-c, x2 * x2 * x, 1.2);
+  }
+  return x;
+}
 
 // Stage storage of one thread in shared memory: K[stage][component][thread] (16-byte elements, conflict-free across threads).
 // Keeping the 7 x N complex stages out of the register file leaves ptxas room to schedule the independent products of the
@@ -217,7 +236,7 @@ __device__ int rk45(cd (&y)[N], double T, const LogsvModel& m, const CoefView<TP
   double h_abs;
   {
 #pragma unroll
-    for (int k = 0; k < N; ++k) inv_scale[k] = 1.0 / (kAtol + cmod(y[k]) * kRtol);
+    for (int k = 0; k < N; ++k) inv_scale[k] = ctrl_rcp(kAtol + cmod(y[k]) * kRtol);
     const double d0 = rms_scaled<N>(y, inv_scale), d1 = rms_scaled<N>(f, inv_scale);
     double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
     h0 = fmin(h0, T);
@@ -236,12 +255,16 @@ __device__ int rk45(cd (&y)[N], double T, const LogsvModel& m, const CoefView<TP
   int status = 0;
 #pragma unroll
   for (int k = 0; k < N; ++k) K.at(0, k) = f[k];
-  for (int guard = 0; t < T && guard < 100000; ++guard) {
-    const double min_step = 10.0 * (__longlong_as_double(__double_as_longlong(t) + 1) - t);   // 10*|nextafter(t, inf) - t|, t >= 0
-    if (h_abs < min_step) h_abs = min_step;           // max_step = inf
-    bool rejected = false;
-    for (;;) {
-      if (h_abs < min_step) {
+  // ONE loop over step ATTEMPTS (SciPy nests "while not accepted" inside the step loop): a lane that rejects an attempt simply goes round
+  // again with the lanes that accepted theirs, so a warp runs max-over-lanes of the TOTAL attempts instead of the sum over steps of
+  // the per-step maximum.  Same arithmetic per point.
+  bool rejected = false;
+  for (int guard = 0; t < T && guard < 400000; ++guard) {
+    {
+      const double min_step = 10.0 * (__longlong_as_double(__double_as_longlong(t) + 1) - t);   // 10*|nextafter(t, inf) - t|, t >= 0
+      if (!rejected) {
+        if (h_abs < min_step) h_abs = min_step;       // first attempt of a step (max_step = inf)
+      } else if (h_abs < min_step) {
         status = 1;
         break;
       }
@@ -254,6 +277,7 @@ __device__ int rk45(cd (&y)[N], double T, const LogsvModel& m, const CoefView<TP
       for (int s = 1; s < 6; ++s) {            // rk_step (scipy/integrate/_ivp/rk.py:60-64): dy = (sum_j K_j a_sj) * h
         // not unrolled on purpose: the fully unrolled body (5 inlined right-hand sides) is ~70 KB of SASS and the single resident
         // warp per SM then stalls on instruction fetch; stages >= s still hold zeros / stale finite values and get coefficient 0
+        // (skipping them with a warp-uniform trip count was measured: no gain, more spills)
 #pragma unroll
         for (int k = 0; k < N; ++k) {
           cd acc = K.at(0, k) * c_A[s][0];
@@ -278,29 +302,28 @@ __device__ int rk45(cd (&y)[N], double T, const LogsvModel& m, const CoefView<TP
       cd err[N];
 #pragma unroll
       for (int k = 0; k < N; ++k) {
-        inv_scale[k] = 1.0 / (kAtol + fmax(cmod(y[k]), cmod(yn[k])) * kRtol);
+        inv_scale[k] = ctrl_rcp(kAtol + fmax(cmod(y[k]), cmod(yn[k])) * kRtol);
         cd acc = K.at(0, k) * E[0];
 #pragma unroll
         for (int jj = 2; jj < 6; ++jj) acc = acc + K.at(jj, k) * E[jj];      // E[1] = 0
         err[k] = (acc + kn[k] * E[6]) * h;
       }
       const double en = rms_scaled<N>(err, inv_scale);
-      if (en < 1.0) {
-        double factor = en == 0.0 ? 10.0 : fmin(10.0, 0.9 * pow_m02(en));
-        if (rejected) factor = fmin(1.0, factor);
-        h_abs *= factor;
+      const bool accepted = en < 1.0;
+      const double pf = en == 0.0 ? 10.0 : 0.9 * pow_m02(en);
+      double factor = fmin(10.0, pf);
+      if (rejected) factor = fmin(1.0, factor);
+      h_abs *= accepted ? factor : fmax(0.2, pf);
+      if (accepted) {
         t = t_new;
 #pragma unroll
         for (int k = 0; k < N; ++k) {
           y[k] = yn[k];
           K.at(0, k) = kn[k];     // FSAL: K[6] of this step is K[0] of the next
         }
-        break;
       }
-      h_abs *= fmax(0.2, 0.9 * pow_m02(en));
-      rejected = true;
+      rejected = !accepted;
     }
-    if (status) break;
   }
   if (nfev_out) *nfev_out = nfev;
   return status;
@@ -318,13 +341,22 @@ template <int N, int TPB>
 __global__ void __launch_bounds__(TPB) logsv_mgf_kernel(const cd* __restrict__ phi, const cd* __restrict__ psi, int P, int M,
                                  const ChainSpec* __restrict__ spec, const cd* __restrict__ a_in, cd* __restrict__ a_out,
                                  cd* __restrict__ log_mgf, double y, int* __restrict__ status, int* __restrict__ nfev,
-                                 const double* __restrict__ yb = nullptr, int phi_stride = 0) {
+                                 const double* __restrict__ yb = nullptr, int phi_stride = 0, int set_major_B = 0) {
   __shared__ cd stage_smem[6 * N * TPB];
   __shared__ cd coef_smem[14 * TPB];
-  const int p = blockIdx.x * TPB + threadIdx.x;
+  // Batches (set_major_B = B > 1): the parameter set is the FASTEST thread index, so the lanes of a warp integrate the same grid point
+  // for 32 neighbouring sets -- the sets of a calibration batch are perturbations of one another and take (nearly) the same adaptive
+  // steps, whereas neighbouring grid points of one set do not (24 of 32 lanes active with the point-major mapping, r01 profile).
+  int p = blockIdx.x * TPB + threadIdx.x;
+  size_t b = blockIdx.y;
+  if (set_major_B > 1) {
+    const long long t = (long long)blockIdx.x * TPB + threadIdx.x;
+    if (t >= (long long)set_major_B * P) return;
+    b = (size_t)(t % set_major_B);
+    p = (int)(t / set_major_B);
+  }
   if (p >= P) return;
   if (gridDim.y > 1 || yb) {
-    const size_t b = blockIdx.y;
     spec += b * M;
     phi += b * (size_t)phi_stride;
     a_out += b * (size_t)M * P * N;
@@ -482,7 +514,7 @@ __global__ void __launch_bounds__(32 * kLaneWarpsPerBlock, 1) logsv_mgf_lanes_ke
     double s = 0.0;
 #pragma unroll
     for (int c = 0; c < N; ++c) s += Nn[c];
-    return sqrt(s) * rsqrt((double)N);
+    return ctrl_sqrt(s) * (N == 5 ? 0.44721359549995793 : 0.57735026918962576);   // / sqrt(N)
   };
   // f_k at the point's vector whose k-th entry is `mine_k`
   auto eval = [&](const LaneRow<N>& row, cd mine_k) -> cd {
@@ -500,7 +532,7 @@ __global__ void __launch_bounds__(32 * kLaneWarpsPerBlock, 1) logsv_mgf_lanes_ke
     K[0] = eval(row, yk);
     double h_abs;
     {   // select_initial_step (scipy/integrate/_ivp/common.py:109-134)
-      const double inv_scale = 1.0 / (kAtol + cmod(yk) * kRtol);
+      const double inv_scale = ctrl_rcp(kAtol + cmod(yk) * kRtol);
       const double d0 = point_norm(yk, inv_scale), d1 = point_norm(K[0], inv_scale);
       double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
       h0 = fmin(h0, T);
@@ -540,7 +572,7 @@ __global__ void __launch_bounds__(32 * kLaneWarpsPerBlock, 1) logsv_mgf_lanes_ke
       for (int jj = 2; jj < 6; ++jj) acc = acc + K[jj] * B[jj];
       const cd yn = yk + h * acc;
       K[6] = eval(row, yn);
-      const double inv_scale = 1.0 / (kAtol + fmax(cmod(yk), cmod(yn)) * kRtol);
+      const double inv_scale = ctrl_rcp(kAtol + fmax(cmod(yk), cmod(yn)) * kRtol);
       cd e = K[0] * E[0];
 #pragma unroll
       for (int jj = 2; jj < 6; ++jj) e = e + K[jj] * E[jj];
@@ -749,13 +781,18 @@ static void launch_logsv_mgf(int tpb, int nb, cudaStream_t st, const cd* phi, co
                                                                                                       status, yb, phi_stride);
     return;
   }
-  const dim3 grid(nb, B);
+  static const bool set_major = [] {
+    const char* e = getenv("B200SV_MGF_SET_MAJOR");      // A/B timing switch (tools/bench_calibration.py); default on
+    return !e || atoi(e) != 0;
+  }();
+  const int smB = (B > 1 && set_major) ? B : 0;
+  const dim3 grid = smB ? dim3((unsigned)(((long long)B * P + tpb - 1) / tpb), 1) : dim3(nb, B);
   switch (tpb) {
-    case 4: logsv_mgf_kernel<N, 4><<<grid, 4, 0, st>>>(phi, psi, P, M, spec, a_in, a_out, lm, y, status, nullptr, yb, phi_stride); break;
-    case 8: logsv_mgf_kernel<N, 8><<<grid, 8, 0, st>>>(phi, psi, P, M, spec, a_in, a_out, lm, y, status, nullptr, yb, phi_stride); break;
-    case 16: logsv_mgf_kernel<N, 16><<<grid, 16, 0, st>>>(phi, psi, P, M, spec, a_in, a_out, lm, y, status, nullptr, yb, phi_stride); break;
-    case 32: logsv_mgf_kernel<N, 32><<<grid, 32, 0, st>>>(phi, psi, P, M, spec, a_in, a_out, lm, y, status, nullptr, yb, phi_stride); break;
-    default: logsv_mgf_kernel<N, 64><<<grid, 64, 0, st>>>(phi, psi, P, M, spec, a_in, a_out, lm, y, status, nullptr, yb, phi_stride); break;
+    case 4: logsv_mgf_kernel<N, 4><<<grid, 4, 0, st>>>(phi, psi, P, M, spec, a_in, a_out, lm, y, status, nullptr, yb, phi_stride, smB); break;
+    case 8: logsv_mgf_kernel<N, 8><<<grid, 8, 0, st>>>(phi, psi, P, M, spec, a_in, a_out, lm, y, status, nullptr, yb, phi_stride, smB); break;
+    case 16: logsv_mgf_kernel<N, 16><<<grid, 16, 0, st>>>(phi, psi, P, M, spec, a_in, a_out, lm, y, status, nullptr, yb, phi_stride, smB); break;
+    case 32: logsv_mgf_kernel<N, 32><<<grid, 32, 0, st>>>(phi, psi, P, M, spec, a_in, a_out, lm, y, status, nullptr, yb, phi_stride, smB); break;
+    default: logsv_mgf_kernel<N, 64><<<grid, 64, 0, st>>>(phi, psi, P, M, spec, a_in, a_out, lm, y, status, nullptr, yb, phi_stride, smB); break;
   }
 }
 
