@@ -253,6 +253,22 @@ int b200sv_hawkesjd_device_draws(uint64_t seed, long long path0, long long n, in
 /* moments_out[2] (device) = (sum over non-NaN paths of forward*exp(x), count) for externally produced float64 states. */
 int b200sv_dev_spot_moments(const double* x, long long n, double forward, double* moments_out, void* stream);
 
+/* Sharded slices of the two neighbouring Monte Carlo routes (SURVEY.md 8e applied to 8f #4), same contract as b200sv_dev_logsv_slice:
+ * local paths [0, n_local) with global ids from path_offset, float64 device state, moments_out[2] (device) = this rank's re-centring
+ * moments, published to the peer-memory mailbox when p2p_ctx is given; b200sv_dev_payoff_sums / _finalize complete the maturity.
+ *  - Hawkes jump-diffusion (replaces the loop body of hawkes_jd_pricer.py:687-715): state (x, lambda_p, lambda_m); init != 0 starts from
+ *    (0, params->lambda_p, params->lambda_m).
+ *  - rough LogSV (logsv_pricer.py:1199-1216 -> rough_logsv/split_simulation.py:466): EVERY maturity restarts at t = 0 on its own grid
+ *    (nsteps steps of size h) and draws from slice 0 of the path's stream; vol_factors is [n_factors][n_local] (may be NULL),
+ *    weights / nodes are HOST arrays of n_factors entries.  The payoff uses (log_spot, qvar) and, as in the reference on this route,
+ *    total_paths = 1 in b200sv_dev_payoff_finalize (its "standard errors" carry no 1/sqrt(N)). */
+int b200sv_dev_hawkesjd_slice(double* x, double* lambda_p, double* lambda_m, long long n_local, long long path_offset, int init,
+                              const b200sv_hawkes_params* params, int nsteps, double dt, int slice_index, double forward, uint64_t seed,
+                              int flags, double* moments_out, void* p2p_ctx, void* stream);
+int b200sv_dev_rough_logsv_slice(double* log_spot, double* vol_factors, double* qvar, long long n_local, long long path_offset,
+                                 const b200sv_logsv_params* params, int n_factors, const double* weights, const double* nodes, int nsteps,
+                                 double h, double forward, uint64_t seed, int flags, double* moments_out, void* p2p_ctx, void* stream);
+
 /* test hook: out[2i] = exp(L[i]), out[2i+1] = exp(-L[i]) through the stepper's shared-polynomial exp pair (host arrays). */
 int b200sv_debug_exp_pair(const double* L, long long n, double* out);
 /* same for the variant the stepper runs on its table-unit state: out[2i] = exp(Ls[i] ln2/256), out[2i+1] = exp(-Ls[i] ln2/256) */

@@ -94,6 +94,10 @@ SIGNATURES = {
                                     c_int, c_int, c_void_p],
     "b200sv_dev_heston_step_fixed": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_double, _hp, c_void_p],
     "b200sv_dev_spot_moments": [c_void_p, c_longlong, c_double, c_void_p, c_void_p],
+    "b200sv_dev_hawkesjd_slice": [c_void_p, c_void_p, c_void_p, c_longlong, c_longlong, c_int, _kp, c_int, c_double, c_int, c_double, c_uint64,
+                                  c_int, c_void_p, c_void_p, c_void_p],
+    "b200sv_dev_rough_logsv_slice": [c_void_p, c_void_p, c_void_p, c_longlong, c_longlong, _lp, c_int, _dp, _dp, c_int, c_double, c_double,
+                                     c_uint64, c_int, c_void_p, c_void_p, c_void_p],
     "b200sv_debug_exp_pair": [_dp, c_longlong, _dp],
     "b200sv_debug_exp_pair_scaled": [_dp, c_longlong, _dp],
     "b200sv_logsv_price_chain": [_lp, c_int, _dp, _dp, _dp, _dp, _ip, _dp, _i8p, c_int, c_int, c_int, c_double, c_int, _dp, _dp, _dp],

@@ -189,7 +189,7 @@ __global__ void hawkes_device_draws_kernel(unsigned long long seed, unsigned lon
 
 static int launch_hawkes_slice(double* x, double* lp, double* lm, long long n, long long path_offset, int init, const b200sv_hawkes_params& p,
                                int nsteps, double dt, int slice_index, double forward, uint64_t seed, int flags, double* moments_out,
-                               cudaStream_t st) {
+                               cudaStream_t st, P2pCtx* p2p = nullptr) {
   const int g = gauss_mode(flags);
   if (g != kGaussF32 && g != kGaussF64) return fail(-1, "invalid argument: gauss flags");
   HawkesSliceArgs a;
@@ -216,7 +216,7 @@ static int launch_hawkes_slice(double* x, double* lp, double* lm, long long n, l
   else
     hawkes_slice_kernel<kGaussF32><<<grid.blocks, grid.threads, 0, st>>>(a, c);
   if (int rc = check_launch("hawkes_slice_kernel")) return rc;
-  reduce_partials_kernel<<<1, 64, 0, st>>>(partials, grid.blocks, 2, 2, moments_out, P2pPublish{});
+  reduce_partials_kernel<<<1, 64, 0, st>>>(partials, grid.blocks, 2, 2, moments_out, make_publish(p2p, st));   // exchange #1 (producer)
   if (int rc = check_launch("reduce_partials_kernel")) return rc;
   B200SV_CUDA(cudaFreeAsync(partials, st));
   return 0;

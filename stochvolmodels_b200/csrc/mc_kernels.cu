@@ -1599,19 +1599,50 @@ int b200sv_dev_heston_step_fixed(double* x, double* var, double* qvar, const dou
   return check_launch("heston_step_fixed_kernel");
 }
 
-int b200sv_dev_spot_moments(const double* x, long long n, double forward, double* moments_out, void* stream) {
-  B200SV_REQUIRE(x && moments_out && n >= 1, "null pointer / n");
-  cudaStream_t st = (cudaStream_t)stream;
+static int spot_moments_impl(const double* x, long long n, double forward, double* moments_out, cudaStream_t st, P2pCtx* p2p) {
   Grid g = persistent_grid(spot_moments_kernel, kThreads, n);
   double* partials = nullptr;
   ensure_pool_threshold();
   B200SV_CUDA(cudaMallocAsync(&partials, sizeof(double) * 2 * g.blocks, st));
   spot_moments_kernel<<<g.blocks, g.threads, 0, st>>>(x, n, forward, partials);
   if (int rc = check_launch("spot_moments_kernel")) return rc;
-  reduce_partials_kernel<<<1, 64, 0, st>>>(partials, g.blocks, 2, 2, moments_out, P2pPublish{});
+  reduce_partials_kernel<<<1, 64, 0, st>>>(partials, g.blocks, 2, 2, moments_out, make_publish(p2p, st));
   if (int rc = check_launch("reduce_partials_kernel")) return rc;
   B200SV_CUDA(cudaFreeAsync(partials, st));
   return 0;
+}
+
+int b200sv_dev_spot_moments(const double* x, long long n, double forward, double* moments_out, void* stream) {
+  B200SV_REQUIRE(x && moments_out && n >= 1, "null pointer / n");
+  return spot_moments_impl(x, n, forward, moments_out, (cudaStream_t)stream, nullptr);
+}
+
+// sharded rough-LogSV / Hawkes slices (multi_gpu.py): the steppers of rough_kernels.cuh / hawkes_kernels.cuh on a contiguous range of GLOBAL
+// path ids, followed by this rank's re-centring moments (published to the peer-memory mailbox when `p2p` is given) -- the same two
+// exchanges per maturity as the LogSV chain
+int b200sv_dev_hawkesjd_slice(double* x, double* lambda_p, double* lambda_m, long long n_local, long long path_offset, int init,
+                              const b200sv_hawkes_params* params, int nsteps, double dt, int slice_index, double forward, uint64_t seed,
+                              int flags, double* moments_out, void* p2p, void* stream) {
+  B200SV_REQUIRE(x && lambda_p && lambda_m && params && moments_out, "null pointer");
+  B200SV_REQUIRE(n_local >= 1 && nsteps >= 1 && dt > 0.0 && slice_index >= 0, "n_local, nsteps, dt must be positive");
+  B200SV_REQUIRE(!(flags & B200SV_STATE_F32), "the Hawkes route is float64 only");
+  return launch_hawkes_slice(x, lambda_p, lambda_m, n_local, path_offset, init, *params, nsteps, dt, slice_index, forward, seed, flags,
+                             moments_out, (cudaStream_t)stream, (P2pCtx*)p2p);
+}
+
+int b200sv_dev_rough_logsv_slice(double* log_spot, double* vol_factors, double* qvar, long long n_local, long long path_offset,
+                                 const b200sv_logsv_params* params, int n_factors, const double* weights, const double* nodes, int nsteps,
+                                 double h, double forward, uint64_t seed, int flags, double* moments_out, void* p2p, void* stream) {
+  B200SV_REQUIRE(log_spot && qvar && params && weights && nodes && moments_out, "null pointer");
+  B200SV_REQUIRE(n_local >= 1 && nsteps >= 1 && h > 0.0, "n_local, nsteps, h must be positive");
+  B200SV_REQUIRE(n_factors >= 1 && n_factors <= kMaxRoughFactors, "1 <= n_factors <= 8");
+  B200SV_REQUIRE(!(flags & B200SV_STATE_F32), "the rough-vol route is float64 only");
+  const int g = gauss_mode(flags);
+  B200SV_REQUIRE(g == kGaussF32 || g == kGaussF64, "gauss flags");
+  const RoughConsts c = make_rough_consts(*params, n_factors, weights, nodes, h);
+  if (int rc = launch_rough(n_factors, log_spot, vol_factors, qvar, nullptr, nullptr, nsteps, n_local, c, seed, path_offset, g, (cudaStream_t)stream))
+    return rc;
+  return spot_moments_impl(log_spot, n_local, forward, moments_out, (cudaStream_t)stream, (P2pCtx*)p2p);
 }
 
 // ---- host-level fixed-random steppers and payoffs ------------------------------------------------------------------------

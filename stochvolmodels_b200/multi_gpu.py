@@ -111,18 +111,20 @@ def release_engines():
     _ENGINE_CACHE.clear()
 
 
-def _cached_engine(model, params_c, n_local, offset, flags, Jmax, scheme):
+def _cached_engine(model, params_c, n_local, offset, flags, Jmax, scheme, factors=None):
     import torch
     if os.environ.get("B200SV_ENGINE_CACHE", "1") == "0":
-        return CudaMcEngine(model, params_c, n_local, offset, flags, Jmax, scheme=scheme)
-    key = (model, int(n_local), int(offset), int(flags), int(scheme), torch.cuda.current_device())
+        return CudaMcEngine(model, params_c, n_local, offset, flags, Jmax, scheme=scheme, factors=factors)
+    rows = 0 if factors is None else len(factors[0])
+    key = (model, int(n_local), int(offset), int(flags), int(scheme), rows, torch.cuda.current_device())
     eng = _ENGINE_CACHE.get(key)
     if eng is None or eng.cap < max(Jmax, 1):
         for k in [k for k in _ENGINE_CACHE if k[0] == model and k[-1] == key[-1]]:    # one resident shard per model and device
             del _ENGINE_CACHE[k]
-        eng = CudaMcEngine(model, params_c, n_local, offset, flags, Jmax, scheme=scheme)
+        eng = CudaMcEngine(model, params_c, n_local, offset, flags, Jmax, scheme=scheme, factors=factors)
         _ENGINE_CACHE[key] = eng
     eng.params_c = params_c
+    eng.set_factors(factors)
     return eng
 
 
@@ -138,10 +140,17 @@ def release_p2p():
 class CudaMcEngine:
     """Device-resident MC state + kernel launches on the current CUDA device (used for N>=1 ranks and by bench.py)."""
 
-    def __init__(self, model: str, params_c, n_local: int, path_offset: int, flags: int, max_strikes: int, device=None, scheme: int = 0):
+    MODELS = ("logsv", "heston", "hawkes", "rough")
+
+    def __init__(self, model: str, params_c, n_local: int, path_offset: int, flags: int, max_strikes: int, device=None, scheme: int = 0,
+                 factors=None):
+        """``model``: 'logsv' / 'heston' (state x, vol or var, qvar), 'hawkes' (state x, lambda_p, lambda_m; x stands in for qvar in the
+        payoff, hawkes_jd_pricer.py:703) or 'rough' (state log_spot, n vol factors, qvar; ``factors`` = (weights, nodes) of the kernel)."""
         import torch
         if not torch.cuda.is_available():
             raise RuntimeError("CudaMcEngine needs a CUDA device; stochvolmodels_b200 has no CPU fallback")
+        if model not in self.MODELS:
+            raise ValueError(f"unknown model {model!r}")
         C.load_library()
         self.torch = torch
         self.model = model
@@ -149,8 +158,14 @@ class CudaMcEngine:
         self.params_c = params_c
         self.n_local, self.path_offset, self.flags = int(n_local), int(path_offset), int(flags)
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        if model in ("hawkes", "rough") and (flags & C.STATE_F32):
+            raise ValueError("the Hawkes and rough-vol routes are float64 only")
         sdtype = torch.float32 if (flags & C.STATE_F32) else torch.float64
-        self.state = torch.empty((3, max(self.n_local, 1)), dtype=sdtype, device=self.device)
+        self.factors = None
+        self.set_factors(factors)
+        rows = 3 if model != "rough" else len(self.factors[0]) + 2
+        self.qrow = {"hawkes": 0, "rough": rows - 1}.get(model, 2)          # the state row the Q_VAR payoff reads
+        self.state = torch.empty((rows, max(self.n_local, 1)), dtype=sdtype, device=self.device)
         self.moments = torch.zeros(2, dtype=torch.float64, device=self.device)
         self.sums = torch.zeros(3 * max(max_strikes, 1), dtype=torch.float64, device=self.device)
         self.out = torch.zeros(2 * max(max_strikes, 1), dtype=torch.float64, device=self.device)
@@ -158,6 +173,19 @@ class CudaMcEngine:
         self.p2p = None          # libb200sv P2P mailbox context (void*), see enable_p2p
         self._chain_dev = None   # per-chain buffers reused across calls (see chain_buffers)
         self._chain_host = None
+
+    def set_factors(self, factors):
+        """(weights, nodes) of the rough kernel's Markovian lift (host float64 arrays of equal length <= 8); None for the other models."""
+        if self.model != "rough":
+            return
+        if factors is None:
+            raise ValueError("the rough-vol engine needs factors=(weights, nodes)")
+        w, x = (np.ascontiguousarray(a, dtype=np.float64).ravel() for a in factors)
+        if w.shape != x.shape or not 1 <= w.shape[0] <= 8:
+            raise ValueError("weights and nodes must have the same length, 1..8")
+        if self.factors is not None and self.factors[0].shape != w.shape:
+            raise ValueError("the number of factors of a cached engine cannot change")
+        self.factors = (w, x)
 
     def chain_buffers(self, Jtot: int):
         """(strikes f64[J], types i8[J], out f64[2, J]) on the device + a pinned host mirror of `out`, grown on demand and reused."""
@@ -200,6 +228,14 @@ class CudaMcEngine:
             C.call("b200sv_dev_logsv_slice", x, v, q, self.n_local, self.path_offset, int(init), byref(self.params_c), float(eta),
                    int(bool(is_spot)), int(nsteps), float(dt), int(m), float(forward), int(seed) & 0xFFFFFFFFFFFFFFFF, self.flags,
                    c_void_p(self.moments.data_ptr()), self.p2p, self._stream())
+        elif self.model == "hawkes":
+            C.call("b200sv_dev_hawkesjd_slice", x, v, q, self.n_local, self.path_offset, int(init), byref(self.params_c), int(nsteps), float(dt),
+                   int(m), float(forward), int(seed) & 0xFFFFFFFFFFFFFFFF, self.flags, c_void_p(self.moments.data_ptr()), self.p2p, self._stream())
+        elif self.model == "rough":       # every maturity restarts at t = 0 on its own grid: `init` and `m` do not enter
+            w, nodes = self.factors
+            C.call("b200sv_dev_rough_logsv_slice", x, c_void_p(self.state[1].data_ptr()), c_void_p(self.state[self.qrow].data_ptr()), self.n_local,
+                   self.path_offset, byref(self.params_c), int(w.shape[0]), C.dptr(w), C.dptr(nodes), int(nsteps), float(dt), float(forward),
+                   int(seed) & 0xFFFFFFFFFFFFFFFF, self.flags, c_void_p(self.moments.data_ptr()), self.p2p, self._stream())
         else:
             C.call("b200sv_dev_heston_slice", x, v, q, self.n_local, self.path_offset, int(init), byref(self.params_c), int(nsteps),
                    float(dt), int(m), float(forward), int(seed) & 0xFFFFFFFFFFFFFFFF, self.flags, self.scheme,
@@ -214,7 +250,7 @@ class CudaMcEngine:
             if self.p2p is not None:
                 C.call("b200sv_dev_p2p_publish", self.p2p, c_void_p(sums.data_ptr()), 3 * J, self._stream())
             return sums
-        C.call("b200sv_dev_payoff_sums", c_void_p(self.state[0].data_ptr()), c_void_p(self.state[2].data_ptr()), self.n_local,
+        C.call("b200sv_dev_payoff_sums", c_void_p(self.state[0].data_ptr()), c_void_p(self.state[self.qrow].data_ptr()), self.n_local,
                self.flags, float(ttm), float(forward), c_void_p(strikes_dev.data_ptr()), c_void_p(types_dev.data_ptr()), int(J),
                int(variable_type), int(kinds), c_void_p(self.moments.data_ptr()), c_void_p(sums.data_ptr()), self.p2p, self._stream())
         return sums
@@ -231,12 +267,15 @@ class CudaMcEngine:
 def mc_chain_distributed(model: str, params_c, ttms, forwards, discfactors, etas, strikes_ttms, optiontypes_ttms, nb_path: int,
                          nb_steps_per_year: int, is_spot_measure: bool, variable_type: int, seed: int, flags: int,
                          group=None, engine_factory: Optional[Callable] = None, return_engine: bool = False, scheme: int = 0,
-                         exchange: Optional[str] = None):
+                         exchange: Optional[str] = None, grid: Optional[Sequence[Tuple[int, float]]] = None, factors=None,
+                         se_paths: Optional[int] = None):
     """Chain MC with ``nb_path`` TOTAL paths split over the ranks of ``group`` (default: the world; works unsharded when
     torch.distributed is not initialised).  Every rank returns the same (prices, std errors) lists.
 
     Mirrors the slice loop of logsv_mc_chain_pricer / heston_mc_chain_pricer (pricers/logsv_pricer.py:840-865,
-    pricers/heston_pricer.py:304-329): the terminal state of slice m seeds slice m+1.
+    pricers/heston_pricer.py:304-329): the terminal state of slice m seeds slice m+1.  ``model`` 'hawkes' (hawkes_jd_pricer.py:687-715,
+    ``nb_steps_per_year`` = 1800 there) and 'rough' (logsv_pricer.py:1199-1216: ``grid`` = the (nb_steps, h) of every maturity's OWN grid
+    from t = 0, ``factors`` = (weights, nodes), ``se_paths`` = 1 for that route's un-normalised standard errors) shard the same way.
     """
     import torch
     import torch.distributed as dist
@@ -250,7 +289,7 @@ def mc_chain_distributed(model: str, params_c, ttms, forwards, discfactors, etas
     sizes = np.diff(offsets)
     Jmax = int(sizes.max()) if M else 0
     if engine_factory is None:
-        eng = _cached_engine(model, params_c, n_local, offset, flags, Jmax, scheme)
+        eng = _cached_engine(model, params_c, n_local, offset, flags, Jmax, scheme, factors)
     else:
         eng = engine_factory(model, params_c, n_local, offset, flags, Jmax, scheme=scheme) if scheme else engine_factory(model, params_c, n_local, offset, flags, Jmax)
     # exchange mode: P2P mailbox on CUDA engines of a multi-rank group unless the caller asks for the collective
@@ -293,7 +332,10 @@ def mc_chain_distributed(model: str, params_c, ttms, forwards, discfactors, etas
     results = []
     t0 = 0.0
     for m in range(M):
-        nsteps, dt, _ = set_time_grid(ttms[m] - t0, nb_steps_per_year)
+        if grid is None:
+            nsteps, dt, _ = set_time_grid(ttms[m] - t0, nb_steps_per_year)
+        else:
+            nsteps, dt = int(grid[m][0]), float(grid[m][1])
         t0 = ttms[m]
         moments = eng.simulate_slice(m, m == 0, nsteps, dt, float(etas[m]), is_spot_measure, float(forwards[m]), seed)
         if world > 1 and not use_p2p:
@@ -308,10 +350,10 @@ def mc_chain_distributed(model: str, params_c, ttms, forwards, discfactors, etas
         if world > 1 and not use_p2p:
             dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)                 # exchange (2): 24*J bytes
         if chain_out:
-            eng.finalize(sums, J, float(discfactors[m]), int(nb_path), out_dev[0, jo: jo + J], out_dev[1, jo: jo + J])
+            eng.finalize(sums, J, float(discfactors[m]), int(nb_path if se_paths is None else se_paths), out_dev[0, jo: jo + J], out_dev[1, jo: jo + J])
             results.append((jo, J))
         else:
-            prices, stds = eng.finalize(sums, J, float(discfactors[m]), int(nb_path))
+            prices, stds = eng.finalize(sums, J, float(discfactors[m]), int(nb_path if se_paths is None else se_paths))
             results.append((prices.clone(), stds.clone()))
     prices_out: List[np.ndarray] = []
     stds_out: List[np.ndarray] = []

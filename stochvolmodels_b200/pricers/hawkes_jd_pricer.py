@@ -95,7 +95,8 @@ class HawkesJDPricer(ModelPricer):
         return hawkesjd_mc_chain_pricer(ttms=option_chain.ttms, forwards=option_chain.forwards, discfactors=option_chain.discfactors,
                                         strikes_ttms=option_chain.strikes_ttms, optiontypes_ttms=option_chain.optiontypes_ttms, nb_path=nb_path,
                                         seed=kwargs.get("seed"), gauss=kwargs.get("gauss", "fp32"),
-                                        variable_type=kwargs.get("variable_type", VariableType.LOG_RETURN), **d)
+                                        variable_type=kwargs.get("variable_type", VariableType.LOG_RETURN),
+                                        distributed=kwargs.get("distributed", True), exchange=kwargs.get("exchange"), **d)
 
     @timer
     def simulate_terminal_values(self, params: HawkesJDParams, ttm: float = 1.0, nb_path: int = 100000, is_spot_measure: bool = True, **kwargs
@@ -109,16 +110,24 @@ def hawkesjd_mc_chain_pricer(ttms, forwards, discfactors, strikes_ttms, optionty
                              shift_p: float, mean_p: float, shift_m: float, mean_m: float, theta_p: float, kappa_p: float, beta1_p: float,
                              beta2_p: float, theta_m: float, kappa_m: float, beta1_m: float, beta2_m: float, risk_premia_gamma: float = 0.0,
                              nb_path: int = 100000, variable_type: VariableType = VariableType.LOG_RETURN, seed: Optional[int] = None,
-                             gauss: str = "fp32") -> Tuple[List[np.ndarray], List[np.ndarray]]:
+                             gauss: str = "fp32", distributed: bool = True, exchange: Optional[str] = None
+                             ) -> Tuple[List[np.ndarray], List[np.ndarray]]:
     """chain prices and standard errors by simulating the jump-diffusion (reference :644-715): the terminal (x, lambda_p, lambda_m) of slice m
-    seeds slice m+1; payoffs are forward-recentred on x (utils/mc_payoffs.py)."""
+    seeds slice m+1; payoffs are forward-recentred on x (utils/mc_payoffs.py).  Under an initialised torch.distributed world ``nb_path`` is
+    the TOTAL path count, sharded over the ranks by global path id (the LogSV chain's two exchanges per maturity, multi_gpu.py)."""
     vt = engine.variable_code(variable_type)
-    M, ttms, forwards, discfactors, offsets, strikes, types = engine._chain_arrays(ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms)
     pc = _params_c(**locals())
+    seed = engine.fresh_seed() if seed is None else int(seed)
+    from .logsv_pricer import _use_distributed
+    if _use_distributed({"distributed": distributed}):
+        from ..multi_gpu import mc_chain_distributed
+        C.encode_types(np.concatenate([np.asarray(t) for t in optiontypes_ttms]))
+        return mc_chain_distributed("hawkes", pc, ttms, forwards, discfactors, None, strikes_ttms, optiontypes_ttms, nb_path, STEPS_PER_YEAR,
+                                    True, vt, seed, engine.mc_flags("fp64", gauss), exchange=exchange)
+    M, ttms, forwards, discfactors, offsets, strikes, types = engine._chain_arrays(ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms)
     prices, stds = np.empty(strikes.shape[0]), np.empty(strikes.shape[0])
     C.call("b200sv_hawkesjd_mc_chain", byref(pc), M, C.dptr(ttms), C.dptr(forwards), C.dptr(discfactors), C.iptr(offsets), C.dptr(strikes),
-           C.i8ptr(types), int(nb_path), vt, (engine.fresh_seed() if seed is None else int(seed)) & 0xFFFFFFFFFFFFFFFF, engine.mc_flags("fp64", gauss),
-           C.dptr(prices), C.dptr(stds))
+           C.i8ptr(types), int(nb_path), vt, seed & 0xFFFFFFFFFFFFFFFF, engine.mc_flags("fp64", gauss), C.dptr(prices), C.dptr(stds))
     return C.split_chain(prices, offsets), C.split_chain(stds, offsets)
 
 

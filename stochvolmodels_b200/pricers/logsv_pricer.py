@@ -171,7 +171,8 @@ class LogSVPricer(ModelPricer):
                                                              theta=params.theta, kappa1=params.kappa1, kappa2=params.kappa2, beta=params.beta,
                                                              orthog_vol=params.volvol, weights=params.weights, nodes=params.nodes,
                                                              timegrids=grid_ttms, variable_type=variable_type, nb_path=nb_path,
-                                                             seed=kwargs["seed"], gauss=gauss or "fp32")
+                                                             seed=kwargs["seed"], gauss=gauss or "fp32",
+                                                             distributed=kwargs.get("distributed", True), exchange=kwargs.get("exchange"))
         vol_backbone_etas = params.get_vol_backbone_etas(ttms=option_chain.ttms)
         return logsv_mc_chain_pricer(v0=params.sigma0, theta=params.theta, kappa1=params.kappa1, kappa2=params.kappa2,
                                      beta=params.beta, volvol=params.volvol, vol_backbone_etas=vol_backbone_etas,
@@ -444,11 +445,13 @@ def rough_logsv_mc_chain_pricer_fixed_randoms(ttms, forwards, discfactors, strik
                                               kappa1: float, kappa2: float, beta: float, orthog_vol: float, weights: np.ndarray, nodes: np.ndarray,
                                               timegrids: List[np.ndarray], variable_type: VariableType = VariableType.LOG_RETURN,
                                               debug: bool = False, nb_path: Optional[int] = None, seed: Optional[int] = None, gauss: str = "fp32",
-                                              return_states: bool = False):
+                                              return_states: bool = False, distributed: bool = True, exchange: Optional[str] = None):
     """rough-LogSV chain prices by the multi-factor Strang-splitting scheme with caller-supplied normals (reference :1164-1232 ->
     rough_logsv/split_simulation.py:466): every maturity restarts at t = 0 on ITS grid and uses the first rows of ``Z0`` / ``Z1``.
     Returned "standard errors" are, as in the reference on this route, discfactor * nanstd(payoff) without the 1/sqrt(nb_path).
-    ``Z0 = Z1 = None`` (extra): the normals are drawn in-kernel (Philox stream keyed by ``seed``; ``nb_path`` required)."""
+    ``Z0 = Z1 = None`` (extra): the normals are drawn in-kernel (Philox stream keyed by ``seed``; ``nb_path`` required); in that mode, under
+    an initialised torch.distributed world, ``nb_path`` is the TOTAL path count sharded over the ranks by global path id (multi_gpu.py).
+    Caller-supplied normals are not sharded: every rank prices all of them."""
     weights, nodes = np.asarray(weights, dtype=np.float64), np.asarray(nodes, dtype=np.float64)
     assert weights.shape == nodes.shape and weights.ndim == 1            # :1188
     if Z0 is not None:
@@ -458,6 +461,13 @@ def rough_logsv_mc_chain_pricer_fixed_randoms(ttms, forwards, discfactors, strik
     nsteps = [int(np.asarray(g).size) - 1 for g in timegrids]
     hs = [float(np.asarray(g)[1] - np.asarray(g)[0]) for g in timegrids]             # split_simulation.py:346
     params_c = engine.logsv_params_c(sigma0, theta, kappa1, kappa2, beta, orthog_vol)
+    if Z0 is None and not (return_states or debug) and _use_distributed({"distributed": distributed}):
+        from ..multi_gpu import mc_chain_distributed
+        C.encode_types(np.concatenate([np.asarray(t) for t in optiontypes_ttms]))
+        return mc_chain_distributed("rough", params_c, ttms, forwards, discfactors, None, strikes_ttms, optiontypes_ttms, nb_path, 0, True,
+                                    engine.variable_code(variable_type), engine.fresh_seed() if seed is None else int(seed),
+                                    engine.mc_flags("fp64", gauss), exchange=exchange, grid=list(zip(nsteps, hs)), factors=(weights, nodes),
+                                    se_paths=1)
     prices, stds, _, states, offsets = engine.rough_logsv_mc_chain([params_c], weights, nodes, ttms, forwards, discfactors, strikes_ttms,
                                                                    optiontypes_ttms, nb_path, nsteps, hs, Z0, Z1, variable_type,
                                                                    engine.fresh_seed() if seed is None else int(seed),

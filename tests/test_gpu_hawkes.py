@@ -89,3 +89,42 @@ def test_chain_prices_within_mc_error_of_reference_mc_golden(cuda_lib):
     assert abs(m1.mean() - np.exp(params.mu * 0.1)) < 4 * m1.std() / np.sqrt(x.size)
     with pytest.raises(NotImplementedError):
         HawkesJDPricer().price_chain(chain, params)
+
+
+def test_sharded_driver_equals_the_host_level_chain(cuda_lib):
+    """multi_gpu.mc_chain_distributed('hawkes', ...) (device-level b200sv_dev_hawkesjd_slice + the LogSV chain's payoff / finalize calls) on
+    one rank == b200sv_hawkesjd_mc_chain; two half-shards run back to back on this GPU hold the same terminal states as the unsharded run
+    (global path ids), which is what makes the prices independent of the number of GPUs."""
+    import torch
+    from ctypes import byref, c_void_p
+    from stochvolmodels_b200 import HawkesJDParams, HawkesJDPricer, engine, get_btc_test_chain_data
+    from stochvolmodels_b200 import _capi as C
+    from stochvolmodels_b200.multi_gpu import CudaMcEngine, mc_chain_distributed
+    from stochvolmodels_b200.pricers.hawkes_jd_pricer import STEPS_PER_YEAR, _params_c
+    chain = get_btc_test_chain_data()
+    params = HawkesJDParams()
+    d = params.to_dict()
+    d.pop("risk_premia_gamma", None)
+    pc = _params_c(**d)
+    N, seed = 200_003, 17
+    flags = engine.mc_flags("fp64", "fp32")
+    p_h, e_h = HawkesJDPricer().model_mc_price_chain(chain, params, nb_path=N, seed=seed)
+    p_d, e_d = mc_chain_distributed("hawkes", pc, chain.ttms, chain.forwards, chain.discfactors, None, chain.strikes_ttms, chain.optiontypes_ttms,
+                                    N, STEPS_PER_YEAR, True, C.LOG_RETURN, seed, flags)
+    for m in range(len(p_h)):
+        np.testing.assert_allclose(p_d[m], p_h[m], rtol=1e-12)
+        np.testing.assert_allclose(e_d[m], e_h[m], rtol=1e-10)
+    # two shards vs one engine over all paths: identical terminal states
+    from stochvolmodels_b200.utils.funcs import set_time_grid
+    S, dt, _ = set_time_grid(float(chain.ttms[0]), STEPS_PER_YEAR)
+    whole = CudaMcEngine("hawkes", pc, N, 0, flags, 4)
+    whole.simulate_slice(0, True, S, dt, 1.0, True, float(chain.forwards[0]), seed)
+    n0 = N // 2
+    parts = [CudaMcEngine("hawkes", pc, n0, 0, flags, 4), CudaMcEngine("hawkes", pc, N - n0, n0, flags, 4)]
+    moments = 0.0
+    for e in parts:
+        moments = moments + e.simulate_slice(0, True, S, dt, 1.0, True, float(chain.forwards[0]), seed).cpu().numpy()
+    torch.cuda.synchronize()
+    joined = torch.cat([e.state for e in parts], dim=1)
+    assert torch.equal(joined, whole.state)
+    np.testing.assert_allclose(moments, whole.moments.cpu().numpy(), rtol=1e-12)

@@ -209,3 +209,39 @@ def test_rough_and_hawkes_edge_cases(cuda_lib):
                                         strikes_ttms=[np.zeros(0), np.array([0.95, 1.05])],
                                         optiontypes_ttms=[np.zeros(0, dtype="U2"), np.array(["P", "C"])], nb_path=P, seed=4, **d)
         assert p[0].shape == (0,) and p[1].shape == (2,) and np.all(np.isfinite(p[1])) and np.all(e[1] >= 0.0)
+
+
+def test_rough_sharded_driver_equals_the_host_level_chain(cuda_lib):
+    """multi_gpu.mc_chain_distributed('rough', ...) (device-level b200sv_dev_rough_logsv_slice, every maturity from t = 0 on its own grid,
+    se_paths = 1) on one rank == b200sv_rough_logsv_mc_chain with in-kernel draws; two half-shards hold the unsharded terminal states."""
+    import torch
+    from stochvolmodels_b200 import LogSvParams, LogSVPricer, engine, get_btc_test_chain_data
+    from stochvolmodels_b200 import _capi as C
+    from stochvolmodels_b200.multi_gpu import CudaMcEngine, mc_chain_distributed
+    from stochvolmodels_b200.utils.funcs import set_time_grid
+    chain = get_btc_test_chain_data()
+    p = LogSvParams(sigma0=0.8, theta=1.0, kappa1=2.2, kappa2=2.2, beta=0.2, volvol=1.6, H=0.3, weights=np.array([0.7, 0.5, 0.3]),
+                    nodes=np.array([0.05, 1.5, 20.0]))
+    N, npy, seed = 100_003, 360, 9
+    for gauss in ("fp32", "fp64"):
+        flags = engine.mc_flags("fp64", gauss)
+        p_h, e_h = LogSVPricer().model_mc_price_chain(chain, p, nb_path=N, nb_steps=npy, use_rough_mc=True, seed=seed, gauss=gauss)
+        grids = [set_time_grid(float(t), npy)[2] for t in chain.ttms]
+        grid = [(g.size - 1, float(g[1] - g[0])) for g in grids]        # split_simulation.py:346
+        pc = engine.logsv_params_c(p.sigma0, p.theta, p.kappa1, p.kappa2, p.beta, p.volvol)
+        p_d, e_d = mc_chain_distributed("rough", pc, chain.ttms, chain.forwards, chain.discfactors, None, chain.strikes_ttms, chain.optiontypes_ttms,
+                                        N, 0, True, C.LOG_RETURN, seed, flags, grid=grid, factors=(p.weights, p.nodes), se_paths=1)
+        for m in range(len(p_h)):
+            np.testing.assert_allclose(p_d[m], p_h[m], rtol=1e-12)
+            np.testing.assert_allclose(e_d[m], e_h[m], rtol=1e-10)
+    whole = CudaMcEngine("rough", pc, N, 0, flags, 4, factors=(p.weights, p.nodes))
+    whole.simulate_slice(0, True, grid[1][0], grid[1][1], 1.0, True, float(chain.forwards[1]), seed)
+    n0 = N // 3
+    parts = [CudaMcEngine("rough", pc, n0, 0, flags, 4, factors=(p.weights, p.nodes)),
+             CudaMcEngine("rough", pc, N - n0, n0, flags, 4, factors=(p.weights, p.nodes))]
+    for e in parts:
+        e.simulate_slice(0, True, grid[1][0], grid[1][1], 1.0, True, float(chain.forwards[1]), seed)
+    torch.cuda.synchronize()
+    assert whole.state.shape[0] == 5 and torch.equal(torch.cat([e.state for e in parts], dim=1), whole.state)
+    with pytest.raises(ValueError):
+        CudaMcEngine("rough", pc, 10, 0, flags, 4)                       # factors are required

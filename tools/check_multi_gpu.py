@@ -30,6 +30,22 @@ for name, pricer, params, kw in (("logsv", LogSVPricer(), LOGSV_BTC_PARAMS, dict
         print(f"{name}: world={world} N={N} max rel diff prices {rel_p:.2e} stderr {rel_e:.2e}", flush=True)
     ok &= rel_p < 1e-12 and rel_e < 1e-10
 
+# the two neighbouring Monte Carlo routes shard the same way (Philox draws; global path ids): Hawkes jump-diffusion and rough LogSV
+from stochvolmodels_b200 import HawkesJDParams, HawkesJDPricer, LogSvParams
+rough_params = LogSvParams(sigma0=0.8, theta=1.0, kappa1=2.2, kappa2=2.2, beta=0.2, volvol=1.6, H=0.3, weights=np.array([0.7, 0.5, 0.3]),
+                           nodes=np.array([0.05, 1.5, 20.0]))
+for name, pricer, params, kw, n in (("hawkes", HawkesJDPricer(), HawkesJDParams(), {}, 400_001),
+                                    ("rough", LogSVPricer(), rough_params, dict(use_rough_mc=True, gauss="fp32", nb_steps=360), 400_001)):
+    p_d, e_d = pricer.model_mc_price_chain(chain, params, nb_path=n, seed=321, **kw)
+    p_c, e_c = pricer.model_mc_price_chain(chain, params, nb_path=n, seed=321, exchange="collective", **kw)
+    p_s, e_s = pricer.model_mc_price_chain(chain, params, nb_path=n, seed=321, distributed=False, **kw)
+    rel_p = max(np.max(np.abs(a / b - 1)) for a, b in zip(p_d, p_s))
+    rel_c = max(np.max(np.abs(a / b - 1)) for a, b in zip(p_c, p_s))
+    rel_e = max(np.max(np.abs(a / b - 1)) for a, b in zip(e_d, e_s))
+    if rank == 0:
+        print(f"{name}: world={world} N={n} max rel diff vs single GPU: prices p2p {rel_p:.2e} NCCL {rel_c:.2e} stderr {rel_e:.2e}", flush=True)
+    ok &= rel_p < 1e-12 and rel_c < 1e-12 and rel_e < 1e-10
+
 # ragged corner cases through the peer-memory exchange: a maturity without strikes, fewer paths than ranks (ranks without paths),
 # IC/IP payoffs (general payoff kernel), and many repeated calls (epoch wrap of the double-buffered mailbox)
 from stochvolmodels_b200.pricers.logsv_pricer import logsv_mc_chain_pricer
