@@ -9,8 +9,9 @@ from stochvolmodels_b200 import _capi as C
 
 
 class OracleEngine:
-    def __init__(self, model, params_c, n_local, path_offset, flags, max_strikes, device=None):
+    def __init__(self, model, params_c, n_local, path_offset, flags, max_strikes, device=None, factors=None):
         self.model, self.p, self.n_local, self.path_offset, self.flags = model, params_c, n_local, path_offset, flags
+        self.factors = factors
         self.x = self.v = self.q = None
         self.moments = torch.zeros(2, dtype=torch.float64)
         self.device = torch.device("cpu")
@@ -21,8 +22,18 @@ class OracleEngine:
     def simulate_slice(self, m, init, nsteps, dt, eta, is_spot, forward, seed):
         n = self.n_local
         ids = self.path_offset + np.arange(n, dtype=np.uint64)
-        Z0, Z1 = mc.device_normals(seed, ids, m, nsteps, "f64" if self.flags & C.GAUSS_F64 else "f32")
-        if self.model == "logsv":
+        Z0, Z1 = mc.device_normals(seed, ids, 0 if self.model == "rough" else m, nsteps, "f64" if self.flags & C.GAUSS_F64 else "f32")
+        if self.model == "rough":          # every maturity from t = 0 on its own grid, slice 0 of the path's stream (oracle/rough.py)
+            from oracle import rough
+            w, nodes = (np.asarray(a, dtype=float) for a in self.factors)
+            volvol = np.sqrt(self.p.beta ** 2 + self.p.volvol ** 2)
+            v0 = np.repeat(np.full((w.size,), self.p.sigma0 / w.sum())[:, None], n, axis=1)
+            grid = dt * np.arange(nsteps + 1)
+            grid[1] = dt                      # h = grid[1] - grid[0] exactly
+            ls, _, qv = rough.log_spot_full_combined(np.repeat(nodes[:, None], n, axis=1), np.repeat(w[:, None], n, axis=1), v0, self.p.theta,
+                                                     self.p.kappa1, self.p.kappa2, 0.0, v0.copy(), self.p.beta / volvol, volvol, grid, Z0, Z1)
+            self.x, self.q = ls[0], qv[0]
+        elif self.model == "logsv":
             if init:
                 self.x, self.v, self.q = np.zeros(n), self.p.sigma0 * np.ones(n), np.zeros(n)
             self.x, self.v, self.q = mc.logsv_step_fixed(self.x, self.v, self.q, Z0, Z1, dt, self.p.theta, self.p.kappa1, self.p.kappa2,

@@ -98,3 +98,53 @@ def test_unsharded_path_through_the_same_driver():
     for m in range(2):
         np.testing.assert_allclose(p[m], pe[m], rtol=1e-11, atol=1e-14)
         np.testing.assert_allclose(e[m], ee[m], rtol=1e-9, atol=1e-14)
+
+
+ROUGH = dict(params=(0.8, 1.0, 2.2, 2.2, 0.2, 1.6), weights=np.array([0.7, 0.5, 0.3]), nodes=np.array([0.05, 1.5, 20.0]),
+             ttms=np.array([0.05, 0.15]), types=[np.array(["P", "P", "C", "C", "C"])] * 2)
+N_ROUGH, NPY_ROUGH = 801, 120
+
+
+def _rough_grid():
+    from oracle.mc import set_time_grid
+    grids = []
+    for t in ROUGH["ttms"]:
+        S, _ = set_time_grid(t, NPY_ROUGH)
+        grids.append(np.linspace(0.0, t, S + 1))
+    return grids
+
+
+def _rough_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import sys
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        from fake_engine import OracleEngine
+        from stochvolmodels_b200 import _capi as C, engine
+        from stochvolmodels_b200.multi_gpu import mc_chain_distributed
+        grid = [(g.size - 1, float(g[1] - g[0])) for g in _rough_grid()]
+        factory = lambda *a, **k: OracleEngine(*a, factors=(ROUGH["weights"], ROUGH["nodes"]), **k)
+        out[rank] = mc_chain_distributed("rough", engine.logsv_params_c(*ROUGH["params"]), ROUGH["ttms"], np.ones(2), np.ones(2), None, [K5, K5],
+                                         ROUGH["types"], N_ROUGH, 0, True, C.LOG_RETURN, SEED, C.GAUSS_F64, engine_factory=factory, grid=grid,
+                                         se_paths=1)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_rough_chain_equals_unsharded_under_gloo():
+    """the rough-vol route through the same driver: per-maturity grids from t = 0 (`grid=`), slice-0 draws, un-normalised standard errors
+    (`se_paths=1`), two ranks == the oracle's unsharded chain on the same Philox normals"""
+    from oracle import rough
+    world, port = 2, _free_port()
+    out = mp.Manager().dict()
+    mp.spawn(_rough_worker, args=(world, port, out), nprocs=world, join=True)
+    grids = _rough_grid()
+    Z0, Z1 = mc.device_normals(SEED, np.arange(N_ROUGH), 0, grids[-1].size - 1, "f64")
+    pe, ee = rough.rough_chain_fixed(ROUGH["ttms"], np.ones(2), np.ones(2), [K5, K5], ROUGH["types"], Z0, Z1, *ROUGH["params"], ROUGH["weights"],
+                                     ROUGH["nodes"], grids)
+    for rank in range(world):
+        p, e = out[rank]
+        for m in range(2):
+            np.testing.assert_allclose(p[m], pe[m], rtol=1e-11, atol=1e-14)
+            np.testing.assert_allclose(e[m], ee[m], rtol=1e-9, atol=1e-14)
