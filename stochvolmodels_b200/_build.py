@@ -31,7 +31,7 @@ def needs_build() -> bool:
         return True
     t = os.path.getmtime(LIB)
     import glob
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + glob.glob(os.path.join(CSRC, "*.cuh")) \
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.inc")) \
         + [os.path.join(PKG, "..", "include", "b200sv.h"), os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps)
 
