@@ -11,9 +11,8 @@
 // evaluation order without FMA contraction (the reference is plain numpy: IEEE operations one by one) -- the parity entry, 40 B of inputs
 // per path-step from HBM.  hawkes_slice_kernel: the same update with every draw made in-kernel (no HBM traffic but the state):
 //   normals      the stepper's stream (philox.cuh, counter word 3 = slice): one Philox call feeds 4 steps (float draws) or 2 (fp64 draws)
-//   jump clocks  a second Philox stream (counter word 3 = slice | 0x80000000), one call per step: u = (r + 1/2) 2^-32 for the two clocks and
-//   and sizes    the two sizes.  A jump needs -ln(u) < lambda dt; since -ln(u) >= 1 - u the logarithm is only evaluated when
-//                1 - u < lambda dt (1 + 1e-9), i.e. on ~lambda dt = 0.5 % of the steps, and the jump size only when a jump fires.
+//   jump clocks  a second stream (slice | 0x80000000), one call per TWO steps; a third (slice | 0x40000000) holds the jump sizes and is only
+//   and sizes    evaluated when a clock fires (~lambda dt = 0.5 % of the steps).  u = (r + 1/2) 2^-32.
 // b200sv_hawkesjd_device_draws exports the in-kernel draws in the reference's form so that the fused kernel is checked path by path
 // against the oracle on ITS OWN inputs.
 #pragma once
@@ -82,14 +81,17 @@ __global__ void __launch_bounds__(kThreads) hawkes_step_fixed_kernel(double* __r
   }
 }
 
-// the jump-stream draws of one (path, step): uniforms in (0, 1) of the two clocks and the two sizes
-__device__ __forceinline__ void hawkes_jump_uniforms(uint2 key, uint32_t plo, uint32_t phi, uint32_t step, uint32_t slice, double (&u)[4]) {
-  const uint4 r = philox4x32_10(make_uint4(plo, phi, step, slice | 0x80000000u), key);
-  u[0] = fma((double)r.x, 2.3283064365386963e-10, 1.1641532182693481e-10);
-  u[1] = fma((double)r.y, 2.3283064365386963e-10, 1.1641532182693481e-10);
-  u[2] = fma((double)r.z, 2.3283064365386963e-10, 1.1641532182693481e-10);
-  u[3] = fma((double)r.w, 2.3283064365386963e-10, 1.1641532182693481e-10);
+// Jump streams of one path (counter word 3 = slice | flag; the stepper's normals use the plain slice):
+//   clocks  flag 0x80000000, call k = step / 2:  words (x, y) = the (+, -) clocks of step 2k, (z, w) = those of step 2k + 1
+//   sizes   flag 0x40000000, call = step:        words (x, y) = the (+, -) jump sizes -- evaluated only when a clock fires
+// uniform in (0, 1) of a 32-bit word: (r + 1/2) 2^-32
+__device__ __forceinline__ uint4 hawkes_clock_words(uint2 key, uint32_t plo, uint32_t phi, uint32_t pair, uint32_t slice) {
+  return philox4x32_10(make_uint4(plo, phi, pair, slice | 0x80000000u), key);
 }
+__device__ __forceinline__ uint4 hawkes_size_words(uint2 key, uint32_t plo, uint32_t phi, uint32_t step, uint32_t slice) {
+  return philox4x32_10(make_uint4(plo, phi, step, slice | 0x40000000u), key);
+}
+__device__ __forceinline__ double hawkes_uniform(uint32_t r) { return fma((double)r, 2.3283064365386963e-10, 1.1641532182693481e-10); }
 // exponential clock -ln(U)/dt and shifted-exponential sizes exactly as b200sv_hawkesjd_device_draws exports them
 __device__ __forceinline__ double hawkes_clock(double u, const HawkesConsts& c) { return __ddiv_rn(-log(u), c.dt); }
 __device__ __forceinline__ double hawkes_size_p(double u, const HawkesConsts& c) { return __dadd_rn(c.shift_p, __dmul_rn(c.mean_p, -log(u))); }
@@ -108,12 +110,42 @@ struct HawkesSliceArgs {
   double* partials;            // [gridDim.x][2]: (sum F e^x over non-NaN, count) for the forward re-centring
 };
 
+// Throughput stepper.  Per step the common case (no jump, ~99.5 % of the steps at the reference's parameters) is 8 contracted fp64
+// operations; whether a clock CAN fire is decided on the raw 32-bit word: -ln(u) >= 1 - u, so a jump needs 1 - u < lambda dt, i.e.
+// r >= floor(2^32 (1 - lambda dt (1 + 1e-9))) - 1 (one DFMA + F2I + integer compare; the margins cover the rounding of the product and of
+// the floor).  Only then are the logarithm, the exact comparison lambda > -ln(u)/dt of the reference (:767-768) and -- if it fires -- the
+// size stream evaluated.  Same draws as b200sv_hawkesjd_device_draws exports; agreement with the strict kernel ~1e-15 (FMA contraction).
+struct HawkesFast {
+  double ssd;                // sigma sqrt(dt)
+  double kdt_p, kdt_m;       // kappa dt
+  double thr;                // dt (1 + 1e-9) 2^32
+  double dt_lo;              // dt (1 - 1e-9)
+};
+
+// Does the clock with word r fire against intensity lam, i.e. is lam > -ln(u)/dt as the reference evaluates it (:767-768)?  With e = 1 - u
+// (exact in fp64): -ln(u) <= e + e^2 for e <= 1/2, so e + e^2 < lam dt (1 - 1e-9) settles it without a logarithm; the band in between
+// (relative width ~e, i.e. ~0.5 % of the candidates) takes the exact comparison, out of line.
+__device__ __noinline__ bool hawkes_fires_exact(double lam, double u, double dt) { return lam > __ddiv_rn(-log(u), dt); }
+__device__ __forceinline__ bool hawkes_fires(double lam, uint32_t r, double dt, double dt_lo) {
+  const double u = hawkes_uniform(r), e = 1.0 - u;
+  if (e <= 0.5 && fma(e, e, e) < lam * dt_lo) return true;
+  return hawkes_fires_exact(lam, u, dt);
+}
+// both clocks firing in one step (~1e-5 of the steps): out of line
+__device__ __noinline__ double2 hawkes_two_sizes(uint32_t wx, uint32_t wy, double shift_p, double mean_p, double shift_m, double mean_m) {
+  return make_double2(__dadd_rn(shift_p, __dmul_rn(mean_p, -log(hawkes_uniform(wx)))), __dadd_rn(shift_m, -__dmul_rn(-mean_m, -log(hawkes_uniform(wy)))));
+}
+
+#ifndef B200SV_HAWKES_MINBLOCKS
+#define B200SV_HAWKES_MINBLOCKS 2
+#endif
 template <int GAUSS>
-__global__ void __launch_bounds__(kThreads) hawkes_slice_kernel(HawkesSliceArgs a, HawkesConsts c) {
+__global__ void __launch_bounds__(kThreads, B200SV_HAWKES_MINBLOCKS) hawkes_slice_kernel(HawkesSliceArgs a, HawkesConsts c) {
   __shared__ double red[2 * kThreads / 32];
   if constexpr (GAUSS != kGaussF32) gauss64_table_init();
   double acc[2] = {0.0, 0.0};
   const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+  const HawkesFast f{c.sigma * c.sqrt_dt, c.kappa_p * c.dt, c.kappa_m * c.dt, c.dt * (1.0 + 1e-9) * 4294967296.0, c.dt * (1.0 - 1e-9)};
   const long long stride = (long long)gridDim.x * kThreads;
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < a.n; i += stride) {
     double xi = 0.0, lp = a.lam_p0, lm = a.lam_m0;
@@ -125,22 +157,54 @@ __global__ void __launch_bounds__(kThreads) hawkes_slice_kernel(HawkesSliceArgs 
     const unsigned long long path = a.path_offset + (unsigned long long)i;
     const uint32_t plo = (uint32_t)path, phi = (uint32_t)(path >> 32);
     StepNormals<double, GAUSS> rng(a.seed, path, a.slice);
-    double z[4];
-    for (int s = 0; s < a.nsteps; ++s) {
-      // normals: float draws -> call s/4 yields (z for steps 4k .. 4k+3); fp64 draws -> call s/2 yields two
-      if constexpr (GAUSS == kGaussF64) {
-        if ((s & 1) == 0) rng.get((uint32_t)(s >> 1), z[0], z[1]);
-      } else {
-        if ((s & 3) == 0) rng.get2((uint32_t)(s >> 2), z[0], z[1], z[2], z[3]);
-      }
-      const double w0 = __dmul_rn(c.sqrt_dt, GAUSS == kGaussF64 ? z[s & 1] : z[s & 3]);
-      double u[4];
-      hawkes_jump_uniforms(key, plo, phi, (uint32_t)s, a.slice, u);
+    auto one_step = [&](double z, uint32_t rp, uint32_t rm, uint32_t step) {
+      const uint32_t tp = __double2uint_rd(fma(-lp, f.thr, 4294967296.0)), tm = __double2uint_rd(fma(-lm, f.thr, 4294967296.0));
+      const bool cand_p = rp >= max(tp, 1u) - 1u, cand_m = rm >= max(tm, 1u) - 1u;
       double jp = 0.0, jm = 0.0;
-      // -ln(u) >= 1 - u: a clock can only fire below lambda when 1 - u < lambda dt (margin 1e-9 against rounding of the product)
-      if (1.0 - u[0] < lp * c.dt * (1.0 + 1e-9) && lp > hawkes_clock(u[0], c)) jp = hawkes_size_p(u[2], c);
-      if (1.0 - u[1] < lm * c.dt * (1.0 + 1e-9) && lm > hawkes_clock(u[1], c)) jm = hawkes_size_m(u[3], c);
-      hawkes_update(xi, lp, lm, w0, jp, jm, c);
+      if (cand_p || cand_m) {                                                     // ~1 % of the lane-steps: a clock may fire
+        const bool fp_ = cand_p && hawkes_fires(lp, rp, c.dt, f.dt_lo), fm_ = cand_m && hawkes_fires(lm, rm, c.dt, f.dt_lo);
+        if (fp_ || fm_) {
+          const uint4 w = hawkes_size_words(key, plo, phi, step, a.slice);
+          if (fp_ && fm_) {
+            const double2 jj = hawkes_two_sizes(w.x, w.y, c.shift_p, c.mean_p, c.shift_m, c.mean_m);
+            jp = jj.x;
+            jm = jj.y;
+          } else {                                                                // one logarithm serves whichever clock fired
+            const double l = -log(hawkes_uniform(fp_ ? w.x : w.y));
+            if (fp_) jp = __dadd_rn(c.shift_p, __dmul_rn(c.mean_p, l));            // = hawkes_size_p
+            else jm = __dadd_rn(c.shift_m, -__dmul_rn(-c.mean_m, l));              // = hawkes_size_m
+          }
+        }
+      }
+      double d = fma(-c.comp_p, lp, c.drift_dt);
+      d = fma(-c.comp_m, lm, d);
+      d = fma(f.ssd, z, d);
+      xi += d;
+      lp = fma(f.kdt_p, c.theta_p - lp, lp);
+      lm = fma(f.kdt_m, c.theta_m - lm, lm);
+      if (jp != 0.0 || jm != 0.0) {
+        xi += jp + jm;
+        lp += fma(c.beta1_p, jp, c.beta2_p * jm);
+        lm += fma(c.beta1_m, jp, c.beta2_m * jm);
+      }
+    };
+    const int S = a.nsteps;
+    for (int s = 0; s < S; s += 4) {                  // four steps: one (float) or two (fp64) calls of normals, two calls of clocks
+      double z[4];
+      if constexpr (GAUSS == kGaussF64) {
+        rng.get((uint32_t)(s >> 1), z[0], z[1]);
+        if (s + 2 < S) rng.get((uint32_t)(s >> 1) + 1u, z[2], z[3]);
+      } else {
+        rng.get2((uint32_t)(s >> 2), z[0], z[1], z[2], z[3]);
+      }
+      const uint4 c0 = hawkes_clock_words(key, plo, phi, (uint32_t)(s >> 1), a.slice);
+      one_step(z[0], c0.x, c0.y, (uint32_t)s);
+      if (s + 1 < S) one_step(z[1], c0.z, c0.w, (uint32_t)s + 1u);
+      if (s + 2 < S) {
+        const uint4 c1 = hawkes_clock_words(key, plo, phi, (uint32_t)(s >> 1) + 1u, a.slice);
+        one_step(z[2], c1.x, c1.y, (uint32_t)s + 2u);
+        if (s + 3 < S) one_step(z[3], c1.z, c1.w, (uint32_t)s + 3u);
+      }
     }
     a.x[i] = xi;
     a.lam_p[i] = lp;
@@ -176,14 +240,14 @@ __global__ void hawkes_device_draws_kernel(unsigned long long seed, unsigned lon
     } else {
       if ((s & 3) == 0) rng.get2((uint32_t)(s >> 2), z[0], z[1], z[2], z[3]);
     }
-    double u[4];
-    hawkes_jump_uniforms(key, (uint32_t)path, (uint32_t)(path >> 32), (uint32_t)s, slice, u);
+    const uint4 ck = hawkes_clock_words(key, (uint32_t)path, (uint32_t)(path >> 32), (uint32_t)(s >> 1), slice);
+    const uint4 sz = hawkes_size_words(key, (uint32_t)path, (uint32_t)(path >> 32), (uint32_t)s, slice);
     const size_t o = (size_t)s * n + i;
     W0[o] = __dmul_rn(c.sqrt_dt, GAUSS == kGaussF64 ? z[s & 1] : z[s & 3]);
-    U_P[o] = hawkes_clock(u[0], c);
-    U_M[o] = hawkes_clock(u[1], c);
-    J_P[o] = hawkes_size_p(u[2], c);
-    J_M[o] = hawkes_size_m(u[3], c);
+    U_P[o] = hawkes_clock(hawkes_uniform((s & 1) ? ck.z : ck.x), c);
+    U_M[o] = hawkes_clock(hawkes_uniform((s & 1) ? ck.w : ck.y), c);
+    J_P[o] = hawkes_size_p(hawkes_uniform(sz.x), c);
+    J_M[o] = hawkes_size_m(hawkes_uniform(sz.y), c);
   }
 }
 
