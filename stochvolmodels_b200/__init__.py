@@ -9,7 +9,10 @@ from .pricers.logsv.affine_expansion import ExpansionOrder
 from .pricers.logsv_pricer import LOGSV_BTC_PARAMS, LogSvParams, LogSVPricer
 from .pricers.model_pricer import ModelParams, ModelPricer
 from .utils.config import OptionType, VariableType
+from .utils.funcs import set_seed, set_time_grid
+from .utils.mgf_pricer import compute_integration_weights
 
 __version__ = "0.1.0"
 __all__ = ["HawkesJDParams", "HawkesJDPricer", "OptionChain", "get_btc_test_chain_data", "HestonParams", "HestonPricer", "BTC_HESTON_PARAMS", "ExpansionOrder",
-           "LogSvParams", "LogSVPricer", "CalibrationEngine", "CalibrationError", "ConstraintsType", "LogsvModelCalibrationType", "LOGSV_BTC_PARAMS", "ModelParams", "ModelPricer", "OptionType", "VariableType"]
+           "LogSvParams", "LogSVPricer", "CalibrationEngine", "CalibrationError", "ConstraintsType", "LogsvModelCalibrationType", "LOGSV_BTC_PARAMS", "ModelParams", "ModelPricer", "OptionType", "VariableType", "set_seed", "set_time_grid",
+           "compute_integration_weights"]

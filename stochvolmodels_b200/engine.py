@@ -15,8 +15,22 @@ from . import _capi as C
 from .utils.config import VariableType
 
 
+_SEED_STREAM = None          # set_seed(): a deterministic stream of per-call Philox seeds; None: OS entropy
+
+
+def set_seed(value) -> None:
+    """the reference's ``set_seed`` (utils/funcs.py:51-60) seeds Numba's process-global generator so that the Monte Carlo calls that follow
+    are reproducible.  Here every MC call takes an explicit ``seed``; calls WITHOUT one draw theirs from a process-global stream that this
+    function (re)starts, so `set_seed(8); price(); price()` gives the same two results in every run, as with the reference.  ``None``
+    returns to OS entropy."""
+    global _SEED_STREAM
+    _SEED_STREAM = None if value is None else np.random.Generator(np.random.Philox(int(value)))
+
+
 def fresh_seed() -> int:
-    """explicit seeds replace the reference's process-global Numba RNG (utils/funcs.py:51-60); default = OS entropy."""
+    """seed of an MC call that was not given one: next value of the set_seed() stream, else OS entropy."""
+    if _SEED_STREAM is not None:
+        return int(_SEED_STREAM.integers(0, 1 << 63))
     return int.from_bytes(os.urandom(8), "little")
 
 

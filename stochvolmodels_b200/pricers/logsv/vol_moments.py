@@ -72,3 +72,45 @@ def fit_vol_backbone_to_varswaps(params, varswap_strikes, n_terms: int = 4):
     eta = np.where(eta > 0.0, eta, 1.0)
     eta = np.where(ttms < 0.06, np.sqrt(eta), eta)
     return pd.Series(eta, index=ttms)
+
+
+# ---- the reference's entry-point names and signatures (pricers/logsv/vol_moments_ode.py:29-217) over the functions above -------------
+def compute_analytic_vol_moments(params, t: float = 1.0, n_terms: int = 4, is_qvar: bool = False) -> np.ndarray:
+    """moments of Y at ``t`` (``is_qvar``: their integrals over [0, t]) -- vol_moments_ode.py:29"""
+    return vol_moments(params, t=t, n_terms=n_terms, integrated=is_qvar)
+
+
+def compute_analytic_qvar(params, ttm: float = 1.0, n_terms: int = 4) -> float:
+    """annualised expected quadratic variance, Eq. (3.53) -- vol_moments_ode.py:110"""
+    return expected_qvar(params, ttm=ttm, n_terms=n_terms)
+
+
+def compute_vol_moments_t(params, ttm: np.ndarray, n_terms: int = 4, is_print: bool = False) -> np.ndarray:
+    """[len(ttm), n_terms] table of the moments (vol_moments_ode.py:149)"""
+    table = np.array([vol_moments(params, t=float(t_), n_terms=n_terms) for t_ in ttm]).reshape(len(ttm), n_terms)
+    if is_print:
+        for t_, row in zip(ttm, table):
+            print(f"t={t_}: {row}")
+    return table
+
+
+def compute_expected_vol_t(params, t: np.ndarray, n_terms: int = 4) -> np.ndarray:
+    """E[sigma_t] = E[Y_t] + theta over an array of times (vol_moments_ode.py:164)"""
+    return np.array([vol_moments(params, t=float(t_), n_terms=n_terms)[0] + params.theta for t_ in t])
+
+
+def compute_sqrt_qvar_t(params, t: np.ndarray, n_terms: int = 4) -> np.ndarray:
+    """model variance-swap rate in vol terms over an array of maturities (vol_moments_ode.py:178)"""
+    return np.sqrt(np.array([expected_qvar(params, ttm=float(t_), n_terms=n_terms) for t_ in t]))
+
+
+def fit_model_vol_backbone_to_varswaps(log_sv_params, varswap_strikes, n_terms: int = 4, verbose: bool = False):
+    """vol_moments_ode.py:186; ``verbose`` prints the market / model forward variances next to the fitted eta"""
+    eta = fit_vol_backbone_to_varswaps(log_sv_params, varswap_strikes, n_terms=n_terms)
+    if verbose:
+        ttms = np.asarray(varswap_strikes.index, dtype=float)
+        print("vars_swaps")
+        for t_, k, e in zip(ttms, np.asarray(varswap_strikes, dtype=float), np.asarray(eta)):
+            print(f"  ttm={t_:.4f} strike={k:.4f} market_qvar_dt={t_ * k * k:.6f} model_qvar_dt={expected_qvar(log_sv_params, t_, n_terms) * t_:.6f} "
+                  f"model_eta={e:.4f}")
+    return eta

@@ -97,6 +97,58 @@ class LogSvParams(ModelParams):
     def vartheta2(self) -> float:
         return self.beta * self.beta + self.volvol * self.volvol
 
+    @property
+    def gamma(self) -> float:
+        """kappa1 / theta: the quadratic mean-reversion rate of the pure quadratic drift (logsv_params.py:189-196)"""
+        return self.kappa1 / self.theta
+
+    @property
+    def eta(self) -> float:
+        """exponent of the steady-state (generalised inverse Gaussian) vol density, 2 (kappa2 theta - kappa1) / vartheta^2 - 1 (:198-207)"""
+        return 2.0 * (self.kappa2 * self.theta - self.kappa1) / self.vartheta2 - 1.0
+
+    # spatial grids for the densities of logsv_pdfs (logsv_params.py:209-267): n points; width set by the average of sigma0^2 and theta^2
+    def get_x_grid(self, ttm: float = 1.0, n_stdevs: float = 3.0, n: int = 200) -> np.ndarray:
+        total_vol = np.sqrt(0.5 * ttm * (self.sigma0 ** 2 + self.theta ** 2))
+        centre, half_width = -0.5 * total_vol * total_vol, (n_stdevs + 1) * total_vol
+        return np.linspace(centre - half_width, centre + half_width, n)
+
+    def get_sigma_grid(self, ttm: float = 1.0, n_stdevs: float = 3.0, n: int = 200) -> np.ndarray:
+        level = np.sqrt(0.5 * (self.sigma0 ** 2 + self.theta ** 2))
+        return np.linspace(0.0, level + n_stdevs * 0.5 * np.sqrt(self.vartheta2 * ttm), n)
+
+    def get_qvar_grid(self, ttm: float = 1.0, n_stdevs: float = 3.0, n: int = 200) -> np.ndarray:
+        level = np.sqrt(ttm * (self.sigma0 ** 2 + self.theta ** 2))
+        return np.linspace(0.0, level + n_stdevs * np.sqrt(self.vartheta2) * ttm, n)
+
+    def get_variable_space_grid(self, variable_type: VariableType = VariableType.LOG_RETURN, ttm: float = 1.0, n_stdevs: float = 3,
+                                n: int = 200) -> np.ndarray:
+        code = getattr(variable_type, "value", variable_type)            # by value: the reference's own enum duck-types
+        grid = {VariableType.LOG_RETURN.value: self.get_x_grid, VariableType.SIGMA.value: self.get_sigma_grid,
+                VariableType.Q_VAR.value: self.get_qvar_grid}.get(code)
+        if grid is None:
+            raise NotImplementedError
+        return grid(ttm=ttm, n_stdevs=n_stdevs, n=n)
+
+    def get_vol_moments_lambda(self, n_terms: int = 4) -> np.ndarray:
+        """generator Lambda^(1,k*) of the truncated vol-moment system, Eq. (3.48) (logsv_params.py:269-323)"""
+        from .logsv.vol_moments import vol_moments_generator
+        return vol_moments_generator(self, n_terms=n_terms)
+
+    def assert_vol_moments_stability(self, n_terms: int = 4):
+        """prints (does not assert, as in the reference :325-335) whether every eigenvalue of Lambda has a negative real part"""
+        stable = bool(np.all(np.linalg.eigvals(self.get_vol_moments_lambda(n_terms)).real < 0.0))
+        print(f"vol moments stable = {stable}")
+
+    def print_vol_moments_stability(self, n_terms: int = 4) -> None:
+        for order, label in ((2, "con2"), (3, "con3"), (4, "cond4")):       # diagonal conditions c(n) - n kappa (:337-357)
+            print(f"{label}:\n{0.5 * self.vartheta2 * order * (order - 1.0) - order * self.kappa}")
+        lam = self.get_vol_moments_lambda(n_terms)
+        w = np.linalg.eigvals(lam)
+        print(f"lambda_m:\n{lam}")
+        print(f"eigenvalues w:\n{w}")
+        print(f"vol moments stable = {bool(np.all(w.real < 0.0))}")
+
 
 LOGSV_BTC_PARAMS = LogSvParams(sigma0=0.8376, theta=1.0413, kappa1=3.1844, kappa2=3.058, beta=0.1514, volvol=1.8458)   # logsv_pricer.py:102
 

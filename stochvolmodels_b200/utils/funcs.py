@@ -32,3 +32,9 @@ def timer(func):
         logging.getLogger(func.__module__).debug("Finished %r in %.4f secs", func.__name__, time.perf_counter() - start)
         return value
     return wrapper_timer
+
+
+def set_seed(value) -> None:
+    """reference utils/funcs.py:51-60: make the seedless Monte Carlo calls that follow reproducible (see engine.set_seed)."""
+    from .. import engine
+    engine.set_seed(value)

@@ -71,3 +71,29 @@ def pdf_with_mgf_grid(log_mgf_grid: np.ndarray, transform_var_grid: np.ndarray, 
     z = (space_grid - shift) / scale
     dx = space_grid[1] - space_grid[0]
     return dx * engine.fourier_pdf_sums(log_mgf_grid, transform_var_grid, z)
+
+
+def compute_integration_weights(var_grid: np.ndarray, is_simpson: bool = True) -> np.ndarray:
+    """composite Simpson (odd point count) or trapezoidal weights on the imaginary part of a transform grid, with the validation of the
+    reference's public helper (utils/mgf_pricer.py:98-154: finite, strictly increasing, uniformly spaced to 1e-12 relative; the error texts
+    are part of its contract).  Host numpy: the pricing kernels build the reference's *legacy* weights (:158-171, even-grid quirk included)
+    in registers and never materialise a weight array."""
+    p = np.imag(np.asarray(var_grid))
+    if p.size < (3 if is_simpson else 2):
+        raise ValueError("integration grid is too short for the selected rule")
+    if not np.isfinite(p).all():
+        raise ValueError("integration grid must contain only finite values")
+    h = np.diff(p)
+    if (h <= 0.0).any():
+        raise ValueError("integration grid must be strictly increasing")
+    if (np.abs(h - h[0]) > 1.0e-12 * max(1.0, abs(h[0]))).any():
+        raise ValueError("integration grid must be uniformly spaced")
+    if is_simpson:
+        if p.size % 2 == 0:
+            raise ValueError("Simpson integration requires an odd number of grid points")
+        pattern = np.where(np.arange(p.size) % 2 == 1, 4.0, 2.0)
+        pattern[0] = pattern[-1] = 1.0
+        return (p[1] - p[0]) / 3.0 * pattern
+    w = np.full(p.size, h[0])
+    w[0] = w[-1] = 0.5 * h[0]
+    return w

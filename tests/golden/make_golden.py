@@ -758,6 +758,37 @@ HAWKES_KEYS = ("mu", "sigma", "shift_p", "mean_p", "shift_m", "mean_m", "lambda_
                "kappa_m", "beta1_m", "beta2_m")
 
 
+def params_helpers() -> None:
+    """LogSvParams helper methods (spatial grids, steady-state exponents, vol-moment generator) and the vol-moment / variance-swap functions of
+    pricers/logsv/vol_moments_ode.py for three parameter sets -> logsv_params_helpers.npz.   python tests/golden/make_golden.py --only-helpers"""
+    _import_reference()
+    import pandas as pd
+    from stochvolmodels.pricers.logsv.logsv_params import LogSvParams
+    from stochvolmodels.pricers.logsv import vol_moments_ode as vmo
+    from stochvolmodels.utils.config import VariableType
+    sets = np.array([[1.0, 1.0, 5.0, 5.0, 0.2, 2.0], [0.8376, 1.0413, 3.1844, 3.058, 0.1514, 1.8458], [0.35, 0.5, 2.0, 1.2, -0.6, 0.9]])
+    ts = np.array([0.0, 0.05, 0.25, 1.0, 2.5])
+    out = dict(sets=sets, ts=ts)
+    for i, row in enumerate(sets):
+        p = LogSvParams(*row)
+        out[f"scalars_{i}"] = np.array([p.gamma, p.eta, p.kappa, p.theta2, p.vartheta2])
+        for name, vt in (("x", VariableType.LOG_RETURN), ("sigma", VariableType.SIGMA), ("qvar", VariableType.Q_VAR)):
+            out[f"grid_{name}_{i}"] = p.get_variable_space_grid(variable_type=vt, ttm=0.7, n_stdevs=2.5, n=37)
+        out[f"grid_x_default_{i}"] = p.get_x_grid()
+        out[f"lambda4_{i}"] = p.get_vol_moments_lambda(n_terms=4)
+        out[f"lambda8_{i}"] = p.get_vol_moments_lambda(n_terms=8)
+        out[f"moments_{i}"] = vmo.compute_vol_moments_t(params=p, ttm=ts, n_terms=4)
+        out[f"moments8_{i}"] = vmo.compute_vol_moments_t(params=p, ttm=ts[1:], n_terms=8)
+        out[f"int_moments_{i}"] = np.array([vmo.compute_analytic_vol_moments(params=p, t=t, n_terms=4, is_qvar=True) for t in ts[1:]])
+        out[f"expected_vol_{i}"] = vmo.compute_expected_vol_t(params=p, t=ts, n_terms=4)
+        out[f"sqrt_qvar_{i}"] = vmo.compute_sqrt_qvar_t(params=p, t=ts, n_terms=4)
+        strikes = pd.Series(np.array([0.9, 0.95, 1.0, 1.05]) * row[0], index=np.array([0.04, 0.1, 0.5, 1.0]))
+        out[f"varswap_strikes_{i}"] = np.stack([strikes.index.to_numpy(), strikes.to_numpy()])
+        out[f"backbone_{i}"] = vmo.fit_model_vol_backbone_to_varswaps(log_sv_params=p, varswap_strikes=strikes).to_numpy()
+    np.savez(os.path.join(OUT, "logsv_params_helpers.npz"), **out)
+    print("wrote logsv_params_helpers.npz")
+
+
 def _chain(ttms, fw, df, K, T):
     from stochvolmodels.data.option_chain import OptionChain
     from numba.typed import List
@@ -766,6 +797,9 @@ def _chain(ttms, fw, df, K, T):
 
 
 if __name__ == "__main__":
+    if "--only-helpers" in sys.argv:
+        params_helpers()
+        sys.exit(0)
     if "--only-bdf" in sys.argv:
         bdf_branch()
         sys.exit(0)

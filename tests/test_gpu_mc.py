@@ -511,3 +511,19 @@ def test_terminal_values_shards_concatenate_to_the_single_gpu_arrays(cuda_lib):
         np.testing.assert_array_equal(np.concatenate([part[k] for part in parts]), full[k])
     with pytest.raises(ValueError):
         LogSVPricer().simulate_terminal_values(p, ttm=0.3, nb_path=N, path_range=(0, 10))
+
+
+def test_set_seed_reproduces_seedless_monte_carlo(cuda_lib):
+    """reference usage `set_seed(123)` before MC (its tests/test_heston_characterization.py:282): seedless calls after the same set_seed
+    return the same prices, consecutive seedless calls differ"""
+    from stochvolmodels_b200 import LOGSV_BTC_PARAMS, LogSVPricer, get_btc_test_chain_data, set_seed
+    chain, pricer = get_btc_test_chain_data(), LogSVPricer()
+    runs = []
+    for _ in range(2):
+        set_seed(123)
+        runs.append([pricer.model_mc_price_chain(chain, LOGSV_BTC_PARAMS, nb_path=20000, nb_steps=100)[0] for _ in range(2)])
+    set_seed(None)
+    for a, b in zip(runs[0], runs[1]):
+        for x, y in zip(a, b):
+            np.testing.assert_array_equal(x, y)
+    assert not np.array_equal(runs[0][0][0], runs[0][1][0])

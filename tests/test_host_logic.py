@@ -207,3 +207,71 @@ def test_rough_random_grid_replays_seed_and_has_aligned_shapes():
     np.testing.assert_array_equal(p.nodes, q.nodes)
     with pytest.raises(AssertionError):
         LogSvParams(H=0.7)
+
+
+def test_logsv_params_helpers_and_vol_moment_entry_points_vs_reference_golden(capsys):
+    """LogSvParams.gamma / eta / spatial grids / get_vol_moments_lambda and the reference-named functions of pricers/logsv/vol_moments
+    (compute_analytic_vol_moments, compute_vol_moments_t, compute_expected_vol_t, compute_sqrt_qvar_t, fit_model_vol_backbone_to_varswaps)
+    against the reference's own outputs (logsv_params_helpers.npz, three parameter sets)"""
+    import pandas as pd
+    from conftest import load_golden
+    from stochvolmodels_b200 import LogSvParams, VariableType
+    from stochvolmodels_b200.pricers.logsv import vol_moments as vm
+    g = load_golden("logsv_params_helpers.npz")
+    ts = g["ts"]
+    for i, row in enumerate(g["sets"]):
+        p = LogSvParams(*row)
+        np.testing.assert_allclose([p.gamma, p.eta, p.kappa, p.theta2, p.vartheta2], g[f"scalars_{i}"], rtol=1e-15)
+        for name, vt in (("x", VariableType.LOG_RETURN), ("sigma", VariableType.SIGMA), ("qvar", VariableType.Q_VAR)):
+            np.testing.assert_allclose(p.get_variable_space_grid(variable_type=vt, ttm=0.7, n_stdevs=2.5, n=37), g[f"grid_{name}_{i}"], rtol=1e-14,
+                                       atol=1e-15)
+        np.testing.assert_allclose(p.get_x_grid(), g[f"grid_x_default_{i}"], rtol=1e-14, atol=1e-15)
+        np.testing.assert_allclose(p.get_vol_moments_lambda(4), g[f"lambda4_{i}"], rtol=1e-15)
+        np.testing.assert_allclose(p.get_vol_moments_lambda(n_terms=8), g[f"lambda8_{i}"], rtol=1e-15)
+        np.testing.assert_allclose(vm.compute_vol_moments_t(params=p, ttm=ts, n_terms=4), g[f"moments_{i}"], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(vm.compute_vol_moments_t(params=p, ttm=ts[1:], n_terms=8), g[f"moments8_{i}"], rtol=1e-7, atol=1e-10)
+        ints = np.array([vm.compute_analytic_vol_moments(params=p, t=t, n_terms=4, is_qvar=True) for t in ts[1:]])
+        np.testing.assert_allclose(ints, g[f"int_moments_{i}"], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(vm.compute_expected_vol_t(params=p, t=ts), g[f"expected_vol_{i}"], rtol=1e-10)
+        np.testing.assert_allclose(vm.compute_sqrt_qvar_t(params=p, t=ts), g[f"sqrt_qvar_{i}"], rtol=1e-10)
+        idx, k = g[f"varswap_strikes_{i}"]
+        eta = vm.fit_model_vol_backbone_to_varswaps(log_sv_params=p, varswap_strikes=pd.Series(k, index=idx), verbose=(i == 0))
+        np.testing.assert_allclose(eta.to_numpy(), g[f"backbone_{i}"], rtol=1e-9)
+        np.testing.assert_array_equal(eta.index.to_numpy(), idx)
+    with pytest.raises(NotImplementedError):
+        p.get_variable_space_grid(variable_type=7)
+    p.assert_vol_moments_stability()
+    p.print_vol_moments_stability()
+    out = capsys.readouterr().out
+    assert "vol moments stable = True" in out and "lambda_m" in out and "vars_swaps" in out
+
+
+def test_compute_integration_weights_properties_and_errors():
+    """the reference's own assertions about its public quadrature helper (its tests/test_numerical_utilities.py:9-60): Simpson integrates
+    cubics exactly, trapezoid integrates linears, even-sized / short / non-uniform / decreasing / non-finite grids raise ValueError"""
+    from stochvolmodels_b200 import compute_integration_weights
+    x = np.linspace(-2.0, 2.0, 9)
+    w = compute_integration_weights(0.5 + 1j * x, is_simpson=True)
+    np.testing.assert_allclose([w @ np.ones(9), w @ x, w @ x ** 2, w @ x ** 3], [4.0, 0.0, 16.0 / 3.0, 0.0], atol=1e-14)
+    y = np.linspace(0.0, 1.0, 5)
+    w = compute_integration_weights(-0.5 + 1j * y, is_simpson=False)
+    np.testing.assert_allclose([w @ np.ones(5), w @ y], [1.0, 0.5], atol=1e-14)
+    with pytest.raises(ValueError, match="odd"):
+        compute_integration_weights(1j * np.linspace(0.0, 1.0, 4), is_simpson=True)
+    for grid, simpson, message in ((np.array([0.0]), False, "too short"), (np.array([0.0, 0.5, 1.1]), True, "uniform"),
+                                   (np.array([0.0, 0.5, 0.4]), True, "increasing"), (np.array([0.0, np.nan, 1.0]), True, "finite")):
+        with pytest.raises(ValueError, match=message):
+            compute_integration_weights(1j * grid, is_simpson=simpson)
+
+
+def test_set_seed_makes_seedless_calls_reproducible():
+    from stochvolmodels_b200 import engine, set_seed
+    set_seed(8)
+    a = [engine.fresh_seed() for _ in range(3)]
+    set_seed(8)
+    b = [engine.fresh_seed() for _ in range(3)]
+    set_seed(9)
+    c = engine.fresh_seed()
+    set_seed(None)
+    d, e = engine.fresh_seed(), engine.fresh_seed()
+    assert a == b and len(set(a)) == 3 and c != a[0] and d != e and all(0 <= s < 1 << 64 for s in a + [c, d, e])
