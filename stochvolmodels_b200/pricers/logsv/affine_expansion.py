@@ -110,3 +110,38 @@ def solve_a_ode_grid(phi_grid: np.ndarray, psi_grid: np.ndarray, ttm: float, the
     a_t1, _ = solver(phi_grid, psi_grid, ttm, a_t0, engine.logsv_params_c(theta, theta, kappa1, kappa2, beta, volvol), vol_backbone_eta,
                      is_spot_measure, order)
     return a_t1
+
+
+# ---- single-point entry points of the reference (affine_expansion.py:209-384): one-element grids through the same kernels ---------------
+def func_rhs_jac(t: float, A0: np.ndarray, M, L: np.ndarray, H: np.ndarray) -> np.ndarray:
+    """Jacobian of func_rhs in A, d/dA (A^T M^(k) A) = 2 M^(k) A for the symmetric M^(k), plus L (affine_expansion.py:209-225; the argument
+    order is solve_ivp's, ``t`` and ``H`` are unused).  Interface helper for callers that drive their own stiff solver: n <= 5 complex
+    entries on the host -- the BDF kernel evaluates its Jacobian in registers from the row tables."""
+    return 2.0 * np.einsum("kij,j->ki", np.asarray(M, dtype=np.complex128), np.asarray(A0, dtype=np.complex128)) + np.asarray(L)
+
+
+def solve_ode_for_a(ttm: float, theta: float, kappa1: float, kappa2: float, beta: float, volvol: float, phi: complex, psi: complex,
+                    is_spot_measure: bool = True, a_t0: Optional[np.ndarray] = None, expansion_order: ExpansionOrder = ExpansionOrder.FIRST,
+                    is_stiff_solver: bool = False, dense_output: bool = False, vol_backbone_eta: float = 1.0):
+    """coefficient ODEs of Eq. (4.14) for ONE transform point (affine_expansion.py:229-303).  Returns a SciPy ``OdeResult`` holding the two
+    ends of the integration (``t = [0, ttm]``, ``y[:, -1] = A(ttm)`` as the reference's callers read it); the accepted intermediate steps stay
+    on the device and a continuous extension is not built, so ``dense_output=True`` raises."""
+    if dense_output:
+        raise NotImplementedError("dense_output: the GPU solver returns A(ttm) only")
+    from scipy.integrate._ivp.ivp import OdeResult
+    n = get_expansion_n(ExpansionOrder(_order_code(expansion_order)))
+    y0 = np.zeros(n, dtype=np.complex128) if a_t0 is None else np.asarray(a_t0, dtype=np.complex128).reshape(n)
+    a_t1 = solve_a_ode_grid(np.array([phi], dtype=np.complex128), np.array([psi], dtype=np.complex128), ttm, theta, kappa1, kappa2, beta, volvol,
+                            is_spot_measure=is_spot_measure, a_t0=y0[None, :], is_stiff_solver=is_stiff_solver, expansion_order=expansion_order,
+                            vol_backbone_eta=vol_backbone_eta)[0]
+    return OdeResult(t=np.array([0.0, float(ttm)]), y=np.stack([y0, a_t1], axis=1), sol=None, t_events=None, y_events=None, nfev=0, njev=0, nlu=0,
+                     status=0, message="The solver successfully reached the end of the integration interval.", success=True)
+
+
+def solve_analytic_ode_for_a(ttm: float, theta: float, kappa1: float, kappa2: float, beta: float, volvol: float, phi: complex, psi: complex,
+                             is_spot_measure: bool, a_t0: Optional[np.ndarray] = None, expansion_order: ExpansionOrder = ExpansionOrder.FIRST,
+                             year_days: int = 260) -> np.ndarray:
+    """A(ttm) for ONE transform point by the semi-analytic scheme (affine_expansion.py:306-384)"""
+    a0 = None if a_t0 is None else np.asarray(a_t0, dtype=np.complex128).reshape(1, -1)
+    return solve_analytic_ode_grid_phi(np.array([phi], dtype=np.complex128), np.array([psi], dtype=np.complex128), ttm, theta, kappa1, kappa2, beta,
+                                       volvol, is_spot_measure=is_spot_measure, a_t0=a0, expansion_order=expansion_order, year_days=year_days)[0]

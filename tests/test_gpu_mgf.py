@@ -312,3 +312,48 @@ def test_bdf_branch_chain_prices_and_oracle(cuda_lib):
                              expansion_order=ExpansionOrder.SECOND, vol_backbone_eta=1.1)
     a_ref = omgf.logsv_bdf_a_grid(0.3, phi, psi, np.zeros((60, 5), complex), 1.0413, 3.1844, 3.058, 0.1514, 1.8458, False, 2, 1.1)
     np.testing.assert_allclose(a_gpu, a_ref, rtol=1e-10, atol=1e-11)
+
+
+def test_single_point_solver_entry_points(cuda_lib):
+    """solve_ode_for_a (RK45 and BDF), solve_analytic_ode_for_a and func_rhs_jac of the reference's interface (affine_expansion.py:209-384):
+    one transform point at a time == the corresponding rows of the grid goldens; the Jacobian == a central difference of func_rhs"""
+    from stochvolmodels_b200.pricers.logsv.affine_expansion import (ExpansionOrder, func_a_ode_quadratic_terms, func_rhs, func_rhs_jac,
+                                                                    solve_analytic_ode_for_a, solve_ode_for_a)
+    g = load_golden("logsv_bdf_branch.npz")
+    name = "quick_second"
+    sigma0, theta, k1, k2, beta, vv, order, spot, eta = g[f"{name}_params"]
+    phi, ttm = g[f"{name}_phi"], float(g["ttms"][0])
+    kw = dict(ttm=ttm, theta=theta, kappa1=k1, kappa2=k2, beta=beta, volvol=vv, psi=0j, is_spot_measure=bool(spot),
+              expansion_order=ExpansionOrder(int(order)), vol_backbone_eta=eta)
+    for j in (0, 17, 124):
+        sol = solve_ode_for_a(phi=phi[j], is_stiff_solver=True, **kw)
+        assert sol.success and sol.t[-1] == ttm and sol.y.shape == (5, 2)
+        np.testing.assert_allclose(sol.y[:, -1], g[f"{name}_a_0"][j], rtol=1e-10, atol=1e-11)
+        nxt = solve_ode_for_a(phi=phi[j], is_stiff_solver=True, a_t0=sol.y[:, -1], **{**kw, "ttm": float(g["ttms"][1]) - ttm})
+        np.testing.assert_allclose(nxt.y[:, -1], g[f"{name}_a_1"][j], rtol=1e-10, atol=1e-11)
+    with pytest.raises(NotImplementedError):
+        solve_ode_for_a(phi=phi[0], dense_output=True, **kw)
+    # RK45 branch: rows of the quickstart Fourier golden (first maturity)
+    q = load_golden("logsv_fourier_g1_quickstart.npz")
+    s0, th, a1, a2, be, vo = q["params"][:6]
+    for j in (1, 400):
+        sol = solve_ode_for_a(ttm=float(q["ttms"][0]), theta=th, kappa1=a1, kappa2=a2, beta=be, volvol=vo, phi=q["phi"][j], psi=0j,
+                              is_spot_measure=bool(q["is_spot"]), expansion_order=ExpansionOrder(int(q["order"])),
+                              vol_backbone_eta=float(q["etas"][0]))
+        np.testing.assert_allclose(sol.y[:, -1], q["a_t1_0"][j], rtol=1e-10, atol=1e-12)
+    # semi-analytic branch
+    ga = load_golden("logsv_analytic_branch.npz")
+    sigma0, theta, k1, k2, beta, vv, order, spot = ga["mild_second_params"]
+    phi_a = ga["mild_second_phi"][::8]
+    for j in (0, 60):
+        a = solve_analytic_ode_for_a(float(ga["ttms"][0]), theta, k1, k2, beta, vv, phi_a[j], 0j, bool(spot), expansion_order=ExpansionOrder(int(order)))
+        np.testing.assert_allclose(a, ga["mild_second_a_0"][j], rtol=1e-8, atol=1e-10)
+    # Jacobian
+    M, L, H = func_a_ode_quadratic_terms(theta, k1, k2, beta, vv, phi_a[5], 0.1 + 0j, is_spot_measure=True, expansion_order=ExpansionOrder.SECOND)
+    A = np.array([0.1 + 0.2j, -0.3 + 0.1j, 0.05j, 0.02, -0.01 + 0.03j])
+    J = func_rhs_jac(0.0, A, M, L, H)
+    h = 1e-6
+    for k in range(5):
+        e = np.zeros(5, dtype=np.complex128)
+        e[k] = h
+        np.testing.assert_allclose(J[:, k], (func_rhs(0.0, A + e, M, L, H) - func_rhs(0.0, A - e, M, L, H)) / (2 * h), rtol=1e-6, atol=1e-8)
