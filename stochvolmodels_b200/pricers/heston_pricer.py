@@ -143,3 +143,8 @@ def simulate_heston_x_vol_terminal(ttm: float, x0: np.ndarray, var0: np.ndarray,
     seed = engine.fresh_seed() if seed is None else int(seed)
     return engine.heston_terminal(_params_c(float(var0[0]), theta, kappa, rho, volvol), ttm, nb_path, nb_steps_per_year, seed,
                                   engine.mc_flags("fp64", gauss), _scheme_code(scheme))
+
+
+def v0_implied(v0: float, volvol: float, ttm: float) -> float:
+    """the reference's placeholder short-maturity adjustment of the initial variance (heston_pricer.py:384-390)"""
+    return v0 - volvol * volvol * ttm / 8.0

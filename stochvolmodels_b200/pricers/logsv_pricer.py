@@ -598,3 +598,17 @@ def logsv_mc_chain_pricer_fixed_randoms(ttms, forwards, discfactors, strikes_ttm
         if return_states:
             states.append((x.copy(), s.copy(), q.copy()))
     return (prices, stds, states) if return_states else (prices, stds)
+
+
+def v0_implied(atm: float, beta: float, volvol: float, theta: float, kappa1: float, ttm: float) -> float:
+    """short-maturity approximation of the initial volatility sigma0 from an ATM vol (reference logsv_pricer.py:638-661; host scalar helper).
+    Regular expansion ``atm - vartheta^2 ttm / 4`` when |beta| > 1 or beta ~ 0; otherwise the positive root of the quadratic in sigma0 the
+    reference solves."""
+    b2, vartheta2 = beta * beta, beta * beta + volvol * volvol
+    regular = atm - vartheta2 * ttm / 4.0
+    lead = 12.0 * beta * ttm
+    if abs(beta) > 1.0 or abs(lead) <= 1e-10:
+        return regular
+    half_b = 24.0 + b2 * ttm + 2.0 * vartheta2 * ttm - 12.0 * kappa1 * ttm
+    disc = half_b * half_b - 288.0 * beta * ttm * (theta * kappa1 * ttm - 2.0 * atm)
+    return (np.sqrt(disc) - half_b) / lead

@@ -275,3 +275,18 @@ def test_set_seed_makes_seedless_calls_reproducible():
     set_seed(None)
     d, e = engine.fresh_seed(), engine.fresh_seed()
     assert a == b and len(set(a)) == 3 and c != a[0] and d != e and all(0 <= s < 1 << 64 for s in a + [c, d, e])
+
+
+def test_v0_implied_short_maturity_helpers():
+    """the reference's assertions about v0_implied (its tests/test_logsv_characterization.py:680-700) + the Heston placeholder"""
+    from stochvolmodels_b200.pricers.heston_pricer import v0_implied as heston_v0
+    from stochvolmodels_b200.pricers.logsv_pricer import LOGSV_BTC_PARAMS as p, v0_implied
+    np.testing.assert_allclose(v0_implied(p.sigma0, 1.1, p.volvol, p.theta, p.kappa1, 0.02), p.sigma0 - (1.1 ** 2 + p.volvol ** 2) * 0.02 / 4.0)
+    np.testing.assert_allclose(v0_implied(p.sigma0, 0.0, p.volvol, p.theta, p.kappa1, 0.02), p.sigma0 - p.volvol ** 2 * 0.02 / 4.0)
+    v = v0_implied(p.sigma0, p.beta, p.volvol, p.theta, p.kappa1, 0.02)
+    assert np.isfinite(v) and abs(v - p.sigma0) < 0.05
+    # root of the reference's quadratic: 6 beta t v^2 + (24 + beta^2 t + 2 vartheta^2 t - 12 kappa1 t) v + 12 (theta kappa1 t - 2 atm) = 0
+    t, b = 0.02, p.beta
+    res = 6 * b * t * v * v + (24 + b * b * t + 2 * p.vartheta2 * t - 12 * p.kappa1 * t) * v + 12 * (p.theta * p.kappa1 * t - 2 * p.sigma0)
+    assert abs(res) < 1e-10
+    assert heston_v0(0.04, 0.5, 0.1) == 0.04 - 0.25 * 0.1 / 8.0
