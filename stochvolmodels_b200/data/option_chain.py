@@ -3,7 +3,9 @@
 Host-side data type only ("boundary input type").  It keeps the attributes the hot path reads --
 ``ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms`` (reference pricers/logsv_pricer.py:358-365, 412-427) -- with the
 reference's validation rules (data/option_chain.py:147-215) and constructors ``slice_to_chain`` (:230-245) and
-``get_uniform_chain`` (:462-492).  The pricers are duck-typed: a reference ``stochvolmodels.OptionChain`` works as well.
+``get_uniform_chain`` (:462-492), the slice views ``OptionSlice`` / ``get_slice`` / ``get_slices_as_chain`` (:72-124, 387-459) and the
+strike transforms ``to_forward_normalised_strikes`` / ``to_uniform_strikes`` (:348-385).  The pricers are duck-typed: a reference
+``stochvolmodels.OptionChain`` works as well.
 """
 from __future__ import annotations
 
@@ -29,6 +31,57 @@ def _validate_option_slice_data(strikes, optiontypes) -> int:
     return strikes.size
 
 
+def _check_quotes(name: str, values, size: int, strictly_positive: bool) -> np.ndarray:
+    """per-slice bid / ask arrays: finite, aligned with the strikes, positive (vols) or non-negative (prices) -- option_chain.py:33-51"""
+    v = np.asarray(values, dtype=float)
+    if v.shape != (size,):
+        raise ValueError(f"{name} must have the same length as strikes")
+    if not np.isfinite(v).all():
+        raise ValueError(f"{name} must contain only finite values")
+    if strictly_positive and (v <= 0.0).any():
+        raise ValueError(f"{name} must contain only positive values")
+    if not strictly_positive and (v < 0.0).any():
+        raise ValueError(f"{name} must contain only non-negative values")
+    return v
+
+
+@dataclass
+class OptionSlice:
+    """one maturity of a chain (reference data/option_chain.py:72-124): discount factor and rate are kept consistent, quotes validated"""
+    ttm: float
+    forward: float
+    strikes: np.ndarray
+    optiontypes: np.ndarray
+    id: str
+    discfactor: Optional[float] = None
+    discount_rate: Optional[float] = None
+    bid_ivs: Optional[np.ndarray] = None
+    ask_ivs: Optional[np.ndarray] = None
+    bid_prices: Optional[np.ndarray] = None
+    ask_prices: Optional[np.ndarray] = None
+
+    def __post_init__(self):
+        for name, value in (("ttm", self.ttm), ("forward", self.forward)):
+            if not np.isscalar(value) or not np.isfinite(value) or value <= 0.0:
+                raise ValueError(f"{name} must be a finite positive scalar")
+        size = _validate_option_slice_data(self.strikes, self.optiontypes)
+        if self.discfactor is not None:
+            if not np.isfinite(self.discfactor) or self.discfactor <= 0.0:
+                raise ValueError("discfactor must be a finite positive scalar")
+            self.discount_rate = -np.log(self.discfactor) / self.ttm
+        elif self.discount_rate is not None:
+            if not np.isfinite(self.discount_rate):
+                raise ValueError("discount_rate must be a finite scalar")
+            self.discfactor = np.exp(-self.discount_rate * self.ttm)
+        else:
+            self.discfactor, self.discount_rate = 1.0, 0.0
+        quotes = {name: _check_quotes(name, getattr(self, name), size, name.endswith("ivs"))
+                  for name in ("bid_ivs", "ask_ivs", "bid_prices", "ask_prices") if getattr(self, name) is not None}
+        for bid, ask in (("bid_ivs", "ask_ivs"), ("bid_prices", "ask_prices")):
+            if bid in quotes and ask in quotes and (quotes[bid] > quotes[ask]).any():
+                raise ValueError(f"{bid} must not exceed {ask}")
+
+
 @dataclass
 class OptionChain:
     ttms: np.ndarray
@@ -41,6 +94,9 @@ class OptionChain:
     ticker: Optional[str] = None
     bid_ivs: Optional[Sequence[np.ndarray]] = None
     ask_ivs: Optional[Sequence[np.ndarray]] = None
+    bid_prices: Optional[Sequence[np.ndarray]] = None
+    ask_prices: Optional[Sequence[np.ndarray]] = None
+    forwards0: Optional[np.ndarray] = None          # the forwards a forward-normalised chain was divided by
 
     def __post_init__(self):
         self.ttms = np.asarray(self.ttms, dtype=float)
@@ -92,6 +148,55 @@ class OptionChain:
         return cls(ttms=ttms, ids=ids, forwards=forwards, strikes_ttms=[strikes for _ in ttms],
                    bid_ivs=[flat_vol * np.ones_like(strikes) for _ in ttms], ask_ivs=[flat_vol * np.ones_like(strikes) for _ in ttms],
                    optiontypes_ttms=[np.where(strikes >= forward, "C", "P") for forward in forwards])
+
+    # ---- slice views and strike transforms (reference :217-227, 348-459) -------------------------------------------------------
+    def _per_slice(self, name: str, idx: int):
+        values = getattr(self, name)
+        return None if values is None else values[idx]
+
+    def _index_of(self, id) -> int:
+        if self.ids is None:
+            raise ValueError("the chain has no ids")
+        return list(self.ids).index(id)
+
+    def print(self) -> None:
+        for name in ("ttms", "forwards", "strikes_ttms", "optiontypes_ttms", "ids", "bid_ivs", "ask_ivs"):
+            print(f"{name}:\n{getattr(self, name)}")
+
+    def get_slice(self, id: str) -> OptionSlice:
+        k = self._index_of(id)
+        return OptionSlice(id=self.ids[k], ttm=float(self.ttms[k]), forward=float(self.forwards[k]), strikes=self.strikes_ttms[k],
+                           optiontypes=self.optiontypes_ttms[k], discfactor=float(self.discfactors[k]),
+                           **{q: self._per_slice(q, k) for q in ("bid_ivs", "ask_ivs", "bid_prices", "ask_prices")})
+
+    @classmethod
+    def get_slices_as_chain(cls, option_chain: "OptionChain", ids: Sequence[str]) -> "OptionChain":
+        """the sub-chain of the maturities named in ``ids`` -- in CHAIN order when several are asked for (``np.isin`` semantics of the
+        reference), labelled with ``ids`` as given"""
+        if len(ids) == 1:
+            keep = [option_chain._index_of(ids[0])]
+        else:
+            keep = list(np.flatnonzero(np.isin(option_chain.ids, ids)))
+        pick = lambda name: None if getattr(option_chain, name) is None else [getattr(option_chain, name)[k] for k in keep]
+        return cls(ids=ids, ttms=option_chain.ttms[keep], ticker=option_chain.ticker, forwards=option_chain.forwards[keep],
+                   strikes_ttms=pick("strikes_ttms"), optiontypes_ttms=pick("optiontypes_ttms"), discfactors=option_chain.discfactors[keep],
+                   bid_ivs=pick("bid_ivs"), ask_ivs=pick("ask_ivs"), bid_prices=pick("bid_prices"), ask_prices=pick("ask_prices"))
+
+    @classmethod
+    def to_forward_normalised_strikes(cls, obj: "OptionChain") -> "OptionChain":
+        """strikes divided by their forward, forwards set to 1 (the originals kept in ``forwards0``); quotes in vols are unchanged"""
+        return cls(ttms=obj.ttms, forwards=np.ones_like(obj.forwards), strikes_ttms=[k / f for k, f in zip(obj.strikes_ttms, obj.forwards)],
+                   optiontypes_ttms=obj.optiontypes_ttms, discfactors=obj.discfactors, ticker=obj.ticker, ids=obj.ids, bid_ivs=obj.bid_ivs,
+                   ask_ivs=obj.ask_ivs, forwards0=obj.forwards)
+
+    @classmethod
+    def to_uniform_strikes(cls, obj: "OptionChain", num_strikes: int = 21) -> "OptionChain":
+        """``num_strikes`` equally spaced strikes between the first and last strike of every slice, calls at and above the forward, puts
+        below; the quotes no longer apply and are dropped"""
+        grids = [np.linspace(k[0], k[-1], num_strikes) for k in obj.strikes_ttms]
+        return cls(ttms=obj.ttms, forwards=obj.forwards, strikes_ttms=grids,
+                   optiontypes_ttms=[np.where(g >= f, "C", "P") for g, f in zip(grids, obj.forwards)], discfactors=obj.discfactors,
+                   ticker=obj.ticker, ids=obj.ids, bid_ivs=None, ask_ivs=None)
 
     def get_mid_vols(self) -> Optional[List[np.ndarray]]:
         if self.bid_ivs is not None and self.ask_ivs is not None:
@@ -169,5 +274,16 @@ def get_btc_test_chain_data() -> OptionChain:
         np.array([35000., 40000., 60000., 80000., 100000., 120000., 150000., 250000., 300000.]))
     optiontypes_ttms = (np.array(["P"] * 6 + ["C"] * 6), np.array(["P"] * 6 + ["C"] * 7), np.array(["P"] * 7 + ["C"] * 8),
                         np.array(["P"] * 3 + ["C"] * 6))
+    # quoted implied vols of the same snapshot (market data): what the calibration examples of the reference fit to
+    bid_ivs = (
+        np.array([0.9231, 0.8835, 0.8695, 0.8621, 0.855, 0.8589, 0.8822, 0.8856, 0.8944, 0.8996, 0.9607, 0.9718]),
+        np.array([0.9475, 0.9211, 0.8917, 0.8863, 0.8873, 0.8913, 0.9012, 0.9102, 0.9244, 0.9377, 0.9494, 0.9755, 1.0317]),
+        np.array([0.9882, 0.9595, 0.94, 0.9247, 0.914, 0.9131, 0.9109, 0.9168, 0.9244, 0.9305, 0.941, 0.9544, 0.9682, 1.047, 1.0887]),
+        np.array([1.0052, 0.981, 0.9593, 0.9722, 0.9924, 1.013, 1.0419, 1.1222, 1.1489]))
+    ask_ivs = (
+        np.array([0.9399, 0.8944, 0.8967, 0.8856, 0.8744, 0.8774, 0.9006, 0.9047, 0.9144, 0.9202, 0.9762, 1.0151]),
+        np.array([0.972, 0.9401, 0.9092, 0.9014, 0.9041, 0.9079, 0.917, 0.9264, 0.9417, 0.952, 0.9602, 0.9899, 1.0585]),
+        np.array([1.0167, 0.9739, 0.9568, 0.9372, 0.9285, 0.9261, 0.9261, 0.9225, 0.9358, 0.9362, 0.9558, 0.9637, 0.9823, 1.0664, 1.1144]),
+        np.array([1.0204, 0.9968, 0.9683, 0.976, 0.9963, 1.0173, 1.047, 1.1411, 1.1736]))
     return OptionChain(ids=np.array(["2w", "1m", "2m", "3m"]), ttms=ttms, ticker="BTC", forwards=forwards,
-                       strikes_ttms=strikes_ttms, optiontypes_ttms=optiontypes_ttms, discfactors=np.ones(4))
+                       strikes_ttms=strikes_ttms, optiontypes_ttms=optiontypes_ttms, discfactors=np.ones(4), bid_ivs=bid_ivs, ask_ivs=ask_ivs)

@@ -758,6 +758,35 @@ HAWKES_KEYS = ("mu", "sigma", "shift_p", "mean_p", "shift_m", "mean_m", "lambda_
                "kappa_m", "beta1_m", "beta2_m")
 
 
+def chain_transforms() -> None:
+    """OptionChain slice views and strike transforms on the BTC sample chain -> option_chain_transforms.npz.
+    python tests/golden/make_golden.py --only-chain"""
+    _import_reference()
+    from stochvolmodels.data.option_chain import OptionChain
+    from stochvolmodels.data.sample_option_chains import get_btc_test_chain_data
+    c = get_btc_test_chain_data()
+    out = dict(ids=np.asarray(c.ids), ttms=c.ttms, forwards=c.forwards)
+    for m in range(len(c.ttms)):
+        out[f"bid_ivs_{m}"], out[f"ask_ivs_{m}"], out[f"strikes_{m}"] = c.bid_ivs[m], c.ask_ivs[m], c.strikes_ttms[m]
+    n = OptionChain.to_forward_normalised_strikes(c)
+    u = OptionChain.to_uniform_strikes(c, num_strikes=7)
+    for m in range(len(c.ttms)):
+        out[f"norm_strikes_{m}"] = n.strikes_ttms[m]
+        out[f"uni_strikes_{m}"], out[f"uni_types_{m}"] = u.strikes_ttms[m], np.asarray(u.optiontypes_ttms[m])
+    out["norm_forwards"], out["norm_forwards0"] = n.forwards, n.forwards0
+    sub = OptionChain.get_slices_as_chain(c, ids=["3m", "1m"])
+    out["sub_ttms"], out["sub_forwards"], out["sub_ids"] = sub.ttms, sub.forwards, np.asarray(sub.ids)
+    out["sub_strikes_0"], out["sub_bid_1"] = sub.strikes_ttms[0], sub.bid_ivs[1]
+    one = OptionChain.get_slices_as_chain(c, ids=["2m"])
+    out["one_ttms"], out["one_strikes"] = one.ttms, one.strikes_ttms[0]
+    sl = c.get_slice("2w")
+    out["slice_scalars"] = np.array([sl.ttm, sl.forward, sl.discfactor, sl.discount_rate])
+    out["slice_ask"] = sl.ask_ivs
+    out["mid_vols_0"] = c.get_mid_vols()[0]
+    np.savez(os.path.join(OUT, "option_chain_transforms.npz"), **out)
+    print("wrote option_chain_transforms.npz")
+
+
 def params_helpers() -> None:
     """LogSvParams helper methods (spatial grids, steady-state exponents, vol-moment generator) and the vol-moment / variance-swap functions of
     pricers/logsv/vol_moments_ode.py for three parameter sets -> logsv_params_helpers.npz.   python tests/golden/make_golden.py --only-helpers"""
@@ -797,6 +826,9 @@ def _chain(ttms, fw, df, K, T):
 
 
 if __name__ == "__main__":
+    if "--only-chain" in sys.argv:
+        chain_transforms()
+        sys.exit(0)
     if "--only-helpers" in sys.argv:
         params_helpers()
         sys.exit(0)

@@ -290,3 +290,50 @@ def test_v0_implied_short_maturity_helpers():
     res = 6 * b * t * v * v + (24 + b * b * t + 2 * p.vartheta2 * t - 12 * p.kappa1 * t) * v + 12 * (p.theta * p.kappa1 * t - 2 * p.sigma0)
     assert abs(res) < 1e-10
     assert heston_v0(0.04, 0.5, 0.1) == 0.04 - 0.25 * 0.1 / 8.0
+
+
+def test_option_chain_slice_views_and_strike_transforms_vs_reference_golden(capsys):
+    """OptionChain.get_slice / get_slices_as_chain / to_forward_normalised_strikes / to_uniform_strikes and the BTC sample chain's market
+    quotes against the reference's own outputs (option_chain_transforms.npz); OptionSlice validation"""
+    from conftest import load_golden
+    from stochvolmodels_b200 import OptionChain, get_btc_test_chain_data
+    from stochvolmodels_b200.data.option_chain import OptionSlice
+    g = load_golden("option_chain_transforms.npz")
+    c = get_btc_test_chain_data()
+    np.testing.assert_array_equal(np.asarray(c.ids), g["ids"])
+    np.testing.assert_array_equal(c.ttms, g["ttms"])
+    np.testing.assert_array_equal(c.forwards, g["forwards"])
+    n, u = OptionChain.to_forward_normalised_strikes(c), OptionChain.to_uniform_strikes(c, num_strikes=7)
+    for m in range(4):
+        np.testing.assert_array_equal(c.strikes_ttms[m], g[f"strikes_{m}"])
+        np.testing.assert_array_equal(c.bid_ivs[m], g[f"bid_ivs_{m}"])
+        np.testing.assert_array_equal(c.ask_ivs[m], g[f"ask_ivs_{m}"])
+        np.testing.assert_array_equal(n.strikes_ttms[m], g[f"norm_strikes_{m}"])
+        np.testing.assert_array_equal(u.strikes_ttms[m], g[f"uni_strikes_{m}"])
+        np.testing.assert_array_equal(np.asarray(u.optiontypes_ttms[m]), g[f"uni_types_{m}"])
+    np.testing.assert_array_equal(n.forwards, g["norm_forwards"])
+    np.testing.assert_array_equal(n.forwards0, g["norm_forwards0"])
+    assert u.bid_ivs is None and n.bid_ivs is c.bid_ivs
+    sub = OptionChain.get_slices_as_chain(c, ids=["3m", "1m"])
+    np.testing.assert_array_equal(sub.ttms, g["sub_ttms"])
+    np.testing.assert_array_equal(sub.forwards, g["sub_forwards"])
+    np.testing.assert_array_equal(np.asarray(sub.ids), g["sub_ids"])
+    np.testing.assert_array_equal(sub.strikes_ttms[0], g["sub_strikes_0"])
+    np.testing.assert_array_equal(sub.bid_ivs[1], g["sub_bid_1"])
+    one = OptionChain.get_slices_as_chain(c, ids=["2m"])
+    np.testing.assert_array_equal(one.ttms, g["one_ttms"])
+    np.testing.assert_array_equal(one.strikes_ttms[0], g["one_strikes"])
+    sl = c.get_slice("2w")
+    np.testing.assert_allclose([sl.ttm, sl.forward, sl.discfactor, sl.discount_rate], g["slice_scalars"], rtol=0, atol=0)
+    np.testing.assert_array_equal(sl.ask_ivs, g["slice_ask"])
+    np.testing.assert_array_equal(c.get_mid_vols()[0], g["mid_vols_0"])
+    with pytest.raises(ValueError):
+        c.get_slice("9y")
+    k, t = np.array([0.9, 1.0]), np.array(["P", "C"])
+    assert OptionSlice(ttm=0.5, forward=1.0, strikes=k, optiontypes=t, id="x", discount_rate=0.02).discfactor == np.exp(-0.01)
+    for bad in (dict(ttm=-1.0), dict(bid_ivs=np.array([0.3, 0.2]), ask_ivs=np.array([0.2, 0.3])), dict(bid_prices=np.array([-1.0, 0.1])),
+                dict(ask_ivs=np.array([0.2])), dict(discfactor=0.0)):
+        with pytest.raises(ValueError):
+            OptionSlice(**{**dict(ttm=0.5, forward=1.0, strikes=k, optiontypes=t, id="x"), **bad})
+    c.print()
+    assert "strikes_ttms" in capsys.readouterr().out
