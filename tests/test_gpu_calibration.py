@@ -253,3 +253,20 @@ def test_logsv_calibration_mc_engine_philox_common_random_numbers(cuda_lib):
     _, _, fit_iv = engine.logsv_mc_chain_batch([_params_c(fit)], ttms, fw, np.ones(2), None, [K5, K5], [T5, T5], 200_000, 360, True, 10,
                                                engine.mc_flags("fp64", "fp32"))
     np.testing.assert_allclose(fit_iv[0], iv[0], atol=5e-3)
+
+
+def test_calibration_to_the_btc_market_quotes_recovers_the_references_published_fit(cuda_lib):
+    """the reference ships LOGSV_BTC_PARAMS as its fit of the BTC sample chain (logsv_pricer.py:102).  Calibrating to the chain's bid/ask
+    vols on the GPU, from a perturbed start, lands on those values to the precision they are quoted at, with an objective no worse than
+    at the published point."""
+    from stochvolmodels_b200 import LOGSV_BTC_PARAMS as ref, LogSvParams, LogSVPricer, LogsvModelCalibrationType, get_btc_test_chain_data
+    chain, pricer = get_btc_test_chain_data(), LogSVPricer()
+    start = LogSvParams(sigma0=0.7, theta=0.9, kappa1=ref.kappa1, kappa2=ref.kappa2, beta=0.0, volvol=1.4)
+    fit, info = pricer.calibrate_model_params_to_chain(chain, start, model_calibration_type=LogsvModelCalibrationType.PARAMS4, return_info=True)
+    at_ref = pricer.calibrate_model_params_to_chain(chain, ref, model_calibration_type=LogsvModelCalibrationType.PARAMS4, return_info=True)[1]
+    assert info["fun"] <= at_ref["fun"] * (1 + 1e-3)
+    for name, tol in (("sigma0", 0.03), ("theta", 0.03), ("beta", 0.03), ("volvol", 0.08)):
+        assert abs(getattr(fit, name) - getattr(ref, name)) < tol, (name, getattr(fit, name), getattr(ref, name))
+    model = pricer.compute_model_ivols_for_chain(chain, fit)
+    rms = np.sqrt(np.mean(np.concatenate([a - b for a, b in zip(model, chain.get_mid_vols())]) ** 2))
+    assert rms < 0.02          # 1.5 vol points on a 49-quote BTC surface with vols of 0.85 .. 1.15
