@@ -224,6 +224,34 @@ class OptionChain:
             out.append(forward * np.exp(-0.5 * d1 * d1) / np.sqrt(2.0 * np.pi) * np.sqrt(ttm))
         return out
 
+    def get_chain_deltas(self) -> List[np.ndarray]:
+        """Black-76 forward deltas at the mid vols, N(d1) for calls and N(d1) - 1 for puts (inverse options take the vanilla delta of their
+        payoff side) -- reference :254-261 -> third-party ``vanilla_option_pricers.bsm.compute_bsm_vanilla_deltas_ttms``, absent from the
+        reference tree: the convention is the textbook one, its bit-level parity is unpinned like the Black inversion's."""
+        from scipy.special import ndtr
+        out = []
+        for ttm, forward, strikes, types, vols in zip(self.ttms, self.forwards, self.strikes_ttms, self.optiontypes_ttms, self.get_mid_vols()):
+            sdev = vols * np.sqrt(ttm)
+            n_d1 = ndtr(np.log(forward / strikes) / sdev + 0.5 * sdev)
+            out.append(np.where(np.isin(types, ("C", "IC")), n_d1, n_d1 - 1.0))
+        return out
+
+    def get_chain_skews(self, delta: float = 0.25) -> np.ndarray:
+        """(vol of the ``delta`` put - vol of the ``delta`` call) / ATM vol per slice, each read off the slice's own quotes by linear
+        interpolation in delta (reference :288-316); a slice needs quotes on both sides"""
+        skews = np.zeros(self.ttms.size)
+        for m, (deltas, vols, types, atm) in enumerate(zip(self.get_chain_deltas(), self.get_mid_vols(), self.optiontypes_ttms,
+                                                           self.get_chain_atm_vols())):
+            sides = []
+            for flag, target in (("P", -delta), ("C", delta)):
+                pick = np.asarray(types) == flag
+                if not pick.any():
+                    raise ValueError("skew interpolation requires both put and call quotes")
+                order = np.argsort(deltas[pick])
+                sides.append(np.interp(target, deltas[pick][order], vols[pick][order]))
+            skews[m] = (sides[0] - sides[1]) / atm
+        return skews
+
     def get_slice_varswap_strikes(self, floor_with_atm_vols: bool = True):
         """variance-swap VOL per maturity by static replication from the quoted strip (reference data/option_chain.py:402-426 with
         utils/var_swap_pricer.py:8-56): K_var = (2/T) sum_i dk_i O(K_i)/K_i^2 - (F/K_atm - 1)^2 / T with Black mid prices O (puts below

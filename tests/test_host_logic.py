@@ -337,3 +337,29 @@ def test_option_chain_slice_views_and_strike_transforms_vs_reference_golden(caps
             OptionSlice(**{**dict(ttm=0.5, forward=1.0, strikes=k, optiontypes=t, id="x"), **bad})
     c.print()
     assert "strikes_ttms" in capsys.readouterr().out
+
+
+def test_chain_deltas_and_skews():
+    """Black-76 deltas at the mid vols (put-call parity in delta, monotone in strike) and the delta-interpolated skew: on a flat-vol chain the
+    skew is zero, on a downward-sloping smile it is positive; a one-sided slice raises like the reference (option_chain.py:301-302)"""
+    from stochvolmodels_b200 import OptionChain, get_btc_test_chain_data
+    c = get_btc_test_chain_data()
+    d = c.get_chain_deltas()
+    for m in range(4):
+        puts = np.asarray(c.optiontypes_ttms[m]) == "P"
+        assert np.all(d[m][puts] < 0) and np.all(d[m][~puts] > 0) and np.all(np.abs(d[m]) < 1)
+        n_d1 = np.where(puts, d[m] + 1.0, d[m])                   # N(d1) falls with the strike
+        assert np.all(np.diff(n_d1) < 0)
+    assert c.get_chain_skews(0.25).shape == (4,)
+    K = np.linspace(0.7, 1.4, 15)
+    types = np.where(K >= 1.0, "C", "P")
+    flat = OptionChain(ttms=np.array([0.25]), forwards=np.ones(1), strikes_ttms=[K], optiontypes_ttms=[types], bid_ivs=[0.5 * np.ones(15)],
+                       ask_ivs=[0.5 * np.ones(15)])
+    np.testing.assert_allclose(flat.get_chain_skews(), 0.0, atol=1e-15)
+    smile = 0.5 - 0.3 * np.log(K)
+    down = OptionChain(ttms=np.array([0.25]), forwards=np.ones(1), strikes_ttms=[K], optiontypes_ttms=[types], bid_ivs=[smile], ask_ivs=[smile])
+    assert down.get_chain_skews()[0] > 0.05
+    calls_only = OptionChain(ttms=np.array([0.25]), forwards=np.ones(1), strikes_ttms=[K], optiontypes_ttms=[np.array(["C"] * 15)], bid_ivs=[smile],
+                             ask_ivs=[smile])
+    with pytest.raises(ValueError, match="both put and call"):
+        calls_only.get_chain_skews()
