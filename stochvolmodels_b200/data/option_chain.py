@@ -127,8 +127,18 @@ class OptionChain:
         else:
             self.discfactors = np.ones_like(ttms)
             self.discount_rates = np.zeros_like(ttms)
-        for strikes, optiontypes in zip(self.strikes_ttms, self.optiontypes_ttms):
-            _validate_option_slice_data(strikes, optiontypes)
+        if self.forwards0 is not None:
+            _check_quotes("forwards0", self.forwards0, ttms.size, True)
+        quoted = [q for q in ("bid_ivs", "ask_ivs", "bid_prices", "ask_prices") if getattr(self, q) is not None]
+        for q in quoted:
+            if len(getattr(self, q)) != ttms.size:
+                raise ValueError(f"{q} and ttms must have the same length")
+        for m, (strikes, optiontypes) in enumerate(zip(self.strikes_ttms, self.optiontypes_ttms)):
+            size = _validate_option_slice_data(strikes, optiontypes)
+            ok = {q: _check_quotes(f"{q}[{m}]", getattr(self, q)[m], size, q.endswith("ivs")) for q in quoted}     # reference :187-215
+            for bid, ask in (("bid_ivs", "ask_ivs"), ("bid_prices", "ask_prices")):
+                if bid in ok and ask in ok and (ok[bid] > ok[ask]).any():
+                    raise ValueError(f"{bid}[{m}] must not exceed {ask}[{m}]")
 
     @classmethod
     def slice_to_chain(cls, ttm: float, forward: float, strikes: np.ndarray, optiontypes: np.ndarray,

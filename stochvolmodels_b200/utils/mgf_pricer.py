@@ -97,3 +97,17 @@ def compute_integration_weights(var_grid: np.ndarray, is_simpson: bool = True) -
     w = np.full(p.size, h[0])
     w[0] = w[-1] = 0.5 * h[0]
     return w
+
+
+def _compute_legacy_pricer_weights(var_grid: np.ndarray, is_simpson: bool = True) -> np.ndarray:
+    """the weights the pricing formulas actually use (reference utils/mgf_pricer.py:158-171; the CUDA sum kernels build the same pattern in
+    registers): Simpson 1,4,2,...,4,1 scaled by h/3 WITHOUT the odd-size check -- on an even grid the last weight is 4h/3 -- or, without
+    Simpson, the first half step followed by the forward differences."""
+    p = np.imag(np.asarray(var_grid))
+    if is_simpson:
+        pattern = np.where(np.arange(p.size) % 2 == 1, 4.0, 2.0)
+        pattern[0] = 1.0
+        if p.size % 2 == 1:
+            pattern[-1] = 1.0
+        return (p[1] - p[0]) / 3.0 * pattern
+    return np.concatenate(([0.5 * (p[1] - p[0])], np.diff(p)))
