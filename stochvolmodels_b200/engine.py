@@ -515,6 +515,18 @@ def bsm_implied_vols(ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms
     return C.split_chain(ivols, offsets)
 
 
+def infer_bsm_ivols_from_model_chain_prices(ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms, model_prices_ttms):
+    """the chain inversion the reference delegates to its third-party Black package (data/option_chain.py:340-345), keyword for keyword"""
+    return bsm_implied_vols(ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms, model_prices_ttms)
+
+
+def infer_bsm_ivols_from_slice_prices(ttm: float, forward: float, strikes, optiontypes, model_prices, discfactor: float = 1.0) -> np.ndarray:
+    """Black-76 implied vols of one slice on the GPU (NaN where a price is outside the no-arbitrage bounds) -- the slice form of the same
+    third-party call, used by ModelPricer.price_slice-style callers"""
+    return bsm_implied_vols(np.array([ttm]), np.array([forward]), np.array([discfactor]), [np.asarray(strikes, dtype=np.float64)],
+                            [np.asarray(optiontypes)], [np.asarray(model_prices, dtype=np.float64)])[0]
+
+
 def logsv_vol_paths(params: C.LogsvParamsC, ttm: float, nb_path: int, nb_steps_per_year: int, is_spot_measure: bool, seed: int,
                     brownians=None):
     from .utils.funcs import set_time_grid

@@ -198,6 +198,13 @@ def test_gpu_black_implied_vols(cuda_lib):
     out = chain.compute_model_ivols_from_chain_data([np.array([0.197330882838064, 1.5])])[0]
     np.testing.assert_allclose(out[0], 0.999577, rtol=5e-6)            # examples/getting_started/quickstart.py:44
     assert np.isnan(out[1])                                              # above the no-arbitrage bound
+    # the third-party entry points the reference re-exports, keyword for keyword (slice and chain form)
+    import stochvolmodels_b200 as sv
+    one = sv.infer_bsm_ivols_from_slice_prices(ttm=ttms[1], forward=fw[1], strikes=K, optiontypes=types, model_prices=prices[1], discfactor=df[1])
+    np.testing.assert_array_equal(one, iv[1])
+    whole = sv.infer_bsm_ivols_from_model_chain_prices(ttms=ttms, forwards=fw, discfactors=df, strikes_ttms=[K] * 3, optiontypes_ttms=[types] * 3,
+                                                       model_prices_ttms=prices)
+    np.testing.assert_array_equal(whole[2], iv[2])
 
 
 def test_mc_chain_implied_vols_api(cuda_lib):

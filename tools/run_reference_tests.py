@@ -43,6 +43,7 @@ ALIASES = {
 }
 DEFAULT_FILES = ["test_heston_characterization", "test_numerical_utilities", "test_logsv_characterization", "test_model_calibration_contracts",
                  "test_option_chain_characterization", "test_mgf_pricer_identities", "test_rough_logsv_pricer_regression"]
+# test_rough_logsv_characterization: 2 of 9 pass -- the other 7 exercise the rough kernel's quadrature optimiser (european_rule), not rebuilt
 
 
 # modules of the reference this package does not rebuild: importable as empty placeholders so that the test MODULE can be collected and only the
