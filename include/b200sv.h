@@ -243,6 +243,19 @@ int b200sv_rough_logsv_mc_chain(const b200sv_logsv_params* params, int B, int n_
 int b200sv_hawkesjd_mc_chain(const b200sv_hawkes_params* params, int M, const double* ttms, const double* forwards, const double* discfactors,
                              const int* offsets, const double* strikes, const int8_t* types, long long nb_path, int variable_type, uint64_t seed,
                              int flags, double* prices_out, double* stderr_out);
+/* Hawkes jump-diffusion, Fourier route.  Replaces hawkesjd_chain_pricer (pricers/hawkes_jd_pricer.py:365-417) and, with a finite
+ * risk_premia_gamma, hawkesjd_chain_pricer_with_risk_premia (:420-484) incl. hawkesjd_forwards_under_risk_kernel (:487-515),
+ * compute_hawkes_a_mgf_grid / solve_ode_for_a (:518-641: SciPy RK45 per transform point) and the slice pricers of utils/mgf_pricer.py
+ * (:174-221, :273-320).  P <= 0: 500 grid points; vol_scaler <= 0: clip(sigma, 0.2, 0.5) sqrt(min(min ttm, 1/12)) (:360-362);
+ * risk_premia_gamma = NaN: no risk kernel.  a_out [M][P][3] complex128, log_mgf_out [M][P] complex128, normalizers_out / gamma_forwards_out
+ * [M] are optional. */
+int b200sv_hawkesjd_price_chain(const b200sv_hawkes_params* params, int M, const double* ttms, const double* forwards, const double* discfactors,
+                                const int* offsets, const double* strikes, const int8_t* types, int is_spot_measure, double vol_scaler, int P,
+                                double risk_premia_gamma, double* prices_out, double* a_out, double* log_mgf_out, double* normalizers_out,
+                                double* gamma_forwards_out);
+/* slice_pricer_with_mgf_grid_with_gamma (utils/mgf_pricer.py:273-320) on caller-supplied grids (complex128 as interleaved doubles) */
+int b200sv_fourier_gamma(const double* log_mgf, const double* phi, int P, double risk_premia_gamma, double forward, double normalizer,
+                         double gamma_forward, const double* strikes, const int8_t* types, int J, int is_spot_measure, double* prices_out);
 int b200sv_hawkesjd_terminal(const b200sv_hawkes_params* params, double ttm, long long nb_path, uint64_t seed, int flags, int slice_index,
                              int use_initial_arrays, double* x_inout, double* lambda_p_inout, double* lambda_m_inout);
 int b200sv_hawkesjd_step_fixed(double* x, double* lambda_p, double* lambda_m, const double* W0, const double* U_P, const double* U_M,

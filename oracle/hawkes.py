@@ -61,3 +61,105 @@ def chain_prices(params: dict, ttms, forwards, discfactors, strikes_ttms, types_
         prices.append(p)
         stds.append(e)
     return prices, stds
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# Fourier route (hawkes_jd_pricer.py:365-641), pinned by tests/golden/hawkes_fourier.npz (make_golden.py --only-hawkes-fourier)
+#   solve_ode_for_a            :582-641   Riccati system for (a0, a_p, a_m) per transform point, SciPy RK45 with default tolerances
+#   compute_hawkes_a_mgf_grid  :518-547   log-MGF = a0 + a_p lambda_p + a_m lambda_m
+#   hawkesjd_chain_pricer      :365-417   500-point grid, vol_scaler = clip(sigma, 0.2, 0.5) sqrt(min(ttm_min, 1/12)), A carried over maturities
+#   ..._with_risk_premia       :420-515   grid on Re = -1/2 - gamma, normalisers / forwards under the risk kernel from two single-point solves
+# ---------------------------------------------------------------------------------------------------------------------------------
+MAX_PHI = 500                 # :37
+
+
+def fourier_vol_scaler(sigma: float, ttm_min: float) -> float:
+    return float(np.clip(sigma, 0.2, 0.5) * np.sqrt(min(ttm_min, 1.0 / 12.0)))          # :360-362
+
+
+class HawkesRhs:
+    """right-hand side of :607-626 for rows of A (one row per transform point)"""
+
+    def __init__(self, p: dict, phi: np.ndarray, psi: np.ndarray):
+        self.p, self.phi, self.psi = p, np.asarray(phi, dtype=np.complex128), np.asarray(psi, dtype=np.complex128)
+        self.comp_p = np.exp(p["shift_p"]) / (1.0 - p["mean_p"]) - 1.0              # HawkesJDParams.__post_init__ :67-70
+        self.comp_m = np.exp(p["shift_m"]) / (1.0 - p["mean_m"]) - 1.0
+
+    def __call__(self, A: np.ndarray, rows=None) -> np.ndarray:
+        """``rows``: the grid points the rows of A belong to (mgf.rk45_grid passes the active subset)"""
+        p = self.p
+        phi, psi = (self.phi, self.psi) if rows is None else (self.phi[rows], self.psi[rows])
+        zp = phi - p["beta1_p"] * A[:, 1] - p["beta1_m"] * A[:, 2]
+        zm = phi - p["beta2_p"] * A[:, 1] - p["beta2_m"] * A[:, 2]
+        j_p = np.exp(-p["shift_p"] * zp) / (1.0 + p["mean_p"] * zp) - 1.0
+        j_m = np.exp(-p["shift_m"] * zm) / (1.0 + p["mean_m"] * zm) - 1.0
+        out = np.empty_like(A)
+        out[:, 0] = p["kappa_p"] * p["theta_p"] * A[:, 1] + p["kappa_m"] * p["theta_m"] * A[:, 2] + np.square(p["sigma"]) * (0.5 * (phi + 1.0) * phi - psi)
+        out[:, 1] = j_p - p["kappa_p"] * A[:, 1] + self.comp_p * phi
+        out[:, 2] = j_m - p["kappa_m"] * A[:, 2] + self.comp_m * phi
+        return out
+
+
+def a_mgf_grid(dtau: float, phi: np.ndarray, p: dict, a_t0: np.ndarray = None, psi: np.ndarray = None):
+    """(a_t1 [P, 3], log_mgf [P]) of compute_hawkes_a_mgf_grid"""
+    from . import mgf as _mgf
+    phi = np.asarray(phi, dtype=np.complex128)
+    psi = np.zeros_like(phi) if psi is None else psi
+    a_t0 = np.zeros((phi.shape[0], 3), dtype=np.complex128) if a_t0 is None else a_t0
+    a_t1 = _mgf.rk45_grid(HawkesRhs(p, phi, psi), a_t0, float(dtau))
+    return a_t1, a_t1[:, 0] + a_t1[:, 1] * p["lambda_p"] + a_t1[:, 2] * p["lambda_m"]
+
+
+def forwards_under_risk_kernel(p: dict, gamma: float, ttms, forwards):
+    """(normalizers, gamma_forwards) of :487-515: two single-point solves per maturity, each restarted from A = 0"""
+    norm, fwd = np.ones(len(ttms)), np.ones(len(ttms))
+    for m, (ttm, f) in enumerate(zip(ttms, forwards)):
+        lm0 = a_mgf_grid(ttm, np.array([-gamma + 0j]), p)[1]
+        lm1 = a_mgf_grid(ttm, np.array([-gamma - 1.0 + 0j]), p)[1]
+        norm[m] = 1.0 / np.exp(lm0[0].real)
+        fwd[m] = f * np.exp(lm1[0].real) * norm[m]
+    return norm, fwd
+
+
+def gamma_slice_prices(log_mgf, phi, gamma, forward, normalizer, gamma_forward, strikes, types):
+    """slice_pricer_with_mgf_grid_with_gamma (utils/mgf_pricer.py:273-320).  Its fast branch tests Re(phi) == +(1/2 + gamma) while the grid
+    sits on -(1/2 + gamma), so the general weights are what runs; the discount factor is not applied (both reproduced)."""
+    from . import mgf as _mgf
+    dp = _mgf.legacy_simpson_weights(phi)
+    if np.all(np.abs(np.real(phi) - (0.5 + gamma)) < 1e-10):
+        w = (dp / np.pi) / (np.imag(phi) ** 2 + 0.25) + 0j
+    else:
+        w = -(dp / np.pi) / ((phi + gamma + 1.0) * (phi + gamma))
+    out = np.zeros(len(strikes))
+    for j, (k, ty) in enumerate(zip(strikes, types)):
+        capped = np.nansum(np.real(w * np.exp(-np.log(forward / k) * phi + log_mgf)))
+        gk = np.power(k, 1.0 + gamma)
+        if str(ty) == "C":
+            out[j] = gamma_forward - normalizer * gk * capped
+        elif str(ty) == "P":
+            out[j] = k - normalizer * gk * capped
+        else:
+            raise ValueError("not implemented")
+    return out
+
+
+def fourier_chain_prices(p: dict, ttms, forwards, discfactors, strikes_ttms, types_ttms, is_spot_measure=True, vol_scaler=None, gamma=None,
+                         return_grids=False):
+    """hawkesjd_chain_pricer (gamma None) / hawkesjd_chain_pricer_with_risk_premia"""
+    from . import mgf as _mgf
+    if vol_scaler is None:
+        vol_scaler = fourier_vol_scaler(p["sigma"], float(np.min(ttms)))
+    phi = _mgf.phi_grid(vol_scaler, True, MAX_PHI)
+    if gamma is not None:
+        phi = (-0.5 - gamma) + 1j * np.imag(phi)
+        norm, gfw = forwards_under_risk_kernel(p, gamma, ttms, forwards)
+    a, t0, prices, grids = np.zeros((phi.shape[0], 3), dtype=np.complex128), 0.0, [], []
+    for m, ttm in enumerate(ttms):
+        a, lm = a_mgf_grid(ttm - t0, phi, p, a)
+        t0 = ttm
+        if gamma is None:
+            prices.append(_mgf.vanilla_slice_prices(lm, phi, forwards[m], strikes_ttms[m], types_ttms[m], discfactors[m], is_spot_measure))
+        else:
+            prices.append(gamma_slice_prices(lm, phi, gamma, forwards[m], norm[m], gfw[m], strikes_ttms[m], types_ttms[m]))
+        grids.append((a.copy(), lm.copy()))
+    return (prices, grids, phi) if return_grids else prices

@@ -71,6 +71,8 @@ SIGNATURES = {
     "b200sv_rough_logsv_mc_chain": [_lp, c_int, c_int, _dp, _dp, c_int, _dp, _dp, _dp, _ip, _dp, _i8p, c_longlong, _ip, _dp, _dp, _dp, c_longlong,
                                     c_int, c_uint64, c_int, _dp, _dp, _dp, _dp],
     "b200sv_hawkesjd_mc_chain": [_kp, c_int, _dp, _dp, _dp, _ip, _dp, _i8p, c_longlong, c_int, c_uint64, c_int, _dp, _dp],
+    "b200sv_hawkesjd_price_chain": [_kp, c_int, _dp, _dp, _dp, _ip, _dp, _i8p, c_int, c_double, c_int, c_double, _dp, _dp, _dp, _dp, _dp],
+    "b200sv_fourier_gamma": [_dp, _dp, c_int, c_double, c_double, c_double, c_double, _dp, _i8p, c_int, c_int, _dp],
     "b200sv_hawkesjd_terminal": [_kp, c_double, c_longlong, c_uint64, c_int, c_int, c_int, _dp, _dp, _dp],
     "b200sv_hawkesjd_step_fixed": [_dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, c_int, c_longlong, c_double, _kp],
     "b200sv_hawkesjd_device_draws": [c_uint64, c_longlong, c_longlong, c_int, c_int, c_double, _kp, c_int, _dp, _dp, _dp, _dp, _dp],

@@ -217,8 +217,10 @@ struct StageStore {
 };
 
 // returns 0 ok, 1 step size underflow (SciPy: TOO_SMALL_STEP -> solver fails, reference keeps the last accepted state)
-template <int N, int TPB>
-__device__ int rk45(cd (&y)[N], double T, const LogsvModel& m, const CoefView<TPB>& c, StageStore<N, TPB> K, int* nfev_out) {
+// Rhs: functor ``void operator()(const cd (&A)[N], cd (&out)[N]) const`` -- the LogSV coefficient ODEs (LogsvRhsFn) or the Hawkes Riccati
+// system (HawkesRhsFn); the control law does not depend on it.
+template <int N, int TPB, typename Rhs>
+__device__ int rk45_generic(cd (&y)[N], double T, const Rhs& rhs_fn, StageStore<N, TPB> K, int* nfev_out) {
   constexpr double A[6][5] = {{0, 0, 0, 0, 0},
                               {1.0 / 5, 0, 0, 0, 0},
                               {3.0 / 40, 9.0 / 40, 0, 0, 0},
@@ -229,7 +231,7 @@ __device__ int rk45(cd (&y)[N], double T, const LogsvModel& m, const CoefView<TP
   constexpr double E[7] = {-71.0 / 57600, 0, 71.0 / 16695, -71.0 / 1920, 17253.0 / 339200, -22.0 / 525, 1.0 / 40};
 
   cd f[N];                       // f(t, y): registers during the initial-step selection, then stage 0 of the shared-memory store
-  rhs<N, TPB>(y, m, c, f);
+  rhs_fn(y, f);
   int nfev = 1;
   double inv_scale[N];
   // ---- select_initial_step (scipy/integrate/_ivp/common.py:109-134)
@@ -243,7 +245,7 @@ __device__ int rk45(cd (&y)[N], double T, const LogsvModel& m, const CoefView<TP
     cd y1[N], f1[N];
 #pragma unroll
     for (int k = 0; k < N; ++k) y1[k] = y[k] + h0 * f[k];
-    rhs<N, TPB>(y1, m, c, f1);
+    rhs_fn(y1, f1);
     ++nfev;
 #pragma unroll
     for (int k = 0; k < N; ++k) f1[k] = f1[k] - f[k];
@@ -285,7 +287,7 @@ __device__ int rk45(cd (&y)[N], double T, const LogsvModel& m, const CoefView<TP
           for (int jj = 1; jj < 5; ++jj) acc = acc + K.at(jj, k) * c_A[s][jj];
           yt[k] = y[k] + acc * h;
         }
-        rhs<N, TPB>(yt, m, c, kn);
+        rhs_fn(yt, kn);
 #pragma unroll
         for (int k = 0; k < N; ++k) K.at(s, k) = kn[k];
       }
@@ -297,7 +299,7 @@ __device__ int rk45(cd (&y)[N], double T, const LogsvModel& m, const CoefView<TP
         for (int jj = 2; jj < 6; ++jj) acc = acc + K.at(jj, k) * B[jj];      // B[1] = 0
         yn[k] = y[k] + h * acc;
       }
-      rhs<N, TPB>(yn, m, c, kn);                                                   // K[6] = f(t + h, y_new)
+      rhs_fn(yn, kn);                                                   // K[6] = f(t + h, y_new)
       nfev += 6;
       cd err[N];
 #pragma unroll
@@ -327,6 +329,17 @@ __device__ int rk45(cd (&y)[N], double T, const LogsvModel& m, const CoefView<TP
   }
   if (nfev_out) *nfev_out = nfev;
   return status;
+}
+
+template <int N, int TPB>
+struct LogsvRhsFn {
+  const LogsvModel& m;
+  const CoefView<TPB>& c;
+  __device__ __forceinline__ void operator()(const cd (&A)[N], cd (&out)[N]) const { rhs<N, TPB>(A, m, c, out); }
+};
+template <int N, int TPB>
+__device__ __forceinline__ int rk45(cd (&y)[N], double T, const LogsvModel& m, const CoefView<TPB>& c, StageStore<N, TPB> K, int* nfev_out) {
+  return rk45_generic<N, TPB>(y, T, LogsvRhsFn<N, TPB>{m, c}, K, nfev_out);
 }
 
 struct ChainSpec {   // per-maturity scalars (device array of M entries)
@@ -746,6 +759,116 @@ __global__ void __launch_bounds__(kFourierThreads) fourier_sum_kernel(const cd* 
       r = sp.a * ((is_call == (all_calls != 0)) ? S : 1.0 - S);  // :251-264
     }
     out[blockIdx.x] = r;
+  }
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// Hawkes jump-diffusion Fourier route (pricers/hawkes_jd_pricer.py:365-641): Riccati system for (a0, a_p, a_m) per transform point,
+//   a0' = kappa_p theta_p a_p + kappa_m theta_m a_m + sigma^2 ((phi + 1) phi / 2 - psi)
+//   a_p' = E_p(phi - beta1_p a_p - beta1_m a_m) - 1 - kappa_p a_p + comp_p phi        E(z) = exp(-shift z) / (1 + mean z): the jump-size MGF
+//   a_m' = E_m(phi - beta2_p a_p - beta2_m a_m) - 1 - kappa_m a_m + comp_m phi        comp = exp(shift) / (1 - mean) - 1
+// integrated per maturity by the SAME SciPy-RK45 clone as the LogSV coefficient ODEs (solve_ivp defaults, :636-639), A carried over the
+// maturities (:396-416); log-MGF = a0 + a_p lambda_p + a_m lambda_m (:546).  One thread = one transform point.
+// --------------------------------------------------------------------------------------------------------------------
+struct HawkesMgfConsts {
+  double sigma2, shift_p, mean_p, shift_m, mean_m, comp_p, comp_m;
+  double kt_p, kt_m, kappa_p, kappa_m, beta1_p, beta1_m, beta2_p, beta2_m, lambda_p, lambda_m;
+};
+
+static HawkesMgfConsts make_hawkes_mgf_consts(const b200sv_hawkes_params& p) {
+  HawkesMgfConsts c;
+  c.sigma2 = p.sigma * p.sigma;
+  c.shift_p = p.shift_p;
+  c.mean_p = p.mean_p;
+  c.shift_m = p.shift_m;
+  c.mean_m = p.mean_m;
+  c.comp_p = std::exp(p.shift_p) / (1.0 - p.mean_p) - 1.0;
+  c.comp_m = std::exp(p.shift_m) / (1.0 - p.mean_m) - 1.0;
+  c.kt_p = p.kappa_p * p.theta_p;
+  c.kt_m = p.kappa_m * p.theta_m;
+  c.kappa_p = p.kappa_p;
+  c.kappa_m = p.kappa_m;
+  c.beta1_p = p.beta1_p;
+  c.beta1_m = p.beta1_m;
+  c.beta2_p = p.beta2_p;
+  c.beta2_m = p.beta2_m;
+  c.lambda_p = p.lambda_p;
+  c.lambda_m = p.lambda_m;
+  return c;
+}
+
+struct HawkesRhsFn {
+  const HawkesMgfConsts& c;
+  cd phi, drift0;          // drift0 = sigma^2 ((phi + 1) phi / 2 - psi)
+  __device__ __forceinline__ void operator()(const cd (&A)[3], cd (&out)[3]) const {
+    const cd zp = (phi - c.beta1_p * A[1]) - c.beta1_m * A[2], zm = (phi - c.beta2_p * A[1]) - c.beta2_m * A[2];
+    const cd jp = cexp_(-c.shift_p * zp) / (mk(1.0) + c.mean_p * zp) - mk(1.0);
+    const cd jm = cexp_(-c.shift_m * zm) / (mk(1.0) + c.mean_m * zm) - mk(1.0);
+    out[0] = (c.kt_p * A[1] + c.kt_m * A[2]) + drift0;
+    out[1] = (jp - c.kappa_p * A[1]) + c.comp_p * phi;
+    out[2] = (jm - c.kappa_m * A[2]) + c.comp_m * phi;
+  }
+};
+
+// a_io: A(0) per point or nullptr (zeros); restart != 0: every maturity starts from A = 0 and integrates over ITS ttm (the risk-kernel
+// normalisers, :498-509) instead of carrying A over the increments
+template <int TPB>
+__global__ void __launch_bounds__(TPB) hawkes_mgf_kernel(const cd* __restrict__ phi, const cd* __restrict__ psi, int P, int M,
+                                                         const double* __restrict__ dtaus, HawkesMgfConsts c, const cd* __restrict__ a_in,
+                                                         cd* __restrict__ a_out, cd* __restrict__ log_mgf, int restart, int* __restrict__ status) {
+  __shared__ cd stage_smem[6 * 3 * TPB];
+  const int p = blockIdx.x * TPB + threadIdx.x;
+  if (p >= P) return;
+  StageStore<3, TPB> K{stage_smem + threadIdx.x};
+#pragma unroll
+  for (int i = 0; i < 18; ++i) stage_smem[threadIdx.x + i * TPB] = mk(0.0);
+  cd A[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) A[k] = a_in ? a_in[(size_t)p * 3 + k] : mk(0.0);
+  const cd ph = phi[p], ps = psi ? psi[p] : mk(0.0);
+  const HawkesRhsFn f{c, ph, c.sigma2 * (0.5 * ((ph + mk(1.0)) * ph) - ps)};
+  int st = 0;
+  for (int m = 0; m < M; ++m) {
+    if (restart) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) A[k] = mk(0.0);
+    }
+    st |= rk45_generic<3, TPB>(A, dtaus[m], f, K, nullptr);
+    if (a_out) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) a_out[((size_t)m * P + p) * 3 + k] = A[k];
+    }
+    log_mgf[(size_t)m * P + p] = (A[0] + A[1] * c.lambda_p) + A[2] * c.lambda_m;
+  }
+  if (status) status[p] = st;
+}
+
+// slice_pricer_with_mgf_grid_with_gamma (utils/mgf_pricer.py:273-320): general weights -(dp/pi) / ((phi + g + 1)(phi + g)) (its fast branch
+// compares Re(phi) with +(1/2 + g) while the grid sits on -(1/2 + g), so it never runs), calls gamma_forward - n K^(1+g) S, puts K - n K^(1+g) S;
+// no discount factor (both as in the reference).  spec.forward = forward, spec.discfactor = normalizer n, spec.ttm = gamma_forward.
+__global__ void __launch_bounds__(kFourierThreads) fourier_gamma_kernel(const cd* __restrict__ log_mgf, const cd* __restrict__ phi, int P,
+                                                                       const StrikeSpec* __restrict__ specs, double gamma,
+                                                                       double* __restrict__ prices) {
+  __shared__ double red[kFourierThreads / 32];
+  const StrikeSpec sp = specs[blockIdx.x];
+  const cd* lm = log_mgf + (size_t)sp.slice * P;
+  const double x = log(sp.forward / sp.strike);
+  const double h3 = (phi[1].im - phi[0].im) / 3.0;
+  const bool fast = fabs(phi[0].re - (0.5 + gamma)) < 1e-10;
+  double acc[1] = {0.0};
+  for (int j = threadIdx.x; j < P; j += kFourierThreads) {
+    const double wq = (j & 1) ? 4.0 : ((j == 0 || j == P - 1) ? 1.0 : 2.0);
+    const double dp = h3 * wq;
+    const cd ph = phi[j];
+    const cd pg = ph + mk(gamma);
+    const cd w = fast ? mk((dp / M_PI) / (ph.im * ph.im + 0.25)) : -(mk(dp / M_PI) / ((pg + mk(1.0)) * pg));
+    const cd term = w * cexp_(lm[j] - x * ph);
+    if (term.re == term.re) acc[0] += term.re;
+  }
+  block_sum<1, kFourierThreads>(acc, red);
+  if (threadIdx.x == 0) {
+    const double gk = pow(sp.strike, 1.0 + gamma);
+    prices[blockIdx.x] = (sp.type == B200SV_CALL ? sp.ttm : sp.strike) - sp.discfactor * gk * acc[0];
   }
 }
 
@@ -1663,6 +1786,102 @@ int b200sv_heston_price_chain_batch(const b200sv_heston_params* params, int B, i
   return 0;
 }
 
+/* Hawkes jump-diffusion Fourier chain (hawkesjd_chain_pricer / hawkesjd_chain_pricer_with_risk_premia, hawkes_jd_pricer.py:365-515).
+ * risk_premia_gamma = NaN: no risk kernel.  Otherwise the grid sits on Re = -1/2 - gamma, the normalisers / forwards under the risk kernel
+ * come from two single-point solves per maturity (each restarted from A = 0) and the gamma slice pricer assembles the prices;
+ * normalizers_out / gamma_forwards_out (M each, optional) return them. */
+int b200sv_hawkesjd_price_chain(const b200sv_hawkes_params* params, int M, const double* ttms, const double* forwards, const double* discfactors,
+                                const int* offsets, const double* strikes, const int8_t* types, int is_spot_measure, double vol_scaler, int P,
+                                double risk_premia_gamma, double* prices_out, double* a_out, double* log_mgf_out, double* normalizers_out,
+                                double* gamma_forwards_out) {
+  B200SV_REQUIRE(params && ttms && forwards && discfactors && offsets && prices_out, "null pointer");
+  if (P <= 0) P = 500;                                                        // MAX_PHI, hawkes_jd_pricer.py:37
+  B200SV_REQUIRE(M >= 1 && P >= 3, "M >= 1, P >= 3");
+  const bool with_gamma = risk_premia_gamma == risk_premia_gamma;
+  const bool spot = is_spot_measure != 0;
+  const int Jtot = offsets[M] - offsets[0];
+  if (with_gamma) {                                                            // utils/mgf_pricer.py:310-318: 'C' / 'P' under the spot measure only
+    if (!spot) return fail(-5, "not implemented");
+    for (int j = offsets[0]; j < offsets[M]; ++j)
+      if (types[j] != B200SV_CALL && types[j] != B200SV_PUT) return fail(-5, "not implemented");
+  } else if (int rc = check_fourier_types(types + offsets[0], Jtot, spot)) {
+    return rc;
+  }
+  std::vector<double> dtaus(M);
+  double t0 = 0.0, tmin = ttms[0];
+  for (int m = 0; m < M; ++m) {
+    B200SV_REQUIRE(ttms[m] > t0, "ttms must be positive and strictly increasing");
+    dtaus[m] = ttms[m] - t0;
+    t0 = ttms[m];
+    tmin = std::min(tmin, ttms[m]);
+  }
+  if (!(vol_scaler > 0.0)) vol_scaler = std::min(std::max(params->sigma, 0.2), 0.5) * std::sqrt(std::min(tmin, 1.0 / 12.0));   // :360-362
+  std::vector<double> phi;
+  build_phi(vol_scaler, true, P, phi);                                         // get_transform_var_grid default is_spot_measure=True (:385)
+  if (with_gamma)
+    for (int i = 0; i < P; ++i) phi[2 * i] = -0.5 - risk_premia_gamma;           // real_phi (:451)
+  const HawkesMgfConsts c = make_hawkes_mgf_consts(*params);
+  cudaStream_t st = current_stream();
+  ensure_pool_threshold();
+  DevBuf d_phi(st), d_dt(st), d_a(st), d_lm(st), d_ss(st), d_pr(st), d_g(st);
+  B200SV_CUDA(d_phi.alloc(sizeof(cd) * P));
+  B200SV_CUDA(d_dt.alloc(sizeof(double) * 2 * M));
+  B200SV_CUDA(d_a.alloc(sizeof(cd) * (size_t)M * P * 3));
+  B200SV_CUDA(d_lm.alloc(sizeof(cd) * (size_t)M * P));
+  B200SV_CUDA(cudaMemcpyAsync(d_phi.p, phi.data(), sizeof(cd) * P, cudaMemcpyHostToDevice, st));
+  std::vector<double> dts(dtaus);
+  dts.insert(dts.end(), ttms, ttms + M);                                        // [increments | full maturities]
+  B200SV_CUDA(cudaMemcpyAsync(d_dt.p, dts.data(), sizeof(double) * 2 * M, cudaMemcpyHostToDevice, st));
+  std::vector<double> normalizers(M, 1.0), gamma_forwards(M, 1.0);
+  if (with_gamma) {                                                            // hawkesjd_forwards_under_risk_kernel (:487-515)
+    const double two[4] = {-risk_premia_gamma, 0.0, -risk_premia_gamma - 1.0, 0.0};
+    B200SV_CUDA(d_g.alloc(sizeof(cd) * (2 + 2 * (size_t)M)));
+    B200SV_CUDA(cudaMemcpyAsync(d_g.p, two, sizeof(two), cudaMemcpyHostToDevice, st));
+    hawkes_mgf_kernel<4><<<1, 4, 0, st>>>(d_g.as<cd>(), nullptr, 2, M, d_dt.as<double>() + M, c, nullptr, nullptr, d_g.as<cd>() + 2, 1, nullptr);
+    if (int rc = launched("hawkes_mgf_kernel")) return rc;
+    std::vector<double> lm2(4 * (size_t)M);
+    B200SV_CUDA(cudaMemcpyAsync(lm2.data(), d_g.as<cd>() + 2, sizeof(cd) * 2 * M, cudaMemcpyDeviceToHost, st));
+    B200SV_CUDA(cudaStreamSynchronize(st));
+    for (int m = 0; m < M; ++m) {                                              // log_mgf layout [m][point]
+      normalizers[m] = 1.0 / std::exp(lm2[2 * (2 * (size_t)m + 0)]);
+      gamma_forwards[m] = forwards[m] * std::exp(lm2[2 * (2 * (size_t)m + 1)]) * normalizers[m];
+    }
+  }
+  std::vector<StrikeSpec> ss(std::max(Jtot, 1));
+  for (int m = 0; m < M; ++m)
+    for (int j = offsets[m]; j < offsets[m + 1]; ++j) {
+      B200SV_REQUIRE(strikes[j] > 0.0, "strikes must be positive");
+      ss[j - offsets[0]] = with_gamma ? StrikeSpec{strikes[j], forwards[m], normalizers[m], (int)types[j], m, gamma_forwards[m], 0}
+                                      : StrikeSpec{strikes[j], forwards[m], discfactors[m], (int)types[j], m, ttms[m], 0};
+    }
+  B200SV_CUDA(d_ss.alloc(sizeof(StrikeSpec) * ss.size()));
+  B200SV_CUDA(d_pr.alloc(sizeof(double) * ss.size()));
+  B200SV_CUDA(cudaMemcpyAsync(d_ss.p, ss.data(), sizeof(StrikeSpec) * ss.size(), cudaMemcpyHostToDevice, st));
+  const int tpb = mgf_block_threads(P), nb = (P + tpb - 1) / tpb;
+  switch (tpb) {
+    case 4: hawkes_mgf_kernel<4><<<nb, 4, 0, st>>>(d_phi.as<cd>(), nullptr, P, M, d_dt.as<double>(), c, nullptr, d_a.as<cd>(), d_lm.as<cd>(), 0, nullptr); break;
+    case 8: hawkes_mgf_kernel<8><<<nb, 8, 0, st>>>(d_phi.as<cd>(), nullptr, P, M, d_dt.as<double>(), c, nullptr, d_a.as<cd>(), d_lm.as<cd>(), 0, nullptr); break;
+    case 16: hawkes_mgf_kernel<16><<<nb, 16, 0, st>>>(d_phi.as<cd>(), nullptr, P, M, d_dt.as<double>(), c, nullptr, d_a.as<cd>(), d_lm.as<cd>(), 0, nullptr); break;
+    case 32: hawkes_mgf_kernel<32><<<nb, 32, 0, st>>>(d_phi.as<cd>(), nullptr, P, M, d_dt.as<double>(), c, nullptr, d_a.as<cd>(), d_lm.as<cd>(), 0, nullptr); break;
+    default: hawkes_mgf_kernel<64><<<nb, 64, 0, st>>>(d_phi.as<cd>(), nullptr, P, M, d_dt.as<double>(), c, nullptr, d_a.as<cd>(), d_lm.as<cd>(), 0, nullptr); break;
+  }
+  if (int rc = launched("hawkes_mgf_kernel")) return rc;
+  if (Jtot > 0) {
+    if (with_gamma)
+      fourier_gamma_kernel<<<Jtot, kFourierThreads, 0, st>>>(d_lm.as<cd>(), d_phi.as<cd>(), P, d_ss.as<StrikeSpec>(), risk_premia_gamma, d_pr.as<double>());
+    else
+      fourier_vanilla_kernel<<<Jtot, kFourierThreads, 0, st>>>(d_lm.as<cd>(), d_phi.as<cd>(), P, d_ss.as<StrikeSpec>(), spot ? 1 : 0, 1, d_pr.as<double>());
+    if (int rc = launched("fourier kernel")) return rc;
+    B200SV_CUDA(cudaMemcpyAsync(prices_out, d_pr.p, sizeof(double) * Jtot, cudaMemcpyDeviceToHost, st));
+  }
+  if (a_out) B200SV_CUDA(cudaMemcpyAsync(a_out, d_a.p, sizeof(cd) * (size_t)M * P * 3, cudaMemcpyDeviceToHost, st));
+  if (log_mgf_out) B200SV_CUDA(cudaMemcpyAsync(log_mgf_out, d_lm.p, sizeof(cd) * (size_t)M * P, cudaMemcpyDeviceToHost, st));
+  B200SV_CUDA(cudaStreamSynchronize(st));
+  if (normalizers_out) std::copy(normalizers.begin(), normalizers.end(), normalizers_out);
+  if (gamma_forwards_out) std::copy(gamma_forwards.begin(), gamma_forwards.end(), gamma_forwards_out);
+  return 0;
+}
+
 int b200sv_logsv_mgf_grid(const double* phi, const double* psi, int P, double dtau, double* a_inout,
                           const b200sv_logsv_params* params, double eta, int is_spot_measure, int expansion_order,
                           double* log_mgf_out) {
@@ -1900,6 +2119,35 @@ int b200sv_fourier_vanilla(const double* log_mgf, const double* phi, int P, doub
   fourier_vanilla_kernel<<<J, kFourierThreads, 0, st>>>(d_lm.as<cd>(), d_phi.as<cd>(), P, d_ss.as<StrikeSpec>(), spot ? 1 : 0,
                                                         all_half_re(phi, P) ? 1 : 0, d_pr.as<double>());
   if (int rc = launched("fourier_vanilla_kernel")) return rc;
+  B200SV_CUDA(cudaMemcpyAsync(prices_out, d_pr.p, sizeof(double) * J, cudaMemcpyDeviceToHost, st));
+  B200SV_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+/* slice_pricer_with_mgf_grid_with_gamma (utils/mgf_pricer.py:273-320) on caller-supplied log-MGF / transform grids: 'C' / 'P' under the spot
+ * measure, everything else is ValueError("not implemented") there (-5 here) */
+int b200sv_fourier_gamma(const double* log_mgf, const double* phi, int P, double risk_premia_gamma, double forward, double normalizer,
+                         double gamma_forward, const double* strikes, const int8_t* types, int J, int is_spot_measure, double* prices_out) {
+  B200SV_REQUIRE(log_mgf && phi && strikes && types && prices_out, "null pointer");
+  B200SV_REQUIRE(P >= 3 && J >= 1, "P >= 3, J >= 1");
+  if (!is_spot_measure) return fail(-5, "not implemented");
+  std::vector<StrikeSpec> ss(J);
+  for (int j = 0; j < J; ++j) {
+    if (types[j] != B200SV_CALL && types[j] != B200SV_PUT) return fail(-5, "not implemented");
+    ss[j] = StrikeSpec{strikes[j], forward, normalizer, (int)types[j], 0, gamma_forward, 0};
+  }
+  cudaStream_t st = current_stream();
+  ensure_pool_threshold();
+  DevBuf d_phi(st), d_lm(st), d_ss(st), d_pr(st);
+  B200SV_CUDA(d_phi.alloc(sizeof(cd) * P));
+  B200SV_CUDA(d_lm.alloc(sizeof(cd) * P));
+  B200SV_CUDA(d_ss.alloc(sizeof(StrikeSpec) * J));
+  B200SV_CUDA(d_pr.alloc(sizeof(double) * J));
+  B200SV_CUDA(cudaMemcpyAsync(d_phi.p, phi, sizeof(cd) * P, cudaMemcpyHostToDevice, st));
+  B200SV_CUDA(cudaMemcpyAsync(d_lm.p, log_mgf, sizeof(cd) * P, cudaMemcpyHostToDevice, st));
+  B200SV_CUDA(cudaMemcpyAsync(d_ss.p, ss.data(), sizeof(StrikeSpec) * J, cudaMemcpyHostToDevice, st));
+  fourier_gamma_kernel<<<J, kFourierThreads, 0, st>>>(d_lm.as<cd>(), d_phi.as<cd>(), P, d_ss.as<StrikeSpec>(), risk_premia_gamma, d_pr.as<double>());
+  if (int rc = launched("fourier_gamma_kernel")) return rc;
   B200SV_CUDA(cudaMemcpyAsync(prices_out, d_pr.p, sizeof(double) * J, cudaMemcpyDeviceToHost, st));
   B200SV_CUDA(cudaStreamSynchronize(st));
   return 0;

@@ -474,6 +474,17 @@ def fourier_vanilla(log_mgf, phi, forward, strikes, optiontypes, discfactor=1.0,
     return prices
 
 
+def fourier_gamma(log_mgf, phi, risk_premia_gamma, forward, normalizer, gamma_forward, strikes, optiontypes, is_spot_measure=True):
+    if not is_spot_measure or any(str(t) not in ("C", "P") for t in optiontypes):
+        raise ValueError("not implemented")           # utils/mgf_pricer.py:310-318
+    log_mgf, phi, strikes = C.c128(log_mgf), C.c128(phi), C.f64(strikes)
+    types = C.encode_types(optiontypes)
+    prices = np.empty(strikes.shape[0])
+    C.call("b200sv_fourier_gamma", log_mgf.ctypes.data_as(C._dp), phi.ctypes.data_as(C._dp), phi.shape[0], float(risk_premia_gamma), float(forward),
+           float(normalizer), float(gamma_forward), C.dptr(strikes), C.i8ptr(types), strikes.shape[0], 1, C.dptr(prices))
+    return prices
+
+
 def fourier_qvar(log_mgf, psi, ttm, strikes, optiontypes, discfactor=1.0):
     _check_qvar_types([optiontypes])
     log_mgf, psi, strikes = C.c128(log_mgf), C.c128(psi), C.f64(strikes)

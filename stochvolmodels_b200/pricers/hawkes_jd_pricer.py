@@ -81,11 +81,13 @@ def _params_c(**kw) -> C.HawkesParamsC:
 
 
 class HawkesJDPricer(ModelPricer):
-    """ModelPricer for the Hawkes jump-diffusion model: Monte Carlo route on the GPU."""
+    """ModelPricer for the Hawkes jump-diffusion model: Fourier and Monte Carlo routes on the GPU."""
 
     def price_chain(self, option_chain: OptionChain, params: HawkesJDParams, is_spot_measure: bool = True, **kwargs) -> List[np.ndarray]:
-        raise NotImplementedError("the Fourier route of the Hawkes jump-diffusion model is outside the B200 hot-path scope (SURVEY.md §8); "
-                                  "use model_mc_price_chain")
+        """Fourier prices of the chain (reference :125-155): the risk-kernel pricer when ``params.risk_premia_gamma`` is set, else the plain one"""
+        pricer = hawkesjd_chain_pricer if params.risk_premia_gamma is None else hawkesjd_chain_pricer_with_risk_premia
+        return pricer(model_params=params, ttms=option_chain.ttms, forwards=option_chain.forwards, discfactors=option_chain.discfactors,
+                      strikes_ttms=option_chain.strikes_ttms, optiontypes_ttms=option_chain.optiontypes_ttms, is_spot_measure=is_spot_measure, **kwargs)
 
     @timer
     def model_mc_price_chain(self, option_chain: OptionChain, params: HawkesJDParams, nb_path: int = 100000, **kwargs
@@ -168,3 +170,67 @@ def hawkesjd_device_draws(seed: int, path0: int, n: int, slice_index: int, ttm: 
     C.call("b200sv_hawkesjd_device_draws", int(seed) & 0xFFFFFFFFFFFFFFFF, int(path0), int(n), int(slice_index), S, dt, byref(pc),
            engine.mc_flags("fp64", gauss), *[C.dptr(o) for o in out])
     return (*out, dt)
+
+
+MAX_PHI = 500           # transform grid size of the Fourier route (reference :37)
+
+
+def set_vol_scaler(sigma0: float, ttm: float) -> float:
+    """grid scaler of the Fourier route (reference :360-362)"""
+    return float(np.clip(sigma0, 0.2, 0.5) * np.sqrt(np.minimum(ttm, 1.0 / 12.0)))
+
+
+def _fourier_chain(model_params: HawkesJDParams, ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms, is_stiff_solver, is_spot_measure,
+                   variable_type, vol_scaler, gamma, return_grids=False):
+    if getattr(variable_type, "value", variable_type) != VariableType.LOG_RETURN.value:
+        raise NotImplementedError           # reference :413-414
+    if is_stiff_solver:
+        raise NotImplementedError("is_stiff_solver: the Hawkes Fourier route runs SciPy's RK45 control law on the GPU; its BDF variant is not built")
+    if gamma is None:
+        engine._check_fourier_types(optiontypes_ttms, bool(is_spot_measure))
+    elif not is_spot_measure or any(str(t) not in ("C", "P") for types in optiontypes_ttms for t in types):
+        raise ValueError("not implemented")           # utils/mgf_pricer.py:310-318
+    M, ttms, forwards, discfactors, offsets, strikes, types = engine._chain_arrays(ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms)
+    d = model_params.to_dict()
+    d.pop("risk_premia_gamma", None)
+    pc = _params_c(**d)
+    prices = np.empty(strikes.shape[0])
+    a = np.empty((M, MAX_PHI, 3), dtype=np.complex128) if return_grids else None
+    lm = np.empty((M, MAX_PHI), dtype=np.complex128) if return_grids else None
+    norm, gfw = np.empty(M), np.empty(M)
+    cptr = lambda arr: None if arr is None else arr.ctypes.data_as(C._dp)
+    C.call("b200sv_hawkesjd_price_chain", byref(pc), M, C.dptr(ttms), C.dptr(forwards), C.dptr(discfactors), C.iptr(offsets), C.dptr(strikes),
+           C.i8ptr(types), int(bool(is_spot_measure)), float(vol_scaler) if vol_scaler is not None else 0.0, MAX_PHI,
+           float("nan") if gamma is None else float(gamma), C.dptr(prices), cptr(a), cptr(lm), C.dptr(norm), C.dptr(gfw))
+    out = C.split_chain(prices, offsets)
+    return (out, a, lm, norm, gfw) if return_grids else out
+
+
+def hawkesjd_chain_pricer(model_params: HawkesJDParams, ttms: np.ndarray, forwards: np.ndarray, discfactors: np.ndarray, strikes_ttms, optiontypes_ttms,
+                          is_stiff_solver: bool = False, is_spot_measure: bool = True, variable_type: VariableType = VariableType.LOG_RETURN,
+                          vol_scaler: float = None, return_grids: bool = False) -> List[np.ndarray]:
+    """Fourier chain prices of the Hawkes jump-diffusion (reference :365-417): Riccati ODEs for (a0, a_p, a_m) on a 500-point transform grid
+    with SciPy's RK45 control law per point, carried over the maturities, then the vanilla slice pricer -- one GPU call"""
+    return _fourier_chain(model_params, ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms, is_stiff_solver, is_spot_measure, variable_type,
+                          vol_scaler, None, return_grids)
+
+
+def hawkesjd_chain_pricer_with_risk_premia(model_params: HawkesJDParams, ttms: np.ndarray, forwards: np.ndarray, discfactors: np.ndarray, strikes_ttms,
+                                           optiontypes_ttms, is_stiff_solver: bool = False, is_spot_measure: bool = True,
+                                           variable_type: VariableType = VariableType.LOG_RETURN, vol_scaler: float = None,
+                                           return_grids: bool = False) -> List[np.ndarray]:
+    """Fourier chain prices under the risk kernel exp(-gamma x) (reference :420-484; grid on Re = -1/2 - gamma, normalisers and forwards under the
+    kernel from two single-point solves per maturity, gamma slice pricer without discounting -- all as in the reference)"""
+    return _fourier_chain(model_params, ttms, forwards, discfactors, strikes_ttms, optiontypes_ttms, is_stiff_solver, is_spot_measure, variable_type,
+                          vol_scaler, model_params.risk_premia_gamma, return_grids)
+
+
+def hawkesjd_forwards_under_risk_kernel(model_params: HawkesJDParams, risk_premia_gamma: float, ttms: np.ndarray, forwards: np.ndarray,
+                                        is_stiff_solver: bool = False) -> Tuple[np.ndarray, np.ndarray]:
+    """(normalizers, gamma_forwards) per maturity (reference :487-515)"""
+    ttms, forwards = np.asarray(ttms, dtype=float), np.asarray(forwards, dtype=float)
+    one = [np.ones(1) for _ in ttms]
+    p = HawkesJDParams(**{**model_params.to_dict(), "risk_premia_gamma": float(risk_premia_gamma)})
+    _, _, _, norm, gfw = _fourier_chain(p, ttms, forwards, np.ones_like(ttms), one, [np.array(["C"]) for _ in ttms], is_stiff_solver, True,
+                                        VariableType.LOG_RETURN, None, float(risk_premia_gamma), return_grids=True)
+    return norm, gfw

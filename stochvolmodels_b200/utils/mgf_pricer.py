@@ -51,6 +51,17 @@ def vanilla_slice_pricer_with_mgf_grid(log_mgf_grid: np.ndarray, phi_grid: np.nd
     return engine.fourier_vanilla(log_mgf_grid, phi_grid, forward, strikes, optiontypes, discfactor, is_spot_measure)
 
 
+def slice_pricer_with_mgf_grid_with_gamma(log_mgf_grid: np.ndarray, phi_grid: np.ndarray, risk_premia_gamma: float, ttm: float, forward: float,
+                                          normalizer: float, gamma_forward: float, strikes: np.ndarray, optiontypes: np.ndarray,
+                                          discfactor: float = 1.0, is_spot_measure: bool = True, is_simpson: bool = True) -> np.ndarray:
+    """vanilla prices under the risk kernel exp(-gamma x) from a log-MGF grid on Re(phi) = -1/2 - gamma (utils/mgf_pricer.py:273-320):
+    calls ``gamma_forward - normalizer K^(1+gamma) S``, puts ``K - normalizer K^(1+gamma) S``; ``ttm`` and ``discfactor`` are accepted and
+    unused, as in the reference; anything but 'C' / 'P' under the spot measure is ``ValueError("not implemented")``."""
+    if not is_simpson:
+        raise NotImplementedError("is_simpson=False: the CUDA sums build the legacy Simpson weights")
+    return engine.fourier_gamma(log_mgf_grid, phi_grid, risk_premia_gamma, forward, normalizer, gamma_forward, strikes, optiontypes, is_spot_measure)
+
+
 def slice_qvar_pricer_with_a_grid(log_mgf_grid: np.ndarray, psi_grid: np.ndarray, ttm: float, strikes: np.ndarray, optiontypes: np.ndarray,
                                   forward: float, discfactor: float = 1.0, is_spot_measure: bool = True) -> np.ndarray:
     """calls on the annualised quadratic variance from the log-MGF on the psi grid, on the GPU (utils/mgf_pricer.py:323-358);

@@ -758,6 +758,47 @@ HAWKES_KEYS = ("mu", "sigma", "shift_p", "mean_p", "shift_m", "mean_m", "lambda_
                "kappa_m", "beta1_m", "beta2_m")
 
 
+def hawkes_fourier() -> None:
+    """Hawkes jump-diffusion Fourier route (pricers/hawkes_jd_pricer.py:365-641): per-maturity ODE grids (500 transform points, SciPy RK45 per
+    point), log-MGF and chain prices, without and with the risk-premium kernel -> hawkes_fourier.npz.
+    python tests/golden/make_golden.py --only-hawkes-fourier"""
+    _import_reference()
+    from stochvolmodels.pricers import hawkes_jd_pricer as hj
+    from stochvolmodels.utils import mgf_pricer as mgfp
+    K = np.array([0.8, 0.9, 1.0, 1.1, 1.2])
+    T = np.array(['P', 'P', 'C', 'C', 'C'])
+    ttms, fw, df = np.array([0.05, 0.12, 0.3]), np.array([1.0, 1.01, 1.02]), np.array([0.999, 0.995, 0.99])
+    sets = {"dflt": hj.HawkesJDParams(),
+            "alt": hj.HawkesJDParams(mu=0.05, sigma=0.3, shift_p=0.04, mean_p=0.05, shift_m=-0.03, mean_m=-0.06, lambda_p=12.0, theta_p=9.0, kappa_p=15.0,
+                                     beta1_p=40.0, beta2_p=-30.0, lambda_m=10.0, theta_m=11.0, kappa_m=20.0, beta1_m=50.0, beta2_m=-60.0)}
+    out = dict(ttms=ttms, forwards=fw, discfactors=df, strikes=K, types=T, keys=np.array(HAWKES_KEYS))
+    from numba.typed import List
+    for name, params in sets.items():
+        out[f"{name}_params"] = np.array([params.to_dict()[k] for k in HAWKES_KEYS])
+        vol_scaler = hj.set_vol_scaler(sigma0=params.sigma, ttm=np.min(ttms))
+        phi, psi, theta = mgfp.get_transform_var_grid(max_phi=hj.MAX_PHI, vol_scaler=vol_scaler)
+        out[f"{name}_phi"] = phi
+        a, t0 = np.zeros((phi.shape[0], 3), dtype=np.complex128), 0.0
+        for m, ttm in enumerate(ttms):
+            a, lm = hj.compute_hawkes_a_mgf_grid(ttm=ttm - t0, phi_grid=phi, psi_grid=psi, theta_grid=theta, a_t0=a, model_params=params)
+            out[f"{name}_a_{m}"], out[f"{name}_lm_{m}"] = a.copy(), lm.copy()
+            t0 = ttm
+        prices = hj.hawkesjd_chain_pricer(model_params=params, ttms=ttms, forwards=fw, discfactors=df, strikes_ttms=List([K * f for f in fw]),
+                                          optiontypes_ttms=List([T for _ in fw]))
+        out[f"{name}_prices"] = np.array([np.asarray(p) for p in prices])
+        print(name, out[f"{name}_prices"])
+    # risk-premium kernel
+    gamma = 0.4
+    pg = hj.HawkesJDParams(risk_premia_gamma=gamma)
+    normalizers, gamma_forwards = hj.hawkesjd_forwards_under_risk_kernel(model_params=pg, forwards=fw, risk_premia_gamma=gamma, ttms=ttms)
+    prices = hj.hawkesjd_chain_pricer_with_risk_premia(model_params=pg, ttms=ttms, forwards=fw, discfactors=df, strikes_ttms=List([K * f for f in fw]),
+                                                       optiontypes_ttms=List([T for _ in fw]))
+    out.update(gamma=np.array(gamma), gamma_normalizers=normalizers, gamma_forwards=gamma_forwards, gamma_prices=np.array([np.asarray(p) for p in prices]))
+    print("gamma", out["gamma_prices"], normalizers, gamma_forwards)
+    np.savez(os.path.join(OUT, "hawkes_fourier.npz"), **out)
+    print("wrote hawkes_fourier.npz")
+
+
 def chain_transforms() -> None:
     """OptionChain slice views and strike transforms on the BTC sample chain -> option_chain_transforms.npz.
     python tests/golden/make_golden.py --only-chain"""
@@ -826,6 +867,9 @@ def _chain(ttms, fw, df, K, T):
 
 
 if __name__ == "__main__":
+    if "--only-hawkes-fourier" in sys.argv:
+        hawkes_fourier()
+        sys.exit(0)
     if "--only-chain" in sys.argv:
         chain_transforms()
         sys.exit(0)

@@ -88,8 +88,10 @@ def test_chain_prices_within_mc_error_of_reference_mc_golden(cuda_lib):
     x, _, _ = HawkesJDPricer().simulate_terminal_values(params, ttm=0.1, nb_path=2_000_000, seed=6)
     m1 = np.exp(x)
     assert abs(m1.mean() - np.exp(params.mu * 0.1)) < 4 * m1.std() / np.sqrt(x.size)
-    with pytest.raises(NotImplementedError):
-        HawkesJDPricer().price_chain(chain, params)
+    # and the Fourier route prices the same chain within the MC error
+    four = HawkesJDPricer().price_chain(chain, params)
+    for m in range(M):
+        assert np.all(np.abs(p[m] - four[m]) < 4.5 * e[m] + 2e-4), (p[m], four[m], e[m])
 
 
 def test_sharded_driver_equals_the_host_level_chain(cuda_lib):
@@ -129,3 +131,44 @@ def test_sharded_driver_equals_the_host_level_chain(cuda_lib):
     joined = torch.cat([e.state for e in parts], dim=1)
     assert torch.equal(joined, whole.state)
     np.testing.assert_allclose(moments, whole.moments.cpu().numpy(), rtol=1e-12)
+
+
+def test_fourier_route_vs_reference_golden_and_oracle(cuda_lib):
+    """hawkesjd_chain_pricer / hawkesjd_chain_pricer_with_risk_premia (reference :365-515): per-maturity ODE grids (a0, a_p, a_m), log-MGF and chain
+    prices of the CUDA path against the reference's own outputs (hawkes_fourier.npz, two parameter sets, three carried maturities), the
+    risk-kernel normalisers / forwards / prices, the pricer API, and the error conventions"""
+    from stochvolmodels_b200 import HawkesJDParams, HawkesJDPricer, OptionChain
+    from stochvolmodels_b200.pricers.hawkes_jd_pricer import (hawkesjd_chain_pricer, hawkesjd_chain_pricer_with_risk_premia,
+                                                              hawkesjd_forwards_under_risk_kernel, set_vol_scaler)
+    g = load_golden("hawkes_fourier.npz")
+    K, T, ttms, fw, df = g["strikes"], g["types"], g["ttms"], g["forwards"], g["discfactors"]
+    Ks, Ts = [K * f for f in fw], [T] * 3
+    for name in ("dflt", "alt"):
+        params = HawkesJDParams(**dict(zip(hawkes.KEYS, g[f"{name}_params"])))
+        prices, a, lm, _, _ = hawkesjd_chain_pricer(params, ttms, fw, df, Ks, Ts, return_grids=True)
+        for m in range(3):
+            np.testing.assert_allclose(a[m], g[f"{name}_a_{m}"], rtol=1e-10, atol=1e-11)
+            np.testing.assert_allclose(lm[m], g[f"{name}_lm_{m}"], rtol=1e-10, atol=1e-11)
+            np.testing.assert_allclose(prices[m], g[f"{name}_prices"][m], rtol=1e-10, atol=1e-13)
+    params = HawkesJDParams(**dict(zip(hawkes.KEYS, g["dflt_params"])), risk_premia_gamma=float(g["gamma"]))
+    norm, gfw = hawkesjd_forwards_under_risk_kernel(params, float(g["gamma"]), ttms, fw)
+    np.testing.assert_allclose(norm, g["gamma_normalizers"], rtol=1e-11)
+    np.testing.assert_allclose(gfw, g["gamma_forwards"], rtol=1e-11)
+    gp = hawkesjd_chain_pricer_with_risk_premia(params, ttms, fw, df, Ks, Ts)
+    chain = OptionChain(ttms=ttms, forwards=fw, discfactors=df, strikes_ttms=Ks, optiontypes_ttms=Ts)
+    api = HawkesJDPricer().price_chain(chain, params)
+    for m in range(3):
+        np.testing.assert_allclose(gp[m], g["gamma_prices"][m], rtol=1e-10, atol=1e-13)
+        np.testing.assert_array_equal(api[m], gp[m])
+    assert set_vol_scaler(0.45, 0.05) == np.clip(0.45, 0.2, 0.5) * np.sqrt(0.05)
+    # a grid the goldens do not cover: the oracle (SciPy-RK45 clone on the same Riccati system), inverse-measure payoffs
+    po = hawkes.fourier_chain_prices(dict(zip(hawkes.KEYS, g["alt_params"])), ttms[:2], fw[:2], df[:2], Ks[:2], [np.array(["IP", "P", "C", "IC", "IC"])] * 2,
+                                     is_spot_measure=False, vol_scaler=0.2)
+    pg = hawkesjd_chain_pricer(HawkesJDParams(**dict(zip(hawkes.KEYS, g["alt_params"]))), ttms[:2], fw[:2], df[:2], Ks[:2],
+                               [np.array(["IP", "P", "C", "IC", "IC"])] * 2, is_spot_measure=False, vol_scaler=0.2)
+    for m in range(2):
+        np.testing.assert_allclose(pg[m], po[m], rtol=1e-10, atol=1e-13)
+    with pytest.raises(ValueError, match="not implemented"):
+        hawkesjd_chain_pricer_with_risk_premia(params, ttms, fw, df, Ks, [np.array(["IP", "P", "C", "C", "C"])] * 3)
+    with pytest.raises(NotImplementedError):
+        hawkesjd_chain_pricer(params, ttms, fw, df, Ks, Ts, is_stiff_solver=True)

@@ -347,3 +347,27 @@ def test_bdf_branch_oracle_vs_reference_golden(name):
         a = mgf.logsv_bdf_a_grid(ttm - t0, phi, np.zeros_like(phi), a, theta, k1, k2, beta, vv, bool(spot), int(order), eta)
         np.testing.assert_allclose(a, g[f"{name}_a_{m}"], rtol=1e-11, atol=1e-12)
         t0 = ttm
+
+
+def test_hawkes_fourier_oracle_vs_reference_golden():
+    """oracle/hawkes.py Fourier route (the Riccati system through the SciPy-RK45 clone) vs the reference's own outputs: ODE grids, log-MGF, chain
+    prices, and the risk-kernel normalisers / forwards / prices"""
+    from oracle import hawkes
+    g = load_golden("hawkes_fourier.npz")
+    K, T, ttms, fw, df = g["strikes"], g["types"], g["ttms"], g["forwards"], g["discfactors"]
+    Ks, Ts = [K * f for f in fw], [T] * 3
+    for name in ("dflt", "alt"):
+        p = dict(zip(hawkes.KEYS, g[f"{name}_params"]))
+        prices, grids, phi = hawkes.fourier_chain_prices(p, ttms, fw, df, Ks, Ts, return_grids=True)
+        np.testing.assert_allclose(phi, g[f"{name}_phi"], rtol=0, atol=1e-13)
+        for m in range(3):
+            np.testing.assert_allclose(grids[m][0], g[f"{name}_a_{m}"], rtol=1e-11, atol=5e-12)
+            np.testing.assert_allclose(grids[m][1], g[f"{name}_lm_{m}"], rtol=1e-11, atol=5e-12)
+            np.testing.assert_allclose(prices[m], g[f"{name}_prices"][m], rtol=1e-11)
+    p, gamma = dict(zip(hawkes.KEYS, g["dflt_params"])), float(g["gamma"])
+    norm, gfw = hawkes.forwards_under_risk_kernel(p, gamma, ttms, fw)
+    np.testing.assert_allclose(norm, g["gamma_normalizers"], rtol=1e-12)
+    np.testing.assert_allclose(gfw, g["gamma_forwards"], rtol=1e-12)
+    prices = hawkes.fourier_chain_prices(p, ttms, fw, df, Ks, Ts, gamma=gamma)
+    for m in range(3):
+        np.testing.assert_allclose(prices[m], g["gamma_prices"][m], rtol=1e-11)
