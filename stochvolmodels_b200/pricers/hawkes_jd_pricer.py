@@ -100,6 +100,65 @@ class HawkesJDPricer(ModelPricer):
                                         variable_type=kwargs.get("variable_type", VariableType.LOG_RETURN),
                                         distributed=kwargs.get("distributed", True), exchange=kwargs.get("exchange"), **d)
 
+    # ---- calibration drivers (reference :230-357): SLSQP on the host around the GPU Fourier chain pricer -----------------------------
+    def _vol_objective(self, option_chain: OptionChain, unpack, is_vega_weighted: bool, is_unit_ttm_vega: bool, scale: float = 1.0):
+        """weighted squared difference of model and mid implied vols (nansum: quotes whose model price leaves the no-arbitrage bounds drop out)"""
+        market = np.concatenate([np.asarray(v, dtype=float) for v in option_chain.get_mid_vols()])
+        if is_vega_weighted:
+            weights = np.concatenate([v / np.sum(v) for v in option_chain.get_chain_vegas(is_unit_ttm_vega=is_unit_ttm_vega)])
+        else:
+            weights = np.ones_like(market)
+
+        def objective(pars: np.ndarray, *_) -> float:
+            model = np.concatenate(self.compute_model_ivols_for_chain(option_chain=option_chain, params=unpack(pars)))
+            return float(np.nansum(scale * weights * np.square(model - market)))
+        return objective
+
+    @timer
+    def calibrate_model_params_to_chain(self, option_chain: OptionChain, params0: HawkesJDParams, is_vega_weighted: bool = True,
+                                        is_unit_ttm_vega: bool = False, **kwargs) -> HawkesJDParams:
+        """fit (sigma, mean_p, mean_m, theta_p, theta_m, kappa, beta_p, beta_m) to the chain's mid vols with shifts and initial intensities
+        fixed at ``params0``'s; kappa is shared by the two intensities and beta_p / beta_m enter as +beta / -beta pairs (reference :230-300, same
+        start vector -- including its beta_m start 0.5 (beta2_p - beta2_m) --, bounds, stationarity constraint and SLSQP options).
+        ``disp`` / ``maxiter`` (extras) are handed to SLSQP."""
+        from scipy.optimize import minimize
+        p0 = np.array([params0.sigma, params0.mean_p, params0.mean_m, params0.theta_p, params0.theta_m, 0.5 * (params0.kappa_p + params0.kappa_m),
+                       0.5 * (params0.beta1_p - params0.beta2_p), 0.5 * (params0.beta2_p - params0.beta2_m)])
+        bounds = ((0.10, 2.0), (0.01, 0.99), (-0.99, -0.01), (0.01, 100.0), (0.01, 100.0), (1.0, 100.0), (1.0, 100.0), (1.0, 100.0))
+
+        def unpack(x: np.ndarray) -> HawkesJDParams:
+            return HawkesJDParams(mu=0.0, sigma=x[0], shift_p=params0.shift_p, mean_p=x[1], shift_m=params0.shift_m, mean_m=x[2],
+                                  lambda_p=params0.lambda_p, theta_p=x[3], kappa_p=x[5], beta1_p=x[6], beta2_p=-x[6], lambda_m=params0.lambda_m,
+                                  theta_m=x[4], kappa_m=x[5], beta1_m=x[7], beta2_m=-x[7])
+
+        stationary = {"type": "ineq", "fun": lambda x: unpack(x).jump1_cond + unpack(x).jump2_cond}
+        options = {"disp": bool(kwargs.get("disp", False)), "ftol": 1e-8}
+        if "maxiter" in kwargs:
+            options["maxiter"] = int(kwargs["maxiter"])
+        res = minimize(self._vol_objective(option_chain, unpack, is_vega_weighted, is_unit_ttm_vega), p0, args=None, method="SLSQP",
+                       constraints=stationary, bounds=bounds, options=options)
+        return unpack(res.x)
+
+    @timer
+    def calibrate_risk_premia_gamma_to_chain(self, option_chain: OptionChain, params0: HawkesJDParams, is_vega_weighted: bool = True,
+                                             is_unit_ttm_vega: bool = False, maxiter: int = 100, print_iter: bool = True, **kwargs) -> HawkesJDParams:
+        """fit (sigma, risk_premia_gamma) with every other parameter of ``params0`` fixed (reference :303-357: gamma scaled by 8 into (-1, 1),
+        weights x 1e4, SLSQP with finite-difference step 0.025, ftol = tol = 1e-16).  Returns a new object; the reference mutates ``params0``."""
+        from scipy.optimize import minimize
+        gamma_scaler = 8.0
+        fixed = {k: v for k, v in params0.to_dict().items() if k in _KEYS}
+
+        def unpack(x: np.ndarray) -> HawkesJDParams:
+            if print_iter:
+                print(f"unpack_pars: sigma={x[0]}, gamma={gamma_scaler * x[1]}")
+            return HawkesJDParams(**{**fixed, "sigma": float(x[0])}, risk_premia_gamma=float(gamma_scaler * x[1]))
+
+        p0 = np.array([params0.sigma, (params0.risk_premia_gamma or 0.0) / gamma_scaler])
+        res = minimize(self._vol_objective(option_chain, unpack, is_vega_weighted, is_unit_ttm_vega, scale=10000.0), p0, args=None, method="SLSQP",
+                       bounds=((0.01, 1.5), (-1.0, 1.0)), options={"disp": bool(kwargs.get("disp", False)), "ftol": 1e-16, "maxiter": maxiter, "eps": 0.025},
+                       tol=1e-16)
+        return unpack(res.x)
+
     @timer
     def simulate_terminal_values(self, params: HawkesJDParams, ttm: float = 1.0, nb_path: int = 100000, is_spot_measure: bool = True, **kwargs
                                  ) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:

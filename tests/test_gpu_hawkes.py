@@ -172,3 +172,39 @@ def test_fourier_route_vs_reference_golden_and_oracle(cuda_lib):
         hawkesjd_chain_pricer_with_risk_premia(params, ttms, fw, df, Ks, [np.array(["IP", "P", "C", "C", "C"])] * 3)
     with pytest.raises(NotImplementedError):
         hawkesjd_chain_pricer(params, ttms, fw, df, Ks, Ts, is_stiff_solver=True)
+
+
+def test_hawkes_calibration_drivers_recover_a_synthetic_market(cuda_lib):
+    """calibrate_model_params_to_chain / calibrate_risk_premia_gamma_to_chain (reference :230-357) around the GPU Fourier pricer: a market
+    generated by the model itself is re-fitted from a perturbed start (objective -> ~0, implied vols reproduced)"""
+    from stochvolmodels_b200 import HawkesJDParams, HawkesJDPricer, OptionChain
+    pricer = HawkesJDPricer()
+    K = np.linspace(0.75, 1.3, 12)
+    ttms, fw = np.array([0.08, 0.25, 0.5]), np.array([1.0, 1.0, 1.0])
+    mk = lambda vols: OptionChain(ttms=ttms, forwards=fw, strikes_ttms=[K] * 3, optiontypes_ttms=[np.where(K >= 1.0, "C", "P")] * 3,
+                                  ids=np.array(["1m", "3m", "6m"]), bid_ivs=vols, ask_ivs=[v.copy() for v in vols])
+    flat = mk([0.5 * np.ones_like(K)] * 3)
+    # the reference's parametrisation: shared kappa, +-beta pairs
+    true = HawkesJDParams(sigma=0.4, mean_p=0.04, mean_m=-0.05, theta_p=6.0, theta_m=8.0, kappa_p=25.0, kappa_m=25.0, beta1_p=30.0, beta2_p=-30.0,
+                          beta1_m=40.0, beta2_m=-40.0)
+    market = pricer.compute_model_ivols_for_chain(flat, true)
+    assert all(np.all(np.isfinite(v)) for v in market)
+    chain = mk(market)
+    start = HawkesJDParams(sigma=0.45, mean_p=0.03, mean_m=-0.04, theta_p=7.0, theta_m=7.0, kappa_p=22.0, kappa_m=28.0, beta1_p=33.0, beta2_p=-33.0,
+                           beta1_m=36.0, beta2_m=-36.0)
+    fit = pricer.calibrate_model_params_to_chain(chain, start, maxiter=60)
+    refit = pricer.compute_model_ivols_for_chain(chain, fit)
+    before = pricer.compute_model_ivols_for_chain(chain, start)
+    err = lambda v: max(np.max(np.abs(a - b)) for a, b in zip(v, market))
+    assert err(refit) < 5e-3 and err(refit) < 0.2 * err(before), (err(refit), err(before))     # 8 weakly identified parameters, ftol 1e-8
+    assert fit.kappa_p == fit.kappa_m and fit.beta2_p == -fit.beta1_p and fit.beta2_m == -fit.beta1_m and fit.shift_p == start.shift_p
+    assert fit.jump1_cond + fit.jump2_cond >= -1e-8
+    # risk-premium kernel: market generated with gamma = 0.5 and sigma = 0.42, start from (0.45, 0.2)
+    true_g = HawkesJDParams(sigma=0.42, risk_premia_gamma=0.5)
+    chain_g = mk(pricer.compute_model_ivols_for_chain(flat, true_g))
+    fit_g = pricer.calibrate_risk_premia_gamma_to_chain(chain_g, HawkesJDParams(sigma=0.45, risk_premia_gamma=0.2), print_iter=False)
+    vols_g = lambda p_: pricer.compute_model_ivols_for_chain(chain_g, p_)
+    err_g = lambda v: max(np.max(np.abs(a - b)) for a, b in zip(v, chain_g.get_mid_vols()))
+    e_fit, e_start = err_g(vols_g(fit_g)), err_g(vols_g(HawkesJDParams(sigma=0.45, risk_premia_gamma=0.2)))
+    # sigma and gamma trade off along a shallow valley and the reference's finite-difference step is 0.025: the fit is judged on the vols
+    assert e_fit < 0.5 * e_start and 0.3 < fit_g.risk_premia_gamma < 0.7 and abs(fit_g.sigma - 0.42) < 0.01, (e_fit, e_start, fit_g)
