@@ -40,3 +40,17 @@ Kq, Tq = g["strikes"], np.array(["C"] * len(g["strikes"]))
 prices, med, mn = timed(lambda: logsv_chain_pricer(Q, g["ttms"], np.ones(2), g["discfactors"], [Kq, Kq], [Tq, Tq], variable_type=VariableType.Q_VAR), reps=10)
 rel = max(np.max(np.abs(prices[m] / g[f"prices_{m}"] - 1)) for m in range(2))
 print(f"{'logsv Q_VAR 2x5':16s} GPU e2e median {med:8.3f} ms (min {mn:.3f})  max rel err vs reference golden {rel:.2e}  [2 maturities x 40000 RK45 solves]")
+
+# ---- Hawkes jump-diffusion Fourier route (3 maturities x 500-point grid; reference: 3 x 500 solve_ivp calls, 7.9 s on this container's CPU)
+from stochvolmodels_b200 import HawkesJDParams
+from stochvolmodels_b200.pricers.hawkes_jd_pricer import hawkesjd_chain_pricer, hawkesjd_chain_pricer_with_risk_premia
+g = np.load(os.path.join(G, "hawkes_fourier.npz"), allow_pickle=True)
+Kh, Th = [g["strikes"] * f for f in g["forwards"]], [g["types"]] * 3
+hp = HawkesJDParams(**dict(zip([str(k) for k in g["keys"]], g["dflt_params"])))
+prices, med, mn = timed(lambda: hawkesjd_chain_pricer(hp, g["ttms"], g["forwards"], g["discfactors"], Kh, Th))
+rel = max(np.max(np.abs(prices[m] / g["dflt_prices"][m] - 1)) for m in range(3))
+print(f"{'hawkes 3x5':16s} GPU e2e median {med:8.3f} ms (min {mn:.3f})  max rel err vs reference golden {rel:.2e}")
+hg = HawkesJDParams(**dict(zip([str(k) for k in g["keys"]], g["dflt_params"])), risk_premia_gamma=float(g["gamma"]))
+prices, med, mn = timed(lambda: hawkesjd_chain_pricer_with_risk_premia(hg, g["ttms"], g["forwards"], g["discfactors"], Kh, Th))
+rel = max(np.max(np.abs(prices[m] / g["gamma_prices"][m] - 1)) for m in range(3))
+print(f"{'hawkes gamma 3x5':16s} GPU e2e median {med:8.3f} ms (min {mn:.3f})  max rel err vs reference golden {rel:.2e}  [risk kernel]")
