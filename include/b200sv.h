@@ -253,6 +253,10 @@ int b200sv_hawkesjd_price_chain(const b200sv_hawkes_params* params, int M, const
                                 const int* offsets, const double* strikes, const int8_t* types, int is_spot_measure, double vol_scaler, int P,
                                 double risk_premia_gamma, double* prices_out, double* a_out, double* log_mgf_out, double* normalizers_out,
                                 double* gamma_forwards_out);
+/* compute_hawkes_a_mgf_grid / solve_a_ode_grid (pricers/hawkes_jd_pricer.py:518-579) on caller-supplied transform grids (complex128 as interleaved
+ * doubles; psi may be NULL = zeros): a_inout [P][3] holds A(0) on entry and A(dtau) on return, log_mgf_out [P] = a0 + a_p lambda_p + a_m lambda_m */
+int b200sv_hawkesjd_mgf_grid(const double* phi, const double* psi, int P, double dtau, double* a_inout, const b200sv_hawkes_params* params,
+                             double* log_mgf_out);
 /* slice_pricer_with_mgf_grid_with_gamma (utils/mgf_pricer.py:273-320) on caller-supplied grids (complex128 as interleaved doubles) */
 int b200sv_fourier_gamma(const double* log_mgf, const double* phi, int P, double risk_premia_gamma, double forward, double normalizer,
                          double gamma_forward, const double* strikes, const int8_t* types, int J, int is_spot_measure, double* prices_out);

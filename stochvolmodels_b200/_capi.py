@@ -72,6 +72,7 @@ SIGNATURES = {
                                     c_int, c_uint64, c_int, _dp, _dp, _dp, _dp],
     "b200sv_hawkesjd_mc_chain": [_kp, c_int, _dp, _dp, _dp, _ip, _dp, _i8p, c_longlong, c_int, c_uint64, c_int, _dp, _dp],
     "b200sv_hawkesjd_price_chain": [_kp, c_int, _dp, _dp, _dp, _ip, _dp, _i8p, c_int, c_double, c_int, c_double, _dp, _dp, _dp, _dp, _dp],
+    "b200sv_hawkesjd_mgf_grid": [_dp, _dp, c_int, c_double, _dp, _kp, _dp],
     "b200sv_fourier_gamma": [_dp, _dp, c_int, c_double, c_double, c_double, c_double, _dp, _i8p, c_int, c_int, _dp],
     "b200sv_hawkesjd_terminal": [_kp, c_double, c_longlong, c_uint64, c_int, c_int, c_int, _dp, _dp, _dp],
     "b200sv_hawkesjd_step_fixed": [_dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, c_int, c_longlong, c_double, _kp],

@@ -1882,6 +1882,41 @@ int b200sv_hawkesjd_price_chain(const b200sv_hawkes_params* params, int M, const
   return 0;
 }
 
+/* compute_hawkes_a_mgf_grid (hawkes_jd_pricer.py:518-547) on caller-supplied grids: A(0) = a_inout [P][3] -> A(dtau) in place, log_mgf_out [P] */
+int b200sv_hawkesjd_mgf_grid(const double* phi, const double* psi, int P, double dtau, double* a_inout, const b200sv_hawkes_params* params,
+                             double* log_mgf_out) {
+  B200SV_REQUIRE(phi && a_inout && params && log_mgf_out, "null pointer");
+  B200SV_REQUIRE(P >= 1 && dtau > 0.0, "P >= 1, dtau > 0");
+  const HawkesMgfConsts c = make_hawkes_mgf_consts(*params);
+  cudaStream_t st = current_stream();
+  ensure_pool_threshold();
+  DevBuf d_phi(st), d_psi(st), d_dt(st), d_a0(st), d_a1(st), d_lm(st);
+  B200SV_CUDA(d_phi.alloc(sizeof(cd) * P));
+  B200SV_CUDA(d_psi.alloc(sizeof(cd) * P));
+  B200SV_CUDA(d_dt.alloc(sizeof(double)));
+  B200SV_CUDA(d_a0.alloc(sizeof(cd) * (size_t)P * 3));
+  B200SV_CUDA(d_a1.alloc(sizeof(cd) * (size_t)P * 3));
+  B200SV_CUDA(d_lm.alloc(sizeof(cd) * P));
+  B200SV_CUDA(cudaMemcpyAsync(d_phi.p, phi, sizeof(cd) * P, cudaMemcpyHostToDevice, st));
+  if (psi) B200SV_CUDA(cudaMemcpyAsync(d_psi.p, psi, sizeof(cd) * P, cudaMemcpyHostToDevice, st));
+  B200SV_CUDA(cudaMemcpyAsync(d_dt.p, &dtau, sizeof(double), cudaMemcpyHostToDevice, st));
+  B200SV_CUDA(cudaMemcpyAsync(d_a0.p, a_inout, sizeof(cd) * (size_t)P * 3, cudaMemcpyHostToDevice, st));
+  const cd* dpsi = psi ? d_psi.as<cd>() : nullptr;
+  const int tpb = mgf_block_threads(P), nb = (P + tpb - 1) / tpb;
+  switch (tpb) {
+    case 4: hawkes_mgf_kernel<4><<<nb, 4, 0, st>>>(d_phi.as<cd>(), dpsi, P, 1, d_dt.as<double>(), c, d_a0.as<cd>(), d_a1.as<cd>(), d_lm.as<cd>(), 0, nullptr); break;
+    case 8: hawkes_mgf_kernel<8><<<nb, 8, 0, st>>>(d_phi.as<cd>(), dpsi, P, 1, d_dt.as<double>(), c, d_a0.as<cd>(), d_a1.as<cd>(), d_lm.as<cd>(), 0, nullptr); break;
+    case 16: hawkes_mgf_kernel<16><<<nb, 16, 0, st>>>(d_phi.as<cd>(), dpsi, P, 1, d_dt.as<double>(), c, d_a0.as<cd>(), d_a1.as<cd>(), d_lm.as<cd>(), 0, nullptr); break;
+    case 32: hawkes_mgf_kernel<32><<<nb, 32, 0, st>>>(d_phi.as<cd>(), dpsi, P, 1, d_dt.as<double>(), c, d_a0.as<cd>(), d_a1.as<cd>(), d_lm.as<cd>(), 0, nullptr); break;
+    default: hawkes_mgf_kernel<64><<<nb, 64, 0, st>>>(d_phi.as<cd>(), dpsi, P, 1, d_dt.as<double>(), c, d_a0.as<cd>(), d_a1.as<cd>(), d_lm.as<cd>(), 0, nullptr); break;
+  }
+  if (int rc = launched("hawkes_mgf_kernel")) return rc;
+  B200SV_CUDA(cudaMemcpyAsync(a_inout, d_a1.p, sizeof(cd) * (size_t)P * 3, cudaMemcpyDeviceToHost, st));
+  B200SV_CUDA(cudaMemcpyAsync(log_mgf_out, d_lm.p, sizeof(cd) * P, cudaMemcpyDeviceToHost, st));
+  B200SV_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
 int b200sv_logsv_mgf_grid(const double* phi, const double* psi, int P, double dtau, double* a_inout,
                           const b200sv_logsv_params* params, double eta, int is_spot_measure, int expansion_order,
                           double* log_mgf_out) {

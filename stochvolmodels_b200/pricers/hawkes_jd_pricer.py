@@ -293,3 +293,28 @@ def hawkesjd_forwards_under_risk_kernel(model_params: HawkesJDParams, risk_premi
     _, _, _, norm, gfw = _fourier_chain(p, ttms, forwards, np.ones_like(ttms), one, [np.array(["C"]) for _ in ttms], is_stiff_solver, True,
                                         VariableType.LOG_RETURN, None, float(risk_premia_gamma), return_grids=True)
     return norm, gfw
+
+
+def compute_hawkes_a_mgf_grid(ttm: float, phi_grid: np.ndarray, model_params: HawkesJDParams, psi_grid: Optional[np.ndarray] = None,
+                              a_t0: Optional[np.ndarray] = None, is_stiff_solver: bool = False, **kwargs) -> Tuple[np.ndarray, np.ndarray]:
+    """(a_t1 [P, 3], log_mgf [P]) over a caller-supplied transform grid (reference :518-547): A(ttm) from A(0) = ``a_t0`` (zeros by default) and
+    log-MGF = a0 + a_p lambda_p + a_m lambda_m"""
+    if is_stiff_solver:
+        raise NotImplementedError("is_stiff_solver: the Hawkes Fourier route runs SciPy's RK45 control law on the GPU; its BDF variant is not built")
+    phi = C.c128(phi_grid)
+    psi = None if psi_grid is None else C.c128(psi_grid)
+    a = np.zeros((phi.shape[0], 3), dtype=np.complex128) if a_t0 is None else np.ascontiguousarray(a_t0, dtype=np.complex128).copy()
+    if a.shape != (phi.shape[0], 3):
+        raise ValueError("a_t0 must have shape (len(phi_grid), 3)")
+    d = model_params.to_dict()
+    d.pop("risk_premia_gamma", None)
+    lm = np.empty(phi.shape[0], dtype=np.complex128)
+    cp = lambda arr: None if arr is None else arr.ctypes.data_as(C._dp)
+    C.call("b200sv_hawkesjd_mgf_grid", cp(phi), cp(psi), phi.shape[0], float(ttm), cp(a), byref(_params_c(**d)), cp(lm))
+    return a, lm
+
+
+def solve_a_ode_grid(phi_grid: np.ndarray, ttm: float, model_params: HawkesJDParams, psi_grid: Optional[np.ndarray] = None,
+                     a_t0: Optional[np.ndarray] = None, is_stiff_solver: bool = False) -> np.ndarray:
+    """A(ttm) per transform point (reference :550-579)"""
+    return compute_hawkes_a_mgf_grid(ttm, phi_grid, model_params, psi_grid=psi_grid, a_t0=a_t0, is_stiff_solver=is_stiff_solver)[0]

@@ -161,6 +161,17 @@ def test_fourier_route_vs_reference_golden_and_oracle(cuda_lib):
         np.testing.assert_allclose(gp[m], g["gamma_prices"][m], rtol=1e-10, atol=1e-13)
         np.testing.assert_array_equal(api[m], gp[m])
     assert set_vol_scaler(0.45, 0.05) == np.clip(0.45, 0.2, 0.5) * np.sqrt(0.05)
+    # grid entry points: the second maturity from the first one's A on a sub-grid; a psi grid against the oracle
+    from stochvolmodels_b200.pricers.hawkes_jd_pricer import compute_hawkes_a_mgf_grid, solve_a_ode_grid
+    pa = HawkesJDParams(**dict(zip(hawkes.KEYS, g["alt_params"])))
+    sub = slice(0, 500, 7)
+    a1, lm1 = compute_hawkes_a_mgf_grid(ttms[1] - ttms[0], g["alt_phi"][sub], pa, a_t0=g["alt_a_0"][sub])
+    np.testing.assert_allclose(a1, g["alt_a_1"][sub], rtol=1e-10, atol=1e-11)
+    np.testing.assert_allclose(lm1, g["alt_lm_1"][sub], rtol=1e-10, atol=1e-11)
+    psi = -0.3 + 1j * np.linspace(0.0, 40.0, 33)
+    phi0 = np.zeros_like(psi)
+    ao, _ = hawkes.a_mgf_grid(0.2, phi0, dict(zip(hawkes.KEYS, g["alt_params"])), psi=psi)
+    np.testing.assert_allclose(solve_a_ode_grid(phi0, 0.2, pa, psi_grid=psi), ao, rtol=1e-10, atol=1e-11)
     # a grid the goldens do not cover: the oracle (SciPy-RK45 clone on the same Riccati system), inverse-measure payoffs
     po = hawkes.fourier_chain_prices(dict(zip(hawkes.KEYS, g["alt_params"])), ttms[:2], fw[:2], df[:2], Ks[:2], [np.array(["IP", "P", "C", "IC", "IC"])] * 2,
                                      is_spot_measure=False, vol_scaler=0.2)
