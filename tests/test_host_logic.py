@@ -363,3 +363,14 @@ def test_chain_deltas_and_skews():
                              ask_ivs=[smile])
     with pytest.raises(ValueError, match="both put and call"):
         calls_only.get_chain_skews()
+
+
+def test_small_host_utilities_of_utils_funcs():
+    from stochvolmodels_b200.utils.funcs import compute_histogram_data, find_nearest, ncdf, npdf, update_kwargs, erfcc
+    a = np.array([0.1, 0.25, 0.5, 1.0])
+    assert find_nearest(a, 0.3) == 0.25 and find_nearest(a, 0.3, is_equal_or_largest=True) == 0.5 and find_nearest(a, 0.25, is_equal_or_largest=True) == 0.25
+    assert find_nearest(a, 5.0) == 1.0 and find_nearest(a[::-1], 0.45, is_sorted=False) == 0.5 and find_nearest(a, 0.375) == 0.5      # tie: upper
+    assert update_kwargs({"a": 1}, None) == {"a": 1} and update_kwargs({"a": 1}, {"a": 2, "b": 3}) == {"a": 2, "b": 3}
+    np.testing.assert_allclose([ncdf(0.0), ncdf(1.959963984540054), npdf(0.0), erfcc(0.0)], [0.5, 0.975, 1 / np.sqrt(2 * np.pi), 1.0], rtol=1e-12)
+    h = compute_histogram_data(np.array([0.1, 0.2, 0.2, 0.9]), np.linspace(0.0, 1.0, 5))
+    assert h.shape == (5,) and h.iloc[1] == 0.75 and h.iloc[4] == 0.25 and h.index[-1] == 1.0
