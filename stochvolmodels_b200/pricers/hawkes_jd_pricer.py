@@ -178,9 +178,10 @@ def hawkesjd_mc_chain_pricer(ttms, forwards, discfactors, strikes_ttms, optionty
     the TOTAL path count, sharded over the ranks by global path id (the LogSV chain's two exchanges per maturity, multi_gpu.py)."""
     vt = engine.variable_code(variable_type)
     pc = _params_c(**locals())
-    seed = engine.fresh_seed() if seed is None else int(seed)
+    from .logsv_pricer import _shared_seed, _use_distributed
+    seed = _shared_seed(seed)
     from .logsv_pricer import _use_distributed
-    if _use_distributed({"distributed": distributed}):
+    if _use_distributed({"distributed": distributed, "nb_path": nb_path, "exchange": exchange}):
         from ..multi_gpu import mc_chain_distributed
         C.encode_types(np.concatenate([np.asarray(t) for t in optiontypes_ttms]))
         return mc_chain_distributed("hawkes", pc, ttms, forwards, discfactors, None, strikes_ttms, optiontypes_ttms, nb_path, STEPS_PER_YEAR,

@@ -113,8 +113,9 @@ def heston_mc_chain_pricer(ttms, forwards, discfactors, strikes_ttms, optiontype
     from .logsv_pricer import _use_distributed
     params_c = _params_c(v0, theta, kappa, rho, volvol)
     flags = engine.mc_flags(precision, gauss)
-    seed = engine.fresh_seed() if seed is None else int(seed)
-    if _use_distributed({"distributed": distributed}):
+    from .logsv_pricer import _shared_seed
+    seed = _shared_seed(seed)
+    if _use_distributed({"distributed": distributed, "nb_path": nb_path, "exchange": exchange}):
         from ..multi_gpu import mc_chain_distributed
         C.encode_types(np.concatenate([np.asarray(t) for t in optiontypes_ttms]))
         return mc_chain_distributed("heston", params_c, ttms, forwards, discfactors, None, strikes_ttms, optiontypes_ttms, nb_path,

@@ -158,14 +158,46 @@ def _params_c(params) -> C.LogsvParamsC:
     return engine.logsv_params_c(params.sigma0, params.theta, params.kappa1, kappa2, params.beta, params.volvol)
 
 
+def _shared_seed(seed) -> int:
+    """the Philox key of an MC call: the caller's ``seed``, or a fresh one -- which under a torch.distributed world must be the SAME on every rank
+    (sharded: one stream over all paths; replicated: identical prices everywhere), so rank 0 draws it and broadcasts"""
+    if seed is not None:
+        return int(seed)
+    value = engine.fresh_seed()
+    try:
+        import torch
+        import torch.distributed as dist
+    except Exception:
+        return value
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        device = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        box = torch.tensor([value & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64, device=device)
+        dist.broadcast(box, src=0)
+        value = int(box.item())
+    return value
+
+
+SHARD_MIN_PATHS = 500_000      # below this a chain call is launch-bound: one GPU prices it faster than N GPUs exchanging moments (r02 profile)
+
+
 def _use_distributed(kwargs) -> bool:
+    """shard this Monte Carlo call over the ranks of the initialised torch.distributed world?  Small calls (``nb_path`` < SHARD_MIN_PATHS, env
+    B200SV_SHARD_MIN_PATHS) are priced REPLICATED instead -- every rank runs all the paths on its own GPU through the single-launch chain
+    kernel and gets bit-identical prices (the Philox counter is the global path id), 0.17 ms against 0.53 ms sharded at 1e4 paths on 2 GPUs
+    (`profiles/r02_multi_gpu_latency.txt`).  Naming an ``exchange`` forces the sharded route."""
     if not kwargs.get("distributed", True):
         return False
     try:
         import torch.distributed as dist
     except Exception:       # torch absent: single-process only
         return False
-    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return False
+    nb_path = kwargs.get("nb_path")
+    if nb_path is not None and kwargs.get("exchange") is None:
+        import os
+        return int(nb_path) >= int(os.environ.get("B200SV_SHARD_MIN_PATHS", SHARD_MIN_PATHS))
+    return True
 
 
 class LogSVPricer(ModelPricer):
@@ -372,8 +404,8 @@ def logsv_mc_chain_pricer(ttms: np.ndarray, forwards: np.ndarray, discfactors: n
     TOTAL path count, sharded over the ranks (two fp64 all-reduces per maturity)."""
     params_c = engine.logsv_params_c(v0, theta, kappa1, kappa2, beta, volvol)
     flags = engine.mc_flags(precision, gauss)
-    seed = engine.fresh_seed() if seed is None else int(seed)
-    if _use_distributed({"distributed": distributed}):
+    seed = _shared_seed(seed)
+    if _use_distributed({"distributed": distributed, "nb_path": nb_path, "exchange": exchange}):
         from ..multi_gpu import mc_chain_distributed
         C.encode_types(np.concatenate([np.asarray(t) for t in optiontypes_ttms]))
         return mc_chain_distributed("logsv", params_c, ttms, forwards, discfactors, vol_backbone_etas, strikes_ttms,
@@ -513,11 +545,11 @@ def rough_logsv_mc_chain_pricer_fixed_randoms(ttms, forwards, discfactors, strik
     nsteps = [int(np.asarray(g).size) - 1 for g in timegrids]
     hs = [float(np.asarray(g)[1] - np.asarray(g)[0]) for g in timegrids]             # split_simulation.py:346
     params_c = engine.logsv_params_c(sigma0, theta, kappa1, kappa2, beta, orthog_vol)
-    if Z0 is None and not (return_states or debug) and _use_distributed({"distributed": distributed}):
+    if Z0 is None and not (return_states or debug) and _use_distributed({"distributed": distributed, "nb_path": nb_path, "exchange": exchange}):
         from ..multi_gpu import mc_chain_distributed
         C.encode_types(np.concatenate([np.asarray(t) for t in optiontypes_ttms]))
         return mc_chain_distributed("rough", params_c, ttms, forwards, discfactors, None, strikes_ttms, optiontypes_ttms, nb_path, 0, True,
-                                    engine.variable_code(variable_type), engine.fresh_seed() if seed is None else int(seed),
+                                    engine.variable_code(variable_type), _shared_seed(seed),
                                     engine.mc_flags("fp64", gauss), exchange=exchange, grid=list(zip(nsteps, hs)), factors=(weights, nodes),
                                     se_paths=1)
     prices, stds, _, states, offsets = engine.rough_logsv_mc_chain([params_c], weights, nodes, ttms, forwards, discfactors, strikes_ttms,

@@ -148,3 +148,29 @@ def test_sharded_rough_chain_equals_unsharded_under_gloo():
         for m in range(2):
             np.testing.assert_allclose(p[m], pe[m], rtol=1e-11, atol=1e-14)
             np.testing.assert_allclose(e[m], ee[m], rtol=1e-9, atol=1e-14)
+
+
+def _policy_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from stochvolmodels_b200.pricers.logsv_pricer import SHARD_MIN_PATHS, _shared_seed, _use_distributed
+        out[rank] = dict(seed=_shared_seed(None), given=_shared_seed(42),
+                         small=_use_distributed({"nb_path": SHARD_MIN_PATHS - 1}), large=_use_distributed({"nb_path": SHARD_MIN_PATHS}),
+                         forced=_use_distributed({"nb_path": 10, "exchange": "collective"}), off=_use_distributed({"distributed": False, "nb_path": 10 ** 9}),
+                         unknown=_use_distributed({}))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_or_replicate_policy_and_shared_seed_under_gloo():
+    """small Monte Carlo calls are replicated instead of sharded (launch-bound: one GPU is faster), a named exchange forces sharding, and a
+    seedless call uses ONE seed on all ranks (rank 0's, broadcast)"""
+    world, port = 2, _free_port()
+    out = mp.Manager().dict()
+    mp.spawn(_policy_worker, args=(world, port, out), nprocs=world, join=True)
+    assert out[0]["seed"] == out[1]["seed"] and out[0]["given"] == out[1]["given"] == 42
+    for r in range(world):
+        assert out[r]["small"] is False and out[r]["large"] is True and out[r]["forced"] is True and out[r]["off"] is False and out[r]["unknown"] is True
+    from stochvolmodels_b200.pricers.logsv_pricer import _use_distributed
+    assert _use_distributed({"nb_path": 10 ** 9}) is False          # no process group: never sharded

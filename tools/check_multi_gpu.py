@@ -36,7 +36,7 @@ rough_params = LogSvParams(sigma0=0.8, theta=1.0, kappa1=2.2, kappa2=2.2, beta=0
                            nodes=np.array([0.05, 1.5, 20.0]))
 for name, pricer, params, kw, n in (("hawkes", HawkesJDPricer(), HawkesJDParams(), {}, 400_001),
                                     ("rough", LogSVPricer(), rough_params, dict(use_rough_mc=True, gauss="fp32", nb_steps=360), 400_001)):
-    p_d, e_d = pricer.model_mc_price_chain(chain, params, nb_path=n, seed=321, **kw)
+    p_d, e_d = pricer.model_mc_price_chain(chain, params, nb_path=n, seed=321, exchange="p2p", **kw)
     p_c, e_c = pricer.model_mc_price_chain(chain, params, nb_path=n, seed=321, exchange="collective", **kw)
     p_s, e_s = pricer.model_mc_price_chain(chain, params, nb_path=n, seed=321, distributed=False, **kw)
     rel_p = max(np.max(np.abs(a / b - 1)) for a, b in zip(p_d, p_s))
@@ -45,6 +45,20 @@ for name, pricer, params, kw, n in (("hawkes", HawkesJDPricer(), HawkesJDParams(
     if rank == 0:
         print(f"{name}: world={world} N={n} max rel diff vs single GPU: prices p2p {rel_p:.2e} NCCL {rel_c:.2e} stderr {rel_e:.2e}", flush=True)
     ok &= rel_p < 1e-12 and rel_c < 1e-12 and rel_e < 1e-10
+
+# small calls are priced REPLICATED (every rank runs all paths through the single-launch kernel): bit-identical to this rank alone, the same on
+# every rank -- also without a seed (rank 0's fresh seed is broadcast)
+lp = LogSVPricer()
+r_seed = lp.model_mc_price_chain(chain, LOGSV_BTC_PARAMS, nb_path=20_000, nb_steps=252, seed=5)
+r_single = lp.model_mc_price_chain(chain, LOGSV_BTC_PARAMS, nb_path=20_000, nb_steps=252, seed=5, distributed=False)
+same_single = all(np.array_equal(a, b) for a, b in zip(r_seed[0], r_single[0]))
+r_free = lp.model_mc_price_chain(chain, LOGSV_BTC_PARAMS, nb_path=20_000, nb_steps=252)
+gathered = [None] * world
+dist.all_gather_object(gathered, np.concatenate(r_free[0]).tobytes())
+same_ranks = all(g_ == gathered[0] for g_ in gathered)
+if rank == 0:
+    print(f"replicated small call: == single GPU bitwise {same_single}; seedless call identical on all ranks {same_ranks}", flush=True)
+ok &= same_single and same_ranks
 
 # ragged corner cases through the peer-memory exchange: a maturity without strikes, fewer paths than ranks (ranks without paths),
 # IC/IP payoffs (general payoff kernel), and many repeated calls (epoch wrap of the double-buffered mailbox)
@@ -59,7 +73,7 @@ for n in (world - 1, 3 * world + 1, 200_003):
     if n < 1:
         continue
     for rep in range(3):
-        a, ea = logsv_mc_chain_pricer(nb_path=n, seed=7 + rep, **rag)
+        a, ea = logsv_mc_chain_pricer(nb_path=n, seed=7 + rep, exchange="p2p", **rag)       # named exchange: sharded even for a few paths
         b, eb = logsv_mc_chain_pricer(nb_path=n, seed=7 + rep, distributed=False, **rag)
         d = max(np.max(np.abs(x - y)) for x, y in zip(a, b) if x.size)
         good = d < 1e-12 and all(np.all(np.isfinite(x)) for x in a)
@@ -74,3 +88,4 @@ dist.barrier()
 release_p2p()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
+

@@ -16,10 +16,10 @@ chain = get_btc_test_chain_data()
 pricer = LogSVPricer()
 if rank == 0:
     print(f"# BTC chain (4 maturities, 49 strikes), nb_steps=360, {world} GPUs; median of 20 calls, max over ranks; ms per call", flush=True)
-    print("total paths | p2p (fused) | NCCL all-reduce | single GPU (distributed=False)", flush=True)
+    print("total paths | p2p (fused) | NCCL all-reduce | single GPU (distributed=False) | default (replicated below 5e5 paths, else p2p)", flush=True)
 for n in (10_000, 100_000, 1_000_000, 10_000_000, 100_000_000):
     row = []
-    for kw in (dict(exchange="p2p"), dict(exchange="collective"), dict(distributed=False)):
+    for kw in (dict(exchange="p2p"), dict(exchange="collective"), dict(distributed=False), dict()):
         f = lambda: pricer.model_mc_price_chain(chain, LOGSV_BTC_PARAMS, nb_path=n, nb_steps=360, seed=1, **kw)
         for _ in range(3):
             f()
@@ -31,7 +31,7 @@ for n in (10_000, 100_000, 1_000_000, 10_000_000, 100_000_000):
         dist.all_reduce(med, op=dist.ReduceOp.MAX)
         row.append(1e3 * float(med.item()))
     if rank == 0:
-        print(f"{n:>11d} | {row[0]:10.3f} | {row[1]:10.3f} | {row[2]:10.3f}", flush=True)
+        print(f"{n:>11d} | {row[0]:10.3f} | {row[1]:10.3f} | {row[2]:10.3f} | {row[3]:10.3f}", flush=True)
 from stochvolmodels_b200.multi_gpu import release_p2p
 dist.barrier()
 release_p2p()
