@@ -565,6 +565,16 @@ def main():
                          "kernel_path_steps_per_s": sub["slice_path_steps"] / (sub["slice_ms"] / 1e3),
                          "same_prices_as_device_arm": bool(np.allclose(sub_prices_api, sub["prices"][0], rtol=1e-12)),
                          "max_abs_diff_vs_headline_in_se": float(np.max(np.abs(sub["prices"][0] - head["prices"][0]) / head["prices"][1]))}
+        if world == 1 and args.gauss == "fp32" and args.precision == "fp64":
+            # decomposition of the gap between the two draw modes: the fp64 Box-Muller ARITHMETIC on the default stream's 32-bit uniforms (one
+            # Philox call per two steps, |z| <= 6.66 like the float draws) -- what remains to all_fp64 is the second Philox call per two steps
+            try:
+                mid = device_arm("fp64_paired", 3, 3, False)
+                line["f64_box_muller_on_32bit_uniforms"] = {
+                    "dtype_detail": "f64 state / f64 Box-Muller arithmetic on 32-bit Philox uniforms (the check mode gauss='fp64_paired')",
+                    "value": mid["value"], "ms_per_step": mid["ms_per_step"], "steps": 3}
+            except Exception as exc:
+                line["f64_box_muller_on_32bit_uniforms"] = {"error": repr(exc)}
         if checks is not None:
             line["checks"] = checks
         # second half of BASELINE.json's metric: price error of the timed MC chain against the Fourier reference (our GPU Fourier route,
