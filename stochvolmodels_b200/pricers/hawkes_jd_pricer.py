@@ -1,15 +1,18 @@
-"""HawkesJDPricer on B200: the Monte Carlo route of the reference's ``pricers/hawkes_jd_pricer.py``.
+"""HawkesJDPricer on B200: the reference's ``pricers/hawkes_jd_pricer.py``, Monte Carlo and Fourier routes.
 
 * ``HawkesJDParams``                          (hawkes_jd_pricer.py:41-119)
 * ``HawkesJDPricer.model_mc_price_chain``     (:156-171) -> ``hawkesjd_mc_chain_pricer`` (:644-715)
 * ``HawkesJDPricer.simulate_terminal_values`` (:193-224) -> ``simulate_hawkesjd_terminal`` (:718-779)
+* ``HawkesJDPricer.price_chain``              (:125-155) -> ``hawkesjd_chain_pricer`` (:365-417) / ``hawkesjd_chain_pricer_with_risk_premia`` (:420-484),
+  ``hawkesjd_forwards_under_risk_kernel`` (:487-515), ``compute_hawkes_a_mgf_grid`` / ``solve_a_ode_grid`` (:518-579)
+* ``HawkesJDPricer.calibrate_model_params_to_chain`` (:230-300), ``calibrate_risk_premia_gamma_to_chain`` (:303-357): host SLSQP loops around the
+  GPU chain pricer
 
-The reference draws every random input from numpy's process-global generator; here they are drawn in-kernel from the Philox stream keyed
-by an explicit ``seed`` (default: OS entropy).  ``simulate_hawkesjd_terminal`` additionally accepts the five input blocks
-(``W0, U_P, U_M, J_P, J_M`` in the reference's own form) and then reproduces the reference arithmetic operation by operation.
-
-The Fourier route of this model (a 3-equation Riccati system per transform point, :480-640) and its calibration are outside the scope
-contract (SURVEY.md §8 names the Hawkes *Monte Carlo*): ``price_chain`` raises ``NotImplementedError``.
+Monte Carlo: the reference draws every random input from numpy's process-global generator; here they are drawn in-kernel from the Philox
+stream keyed by an explicit ``seed`` (default: the ``set_seed`` stream or OS entropy).  ``simulate_hawkesjd_terminal`` additionally accepts the five
+input blocks (``W0, U_P, U_M, J_P, J_M`` in the reference's own form) and then reproduces the reference arithmetic operation by operation.
+Fourier: the 3-equation Riccati system per transform point goes through the same SciPy-RK45 clone as the LogSV coefficient ODEs
+(csrc/mgf_kernels.cu, ``hawkes_mgf_kernel``); its stiff (BDF) variant is not built and raises.
 """
 from __future__ import annotations
 

@@ -14,7 +14,7 @@ RNG and exposes no seed; default = OS entropy), ``precision`` ('fp64' | 'fp32'),
 Unknown kwargs are accepted and ignored on both routes, as in the reference (:349, :376, :681).
 
 ``LogSVPricer.calibrate_model_params_to_chain`` (:441-558) runs on the batched GPU chain pricer (pricers/calibration.py); the
-rough-vol route (:1164-1232) is a neighbour of the hot path and out of scope.
+rough-vol route (``use_rough_mc=True``, :1164-1232 -> rough_logsv/split_simulation.py) runs on csrc/rough_kernels.cuh.
 """
 from __future__ import annotations
 
