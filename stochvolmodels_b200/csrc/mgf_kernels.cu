@@ -221,12 +221,7 @@ struct StageStore {
 // system (HawkesRhsFn); the control law does not depend on it.
 template <int N, int TPB, typename Rhs>
 __device__ int rk45_generic(cd (&y)[N], double T, const Rhs& rhs_fn, StageStore<N, TPB> K, int* nfev_out) {
-  constexpr double A[6][5] = {{0, 0, 0, 0, 0},
-                              {1.0 / 5, 0, 0, 0, 0},
-                              {3.0 / 40, 9.0 / 40, 0, 0, 0},
-                              {44.0 / 45, -56.0 / 15, 32.0 / 9, 0, 0},
-                              {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729, 0},
-                              {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656}};
+  // stage coefficients: c_A in constant memory (indexed by the non-unrolled stage loop)
   constexpr double B[6] = {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84};
   constexpr double E[7] = {-71.0 / 57600, 0, 71.0 / 16695, -71.0 / 1920, 17253.0 / 339200, -22.0 / 525, 1.0 / 40};
 
