@@ -100,3 +100,32 @@ def test_reference_heston_params_and_enum_values(ref, monkeypatch):
     assert engine.variable_code(ref["VariableType"].Q_VAR) == C.Q_VAR and engine.variable_code(ref["VariableType"].LOG_RETURN) == C.LOG_RETURN
     with pytest.raises(NotImplementedError):
         engine.variable_code(ref["VariableType"].SIGMA)
+
+
+def test_reference_hawkes_params_marshal_like_our_own(ref, monkeypatch):
+    """the reference's own HawkesJDParams (and OptionChain) through HawkesJDPricer: Monte Carlo and Fourier routes, with and without the risk
+    kernel -- same C calls, same sixteen floats, same gamma"""
+    import stochvolmodels_b200 as svm
+    from stochvolmodels_b200 import _capi as C
+    sys.path.insert(0, REF_SRC)
+    try:
+        from stochvolmodels.pricers.hawkes_jd_pricer import HawkesJDParams as RefHawkes
+    finally:
+        sys.path.remove(REF_SRC)
+    rec = Recorder()
+    monkeypatch.setattr(C, "call", rec)
+    ref_chain, our_chain = _chains(ref)
+    kw = dict(sigma=0.4, mean_p=0.04, mean_m=-0.05, theta_p=6.0, lambda_p=7.0, kappa_p=20.0, beta1_p=30.0, beta2_p=-25.0)
+    pricer = svm.HawkesJDPricer()
+    for chain, cls in ((ref_chain, RefHawkes), (our_chain, svm.HawkesJDParams)):
+        pricer.model_mc_price_chain(chain, cls(**kw), nb_path=1000, seed=4, distributed=False)
+        pricer.price_chain(chain, cls(**kw))
+        pricer.price_chain(chain, cls(risk_premia_gamma=0.3, **kw))
+    names = [c[0] for c in rec.calls]
+    assert names == ["b200sv_hawkesjd_mc_chain", "b200sv_hawkesjd_price_chain", "b200sv_hawkesjd_price_chain"] * 2
+    for a, b in zip(rec.calls[:3], rec.calls[3:]):
+        assert a == b or all(x == y or (x != x and y != y) for x, y in zip(a[1], b[1]))        # NaN = "no risk kernel" compares by identity
+    sixteen = rec.calls[0][1][0]
+    assert len(sixteen) == 16 and sixteen[1] == 0.4 and sixteen[6] == 7.0
+    gammas = [c[1][11] for c in rec.calls if c[0] == "b200sv_hawkesjd_price_chain"]
+    assert gammas[0] != gammas[0] and gammas[1] == 0.3 and gammas[3] == 0.3
